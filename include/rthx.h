@@ -1,0 +1,197 @@
+/*
+ * rthx.h — C ABI of the B200-native Monte Carlo exchange-factor ray tracer.
+ *
+ * Drop-in boundary for RayTraceHeatTransfer.jl's `mesh(N_rays; method=:exchange, rec)` path.
+ * The reference (pure Julia, no FFI of its own) would bind these entry points with `ccall`
+ * from a method that replaces
+ *     parallelRayTracing(rtm, rays_total, nudge, verbose; rec)
+ *         src/RayTracing/RayTracing2D/ExchangeFactors2D/parallelRayTracing.jl:1-62
+ *     computeExchangeFactorsBin(rtm, rays_per_emitter, nudge, spectral_bin, ...)
+ *         src/RayTracing/RayTracing2D/ExchangeFactors2D/parallelRayTracing.jl:64-159
+ * (see INTEGRATION.md and julia/RTHXExchange.jl).  In this repository the same ABI is driven
+ * by the Python `ctypes` twin in raytraceheattransfer.jl_b200/_lib.py.
+ *
+ * Conventions
+ *   - plain C, plain pointers and sizes; the caller owns every host buffer; the library copies the
+ *     mesh during rthx_create and never keeps a host pointer after a call returns.
+ *   - every function returns an int status: 0 = OK, non-zero = error, message via rthx_last_error.
+ *   - indices crossing the ABI are 0-based; -1 = none.
+ *   - geometric failures (escaped point location, iteration cap, hit on a non-solid fine wall) are
+ *     NOT errors: such rays are dropped and counted in `lost`, exactly like the `nothing` / `-1`
+ *     returns of traceRay.jl:37-39,48-50,62-64,69 and getGlobalIndex2D.jl:6.
+ *   - there is no CPU fallback: every compute entry point fails with RTHX_ERR_CUDA when no
+ *     sm_100 device is usable.
+ */
+#ifndef RTHX_H
+#define RTHX_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RTHX_VERSION_MAJOR 0
+#define RTHX_VERSION_MINOR 1
+
+/* status codes */
+enum {
+  RTHX_OK = 0,
+  RTHX_ERR_ARG = 1,      /* bad argument / inconsistent mesh */
+  RTHX_ERR_CUDA = 2,     /* CUDA runtime error or no usable device */
+  RTHX_ERR_NOMEM = 3,
+  RTHX_ERR_INTERNAL = 4
+};
+
+/* trace modes.  FIRST_INTERACTION is what method=:exchange computes (traceRay.jl:20-147): every ray
+ * stops at its first gas-extinction event or solid-wall hit; albedo and wall reflectivity are applied
+ * algebraically later by the unchanged host solver. */
+enum { RTHX_FIRST_INTERACTION = 0 };
+
+/* point-location strategy (rthx_trace_args.locator) */
+enum {
+  RTHX_LOCATOR_AUTO = 0,     /* analytic lattice inverse on coarse faces verified to be affine sub-meshes,
+                                grid + point-in-polygon elsewhere */
+  RTHX_LOCATOR_GENERIC = 1   /* uniform grid + crossing-number point-in-polygon everywhere, as
+                                findFace2D.jl:1-101 / spatialAccelerations.jl:2-89 */
+};
+
+/*
+ * Flattened RayTracingDomain2D (DomainStructs.jl:89-130).  One entry per coarse face (user polygon,
+ * 3 or 4 CCW vertices) and per fine cell (sub-mesh cell, 3 or 4 CCW vertices), fine cells stored in
+ * the walk order of createIndexMapping2D.jl:7-18 (coarse-major, then fine index).
+ * Wall i of a polygon spans vertex i -> vertex (i+1) mod nv (PolyVolume2D.jl:8-23).
+ * Unused 4th slots of triangles must be present (any value).
+ */
+typedef struct rthx_mesh {
+  int32_t n_coarse;             /* number of coarse faces */
+  int32_t n_cells;              /* total number of fine cells  (= Nv) */
+  int32_t n_bands;              /* n_spectral_bins (1 for grey) */
+  int32_t n_surfaces;           /* Ns = number of solid fine walls */
+  const int32_t* coarse_nv;     /* [n_coarse]        3 or 4 */
+  const double*  coarse_vx;     /* [n_coarse*4]      vertices */
+  const double*  coarse_vy;     /* [n_coarse*4] */
+  const uint8_t* coarse_solid;  /* [n_coarse*4]      solidWalls of the coarse face */
+  const int32_t* fine_off;      /* [n_coarse+1]      fine cells of coarse c are [fine_off[c], fine_off[c+1]) */
+  const int32_t* cell_nv;       /* [n_cells] */
+  const double*  cell_vx;       /* [n_cells*4] */
+  const double*  cell_vy;       /* [n_cells*4] */
+  const double*  cell_mid;      /* [n_cells*2]       midPoint (x,y) */
+  const double*  cell_volume;   /* [n_cells]         `volume` field (2-D area) */
+  const int32_t* cell_surf_id;  /* [n_cells*4]       global surface index of wall i, -1 if not solid
+                                                     (surface_mapping of RayTracingDomain2D.jl:57-76) */
+  const double*  kappa;         /* [n_bands*n_cells] kappa_g   */
+  const double*  sigma_s;       /* [n_bands*n_cells] sigma_s_g */
+  const double*  epsilon;       /* [n_bands*n_surfaces] wall emissivity; may be NULL (unused by
+                                                     FIRST_INTERACTION) */
+  const double*  uniform_beta;  /* [n_bands]         uniform_across_bin (validateDomainUniformity.jl:57-85):
+                                                     common beta, or -1 when cells disagree */
+} rthx_mesh;
+
+/*
+ * Arguments of one blocking trace.  Matrix index of an element: surfaces 0..Ns-1 then Ns + cell index
+ * (getGlobalIndex2D.jl:5-12).  N = Ns + n_cells.
+ *
+ * RNG contract (the reference is unseeded; this is new): Philox4x32-10, key = seed,
+ * counter = (ray_id lo, ray_id hi, emitter element index, (band << 8) | call#), ray_id in
+ * [ray_id_offset, ray_id_offset + rays_per_emitter).  Results are a pure function of
+ * (mesh, seed, ray_id range, nudge): independent of thread-block shape, chunking and GPU count.
+ */
+typedef struct rthx_trace_args {
+  int64_t  rays_per_emitter;    /* div(rays_total, N), parallelRayTracing.jl:6 */
+  int64_t  ray_id_offset;       /* 0 normally; continuation runs add their counts */
+  uint64_t seed;
+  double   nudge;               /* 1e4*eps(Float64) by default, multiDispatchRayTrace2D.jl:10 */
+  int32_t  n_bins;              /* number of bands traced in this call (batched in the grid) */
+  const int32_t* bins;          /* [n_bins] band indices */
+  int32_t  mode;                /* RTHX_FIRST_INTERACTION */
+  int32_t  locator;             /* RTHX_LOCATOR_* */
+  int32_t  emitter_rank;        /* this call traces emitters e with e % emitter_world == emitter_rank; */
+  int32_t  emitter_world;       /*   rows of other emitters are left zero.  (0,1) = all emitters */
+  int32_t  n_rec_ids;           /* RayRecorder: number of recorded emitter elements (0 = off) */
+  const int32_t* rec_ids;       /* [n_rec_ids] element indices (rec.ids - 1) */
+  int32_t  rec_bin;             /* band index whose rays are recorded (rec.bin - 1) */
+  int32_t  block_threads;       /* 0 = auto */
+  int32_t  row_chunks;          /* thread blocks per (emitter, band) row; 0 = auto */
+} rthx_trace_args;
+
+/* RayRecorder output (parallelRayTracing.jl:108,120-123,135-138): origins (post-nudge emission point)
+ * and endpoints (interaction point) of every successfully tallied ray of the recorded emitters, in
+ * ascending (emitter element, ray id) order.  Caller provides room for `capacity` points each. */
+typedef struct rthx_rec_out {
+  int64_t  capacity;            /* in points; needs >= n_rec_ids * rays_per_emitter */
+  double*  origins;             /* [capacity*2] */
+  double*  endpoints;           /* [capacity*2] */
+  int64_t  n_recorded;          /* out */
+} rthx_rec_out;
+
+typedef struct rthx_stats {
+  int64_t rays_traced;          /* rays_per_emitter * owned emitters * n_bins */
+  int64_t rays_lost;
+  double  kernel_ms;            /* device time of the trace kernel (CUDA events) */
+  double  total_ms;             /* device time of the whole call incl. zeroing and copies */
+  int32_t n_blocks;
+  int32_t block_threads;
+  int32_t row_chunks;
+  int32_t smem_bytes;
+  int32_t hist_in_smem;         /* 1 = per-block shared-memory row histogram, 0 = direct global atomics */
+  int32_t n_launches;           /* kernels launched by the call */
+} rthx_stats;
+
+typedef struct rthx_info {
+  int32_t n_elements;           /* N */
+  int32_t n_surfaces;
+  int32_t n_cells;
+  int32_t n_coarse;
+  int32_t n_bands;
+  int32_t n_affine_faces;       /* coarse faces whose sub-mesh was verified to be an affine lattice */
+  int32_t device_id;
+  int32_t sm_count;
+  int32_t cc_major, cc_minor;
+} rthx_info;
+
+typedef struct rthx_handle rthx_handle;
+
+/* Upload the mesh to `device_id`, derive emitter table, edge normals, locator grids, neighbour table and
+ * lattice descriptors.  Replaces nothing in the reference (it keeps the mesh in Julia structs); it is the
+ * device-side twin of RayTracingDomain2D.jl:2-111 + spatialAccelerations.jl:92-106. */
+int rthx_create(rthx_handle** out, const rthx_mesh* mesh, int device_id);
+int rthx_destroy(rthx_handle* h);
+int rthx_get_info(const rthx_handle* h, rthx_info* info);
+
+/* Blocking trace with HOST outputs.  Replaces computeExchangeFactorsBin (parallelRayTracing.jl:64-159)
+ * for all `bins` at once: counts_out[b][i][j] = number of rays of emitter i whose first interaction is
+ * element j; lost_out[b][i] = rays dropped.  The caller forms F = counts / rowsum exactly as
+ * parallelRayTracing.jl:144-146 + row_normalize! :161-169 compose.
+ *   counts_out: [n_bins*N*N] uint64, lost_out: [n_bins*N] uint64 (may be NULL), rec / stats may be NULL. */
+int rthx_trace_exchange(rthx_handle* h, const rthx_trace_args* args,
+                        uint64_t* counts_out, uint64_t* lost_out,
+                        rthx_rec_out* rec, rthx_stats* stats);
+
+/* Asynchronous trace into DEVICE buffers on `stream` (a cudaStream_t; NULL = default stream):
+ * counts_dev [n_bins*N*N] uint64, lost_dev [n_bins*N] uint64 on the handle's device (or peer-mapped).
+ * zero_first != 0 clears both buffers on the stream before the launch.  Does not synchronise; stats
+ * carries the launch geometry only.  Recording is not available on this entry point. */
+int rthx_trace_exchange_device(rthx_handle* h, const rthx_trace_args* args,
+                               void* counts_dev, void* lost_dev, void* stream,
+                               int zero_first, rthx_stats* stats);
+
+/* Single-process multi-GPU trace: emitters are dealt round-robin to the n handles (one per device, same
+ * mesh), all devices run concurrently and each copies only the rows it owns into the host matrix
+ * (rows are disjoint, so no reduction is needed in-process).  args->emitter_rank/world are ignored. */
+int rthx_trace_exchange_multi(rthx_handle** hs, int n, const rthx_trace_args* args,
+                              uint64_t* counts_out, uint64_t* lost_out,
+                              rthx_rec_out* rec, rthx_stats* stats);
+
+/* FP64 FMA-chain micro-benchmark on the handle's device: the denominator of the FP64 roofline
+ * (MEASURED_PEAKS.json has no FP64 entry).  Returns TFLOP/s (2 flop per DFMA). */
+int rthx_measure_fp64_peak(rthx_handle* h, double* tflops);
+
+/* Message of the last error on this handle (h == NULL: last error of rthx_create on this thread). */
+const char* rthx_last_error(const rthx_handle* h);
+int rthx_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RTHX_H */

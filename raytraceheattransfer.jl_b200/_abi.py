@@ -1,0 +1,70 @@
+"""ctypes mirror of include/rthx.h (struct layouts must stay in lock-step with the header)."""
+from __future__ import annotations
+
+import ctypes as C
+
+RTHX_OK = 0
+RTHX_FIRST_INTERACTION = 0
+RTHX_LOCATOR_AUTO = 0
+RTHX_LOCATOR_GENERIC = 1
+
+c_i32p = C.POINTER(C.c_int32)
+c_f64p = C.POINTER(C.c_double)
+c_u8p = C.POINTER(C.c_uint8)
+c_u64p = C.POINTER(C.c_uint64)
+
+
+class rthx_mesh(C.Structure):
+    _fields_ = [
+        ("n_coarse", C.c_int32), ("n_cells", C.c_int32), ("n_bands", C.c_int32), ("n_surfaces", C.c_int32),
+        ("coarse_nv", c_i32p), ("coarse_vx", c_f64p), ("coarse_vy", c_f64p), ("coarse_solid", c_u8p),
+        ("fine_off", c_i32p),
+        ("cell_nv", c_i32p), ("cell_vx", c_f64p), ("cell_vy", c_f64p), ("cell_mid", c_f64p),
+        ("cell_volume", c_f64p), ("cell_surf_id", c_i32p),
+        ("kappa", c_f64p), ("sigma_s", c_f64p), ("epsilon", c_f64p), ("uniform_beta", c_f64p),
+    ]
+
+
+class rthx_trace_args(C.Structure):
+    _fields_ = [
+        ("rays_per_emitter", C.c_int64), ("ray_id_offset", C.c_int64), ("seed", C.c_uint64),
+        ("nudge", C.c_double),
+        ("n_bins", C.c_int32), ("bins", c_i32p),
+        ("mode", C.c_int32), ("locator", C.c_int32),
+        ("emitter_rank", C.c_int32), ("emitter_world", C.c_int32),
+        ("n_rec_ids", C.c_int32), ("rec_ids", c_i32p), ("rec_bin", C.c_int32),
+        ("block_threads", C.c_int32), ("row_chunks", C.c_int32),
+    ]
+
+
+class rthx_rec_out(C.Structure):
+    _fields_ = [("capacity", C.c_int64), ("origins", c_f64p), ("endpoints", c_f64p), ("n_recorded", C.c_int64)]
+
+
+class rthx_stats(C.Structure):
+    _fields_ = [
+        ("rays_traced", C.c_int64), ("rays_lost", C.c_int64), ("kernel_ms", C.c_double), ("total_ms", C.c_double),
+        ("n_blocks", C.c_int32), ("block_threads", C.c_int32), ("row_chunks", C.c_int32), ("smem_bytes", C.c_int32),
+        ("hist_in_smem", C.c_int32), ("n_launches", C.c_int32),
+    ]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class rthx_info(C.Structure):
+    _fields_ = [
+        ("n_elements", C.c_int32), ("n_surfaces", C.c_int32), ("n_cells", C.c_int32), ("n_coarse", C.c_int32),
+        ("n_bands", C.c_int32), ("n_affine_faces", C.c_int32), ("device_id", C.c_int32), ("sm_count", C.c_int32),
+        ("cc_major", C.c_int32), ("cc_minor", C.c_int32),
+    ]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+# every symbol include/rthx.h declares (tests check the built library exports all of them)
+EXPORTED_SYMBOLS = (
+    "rthx_create", "rthx_destroy", "rthx_get_info", "rthx_trace_exchange", "rthx_trace_exchange_device",
+    "rthx_trace_exchange_multi", "rthx_measure_fp64_peak", "rthx_last_error", "rthx_version",
+)

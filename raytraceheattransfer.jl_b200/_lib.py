@@ -1,0 +1,224 @@
+"""ctypes binding of the C ABI in include/rthx.h (the Python twin of the Julia `ccall` shim, julia/RTHXExchange.jl).
+
+The shared library `csrc/librthx.so` is built in-tree by `build_library()` (nvcc, sm_100a).  There is no CPU
+fallback: if the library is missing or no device is usable, every compute call raises `RthxError`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import shutil
+import subprocess
+from typing import Optional, Sequence
+
+import numpy as np
+
+from ._abi import (rthx_mesh, rthx_trace_args, rthx_rec_out, rthx_stats, rthx_info, c_i32p, c_f64p, c_u64p,
+                   RTHX_FIRST_INTERACTION, RTHX_LOCATOR_AUTO, RTHX_LOCATOR_GENERIC, EXPORTED_SYMBOLS)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CSRC = os.path.join(_HERE, "csrc")
+_LIB = None
+
+DEFAULT_SEED = 0x5EED0001
+DEFAULT_NUDGE = 10_000 * float(np.finfo(np.float64).eps)  # multiDispatchRayTrace2D.jl:10
+
+
+class RthxError(RuntimeError):
+    pass
+
+
+def library_path() -> str:
+    return os.path.join(_CSRC, "librthx.so")
+
+
+def build_library(force: bool = False, verbose: bool = False) -> str:
+    """Compile csrc/*.cu into csrc/librthx.so for sm_100a (nvcc cross-compiles without a GPU)."""
+    so = library_path()
+    srcs = [os.path.join(_CSRC, f) for f in sorted(os.listdir(_CSRC)) if f.endswith((".cu", ".cuh", ".h"))]
+    srcs.append(os.path.join(os.path.dirname(_HERE), "include", "rthx.h"))
+    if not force and os.path.exists(so) and all(os.path.getmtime(so) >= os.path.getmtime(s) for s in srcs):
+        return so
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+           "-Xcompiler", "-fPIC,-O2", "-shared", "--fmad=true",
+           "-I", os.path.join(os.path.dirname(_HERE), "include"), "-I", _CSRC,
+           "-o", so] + [s for s in srcs if s.endswith(".cu")]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    env = dict(os.environ)
+    env.pop("CC", None)
+    env.pop("CXX", None)
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env)
+    if r.returncode != 0:
+        raise RthxError("nvcc failed:\n" + r.stdout + r.stderr)
+    if verbose:
+        print(r.stdout + r.stderr)
+    return so
+
+
+def load_library():
+    """Load csrc/librthx.so (raises RthxError if it has not been built — no fallback)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    so = library_path()
+    if not os.path.exists(so):
+        raise RthxError(f"{so} not built; run `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(there is no CPU fallback)")
+    L = C.CDLL(so)
+    L.rthx_create.restype = C.c_int
+    L.rthx_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(rthx_mesh), C.c_int]
+    L.rthx_destroy.restype = C.c_int
+    L.rthx_destroy.argtypes = [C.c_void_p]
+    L.rthx_get_info.restype = C.c_int
+    L.rthx_get_info.argtypes = [C.c_void_p, C.POINTER(rthx_info)]
+    L.rthx_trace_exchange.restype = C.c_int
+    L.rthx_trace_exchange.argtypes = [C.c_void_p, C.POINTER(rthx_trace_args), c_u64p, c_u64p,
+                                      C.POINTER(rthx_rec_out), C.POINTER(rthx_stats)]
+    L.rthx_trace_exchange_device.restype = C.c_int
+    L.rthx_trace_exchange_device.argtypes = [C.c_void_p, C.POINTER(rthx_trace_args), C.c_void_p, C.c_void_p,
+                                             C.c_void_p, C.c_int, C.POINTER(rthx_stats)]
+    L.rthx_trace_exchange_multi.restype = C.c_int
+    L.rthx_trace_exchange_multi.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(rthx_trace_args), c_u64p,
+                                            c_u64p, C.POINTER(rthx_rec_out), C.POINTER(rthx_stats)]
+    L.rthx_measure_fp64_peak.restype = C.c_int
+    L.rthx_measure_fp64_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+    L.rthx_last_error.restype = C.c_char_p
+    L.rthx_last_error.argtypes = [C.c_void_p]
+    L.rthx_version.restype = C.c_int
+    L.rthx_version.argtypes = []
+    _LIB = L
+    return L
+
+
+def make_trace_args(rays_per_emitter: int, seed: int = DEFAULT_SEED, bins: Sequence[int] = (0,),
+                    nudge: Optional[float] = None, rec_ids: Optional[Sequence[int]] = None, rec_bin: int = 0,
+                    ray_id_offset: int = 0, emitter_rank: int = 0, emitter_world: int = 1,
+                    locator: int = RTHX_LOCATOR_AUTO, block_threads: int = 0, row_chunks: int = 0):
+    """Build an rthx_trace_args; returns (args, keepalive) — keep `keepalive` referenced during the call."""
+    a = rthx_trace_args()
+    a.rays_per_emitter = int(rays_per_emitter)
+    a.ray_id_offset = int(ray_id_offset)
+    a.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    a.nudge = DEFAULT_NUDGE if nudge is None else float(nudge)
+    bins_arr = np.ascontiguousarray(bins, dtype=np.int32)
+    a.n_bins = len(bins_arr)
+    a.bins = bins_arr.ctypes.data_as(c_i32p)
+    a.mode = RTHX_FIRST_INTERACTION
+    a.locator = int(locator)
+    a.emitter_rank = int(emitter_rank)
+    a.emitter_world = int(emitter_world)
+    rec_arr = np.ascontiguousarray(rec_ids if rec_ids else [], dtype=np.int32)
+    a.n_rec_ids = len(rec_arr)
+    a.rec_ids = rec_arr.ctypes.data_as(c_i32p) if len(rec_arr) else None
+    a.rec_bin = int(rec_bin)
+    a.block_threads = int(block_threads)
+    a.row_chunks = int(row_chunks)
+    return a, (bins_arr, rec_arr)
+
+
+class DeviceTracer:
+    """Owns one `rthx_handle` (mesh resident on one GPU)."""
+
+    def __init__(self, flat, device: int = 0):
+        self._L = load_library()
+        self.flat = flat
+        self.device = int(device)
+        h = C.c_void_p()
+        rc = self._L.rthx_create(C.byref(h), C.byref(flat.c), self.device)
+        if rc != 0:
+            msg = self._L.rthx_last_error(None)
+            raise RthxError(f"rthx_create failed ({rc}): {msg.decode() if msg else ''}")
+        self._h = h
+        info = rthx_info()
+        self._check(self._L.rthx_get_info(self._h, C.byref(info)))
+        self.info = info.as_dict()
+        self.n_elements = info.n_elements
+
+    def _check(self, rc: int):
+        if rc != 0:
+            msg = self._L.rthx_last_error(self._h)
+            raise RthxError(f"rthx call failed ({rc}): {msg.decode() if msg else ''}")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.rthx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def trace(self, rays_per_emitter: int, counts_out: Optional[np.ndarray] = None, **kw):
+        """Blocking trace with host outputs (rthx_trace_exchange).  Returns a dict with counts [nb,N,N] u64,
+        lost [nb,N] u64, stats, and origins/endpoints when rec_ids is given."""
+        rec_ids = kw.get("rec_ids")
+        args, keep = make_trace_args(rays_per_emitter, **kw)
+        N, nb = self.n_elements, args.n_bins
+        counts = counts_out if counts_out is not None else np.empty((nb, N, N), np.uint64)
+        assert counts.dtype == np.uint64 and counts.size == nb * N * N and counts.flags["C_CONTIGUOUS"]
+        lost = np.empty((nb, N), np.uint64)
+        st = rthx_stats()
+        rec = None
+        origins = endpoints = None
+        if rec_ids:
+            cap = len(rec_ids) * int(rays_per_emitter)
+            origins = np.zeros((max(cap, 1), 2))
+            endpoints = np.zeros((max(cap, 1), 2))
+            rec = rthx_rec_out(cap, origins.ctypes.data_as(c_f64p), endpoints.ctypes.data_as(c_f64p), 0)
+        self._check(self._L.rthx_trace_exchange(self._h, C.byref(args), counts.ctypes.data_as(c_u64p),
+                                                lost.ctypes.data_as(c_u64p), C.byref(rec) if rec else None,
+                                                C.byref(st)))
+        out = dict(counts=counts.reshape(nb, N, N), lost=lost, stats=st.as_dict())
+        if rec is not None:
+            out["origins"] = origins[: rec.n_recorded].copy()
+            out["endpoints"] = endpoints[: rec.n_recorded].copy()
+        return out
+
+    def trace_device(self, rays_per_emitter: int, counts_ptr: int, lost_ptr: int, stream: int = 0,
+                     zero_first: bool = True, **kw):
+        """Asynchronous trace into device buffers (rthx_trace_exchange_device); pointers are raw device addresses
+        (e.g. torch.Tensor.data_ptr()), stream a cudaStream_t handle (e.g. torch.cuda.current_stream().cuda_stream)."""
+        args, keep = make_trace_args(rays_per_emitter, **kw)
+        st = rthx_stats()
+        self._check(self._L.rthx_trace_exchange_device(self._h, C.byref(args), C.c_void_p(counts_ptr),
+                                                       C.c_void_p(lost_ptr), C.c_void_p(stream),
+                                                       1 if zero_first else 0, C.byref(st)))
+        return st.as_dict()
+
+    def measure_fp64_peak(self) -> float:
+        v = C.c_double(0.0)
+        self._check(self._L.rthx_measure_fp64_peak(self._h, C.byref(v)))
+        return v.value
+
+
+def trace_multi(tracers: Sequence[DeviceTracer], rays_per_emitter: int, **kw):
+    """Single-process multi-GPU trace (rthx_trace_exchange_multi)."""
+    L = load_library()
+    rec_ids = kw.get("rec_ids")
+    args, keep = make_trace_args(rays_per_emitter, **kw)
+    N, nb = tracers[0].n_elements, args.n_bins
+    counts = np.empty((nb, N, N), np.uint64)
+    lost = np.empty((nb, N), np.uint64)
+    st = rthx_stats()
+    hs = (C.c_void_p * len(tracers))(*[t._h for t in tracers])
+    rec = None
+    origins = endpoints = None
+    if rec_ids:
+        cap = len(rec_ids) * int(rays_per_emitter)
+        origins = np.zeros((max(cap, 1), 2))
+        endpoints = np.zeros((max(cap, 1), 2))
+        rec = rthx_rec_out(cap, origins.ctypes.data_as(c_f64p), endpoints.ctypes.data_as(c_f64p), 0)
+    rc = L.rthx_trace_exchange_multi(hs, len(tracers), C.byref(args), counts.ctypes.data_as(c_u64p),
+                                     lost.ctypes.data_as(c_u64p), C.byref(rec) if rec else None, C.byref(st))
+    if rc != 0:
+        msg = L.rthx_last_error(tracers[0]._h)
+        raise RthxError(f"rthx_trace_exchange_multi failed ({rc}): {msg.decode() if msg else ''}")
+    out = dict(counts=counts, lost=lost, stats=st.as_dict())
+    if rec is not None:
+        out["origins"] = origins[: rec.n_recorded].copy()
+        out["endpoints"] = endpoints[: rec.n_recorded].copy()
+    return out

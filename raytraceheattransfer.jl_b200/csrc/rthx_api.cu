@@ -1,0 +1,714 @@
+// rthx_api.cu — host side of the C ABI in include/rthx.h: mesh preparation, device residency, launches, copies.
+//
+// Mesh preparation derives, once per rthx_create, everything the kernels need beyond the caller's arrays:
+//   emitter table (createIndexMapping2D.jl:1-20), unit edge normals (calculateInwardNormal.jl:1-12),
+//   reference-faithful locator grids (spatialAccelerations.jl:2-89), a coarse-face neighbour table (new) and,
+//   where the fine cells of a coarse face are verified to be the affine lattice produced by meshQuad.jl:116-136 /
+//   meshTriangle.jl:40-97, the analytic lattice inverse used instead of grid + point-in-polygon.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "rthx_internal.h"
+
+using namespace rthx;
+
+struct rthx_handle {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaDeviceProp prop{};
+  int n_coarse = 0, n_cells = 0, n_bands = 0, ns = 0, N = 0, n_affine = 0;
+  bool coarse_fits_smem = false;
+  std::vector<void*> allocs;   // mesh allocations
+  TraceParams base{};          // mesh pointers filled once
+  // per-call scratch, grown on demand
+  unsigned long long* counts_dev = nullptr; size_t counts_cap = 0;
+  unsigned long long* lost_dev = nullptr;   size_t lost_cap = 0;
+  int32_t* bins_dev = nullptr;              size_t bins_cap = 0;
+  int32_t* rec_slot_dev = nullptr;
+  double* rec_pts_dev = nullptr;            size_t rec_pts_cap = 0;
+  uint8_t* rec_valid_dev = nullptr;         size_t rec_valid_cap = 0;
+  double* peak_dev = nullptr;
+  std::string err;
+};
+
+static thread_local std::string g_create_err;
+
+static int fail(rthx_handle* h, int code, const std::string& msg) {
+  if (h) h->err = msg; else g_create_err = msg;
+  return code;
+}
+#define CU(h, call)                                                                                   \
+  do {                                                                                                \
+    cudaError_t e_ = (call);                                                                          \
+    if (e_ != cudaSuccess)                                                                            \
+      return fail(h, RTHX_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));             \
+  } while (0)
+
+template <class T>
+static cudaError_t upload(rthx_handle* h, const std::vector<T>& v, const T** out) {
+  void* d = nullptr;
+  const size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
+  cudaError_t e = cudaMalloc(&d, bytes);
+  if (e != cudaSuccess) return e;
+  h->allocs.push_back(d);
+  if (!v.empty()) e = cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+  *out = static_cast<const T*>(d);
+  return e;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host-side mesh preparation
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+
+struct Poly { int n; double vx[4], vy[4], nx[4], ny[4], midx, midy, volume, bb[4]; };
+
+void edge_normal(double x1, double y1, double x2, double y2, double midx, double midy, double* nx, double* ny) {
+  const double ex = x2 - x1, ey = y2 - y1;
+  double ax = ey, ay = -ex;
+  const double len = std::sqrt(ax * ax + ay * ay);
+  ax /= len; ay /= len;
+  const double wmx = (x1 + x2) / 2, wmy = (y1 + y2) / 2;
+  if (ax * (wmx - midx) + ay * (wmy - midy) < 0) { ax = -ax; ay = -ay; }
+  *nx = ax; *ny = ay;
+}
+
+void poly_finish(Poly& p) {
+  p.bb[0] = p.bb[2] = INFINITY; p.bb[1] = p.bb[3] = -INFINITY;
+  for (int i = 0; i < p.n; ++i) {
+    const int j = (i + 1) % p.n;
+    edge_normal(p.vx[i], p.vy[i], p.vx[j], p.vy[j], p.midx, p.midy, &p.nx[i], &p.ny[i]);
+    p.bb[0] = std::min(p.bb[0], p.vx[i]); p.bb[1] = std::max(p.bb[1], p.vx[i]);
+    p.bb[2] = std::min(p.bb[2], p.vy[i]); p.bb[3] = std::max(p.bb[3], p.vy[i]);
+  }
+  for (int i = p.n; i < 4; ++i) { p.vx[i] = p.vy[i] = p.nx[i] = p.ny[i] = 0.0; }
+}
+
+// spatialAccelerations.jl:72-89 + :2-59; buckets appended to the global CSR arrays.
+void build_grid(const Poly* faces, int n, int poly_base, FaceSetDev& fs, std::vector<int32_t>& bstart, std::vector<int32_t>& bitems) {
+  double total = 0;
+  for (int i = 0; i < n; ++i) total += faces[i].volume;
+  const double cell = std::sqrt(total / n) * 2.0;
+  double min_x = INFINITY, min_y = INFINITY, max_x = -INFINITY, max_y = -INFINITY;
+  for (int i = 0; i < n; ++i) {
+    min_x = std::min(min_x, faces[i].bb[0]); max_x = std::max(max_x, faces[i].bb[1]);
+    min_y = std::min(min_y, faces[i].bb[2]); max_y = std::max(max_y, faces[i].bb[3]);
+  }
+  const double pad = cell * 0.1;
+  min_x -= pad; min_y -= pad; max_x += pad; max_y += pad;
+  int nx = std::max(1, (int)std::ceil((max_x - min_x) / cell)), ny = std::max(1, (int)std::ceil((max_y - min_y) / cell));
+  std::vector<std::vector<int32_t>> cells((size_t)nx * ny);
+  for (int f = 0; f < n; ++f) {
+    int si = std::max(1, (int)std::floor((faces[f].bb[0] - min_x) / cell) + 1), ei = std::min(nx, (int)std::ceil((faces[f].bb[1] - min_x) / cell));
+    int sj = std::max(1, (int)std::floor((faces[f].bb[2] - min_y) / cell) + 1), ej = std::min(ny, (int)std::ceil((faces[f].bb[3] - min_y) / cell));
+    for (int i = si; i <= ei; ++i)
+      for (int j = sj; j <= ej; ++j) cells[(size_t)(i - 1) + (size_t)(j - 1) * nx].push_back(f);
+  }
+  fs.ox = min_x; fs.oy = min_y; fs.inv_cell = 1.0 / cell; fs.nx = nx; fs.ny = ny;
+  fs.poly_base = poly_base; fs.n_faces = n; fs.pad_ = 0;
+  // bucket_start holds absolute offsets into bucket_items; one shared terminator per set is written by the caller
+  if (bstart.empty()) bstart.push_back(0);
+  fs.bucket_off = (int32_t)bstart.size() - 1;
+  for (auto& c : cells) {
+    bitems.insert(bitems.end(), c.begin(), c.end());
+    bstart.push_back((int32_t)bitems.size());
+  }
+}
+
+bool close_pt(double ax, double ay, double bx, double by, double tol) { return std::fabs(ax - bx) <= tol && std::fabs(ay - by) <= tol; }
+
+// Try to recognise the fine cells of coarse face `cf` as the affine lattice of meshQuad / meshTriangle.
+// On success fills the lattice fields of `out` (+ the lattice->fine table for triangles) and returns true.
+bool detect_affine(const Poly& cp, const Poly* cells, int n_fine, CoarseDev& out, std::vector<int32_t>& lattice) {
+  double scale = 0;
+  for (int i = 0; i < cp.n; ++i) scale = std::max(scale, std::max(std::fabs(cp.vx[i]), std::fabs(cp.vy[i])));
+  const double ext = std::max(cp.bb[1] - cp.bb[0], cp.bb[3] - cp.bb[2]);
+  const double tol = 1e-9 * std::max(ext, 1e-300);
+  double qx[4], qy[4];
+  int Nx = 0, Ny = 0, mirror = -1, diag = -1;
+  if (cp.n == 4) {
+    for (int i = 0; i < 4; ++i) { qx[i] = cp.vx[i]; qy[i] = cp.vy[i]; }
+    if (!close_pt(qx[0] - qx[1] + qx[2] - qx[3], qy[0] - qy[1] + qy[2] - qy[3], 0, 0, 1e-12 * std::max(scale, ext))) return false;
+    if (cells[0].n != 4) return false;
+    const double e0 = std::hypot(cells[0].vx[1] - cells[0].vx[0], cells[0].vy[1] - cells[0].vy[0]);
+    const double ab = std::hypot(qx[1] - qx[0], qy[1] - qy[0]);
+    if (!(e0 > 0)) return false;
+    Nx = (int)std::llround(ab / e0);
+    if (Nx < 1 || n_fine % Nx != 0) return false;
+    Ny = n_fine / Nx;
+  } else {
+    // meshTriangle.jl:15-53: longest edge (first maximum) is the cut diagonal, opposite vertex point-mirrored
+    const double l0 = std::hypot(cp.vx[0] - cp.vx[1], cp.vy[0] - cp.vy[1]);
+    const double l1 = std::hypot(cp.vx[1] - cp.vx[2], cp.vy[1] - cp.vy[2]);
+    const double l2 = std::hypot(cp.vx[2] - cp.vx[0], cp.vy[2] - cp.vy[0]);
+    int mi = 0;
+    if (l1 > l0) mi = 1;
+    if (l2 > std::max(l0, l1)) mi = 2;
+    const int a = mi, b = (mi + 1) % 3, o = (mi + 2) % 3;  // edge a->b is the diagonal, o the opposite vertex
+    const double mx = cp.vx[a] + (cp.vx[b] - cp.vx[a]) / 2, my = cp.vy[a] + (cp.vy[b] - cp.vy[a]) / 2;
+    const double rx = -(cp.vx[o] - mx) + mx, ry = -(cp.vy[o] - my) + my;
+    // new_points: mirrored vertex inserted after the start of the longest edge
+    int w = 0;
+    for (int i = 0; i < 3; ++i) {
+      qx[w] = cp.vx[i]; qy[w] = cp.vy[i]; ++w;
+      if (i == mi) { qx[w] = rx; qy[w] = ry; mirror = w; ++w; }
+    }
+    diag = mi;
+    const long long nd = (long long)std::llround((std::sqrt(8.0 * n_fine + 1.0) - 1.0) / 2.0);
+    if (nd < 1 || nd * (nd + 1) / 2 != n_fine) return false;
+    Nx = Ny = (int)nd;
+  }
+  // lattice vertex (n,m) of the affine map  A + n/Nx (B-A) + m/Ny (D-A)
+  auto lat = [&](int n, int m, double& x, double& y) {
+    const double s = (double)n / Nx, t = (double)m / Ny;
+    x = qx[0] + s * (qx[1] - qx[0]) + t * (qx[3] - qx[0]);
+    y = qy[0] + s * (qy[1] - qy[0]) + t * (qy[3] - qy[0]);
+  };
+  std::vector<int32_t> table;
+  if (cp.n == 3) table.assign((size_t)Nx * Ny, -1);
+  int idx = 0;
+  for (int m = 0; m < Ny; ++m)
+    for (int n = 0; n < Nx; ++n) {
+      double lx[4], ly[4];
+      lat(n, m, lx[0], ly[0]); lat(n + 1, m, lx[1], ly[1]); lat(n + 1, m + 1, lx[2], ly[2]); lat(n, m + 1, lx[3], ly[3]);
+      if (idx < n_fine) {
+        const Poly& c = cells[idx];
+        bool match = false;
+        if (c.n == 4) {
+          match = true;
+          for (int i = 0; i < 4; ++i) match = match && close_pt(c.vx[i], c.vy[i], lx[i], ly[i], tol);
+        } else if (cp.n == 3) {
+          // diagonal cell: the three lattice corners other than the mirrored one (meshTriangle.jl:55,83)
+          match = true;
+          int w = 0;
+          for (int i = 0; i < 4; ++i) {
+            if (i == mirror) continue;
+            match = match && close_pt(c.vx[w], c.vy[w], lx[i], ly[i], tol);
+            ++w;
+          }
+        }
+        if (match) {
+          if (cp.n == 3) table[(size_t)n + (size_t)m * Nx] = idx;
+          ++idx;
+          continue;
+        }
+      }
+      if (cp.n == 4) return false;  // every lattice cell of a quad must be present, in order
+    }
+  if (idx != n_fine) return false;
+  // inverse map: [s;t] = diag(Nx,Ny) * inv([B-A, D-A]) * (p - A)
+  const double ux = qx[1] - qx[0], uy = qy[1] - qy[0], vx = qx[3] - qx[0], vy = qy[3] - qy[0];
+  const double det = ux * vy - uy * vx;
+  if (!(std::fabs(det) > 0)) return false;
+  out.ax = qx[0]; out.ay = qy[0];
+  out.g1x = Nx * (vy / det);  out.g1y = Nx * (-vx / det);
+  out.g2x = Ny * (-uy / det); out.g2y = Ny * (ux / det);
+  out.Nx = Nx; out.Ny = Ny;
+  if (cp.n == 4) { out.kind = KIND_AFFINE_QUAD; out.lat_off = -1; out.diag = -1; }
+  else {
+    out.kind = KIND_AFFINE_TRI; out.diag = diag;
+    out.lat_off = (int32_t)lattice.size();
+    lattice.insert(lattice.end(), table.begin(), table.end());
+  }
+  return true;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------
+// create / destroy / info
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int rthx_version(void) { return RTHX_VERSION_MAJOR * 100 + RTHX_VERSION_MINOR; }
+
+extern "C" const char* rthx_last_error(const rthx_handle* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+extern "C" int rthx_destroy(rthx_handle* h) {
+  if (!h) return RTHX_OK;
+  cudaSetDevice(h->device);
+  for (void* d : h->allocs) cudaFree(d);
+  cudaFree(h->counts_dev); cudaFree(h->lost_dev); cudaFree(h->bins_dev); cudaFree(h->rec_slot_dev);
+  cudaFree(h->rec_pts_dev); cudaFree(h->rec_valid_dev); cudaFree(h->peak_dev);
+  for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return RTHX_OK;
+}
+
+extern "C" int rthx_create(rthx_handle** out, const rthx_mesh* m, int device_id) {
+  if (!out) return fail(nullptr, RTHX_ERR_ARG, "rthx_create: out is NULL");
+  *out = nullptr;
+  if (!m || m->n_coarse < 1 || m->n_cells < 1 || m->n_bands < 1 || m->n_surfaces < 0 || !m->coarse_nv || !m->coarse_vx ||
+      !m->coarse_vy || !m->coarse_solid || !m->fine_off || !m->cell_nv || !m->cell_vx || !m->cell_vy || !m->cell_mid ||
+      !m->cell_volume || !m->cell_surf_id || !m->kappa || !m->sigma_s || !m->uniform_beta)
+    return fail(nullptr, RTHX_ERR_ARG, "rthx_create: NULL or empty mesh field");
+  int n_dev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&n_dev);
+  if (ce != cudaSuccess || n_dev == 0)
+    return fail(nullptr, RTHX_ERR_CUDA, std::string("rthx_create: no CUDA device (") + cudaGetErrorString(ce) + "); there is no CPU fallback");
+  if (device_id < 0 || device_id >= n_dev) return fail(nullptr, RTHX_ERR_ARG, "rthx_create: bad device id");
+  rthx_handle* h = new rthx_handle();
+  h->device = device_id;
+  auto bail = [&](int code, const std::string& msg) { g_create_err = msg; rthx_destroy(h); return code; };
+  if ((ce = cudaSetDevice(device_id)) != cudaSuccess) return bail(RTHX_ERR_CUDA, cudaGetErrorString(ce));
+  if ((ce = cudaGetDeviceProperties(&h->prop, device_id)) != cudaSuccess) return bail(RTHX_ERR_CUDA, cudaGetErrorString(ce));
+  if (h->prop.major < 10) return bail(RTHX_ERR_CUDA, "rthx_create: device is not sm_100 class (kernels are built for sm_100a only)");
+  if ((ce = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(RTHX_ERR_CUDA, cudaGetErrorString(ce));
+  for (auto& e : h->ev) if ((ce = cudaEventCreate(&e)) != cudaSuccess) return bail(RTHX_ERR_CUDA, cudaGetErrorString(ce));
+
+  const int nc = m->n_coarse, ncell = m->n_cells, ns = m->n_surfaces, N = ns + ncell, nb = m->n_bands;
+  h->n_coarse = nc; h->n_cells = ncell; h->ns = ns; h->N = N; h->n_bands = nb;
+  if (m->fine_off[0] != 0 || m->fine_off[nc] != ncell) return bail(RTHX_ERR_ARG, "rthx_create: fine_off must span [0, n_cells]");
+
+  // polygons: cells first, then coarse faces
+  std::vector<Poly> polys((size_t)ncell + nc);
+  for (int g = 0; g < ncell; ++g) {
+    Poly& p = polys[g];
+    p.n = m->cell_nv[g];
+    if (p.n != 3 && p.n != 4) return bail(RTHX_ERR_ARG, "rthx_create: cell_nv must be 3 or 4");
+    for (int i = 0; i < p.n; ++i) { p.vx[i] = m->cell_vx[4 * g + i]; p.vy[i] = m->cell_vy[4 * g + i]; }
+    p.midx = m->cell_mid[2 * g]; p.midy = m->cell_mid[2 * g + 1]; p.volume = m->cell_volume[g];
+    poly_finish(p);
+  }
+  for (int c = 0; c < nc; ++c) {
+    Poly& p = polys[(size_t)ncell + c];
+    p.n = m->coarse_nv[c];
+    if (p.n != 3 && p.n != 4) return bail(RTHX_ERR_ARG, "rthx_create: coarse_nv must be 3 or 4");
+    double sx = 0, sy = 0;
+    for (int i = 0; i < p.n; ++i) { p.vx[i] = m->coarse_vx[4 * c + i]; p.vy[i] = m->coarse_vy[4 * c + i]; sx += p.vx[i]; sy += p.vy[i]; }
+    p.midx = sx / p.n; p.midy = sy / p.n;
+    if (p.n == 4)
+      p.volume = 0.5 * (p.vx[0] * (p.vy[1] - p.vy[2]) + p.vx[1] * (p.vy[2] - p.vy[0]) + p.vx[2] * (p.vy[0] - p.vy[1])) +
+                 0.5 * (p.vx[2] * (p.vy[3] - p.vy[0]) + p.vx[3] * (p.vy[0] - p.vy[2]) + p.vx[0] * (p.vy[2] - p.vy[3]));
+    else
+      p.volume = 0.5 * (p.vx[0] * (p.vy[1] - p.vy[2]) + p.vx[1] * (p.vy[2] - p.vy[0]) + p.vx[2] * (p.vy[0] - p.vy[1]));
+    poly_finish(p);
+    if (m->fine_off[c + 1] <= m->fine_off[c]) return bail(RTHX_ERR_ARG, "rthx_create: every coarse face needs at least one fine cell");
+  }
+
+  // emitter table
+  std::vector<int32_t> em_cell(N, -1), em_wall(N, -1), em_coarse(N, -1);
+  for (int c = 0; c < nc; ++c)
+    for (int g = m->fine_off[c]; g < m->fine_off[c + 1]; ++g) {
+      em_cell[ns + g] = g; em_wall[ns + g] = -1; em_coarse[ns + g] = c;
+      for (int w = 0; w < polys[g].n; ++w) {
+        const int s = m->cell_surf_id[4 * g + w];
+        if (s < 0) continue;
+        if (s >= ns || em_cell[s] != -1) return bail(RTHX_ERR_ARG, "rthx_create: cell_surf_id is not a permutation of 0..Ns-1");
+        em_cell[s] = g; em_wall[s] = w; em_coarse[s] = c;
+      }
+    }
+  for (int e = 0; e < N; ++e) if (em_cell[e] < 0) return bail(RTHX_ERR_ARG, "rthx_create: surface index without a wall");
+
+  // locator grids + coarse descriptors
+  std::vector<FaceSetDev> sets(1 + (size_t)nc);
+  std::vector<int32_t> bstart, bitems, lattice;
+  build_grid(&polys[ncell], nc, ncell, sets[0], bstart, bitems);
+  std::vector<CoarseDev> coarse(nc);
+  const double ext_tol = 1e-9;
+  for (int c = 0; c < nc; ++c) {
+    const Poly& cp = polys[(size_t)ncell + c];
+    const int f0 = m->fine_off[c], nf = m->fine_off[c + 1] - f0;
+    build_grid(&polys[f0], nf, f0, sets[1 + c], bstart, bitems);
+    CoarseDev& d = coarse[c];
+    std::memset(&d, 0, sizeof(d));
+    for (int i = 0; i < 4; ++i) { d.vx[i] = cp.vx[i]; d.vy[i] = cp.vy[i]; d.nx[i] = cp.nx[i]; d.ny[i] = cp.ny[i]; d.nbr[i] = -1; d.solid[i] = 0; }
+    for (int i = 0; i < cp.n; ++i) d.solid[i] = m->coarse_solid[4 * c + i] ? 1 : 0;
+    d.nv = cp.n; d.fine_off = f0; d.kind = KIND_GENERIC; d.lat_off = -1; d.diag = -1; d.Nx = d.Ny = 0;
+    if (detect_affine(cp, &polys[f0], nf, d, lattice)) h->n_affine++;
+  }
+  // neighbour table: the unique coarse face sharing the (reversed) edge; T-junctions stay -1 (generic search)
+  for (int c = 0; c < nc; ++c) {
+    const Poly& a = polys[(size_t)ncell + c];
+    const double tol = ext_tol * std::max(a.bb[1] - a.bb[0], a.bb[3] - a.bb[2]);
+    for (int k = 0; k < a.n; ++k) {
+      if (coarse[c].solid[k]) continue;
+      const int k2 = (k + 1) % a.n;
+      int found = -1, n_found = 0;
+      for (int c2 = 0; c2 < nc; ++c2) {
+        if (c2 == c) continue;
+        const Poly& b = polys[(size_t)ncell + c2];
+        for (int j = 0; j < b.n; ++j) {
+          const int j2 = (j + 1) % b.n;
+          if (close_pt(a.vx[k], a.vy[k], b.vx[j2], b.vy[j2], tol) && close_pt(a.vx[k2], a.vy[k2], b.vx[j], b.vy[j], tol)) { found = c2; ++n_found; }
+        }
+      }
+      coarse[c].nbr[k] = (n_found == 1) ? found : -1;
+    }
+  }
+
+  std::vector<int32_t> poly_nv(polys.size());
+  std::vector<double> pvx(polys.size() * 4), pvy(polys.size() * 4), pnx(polys.size() * 4), pny(polys.size() * 4);
+  for (size_t i = 0; i < polys.size(); ++i) {
+    poly_nv[i] = polys[i].n;
+    for (int k = 0; k < 4; ++k) { pvx[4 * i + k] = polys[i].vx[k]; pvy[4 * i + k] = polys[i].vy[k]; pnx[4 * i + k] = polys[i].nx[k]; pny[4 * i + k] = polys[i].ny[k]; }
+  }
+  std::vector<double> beta((size_t)nb * ncell), ub(m->uniform_beta, m->uniform_beta + nb);
+  for (size_t i = 0; i < beta.size(); ++i) beta[i] = m->kappa[i] + m->sigma_s[i];
+  std::vector<double> mid(m->cell_mid, m->cell_mid + 2 * (size_t)ncell), vol(m->cell_volume, m->cell_volume + ncell);
+  std::vector<int32_t> surf(m->cell_surf_id, m->cell_surf_id + 4 * (size_t)ncell);
+  if (lattice.empty()) lattice.push_back(-1);
+
+  TraceParams& P = h->base;
+  std::memset(&P, 0, sizeof(P));
+#define UP(vec, field) if ((ce = upload(h, vec, &P.field)) != cudaSuccess) return bail(RTHX_ERR_CUDA, std::string("upload " #field ": ") + cudaGetErrorString(ce));
+  UP(coarse, coarse) UP(sets, sets) UP(bstart, bucket_start) UP(bitems, bucket_items) UP(poly_nv, poly_nv)
+  UP(pvx, poly_vx) UP(pvy, poly_vy) UP(pnx, poly_nx) UP(pny, poly_ny) UP(mid, cell_mid) UP(vol, cell_volume)
+  UP(surf, cell_surf_id) UP(beta, beta) UP(ub, uniform_beta) UP(lattice, lattice) UP(em_cell, em_cell)
+  UP(em_wall, em_wall) UP(em_coarse, em_coarse)
+#undef UP
+  P.n_coarse = nc; P.n_cells = ncell; P.n_surfaces = ns; P.N = N;
+  h->coarse_fits_smem = sizeof(CoarseDev) * (size_t)nc <= 32 * 1024;
+  if ((ce = cudaMalloc(&h->rec_slot_dev, sizeof(int32_t) * (size_t)N)) != cudaSuccess) return bail(RTHX_ERR_CUDA, cudaGetErrorString(ce));
+  if ((ce = configure_trace_kernel(h->prop.sharedMemPerBlockOptin)) != cudaSuccess) return bail(RTHX_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce));
+  *out = h;
+  return RTHX_OK;
+}
+
+extern "C" int rthx_get_info(const rthx_handle* h, rthx_info* info) {
+  if (!h || !info) return RTHX_ERR_ARG;
+  info->n_elements = h->N; info->n_surfaces = h->ns; info->n_cells = h->n_cells; info->n_coarse = h->n_coarse;
+  info->n_bands = h->n_bands; info->n_affine_faces = h->n_affine; info->device_id = h->device;
+  info->sm_count = h->prop.multiProcessorCount; info->cc_major = h->prop.major; info->cc_minor = h->prop.minor;
+  return RTHX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// trace
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+
+struct LaunchPlan { int n_owned, n_blocks, block_threads, row_chunks, hist_in_smem; size_t smem_bytes; };
+
+int check_args(rthx_handle* h, const rthx_trace_args* a) {
+  if (!a) return fail(h, RTHX_ERR_ARG, "trace: args is NULL");
+  if (a->rays_per_emitter < 0) return fail(h, RTHX_ERR_ARG, "trace: rays_per_emitter out of range");
+  if (a->n_bins < 1 || !a->bins) return fail(h, RTHX_ERR_ARG, "trace: n_bins must be >= 1");
+  for (int i = 0; i < a->n_bins; ++i) if (a->bins[i] < 0 || a->bins[i] >= h->n_bands) return fail(h, RTHX_ERR_ARG, "trace: band index out of range");
+  if (a->mode != RTHX_FIRST_INTERACTION) return fail(h, RTHX_ERR_ARG, "trace: unknown mode");
+  if (a->emitter_world < 1 || a->emitter_rank < 0 || a->emitter_rank >= a->emitter_world) return fail(h, RTHX_ERR_ARG, "trace: bad emitter_rank/world");
+  if (a->n_rec_ids < 0 || (a->n_rec_ids > 0 && !a->rec_ids)) return fail(h, RTHX_ERR_ARG, "trace: bad recorder ids");
+  if (a->block_threads != 0 && (a->block_threads < 32 || a->block_threads > 256 || a->block_threads % 32)) return fail(h, RTHX_ERR_ARG, "trace: block_threads must be a multiple of 32 in [32,256]");
+  if (a->row_chunks < 0) return fail(h, RTHX_ERR_ARG, "trace: row_chunks < 0");
+  return RTHX_OK;
+}
+
+LaunchPlan make_plan(const rthx_handle* h, const rthx_trace_args* a, int rank, int world) {
+  LaunchPlan pl{};
+  pl.n_owned = (h->N - rank + world - 1) / world;
+  if (pl.n_owned < 0) pl.n_owned = 0;
+  pl.block_threads = a->block_threads ? a->block_threads : 256;
+  const size_t coarse_bytes = h->coarse_fits_smem ? sizeof(CoarseDev) * (size_t)h->n_coarse : 0;
+  const size_t hist_bytes = sizeof(uint32_t) * (size_t)h->N;
+  pl.hist_in_smem = (coarse_bytes + hist_bytes <= h->prop.sharedMemPerBlockOptin) ? 1 : 0;
+  pl.smem_bytes = coarse_bytes + (pl.hist_in_smem ? hist_bytes : 0);
+  const long long rows = (long long)pl.n_owned * a->n_bins;
+  long long chunks = a->row_chunks;
+  if (chunks <= 0) {
+    // enough blocks for ~32 waves of the resident set, but keep >= 2048 rays (and >= N/2, the flush scan) per block
+    const int per_sm = std::max(1, trace_kernel_max_blocks_per_sm(pl.block_threads, pl.smem_bytes));
+    const long long target = (long long)h->prop.multiProcessorCount * per_sm * 32;
+    chunks = rows > 0 ? (target + rows - 1) / rows : 1;
+    const long long min_rays = std::max<long long>(2048, h->N / 2);
+    const long long max_chunks = std::max<long long>(1, a->rays_per_emitter / min_rays);
+    chunks = std::max<long long>(1, std::min(chunks, max_chunks));
+  }
+  // a u32 row histogram must not overflow
+  while ((a->rays_per_emitter + chunks - 1) / chunks > 0xFFFFFFFFll) chunks *= 2;
+  while (rows * chunks > 0x7FFFFFFFll && chunks > 1) chunks /= 2;
+  pl.row_chunks = (int)chunks;
+  pl.n_blocks = (int)(rows * chunks);
+  return pl;
+}
+
+void fill_params(const rthx_handle* h, const rthx_trace_args* a, const LaunchPlan& pl, int rank, int world, bool compact,
+                 unsigned long long* counts, unsigned long long* lost, TraceParams& P) {
+  P = h->base;
+  P.bins = h->bins_dev;
+  P.counts = counts; P.lost = lost;
+  P.n_bins = a->n_bins;
+  P.emitter_rank = rank; P.emitter_world = world; P.n_owned = pl.n_owned;
+  P.compact_rows = compact ? 1 : 0;
+  P.row_chunks = pl.row_chunks;
+  P.coarse_in_smem = h->coarse_fits_smem ? 1 : 0;
+  P.hist_in_smem = pl.hist_in_smem;
+  P.force_generic = a->locator == RTHX_LOCATOR_GENERIC ? 1 : 0;
+  P.rec_bin = a->rec_bin;
+  P.rays_per_emitter = a->rays_per_emitter;
+  P.ray_id_offset = a->ray_id_offset;
+  P.seed = a->seed;
+  P.nudge = a->nudge;
+  P.rec_slot = nullptr; P.rec_pts = nullptr; P.rec_valid = nullptr;
+}
+
+template <class T>
+cudaError_t ensure(T** ptr, size_t* cap, size_t need) {
+  if (*cap >= need && *ptr) return cudaSuccess;
+  if (*ptr) cudaFree(*ptr);
+  *ptr = nullptr; *cap = 0;
+  cudaError_t e = cudaMalloc((void**)ptr, std::max<size_t>(need, 1) * sizeof(T));
+  if (e == cudaSuccess) *cap = need;
+  return e;
+}
+
+void fill_stats(rthx_stats* st, const LaunchPlan& pl, const rthx_trace_args* a) {
+  if (!st) return;
+  std::memset(st, 0, sizeof(*st));
+  st->rays_traced = (int64_t)pl.n_owned * a->n_bins * a->rays_per_emitter;
+  st->n_blocks = pl.n_blocks; st->block_threads = pl.block_threads; st->row_chunks = pl.row_chunks;
+  st->smem_bytes = (int32_t)pl.smem_bytes; st->hist_in_smem = pl.hist_in_smem;
+}
+
+// Enqueue (zero +) kernel for one handle on `stream`; counts layout compact (owned rows) or full.
+int enqueue_trace(rthx_handle* h, const rthx_trace_args* a, int rank, int world, bool compact, unsigned long long* counts,
+                  unsigned long long* lost, bool zero_first, bool with_rec, int n_rec_slots, cudaStream_t stream,
+                  LaunchPlan* plan_out, int* n_launches) {
+  LaunchPlan pl = make_plan(h, a, rank, world);
+  CU(h, ensure(&h->bins_dev, &h->bins_cap, (size_t)a->n_bins));
+  CU(h, cudaMemcpyAsync(h->bins_dev, a->bins, sizeof(int32_t) * (size_t)a->n_bins, cudaMemcpyHostToDevice, stream));
+  const size_t rows = compact ? (size_t)pl.n_owned : (size_t)h->N;
+  if (zero_first) {
+    CU(h, cudaMemsetAsync(counts, 0, sizeof(unsigned long long) * (size_t)a->n_bins * rows * h->N, stream));
+    CU(h, cudaMemsetAsync(lost, 0, sizeof(unsigned long long) * (size_t)a->n_bins * h->N, stream));
+    *n_launches += 2;
+  }
+  TraceParams P;
+  fill_params(h, a, pl, rank, world, compact, counts, lost, P);
+  if (with_rec && n_rec_slots > 0) { P.rec_slot = h->rec_slot_dev; P.rec_pts = h->rec_pts_dev; P.rec_valid = h->rec_valid_dev; }
+  CU(h, launch_trace_exchange(P, pl.n_blocks, pl.block_threads, pl.smem_bytes, stream));
+  if (pl.n_blocks > 0) *n_launches += 1;
+  *plan_out = pl;
+  return RTHX_OK;
+}
+
+// Recorder slots: rank (0..n_rec-1) of each recorded element in ascending element order, -1 elsewhere.
+int prepare_recorder(rthx_handle* h, const rthx_trace_args* a, rthx_rec_out* rec, int* n_slots, cudaStream_t stream) {
+  *n_slots = 0;
+  if (!rec || a->n_rec_ids <= 0) return RTHX_OK;
+  std::vector<int32_t> slot(h->N, -1);
+  for (int i = 0; i < a->n_rec_ids; ++i) if (a->rec_ids[i] >= 0 && a->rec_ids[i] < h->N) slot[a->rec_ids[i]] = 0;
+  int n = 0;
+  for (int e = 0; e < h->N; ++e) if (slot[e] == 0) slot[e] = n++;
+  *n_slots = n;
+  if (n == 0) return RTHX_OK;
+  const size_t pts = (size_t)n * (size_t)a->rays_per_emitter;
+  CU(h, ensure(&h->rec_pts_dev, &h->rec_pts_cap, pts * 4));
+  CU(h, ensure(&h->rec_valid_dev, &h->rec_valid_cap, pts));
+  CU(h, cudaMemcpyAsync(h->rec_slot_dev, slot.data(), sizeof(int32_t) * (size_t)h->N, cudaMemcpyHostToDevice, stream));
+  CU(h, cudaMemsetAsync(h->rec_valid_dev, 0, pts, stream));
+  return RTHX_OK;
+}
+
+int collect_recorder(rthx_handle* h, const rthx_trace_args* a, rthx_rec_out* rec, int n_slots, cudaStream_t stream, bool append) {
+  if (!rec) return RTHX_OK;
+  if (!append) rec->n_recorded = 0;
+  if (n_slots == 0) return RTHX_OK;
+  const size_t pts = (size_t)n_slots * (size_t)a->rays_per_emitter;
+  std::vector<double> buf(pts * 4);
+  std::vector<uint8_t> valid(pts);
+  CU(h, cudaMemcpyAsync(buf.data(), h->rec_pts_dev, sizeof(double) * pts * 4, cudaMemcpyDeviceToHost, stream));
+  CU(h, cudaMemcpyAsync(valid.data(), h->rec_valid_dev, pts, cudaMemcpyDeviceToHost, stream));
+  CU(h, cudaStreamSynchronize(stream));
+  for (size_t s = 0; s < pts; ++s) {
+    if (!valid[s]) continue;
+    if (rec->n_recorded >= rec->capacity) break;
+    const int64_t k = rec->n_recorded++;
+    rec->origins[2 * k] = buf[4 * s]; rec->origins[2 * k + 1] = buf[4 * s + 1];
+    rec->endpoints[2 * k] = buf[4 * s + 2]; rec->endpoints[2 * k + 1] = buf[4 * s + 3];
+  }
+  return RTHX_OK;
+}
+
+}  // namespace
+
+extern "C" int rthx_trace_exchange(rthx_handle* h, const rthx_trace_args* a, uint64_t* counts_out, uint64_t* lost_out,
+                                   rthx_rec_out* rec, rthx_stats* st) {
+  if (!h) return RTHX_ERR_ARG;
+  int rc = check_args(h, a);
+  if (rc) return rc;
+  if (!counts_out) return fail(h, RTHX_ERR_ARG, "trace: counts_out is NULL");
+  CU(h, cudaSetDevice(h->device));
+  const int rank = a->emitter_rank, world = a->emitter_world;
+  const int N = h->N;
+  const size_t n_owned = (size_t)((N - rank + world - 1) / world);
+  CU(h, ensure(&h->counts_dev, &h->counts_cap, (size_t)a->n_bins * n_owned * N));
+  CU(h, ensure(&h->lost_dev, &h->lost_cap, (size_t)a->n_bins * N));
+  int n_slots = 0, n_launches = 0;
+  CU(h, cudaEventRecord(h->ev[0], h->stream));
+  rc = prepare_recorder(h, a, rec, &n_slots, h->stream);
+  if (rc) return rc;
+  LaunchPlan pl{};
+  // kernel timing brackets only the trace kernel: zeroing is enqueued first, then ev[1], kernel, ev[2]
+  CU(h, cudaMemsetAsync(h->counts_dev, 0, sizeof(unsigned long long) * (size_t)a->n_bins * n_owned * N, h->stream));
+  CU(h, cudaMemsetAsync(h->lost_dev, 0, sizeof(unsigned long long) * (size_t)a->n_bins * N, h->stream));
+  n_launches += 2;
+  CU(h, cudaEventRecord(h->ev[1], h->stream));
+  rc = enqueue_trace(h, a, rank, world, /*compact=*/true, h->counts_dev, h->lost_dev, /*zero_first=*/false, rec != nullptr, n_slots,
+                     h->stream, &pl, &n_launches);
+  if (rc) return rc;
+  CU(h, cudaEventRecord(h->ev[2], h->stream));
+  // device -> host: owned rows scatter into the full [n_bins][N][N] host matrix (other rows zeroed)
+  if (world == 1) {
+    CU(h, cudaMemcpyAsync(counts_out, h->counts_dev, sizeof(uint64_t) * (size_t)a->n_bins * N * N, cudaMemcpyDeviceToHost, h->stream));
+  } else {
+    std::memset(counts_out, 0, sizeof(uint64_t) * (size_t)a->n_bins * N * N);
+    for (int b = 0; b < a->n_bins; ++b)
+      if (n_owned > 0)
+        CU(h, cudaMemcpy2DAsync(counts_out + ((size_t)b * N + rank) * N, sizeof(uint64_t) * (size_t)world * N,
+                                h->counts_dev + (size_t)b * n_owned * N, sizeof(uint64_t) * (size_t)N, sizeof(uint64_t) * (size_t)N,
+                                n_owned, cudaMemcpyDeviceToHost, h->stream));
+  }
+  std::vector<uint64_t> lost_host((size_t)a->n_bins * N);
+  CU(h, cudaMemcpyAsync(lost_host.data(), h->lost_dev, sizeof(uint64_t) * lost_host.size(), cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaEventRecord(h->ev[3], h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  if (lost_out) std::memcpy(lost_out, lost_host.data(), sizeof(uint64_t) * lost_host.size());
+  rc = collect_recorder(h, a, rec, n_slots, h->stream, false);
+  if (rc) return rc;
+  if (st) {
+    fill_stats(st, pl, a);
+    float ms = 0;
+    CU(h, cudaEventElapsedTime(&ms, h->ev[1], h->ev[2])); st->kernel_ms = ms;
+    CU(h, cudaEventElapsedTime(&ms, h->ev[0], h->ev[3])); st->total_ms = ms;
+    int64_t nl = 0;
+    for (uint64_t v : lost_host) nl += (int64_t)v;
+    st->rays_lost = nl;
+    st->n_launches = n_launches;
+  }
+  return RTHX_OK;
+}
+
+extern "C" int rthx_trace_exchange_device(rthx_handle* h, const rthx_trace_args* a, void* counts_dev, void* lost_dev, void* stream,
+                                          int zero_first, rthx_stats* st) {
+  if (!h) return RTHX_ERR_ARG;
+  int rc = check_args(h, a);
+  if (rc) return rc;
+  if (!counts_dev || !lost_dev) return fail(h, RTHX_ERR_ARG, "trace_device: NULL device buffer");
+  CU(h, cudaSetDevice(h->device));
+  LaunchPlan pl{};
+  int n_launches = 0;
+  rc = enqueue_trace(h, a, a->emitter_rank, a->emitter_world, /*compact=*/false, (unsigned long long*)counts_dev,
+                     (unsigned long long*)lost_dev, zero_first != 0, false, 0, (cudaStream_t)stream, &pl, &n_launches);
+  if (rc) return rc;
+  if (st) { fill_stats(st, pl, a); st->n_launches = n_launches; }
+  return RTHX_OK;
+}
+
+extern "C" int rthx_trace_exchange_multi(rthx_handle** hs, int n, const rthx_trace_args* a, uint64_t* counts_out, uint64_t* lost_out,
+                                         rthx_rec_out* rec, rthx_stats* st) {
+  if (!hs || n < 1 || !hs[0]) return RTHX_ERR_ARG;
+  rthx_handle* h0 = hs[0];
+  int rc = check_args(h0, a);
+  if (rc) return rc;
+  if (!counts_out) return fail(h0, RTHX_ERR_ARG, "trace_multi: counts_out is NULL");
+  const int N = h0->N;
+  for (int i = 0; i < n; ++i) if (!hs[i] || hs[i]->N != N || hs[i]->n_bands != h0->n_bands) return fail(h0, RTHX_ERR_ARG, "trace_multi: handles differ");
+  std::vector<LaunchPlan> plans(n);
+  std::vector<int> slots(n, 0);
+  int n_launches = 0;
+  // enqueue on every device first, then drain: the devices run concurrently
+  for (int i = 0; i < n; ++i) {
+    rthx_handle* h = hs[i];
+    CU(h0, cudaSetDevice(h->device));
+    const size_t n_owned = (size_t)((N - i + n - 1) / n);
+    CU(h0, ensure(&h->counts_dev, &h->counts_cap, (size_t)a->n_bins * n_owned * N));
+    CU(h0, ensure(&h->lost_dev, &h->lost_cap, (size_t)a->n_bins * N));
+    CU(h0, cudaEventRecord(h->ev[0], h->stream));
+    rc = prepare_recorder(h, a, rec, &slots[i], h->stream);
+    if (rc) return fail(h0, rc, h->err);
+    rc = enqueue_trace(h, a, i, n, true, h->counts_dev, h->lost_dev, true, rec != nullptr, slots[i], h->stream, &plans[i], &n_launches);
+    if (rc) return fail(h0, rc, h->err);
+    for (int b = 0; b < a->n_bins; ++b)
+      if (n_owned > 0)
+        CU(h0, cudaMemcpy2DAsync(counts_out + ((size_t)b * N + i) * N, sizeof(uint64_t) * (size_t)n * N, h->counts_dev + (size_t)b * n_owned * N,
+                                 sizeof(uint64_t) * (size_t)N, sizeof(uint64_t) * (size_t)N, n_owned, cudaMemcpyDeviceToHost, h->stream));
+    CU(h0, cudaEventRecord(h->ev[3], h->stream));
+  }
+  std::vector<uint64_t> lost_sum((size_t)a->n_bins * N, 0), lost_host((size_t)a->n_bins * N);
+  double max_ms = 0;
+  if (rec) rec->n_recorded = 0;
+  // recorded rays must come out in ascending element order: gather per device, then merge by element
+  struct RecChunk { int elem; std::vector<double> o, e; };
+  std::vector<RecChunk> chunks;
+  for (int i = 0; i < n; ++i) {
+    rthx_handle* h = hs[i];
+    CU(h0, cudaSetDevice(h->device));
+    CU(h0, cudaMemcpyAsync(lost_host.data(), h->lost_dev, sizeof(uint64_t) * lost_host.size(), cudaMemcpyDeviceToHost, h->stream));
+    CU(h0, cudaStreamSynchronize(h->stream));
+    for (size_t k = 0; k < lost_sum.size(); ++k) lost_sum[k] += lost_host[k];
+    float ms = 0;
+    CU(h0, cudaEventElapsedTime(&ms, h->ev[0], h->ev[3]));
+    max_ms = std::max(max_ms, (double)ms);
+    if (rec && slots[i] > 0) {
+      // every device holds slots for all recorded elements; only the rows it owns were written
+      const size_t rpe = (size_t)a->rays_per_emitter, pts = (size_t)slots[i] * rpe;
+      std::vector<double> buf(pts * 4);
+      std::vector<uint8_t> valid(pts);
+      CU(h0, cudaMemcpy(buf.data(), h->rec_pts_dev, sizeof(double) * pts * 4, cudaMemcpyDeviceToHost));
+      CU(h0, cudaMemcpy(valid.data(), h->rec_valid_dev, pts, cudaMemcpyDeviceToHost));
+      std::vector<int32_t> slot(N, -1);
+      for (int k = 0; k < a->n_rec_ids; ++k) if (a->rec_ids[k] >= 0 && a->rec_ids[k] < N) slot[a->rec_ids[k]] = 0;
+      int ord = 0;
+      for (int e = 0; e < N; ++e) {
+        if (slot[e] != 0) continue;
+        const int s_ = ord++;
+        if (e % n != i) continue;
+        RecChunk c; c.elem = e;
+        for (size_t r = 0; r < rpe; ++r) {
+          const size_t s = (size_t)s_ * rpe + r;
+          if (!valid[s]) continue;
+          c.o.push_back(buf[4 * s]); c.o.push_back(buf[4 * s + 1]); c.e.push_back(buf[4 * s + 2]); c.e.push_back(buf[4 * s + 3]);
+        }
+        chunks.push_back(std::move(c));
+      }
+    }
+  }
+  if (rec) {
+    std::sort(chunks.begin(), chunks.end(), [](const RecChunk& x, const RecChunk& y) { return x.elem < y.elem; });
+    for (auto& c : chunks)
+      for (size_t k = 0; k < c.o.size(); k += 2) {
+        if (rec->n_recorded >= rec->capacity) break;
+        const int64_t q = rec->n_recorded++;
+        rec->origins[2 * q] = c.o[k]; rec->origins[2 * q + 1] = c.o[k + 1];
+        rec->endpoints[2 * q] = c.e[k]; rec->endpoints[2 * q + 1] = c.e[k + 1];
+      }
+  }
+  if (lost_out) std::memcpy(lost_out, lost_sum.data(), sizeof(uint64_t) * lost_sum.size());
+  if (st) {
+    fill_stats(st, plans[0], a);
+    st->rays_traced = (int64_t)N * a->n_bins * a->rays_per_emitter;
+    int64_t nl = 0;
+    for (uint64_t v : lost_sum) nl += (int64_t)v;
+    st->rays_lost = nl; st->total_ms = max_ms; st->kernel_ms = 0; st->n_launches = n_launches;
+    int nbk = 0;
+    for (auto& p : plans) nbk += p.n_blocks;
+    st->n_blocks = nbk;
+  }
+  return RTHX_OK;
+}
+
+extern "C" int rthx_measure_fp64_peak(rthx_handle* h, double* tflops) {
+  if (!h || !tflops) return RTHX_ERR_ARG;
+  CU(h, cudaSetDevice(h->device));
+  const int threads = 256, blocks = h->prop.multiProcessorCount * 8, iters = 1 << 15;
+  if (!h->peak_dev) CU(h, cudaMalloc(&h->peak_dev, sizeof(double) * (size_t)threads * blocks));
+  CU(h, launch_fp64_peak(h->peak_dev, blocks, threads, 1024, h->stream));  // warm-up
+  double best = 0;
+  for (int rep = 0; rep < 3; ++rep) {
+    CU(h, cudaEventRecord(h->ev[0], h->stream));
+    CU(h, launch_fp64_peak(h->peak_dev, blocks, threads, iters, h->stream));
+    CU(h, cudaEventRecord(h->ev[1], h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    float ms = 0;
+    CU(h, cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
+    const double flops = 2.0 * 8.0 * (double)iters * threads * blocks;
+    best = std::max(best, flops / (ms * 1e-3) / 1e12);
+  }
+  *tflops = best;
+  return RTHX_OK;
+}

@@ -1,0 +1,91 @@
+// rthx_internal.h — structures shared between the host API (rthx_api.cu) and the kernels (rthx_kernels.cu).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "rthx.h"
+
+namespace rthx {
+
+enum : int { KIND_GENERIC = 0, KIND_AFFINE_QUAD = 1, KIND_AFFINE_TRI = 2 };
+
+// One coarse face (user polygon).  Staged in shared memory by every thread block when the whole array fits.
+struct CoarseDev {
+  double vx[4], vy[4];   // CCW vertices
+  double nx[4], ny[4];   // unit outward edge normals (the reference's `inwardNormals`, calculateInwardNormal.jl:1-12)
+  // affine lattice inverse (kinds 1,2): s = (p-a)·g1, t = (p-a)·g2, lattice cell (floor s, floor t) in [0,Nx)x[0,Ny)
+  double ax, ay, g1x, g1y, g2x, g2y;
+  int32_t nv;
+  int32_t kind;
+  int32_t Nx, Ny;
+  int32_t fine_off;      // first fine cell (global cell index)
+  int32_t lat_off;       // kind 2: offset of this face's lattice -> local fine index table, else -1
+  int32_t diag;          // kind 2: 0-based coarse edge that is the cut diagonal, else -1
+  int32_t nbr[4];        // coarse face across edge k (-1: locate generically / none)
+  uint8_t solid[4];
+  int32_t pad_;
+};
+static_assert(sizeof(CoarseDev) % 8 == 0, "CoarseDev must stay 8-byte sized");
+
+// Uniform-grid face set for the reference-faithful locator (spatialAccelerations.jl:2-59).
+// Set 0 = coarse mesh, set 1+c = fine cells of coarse face c.
+struct FaceSetDev {
+  double ox, oy, inv_cell;
+  int32_t nx, ny;
+  int32_t bucket_off;    // offset into bucket_start (which holds absolute offsets into bucket_items)
+  int32_t poly_base;     // local face f of this set is polygon poly_base + f (cells first, then coarse faces)
+  int32_t n_faces;
+  int32_t pad_;
+};
+
+struct TraceParams {
+  // mesh (device pointers)
+  const CoarseDev* coarse;
+  const FaceSetDev* sets;
+  const int32_t* bucket_start;
+  const int32_t* bucket_items;
+  const int32_t* poly_nv;
+  const double* poly_vx;       // [n_poly*4]
+  const double* poly_vy;
+  const double* poly_nx;       // unit outward normals per polygon edge
+  const double* poly_ny;
+  const double* cell_mid;      // [n_cells*2]
+  const double* cell_volume;   // [n_cells]
+  const int32_t* cell_surf_id; // [n_cells*4]
+  const double* beta;          // [n_bands*n_cells]
+  const double* uniform_beta;  // [n_bands]
+  const int32_t* lattice;      // lattice -> local fine index tables (kind 2)
+  const int32_t* em_cell;      // [N]
+  const int32_t* em_wall;      // [N]  -1 for volume emitters
+  const int32_t* em_coarse;    // [N]
+  const int32_t* bins;         // [n_bins] traced band indices
+  const int32_t* rec_slot;     // [N] recorder slot of element or -1 (nullptr = recording off)
+  // outputs
+  unsigned long long* counts;  // row (bi, y) at ((bi*rows_per_bin + y) * N)
+  unsigned long long* lost;    // [n_bins*N]
+  double* rec_pts;             // [n_rec*rays_per_emitter*4] origin xy, endpoint xy
+  uint8_t* rec_valid;          // [n_rec*rays_per_emitter]
+  // scalars
+  int32_t n_coarse, n_cells, n_surfaces, N;
+  int32_t n_bins;
+  int32_t emitter_rank, emitter_world, n_owned;
+  int32_t compact_rows;        // 1: counts row index is the owned-emitter ordinal, 0: the element index
+  int32_t row_chunks;
+  int32_t coarse_in_smem;
+  int32_t hist_in_smem;
+  int32_t force_generic;
+  int32_t rec_bin;
+  int64_t rays_per_emitter;
+  int64_t ray_id_offset;
+  uint64_t seed;
+  double nudge;
+};
+
+// launchers implemented in rthx_kernels.cu
+cudaError_t launch_trace_exchange(const TraceParams& p, int n_blocks, int block_threads, size_t smem_bytes,
+                                  cudaStream_t stream);
+cudaError_t configure_trace_kernel(size_t smem_bytes);
+cudaError_t launch_fp64_peak(double* out, int n_blocks, int block_threads, int iters, cudaStream_t stream);
+int trace_kernel_max_blocks_per_sm(int block_threads, size_t smem_bytes);
+
+}  // namespace rthx

@@ -1,0 +1,393 @@
+// rthx_kernels.cu — sm_100a kernels of the exchange-factor tracer.
+//
+// K1 trace_exchange_kernel fuses the four stages of the path for one (emitter row, band, ray chunk) per block:
+//   (1) emitter sampling, one thread per ray, counter-based Philox4x32-10 keyed by (seed | ray id, emitter, band)
+//       — emitSurfaceRay2D.jl:1-27 + lambertSample2D.jl:1-11, emitVolumeRay2D.jl:1-33;
+//   (2) first-interaction traversal (traceRay.jl:20-147 with distToSurface2D.jl:2-18 and the point location of
+//       findFace2D.jl:1-101, replaced by an analytic lattice inverse on verified affine sub-meshes);
+//   (3) tally into a per-block shared-memory u32 histogram of the block's source row, flushed with red.add.u64
+//       into the global count matrix (parallelRayTracing.jl:104,124,144-146);
+//   (4) optional RayRecorder output of origin / endpoint (parallelRayTracing.jl:108,120-123,135-138).
+// No tensor cores: the path is branchy FP64 geometry + integer RNG + integer atomics, not a contraction.
+#include "rthx_internal.h"
+
+#include <math_constants.h>
+
+namespace rthx {
+
+// ------------------------------------------------------------------------------------------------------------
+// RNG: Philox4x32-10 and the uniform conversions of the rthx.h contract
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+
+// ((x >> 12) + 0.5) * 2^-52 with x = hi:lo, built by mantissa injection: [1,2) - (1 - 2^-53), exact.
+__device__ __forceinline__ double u52(uint32_t lo, uint32_t hi) {
+  const double d = __hiloint2double((int)(0x3FF00000u | (hi >> 12)), (int)((hi << 20) | (lo >> 12)));
+  return d - 0.99999999999999988897769753748;  // 1 - 2^-53
+}
+// ((w >> 9) + 0.5) * 2^-23, exact.
+__device__ __forceinline__ float u23(uint32_t w) {
+  return __uint_as_float(0x3F800000u | (w >> 9)) - 0.999999940395355224609375f;  // 1 - 2^-24
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// geometry primitives
+// ------------------------------------------------------------------------------------------------------------
+// distToSurface2D.jl:2-18 on a coarse face: smallest positive u_i = ((v_i - p)·n_i)/(d·n_i) over edges with
+// |d·n_i| >= 1e-10, first index on ties.  The argmin is found on cross-multiplied fractions (one division
+// instead of nv); ties/rounding differ from the reference only on a set of measure ~1e-16.
+__device__ __forceinline__ double dist_to_coarse(const CoarseDev& f, double px, double py, double dx, double dy, int& k) {
+  double bn = 0.0, bd = 0.0;  // best numerator / denominator (bd > 0 when a candidate exists)
+  int bk = 0;
+  bool have = false;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (i < f.nv) {
+      const double den = dx * f.nx[i] + dy * f.ny[i];
+      const double num = (f.vx[i] - px) * f.nx[i] + (f.vy[i] - py) * f.ny[i];
+      // u = num/den > 0  <=>  num and den have the same sign (and num != 0)
+      const bool ok = (fabs(den) >= 1e-10) && ((num > 0.0 && den > 0.0) || (num < 0.0 && den < 0.0));
+      if (ok) {
+        const double an = fabs(num), ad = fabs(den);
+        if (!have || an * bd < bn * ad) { bn = an; bd = ad; bk = i; have = true; }
+      }
+    }
+  }
+  k = bk;
+  return have ? bn / bd : CUDART_INF;
+}
+
+// Faithful distToSurface2D on an arbitrary polygon of the generic tables (used by the generic locator for the
+// wall index of a fine cell, traceRay.jl:51).
+__device__ __forceinline__ int wall_of_poly(const TraceParams& p, int poly, double px, double py, double dx, double dy) {
+  const int nv = p.poly_nv[poly];
+  double best = CUDART_INF;
+  int bi = 0;
+  for (int i = 0; i < nv; ++i) {
+    const double nx = p.poly_nx[poly * 4 + i], ny = p.poly_ny[poly * 4 + i];
+    const double den = dx * nx + dy * ny;
+    double u = CUDART_INF;
+    if (fabs(den) >= 1e-10) u = ((p.poly_vx[poly * 4 + i] - px) * nx + (p.poly_vy[poly * 4 + i] - py) * ny) / den;
+    if (u <= 0.0) u = CUDART_INF;
+    if (u < best) { best = u; bi = i; }
+  }
+  return bi;
+}
+
+// pointInPolygonFast2D, findFace2D.jl:77-101 (crossing number).
+__device__ __forceinline__ bool point_in_poly(const TraceParams& p, int poly, double px, double py) {
+  const int nv = p.poly_nv[poly];
+  bool inside = false;
+  int j = nv - 1;
+  for (int i = 0; i < nv; ++i) {
+    const double xi = p.poly_vx[poly * 4 + i], yi = p.poly_vy[poly * 4 + i];
+    const double xj = p.poly_vx[poly * 4 + j], yj = p.poly_vy[poly * 4 + j];
+    if ((yi > py) != (yj > py)) {
+      const double slope = (xj - xi) / (yj - yi);
+      const double ix = xi + slope * (py - yi);
+      if (px < ix) inside = !inside;
+    }
+    j = i;
+  }
+  return inside;
+}
+
+// findFaceUniformGrid2D, findFace2D.jl:2-27: bucket of the uniform grid, first face passing the PIP test.
+// (The bbox-prefilter fallback of :30-45 can only succeed where the bucket scan succeeds, up to rounding of the
+// bucket index on a set of measure zero; it is restated in the CPU oracle and omitted here.)
+__device__ __noinline__ int find_face_generic(const TraceParams& p, int set, double px, double py) {
+  const FaceSetDev fs = p.sets[set];
+  const double fi = floor((px - fs.ox) * fs.inv_cell), fj = floor((py - fs.oy) * fs.inv_cell);
+  if (!(fi >= 0.0 && fi < (double)fs.nx && fj >= 0.0 && fj < (double)fs.ny)) return -1;
+  const int b = fs.bucket_off + (int)fi + (int)fj * fs.nx;
+  const int k0 = p.bucket_start[b], k1 = p.bucket_start[b + 1];
+  for (int k = k0; k < k1; ++k) {
+    const int f = p.bucket_items[k];
+    if (point_in_poly(p, fs.poly_base + f, px, py)) return f;
+  }
+  return -1;
+}
+
+// Fine-cell location inside coarse face c: returns the local fine index or -1.
+__device__ __forceinline__ int locate_fine(const TraceParams& p, const CoarseDev& cf, int c, int kind, double px, double py) {
+  if (kind == KIND_GENERIC) return find_face_generic(p, 1 + c, px, py);
+  const double rx = px - cf.ax, ry = py - cf.ay;
+  const double s = rx * cf.g1x + ry * cf.g1y, t = rx * cf.g2x + ry * cf.g2y;
+  if (!(s >= 0.0 && t >= 0.0 && s < (double)cf.Nx && t < (double)cf.Ny)) return -1;
+  const int n = __double2int_rd(s), m = __double2int_rd(t);
+  const int cell = n + m * cf.Nx;
+  if (kind == KIND_AFFINE_QUAD) return cell;
+  return __ldg(p.lattice + cf.lat_off + cell);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K1: fused emit + trace + tally (+ record)
+// ------------------------------------------------------------------------------------------------------------
+struct EmitterRegs {
+  // surface: p1, edge e = p2 - p1, local frame xl (unit edge), yl (left normal)
+  // volume : triangle vertices A,B,C,(D) and ABC area fraction
+  double ax, ay, bx, by, cx, cy, dx, dy;
+  double midx, midy;
+  double frac_abc;
+  int nv;
+};
+
+template <bool HIST_SMEM>
+__global__ void __launch_bounds__(256) trace_exchange_kernel(const __grid_constant__ TraceParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  CoarseDev* s_coarse = reinterpret_cast<CoarseDev*>(smem_raw);
+  const size_t coarse_bytes = p.coarse_in_smem ? sizeof(CoarseDev) * (size_t)p.n_coarse : 0;
+  uint32_t* hist = reinterpret_cast<uint32_t*>(smem_raw + coarse_bytes);
+
+  // block -> (owned emitter ordinal y, traced bin bi, ray chunk)
+  const unsigned bid = blockIdx.x;
+  const int chunk = (int)(bid % (unsigned)p.row_chunks);
+  const unsigned t1 = bid / (unsigned)p.row_chunks;
+  const int bi = (int)(t1 % (unsigned)p.n_bins);
+  const int y = (int)(t1 / (unsigned)p.n_bins);
+  const int e = p.emitter_rank + y * p.emitter_world;
+  const int band = p.bins[bi];
+  const int N = p.N;
+
+  // stage coarse faces, clear the row histogram
+  if (p.coarse_in_smem) {
+    const int nw = (int)(coarse_bytes / 8);
+    const double* src = reinterpret_cast<const double*>(p.coarse);
+    double* dst = reinterpret_cast<double*>(s_coarse);
+    for (int i = threadIdx.x; i < nw; i += blockDim.x) dst[i] = src[i];
+  }
+  if (HIST_SMEM)
+    for (int i = threadIdx.x; i < N; i += blockDim.x) hist[i] = 0u;
+  const CoarseDev* coarse = p.coarse_in_smem ? s_coarse : p.coarse;
+
+  // ray range of this chunk
+  const int64_t per = (p.rays_per_emitter + p.row_chunks - 1) / p.row_chunks;
+  const int64_t r_begin = (int64_t)chunk * per;
+  int64_t r_end = r_begin + per;
+  if (r_end > p.rays_per_emitter) r_end = p.rays_per_emitter;
+
+  // block-uniform emitter data (all threads read the same addresses: broadcast loads)
+  const int g = p.em_cell[e];
+  const int wall = p.em_wall[e];
+  const int c0 = p.em_coarse[e];
+  const bool is_surface = wall >= 0;
+  EmitterRegs em;
+  em.nv = p.poly_nv[g];
+  em.midx = p.cell_mid[2 * g];
+  em.midy = p.cell_mid[2 * g + 1];
+  if (is_surface) {
+    const int j = (wall + 1 == em.nv) ? 0 : wall + 1;
+    const double p1x = p.poly_vx[4 * g + wall], p1y = p.poly_vy[4 * g + wall];
+    const double p2x = p.poly_vx[4 * g + j], p2y = p.poly_vy[4 * g + j];
+    const double ex = p2x - p1x, ey = p2y - p1y;
+    const double len = sqrt(ex * ex + ey * ey);
+    em.ax = p1x; em.ay = p1y;          // p1
+    em.bx = ex;  em.by = ey;           // edge
+    em.cx = ex / len; em.cy = ey / len;  // xVecLocal
+    em.dx = -em.cy; em.dy = em.cx;     // yVecLocal
+    em.frac_abc = 0.0;
+  } else {
+    em.ax = p.poly_vx[4 * g + 0]; em.ay = p.poly_vy[4 * g + 0];
+    em.bx = p.poly_vx[4 * g + 1]; em.by = p.poly_vy[4 * g + 1];
+    em.cx = p.poly_vx[4 * g + 2]; em.cy = p.poly_vy[4 * g + 2];
+    em.dx = p.poly_vx[4 * g + 3]; em.dy = p.poly_vy[4 * g + 3];
+    em.frac_abc = 0.5 * (em.ax * (em.by - em.cy) + em.bx * (em.cy - em.ay) + em.cx * (em.ay - em.by)) / p.cell_volume[g];
+  }
+  const double ub = p.uniform_beta[band];
+  const bool uniform = ub > -0.1;                      // traceRay.jl:4
+  const double* beta_band = p.beta + (size_t)band * p.n_cells;
+  const double beta_u = beta_band[0];                  // traceRay.jl:6-11: beta of fine_mesh[1][1]
+  const double nudge = p.nudge;
+  const int rec_slot = (p.rec_slot != nullptr && band == p.rec_bin) ? p.rec_slot[e] : -1;
+  const size_t row = p.compact_rows ? ((size_t)bi * p.n_owned + y) : ((size_t)bi * N + e);
+  unsigned long long* count_row = p.counts + row * (size_t)N;
+
+  __syncthreads();
+
+  const uint2 key = make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32));
+  unsigned int n_lost = 0;
+
+  for (int64_t r = r_begin + threadIdx.x; r < r_end; r += blockDim.x) {
+    const uint64_t ray_id = (uint64_t)(p.ray_id_offset + r);
+    const uint32_t c_lo = (uint32_t)ray_id, c_hi = (uint32_t)(ray_id >> 32);
+    const uint32_t cw = ((uint32_t)band << 8);
+    double px, py, dx, dy, R_S;
+    // ---- stage 1: emission --------------------------------------------------------------------------------
+    if (is_surface) {
+      const uint4 w0 = philox4x32_10(make_uint4(c_lo, c_hi, (uint32_t)e, cw | 0u), key);
+      const uint4 w1 = philox4x32_10(make_uint4(c_lo, c_hi, (uint32_t)e, cw | 1u), key);
+      const double R = u52(w0.x, w0.y);
+      px = em.ax + em.bx * R;
+      py = em.ay + em.by * R;
+      px = px + (em.midx - px) * nudge;
+      py = py + (em.midy - py) * nudge;
+      // lambertSample2D: Float32 variates / sqrt / square, the rest in Float64
+      const float cosT = __fsqrt_rn(u23(w0.z));
+      const float cos2 = __fmul_rn(cosT, cosT);
+      const double sinT = sqrt(1.0 - (double)cos2);
+      const double xdir = sinT * cospi(2.0 * (double)u23(w0.w));   // cos(2*pi*R)
+      const double zdir = (double)cosT;
+      dx = em.cx * xdir + em.dx * zdir;
+      dy = em.cy * xdir + em.dy * zdir;
+      R_S = u52(w1.x, w1.y);
+    } else {
+      const uint4 w0 = philox4x32_10(make_uint4(c_lo, c_hi, (uint32_t)e, cw | 0u), key);
+      const uint4 w1 = philox4x32_10(make_uint4(c_lo, c_hi, (uint32_t)e, cw | 1u), key);
+      const uint4 w2 = philox4x32_10(make_uint4(c_lo, c_hi, (uint32_t)e, cw | 2u), key);
+      const double R1 = u52(w0.x, w0.y), R2 = u52(w0.z, w0.w);
+      const double sq = sqrt(R1);
+      const bool first = (em.nv == 3) || (u52(w1.x, w1.y) < em.frac_abc);
+      // (1-sqrt R1) V0 + sqrt R1 (1-R2) V1 + sqrt R1 R2 V2 with (V0,V1,V2) = (A,B,C) or (C,D,A)
+      const double v0x = first ? em.ax : em.cx, v0y = first ? em.ay : em.cy;
+      const double v1x = first ? em.bx : em.dx, v1y = first ? em.by : em.dy;
+      const double v2x = first ? em.cx : em.ax, v2y = first ? em.cy : em.ay;
+      const double a0 = 1.0 - sq, a1 = sq * (1.0 - R2), a2 = sq * R2;
+      px = a0 * v0x + a1 * v1x + a2 * v2x;
+      py = a0 * v0y + a1 * v1y + a2 * v2y;
+      px = px + (em.midx - px) * nudge;
+      py = py + (em.midy - py) * nudge;
+      // theta = acos(1-2R): cos(theta) = 1-2R, sin(theta) = 2 sqrt(R(1-R)) (algebraically identical)
+      const double Rt = u52(w1.z, w1.w);
+      const double cosT = 1.0 - 2.0 * Rt;
+      const double sinT = 2.0 * sqrt(Rt * (1.0 - Rt));
+      dx = sinT * cospi(2.0 * u52(w2.x, w2.y));
+      dy = cosT;
+      R_S = u52(w2.z, w2.w);
+    }
+    const double ox = px, oy = py;
+
+    // ---- stage 2: first-interaction traversal (traceRayUniform / traceRayVariable) --------------------------
+    const double neg_log = -log(R_S);
+    double S = uniform ? (beta_u > 0.0 ? neg_log / beta_u : CUDART_INF) : 0.0;  // remaining free path (uniform)
+    double acc = 0.0;                                                          // accumulated tau (variable)
+    int c = c0;
+    int absorber = -1;
+    for (int it = 0; it < 10000; ++it) {
+      const CoarseDev& cf = coarse[c];
+      const int kind = p.force_generic ? KIND_GENERIC : cf.kind;
+      int k;
+      const double u = dist_to_coarse(cf, px, py, dx, dy, k);
+      bool gas;
+      double tau_b = 0.0;
+      if (uniform) {
+        gas = S < u;
+      } else {
+        const int f0 = locate_fine(p, cf, c, kind, px, py);      // traceRay.jl:87-100
+        if (f0 < 0) break;
+        const double local_beta = beta_band[cf.fine_off + f0];
+        tau_b = local_beta * u;
+        gas = acc + tau_b >= neg_log;
+        if (gas) S = (neg_log - acc) / local_beta;
+      }
+      if (gas) {
+        px = px + (S - nudge) * dx;
+        py = py + (S - nudge) * dy;
+        const int f = locate_fine(p, cf, c, kind, px, py);
+        if (f >= 0) absorber = p.n_surfaces + cf.fine_off + f;
+        break;
+      } else if (!(u < CUDART_INF)) {
+        break;                                                  // no edge ahead: the reference ends in NaN -> lost
+      } else if (cf.solid[k]) {
+        px = px + (u - nudge) * dx;
+        py = py + (u - nudge) * dy;
+        const int f = locate_fine(p, cf, c, kind, px, py);
+        if (f < 0) break;
+        const int gc = cf.fine_off + f;
+        int w;
+        if (kind == KIND_GENERIC) {
+          w = wall_of_poly(p, gc, px, py, dx, dy);              // traceRay.jl:51
+        } else if (kind == KIND_AFFINE_QUAD || p.poly_nv[gc] == 3) {
+          w = k;                                                // fine wall lying on coarse edge k
+        } else {
+          if (k == cf.diag) break;
+          w = (k < cf.diag) ? k : k + 1;                        // quad cell of a mirrored-triangle lattice
+        }
+        absorber = __ldg(p.cell_surf_id + 4 * gc + w);          // -1: fine wall not solid -> lost
+        break;
+      } else {
+        px = px + (u + nudge) * dx;
+        py = py + (u + nudge) * dy;
+        if (uniform) S -= u; else acc += tau_b;
+        int nc = (kind == KIND_GENERIC) ? -1 : cf.nbr[k];
+        if (nc < 0) nc = find_face_generic(p, 0, px, py);       // traceRay.jl:59-65
+        if (nc < 0) break;
+        c = nc;
+      }
+    }
+
+    // ---- stage 3/4: tally (+ record) -------------------------------------------------------------------------
+    if (absorber >= 0) {
+      if (HIST_SMEM) atomicAdd(&hist[absorber], 1u);
+      else atomicAdd(&count_row[absorber], 1ULL);
+      if (rec_slot >= 0) {
+        const size_t s = (size_t)rec_slot * (size_t)p.rays_per_emitter + (size_t)r;
+        double* o = p.rec_pts + 4 * s;
+        o[0] = ox; o[1] = oy; o[2] = px; o[3] = py;
+        p.rec_valid[s] = 1;
+      }
+    } else {
+      ++n_lost;
+    }
+  }
+
+  // ---- flush --------------------------------------------------------------------------------------------------
+  for (int off = 16; off > 0; off >>= 1) n_lost += __shfl_down_sync(0xffffffffu, n_lost, off);
+  if ((threadIdx.x & 31) == 0 && n_lost) atomicAdd(&p.lost[(size_t)bi * N + e], (unsigned long long)n_lost);
+  if (HIST_SMEM) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+      const uint32_t v = hist[i];
+      if (v) atomicAdd(&count_row[i], (unsigned long long)v);   // red.global.add.u64, result unused
+    }
+  }
+}
+
+cudaError_t configure_trace_kernel(size_t smem_bytes) {
+  cudaError_t e = cudaFuncSetAttribute(trace_exchange_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(trace_exchange_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+}
+
+int trace_kernel_max_blocks_per_sm(int block_threads, size_t smem_bytes) {
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, trace_exchange_kernel<true>, block_threads, smem_bytes) != cudaSuccess) return 0;
+  return n;
+}
+
+cudaError_t launch_trace_exchange(const TraceParams& p, int n_blocks, int block_threads, size_t smem_bytes, cudaStream_t stream) {
+  if (n_blocks <= 0) return cudaSuccess;
+  if (p.hist_in_smem) trace_exchange_kernel<true><<<n_blocks, block_threads, smem_bytes, stream>>>(p);
+  else trace_exchange_kernel<false><<<n_blocks, block_threads, smem_bytes, stream>>>(p);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// FP64 FMA-chain micro-benchmark: the measured denominator of the FP64 roofline.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters) {
+  double a0 = 1.0 + threadIdx.x * 1e-9, a1 = a0 + 1e-3, a2 = a0 + 2e-3, a3 = a0 + 3e-3;
+  double a4 = a0 + 4e-3, a5 = a0 + 5e-3, a6 = a0 + 6e-3, a7 = a0 + 7e-3;
+  const double m = 0.999999999, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+cudaError_t launch_fp64_peak(double* out, int n_blocks, int block_threads, int iters, cudaStream_t stream) {
+  fp64_peak_kernel<<<n_blocks, block_threads, 0, stream>>>(out, iters);
+  return cudaGetLastError();
+}
+
+}  // namespace rthx

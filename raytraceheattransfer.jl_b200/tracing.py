@@ -1,0 +1,206 @@
+"""Host-side mirror of the reference's exchange-factor driver, with the emitter loop replaced by the CUDA library.
+
+  dispatch_ray_trace         functor, RT2D/Shared2D/multiDispatchRayTrace2D.jl:1-18
+  exchangeRayTracing         RT2D/ExchangeFactors2D/exchangeRayTracing.jl:1-74
+  parallelRayTracing         RT2D/ExchangeFactors2D/parallelRayTracing.jl:1-62
+  computeExchangeFactorsBin  RT2D/ExchangeFactors2D/parallelRayTracing.jl:64-159 (+ row_normalize! :161-169)
+  group_uniform_bins         RT2D/ExchangeFactors2D/parallelRayTracing.jl:171-191
+  get_w / get_b              HeatTransfer/exchangeFactorSmoothing/smoothExchangeFactors.jl:320-375
+
+(RT2D = src/RayTracing/RayTracing2D.)  All bands that need a trace are batched into ONE device launch; the
+per-band `SparseMatrixCSC` of the reference becomes a `scipy.sparse.csc_matrix`.  New optional keywords that
+the reference does not have: `seed` (its RNG is unseeded), `device`, `locator`.
+"""
+from __future__ import annotations
+
+import secrets
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import scipy.sparse as sp
+
+from .flatten import flatten_domain
+from ._lib import DeviceTracer, DEFAULT_NUDGE
+from ._abi import RTHX_LOCATOR_AUTO
+
+
+def _isapprox(a: float, b: float, atol: float, rtol: float) -> bool:
+    return abs(a - b) <= max(atol, rtol * max(abs(a), abs(b)))
+
+
+def group_uniform_bins(uniform_across_bin: Sequence[float], atol: float = 1e-8, rtol: float = 1e-8):
+    """parallelRayTracing.jl:171-191.  Returns (groups, reps, nonuniform) with 1-based bin indices."""
+    groups: List[List[int]] = []
+    reps: List[float] = []
+    nonuniform: List[int] = []
+    for i, v in enumerate(uniform_across_bin, start=1):
+        if v < -0.1:
+            nonuniform.append(i)
+            continue
+        idx = next((k for k, r in enumerate(reps) if _isapprox(r, v, atol, rtol)), None)
+        if idx is None:
+            reps.append(v)
+            groups.append([i])
+        else:
+            groups[idx].append(i)
+    return groups, reps, nonuniform
+
+
+def counts_to_F(counts: np.ndarray, rays_per_emitter: int, verbose_loss: bool = True) -> sp.csc_matrix:
+    """Integer tallies -> row-normalised sparse F, composing parallelRayTracing.jl:144-146 (value c/rays) with
+    row_normalize! (:161-169): F[i,j] = (c_ij/R) / sum_j(c_ij/R); zero tallies are not stored; the loss line
+    is printed unconditionally like the reference (:163)."""
+    c = sp.csr_matrix(counts)            # drops zeros
+    inv_rays = 1.0 / rays_per_emitter if rays_per_emitter else 0.0
+    vals = c.data.astype(np.float64) * inv_rays
+    F = sp.csr_matrix((vals, c.indices, c.indptr), shape=c.shape)
+    rs = np.asarray(F.sum(axis=1)).ravel()
+    if verbose_loss:
+        max_loss = int(round(rays_per_emitter * float(np.max(np.abs(1.0 - rs))))) if len(rs) else 0
+        print(f"Maximum ray tracing ray loss per emitter: {max_loss}/{rays_per_emitter}")
+    with np.errstate(divide="ignore", invalid="ignore"):
+        F.data /= np.repeat(rs, np.diff(F.indptr))
+    return F.tocsc()
+
+
+def _tracer_for(rtm, device: int):
+    """Re-flatten on every call (user code mutates properties between construction and tracing) and create the
+    device handle; the handle of the previous call is dropped."""
+    flat = flatten_domain(rtm)
+    old = getattr(rtm, "_device", None)
+    if old is not None:
+        old.close()
+    rtm._device = DeviceTracer(flat, device=device)
+    return rtm._device
+
+
+def computeExchangeFactorsBins(rtm, rays_per_emitter: int, nudge: float, spectral_bins: Sequence[int],
+                               verbose: bool, rec, seed: int, device: int = 0,
+                               locator: int = RTHX_LOCATOR_AUTO) -> List[sp.csc_matrix]:
+    """Batched form of computeExchangeFactorsBin: traces every requested (1-based) bin in one launch."""
+    tr = _tracer_for(rtm, device)
+    rec_ids = [i - 1 for i in rec.ids] if rec is not None else None
+    rec_bin = (rec.bin - 1) if rec is not None else 0
+    verbose and print(f"  Using CUDA device {device} for spectral bins {list(spectral_bins)}")
+    out = tr.trace(rays_per_emitter, seed=seed, bins=[b - 1 for b in spectral_bins], nudge=nudge,
+                   rec_ids=rec_ids, rec_bin=rec_bin, locator=locator)
+    rtm.last_trace_stats = out["stats"]
+    rtm.last_counts = out["counts"]
+    rtm.last_lost = out["lost"]
+    if rec is not None and "origins" in out:
+        # parallelRayTracing.jl:120-123 push into rec.origins[tid]; any slot works for collect_rays
+        rec.origins[0] = np.concatenate([rec.origins[0], out["origins"]], axis=0)
+        rec.endpoints[0] = np.concatenate([rec.endpoints[0], out["endpoints"]], axis=0)
+    return [counts_to_F(out["counts"][k], rays_per_emitter) for k in range(len(spectral_bins))]
+
+
+def computeExchangeFactorsBin(rtm, rays_per_emitter: int, nudge: float, spectral_bin: int, verbose: bool = False,
+                              rec=None, seed: int = 0x5EED0001, device: int = 0,
+                              locator: int = RTHX_LOCATOR_AUTO) -> sp.csc_matrix:
+    """computeExchangeFactorsBin(rtm, rays_per_emitter, nudge, spectral_bin, ..., rec) -> sparse F (1-based bin)."""
+    return computeExchangeFactorsBins(rtm, rays_per_emitter, nudge, [spectral_bin], verbose, rec, seed, device,
+                                      locator)[0]
+
+
+def parallelRayTracing(rtm, rays_total: int, nudge: float, verbose: bool, rec=None, seed: Optional[int] = None,
+                       device: int = 0, locator: int = RTHX_LOCATOR_AUTO):
+    """parallelRayTracing(rtm, rays_total, nudge, verbose; rec) -> (F_raw, rays_per_emitter)."""
+    if seed is None:
+        seed = secrets.randbits(64)   # the reference is unseeded: a fresh stream per call
+    num_emitters = rtm.num_elements
+    rays_per_emitter = rays_total // num_emitters                        # parallelRayTracing.jl:6
+    n_bins = rtm.n_spectral_bins
+    if rtm.spectral_mode == "spectral_variable":
+        verbose and print(f"Computing {n_bins} separate F matrices for variable spectral extinction")
+        groups, reps, nonuniform = group_uniform_bins(rtm.uniform_across_bin)
+        to_trace = list(nonuniform) + [g[0] for g in groups]
+        mats = computeExchangeFactorsBins(rtm, rays_per_emitter, nudge, to_trace, verbose, rec, seed, device, locator)
+        F_raw_vector: List[Optional[sp.csc_matrix]] = [None] * n_bins
+        for b, F in zip(to_trace[: len(nonuniform)], mats[: len(nonuniform)]):
+            F_raw_vector[b - 1] = F
+        for g, F in zip(groups, mats[len(nonuniform):]):
+            for j in g:
+                F_raw_vector[j - 1] = F                                  # group members alias one matrix (:38-41)
+        return F_raw_vector, rays_per_emitter
+    if rtm.spectral_mode != "grey":
+        verbose and print(f"Computing single F matrix for uniform spectral extinction ({n_bins} bins)")
+    else:
+        verbose and print("Computing single F matrix for grey extinction")
+    F_raw = computeExchangeFactorsBins(rtm, rays_per_emitter, nudge, [1], verbose, rec, seed, device, locator)[0]
+    return F_raw, rays_per_emitter
+
+
+def get_w(rtm, spectral_bin: int = 1) -> np.ndarray:
+    """Reciprocity weights: wall length for surfaces, max(1e-6, 4*beta*V) for volumes
+    (smoothExchangeFactors.jl:320-341)."""
+    ns = rtm.num_surfaces
+    w = np.zeros(rtm.num_elements)
+    for (c, f, wall), s in rtm.surface_mapping.items():
+        w[s - 1] = rtm.fine_mesh[c - 1][f - 1].area[wall - 1]
+    for (c, f), v in rtm.volume_mapping.items():
+        cell = rtm.fine_mesh[c - 1][f - 1]
+        w[ns + v - 1] = max(1e-6, 4 * cell.beta(spectral_bin - 1) * cell.volume)
+    return w
+
+
+def get_b(rtm) -> np.ndarray:
+    """Reflection-scattering coefficient b: 1-eps for surfaces, sigma_s/(sigma_s+kappa) for volumes, per band
+    (smoothExchangeFactors.jl:343-357)."""
+    ns = rtm.num_surfaces
+    nb = rtm.n_spectral_bins
+    b = np.zeros((rtm.num_elements, nb))
+    for m in range(nb):
+        for (c, f, wall), s in rtm.surface_mapping.items():
+            b[s - 1, m] = 1 - rtm.fine_mesh[c - 1][f - 1].eps(wall - 1, m)
+        for (c, f), v in rtm.volume_mapping.items():
+            cell = rtm.fine_mesh[c - 1][f - 1]
+            k = cell.kappa_g[m] if isinstance(cell.kappa_g, list) else cell.kappa_g
+            s_ = cell.sigma_s_g[m] if isinstance(cell.sigma_s_g, list) else cell.sigma_s_g
+            b[ns + v - 1, m] = s_ / (s_ + k) if (s_ + k) != 0 else 0.0
+    return b
+
+
+def exchangeRayTracing(rtm, rays_tot: int, nudge: float, max_iters: int, k_dykstra, verbose: bool, rec,
+                       seed: Optional[int] = None, device: int = 0, locator: int = RTHX_LOCATOR_AUTO,
+                       smooth: bool = True):
+    """exchangeRayTracing!(rtm, rays_tot, nudge, max_iters, k_dykstra, verbose, rec): trace, optional
+    surfaces-only crop (:9-11), smooth (:14-70), store rtm.F_raw / rtm.F_smooth (:73-74)."""
+    from .smoothing import smooth_F
+    F_raw, rays_per_emitter = parallelRayTracing(rtm, rays_tot, nudge, verbose, rec=rec, seed=seed, device=device,
+                                                 locator=locator)
+    ns = rtm.num_surfaces
+    if rtm.surfaces_only and not isinstance(F_raw, list):
+        F_raw = F_raw[:ns, :ns]
+    if not smooth:
+        F_smooth = F_raw
+    elif rtm.spectral_mode == "spectral_variable":
+        groups, reps, nonuniform = group_uniform_bins(rtm.uniform_across_bin)
+        F_smooth = [None] * rtm.n_spectral_bins
+        for b in nonuniform:
+            F_smooth[b - 1] = smooth_F(F_raw[b - 1], get_w(rtm, spectral_bin=b), ns, max_iters=max_iters,
+                                       k_dykstra=k_dykstra, verbose=verbose,
+                                       smooth_surfaces_only=rtm.surfaces_only)
+        for g in groups:
+            rep = g[0]
+            Fs = smooth_F(F_raw[rep - 1], get_w(rtm, spectral_bin=rep), ns, max_iters=max_iters,
+                          k_dykstra=k_dykstra, verbose=verbose, smooth_surfaces_only=rtm.surfaces_only)
+            for j in g:
+                F_smooth[j - 1] = Fs
+    else:
+        F_smooth = smooth_F(F_raw, get_w(rtm), ns, max_iters=max_iters, k_dykstra=k_dykstra, verbose=verbose,
+                            smooth_surfaces_only=rtm.surfaces_only)
+    rtm.F_raw = F_raw
+    rtm.F_smooth = F_smooth
+    return F_smooth
+
+
+def dispatch_ray_trace(rtm, rays_tot: int, method: str = "exchange", nudge: Optional[float] = None,
+                       k_dykstra=None, max_iters: int = 1000, verbose: bool = True, rec=None, **kw):
+    """(rtm)(rays_tot; method, nudge, k_dykstra, max_iters, verbose, rec) — multiDispatchRayTrace2D.jl:1-18."""
+    trace_nudge = DEFAULT_NUDGE if nudge is None else nudge
+    method = method.lstrip(":")
+    if method == "exchange":
+        return exchangeRayTracing(rtm, rays_tot, trace_nudge, max_iters, k_dykstra, verbose, rec, **kw)
+    if method == "direct":
+        raise NotImplementedError("method=:direct is outside the scope of this drop-in (exchange path only)")
+    raise ValueError(f"Unknown ray tracing method: {method}, must be :exchange or :direct")
