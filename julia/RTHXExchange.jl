@@ -1,0 +1,187 @@
+# RTHXExchange.jl — the reference-side binding of librthx.so (include/rthx.h).
+#
+# `include("RTHXExchange.jl")` after `using RayTraceHeatTransfer` replaces the emitter loop of
+#     RayTraceHeatTransfer.parallelRayTracing(rtm, rays_total, nudge, verbose; rec)
+#         (src/RayTracing/RayTracing2D/ExchangeFactors2D/parallelRayTracing.jl:1-62)
+# by one `ccall` into the CUDA library; `exchangeRayTracing!`, `smooth_F` and `solveEquilibrium!` stay untouched, so
+# `mesh(N_rays; method=:exchange, rec)` keeps its signature, its F_raw / F_smooth outputs and its RayRecorder
+# semantics.  Julia is not available in the build image of this repository: this file is exercised only through its
+# 1:1 Python twin (raytraceheattransfer.jl_b200/{flatten,tracing,_lib}.py), which drives the same C ABI.
+module RTHXExchange
+
+using RayTraceHeatTransfer
+using SparseArrays
+using GeometryBasics: Point2
+import RayTraceHeatTransfer: RayTracingDomain2D, group_uniform_bins
+
+const LIB = get(ENV, "RTHX_LIB", "librthx.so")
+const SEED = Ref{UInt64}(rand(UInt64))      # set RTHXExchange.SEED[] for reproducible runs
+const DEVICES = Ref{Vector{Cint}}(Cint[0])  # devices used by the single-process multi-GPU entry point
+
+# ---- struct twins of include/rthx.h (field order and types must match) -------------------------------------------
+struct RthxMesh
+    n_coarse::Int32; n_cells::Int32; n_bands::Int32; n_surfaces::Int32
+    coarse_nv::Ptr{Int32}; coarse_vx::Ptr{Float64}; coarse_vy::Ptr{Float64}; coarse_solid::Ptr{UInt8}
+    fine_off::Ptr{Int32}
+    cell_nv::Ptr{Int32}; cell_vx::Ptr{Float64}; cell_vy::Ptr{Float64}; cell_mid::Ptr{Float64}
+    cell_volume::Ptr{Float64}; cell_surf_id::Ptr{Int32}
+    kappa::Ptr{Float64}; sigma_s::Ptr{Float64}; epsilon::Ptr{Float64}; uniform_beta::Ptr{Float64}
+end
+
+struct RthxTraceArgs
+    rays_per_emitter::Int64; ray_id_offset::Int64; seed::UInt64; nudge::Float64
+    n_bins::Int32; bins::Ptr{Int32}
+    mode::Int32; locator::Int32
+    emitter_rank::Int32; emitter_world::Int32
+    n_rec_ids::Int32; rec_ids::Ptr{Int32}; rec_bin::Int32
+    block_threads::Int32; row_chunks::Int32
+end
+
+mutable struct RthxRecOut
+    capacity::Int64; origins::Ptr{Float64}; endpoints::Ptr{Float64}; n_recorded::Int64
+end
+
+mutable struct RthxStats
+    rays_traced::Int64; rays_lost::Int64; kernel_ms::Float64; total_ms::Float64
+    n_blocks::Int32; block_threads::Int32; row_chunks::Int32; smem_bytes::Int32; hist_in_smem::Int32; n_launches::Int32
+    RthxStats() = new(0, 0, 0.0, 0.0, 0, 0, 0, 0, 0, 0)
+end
+
+bandvalue(x::AbstractVector, b) = x[b]
+bandvalue(x::Number, b) = x
+
+# ---- flatten RayTracingDomain2D (DomainStructs.jl:89-130) into the SoA of rthx_mesh; indices become 0-based -------
+function flatten(rtm::RayTracingDomain2D)
+    nc = length(rtm.coarse_mesh); nb = rtm.n_spectral_bins
+    ncell = length(rtm.volume_mapping); ns = length(rtm.surface_mapping)
+    coarse_nv = zeros(Int32, nc); coarse_vx = zeros(4, nc); coarse_vy = zeros(4, nc); coarse_solid = zeros(UInt8, 4, nc)
+    fine_off = zeros(Int32, nc + 1)
+    cell_nv = zeros(Int32, ncell); cell_vx = zeros(4, ncell); cell_vy = zeros(4, ncell); cell_mid = zeros(2, ncell)
+    cell_volume = zeros(ncell); cell_surf_id = fill(Int32(-1), 4, ncell)
+    kappa = zeros(ncell, nb); sigma_s = zeros(ncell, nb); epsilon = zeros(max(ns, 1), nb)
+    g = 0
+    for (c, face) in enumerate(rtm.coarse_mesh)
+        coarse_nv[c] = length(face.vertices)
+        for (i, v) in enumerate(face.vertices)
+            coarse_vx[i, c] = v[1]; coarse_vy[i, c] = v[2]; coarse_solid[i, c] = face.solidWalls[i]
+        end
+        fine_off[c] = g
+        for (f, cell) in enumerate(rtm.fine_mesh[c])
+            g += 1
+            cell_nv[g] = length(cell.vertices)
+            for (i, v) in enumerate(cell.vertices)
+                cell_vx[i, g] = v[1]; cell_vy[i, g] = v[2]
+            end
+            cell_mid[1, g] = cell.midPoint[1]; cell_mid[2, g] = cell.midPoint[2]
+            cell_volume[g] = cell.volume
+            for w in 1:length(cell.vertices)
+                s = get(rtm.surface_mapping, (c, f, w), 0)
+                if s > 0
+                    cell_surf_id[w, g] = s - 1
+                    for b in 1:nb
+                        epsilon[s, b] = bandvalue(cell.epsilon[w], b)
+                    end
+                end
+            end
+            for b in 1:nb
+                kappa[g, b] = bandvalue(cell.kappa_g, b); sigma_s[g, b] = bandvalue(cell.sigma_s_g, b)
+            end
+        end
+    end
+    fine_off[nc + 1] = g
+    ub = Float64.(rtm.uniform_across_bin)
+    arrays = (coarse_nv, coarse_vx, coarse_vy, coarse_solid, fine_off, cell_nv, cell_vx, cell_vy, cell_mid,
+              cell_volume, cell_surf_id, kappa, sigma_s, epsilon, ub)
+    mesh = RthxMesh(nc, ncell, nb, ns, map(pointer, arrays)...)
+    return mesh, arrays      # keep `arrays` alive (GC.@preserve) while `mesh` is in use
+end
+
+check(rc, h) = rc == 0 || error("rthx: " * unsafe_string(ccall((:rthx_last_error, LIB), Cstring, (Ptr{Cvoid},), h)))
+
+"""
+    trace_bins(rtm, rays_per_emitter, nudge, bins, rec) -> Vector{SparseMatrixCSC{Float64,Int}}
+
+Batched replacement of `computeExchangeFactorsBin` (parallelRayTracing.jl:64-159): all `bins` in one launch.
+"""
+function trace_bins(rtm::RayTracingDomain2D, rays_per_emitter::Integer, nudge::Float64, bins::Vector{Int}, rec)
+    mesh, arrays = flatten(rtm)
+    N = Int(mesh.n_surfaces + mesh.n_cells)
+    nbins = length(bins)
+    counts = Array{UInt64}(undef, N, N, nbins)           # [j, i, b]: column-major view of the C [b][i][j] layout
+    lost = Array{UInt64}(undef, N, nbins)
+    bins0 = Int32.(bins .- 1)
+    rec_ids = rec === nothing ? Int32[] : Int32.(rec.ids .- 1)
+    cap = length(rec_ids) * rays_per_emitter
+    origins = zeros(2, max(cap, 1)); endpoints = zeros(2, max(cap, 1))
+    recout = RthxRecOut(cap, pointer(origins), pointer(endpoints), 0)
+    stats = RthxStats()
+    handles = Ptr{Cvoid}[]
+    GC.@preserve arrays counts lost bins0 rec_ids origins endpoints begin
+        for d in DEVICES[]
+            h = Ref{Ptr{Cvoid}}(C_NULL)
+            check(ccall((:rthx_create, LIB), Cint, (Ref{Ptr{Cvoid}}, Ref{RthxMesh}, Cint), h, mesh, d), C_NULL)
+            push!(handles, h[])
+        end
+        args = RthxTraceArgs(rays_per_emitter, 0, SEED[], nudge, nbins, pointer(bins0), 0, 0, 0, 1,
+                             length(rec_ids), isempty(rec_ids) ? C_NULL : pointer(rec_ids),
+                             rec === nothing ? 0 : rec.bin - 1, 0, 0)
+        rc = ccall((:rthx_trace_exchange_multi, LIB), Cint,
+                   (Ptr{Ptr{Cvoid}}, Cint, Ref{RthxTraceArgs}, Ptr{UInt64}, Ptr{UInt64}, Ref{RthxRecOut}, Ref{RthxStats}),
+                   handles, length(handles), args, counts, lost, recout, stats)
+        check(rc, handles[1])
+        foreach(h -> ccall((:rthx_destroy, LIB), Cint, (Ptr{Cvoid},), h), handles)
+    end
+    SEED[] += 0x9E3779B97F4A7C15                          # a fresh stream for the next call, like unseeded rand()
+    if rec !== nothing
+        for k in 1:recout.n_recorded                      # parallelRayTracing.jl:120-123; any slot works for collect_rays
+            push!(rec.origins[1], Point2{Float64}(origins[1, k], origins[2, k]))
+            push!(rec.endpoints[1], Point2{Float64}(endpoints[1, k], endpoints[2, k]))
+        end
+    end
+    Fs = Vector{SparseMatrixCSC{Float64,Int}}(undef, nbins)
+    for b in 1:nbins
+        I = Int[]; J = Int[]; V = Float64[]
+        maxloss = 0
+        for i in 1:N
+            rowsum = sum(@view counts[:, i, b])
+            maxloss = max(maxloss, rays_per_emitter - Int(rowsum))
+            rowsum == 0 && continue
+            for j in 1:N
+                c = counts[j, i, b]
+                c == 0 && continue
+                push!(I, i); push!(J, j); push!(V, c / rowsum)   # (c/R) / Σ(c/R): :144-146 + row_normalize! :161-169
+            end
+        end
+        println("Maximum ray tracing ray loss per emitter: $maxloss/$rays_per_emitter")   # unconditional, :163
+        Fs[b] = sparse(I, J, V, N, N)
+    end
+    return Fs
+end
+
+# ---- method replacement: same signature and return value as parallelRayTracing.jl:1-62 ---------------------------
+function RayTraceHeatTransfer.parallelRayTracing(rtm::RayTracingDomain2D, rays_total::P, nudge::G, verbose::Bool;
+                                                 rec=nothing) where {P<:Integer, G}
+    num_emitters = length(rtm.surface_mapping) + length(rtm.volume_mapping)
+    rays_per_emitter = div(rays_total, num_emitters)
+    n_bins = rtm.n_spectral_bins
+    if rtm.spectral_mode == :spectral_variable
+        verbose && println("Computing $n_bins separate F matrices for variable spectral extinction")
+        groups, reps, nonuniform = group_uniform_bins(rtm.uniform_across_bin)
+        to_trace = vcat(nonuniform, [first(g) for g in groups])
+        Fs = trace_bins(rtm, rays_per_emitter, Float64(nudge), to_trace, rec)
+        F_raw_vector = Vector{AbstractMatrix}(undef, n_bins)
+        for (k, bin) in enumerate(nonuniform)
+            F_raw_vector[bin] = Fs[k]
+        end
+        for (k, g) in enumerate(groups), j in g
+            F_raw_vector[j] = Fs[length(nonuniform) + k]        # grouped bins alias one matrix (:38-41)
+        end
+        return F_raw_vector, rays_per_emitter
+    end
+    verbose && println(rtm.spectral_mode != :grey ?
+                       "Computing single F matrix for uniform spectral extinction ($n_bins bins)" :
+                       "Computing single F matrix for grey extinction")
+    return trace_bins(rtm, rays_per_emitter, Float64(nudge), [1], rec)[1], rays_per_emitter
+end
+
+end # module

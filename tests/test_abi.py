@@ -1,0 +1,80 @@
+"""The C-ABI library: builds, loads, exports every symbol of include/rthx.h, struct layouts agree with the header,
+and — with no GPU — fails loudly instead of falling back."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_header_symbols_all_exported(cuda_lib, rthx_mod):
+    from rthx._abi import EXPORTED_SYMBOLS
+    header = open(os.path.join(ROOT, "include", "rthx.h")).read()
+    declared = set(re.findall(r"\b(rthx_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(EXPORTED_SYMBOLS)
+    for name in declared:
+        assert getattr(cuda_lib, name) is not None
+    assert cuda_lib.rthx_version() == 1
+
+
+def test_struct_layouts_match_header(rthx_mod):
+    from rthx import _abi
+    src = r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "rthx.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu\n", sizeof(rthx_mesh), sizeof(rthx_trace_args), sizeof(rthx_rec_out), sizeof(rthx_stats), sizeof(rthx_info));
+  printf("%zu %zu %zu %zu\n", offsetof(rthx_trace_args, nudge), offsetof(rthx_trace_args, bins), offsetof(rthx_trace_args, rec_ids), offsetof(rthx_trace_args, row_chunks));
+  printf("%zu %zu\n", offsetof(rthx_mesh, uniform_beta), offsetof(rthx_stats, n_launches));
+  return 0;
+}'''
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "t.c"), "w").write(src)
+        subprocess.run(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "t.c"), "-o", os.path.join(d, "t")], check=True)
+        out = subprocess.run([os.path.join(d, "t")], check=True, capture_output=True, text=True).stdout.split()
+    got = [int(x) for x in out]
+    A = _abi.rthx_trace_args
+    want = [C.sizeof(_abi.rthx_mesh), C.sizeof(A), C.sizeof(_abi.rthx_rec_out), C.sizeof(_abi.rthx_stats), C.sizeof(_abi.rthx_info),
+            A.nudge.offset, A.bins.offset, A.rec_ids.offset, A.row_chunks.offset,
+            _abi.rthx_mesh.uniform_beta.offset, _abi.rthx_stats.n_launches.offset]
+    assert got == want
+
+
+def test_no_gpu_fails_loudly(cuda_lib, rthx_mod):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    flat = rthx_mod.flatten_domain(rthx_mod.meshes.square_domain(3))
+    with pytest.raises(rthx_mod.RthxError, match="no CUDA device|CPU fallback"):
+        rthx_mod.DeviceTracer(flat, device=0)
+    rtm = rthx_mod.meshes.square_domain(3)
+    with pytest.raises(rthx_mod.RthxError):
+        rtm(1000, method="exchange", verbose=False)               # the public call has no CPU fallback either
+
+
+def test_bad_mesh_rejected_before_touching_the_device(cuda_lib, rthx_mod):
+    from rthx._abi import rthx_mesh
+    h = C.c_void_p()
+    rc = cuda_lib.rthx_create(C.byref(h), C.byref(rthx_mesh()), 0)
+    assert rc == 1 and b"NULL or empty" in cuda_lib.rthx_last_error(None)
+    assert cuda_lib.rthx_create(None, None, 0) == 1
+
+
+def test_product_path_does_not_touch_the_oracle():
+    """The oracle is test infrastructure: nothing under the package may import or link it."""
+    pkg = os.path.join(ROOT, "raytraceheattransfer.jl_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h", ".cuh")):
+                txt = open(os.path.join(dp, f), errors="ignore").read()
+                assert "oracle" not in txt.replace("the CPU oracle", "").replace("CPU oracle", ""), f"{f} mentions the oracle"
+    so = os.path.join(pkg, "csrc", "librthx.so")
+    if os.path.exists(so):
+        out = subprocess.run(["ldd", so], capture_output=True, text=True).stdout
+        assert "oracle" not in out
