@@ -94,7 +94,13 @@ typedef struct rthx_mesh {
  *
  * RNG contract (the reference is unseeded; this is new): Philox4x32-10, key = seed,
  * counter = (ray_id lo, ray_id hi, emitter element index, (band << 8) | call#), ray_id in
- * [ray_id_offset, ray_id_offset + rays_per_emitter).  Results are a pure function of
+ * [ray_id_offset, ray_id_offset + rays_per_emitter); two calls per ray, words w0..w3 (call 0), w4..w7 (call 1).
+ *   surface emitter: w0 position (32-bit uniform), w1 cos(theta) and w2 psi (23-bit Float32 uniforms, as
+ *                    lambertSample2D.jl:2,5 quantises them), (w4,w5) free path (52-bit);
+ *   volume emitter : w0 R_1, w1 R_2, w2 triangle selector (quads only), w3 phi (32-bit), (w4,w5) theta (52-bit),
+ *                    (w6,w7) free path / optical depth (52-bit).
+ *   uniforms: (w + 0.5) 2^-32, ((w >> 9) + 0.5) 2^-23, ((hi:lo >> 12) + 0.5) 2^-52 — all in the open interval (0,1).
+ * Results are a pure function of
  * (mesh, seed, ray_id range, nudge): independent of thread-block shape, chunking and GPU count.
  */
 typedef struct rthx_trace_args {

@@ -68,11 +68,12 @@ double rthx_oracle_u52(uint32_t lo, uint32_t hi) {
   return ((double)(x >> 12) + 0.5) * 0x1p-52;
 }
 float rthx_oracle_u23(uint32_t w) { return ((float)(w >> 9) + 0.5f) * 0x1p-23f; }
+double rthx_oracle_u32(uint32_t w) { return ((double)w + 0.5) * 0x1p-32; }
 
 typedef struct {
   uint32_t key[2];
   uint32_t ctr[4];
-  uint32_t w[12];
+  uint32_t w[8];
 } draws_t;
 
 static void draws_init(draws_t* d, uint64_t seed, uint64_t ray_id, uint32_t emitter, uint32_t band, int ncalls) {
@@ -318,21 +319,21 @@ static int omesh_build(omesh_t* o, const rthx_mesh* m) {
 /* ------------------------------------------------------------------------------------------------ */
 typedef struct { double px, py, dx, dy; } ray_t;
 
-/* emitSurfaceRay2D.jl:1-27 + lambertSample2D.jl:1-11.  draws: w0,w1 position; w2 cos-theta (Float32);
- * w3 psi (Float32).  The free-path draw is w4,w5. */
+/* emitSurfaceRay2D.jl:1-27 + lambertSample2D.jl:1-11.  draws (rthx.h contract): w0 position (32-bit);
+ * w1 cos-theta (Float32); w2 psi (Float32).  The free-path draw is (w4,w5), 52-bit. */
 static ray_t emit_surface(const poly_t* face, int wall, double nudge, const draws_t* d) {
   const int j = (wall + 1) % face->n;
   const double p1x = face->vx[wall], p1y = face->vy[wall], p2x = face->vx[j], p2y = face->vy[j];
-  const double R = rthx_oracle_u52(d->w[0], d->w[1]);
+  const double R = rthx_oracle_u32(d->w[0]);
   double px = p1x + (p2x - p1x) * R, py = p1y + (p2y - p1y) * R;
   px = px + (face->midx - px) * nudge;
   py = py + (face->midy - py) * nudge;
   /* lambertSample2D: Float32 variates, Float32 sqrt and square, the rest in Float64 */
-  const float R_angle1 = rthx_oracle_u23(d->w[2]);
+  const float R_angle1 = rthx_oracle_u23(d->w[1]);
   const float cosTheta = sqrtf(R_angle1);
   const float cos2 = cosTheta * cosTheta;
   const double sinTheta = sqrt(1.0 - (double)cos2);
-  const double psi = (2.0 * M_PI) * (double)rthx_oracle_u23(d->w[3]);
+  const double psi = (2.0 * M_PI) * (double)rthx_oracle_u23(d->w[2]);
   const double xdir = sinTheta * cos(psi);
   const double zdir = (double)cosTheta;
   const double ex = p2x - p1x, ey = p2y - p1y;
@@ -346,16 +347,16 @@ static ray_t emit_surface(const poly_t* face, int wall, double nudge, const draw
   return r;
 }
 
-/* emitVolumeRay2D.jl:1-33.  draws: (w0,w1) R_1, (w2,w3) R_2, (w4,w5) triangle selector (quads only; the slot is
- * skipped for triangles), (w6,w7) theta, (w8,w9) phi.  The free-path draw is (w10,w11). */
+/* emitVolumeRay2D.jl:1-33.  draws (rthx.h contract): w0 R_1, w1 R_2, w2 triangle selector (quads only; the slot is
+ * skipped for triangles), w3 phi — 32-bit each; (w4,w5) theta, 52-bit.  The free-path draw is (w6,w7), 52-bit. */
 static ray_t emit_volume(const poly_t* face, double nudge, const draws_t* d) {
-  const double R_1 = rthx_oracle_u52(d->w[0], d->w[1]), R_2 = rthx_oracle_u52(d->w[2], d->w[3]);
+  const double R_1 = rthx_oracle_u32(d->w[0]), R_2 = rthx_oracle_u32(d->w[1]);
   const double sqrt_R1 = sqrt(R_1);
   double px, py;
   const double Ax = face->vx[0], Ay = face->vy[0], Bx = face->vx[1], By = face->vy[1], Cx = face->vx[2], Cy = face->vy[2];
   if (face->n == 4) {
     const double Dx = face->vx[3], Dy = face->vy[3];
-    const double sel = rthx_oracle_u52(d->w[4], d->w[5]);
+    const double sel = rthx_oracle_u32(d->w[2]);
     if (sel < 0.5 * (Ax * (By - Cy) + Bx * (Cy - Ay) + Cx * (Ay - By)) / face->volume) {
       px = (1 - sqrt_R1) * Ax + sqrt_R1 * (1 - R_2) * Bx + sqrt_R1 * R_2 * Cx;
       py = (1 - sqrt_R1) * Ay + sqrt_R1 * (1 - R_2) * By + sqrt_R1 * R_2 * Cy;
@@ -369,8 +370,8 @@ static ray_t emit_volume(const poly_t* face, double nudge, const draws_t* d) {
   }
   px = px + (face->midx - px) * nudge;
   py = py + (face->midy - py) * nudge;
-  const double theta = acos(1 - 2 * rthx_oracle_u52(d->w[6], d->w[7]));
-  const double phi = (2.0 * M_PI) * rthx_oracle_u52(d->w[8], d->w[9]);
+  const double theta = acos(1 - 2 * rthx_oracle_u52(d->w[4], d->w[5]));
+  const double phi = (2.0 * M_PI) * rthx_oracle_u32(d->w[3]);
   ray_t r;
   r.px = px; r.py = py;
   r.dx = sin(theta) * cos(phi);
@@ -473,9 +474,9 @@ static int shoot(const omesh_t* o, const double* beta_all, const rthx_trace_args
     r = emit_surface(cell, o->em_wall[e], a->nudge, &d);
     R_S = rthx_oracle_u52(d.w[4], d.w[5]);
   } else {
-    draws_init(&d, a->seed, ray_id, (uint32_t)e, (uint32_t)band, 3);
+    draws_init(&d, a->seed, ray_id, (uint32_t)e, (uint32_t)band, 2);
     r = emit_volume(cell, a->nudge, &d);
-    R_S = rthx_oracle_u52(d.w[10], d.w[11]);
+    R_S = rthx_oracle_u52(d.w[6], d.w[7]);
   }
   const double* beta_band = beta_all + (size_t)band * m->n_cells;
   hit_t h;
@@ -607,7 +608,7 @@ int rthx_oracle_emit(const rthx_mesh* m, const rthx_trace_args* a, int emitter, 
   for (int64_t i = 0; i < n; ++i) {
     draws_t d;
     ray_t r;
-    draws_init(&d, a->seed, (uint64_t)(a->ray_id_offset + i), (uint32_t)emitter, (uint32_t)band, 3);
+    draws_init(&d, a->seed, (uint64_t)(a->ray_id_offset + i), (uint32_t)emitter, (uint32_t)band, 2);
     r = emitter < o.ns ? emit_surface(cell, o.em_wall[emitter], a->nudge, &d) : emit_volume(cell, a->nudge, &d);
     out[4 * i] = r.px; out[4 * i + 1] = r.py; out[4 * i + 2] = r.dx; out[4 * i + 3] = r.dy;
   }

@@ -22,6 +22,7 @@ double rthx_oracle_dist_to_surface(int n, const double* vx, const double* vy, do
 void rthx_oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 double rthx_oracle_u52(uint32_t lo, uint32_t hi);
 float rthx_oracle_u23(uint32_t w);
+double rthx_oracle_u32(uint32_t w);
 
 #ifdef __cplusplus
 }

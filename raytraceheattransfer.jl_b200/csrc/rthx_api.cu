@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -24,6 +25,7 @@ struct rthx_handle {
   cudaDeviceProp prop{};
   int n_coarse = 0, n_cells = 0, n_bands = 0, ns = 0, N = 0, n_affine = 0;
   bool coarse_fits_smem = false;
+  bool fast_ok = false;        // every coarse face affine + complete neighbour table + descriptors fit in smem
   std::vector<void*> allocs;   // mesh allocations
   TraceParams base{};          // mesh pointers filled once
   // per-call scratch, grown on demand
@@ -364,6 +366,10 @@ extern "C" int rthx_create(rthx_handle** out, const rthx_mesh* m, int device_id)
 #undef UP
   P.n_coarse = nc; P.n_cells = ncell; P.n_surfaces = ns; P.N = N;
   h->coarse_fits_smem = sizeof(CoarseDev) * (size_t)nc <= 32 * 1024;
+  h->fast_ok = h->coarse_fits_smem && h->n_affine == nc;
+  for (int c = 0; c < nc && h->fast_ok; ++c)
+    for (int k = 0; k < coarse[c].nv; ++k)
+      if (!coarse[c].solid[k] && coarse[c].nbr[k] < 0) h->fast_ok = false;   // open / T-junction edge: needs the generic search
   if ((ce = cudaMalloc(&h->rec_slot_dev, sizeof(int32_t) * (size_t)N)) != cudaSuccess) return bail(RTHX_ERR_CUDA, cudaGetErrorString(ce));
   if ((ce = configure_trace_kernel(h->prop.sharedMemPerBlockOptin)) != cudaSuccess) return bail(RTHX_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce));
   *out = h;
@@ -383,7 +389,7 @@ extern "C" int rthx_get_info(const rthx_handle* h, rthx_info* info) {
 // ---------------------------------------------------------------------------------------------------------------
 namespace {
 
-struct LaunchPlan { int n_owned, n_blocks, block_threads, row_chunks, hist_in_smem; size_t smem_bytes; };
+struct LaunchPlan { int n_owned, n_blocks, block_threads, row_chunks, hist_in_smem, fast, minb; size_t smem_bytes; };
 
 int check_args(rthx_handle* h, const rthx_trace_args* a) {
   if (!a) return fail(h, RTHX_ERR_ARG, "trace: args is NULL");
@@ -403,6 +409,9 @@ LaunchPlan make_plan(const rthx_handle* h, const rthx_trace_args* a, int rank, i
   pl.n_owned = (h->N - rank + world - 1) / world;
   if (pl.n_owned < 0) pl.n_owned = 0;
   pl.block_threads = a->block_threads ? a->block_threads : 256;
+  pl.fast = (h->fast_ok && a->locator != RTHX_LOCATOR_GENERIC) ? 1 : 0;
+  pl.minb = 4;
+  if (const char* ev = std::getenv("RTHX_MINB")) { const int v = std::atoi(ev); if (v >= 2 && v <= 4) pl.minb = v; }   // tuning knob
   const size_t coarse_bytes = h->coarse_fits_smem ? sizeof(CoarseDev) * (size_t)h->n_coarse : 0;
   const size_t hist_bytes = sizeof(uint32_t) * (size_t)h->N;
   pl.hist_in_smem = (coarse_bytes + hist_bytes <= h->prop.sharedMemPerBlockOptin) ? 1 : 0;
@@ -411,7 +420,7 @@ LaunchPlan make_plan(const rthx_handle* h, const rthx_trace_args* a, int rank, i
   long long chunks = a->row_chunks;
   if (chunks <= 0) {
     // enough blocks for ~32 waves of the resident set, but keep >= 2048 rays (and >= N/2, the flush scan) per block
-    const int per_sm = std::max(1, trace_kernel_max_blocks_per_sm(pl.block_threads, pl.smem_bytes));
+    const int per_sm = std::max(1, trace_kernel_max_blocks_per_sm(pl.block_threads, pl.smem_bytes, pl.hist_in_smem != 0, pl.fast != 0, pl.minb));
     const long long target = (long long)h->prop.multiProcessorCount * per_sm * 32;
     chunks = rows > 0 ? (target + rows - 1) / rows : 1;
     const long long min_rays = std::max<long long>(2048, h->N / 2);
@@ -444,6 +453,7 @@ void fill_params(const rthx_handle* h, const rthx_trace_args* a, const LaunchPla
   P.seed = a->seed;
   P.nudge = a->nudge;
   P.rec_slot = nullptr; P.rec_pts = nullptr; P.rec_valid = nullptr;
+  P.k_u52 = 1.0 - 0x1p-53; P.k_u32 = 1.0 - 0x1p-33; P.k_eps = 1e-10;
 }
 
 template <class T>
@@ -480,7 +490,7 @@ int enqueue_trace(rthx_handle* h, const rthx_trace_args* a, int rank, int world,
   TraceParams P;
   fill_params(h, a, pl, rank, world, compact, counts, lost, P);
   if (with_rec && n_rec_slots > 0) { P.rec_slot = h->rec_slot_dev; P.rec_pts = h->rec_pts_dev; P.rec_valid = h->rec_valid_dev; }
-  CU(h, launch_trace_exchange(P, pl.n_blocks, pl.block_threads, pl.smem_bytes, stream));
+  CU(h, launch_trace_exchange(P, pl.n_blocks, pl.block_threads, pl.smem_bytes, pl.fast != 0, pl.minb, stream));
   if (pl.n_blocks > 0) *n_launches += 1;
   *plan_out = pl;
   return RTHX_OK;

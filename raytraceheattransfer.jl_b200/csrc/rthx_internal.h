@@ -79,13 +79,17 @@ struct TraceParams {
   int64_t ray_id_offset;
   uint64_t seed;
   double nudge;
+  // constants kept in the parameter bank so FP64 instructions can take them as c[0][..] operands
+  double k_u52;   // 1 - 2^-53
+  double k_u32;   // 1 - 2^-33
+  double k_eps;   // 1e-10, the near-parallel threshold of distToSurface2D.jl:10
 };
 
 // launchers implemented in rthx_kernels.cu
-cudaError_t launch_trace_exchange(const TraceParams& p, int n_blocks, int block_threads, size_t smem_bytes,
+cudaError_t launch_trace_exchange(const TraceParams& p, int n_blocks, int block_threads, size_t smem_bytes, bool fast, int minb,
                                   cudaStream_t stream);
 cudaError_t configure_trace_kernel(size_t smem_bytes);
 cudaError_t launch_fp64_peak(double* out, int n_blocks, int block_threads, int iters, cudaStream_t stream);
-int trace_kernel_max_blocks_per_sm(int block_threads, size_t smem_bytes);
+int trace_kernel_max_blocks_per_sm(int block_threads, size_t smem_bytes, bool hist, bool fast, int minb);
 
 }  // namespace rthx

@@ -30,12 +30,17 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
   return c;
 }
 
-// ((x >> 12) + 0.5) * 2^-52 with x = hi:lo, built by mantissa injection: [1,2) - (1 - 2^-53), exact.
-__device__ __forceinline__ double u52(uint32_t lo, uint32_t hi) {
-  const double d = __hiloint2double((int)(0x3FF00000u | (hi >> 12)), (int)((hi << 20) | (lo >> 12)));
-  return d - 0.99999999999999988897769753748;  // 1 - 2^-53
+// Uniforms by mantissa injection.  The subtrahends live in the kernel parameter bank (p.k_*), so each conversion is
+// two integer ops + one DADD with a constant-bank operand instead of a 64-bit immediate materialised by two UMOVs.
+//   u52: ((x >> 12) + 0.5) * 2^-52, x = hi:lo   = [1,2) - (1 - 2^-53), exact
+//   u32: (w + 0.5) * 2^-32                      = [1,2) - (1 - 2^-33), exact
+//   u23: ((w >> 9) + 0.5) * 2^-23 (Float32)     = [1,2) - (1 - 2^-24), exact
+__device__ __forceinline__ double u52(uint32_t lo, uint32_t hi, double k_u52) {
+  return __hiloint2double((int)(0x3FF00000u | (hi >> 12)), (int)((hi << 20) | (lo >> 12))) - k_u52;
 }
-// ((w >> 9) + 0.5) * 2^-23, exact.
+__device__ __forceinline__ double u32d(uint32_t w, double k_u32) {
+  return __hiloint2double((int)(0x3FF00000u | (w >> 12)), (int)(w << 20)) - k_u32;
+}
 __device__ __forceinline__ float u23(uint32_t w) {
   return __uint_as_float(0x3F800000u | (w >> 9)) - 0.999999940395355224609375f;  // 1 - 2^-24
 }
@@ -44,27 +49,25 @@ __device__ __forceinline__ float u23(uint32_t w) {
 // geometry primitives
 // ------------------------------------------------------------------------------------------------------------
 // distToSurface2D.jl:2-18 on a coarse face: smallest positive u_i = ((v_i - p)·n_i)/(d·n_i) over edges with
-// |d·n_i| >= 1e-10, first index on ties.  The argmin is found on cross-multiplied fractions (one division
-// instead of nv); ties/rounding differ from the reference only on a set of measure ~1e-16.
-__device__ __forceinline__ double dist_to_coarse(const CoarseDev& f, double px, double py, double dx, double dy, int& k) {
-  double bn = 0.0, bd = 0.0;  // best numerator / denominator (bd > 0 when a candidate exists)
+// |d·n_i| >= 1e-10, first index on ties.  Branch-free: the argmin runs on cross-multiplied fractions (one division
+// instead of nv; u_i > 0 <=> num_i*den_i > 0), and the unused 4th edge of a triangle has a zero normal, so it can
+// never pass the |den| test.  Ties/rounding differ from the reference only on a set of measure ~1e-16.
+__device__ __forceinline__ double dist_to_coarse(const CoarseDev& f, double px, double py, double dx, double dy, double eps, int& k) {
+  double bn = 1.0, bd = 0.0;  // best |num| / |den|; bd == 0 <=> no candidate yet (any candidate beats it)
   int bk = 0;
-  bool have = false;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    if (i < f.nv) {
-      const double den = dx * f.nx[i] + dy * f.ny[i];
-      const double num = (f.vx[i] - px) * f.nx[i] + (f.vy[i] - py) * f.ny[i];
-      // u = num/den > 0  <=>  num and den have the same sign (and num != 0)
-      const bool ok = (fabs(den) >= 1e-10) && ((num > 0.0 && den > 0.0) || (num < 0.0 && den < 0.0));
-      if (ok) {
-        const double an = fabs(num), ad = fabs(den);
-        if (!have || an * bd < bn * ad) { bn = an; bd = ad; bk = i; have = true; }
-      }
-    }
+    const double nx = f.nx[i], ny = f.ny[i];
+    const double den = dx * nx + dy * ny;
+    const double num = (f.vx[i] - px) * nx + (f.vy[i] - py) * ny;
+    const double an = fabs(num), ad = fabs(den);
+    const bool better = (ad >= eps) & (num * den > 0.0) & (an * bd < bn * ad);
+    bn = better ? an : bn;
+    bd = better ? ad : bd;
+    bk = better ? i : bk;
   }
   k = bk;
-  return have ? bn / bd : CUDART_INF;
+  return bd > 0.0 ? bn / bd : CUDART_INF;
 }
 
 // Faithful distToSurface2D on an arbitrary polygon of the generic tables (used by the generic locator for the
@@ -118,20 +121,29 @@ __device__ __noinline__ int find_face_generic(const TraceParams& p, int set, dou
   return -1;
 }
 
-// Fine-cell location inside coarse face c: returns the local fine index or -1.
-__device__ __forceinline__ int locate_fine(const TraceParams& p, const CoarseDev& cf, int c, int kind, double px, double py) {
-  if (kind == KIND_GENERIC) return find_face_generic(p, 1 + c, px, py);
+// Fine-cell location by the analytic lattice inverse: returns the local fine index or -1.
+__device__ __forceinline__ int locate_affine(const TraceParams& p, const CoarseDev& cf, double px, double py) {
   const double rx = px - cf.ax, ry = py - cf.ay;
   const double s = rx * cf.g1x + ry * cf.g1y, t = rx * cf.g2x + ry * cf.g2y;
-  if (!(s >= 0.0 && t >= 0.0 && s < (double)cf.Nx && t < (double)cf.Ny)) return -1;
-  const int n = __double2int_rd(s), m = __double2int_rd(t);
+  const int n = __double2int_rd(s), m = __double2int_rd(t);   // NaN -> 0, caught by the range test on s,t below
+  if (!((s >= 0.0) & (t >= 0.0) & (n < cf.Nx) & (m < cf.Ny))) return -1;
   const int cell = n + m * cf.Nx;
-  if (kind == KIND_AFFINE_QUAD) return cell;
+  if (cf.kind == KIND_AFFINE_QUAD) return cell;
   return __ldg(p.lattice + cf.lat_off + cell);
+}
+
+template <bool FAST>
+__device__ __forceinline__ int locate_fine(const TraceParams& p, const CoarseDev& cf, int c, int kind, double px, double py) {
+  if (!FAST && kind == KIND_GENERIC) return find_face_generic(p, 1 + c, px, py);
+  return locate_affine(p, cf, px, py);
 }
 
 // ------------------------------------------------------------------------------------------------------------
 // K1: fused emit + trace + tally (+ record)
+//   HIST_SMEM: per-block shared-memory row histogram (else direct global atomics, N > ~57 k elements)
+//   FAST     : every coarse face is a verified affine lattice with a complete neighbour table and the coarse
+//              descriptors fit in shared memory -> no generic locator code in the kernel at all
+//   MINB     : minimum resident blocks per SM the register allocation is bounded for
 // ------------------------------------------------------------------------------------------------------------
 struct EmitterRegs {
   // surface: p1, edge e = p2 - p1, local frame xl (unit edge), yl (left normal)
@@ -142,11 +154,12 @@ struct EmitterRegs {
   int nv;
 };
 
-template <bool HIST_SMEM>
-__global__ void __launch_bounds__(256) trace_exchange_kernel(const __grid_constant__ TraceParams p) {
+template <bool HIST_SMEM, bool FAST, int MINB>
+__global__ void __launch_bounds__(256, MINB) trace_exchange_kernel(const __grid_constant__ TraceParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   CoarseDev* s_coarse = reinterpret_cast<CoarseDev*>(smem_raw);
-  const size_t coarse_bytes = p.coarse_in_smem ? sizeof(CoarseDev) * (size_t)p.n_coarse : 0;
+  const bool coarse_smem = FAST || p.coarse_in_smem;
+  const size_t coarse_bytes = coarse_smem ? sizeof(CoarseDev) * (size_t)p.n_coarse : 0;
   uint32_t* hist = reinterpret_cast<uint32_t*>(smem_raw + coarse_bytes);
 
   // block -> (owned emitter ordinal y, traced bin bi, ray chunk)
@@ -160,7 +173,7 @@ __global__ void __launch_bounds__(256) trace_exchange_kernel(const __grid_consta
   const int N = p.N;
 
   // stage coarse faces, clear the row histogram
-  if (p.coarse_in_smem) {
+  if (coarse_smem) {
     const int nw = (int)(coarse_bytes / 8);
     const double* src = reinterpret_cast<const double*>(p.coarse);
     double* dst = reinterpret_cast<double*>(s_coarse);
@@ -168,7 +181,8 @@ __global__ void __launch_bounds__(256) trace_exchange_kernel(const __grid_consta
   }
   if (HIST_SMEM)
     for (int i = threadIdx.x; i < N; i += blockDim.x) hist[i] = 0u;
-  const CoarseDev* coarse = p.coarse_in_smem ? s_coarse : p.coarse;
+  // FAST: a plain shared-memory pointer (LDS); otherwise a generic pointer that may be shared or global
+  const CoarseDev* coarse = FAST ? s_coarse : (p.coarse_in_smem ? s_coarse : p.coarse);
 
   // ray range of this chunk
   const int64_t per = (p.rays_per_emitter + p.row_chunks - 1) / p.row_chunks;
@@ -207,6 +221,7 @@ __global__ void __launch_bounds__(256) trace_exchange_kernel(const __grid_consta
   const bool uniform = ub > -0.1;                      // traceRay.jl:4
   const double* beta_band = p.beta + (size_t)band * p.n_cells;
   const double beta_u = beta_band[0];                  // traceRay.jl:6-11: beta of fine_mesh[1][1]
+  const double inv_beta_u = beta_u > 0.0 ? 1.0 / beta_u : CUDART_INF;
   const double nudge = p.nudge;
   const int rec_slot = (p.rec_slot != nullptr && band == p.rec_bin) ? p.rec_slot[e] : -1;
   const size_t row = p.compact_rows ? ((size_t)bi * p.n_owned + y) : ((size_t)bi * N + e);
@@ -215,38 +230,36 @@ __global__ void __launch_bounds__(256) trace_exchange_kernel(const __grid_consta
   __syncthreads();
 
   const uint2 key = make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32));
+  const uint32_t cw = ((uint32_t)band << 8);
   unsigned int n_lost = 0;
 
   for (int64_t r = r_begin + threadIdx.x; r < r_end; r += blockDim.x) {
     const uint64_t ray_id = (uint64_t)(p.ray_id_offset + r);
     const uint32_t c_lo = (uint32_t)ray_id, c_hi = (uint32_t)(ray_id >> 32);
-    const uint32_t cw = ((uint32_t)band << 8);
+    // two Philox calls per ray: w0 (call 0) feeds the emission point/azimuth, w1 (call 1) the 52-bit draws
+    const uint4 w0 = philox4x32_10(make_uint4(c_lo, c_hi, (uint32_t)e, cw | 0u), key);
+    const uint4 w1 = philox4x32_10(make_uint4(c_lo, c_hi, (uint32_t)e, cw | 1u), key);
     double px, py, dx, dy, R_S;
     // ---- stage 1: emission --------------------------------------------------------------------------------
     if (is_surface) {
-      const uint4 w0 = philox4x32_10(make_uint4(c_lo, c_hi, (uint32_t)e, cw | 0u), key);
-      const uint4 w1 = philox4x32_10(make_uint4(c_lo, c_hi, (uint32_t)e, cw | 1u), key);
-      const double R = u52(w0.x, w0.y);
+      const double R = u32d(w0.x, p.k_u32);
       px = em.ax + em.bx * R;
       py = em.ay + em.by * R;
       px = px + (em.midx - px) * nudge;
       py = py + (em.midy - py) * nudge;
       // lambertSample2D: Float32 variates / sqrt / square, the rest in Float64
-      const float cosT = __fsqrt_rn(u23(w0.z));
+      const float cosT = __fsqrt_rn(u23(w0.y));
       const float cos2 = __fmul_rn(cosT, cosT);
       const double sinT = sqrt(1.0 - (double)cos2);
-      const double xdir = sinT * cospi(2.0 * (double)u23(w0.w));   // cos(2*pi*R)
+      const double xdir = sinT * cospi(2.0 * (double)u23(w0.z));   // cos(2*pi*R)
       const double zdir = (double)cosT;
       dx = em.cx * xdir + em.dx * zdir;
       dy = em.cy * xdir + em.dy * zdir;
-      R_S = u52(w1.x, w1.y);
+      R_S = u52(w1.x, w1.y, p.k_u52);
     } else {
-      const uint4 w0 = philox4x32_10(make_uint4(c_lo, c_hi, (uint32_t)e, cw | 0u), key);
-      const uint4 w1 = philox4x32_10(make_uint4(c_lo, c_hi, (uint32_t)e, cw | 1u), key);
-      const uint4 w2 = philox4x32_10(make_uint4(c_lo, c_hi, (uint32_t)e, cw | 2u), key);
-      const double R1 = u52(w0.x, w0.y), R2 = u52(w0.z, w0.w);
+      const double R1 = u32d(w0.x, p.k_u32), R2 = u32d(w0.y, p.k_u32);
       const double sq = sqrt(R1);
-      const bool first = (em.nv == 3) || (u52(w1.x, w1.y) < em.frac_abc);
+      const bool first = (em.nv == 3) || (u32d(w0.z, p.k_u32) < em.frac_abc);
       // (1-sqrt R1) V0 + sqrt R1 (1-R2) V1 + sqrt R1 R2 V2 with (V0,V1,V2) = (A,B,C) or (C,D,A)
       const double v0x = first ? em.ax : em.cx, v0y = first ? em.ay : em.cy;
       const double v1x = first ? em.bx : em.dx, v1y = first ? em.by : em.dy;
@@ -257,32 +270,32 @@ __global__ void __launch_bounds__(256) trace_exchange_kernel(const __grid_consta
       px = px + (em.midx - px) * nudge;
       py = py + (em.midy - py) * nudge;
       // theta = acos(1-2R): cos(theta) = 1-2R, sin(theta) = 2 sqrt(R(1-R)) (algebraically identical)
-      const double Rt = u52(w1.z, w1.w);
+      const double Rt = u52(w1.x, w1.y, p.k_u52);
       const double cosT = 1.0 - 2.0 * Rt;
       const double sinT = 2.0 * sqrt(Rt * (1.0 - Rt));
-      dx = sinT * cospi(2.0 * u52(w2.x, w2.y));
+      dx = sinT * cospi(2.0 * u32d(w0.w, p.k_u32));
       dy = cosT;
-      R_S = u52(w2.z, w2.w);
+      R_S = u52(w1.z, w1.w, p.k_u52);
     }
     const double ox = px, oy = py;
 
     // ---- stage 2: first-interaction traversal (traceRayUniform / traceRayVariable) --------------------------
     const double neg_log = -log(R_S);
-    double S = uniform ? (beta_u > 0.0 ? neg_log / beta_u : CUDART_INF) : 0.0;  // remaining free path (uniform)
-    double acc = 0.0;                                                          // accumulated tau (variable)
+    double S = uniform ? neg_log * inv_beta_u : 0.0;   // remaining free path (uniform); beta = 0 -> Inf
+    double acc = 0.0;                                  // accumulated tau (variable)
     int c = c0;
     int absorber = -1;
     for (int it = 0; it < 10000; ++it) {
       const CoarseDev& cf = coarse[c];
-      const int kind = p.force_generic ? KIND_GENERIC : cf.kind;
+      const int kind = FAST ? cf.kind : (p.force_generic ? KIND_GENERIC : cf.kind);
       int k;
-      const double u = dist_to_coarse(cf, px, py, dx, dy, k);
+      const double u = dist_to_coarse(cf, px, py, dx, dy, p.k_eps, k);
       bool gas;
       double tau_b = 0.0;
       if (uniform) {
         gas = S < u;
       } else {
-        const int f0 = locate_fine(p, cf, c, kind, px, py);      // traceRay.jl:87-100
+        const int f0 = locate_fine<FAST>(p, cf, c, kind, px, py);   // traceRay.jl:87-100
         if (f0 < 0) break;
         const double local_beta = beta_band[cf.fine_off + f0];
         tau_b = local_beta * u;
@@ -292,7 +305,7 @@ __global__ void __launch_bounds__(256) trace_exchange_kernel(const __grid_consta
       if (gas) {
         px = px + (S - nudge) * dx;
         py = py + (S - nudge) * dy;
-        const int f = locate_fine(p, cf, c, kind, px, py);
+        const int f = locate_fine<FAST>(p, cf, c, kind, px, py);
         if (f >= 0) absorber = p.n_surfaces + cf.fine_off + f;
         break;
       } else if (!(u < CUDART_INF)) {
@@ -300,14 +313,16 @@ __global__ void __launch_bounds__(256) trace_exchange_kernel(const __grid_consta
       } else if (cf.solid[k]) {
         px = px + (u - nudge) * dx;
         py = py + (u - nudge) * dy;
-        const int f = locate_fine(p, cf, c, kind, px, py);
+        const int f = locate_fine<FAST>(p, cf, c, kind, px, py);
         if (f < 0) break;
         const int gc = cf.fine_off + f;
         int w;
-        if (kind == KIND_GENERIC) {
+        if (!FAST && kind == KIND_GENERIC) {
           w = wall_of_poly(p, gc, px, py, dx, dy);              // traceRay.jl:51
-        } else if (kind == KIND_AFFINE_QUAD || p.poly_nv[gc] == 3) {
+        } else if (kind == KIND_AFFINE_QUAD) {
           w = k;                                                // fine wall lying on coarse edge k
+        } else if (__ldg(p.poly_nv + gc) == 3) {
+          w = k;                                                // diagonal triangle cell: walls follow the coarse edges
         } else {
           if (k == cf.diag) break;
           w = (k < cf.diag) ? k : k + 1;                        // quad cell of a mirrored-triangle lattice
@@ -318,8 +333,13 @@ __global__ void __launch_bounds__(256) trace_exchange_kernel(const __grid_consta
         px = px + (u + nudge) * dx;
         py = py + (u + nudge) * dy;
         if (uniform) S -= u; else acc += tau_b;
-        int nc = (kind == KIND_GENERIC) ? -1 : cf.nbr[k];
-        if (nc < 0) nc = find_face_generic(p, 0, px, py);       // traceRay.jl:59-65
+        int nc;
+        if (FAST) {
+          nc = cf.nbr[k];
+        } else {
+          nc = (kind == KIND_GENERIC) ? -1 : cf.nbr[k];
+          if (nc < 0) nc = find_face_generic(p, 0, px, py);     // traceRay.jl:59-65
+        }
         if (nc < 0) break;
         c = nc;
       }
@@ -352,23 +372,40 @@ __global__ void __launch_bounds__(256) trace_exchange_kernel(const __grid_consta
   }
 }
 
-cudaError_t configure_trace_kernel(size_t smem_bytes) {
-  cudaError_t e = cudaFuncSetAttribute(trace_exchange_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(trace_exchange_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+// kernel variants: [hist_in_smem][fast][minb - 2]
+typedef void (*TraceKernel)(const TraceParams);
+static TraceKernel kernel_variant(bool hist, bool fast, int minb) {
+  if (!hist) return fast ? (TraceKernel)trace_exchange_kernel<false, true, 2> : (TraceKernel)trace_exchange_kernel<false, false, 2>;
+  if (!fast) return (TraceKernel)trace_exchange_kernel<true, false, 2>;
+  switch (minb) {
+    case 3: return (TraceKernel)trace_exchange_kernel<true, true, 3>;
+    case 4: return (TraceKernel)trace_exchange_kernel<true, true, 4>;
+    default: return (TraceKernel)trace_exchange_kernel<true, true, 2>;
+  }
 }
 
-int trace_kernel_max_blocks_per_sm(int block_threads, size_t smem_bytes) {
+cudaError_t configure_trace_kernel(size_t smem_bytes) {
+  for (int hist = 0; hist < 2; ++hist)
+    for (int fast = 0; fast < 2; ++fast)
+      for (int minb = 2; minb <= 4; ++minb) {
+        cudaError_t e = cudaFuncSetAttribute((const void*)kernel_variant(hist, fast, minb), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        if (e != cudaSuccess) return e;
+      }
+  return cudaSuccess;
+}
+
+int trace_kernel_max_blocks_per_sm(int block_threads, size_t smem_bytes, bool hist, bool fast, int minb) {
   int n = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, trace_exchange_kernel<true>, block_threads, smem_bytes) != cudaSuccess) return 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, (const void*)kernel_variant(hist, fast, minb), block_threads, smem_bytes) != cudaSuccess) return 0;
   return n;
 }
 
-cudaError_t launch_trace_exchange(const TraceParams& p, int n_blocks, int block_threads, size_t smem_bytes, cudaStream_t stream) {
+cudaError_t launch_trace_exchange(const TraceParams& p, int n_blocks, int block_threads, size_t smem_bytes, bool fast, int minb,
+                                  cudaStream_t stream) {
   if (n_blocks <= 0) return cudaSuccess;
-  if (p.hist_in_smem) trace_exchange_kernel<true><<<n_blocks, block_threads, smem_bytes, stream>>>(p);
-  else trace_exchange_kernel<false><<<n_blocks, block_threads, smem_bytes, stream>>>(p);
-  return cudaGetLastError();
+  TraceKernel k = kernel_variant(p.hist_in_smem != 0, fast, minb);
+  void* args[] = {(void*)&p};
+  return cudaLaunchKernel((const void*)k, dim3(n_blocks), dim3(block_threads), args, smem_bytes, stream);
 }
 
 // ------------------------------------------------------------------------------------------------------------
