@@ -274,11 +274,14 @@ def main():
             "coarse_nv", "coarse_vx", "coarse_vy", "coarse_solid", "fine_off", "cell_nv", "cell_vx", "cell_vy", "cell_mid",
             "cell_volume", "cell_surf_id", "kappa", "sigma_s", "epsilon", "uniform_beta"))
 
+        e2e_dev_ms = []
+
         def e2e_step(seed):
             if world == 1:
                 tr = rthx.DeviceTracer(flat, device=local_rank)       # mesh flattening output -> device (H2D)
                 out = tr.trace(rpe, counts_out=counts_host.numpy().view(np.uint64), seed=seed, **kw)
                 tr.close()
+                e2e_dev_ms.append((out["stats"]["kernel_ms"], out["stats"]["total_ms"]))
                 return int(out["lost"].sum())
             tr = rthx.DeviceTracer(flat, device=local_rank)
             tr.trace_device(rpe, sh.counts.data_ptr(), sh.lost.data_ptr(), stream=stream.cuda_stream, zero_first=True,
@@ -306,6 +309,8 @@ def main():
                "h2d_bytes_per_step": int(mesh_bytes + 4 * nb),
                "d2h_bytes_per_step": int(8 * nb * N * N + 8 * nb * N),
                "ms_per_step": dt / args.steps * 1e3,
+               "device_ms_per_step": {"kernel": float(np.mean([a for a, _ in e2e_dev_ms[1:]])),
+                                      "zero+kernel+d2h": float(np.mean([b for _, b in e2e_dev_ms[1:]]))} if e2e_dev_ms else None,
                "path": "rthx_create + rthx_trace_exchange (pinned host count matrix)" if world == 1 else
                        "rthx_create + rthx_trace_exchange_device + NCCL reduce + D2H on rank 0"}
 

@@ -26,7 +26,8 @@ struct rthx_handle {
   int n_coarse = 0, n_cells = 0, n_bands = 0, ns = 0, N = 0, n_affine = 0;
   bool coarse_fits_smem = false;
   bool fast_ok = false;        // every coarse face affine + complete neighbour table + descriptors fit in smem
-  std::vector<void*> allocs;   // mesh allocations
+  std::vector<void*> allocs;   // mesh arena
+  size_t mesh_bytes = 0;
   TraceParams base{};          // mesh pointers filled once
   // per-call scratch, grown on demand
   unsigned long long* counts_dev = nullptr; size_t counts_cap = 0;
@@ -52,17 +53,19 @@ static int fail(rthx_handle* h, int code, const std::string& msg) {
       return fail(h, RTHX_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));             \
   } while (0)
 
-template <class T>
-static cudaError_t upload(rthx_handle* h, const std::vector<T>& v, const T** out) {
-  void* d = nullptr;
-  const size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
-  cudaError_t e = cudaMalloc(&d, bytes);
-  if (e != cudaSuccess) return e;
-  h->allocs.push_back(d);
-  if (!v.empty()) e = cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
-  *out = static_cast<const T*>(d);
-  return e;
-}
+// All mesh tables live in ONE device allocation filled by ONE host-to-device copy: with peer access enabled (NCCL
+// processes) every cudaMalloc / cudaFree maps or unmaps the range on the peers and costs milliseconds.
+struct Arena {
+  std::vector<unsigned char> host;
+  template <class T>
+  size_t add(const std::vector<T>& v, size_t min_elems = 1) {
+    const size_t off = (host.size() + 255) & ~size_t(255);
+    const size_t n = std::max(v.size(), min_elems);
+    host.resize(off + n * sizeof(T), 0);
+    if (!v.empty()) std::memcpy(host.data() + off, v.data(), v.size() * sizeof(T));
+    return off;
+  }
+};
 
 // ---------------------------------------------------------------------------------------------------------------
 // host-side mesh preparation
@@ -234,7 +237,7 @@ extern "C" int rthx_destroy(rthx_handle* h) {
   if (!h) return RTHX_OK;
   cudaSetDevice(h->device);
   for (void* d : h->allocs) cudaFree(d);
-  cudaFree(h->counts_dev); cudaFree(h->lost_dev); cudaFree(h->bins_dev); cudaFree(h->rec_slot_dev);
+  cudaFree(h->counts_dev); cudaFree(h->lost_dev);
   cudaFree(h->rec_pts_dev); cudaFree(h->rec_valid_dev); cudaFree(h->peak_dev);
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -323,6 +326,11 @@ extern "C" int rthx_create(rthx_handle** out, const rthx_mesh* m, int device_id)
     for (int i = 0; i < cp.n; ++i) d.solid[i] = m->coarse_solid[4 * c + i] ? 1 : 0;
     d.nv = cp.n; d.fine_off = f0; d.kind = KIND_GENERIC; d.lat_off = -1; d.diag = -1; d.Nx = d.Ny = 0;
     if (detect_affine(cp, &polys[f0], nf, d, lattice)) h->n_affine++;
+    for (int i = 0; i < cp.n; ++i) d.h[i] = cp.vx[i] * cp.nx[i] + cp.vy[i] * cp.ny[i];
+    if (d.kind == KIND_AFFINE_QUAD) {   // slab form: opposite edges measured along the normals of edges 0 and 1
+      d.h[2] = cp.vx[2] * cp.nx[0] + cp.vy[2] * cp.ny[0];
+      d.h[3] = cp.vx[3] * cp.nx[1] + cp.vy[3] * cp.ny[1];
+    }
   }
   // neighbour table: the unique coarse face sharing the (reversed) edge; T-junctions stay -1 (generic search)
   for (int c = 0; c < nc; ++c) {
@@ -358,19 +366,35 @@ extern "C" int rthx_create(rthx_handle** out, const rthx_mesh* m, int device_id)
 
   TraceParams& P = h->base;
   std::memset(&P, 0, sizeof(P));
-#define UP(vec, field) if ((ce = upload(h, vec, &P.field)) != cudaSuccess) return bail(RTHX_ERR_CUDA, std::string("upload " #field ": ") + cudaGetErrorString(ce));
-  UP(coarse, coarse) UP(sets, sets) UP(bstart, bucket_start) UP(bitems, bucket_items) UP(poly_nv, poly_nv)
-  UP(pvx, poly_vx) UP(pvy, poly_vy) UP(pnx, poly_nx) UP(pny, poly_ny) UP(mid, cell_mid) UP(vol, cell_volume)
-  UP(surf, cell_surf_id) UP(beta, beta) UP(ub, uniform_beta) UP(lattice, lattice) UP(em_cell, em_cell)
-  UP(em_wall, em_wall) UP(em_coarse, em_coarse)
-#undef UP
+  Arena A;
+  const size_t o_coarse = A.add(coarse), o_sets = A.add(sets), o_bstart = A.add(bstart), o_bitems = A.add(bitems),
+               o_nv = A.add(poly_nv), o_pvx = A.add(pvx), o_pvy = A.add(pvy), o_pnx = A.add(pnx), o_pny = A.add(pny),
+               o_mid = A.add(mid), o_vol = A.add(vol), o_surf = A.add(surf), o_beta = A.add(beta), o_ub = A.add(ub),
+               o_lat = A.add(lattice), o_ec = A.add(em_cell), o_ew = A.add(em_wall), o_eco = A.add(em_coarse),
+               o_bins = A.add(std::vector<int32_t>(), (size_t)nb * 4 + 16), o_rec = A.add(std::vector<int32_t>(), (size_t)N);
+  void* base = nullptr;
+  if ((ce = cudaMalloc(&base, A.host.size())) != cudaSuccess) return bail(RTHX_ERR_CUDA, std::string("cudaMalloc(mesh arena): ") + cudaGetErrorString(ce));
+  h->allocs.push_back(base);
+  if ((ce = cudaMemcpy(base, A.host.data(), A.host.size(), cudaMemcpyHostToDevice)) != cudaSuccess)
+    return bail(RTHX_ERR_CUDA, std::string("cudaMemcpy(mesh arena): ") + cudaGetErrorString(ce));
+  h->mesh_bytes = A.host.size();
+  unsigned char* b8 = static_cast<unsigned char*>(base);
+  P.coarse = (const CoarseDev*)(b8 + o_coarse); P.sets = (const FaceSetDev*)(b8 + o_sets);
+  P.bucket_start = (const int32_t*)(b8 + o_bstart); P.bucket_items = (const int32_t*)(b8 + o_bitems);
+  P.poly_nv = (const int32_t*)(b8 + o_nv); P.poly_vx = (const double*)(b8 + o_pvx); P.poly_vy = (const double*)(b8 + o_pvy);
+  P.poly_nx = (const double*)(b8 + o_pnx); P.poly_ny = (const double*)(b8 + o_pny);
+  P.cell_mid = (const double*)(b8 + o_mid); P.cell_volume = (const double*)(b8 + o_vol);
+  P.cell_surf_id = (const int32_t*)(b8 + o_surf); P.beta = (const double*)(b8 + o_beta); P.uniform_beta = (const double*)(b8 + o_ub);
+  P.lattice = (const int32_t*)(b8 + o_lat); P.em_cell = (const int32_t*)(b8 + o_ec); P.em_wall = (const int32_t*)(b8 + o_ew);
+  P.em_coarse = (const int32_t*)(b8 + o_eco);
+  h->bins_dev = (int32_t*)(b8 + o_bins); h->bins_cap = (size_t)nb * 4 + 16;
+  h->rec_slot_dev = (int32_t*)(b8 + o_rec);
   P.n_coarse = nc; P.n_cells = ncell; P.n_surfaces = ns; P.N = N;
   h->coarse_fits_smem = sizeof(CoarseDev) * (size_t)nc <= 32 * 1024;
   h->fast_ok = h->coarse_fits_smem && h->n_affine == nc;
   for (int c = 0; c < nc && h->fast_ok; ++c)
     for (int k = 0; k < coarse[c].nv; ++k)
       if (!coarse[c].solid[k] && coarse[c].nbr[k] < 0) h->fast_ok = false;   // open / T-junction edge: needs the generic search
-  if ((ce = cudaMalloc(&h->rec_slot_dev, sizeof(int32_t) * (size_t)N)) != cudaSuccess) return bail(RTHX_ERR_CUDA, cudaGetErrorString(ce));
   if ((ce = configure_trace_kernel(h->prop.sharedMemPerBlockOptin)) != cudaSuccess) return bail(RTHX_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce));
   *out = h;
   return RTHX_OK;
@@ -413,9 +437,9 @@ LaunchPlan make_plan(const rthx_handle* h, const rthx_trace_args* a, int rank, i
   pl.minb = 4;
   if (const char* ev = std::getenv("RTHX_MINB")) { const int v = std::atoi(ev); if (v >= 2 && v <= 4) pl.minb = v; }   // tuning knob
   const size_t coarse_bytes = h->coarse_fits_smem ? sizeof(CoarseDev) * (size_t)h->n_coarse : 0;
-  const size_t hist_bytes = sizeof(uint32_t) * (size_t)h->N;
-  pl.hist_in_smem = (coarse_bytes + hist_bytes <= h->prop.sharedMemPerBlockOptin) ? 1 : 0;
-  pl.smem_bytes = coarse_bytes + (pl.hist_in_smem ? hist_bytes : 0);
+  const size_t hist_bytes = sizeof(uint32_t) * (size_t)h->N, em_bytes = sizeof(double) * 16;
+  pl.hist_in_smem = (coarse_bytes + em_bytes + hist_bytes <= h->prop.sharedMemPerBlockOptin) ? 1 : 0;
+  pl.smem_bytes = coarse_bytes + em_bytes + (pl.hist_in_smem ? hist_bytes : 0);
   const long long rows = (long long)pl.n_owned * a->n_bins;
   long long chunks = a->row_chunks;
   if (chunks <= 0) {
@@ -441,7 +465,7 @@ void fill_params(const rthx_handle* h, const rthx_trace_args* a, const LaunchPla
   P.bins = h->bins_dev;
   P.counts = counts; P.lost = lost;
   P.n_bins = a->n_bins;
-  P.emitter_rank = rank; P.emitter_world = world; P.n_owned = pl.n_owned;
+  P.emitter_rank = rank; P.emitter_world = world; P.n_owned = pl.n_owned; P.y_offset = 0;
   P.compact_rows = compact ? 1 : 0;
   P.row_chunks = pl.row_chunks;
   P.coarse_in_smem = h->coarse_fits_smem ? 1 : 0;
@@ -454,6 +478,8 @@ void fill_params(const rthx_handle* h, const rthx_trace_args* a, const LaunchPla
   P.nudge = a->nudge;
   P.rec_slot = nullptr; P.rec_pts = nullptr; P.rec_valid = nullptr;
   P.k_u52 = 1.0 - 0x1p-53; P.k_u32 = 1.0 - 0x1p-33; P.k_eps = 1e-10;
+  uint32_t k0 = (uint32_t)a->seed, k1 = (uint32_t)(a->seed >> 32);
+  for (int r = 0; r < 10; ++r) { P.rk[2 * r] = k0; P.rk[2 * r + 1] = k1; k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
 }
 
 template <class T>
@@ -479,7 +505,7 @@ int enqueue_trace(rthx_handle* h, const rthx_trace_args* a, int rank, int world,
                   unsigned long long* lost, bool zero_first, bool with_rec, int n_rec_slots, cudaStream_t stream,
                   LaunchPlan* plan_out, int* n_launches) {
   LaunchPlan pl = make_plan(h, a, rank, world);
-  CU(h, ensure(&h->bins_dev, &h->bins_cap, (size_t)a->n_bins));
+  if ((size_t)a->n_bins > h->bins_cap) return fail(h, RTHX_ERR_ARG, "trace: too many bins in one call");
   CU(h, cudaMemcpyAsync(h->bins_dev, a->bins, sizeof(int32_t) * (size_t)a->n_bins, cudaMemcpyHostToDevice, stream));
   const size_t rows = compact ? (size_t)pl.n_owned : (size_t)h->N;
   if (zero_first) {

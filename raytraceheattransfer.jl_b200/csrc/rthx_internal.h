@@ -13,6 +13,7 @@ enum : int { KIND_GENERIC = 0, KIND_AFFINE_QUAD = 1, KIND_AFFINE_TRI = 2 };
 struct CoarseDev {
   double vx[4], vy[4];   // CCW vertices
   double nx[4], ny[4];   // unit outward edge normals (the reference's `inwardNormals`, calculateInwardNormal.jl:1-12)
+  double h[4];           // plane offsets: quads h0 = v0·n0, h1 = v1·n1, h2 = v2·n0, h3 = v3·n1 (slab form); else h_i = v_i·n_i
   // affine lattice inverse (kinds 1,2): s = (p-a)·g1, t = (p-a)·g2, lattice cell (floor s, floor t) in [0,Nx)x[0,Ny)
   double ax, ay, g1x, g1y, g2x, g2y;
   int32_t nv;
@@ -69,6 +70,7 @@ struct TraceParams {
   int32_t n_coarse, n_cells, n_surfaces, N;
   int32_t n_bins;
   int32_t emitter_rank, emitter_world, n_owned;
+  int32_t y_offset;            // first owned-emitter ordinal of this launch (row batches for copy/compute overlap)
   int32_t compact_rows;        // 1: counts row index is the owned-emitter ordinal, 0: the element index
   int32_t row_chunks;
   int32_t coarse_in_smem;
@@ -83,6 +85,7 @@ struct TraceParams {
   double k_u52;   // 1 - 2^-53
   double k_u32;   // 1 - 2^-33
   double k_eps;   // 1e-10, the near-parallel threshold of distToSurface2D.jl:10
+  uint32_t rk[20];  // Philox round keys (key + r*W), two per round
 };
 
 // launchers implemented in rthx_kernels.cu

@@ -30,6 +30,18 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
   return c;
 }
 
+// Same generator with the 10 round keys precomputed on the host (TraceParams::rk, parameter bank): the key schedule
+// disappears from the instruction stream and the LOP3s take the keys as c[0][..] operands.
+__device__ __forceinline__ uint4 philox4x32_10_rk(uint4 c, const uint32_t* __restrict__ rk) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ rk[2 * r], lo1, hi0 ^ c.w ^ rk[2 * r + 1], lo0);
+  }
+  return c;
+}
+
 // Uniforms by mantissa injection.  The subtrahends live in the kernel parameter bank (p.k_*), so each conversion is
 // two integer ops + one DADD with a constant-bank operand instead of a 64-bit immediate materialised by two UMOVs.
 //   u52: ((x >> 12) + 0.5) * 2^-52, x = hi:lo   = [1,2) - (1 - 2^-53), exact
@@ -64,6 +76,93 @@ __device__ __forceinline__ double dist_to_coarse(const CoarseDev& f, double px, 
     const bool better = (ad >= eps) & (num * den > 0.0) & (an * bd < bn * ad);
     bn = better ? an : bn;
     bd = better ? ad : bd;
+    bk = better ? i : bk;
+  }
+  k = bk;
+  return bd > 0.0 ? bn / bd : CUDART_INF;
+}
+
+// ---- FAST-path math -------------------------------------------------------------------------------------------
+// Coefficients live in __constant__ memory so DFMA takes them as constant-bank operands (a 64-bit immediate costs
+// two UMOVs per use in SASS; libdevice's log/cospi spend ~40 issue slots per ray on those alone).
+__constant__ double c_sinpi[9] = {  // sin(pi z) = z * P(z^2), |z| <= 1/2, max abs error 2.2e-16 (Chebyshev fit, mpmath)
+    0x1.921fb54442d18p+1, -0x1.4abbce625be52p+2, 0x1.466bc6775aa7dp+1, -0x1.32d2cce627c86p-1, 0x1.5078348551854p-4,
+    -0x1.e3074dfaf87afp-8, 0x1.e8f3675ee37ddp-12, -0x1.6f7acdb8f6580p-16, 0x1.9d462020fcc78p-21};
+__constant__ double c_log[9] = {    // fdlibm e_log.c: Lg1..Lg7, ln2_hi, ln2_lo
+    6.666666666666735130e-01, 3.999999999940941908e-01, 2.857142874366239149e-01, 2.222219843214978396e-01,
+    1.818357216161805012e-01, 1.531383769920937332e-01, 1.479819860511658591e-01,
+    6.93147180369123816490e-01, 1.90821492927058770002e-10};
+
+// cos(2 pi R) for R in (0,1): with x = 2R - 1 in (-1,1), cos(2 pi R) = -cos(pi x) = sin(pi (|x| - 1/2)); branch-free.
+__device__ __forceinline__ double cos2pi_unit(double R) {
+  const double z = fabs(fma(R, 2.0, -1.0)) - 0.5;
+  const double w = z * z;
+  double p = c_sinpi[8];
+#pragma unroll
+  for (int k = 7; k >= 0; --k) p = fma(p, w, c_sinpi[k]);
+  return z * p;
+}
+
+// -log(x) for a normal double x in (0,1) (the uniforms of the RNG contract are >= 2^-53): fdlibm's algorithm without
+// the subnormal / special-case branches; s = f/(2+f) by MUFU.RCP64H + two Newton steps.  Error < 2 ulp.
+__device__ __forceinline__ double neg_log_unit(double x) {
+  int hi = __double2hiint(x);
+  const int lo = __double2loint(x);
+  int e = (hi >> 20) - 1023;
+  hi = (hi & 0x000FFFFF) | 0x3FF00000;
+  const bool big = hi >= 0x3FF6A09F;        // m > sqrt(2): halve it
+  hi = big ? hi - 0x00100000 : hi;
+  e = big ? e + 1 : e;
+  const double m = __hiloint2double(hi, lo);
+  const double f = m - 1.0, d = m + 1.0;
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  r = fma(r, fma(-d, r, 1.0), r);
+  r = fma(r, fma(-d, r, 1.0), r);
+  double sq = f * r;
+  sq = fma(r, fma(-d, sq, f), sq);          // s = f/d, correctly rounded to ~1 ulp
+  const double z = sq * sq, w = z * z;
+  const double t1 = w * fma(w, fma(w, c_log[5], c_log[3]), c_log[1]);
+  const double t2 = z * fma(w, fma(w, fma(w, c_log[6], c_log[4]), c_log[2]), c_log[0]);
+  const double R = t2 + t1;
+  const double hfsq = 0.5 * f * f;
+  const double dk = (double)e;
+  // log(x) = dk*ln2_hi - ((hfsq - (s*(hfsq+R) + dk*ln2_lo)) - f)
+  return fma(-dk, c_log[7], (hfsq - fma(sq, hfsq + R, dk * c_log[8])) - f);
+}
+
+// distToSurface2D on a coarse face, FAST path.  The emission / crossing point is inside the face, so edge i can
+// only be hit when the ray moves outward through it (d·n_i >= 1e-10) with a positive plane distance h_i - p·n_i.
+//   quads (parallelograms): slab form — edges 0/2 share the normal n0, edges 1/3 the normal n1: two dot products per
+//                           axis instead of four per edge, and the sign of d·n picks the edge of each pair;
+//   triangles             : three edges.
+// The argmin runs on cross-multiplied fractions (first index on ties), one division at the end.
+__device__ __forceinline__ double dist_fast(const CoarseDev& f, double px, double py, double dx, double dy, double eps, int& k) {
+  if (f.kind == KIND_AFFINE_QUAD) {
+    const double n0x = f.nx[0], n0y = f.ny[0], n1x = f.nx[1], n1y = f.ny[1];
+    const double den0 = dx * n0x + dy * n0y, q0 = px * n0x + py * n0y;
+    const double den1 = dx * n1x + dy * n1y, q1 = px * n1x + py * n1y;
+    const bool p0 = den0 > 0.0, p1 = den1 > 0.0;
+    const double an0 = p0 ? f.h[0] - q0 : q0 - f.h[2], ad0 = fabs(den0);
+    const double an1 = p1 ? f.h[1] - q1 : q1 - f.h[3], ad1 = fabs(den1);
+    const int e0 = p0 ? 0 : 2, e1 = p1 ? 1 : 3;
+    const bool ok0 = (ad0 >= eps) & (an0 > 0.0), ok1 = (ad1 >= eps) & (an1 > 0.0);
+    const double l = an0 * ad1, r = an1 * ad0;
+    const bool take0 = ok0 & (!ok1 | (l < r) | ((l == r) & (e0 < e1)));
+    k = take0 ? e0 : e1;
+    const double an = take0 ? an0 : an1, ad = take0 ? ad0 : ad1;
+    return (ok0 | ok1) ? an / ad : CUDART_INF;
+  }
+  double bn = 1.0, bd = 0.0;
+  int bk = 0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const double nx = f.nx[i], ny = f.ny[i];
+    const double den = dx * nx + dy * ny;
+    const double num = f.h[i] - (px * nx + py * ny);
+    const bool better = (den >= eps) & (num > 0.0) & (num * bd < bn * den);
+    bn = better ? num : bn;
+    bd = better ? den : bd;
     bk = better ? i : bk;
   }
   k = bk;
@@ -145,14 +244,11 @@ __device__ __forceinline__ int locate_fine(const TraceParams& p, const CoarseDev
 //              descriptors fit in shared memory -> no generic locator code in the kernel at all
 //   MINB     : minimum resident blocks per SM the register allocation is bounded for
 // ------------------------------------------------------------------------------------------------------------
-struct EmitterRegs {
-  // surface: p1, edge e = p2 - p1, local frame xl (unit edge), yl (left normal)
-  // volume : triangle vertices A,B,C,(D) and ABC area fraction
-  double ax, ay, bx, by, cx, cy, dx, dy;
-  double midx, midy;
-  double frac_abc;
-  int nv;
-};
+// Block-uniform emitter description, kept in shared memory (broadcast LDS) instead of ~24 registers per thread.
+//   surface emitter: [0,1] p1, [2,3] edge p2-p1, [4,5] xVecLocal (unit edge), [6,7] yVecLocal (left normal)
+//   volume emitter : [0..5] triangle ABC as (V0, V1-V0, V2-V0), [6..11] triangle CDA likewise, [14] area(ABC)/volume
+//   both           : [12,13] cell midPoint
+constexpr int EM_DOUBLES = 16;
 
 template <bool HIST_SMEM, bool FAST, int MINB>
 __global__ void __launch_bounds__(256, MINB) trace_exchange_kernel(const __grid_constant__ TraceParams p) {
@@ -160,19 +256,20 @@ __global__ void __launch_bounds__(256, MINB) trace_exchange_kernel(const __grid_
   CoarseDev* s_coarse = reinterpret_cast<CoarseDev*>(smem_raw);
   const bool coarse_smem = FAST || p.coarse_in_smem;
   const size_t coarse_bytes = coarse_smem ? sizeof(CoarseDev) * (size_t)p.n_coarse : 0;
-  uint32_t* hist = reinterpret_cast<uint32_t*>(smem_raw + coarse_bytes);
+  double* s_em = reinterpret_cast<double*>(smem_raw + coarse_bytes);
+  uint32_t* hist = reinterpret_cast<uint32_t*>(smem_raw + coarse_bytes + sizeof(double) * EM_DOUBLES);
 
   // block -> (owned emitter ordinal y, traced bin bi, ray chunk)
   const unsigned bid = blockIdx.x;
   const int chunk = (int)(bid % (unsigned)p.row_chunks);
   const unsigned t1 = bid / (unsigned)p.row_chunks;
   const int bi = (int)(t1 % (unsigned)p.n_bins);
-  const int y = (int)(t1 / (unsigned)p.n_bins);
+  const int y = p.y_offset + (int)(t1 / (unsigned)p.n_bins);
   const int e = p.emitter_rank + y * p.emitter_world;
   const int band = p.bins[bi];
   const int N = p.N;
 
-  // stage coarse faces, clear the row histogram
+  // stage coarse faces and the emitter description, clear the row histogram
   if (coarse_smem) {
     const int nw = (int)(coarse_bytes / 8);
     const double* src = reinterpret_cast<const double*>(p.coarse);
@@ -184,52 +281,47 @@ __global__ void __launch_bounds__(256, MINB) trace_exchange_kernel(const __grid_
   // FAST: a plain shared-memory pointer (LDS); otherwise a generic pointer that may be shared or global
   const CoarseDev* coarse = FAST ? s_coarse : (p.coarse_in_smem ? s_coarse : p.coarse);
 
+  const int g = p.em_cell[e];
+  const int wall = p.em_wall[e];
+  const int c0 = p.em_coarse[e];
+  const bool is_surface = wall >= 0;
+  const int em_nv = p.poly_nv[g];
+  if (threadIdx.x == 0) {
+    const double* vx = p.poly_vx + 4 * g;
+    const double* vy = p.poly_vy + 4 * g;
+    if (is_surface) {
+      const int j = (wall + 1 == em_nv) ? 0 : wall + 1;
+      const double ex = vx[j] - vx[wall], ey = vy[j] - vy[wall];
+      const double len = sqrt(ex * ex + ey * ey);
+      s_em[0] = vx[wall]; s_em[1] = vy[wall]; s_em[2] = ex; s_em[3] = ey;
+      s_em[4] = ex / len; s_em[5] = ey / len;       // xVecLocal
+      s_em[6] = -(ey / len); s_em[7] = ex / len;    // yVecLocal
+    } else {
+      s_em[0] = vx[0]; s_em[1] = vy[0]; s_em[2] = vx[1] - vx[0]; s_em[3] = vy[1] - vy[0]; s_em[4] = vx[2] - vx[0]; s_em[5] = vy[2] - vy[0];
+      s_em[6] = vx[2]; s_em[7] = vy[2]; s_em[8] = vx[3] - vx[2]; s_em[9] = vy[3] - vy[2]; s_em[10] = vx[0] - vx[2]; s_em[11] = vy[0] - vy[2];
+      // emitVolumeRay2D.jl:7 — area(ABC)/volume; triangles always take the first (only) triangle
+      s_em[14] = em_nv == 3 ? 2.0 : 0.5 * (vx[0] * (vy[1] - vy[2]) + vx[1] * (vy[2] - vy[0]) + vx[2] * (vy[0] - vy[1])) / p.cell_volume[g];
+    }
+    s_em[12] = p.cell_mid[2 * g]; s_em[13] = p.cell_mid[2 * g + 1];
+  }
+
   // ray range of this chunk
   const int64_t per = (p.rays_per_emitter + p.row_chunks - 1) / p.row_chunks;
   const int64_t r_begin = (int64_t)chunk * per;
   int64_t r_end = r_begin + per;
   if (r_end > p.rays_per_emitter) r_end = p.rays_per_emitter;
 
-  // block-uniform emitter data (all threads read the same addresses: broadcast loads)
-  const int g = p.em_cell[e];
-  const int wall = p.em_wall[e];
-  const int c0 = p.em_coarse[e];
-  const bool is_surface = wall >= 0;
-  EmitterRegs em;
-  em.nv = p.poly_nv[g];
-  em.midx = p.cell_mid[2 * g];
-  em.midy = p.cell_mid[2 * g + 1];
-  if (is_surface) {
-    const int j = (wall + 1 == em.nv) ? 0 : wall + 1;
-    const double p1x = p.poly_vx[4 * g + wall], p1y = p.poly_vy[4 * g + wall];
-    const double p2x = p.poly_vx[4 * g + j], p2y = p.poly_vy[4 * g + j];
-    const double ex = p2x - p1x, ey = p2y - p1y;
-    const double len = sqrt(ex * ex + ey * ey);
-    em.ax = p1x; em.ay = p1y;          // p1
-    em.bx = ex;  em.by = ey;           // edge
-    em.cx = ex / len; em.cy = ey / len;  // xVecLocal
-    em.dx = -em.cy; em.dy = em.cx;     // yVecLocal
-    em.frac_abc = 0.0;
-  } else {
-    em.ax = p.poly_vx[4 * g + 0]; em.ay = p.poly_vy[4 * g + 0];
-    em.bx = p.poly_vx[4 * g + 1]; em.by = p.poly_vy[4 * g + 1];
-    em.cx = p.poly_vx[4 * g + 2]; em.cy = p.poly_vy[4 * g + 2];
-    em.dx = p.poly_vx[4 * g + 3]; em.dy = p.poly_vy[4 * g + 3];
-    em.frac_abc = 0.5 * (em.ax * (em.by - em.cy) + em.bx * (em.cy - em.ay) + em.cx * (em.ay - em.by)) / p.cell_volume[g];
-  }
   const double ub = p.uniform_beta[band];
   const bool uniform = ub > -0.1;                      // traceRay.jl:4
   const double* beta_band = p.beta + (size_t)band * p.n_cells;
   const double beta_u = beta_band[0];                  // traceRay.jl:6-11: beta of fine_mesh[1][1]
   const double inv_beta_u = beta_u > 0.0 ? 1.0 / beta_u : CUDART_INF;
-  const double nudge = p.nudge;
   const int rec_slot = (p.rec_slot != nullptr && band == p.rec_bin) ? p.rec_slot[e] : -1;
   const size_t row = p.compact_rows ? ((size_t)bi * p.n_owned + y) : ((size_t)bi * N + e);
   unsigned long long* count_row = p.counts + row * (size_t)N;
 
   __syncthreads();
 
-  const uint2 key = make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32));
   const uint32_t cw = ((uint32_t)band << 8);
   unsigned int n_lost = 0;
 
@@ -237,50 +329,48 @@ __global__ void __launch_bounds__(256, MINB) trace_exchange_kernel(const __grid_
     const uint64_t ray_id = (uint64_t)(p.ray_id_offset + r);
     const uint32_t c_lo = (uint32_t)ray_id, c_hi = (uint32_t)(ray_id >> 32);
     // two Philox calls per ray: w0 (call 0) feeds the emission point/azimuth, w1 (call 1) the 52-bit draws
-    const uint4 w0 = philox4x32_10(make_uint4(c_lo, c_hi, (uint32_t)e, cw | 0u), key);
-    const uint4 w1 = philox4x32_10(make_uint4(c_lo, c_hi, (uint32_t)e, cw | 1u), key);
+    const uint4 w0 = philox4x32_10_rk(make_uint4(c_lo, c_hi, (uint32_t)e, cw | 0u), p.rk);
+    const uint4 w1 = philox4x32_10_rk(make_uint4(c_lo, c_hi, (uint32_t)e, cw | 1u), p.rk);
     double px, py, dx, dy, R_S;
     // ---- stage 1: emission --------------------------------------------------------------------------------
     if (is_surface) {
       const double R = u32d(w0.x, p.k_u32);
-      px = em.ax + em.bx * R;
-      py = em.ay + em.by * R;
-      px = px + (em.midx - px) * nudge;
-      py = py + (em.midy - py) * nudge;
+      px = fma(s_em[2], R, s_em[0]);
+      py = fma(s_em[3], R, s_em[1]);
       // lambertSample2D: Float32 variates / sqrt / square, the rest in Float64
       const float cosT = __fsqrt_rn(u23(w0.y));
       const float cos2 = __fmul_rn(cosT, cosT);
       const double sinT = sqrt(1.0 - (double)cos2);
-      const double xdir = sinT * cospi(2.0 * (double)u23(w0.z));   // cos(2*pi*R)
+      const double xdir = sinT * (FAST ? cos2pi_unit((double)u23(w0.z)) : cospi(2.0 * (double)u23(w0.z)));
       const double zdir = (double)cosT;
-      dx = em.cx * xdir + em.dx * zdir;
-      dy = em.cy * xdir + em.dy * zdir;
+      dx = s_em[4] * xdir + s_em[6] * zdir;
+      dy = s_em[5] * xdir + s_em[7] * zdir;
       R_S = u52(w1.x, w1.y, p.k_u52);
     } else {
       const double R1 = u32d(w0.x, p.k_u32), R2 = u32d(w0.y, p.k_u32);
       const double sq = sqrt(R1);
-      const bool first = (em.nv == 3) || (u32d(w0.z, p.k_u32) < em.frac_abc);
-      // (1-sqrt R1) V0 + sqrt R1 (1-R2) V1 + sqrt R1 R2 V2 with (V0,V1,V2) = (A,B,C) or (C,D,A)
-      const double v0x = first ? em.ax : em.cx, v0y = first ? em.ay : em.cy;
-      const double v1x = first ? em.bx : em.dx, v1y = first ? em.by : em.dy;
-      const double v2x = first ? em.cx : em.ax, v2y = first ? em.cy : em.ay;
-      const double a0 = 1.0 - sq, a1 = sq * (1.0 - R2), a2 = sq * R2;
-      px = a0 * v0x + a1 * v1x + a2 * v2x;
-      py = a0 * v0y + a1 * v1y + a2 * v2y;
-      px = px + (em.midx - px) * nudge;
-      py = py + (em.midy - py) * nudge;
+      // uniform point of triangle (V0,V1,V2): V0 + sqrt(R1)(1-R2)(V1-V0) + sqrt(R1) R2 (V2-V0), emitVolumeRay2D.jl:9,12
+      const double* tri = s_em + ((u32d(w0.z, p.k_u32) < s_em[14]) ? 0 : 6);
+      const double a2 = sq * R2, a1 = sq - a2;
+      px = fma(a2, tri[4], fma(a1, tri[2], tri[0]));
+      py = fma(a2, tri[5], fma(a1, tri[3], tri[1]));
       // theta = acos(1-2R): cos(theta) = 1-2R, sin(theta) = 2 sqrt(R(1-R)) (algebraically identical)
       const double Rt = u52(w1.x, w1.y, p.k_u52);
-      const double cosT = 1.0 - 2.0 * Rt;
       const double sinT = 2.0 * sqrt(Rt * (1.0 - Rt));
-      dx = sinT * cospi(2.0 * u32d(w0.w, p.k_u32));
-      dy = cosT;
+      const double phiR = u32d(w0.w, p.k_u32);
+      dx = sinT * (FAST ? cos2pi_unit(phiR) : cospi(2.0 * phiR));
+      dy = fma(Rt, -2.0, 1.0);
       R_S = u52(w1.z, w1.w, p.k_u52);
     }
-    const double ox = px, oy = py;
+    px = fma(s_em[12] - px, p.nudge, px);   // nudge towards the cell midpoint (emitSurfaceRay2D.jl:10, emitVolumeRay2D.jl:22)
+    py = fma(s_em[13] - py, p.nudge, py);
+    if (rec_slot >= 0) {                    // RayRecorder origin (kept only if the ray is tallied: rec_valid below)
+      double* o = p.rec_pts + 4 * ((size_t)rec_slot * (size_t)p.rays_per_emitter + (size_t)r);
+      o[0] = px; o[1] = py;
+    }
 
     // ---- stage 2: first-interaction traversal (traceRayUniform / traceRayVariable) --------------------------
-    const double neg_log = -log(R_S);
+    const double neg_log = FAST ? neg_log_unit(R_S) : -log(R_S);
     double S = uniform ? neg_log * inv_beta_u : 0.0;   // remaining free path (uniform); beta = 0 -> Inf
     double acc = 0.0;                                  // accumulated tau (variable)
     int c = c0;
@@ -289,7 +379,7 @@ __global__ void __launch_bounds__(256, MINB) trace_exchange_kernel(const __grid_
       const CoarseDev& cf = coarse[c];
       const int kind = FAST ? cf.kind : (p.force_generic ? KIND_GENERIC : cf.kind);
       int k;
-      const double u = dist_to_coarse(cf, px, py, dx, dy, p.k_eps, k);
+      const double u = FAST ? dist_fast(cf, px, py, dx, dy, p.k_eps, k) : dist_to_coarse(cf, px, py, dx, dy, p.k_eps, k);
       bool gas;
       double tau_b = 0.0;
       if (uniform) {
@@ -303,16 +393,16 @@ __global__ void __launch_bounds__(256, MINB) trace_exchange_kernel(const __grid_
         if (gas) S = (neg_log - acc) / local_beta;
       }
       if (gas) {
-        px = px + (S - nudge) * dx;
-        py = py + (S - nudge) * dy;
+        px = fma(S - p.nudge, dx, px);
+        py = fma(S - p.nudge, dy, py);
         const int f = locate_fine<FAST>(p, cf, c, kind, px, py);
         if (f >= 0) absorber = p.n_surfaces + cf.fine_off + f;
         break;
       } else if (!(u < CUDART_INF)) {
         break;                                                  // no edge ahead: the reference ends in NaN -> lost
       } else if (cf.solid[k]) {
-        px = px + (u - nudge) * dx;
-        py = py + (u - nudge) * dy;
+        px = fma(u - p.nudge, dx, px);
+        py = fma(u - p.nudge, dy, py);
         const int f = locate_fine<FAST>(p, cf, c, kind, px, py);
         if (f < 0) break;
         const int gc = cf.fine_off + f;
@@ -330,8 +420,8 @@ __global__ void __launch_bounds__(256, MINB) trace_exchange_kernel(const __grid_
         absorber = __ldg(p.cell_surf_id + 4 * gc + w);          // -1: fine wall not solid -> lost
         break;
       } else {
-        px = px + (u + nudge) * dx;
-        py = py + (u + nudge) * dy;
+        px = fma(u + p.nudge, dx, px);
+        py = fma(u + p.nudge, dy, py);
         if (uniform) S -= u; else acc += tau_b;
         int nc;
         if (FAST) {
@@ -352,7 +442,7 @@ __global__ void __launch_bounds__(256, MINB) trace_exchange_kernel(const __grid_
       if (rec_slot >= 0) {
         const size_t s = (size_t)rec_slot * (size_t)p.rays_per_emitter + (size_t)r;
         double* o = p.rec_pts + 4 * s;
-        o[0] = ox; o[1] = oy; o[2] = px; o[3] = py;
+        o[2] = px; o[3] = py;
         p.rec_valid[s] = 1;
       }
     } else {
