@@ -20,8 +20,11 @@ using namespace rthx;
 
 struct rthx_handle {
   int device = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;       // compute stream A (+ zeroing, recorder)
+  cudaStream_t stream2 = nullptr;      // compute stream B: row batches alternate A/B so tails overlap
+  cudaStream_t copy_stream = nullptr;  // device->host copies of finished row batches
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t bev[18] = {};            // per-batch completion events (+2 scratch)
   cudaDeviceProp prop{};
   int n_coarse = 0, n_cells = 0, n_bands = 0, ns = 0, N = 0, n_affine = 0;
   bool coarse_fits_smem = false;
@@ -41,6 +44,36 @@ struct rthx_handle {
 };
 
 static thread_local std::string g_create_err;
+
+// Process-wide cache of the large per-call scratch buffers (count matrix), one slot per device: callers re-create
+// handles for every trace (the mesh is re-flattened each call, like the reference re-reads its structs), and a
+// cudaMalloc/cudaFree pair of ~1 GB per call costs milliseconds to hundreds of milliseconds of driver time.
+namespace {
+struct ScratchSlot { void* ptr = nullptr; size_t bytes = 0; bool in_use = false; };
+std::mutex g_scratch_mu;
+ScratchSlot g_scratch[64];
+
+cudaError_t scratch_acquire(int device, size_t bytes, void** out) {
+  std::lock_guard<std::mutex> lk(g_scratch_mu);
+  ScratchSlot& sl = g_scratch[device & 63];
+  if (!sl.in_use && sl.ptr && sl.bytes >= bytes) { sl.in_use = true; *out = sl.ptr; return cudaSuccess; }
+  if (!sl.in_use && sl.ptr) { cudaFree(sl.ptr); sl.ptr = nullptr; sl.bytes = 0; }
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, std::max<size_t>(bytes, 1));
+  if (e != cudaSuccess) return e;
+  if (!sl.in_use) { sl.ptr = p; sl.bytes = bytes; sl.in_use = true; }   // otherwise an uncached private allocation
+  *out = p;
+  return cudaSuccess;
+}
+
+void scratch_release(int device, void* p) {
+  if (!p) return;
+  std::lock_guard<std::mutex> lk(g_scratch_mu);
+  ScratchSlot& sl = g_scratch[device & 63];
+  if (sl.ptr == p) { sl.in_use = false; return; }
+  cudaFree(p);
+}
+}  // namespace
 
 static int fail(rthx_handle* h, int code, const std::string& msg) {
   if (h) h->err = msg; else g_create_err = msg;
@@ -237,10 +270,13 @@ extern "C" int rthx_destroy(rthx_handle* h) {
   if (!h) return RTHX_OK;
   cudaSetDevice(h->device);
   for (void* d : h->allocs) cudaFree(d);
-  cudaFree(h->counts_dev); cudaFree(h->lost_dev);
+  scratch_release(h->device, h->counts_dev);
   cudaFree(h->rec_pts_dev); cudaFree(h->rec_valid_dev); cudaFree(h->peak_dev);
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+  for (auto& e : h->bev) if (e) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->stream2) cudaStreamDestroy(h->stream2);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   delete h;
   return RTHX_OK;
 }
@@ -264,7 +300,10 @@ extern "C" int rthx_create(rthx_handle** out, const rthx_mesh* m, int device_id)
   if ((ce = cudaGetDeviceProperties(&h->prop, device_id)) != cudaSuccess) return bail(RTHX_ERR_CUDA, cudaGetErrorString(ce));
   if (h->prop.major < 10) return bail(RTHX_ERR_CUDA, "rthx_create: device is not sm_100 class (kernels are built for sm_100a only)");
   if ((ce = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(RTHX_ERR_CUDA, cudaGetErrorString(ce));
+  if ((ce = cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking)) != cudaSuccess) return bail(RTHX_ERR_CUDA, cudaGetErrorString(ce));
+  if ((ce = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(RTHX_ERR_CUDA, cudaGetErrorString(ce));
   for (auto& e : h->ev) if ((ce = cudaEventCreate(&e)) != cudaSuccess) return bail(RTHX_ERR_CUDA, cudaGetErrorString(ce));
+  for (auto& e : h->bev) if ((ce = cudaEventCreateWithFlags(&e, cudaEventDisableTiming)) != cudaSuccess) return bail(RTHX_ERR_CUDA, cudaGetErrorString(ce));
 
   const int nc = m->n_coarse, ncell = m->n_cells, ns = m->n_surfaces, N = ns + ncell, nb = m->n_bands;
   h->n_coarse = nc; h->n_cells = ncell; h->ns = ns; h->N = N; h->n_bands = nb;
@@ -371,7 +410,8 @@ extern "C" int rthx_create(rthx_handle** out, const rthx_mesh* m, int device_id)
                o_nv = A.add(poly_nv), o_pvx = A.add(pvx), o_pvy = A.add(pvy), o_pnx = A.add(pnx), o_pny = A.add(pny),
                o_mid = A.add(mid), o_vol = A.add(vol), o_surf = A.add(surf), o_beta = A.add(beta), o_ub = A.add(ub),
                o_lat = A.add(lattice), o_ec = A.add(em_cell), o_ew = A.add(em_wall), o_eco = A.add(em_coarse),
-               o_bins = A.add(std::vector<int32_t>(), (size_t)nb * 4 + 16), o_rec = A.add(std::vector<int32_t>(), (size_t)N);
+               o_bins = A.add(std::vector<int32_t>(), (size_t)nb * 4 + 16), o_rec = A.add(std::vector<int32_t>(), (size_t)N),
+               o_lost = A.add(std::vector<unsigned long long>(), ((size_t)nb * 4 + 16) * (size_t)N);
   void* base = nullptr;
   if ((ce = cudaMalloc(&base, A.host.size())) != cudaSuccess) return bail(RTHX_ERR_CUDA, std::string("cudaMalloc(mesh arena): ") + cudaGetErrorString(ce));
   h->allocs.push_back(base);
@@ -389,6 +429,7 @@ extern "C" int rthx_create(rthx_handle** out, const rthx_mesh* m, int device_id)
   P.em_coarse = (const int32_t*)(b8 + o_eco);
   h->bins_dev = (int32_t*)(b8 + o_bins); h->bins_cap = (size_t)nb * 4 + 16;
   h->rec_slot_dev = (int32_t*)(b8 + o_rec);
+  h->lost_dev = (unsigned long long*)(b8 + o_lost); h->lost_cap = ((size_t)nb * 4 + 16) * (size_t)N;
   P.n_coarse = nc; P.n_cells = ncell; P.n_surfaces = ns; P.N = N;
   h->coarse_fits_smem = sizeof(CoarseDev) * (size_t)nc <= 32 * 1024;
   h->fast_ok = h->coarse_fits_smem && h->n_affine == nc;
@@ -501,12 +542,13 @@ void fill_stats(rthx_stats* st, const LaunchPlan& pl, const rthx_trace_args* a) 
 }
 
 // Enqueue (zero +) kernel for one handle on `stream`; counts layout compact (owned rows) or full.
+// [y0, y1) restricts the launch to a range of owned-emitter ordinals (y1 < 0: all rows).
 int enqueue_trace(rthx_handle* h, const rthx_trace_args* a, int rank, int world, bool compact, unsigned long long* counts,
                   unsigned long long* lost, bool zero_first, bool with_rec, int n_rec_slots, cudaStream_t stream,
-                  LaunchPlan* plan_out, int* n_launches) {
+                  LaunchPlan* plan_out, int* n_launches, int y0 = 0, int y1 = -1, bool upload_bins = true) {
   LaunchPlan pl = make_plan(h, a, rank, world);
   if ((size_t)a->n_bins > h->bins_cap) return fail(h, RTHX_ERR_ARG, "trace: too many bins in one call");
-  CU(h, cudaMemcpyAsync(h->bins_dev, a->bins, sizeof(int32_t) * (size_t)a->n_bins, cudaMemcpyHostToDevice, stream));
+  if (upload_bins) CU(h, cudaMemcpyAsync(h->bins_dev, a->bins, sizeof(int32_t) * (size_t)a->n_bins, cudaMemcpyHostToDevice, stream));
   const size_t rows = compact ? (size_t)pl.n_owned : (size_t)h->N;
   if (zero_first) {
     CU(h, cudaMemsetAsync(counts, 0, sizeof(unsigned long long) * (size_t)a->n_bins * rows * h->N, stream));
@@ -516,8 +558,68 @@ int enqueue_trace(rthx_handle* h, const rthx_trace_args* a, int rank, int world,
   TraceParams P;
   fill_params(h, a, pl, rank, world, compact, counts, lost, P);
   if (with_rec && n_rec_slots > 0) { P.rec_slot = h->rec_slot_dev; P.rec_pts = h->rec_pts_dev; P.rec_valid = h->rec_valid_dev; }
-  CU(h, launch_trace_exchange(P, pl.n_blocks, pl.block_threads, pl.smem_bytes, pl.fast != 0, pl.minb, stream));
-  if (pl.n_blocks > 0) *n_launches += 1;
+  if (y1 < 0) y1 = pl.n_owned;
+  P.y_offset = y0;
+  const long long nb = (long long)(y1 - y0) * a->n_bins * pl.row_chunks;
+  CU(h, launch_trace_exchange(P, (int)nb, pl.block_threads, pl.smem_bytes, pl.fast != 0, pl.minb, stream));
+  if (nb > 0) *n_launches += 1;
+  *plan_out = pl;
+  return RTHX_OK;
+}
+
+// Host-output trace of one handle, pipelined: the owned rows are cut into batches whose kernels alternate between two
+// compute streams (so the tail of one batch overlaps the head of the next) and whose device->host copies run on a third
+// stream as soon as the batch's kernel has finished.  All work is enqueued; the caller synchronises copy_stream.
+//   ev[0] start, ev[1] first kernel start, ev[2] last kernel end, ev[3] last copy end.
+int enqueue_pipelined(rthx_handle* h, const rthx_trace_args* a, int rank, int world, uint64_t* counts_out, bool with_rec, int n_slots,
+                      LaunchPlan* plan_out, int* n_launches) {
+  const int N = h->N;
+  const int n_owned = (N - rank + world - 1) / world;
+  const size_t need = (size_t)a->n_bins * (size_t)n_owned * N;
+  if (!h->counts_dev || h->counts_cap < need) {
+    scratch_release(h->device, h->counts_dev);
+    h->counts_dev = nullptr; h->counts_cap = 0;
+    void* ptr = nullptr;
+    CU(h, scratch_acquire(h->device, need * sizeof(unsigned long long), &ptr));
+    h->counts_dev = (unsigned long long*)ptr; h->counts_cap = need;
+  }
+  LaunchPlan pl = make_plan(h, a, rank, world);
+  // batches: >= ~6 waves of resident blocks each, at most 16
+  const int per_sm = std::max(1, trace_kernel_max_blocks_per_sm(pl.block_threads, pl.smem_bytes, pl.hist_in_smem != 0, pl.fast != 0, pl.minb));
+  const long long resident = (long long)h->prop.multiProcessorCount * per_sm;
+  int n_batches = (int)std::min<long long>(16, std::max<long long>(1, pl.n_blocks / (6 * resident)));
+  n_batches = std::max(1, std::min(n_batches, n_owned));
+  if (const char* ev = std::getenv("RTHX_BATCHES")) { const int v = std::atoi(ev); if (v >= 1 && v <= 16) n_batches = std::min(v, std::max(1, n_owned)); }
+  CU(h, cudaMemcpyAsync(h->bins_dev, a->bins, sizeof(int32_t) * (size_t)a->n_bins, cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaMemsetAsync(h->counts_dev, 0, sizeof(unsigned long long) * (size_t)a->n_bins * (size_t)n_owned * N, h->stream));
+  CU(h, cudaMemsetAsync(h->lost_dev, 0, sizeof(unsigned long long) * (size_t)a->n_bins * N, h->stream));
+  *n_launches += 2;
+  CU(h, cudaEventRecord(h->ev[1], h->stream));
+  CU(h, cudaStreamWaitEvent(h->stream2, h->ev[1], 0));
+  for (int b = 0; b < n_batches; ++b) {
+    const int y0 = (int)((long long)n_owned * b / n_batches), y1 = (int)((long long)n_owned * (b + 1) / n_batches);
+    cudaStream_t cs = (b & 1) ? h->stream2 : h->stream;
+    LaunchPlan tmp{};
+    int rc = enqueue_trace(h, a, rank, world, /*compact=*/true, h->counts_dev, h->lost_dev, false, with_rec, n_slots, cs, &tmp, n_launches, y0, y1,
+                           /*upload_bins=*/false);
+    if (rc) return rc;
+    CU(h, cudaEventRecord(h->bev[b], cs));
+    CU(h, cudaStreamWaitEvent(h->copy_stream, h->bev[b], 0));
+    if (y1 > y0)
+      for (int bin = 0; bin < a->n_bins; ++bin) {
+        const unsigned long long* src = h->counts_dev + ((size_t)bin * n_owned + y0) * N;
+        if (world == 1)
+          CU(h, cudaMemcpyAsync(counts_out + ((size_t)bin * N + y0) * N, src, sizeof(uint64_t) * (size_t)(y1 - y0) * N, cudaMemcpyDeviceToHost, h->copy_stream));
+        else
+          CU(h, cudaMemcpy2DAsync(counts_out + ((size_t)bin * N + rank + (size_t)y0 * world) * N, sizeof(uint64_t) * (size_t)world * N, src,
+                                  sizeof(uint64_t) * (size_t)N, sizeof(uint64_t) * (size_t)N, (size_t)(y1 - y0), cudaMemcpyDeviceToHost, h->copy_stream));
+      }
+  }
+  // last kernel end = both compute streams drained
+  CU(h, cudaEventRecord(h->bev[16], h->stream2));
+  CU(h, cudaStreamWaitEvent(h->stream, h->bev[16], 0));
+  CU(h, cudaEventRecord(h->ev[2], h->stream));
+  CU(h, cudaStreamWaitEvent(h->copy_stream, h->ev[2], 0));
   *plan_out = pl;
   return RTHX_OK;
 }
@@ -569,39 +671,19 @@ extern "C" int rthx_trace_exchange(rthx_handle* h, const rthx_trace_args* a, uin
   if (rc) return rc;
   if (!counts_out) return fail(h, RTHX_ERR_ARG, "trace: counts_out is NULL");
   CU(h, cudaSetDevice(h->device));
-  const int rank = a->emitter_rank, world = a->emitter_world;
   const int N = h->N;
-  const size_t n_owned = (size_t)((N - rank + world - 1) / world);
-  CU(h, ensure(&h->counts_dev, &h->counts_cap, (size_t)a->n_bins * n_owned * N));
-  CU(h, ensure(&h->lost_dev, &h->lost_cap, (size_t)a->n_bins * N));
   int n_slots = 0, n_launches = 0;
   CU(h, cudaEventRecord(h->ev[0], h->stream));
   rc = prepare_recorder(h, a, rec, &n_slots, h->stream);
   if (rc) return rc;
   LaunchPlan pl{};
-  // kernel timing brackets only the trace kernel: zeroing is enqueued first, then ev[1], kernel, ev[2]
-  CU(h, cudaMemsetAsync(h->counts_dev, 0, sizeof(unsigned long long) * (size_t)a->n_bins * n_owned * N, h->stream));
-  CU(h, cudaMemsetAsync(h->lost_dev, 0, sizeof(unsigned long long) * (size_t)a->n_bins * N, h->stream));
-  n_launches += 2;
-  CU(h, cudaEventRecord(h->ev[1], h->stream));
-  rc = enqueue_trace(h, a, rank, world, /*compact=*/true, h->counts_dev, h->lost_dev, /*zero_first=*/false, rec != nullptr, n_slots,
-                     h->stream, &pl, &n_launches);
+  if (a->emitter_world > 1) std::memset(counts_out, 0, sizeof(uint64_t) * (size_t)a->n_bins * N * N);   // rows of other ranks
+  rc = enqueue_pipelined(h, a, a->emitter_rank, a->emitter_world, counts_out, rec != nullptr, n_slots, &pl, &n_launches);
   if (rc) return rc;
-  CU(h, cudaEventRecord(h->ev[2], h->stream));
-  // device -> host: owned rows scatter into the full [n_bins][N][N] host matrix (other rows zeroed)
-  if (world == 1) {
-    CU(h, cudaMemcpyAsync(counts_out, h->counts_dev, sizeof(uint64_t) * (size_t)a->n_bins * N * N, cudaMemcpyDeviceToHost, h->stream));
-  } else {
-    std::memset(counts_out, 0, sizeof(uint64_t) * (size_t)a->n_bins * N * N);
-    for (int b = 0; b < a->n_bins; ++b)
-      if (n_owned > 0)
-        CU(h, cudaMemcpy2DAsync(counts_out + ((size_t)b * N + rank) * N, sizeof(uint64_t) * (size_t)world * N,
-                                h->counts_dev + (size_t)b * n_owned * N, sizeof(uint64_t) * (size_t)N, sizeof(uint64_t) * (size_t)N,
-                                n_owned, cudaMemcpyDeviceToHost, h->stream));
-  }
   std::vector<uint64_t> lost_host((size_t)a->n_bins * N);
-  CU(h, cudaMemcpyAsync(lost_host.data(), h->lost_dev, sizeof(uint64_t) * lost_host.size(), cudaMemcpyDeviceToHost, h->stream));
-  CU(h, cudaEventRecord(h->ev[3], h->stream));
+  CU(h, cudaMemcpyAsync(lost_host.data(), h->lost_dev, sizeof(uint64_t) * lost_host.size(), cudaMemcpyDeviceToHost, h->copy_stream));
+  CU(h, cudaEventRecord(h->ev[3], h->copy_stream));
+  CU(h, cudaStreamSynchronize(h->copy_stream));
   CU(h, cudaStreamSynchronize(h->stream));
   if (lost_out) std::memcpy(lost_out, lost_host.data(), sizeof(uint64_t) * lost_host.size());
   rc = collect_recorder(h, a, rec, n_slots, h->stream, false);
@@ -648,22 +730,16 @@ extern "C" int rthx_trace_exchange_multi(rthx_handle** hs, int n, const rthx_tra
   std::vector<int> slots(n, 0);
   int n_launches = 0;
   // enqueue on every device first, then drain: the devices run concurrently
+  if (n > 1) std::memset(counts_out, 0, sizeof(uint64_t) * (size_t)a->n_bins * N * N);
   for (int i = 0; i < n; ++i) {
     rthx_handle* h = hs[i];
     CU(h0, cudaSetDevice(h->device));
-    const size_t n_owned = (size_t)((N - i + n - 1) / n);
-    CU(h0, ensure(&h->counts_dev, &h->counts_cap, (size_t)a->n_bins * n_owned * N));
-    CU(h0, ensure(&h->lost_dev, &h->lost_cap, (size_t)a->n_bins * N));
     CU(h0, cudaEventRecord(h->ev[0], h->stream));
     rc = prepare_recorder(h, a, rec, &slots[i], h->stream);
     if (rc) return fail(h0, rc, h->err);
-    rc = enqueue_trace(h, a, i, n, true, h->counts_dev, h->lost_dev, true, rec != nullptr, slots[i], h->stream, &plans[i], &n_launches);
+    rc = enqueue_pipelined(h, a, i, n, counts_out, rec != nullptr, slots[i], &plans[i], &n_launches);
     if (rc) return fail(h0, rc, h->err);
-    for (int b = 0; b < a->n_bins; ++b)
-      if (n_owned > 0)
-        CU(h0, cudaMemcpy2DAsync(counts_out + ((size_t)b * N + i) * N, sizeof(uint64_t) * (size_t)n * N, h->counts_dev + (size_t)b * n_owned * N,
-                                 sizeof(uint64_t) * (size_t)N, sizeof(uint64_t) * (size_t)N, n_owned, cudaMemcpyDeviceToHost, h->stream));
-    CU(h0, cudaEventRecord(h->ev[3], h->stream));
+    CU(h0, cudaEventRecord(h->ev[3], h->copy_stream));
   }
   std::vector<uint64_t> lost_sum((size_t)a->n_bins * N, 0), lost_host((size_t)a->n_bins * N);
   double max_ms = 0;
@@ -674,6 +750,7 @@ extern "C" int rthx_trace_exchange_multi(rthx_handle** hs, int n, const rthx_tra
   for (int i = 0; i < n; ++i) {
     rthx_handle* h = hs[i];
     CU(h0, cudaSetDevice(h->device));
+    CU(h0, cudaStreamSynchronize(h->copy_stream));
     CU(h0, cudaMemcpyAsync(lost_host.data(), h->lost_dev, sizeof(uint64_t) * lost_host.size(), cudaMemcpyDeviceToHost, h->stream));
     CU(h0, cudaStreamSynchronize(h->stream));
     for (size_t k = 0; k < lost_sum.size(); ++k) lost_sum[k] += lost_host[k];

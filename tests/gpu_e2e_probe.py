@@ -6,16 +6,11 @@ import rthx
 rtm = rthx.meshes.cfg3(); flat = rthx.flatten_domain(rtm)
 N = flat.n_elements
 pinned = torch.empty((1, N, N), dtype=torch.int64, pin_memory=True)
-pageable = np.empty((1, N, N), np.uint64)
-for rep in range(3):
+torch.cuda.synchronize()
+for rep in range(6):
     t0 = time.perf_counter(); tr = rthx.DeviceTracer(flat, 0); t1 = time.perf_counter()
     out = tr.trace(100000, counts_out=pinned.numpy().view(np.uint64), seed=rep); t2 = time.perf_counter()
     out2 = tr.trace(100000, counts_out=pinned.numpy().view(np.uint64), seed=rep); t3 = time.perf_counter()
-    out3 = tr.trace(100000, counts_out=pageable, seed=rep); t4 = time.perf_counter()
     tr.close(); t5 = time.perf_counter()
     print(f"create {1e3*(t1-t0):.1f} ms | trace#1 pinned {1e3*(t2-t1):.1f} (kernel {out['stats']['kernel_ms']:.1f}, total_dev {out['stats']['total_ms']:.1f}) | "
-          f"trace#2 pinned {1e3*(t3-t2):.1f} (total_dev {out2['stats']['total_ms']:.1f}) | pageable {1e3*(t4-t3):.1f} | close {1e3*(t5-t4):.1f}", flush=True)
-d = torch.empty((N * N,), dtype=torch.int64, device="cuda")
-for _ in range(3):
-    torch.cuda.synchronize(); t0 = time.perf_counter(); pinned.view(-1).copy_(d); torch.cuda.synchronize(); t1 = time.perf_counter()
-    print(f"torch D2H pinned 900MB: {1e3*(t1-t0):.1f} ms = {N*N*8/(t1-t0)/1e9:.1f} GB/s")
+          f"trace#2 pinned {1e3*(t3-t2):.1f} (total_dev {out2['stats']['total_ms']:.1f}) | close {1e3*(t5-t3):.1f}", flush=True)
