@@ -44,6 +44,8 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--block-threads", type=int, default=0)
     ap.add_argument("--row-chunks", type=int, default=0)
+    ap.add_argument("--reduce", default="fused", choices=["fused", "nccl"],
+                    help="N > 1: fused peer-memory flush over NVLink (default) or a private matrix per rank + NCCL reduce")
     return ap.parse_args()
 
 
@@ -215,22 +217,17 @@ def main():
     rpe = int(rays_total) // N      # rays_total applies per traced band (parallelRayTracing.jl:22-25,34-37)
     traced_per_step = rpe * N * nb
 
-    sh = ShardedTracer(flat, device=local_rank, rank=rank, world=world, n_bins=nb)
+    sh = ShardedTracer(flat, device=local_rank, rank=rank, world=world, n_bins=nb, mode=args.reduce)
     kw = dict(bins=bins, block_threads=args.block_threads, row_chunks=args.row_chunks)
     stream = torch.cuda.current_stream(dev)
 
     def step(seed, time_kernel=None):
-        sh.counts.zero_()
-        sh.lost.zero_()
         if time_kernel is not None:
             time_kernel[0].record(stream)
-        st = sh.tracer.trace_device(rpe, sh.counts.data_ptr(), sh.lost.data_ptr(), stream=stream.cuda_stream,
-                                    zero_first=False, emitter_rank=rank, emitter_world=world, seed=seed, **kw)
+        st = sh.enqueue(rpe, seed=seed, **kw)        # zero (own rows) + trace kernel (+ fused peer flush)
         if time_kernel is not None:
             time_kernel[1].record(stream)
-        if world > 1:
-            reduce_counts(sh.counts)
-            reduce_counts(sh.lost)
+        sh.finish()                                  # barrier (fused) or NCCL reduce
         return st
 
     def barrier():
@@ -275,6 +272,7 @@ def main():
             "cell_volume", "cell_surf_id", "kappa", "sigma_s", "epsilon", "uniform_beta"))
 
         e2e_dev_ms = []
+        e2e_phases = []   # N > 1: [create, trace+finish, d2h+sync, barrier, close] ms per step
 
         def e2e_step(seed):
             if world == 1:
@@ -283,15 +281,21 @@ def main():
                 tr.close()
                 e2e_dev_ms.append((out["stats"]["kernel_ms"], out["stats"]["total_ms"]))
                 return int(out["lost"].sum())
-            tr = rthx.DeviceTracer(flat, device=local_rank)
-            tr.trace_device(rpe, sh.counts.data_ptr(), sh.lost.data_ptr(), stream=stream.cuda_stream, zero_first=True,
-                            emitter_rank=rank, emitter_world=world, seed=seed, **kw)
-            reduce_counts(sh.counts)
-            reduce_counts(sh.lost)
+            tp = [time.perf_counter()]
+            old = sh.tracer
+            sh.tracer = rthx.DeviceTracer(flat, device=local_rank)    # this step's mesh -> device (H2D)
+            tp.append(time.perf_counter())
+            sh.trace(rpe, seed=seed, **kw)
+            tp.append(time.perf_counter())
             if rank == 0:
                 counts_host.copy_(sh.counts, non_blocking=True)
             torch.cuda.synchronize(dev)
-            tr.close()
+            tp.append(time.perf_counter())
+            dist.barrier(device_ids=[local_rank])                     # rank 0 has read the matrix: next step may zero it
+            tp.append(time.perf_counter())
+            old.close()
+            tp.append(time.perf_counter())
+            e2e_phases.append([1e3 * (b - a) for a, b in zip(tp[:-1], tp[1:])])
             return 0
 
         e2e_step(3000)
@@ -311,8 +315,9 @@ def main():
                "ms_per_step": dt / args.steps * 1e3,
                "device_ms_per_step": {"kernel": float(np.mean([a for a, _ in e2e_dev_ms[1:]])),
                                       "zero+kernel+d2h": float(np.mean([b for _, b in e2e_dev_ms[1:]]))} if e2e_dev_ms else None,
+               "phases_ms": [float(x) for x in np.mean(np.array(e2e_phases[1:]), axis=0)] if len(e2e_phases) > 1 else None,
                "path": "rthx_create + rthx_trace_exchange (pinned host count matrix)" if world == 1 else
-                       "rthx_create + rthx_trace_exchange_device + NCCL reduce + D2H on rank 0"}
+                       f"rthx_create + rthx_trace_exchange_device ({args.reduce}) + D2H of the matrix on rank 0"}
 
     if rank != 0:
         if world > 1:
@@ -346,10 +351,12 @@ def main():
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {workload_desc(args.workload)}", "elements": N, "bands": nb,
                    "rays_per_step": traced_per_step, "rays_per_emitter": rpe,
-                   "partition": f"emitter rows e % {world} == rank; one reduce of the u64 count matrix to rank 0",
+                   "partition": (f"emitter rows e % {world} == rank; " + ("rows flushed into rank 0's matrix over NVLink peer memory "
+                                 "inside the trace kernel, then a barrier" if sh.mode == "fused" else
+                                 "one NCCL reduce of the u64 count matrix to rank 0" if sh.mode == "nccl" else "single GPU")),
                    "l2": "count matrix (8*N*N bytes) exceeds the 126 MB L2 for cfg3; a fresh Philox seed every step",
                    "launch": {k: st[k] for k in ("n_blocks", "block_threads", "row_chunks", "smem_bytes", "hist_in_smem")}},
-        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps,
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps * world,
         "clocks": sampler.summary() if sampler else None,
         "check": {"tallied_last_step": tallied, "lost_last_step": lost_total},
     }

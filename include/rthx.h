@@ -163,6 +163,9 @@ typedef struct rthx_handle rthx_handle;
  * device-side twin of RayTracingDomain2D.jl:2-111 + spatialAccelerations.jl:92-106. */
 int rthx_create(rthx_handle** out, const rthx_mesh* mesh, int device_id);
 int rthx_destroy(rthx_handle* h);
+/* rthx_destroy parks streams, events and device buffers in a per-device pool that the next rthx_create adopts
+ * (handles are typically re-created for every trace); this frees everything that is parked. */
+int rthx_release_cached(void);
 int rthx_get_info(const rthx_handle* h, rthx_info* info);
 
 /* Blocking trace with HOST outputs.  Replaces computeExchangeFactorsBin (parallelRayTracing.jl:64-159)
@@ -176,8 +179,11 @@ int rthx_trace_exchange(rthx_handle* h, const rthx_trace_args* args,
 
 /* Asynchronous trace into DEVICE buffers on `stream` (a cudaStream_t; NULL = default stream):
  * counts_dev [n_bins*N*N] uint64, lost_dev [n_bins*N] uint64 on the handle's device (or peer-mapped).
- * zero_first != 0 clears both buffers on the stream before the launch.  Does not synchronise; stats
- * carries the launch geometry only.  Recording is not available on this entry point. */
+ * zero_first: RTHX_ZERO_NONE, RTHX_ZERO_ALL (clear both buffers on the stream before the launch) or
+ * RTHX_ZERO_OWN_ROWS (clear only the rows / lost entries of the emitters this call owns — for a matrix shared by
+ * several ranks).  Does not synchronise; stats carries the launch geometry only.  Recording is not available on
+ * this entry point. */
+enum { RTHX_ZERO_NONE = 0, RTHX_ZERO_ALL = 1, RTHX_ZERO_OWN_ROWS = 2 };
 int rthx_trace_exchange_device(rthx_handle* h, const rthx_trace_args* args,
                                void* counts_dev, void* lost_dev, void* stream,
                                int zero_first, rthx_stats* stats);
@@ -188,6 +194,17 @@ int rthx_trace_exchange_device(rthx_handle* h, const rthx_trace_args* args,
 int rthx_trace_exchange_multi(rthx_handle** hs, int n, const rthx_trace_args* args,
                               uint64_t* counts_out, uint64_t* lost_out,
                               rthx_rec_out* rec, rthx_stats* stats);
+
+/* Peer-memory plumbing for the fused flush in one-process-per-GPU runs: rank 0 allocates the UInt64 count matrix
+ * with rthx_shared_alloc and publishes the 64-byte CUDA IPC handle; every other rank maps it with rthx_shared_open
+ * (peer access over NVLink is enabled lazily) and passes the mapped pointer as `counts_dev` to
+ * rthx_trace_exchange_device with zero_first = RTHX_ZERO_OWN_ROWS.  Each rank's kernel then flushes its own (disjoint)
+ * rows straight into rank 0's memory with red.global.add.u64 over NVLink — the reduce is fused into the trace kernel
+ * and only a barrier remains. */
+int rthx_shared_alloc(int device_id, uint64_t bytes, void** dev_ptr, unsigned char ipc_handle[64]);
+int rthx_shared_open(int device_id, const unsigned char ipc_handle[64], void** dev_ptr);
+int rthx_shared_close(int device_id, void* dev_ptr);
+int rthx_shared_free(int device_id, void* dev_ptr);
 
 /* FP64 FMA-chain micro-benchmark on the handle's device: the denominator of the FP64 roofline
  * (MEASURED_PEAKS.json has no FP64 entry).  Returns TFLOP/s (2 flop per DFMA). */

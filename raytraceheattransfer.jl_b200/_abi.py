@@ -7,6 +7,7 @@ RTHX_OK = 0
 RTHX_FIRST_INTERACTION = 0
 RTHX_LOCATOR_AUTO = 0
 RTHX_LOCATOR_GENERIC = 1
+RTHX_ZERO_NONE, RTHX_ZERO_ALL, RTHX_ZERO_OWN_ROWS = 0, 1, 2
 
 c_i32p = C.POINTER(C.c_int32)
 c_f64p = C.POINTER(C.c_double)
@@ -67,4 +68,5 @@ class rthx_info(C.Structure):
 EXPORTED_SYMBOLS = (
     "rthx_create", "rthx_destroy", "rthx_get_info", "rthx_trace_exchange", "rthx_trace_exchange_device",
     "rthx_trace_exchange_multi", "rthx_measure_fp64_peak", "rthx_last_error", "rthx_version",
+    "rthx_shared_alloc", "rthx_shared_open", "rthx_shared_close", "rthx_shared_free", "rthx_release_cached",
 )

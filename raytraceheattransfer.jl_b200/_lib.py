@@ -82,6 +82,14 @@ def load_library():
     L.rthx_trace_exchange_multi.restype = C.c_int
     L.rthx_trace_exchange_multi.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(rthx_trace_args), c_u64p,
                                             c_u64p, C.POINTER(rthx_rec_out), C.POINTER(rthx_stats)]
+    L.rthx_shared_alloc.restype = C.c_int
+    L.rthx_shared_alloc.argtypes = [C.c_int, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_ubyte)]
+    L.rthx_shared_open.restype = C.c_int
+    L.rthx_shared_open.argtypes = [C.c_int, C.POINTER(C.c_ubyte), C.POINTER(C.c_void_p)]
+    L.rthx_shared_close.restype = C.c_int
+    L.rthx_shared_close.argtypes = [C.c_int, C.c_void_p]
+    L.rthx_shared_free.restype = C.c_int
+    L.rthx_shared_free.argtypes = [C.c_int, C.c_void_p]
     L.rthx_measure_fp64_peak.restype = C.c_int
     L.rthx_measure_fp64_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     L.rthx_last_error.restype = C.c_char_p
@@ -179,14 +187,14 @@ class DeviceTracer:
         return out
 
     def trace_device(self, rays_per_emitter: int, counts_ptr: int, lost_ptr: int, stream: int = 0,
-                     zero_first: bool = True, **kw):
+                     zero_first=True, **kw):
         """Asynchronous trace into device buffers (rthx_trace_exchange_device); pointers are raw device addresses
         (e.g. torch.Tensor.data_ptr()), stream a cudaStream_t handle (e.g. torch.cuda.current_stream().cuda_stream)."""
         args, keep = make_trace_args(rays_per_emitter, **kw)
         st = rthx_stats()
         self._check(self._L.rthx_trace_exchange_device(self._h, C.byref(args), C.c_void_p(counts_ptr),
                                                        C.c_void_p(lost_ptr), C.c_void_p(stream),
-                                                       1 if zero_first else 0, C.byref(st)))
+                                                       int(zero_first), C.byref(st)))
         return st.as_dict()
 
     def measure_fp64_peak(self) -> float:
@@ -222,3 +230,40 @@ def trace_multi(tracers: Sequence[DeviceTracer], rays_per_emitter: int, **kw):
         out["origins"] = origins[: rec.n_recorded].copy()
         out["endpoints"] = endpoints[: rec.n_recorded].copy()
     return out
+
+
+class SharedDeviceBuffer:
+    """A device buffer owned by one rank and mapped by the others through CUDA IPC (rthx_shared_alloc / _open).
+    Exposes `__cuda_array_interface__` so `torch.as_tensor(buf, device=...)` gives a zero-copy int64 view."""
+
+    def __init__(self, device: int, n_int64: int, handle: Optional[bytes] = None):
+        self._L = load_library()
+        self.device = int(device)
+        self.n = int(n_int64)
+        self.owner = handle is None
+        ptr = C.c_void_p()
+        if self.owner:
+            hb = (C.c_ubyte * 64)()
+            rc = self._L.rthx_shared_alloc(self.device, self.n * 8, C.byref(ptr), hb)
+            self.handle = bytes(hb)
+        else:
+            hb = (C.c_ubyte * 64)(*handle)
+            rc = self._L.rthx_shared_open(self.device, hb, C.byref(ptr))
+            self.handle = bytes(handle)
+        if rc != 0:
+            msg = self._L.rthx_last_error(None)
+            raise RthxError(f"shared buffer {'alloc' if self.owner else 'open'} failed ({rc}): {msg.decode() if msg else ''}")
+        self.ptr = ptr.value
+        self.__cuda_array_interface__ = {"shape": (self.n,), "typestr": "<i8", "data": (self.ptr, False), "version": 2,
+                                         "strides": None}
+
+    def close(self):
+        if getattr(self, "ptr", None):
+            (self._L.rthx_shared_free if self.owner else self._L.rthx_shared_close)(self.device, C.c_void_p(self.ptr))
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -18,60 +18,66 @@
 
 using namespace rthx;
 
-struct rthx_handle {
-  int device = 0;
+// Device resources that outlive a handle.  Callers re-create handles for every trace (the mesh is re-flattened on
+// each call, like the reference re-reads its structs); creating/destroying streams, events and device allocations
+// each time costs milliseconds on one GPU and >100 ms per cudaFree once peer mappings exist (NCCL / CUDA IPC).
+// rthx_destroy therefore parks the bundle in a per-device pool and rthx_create adopts it; rthx_release_cached frees.
+struct DevRes {
   cudaStream_t stream = nullptr;       // compute stream A (+ zeroing, recorder)
   cudaStream_t stream2 = nullptr;      // compute stream B: row batches alternate A/B so tails overlap
   cudaStream_t copy_stream = nullptr;  // device->host copies of finished row batches
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t bev[18] = {};            // per-batch completion events (+2 scratch)
+  void* arena = nullptr;                    size_t arena_cap = 0;      // mesh tables
+  unsigned long long* counts_dev = nullptr; size_t counts_cap = 0;     // count matrix of the host-output entry points
+  double* rec_pts_dev = nullptr;            size_t rec_pts_cap = 0;
+  uint8_t* rec_valid_dev = nullptr;         size_t rec_valid_cap = 0;
+  double* peak_dev = nullptr;
+  bool valid = false;
+};
+
+struct rthx_handle : DevRes {
+  int device = 0;
   cudaDeviceProp prop{};
   int n_coarse = 0, n_cells = 0, n_bands = 0, ns = 0, N = 0, n_affine = 0;
   bool coarse_fits_smem = false;
   bool fast_ok = false;        // every coarse face affine + complete neighbour table + descriptors fit in smem
-  std::vector<void*> allocs;   // mesh arena
   size_t mesh_bytes = 0;
   TraceParams base{};          // mesh pointers filled once
-  // per-call scratch, grown on demand
-  unsigned long long* counts_dev = nullptr; size_t counts_cap = 0;
+  // views into the arena
   unsigned long long* lost_dev = nullptr;   size_t lost_cap = 0;
   int32_t* bins_dev = nullptr;              size_t bins_cap = 0;
   int32_t* rec_slot_dev = nullptr;
-  double* rec_pts_dev = nullptr;            size_t rec_pts_cap = 0;
-  uint8_t* rec_valid_dev = nullptr;         size_t rec_valid_cap = 0;
-  double* peak_dev = nullptr;
   std::string err;
 };
 
 static thread_local std::string g_create_err;
 
-// Process-wide cache of the large per-call scratch buffers (count matrix), one slot per device: callers re-create
-// handles for every trace (the mesh is re-flattened each call, like the reference re-reads its structs), and a
-// cudaMalloc/cudaFree pair of ~1 GB per call costs milliseconds to hundreds of milliseconds of driver time.
 namespace {
-struct ScratchSlot { void* ptr = nullptr; size_t bytes = 0; bool in_use = false; };
-std::mutex g_scratch_mu;
-ScratchSlot g_scratch[64];
+std::mutex g_pool_mu;
+std::vector<DevRes> g_pool[64];
+cudaDeviceProp g_prop[64];
+bool g_prop_ok[64] = {};
 
-cudaError_t scratch_acquire(int device, size_t bytes, void** out) {
-  std::lock_guard<std::mutex> lk(g_scratch_mu);
-  ScratchSlot& sl = g_scratch[device & 63];
-  if (!sl.in_use && sl.ptr && sl.bytes >= bytes) { sl.in_use = true; *out = sl.ptr; return cudaSuccess; }
-  if (!sl.in_use && sl.ptr) { cudaFree(sl.ptr); sl.ptr = nullptr; sl.bytes = 0; }
-  void* p = nullptr;
-  cudaError_t e = cudaMalloc(&p, std::max<size_t>(bytes, 1));
-  if (e != cudaSuccess) return e;
-  if (!sl.in_use) { sl.ptr = p; sl.bytes = bytes; sl.in_use = true; }   // otherwise an uncached private allocation
-  *out = p;
-  return cudaSuccess;
+void devres_free(DevRes& r) {
+  cudaFree(r.arena); cudaFree(r.counts_dev); cudaFree(r.rec_pts_dev); cudaFree(r.rec_valid_dev); cudaFree(r.peak_dev);
+  for (auto& e : r.ev) if (e) cudaEventDestroy(e);
+  for (auto& e : r.bev) if (e) cudaEventDestroy(e);
+  if (r.stream) cudaStreamDestroy(r.stream);
+  if (r.stream2) cudaStreamDestroy(r.stream2);
+  if (r.copy_stream) cudaStreamDestroy(r.copy_stream);
+  r = DevRes();
 }
 
-void scratch_release(int device, void* p) {
-  if (!p) return;
-  std::lock_guard<std::mutex> lk(g_scratch_mu);
-  ScratchSlot& sl = g_scratch[device & 63];
-  if (sl.ptr == p) { sl.in_use = false; return; }
-  cudaFree(p);
+cudaError_t devres_create(DevRes& r) {
+  cudaError_t e;
+  if ((e = cudaStreamCreateWithFlags(&r.stream, cudaStreamNonBlocking)) != cudaSuccess) return e;
+  if ((e = cudaStreamCreateWithFlags(&r.stream2, cudaStreamNonBlocking)) != cudaSuccess) return e;
+  if ((e = cudaStreamCreateWithFlags(&r.copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return e;
+  for (auto& ev : r.ev) if ((e = cudaEventCreate(&ev)) != cudaSuccess) return e;
+  for (auto& ev : r.bev) if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return e;
+  r.valid = true;
+  return cudaSuccess;
 }
 }  // namespace
 
@@ -269,15 +275,27 @@ extern "C" const char* rthx_last_error(const rthx_handle* h) { return h ? h->err
 extern "C" int rthx_destroy(rthx_handle* h) {
   if (!h) return RTHX_OK;
   cudaSetDevice(h->device);
-  for (void* d : h->allocs) cudaFree(d);
-  scratch_release(h->device, h->counts_dev);
-  cudaFree(h->rec_pts_dev); cudaFree(h->rec_valid_dev); cudaFree(h->peak_dev);
-  for (auto& e : h->ev) if (e) cudaEventDestroy(e);
-  for (auto& e : h->bev) if (e) cudaEventDestroy(e);
-  if (h->stream) cudaStreamDestroy(h->stream);
-  if (h->stream2) cudaStreamDestroy(h->stream2);
-  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  if (h->valid) {
+    // drain this handle's streams, then park the resources for the next handle on this device
+    cudaStreamSynchronize(h->stream); cudaStreamSynchronize(h->stream2); cudaStreamSynchronize(h->copy_stream);
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    g_pool[h->device & 63].push_back(static_cast<DevRes&>(*h));
+  }
   delete h;
+  return RTHX_OK;
+}
+
+extern "C" int rthx_release_cached(void) {
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  int cur = 0;
+  cudaGetDevice(&cur);
+  for (int d = 0; d < 64; ++d) {
+    if (g_pool[d].empty()) continue;
+    cudaSetDevice(d);
+    for (auto& r : g_pool[d]) devres_free(r);
+    g_pool[d].clear();
+  }
+  cudaSetDevice(cur);
   return RTHX_OK;
 }
 
@@ -297,13 +315,18 @@ extern "C" int rthx_create(rthx_handle** out, const rthx_mesh* m, int device_id)
   h->device = device_id;
   auto bail = [&](int code, const std::string& msg) { g_create_err = msg; rthx_destroy(h); return code; };
   if ((ce = cudaSetDevice(device_id)) != cudaSuccess) return bail(RTHX_ERR_CUDA, cudaGetErrorString(ce));
-  if ((ce = cudaGetDeviceProperties(&h->prop, device_id)) != cudaSuccess) return bail(RTHX_ERR_CUDA, cudaGetErrorString(ce));
+  {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    if (!g_prop_ok[device_id & 63]) {
+      if ((ce = cudaGetDeviceProperties(&g_prop[device_id & 63], device_id)) != cudaSuccess) { g_create_err = cudaGetErrorString(ce); delete h; return RTHX_ERR_CUDA; }
+      g_prop_ok[device_id & 63] = true;
+    }
+    h->prop = g_prop[device_id & 63];
+    auto& pool = g_pool[device_id & 63];
+    if (!pool.empty()) { static_cast<DevRes&>(*h) = pool.back(); pool.pop_back(); }
+  }
   if (h->prop.major < 10) return bail(RTHX_ERR_CUDA, "rthx_create: device is not sm_100 class (kernels are built for sm_100a only)");
-  if ((ce = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(RTHX_ERR_CUDA, cudaGetErrorString(ce));
-  if ((ce = cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking)) != cudaSuccess) return bail(RTHX_ERR_CUDA, cudaGetErrorString(ce));
-  if ((ce = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(RTHX_ERR_CUDA, cudaGetErrorString(ce));
-  for (auto& e : h->ev) if ((ce = cudaEventCreate(&e)) != cudaSuccess) return bail(RTHX_ERR_CUDA, cudaGetErrorString(ce));
-  for (auto& e : h->bev) if ((ce = cudaEventCreateWithFlags(&e, cudaEventDisableTiming)) != cudaSuccess) return bail(RTHX_ERR_CUDA, cudaGetErrorString(ce));
+  if (!h->valid && (ce = devres_create(*h)) != cudaSuccess) return bail(RTHX_ERR_CUDA, std::string("stream/event creation: ") + cudaGetErrorString(ce));
 
   const int nc = m->n_coarse, ncell = m->n_cells, ns = m->n_surfaces, N = ns + ncell, nb = m->n_bands;
   h->n_coarse = nc; h->n_cells = ncell; h->ns = ns; h->N = N; h->n_bands = nb;
@@ -412,9 +435,14 @@ extern "C" int rthx_create(rthx_handle** out, const rthx_mesh* m, int device_id)
                o_lat = A.add(lattice), o_ec = A.add(em_cell), o_ew = A.add(em_wall), o_eco = A.add(em_coarse),
                o_bins = A.add(std::vector<int32_t>(), (size_t)nb * 4 + 16), o_rec = A.add(std::vector<int32_t>(), (size_t)N),
                o_lost = A.add(std::vector<unsigned long long>(), ((size_t)nb * 4 + 16) * (size_t)N);
-  void* base = nullptr;
-  if ((ce = cudaMalloc(&base, A.host.size())) != cudaSuccess) return bail(RTHX_ERR_CUDA, std::string("cudaMalloc(mesh arena): ") + cudaGetErrorString(ce));
-  h->allocs.push_back(base);
+  if (h->arena_cap < A.host.size()) {
+    cudaFree(h->arena);
+    h->arena = nullptr; h->arena_cap = 0;
+    const size_t cap = A.host.size() + A.host.size() / 4;
+    if ((ce = cudaMalloc(&h->arena, cap)) != cudaSuccess) return bail(RTHX_ERR_CUDA, std::string("cudaMalloc(mesh arena): ") + cudaGetErrorString(ce));
+    h->arena_cap = cap;
+  }
+  void* base = h->arena;
   if ((ce = cudaMemcpy(base, A.host.data(), A.host.size(), cudaMemcpyHostToDevice)) != cudaSuccess)
     return bail(RTHX_ERR_CUDA, std::string("cudaMemcpy(mesh arena): ") + cudaGetErrorString(ce));
   h->mesh_bytes = A.host.size();
@@ -544,16 +572,28 @@ void fill_stats(rthx_stats* st, const LaunchPlan& pl, const rthx_trace_args* a) 
 // Enqueue (zero +) kernel for one handle on `stream`; counts layout compact (owned rows) or full.
 // [y0, y1) restricts the launch to a range of owned-emitter ordinals (y1 < 0: all rows).
 int enqueue_trace(rthx_handle* h, const rthx_trace_args* a, int rank, int world, bool compact, unsigned long long* counts,
-                  unsigned long long* lost, bool zero_first, bool with_rec, int n_rec_slots, cudaStream_t stream,
+                  unsigned long long* lost, int zero_first, bool with_rec, int n_rec_slots, cudaStream_t stream,
                   LaunchPlan* plan_out, int* n_launches, int y0 = 0, int y1 = -1, bool upload_bins = true) {
   LaunchPlan pl = make_plan(h, a, rank, world);
   if ((size_t)a->n_bins > h->bins_cap) return fail(h, RTHX_ERR_ARG, "trace: too many bins in one call");
   if (upload_bins) CU(h, cudaMemcpyAsync(h->bins_dev, a->bins, sizeof(int32_t) * (size_t)a->n_bins, cudaMemcpyHostToDevice, stream));
   const size_t rows = compact ? (size_t)pl.n_owned : (size_t)h->N;
-  if (zero_first) {
+  if (zero_first == RTHX_ZERO_ALL) {
     CU(h, cudaMemsetAsync(counts, 0, sizeof(unsigned long long) * (size_t)a->n_bins * rows * h->N, stream));
     CU(h, cudaMemsetAsync(lost, 0, sizeof(unsigned long long) * (size_t)a->n_bins * h->N, stream));
     *n_launches += 2;
+  } else if (zero_first == RTHX_ZERO_OWN_ROWS && pl.n_owned > 0) {
+    // rows e = rank + y*world: a strided 2-D memset per traced bin (works on peer-mapped memory too)
+    const size_t rb = sizeof(unsigned long long) * (size_t)h->N;
+    for (int b = 0; b < a->n_bins; ++b) {
+      if (compact) {
+        CU(h, cudaMemsetAsync(counts + (size_t)b * pl.n_owned * h->N, 0, rb * pl.n_owned, stream));
+      } else {
+        CU(h, cudaMemset2DAsync(counts + ((size_t)b * h->N + rank) * h->N, rb * world, 0, rb, (size_t)pl.n_owned, stream));
+      }
+      CU(h, cudaMemset2DAsync(lost + (size_t)b * h->N + rank, sizeof(unsigned long long) * world, 0, sizeof(unsigned long long), (size_t)pl.n_owned, stream));
+      *n_launches += 2;
+    }
   }
   TraceParams P;
   fill_params(h, a, pl, rank, world, compact, counts, lost, P);
@@ -575,14 +615,7 @@ int enqueue_pipelined(rthx_handle* h, const rthx_trace_args* a, int rank, int wo
                       LaunchPlan* plan_out, int* n_launches) {
   const int N = h->N;
   const int n_owned = (N - rank + world - 1) / world;
-  const size_t need = (size_t)a->n_bins * (size_t)n_owned * N;
-  if (!h->counts_dev || h->counts_cap < need) {
-    scratch_release(h->device, h->counts_dev);
-    h->counts_dev = nullptr; h->counts_cap = 0;
-    void* ptr = nullptr;
-    CU(h, scratch_acquire(h->device, need * sizeof(unsigned long long), &ptr));
-    h->counts_dev = (unsigned long long*)ptr; h->counts_cap = need;
-  }
+  CU(h, ensure(&h->counts_dev, &h->counts_cap, (size_t)a->n_bins * (size_t)n_owned * N));
   LaunchPlan pl = make_plan(h, a, rank, world);
   // batches: >= ~6 waves of resident blocks each, at most 16
   const int per_sm = std::max(1, trace_kernel_max_blocks_per_sm(pl.block_threads, pl.smem_bytes, pl.hist_in_smem != 0, pl.fast != 0, pl.minb));
@@ -600,7 +633,7 @@ int enqueue_pipelined(rthx_handle* h, const rthx_trace_args* a, int rank, int wo
     const int y0 = (int)((long long)n_owned * b / n_batches), y1 = (int)((long long)n_owned * (b + 1) / n_batches);
     cudaStream_t cs = (b & 1) ? h->stream2 : h->stream;
     LaunchPlan tmp{};
-    int rc = enqueue_trace(h, a, rank, world, /*compact=*/true, h->counts_dev, h->lost_dev, false, with_rec, n_slots, cs, &tmp, n_launches, y0, y1,
+    int rc = enqueue_trace(h, a, rank, world, /*compact=*/true, h->counts_dev, h->lost_dev, RTHX_ZERO_NONE, with_rec, n_slots, cs, &tmp, n_launches, y0, y1,
                            /*upload_bins=*/false);
     if (rc) return rc;
     CU(h, cudaEventRecord(h->bev[b], cs));
@@ -711,7 +744,7 @@ extern "C" int rthx_trace_exchange_device(rthx_handle* h, const rthx_trace_args*
   LaunchPlan pl{};
   int n_launches = 0;
   rc = enqueue_trace(h, a, a->emitter_rank, a->emitter_world, /*compact=*/false, (unsigned long long*)counts_dev,
-                     (unsigned long long*)lost_dev, zero_first != 0, false, 0, (cudaStream_t)stream, &pl, &n_launches);
+                     (unsigned long long*)lost_dev, zero_first, false, 0, (cudaStream_t)stream, &pl, &n_launches);
   if (rc) return rc;
   if (st) { fill_stats(st, pl, a); st->n_launches = n_launches; }
   return RTHX_OK;
@@ -802,6 +835,54 @@ extern "C" int rthx_trace_exchange_multi(rthx_handle** hs, int n, const rthx_tra
     for (auto& p : plans) nbk += p.n_blocks;
     st->n_blocks = nbk;
   }
+  return RTHX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// peer-memory plumbing (CUDA IPC) for the fused flush
+// ---------------------------------------------------------------------------------------------------------------
+#define CUG(call)                                                                                     \
+  do {                                                                                                \
+    cudaError_t e_ = (call);                                                                          \
+    if (e_ != cudaSuccess) return fail(nullptr, RTHX_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+extern "C" int rthx_shared_alloc(int device_id, uint64_t bytes, void** dev_ptr, unsigned char ipc_handle[64]) {
+  if (!dev_ptr || !ipc_handle || bytes == 0) return fail(nullptr, RTHX_ERR_ARG, "rthx_shared_alloc: bad argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle is 64 bytes");
+  CUG(cudaSetDevice(device_id));
+  void* p = nullptr;
+  CUG(cudaMalloc(&p, (size_t)bytes));
+  cudaIpcMemHandle_t hnd;
+  cudaError_t e = cudaIpcGetMemHandle(&hnd, p);
+  if (e != cudaSuccess) { cudaFree(p); return fail(nullptr, RTHX_ERR_CUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e)); }
+  std::memcpy(ipc_handle, &hnd, 64);
+  *dev_ptr = p;
+  return RTHX_OK;
+}
+
+extern "C" int rthx_shared_open(int device_id, const unsigned char ipc_handle[64], void** dev_ptr) {
+  if (!dev_ptr || !ipc_handle) return fail(nullptr, RTHX_ERR_ARG, "rthx_shared_open: bad argument");
+  CUG(cudaSetDevice(device_id));
+  cudaIpcMemHandle_t hnd;
+  std::memcpy(&hnd, ipc_handle, 64);
+  void* p = nullptr;
+  CUG(cudaIpcOpenMemHandle(&p, hnd, cudaIpcMemLazyEnablePeerAccess));
+  *dev_ptr = p;
+  return RTHX_OK;
+}
+
+extern "C" int rthx_shared_close(int device_id, void* dev_ptr) {
+  if (!dev_ptr) return RTHX_OK;
+  CUG(cudaSetDevice(device_id));
+  CUG(cudaIpcCloseMemHandle(dev_ptr));
+  return RTHX_OK;
+}
+
+extern "C" int rthx_shared_free(int device_id, void* dev_ptr) {
+  if (!dev_ptr) return RTHX_OK;
+  CUG(cudaSetDevice(device_id));
+  CUG(cudaFree(dev_ptr));
   return RTHX_OK;
 }
 
