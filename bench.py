@@ -272,7 +272,7 @@ def main():
             "cell_volume", "cell_surf_id", "kappa", "sigma_s", "epsilon", "uniform_beta"))
 
         e2e_dev_ms = []
-        e2e_phases = []   # N > 1: [create, trace+finish, d2h+sync, barrier, close] ms per step
+        e2e_phases = []   # N > 1: [create, trace+finish, d2h+sync, close] ms per step
 
         def e2e_step(seed):
             if world == 1:
@@ -291,7 +291,6 @@ def main():
                 counts_host.copy_(sh.counts, non_blocking=True)
             torch.cuda.synchronize(dev)
             tp.append(time.perf_counter())
-            dist.barrier(device_ids=[local_rank])                     # rank 0 has read the matrix: next step may zero it
             tp.append(time.perf_counter())
             old.close()
             tp.append(time.perf_counter())

@@ -508,6 +508,7 @@ LaunchPlan make_plan(const rthx_handle* h, const rthx_trace_args* a, int rank, i
   const size_t coarse_bytes = h->coarse_fits_smem ? sizeof(CoarseDev) * (size_t)h->n_coarse : 0;
   const size_t hist_bytes = sizeof(uint32_t) * (size_t)h->N, em_bytes = sizeof(double) * 16;
   pl.hist_in_smem = (coarse_bytes + em_bytes + hist_bytes <= h->prop.sharedMemPerBlockOptin) ? 1 : 0;
+  if (const char* ev = std::getenv("RTHX_FORCE_GLOBAL_TALLY")) { if (std::atoi(ev)) pl.hist_in_smem = 0; }   // test knob: the N > ~57k path
   pl.smem_bytes = coarse_bytes + em_bytes + (pl.hist_in_smem ? hist_bytes : 0);
   const long long rows = (long long)pl.n_owned * a->n_bins;
   long long chunks = a->row_chunks;
@@ -540,6 +541,12 @@ void fill_params(const rthx_handle* h, const rthx_trace_args* a, const LaunchPla
   P.coarse_in_smem = h->coarse_fits_smem ? 1 : 0;
   P.hist_in_smem = pl.hist_in_smem;
   P.force_generic = a->locator == RTHX_LOCATOR_GENERIC ? 1 : 0;
+  // a count matrix that lives on another GPU (fused peer flush) is updated with system-scope reductions
+  P.flush_system = 0;
+  cudaPointerAttributes pa;
+  if (counts && cudaPointerGetAttributes(&pa, counts) == cudaSuccess && pa.type == cudaMemoryTypeDevice && pa.device != h->device) P.flush_system = 1;
+  else cudaGetLastError();
+  if (const char* ev = std::getenv("RTHX_FLUSH_SYSTEM")) P.flush_system = std::atoi(ev) ? 1 : 0;
   P.rec_bin = a->rec_bin;
   P.rays_per_emitter = a->rays_per_emitter;
   P.ray_id_offset = a->ray_id_offset;

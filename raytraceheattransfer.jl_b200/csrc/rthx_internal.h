@@ -76,6 +76,7 @@ struct TraceParams {
   int32_t coarse_in_smem;
   int32_t hist_in_smem;
   int32_t force_generic;
+  int32_t flush_system;        // 1: system-scope atomics for the flush (count matrix in peer memory)
   int32_t rec_bin;
   int64_t rays_per_emitter;
   int64_t ray_id_offset;

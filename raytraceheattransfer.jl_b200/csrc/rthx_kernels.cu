@@ -438,6 +438,7 @@ __global__ void __launch_bounds__(256, MINB) trace_exchange_kernel(const __grid_
     // ---- stage 3/4: tally (+ record) -------------------------------------------------------------------------
     if (absorber >= 0) {
       if (HIST_SMEM) atomicAdd(&hist[absorber], 1u);
+      else if (p.flush_system) atomicAdd_system(&count_row[absorber], 1ULL);
       else atomicAdd(&count_row[absorber], 1ULL);
       if (rec_slot >= 0) {
         const size_t s = (size_t)rec_slot * (size_t)p.rays_per_emitter + (size_t)r;
@@ -452,12 +453,18 @@ __global__ void __launch_bounds__(256, MINB) trace_exchange_kernel(const __grid_
 
   // ---- flush --------------------------------------------------------------------------------------------------
   for (int off = 16; off > 0; off >>= 1) n_lost += __shfl_down_sync(0xffffffffu, n_lost, off);
-  if ((threadIdx.x & 31) == 0 && n_lost) atomicAdd(&p.lost[(size_t)bi * N + e], (unsigned long long)n_lost);
+  if ((threadIdx.x & 31) == 0 && n_lost) {
+    if (p.flush_system) atomicAdd_system(&p.lost[(size_t)bi * N + e], (unsigned long long)n_lost);
+    else atomicAdd(&p.lost[(size_t)bi * N + e], (unsigned long long)n_lost);
+  }
   if (HIST_SMEM) {
     __syncthreads();
     for (int i = threadIdx.x; i < N; i += blockDim.x) {
       const uint32_t v = hist[i];
-      if (v) atomicAdd(&count_row[i], (unsigned long long)v);   // red.global.add.u64, result unused
+      if (v) {
+        if (p.flush_system) atomicAdd_system(&count_row[i], (unsigned long long)v);   // red.sys: matrix lives on a peer GPU
+        else atomicAdd(&count_row[i], (unsigned long long)v);                          // red.gpu.global.add.u64, result unused
+      }
     }
   }
 }

@@ -79,7 +79,11 @@ class ShardedTracer:
             self.lost_ptr = self.lost.data_ptr()
 
     def enqueue(self, rays_per_emitter: int, **kw):
-        """Zero + trace kernel on torch's current stream (no collective)."""
+        """Zero + trace kernel on torch's current stream.  In fused mode the matrix is shared, so a leading barrier
+        (stream-ordered behind rank 0's pending reads of the previous result) keeps any rank from clearing its rows
+        while rank 0 is still consuming them."""
+        if self.mode == "fused":
+            dist.barrier(device_ids=[self.device])
         stream = torch.cuda.current_stream(self.device).cuda_stream
         zero = RTHX_ZERO_OWN_ROWS if self.mode == "fused" else RTHX_ZERO_ALL
         return self.tracer.trace_device(rays_per_emitter, self.counts_ptr, self.lost_ptr, stream=stream,

@@ -225,3 +225,40 @@ def test_public_api_crosbie_schrenker(rthx_mod, cuda_lib):
     A = gs.analytical_centerline(11)
     assert np.linalg.norm(S - A) <= 0.05 * max(np.linalg.norm(S), np.linalg.norm(A))
     assert abs(res["energy_error"]) < 1e-4
+
+
+def test_global_tally_fallback_path(rthx_mod, oracle_mod, cuda_lib, monkeypatch):
+    """N > ~57 k elements does not fit a u32 row histogram in 227 KB of shared memory: the kernel then tallies with
+    direct global atomics.  Forced here on a small mesh (RTHX_FORCE_GLOBAL_TALLY) so the oracle can check it."""
+    flat, tr = tracer(rthx_mod, cuda_lib, rthx_mod.meshes.cfg5())
+    ref = oracle_mod.trace(flat, 3000, seed=31)
+    monkeypatch.setenv("RTHX_FORCE_GLOBAL_TALLY", "1")
+    for loc in (0, GENERIC):
+        got = tr.trace(3000, seed=31, locator=loc)
+        assert got["stats"]["hist_in_smem"] == 0
+        check_exact(got, ref, 3000, budget_frac=2e-4)
+
+
+def test_many_coarse_faces_descriptors_in_global_memory(rthx_mod, oracle_mod, cuda_lib):
+    """More coarse faces than fit the 32 KB shared-memory staging area (150 wedges): descriptors are read through
+    L1/L2 and the kernel takes the non-FAST variant."""
+    rtm = rthx_mod.meshes.circle_domain(150, 2, half_hot=False)
+    flat, tr = tracer(rthx_mod, cuda_lib, rtm)
+    assert tr.info["n_affine_faces"] == 150
+    ref = oracle_mod.trace(flat, 4000, seed=32)
+    check_exact(tr.trace(4000, seed=32, locator=GENERIC), ref, 4000)
+    auto = tr.trace(4000, seed=32)
+    check_exact(auto, ref, 4000, budget_frac=5e-4)
+    assert auto["lost"].sum() <= ref["lost"].sum()
+
+
+def test_open_boundary_loses_rays_like_the_reference(rthx_mod, oracle_mod, cuda_lib):
+    """A non-solid coarse edge with no neighbour: the reference's coarse point location fails and the ray is dropped."""
+    rtm = rthx_mod.meshes.square_domain(6, kappa=0.3, solid=(True, False, True, True))
+    flat, tr = tracer(rthx_mod, cuda_lib, rtm)
+    ref = oracle_mod.trace(flat, 10000, seed=33)
+    assert ref["lost"].sum() > 10000
+    for loc in (0, GENERIC):
+        got = tr.trace(10000, seed=33, locator=loc)
+        check_exact(got, ref, 10000)
+        assert n_differing_rays(got["lost"], ref["lost"]) <= 2
