@@ -12,6 +12,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "rthx_internal.h"
@@ -33,6 +34,8 @@ struct DevRes {
   double* rec_pts_dev = nullptr;            size_t rec_pts_cap = 0;
   uint8_t* rec_valid_dev = nullptr;         size_t rec_valid_cap = 0;
   double* peak_dev = nullptr;
+  void* stage[2] = {nullptr, nullptr};      size_t stage_cap = 0;      // pinned staging for pageable destinations
+  cudaEvent_t cev[2] = {nullptr, nullptr};
   bool valid = false;
 };
 
@@ -63,6 +66,8 @@ void devres_free(DevRes& r) {
   cudaFree(r.arena); cudaFree(r.counts_dev); cudaFree(r.rec_pts_dev); cudaFree(r.rec_valid_dev); cudaFree(r.peak_dev);
   for (auto& e : r.ev) if (e) cudaEventDestroy(e);
   for (auto& e : r.bev) if (e) cudaEventDestroy(e);
+  for (auto& e : r.cev) if (e) cudaEventDestroy(e);
+  for (auto& sp : r.stage) if (sp) cudaFreeHost(sp);
   if (r.stream) cudaStreamDestroy(r.stream);
   if (r.stream2) cudaStreamDestroy(r.stream2);
   if (r.copy_stream) cudaStreamDestroy(r.copy_stream);
@@ -76,6 +81,7 @@ cudaError_t devres_create(DevRes& r) {
   if ((e = cudaStreamCreateWithFlags(&r.copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return e;
   for (auto& ev : r.ev) if ((e = cudaEventCreate(&ev)) != cudaSuccess) return e;
   for (auto& ev : r.bev) if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return e;
+  for (auto& ev : r.cev) if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return e;
   r.valid = true;
   return cudaSuccess;
 }
@@ -614,12 +620,12 @@ int enqueue_trace(rthx_handle* h, const rthx_trace_args* a, int rank, int world,
   return RTHX_OK;
 }
 
-// Host-output trace of one handle, pipelined: the owned rows are cut into batches whose kernels alternate between two
+// Host-output trace of one handle, pipelined (pipeline_launch + pipeline_copy): the owned rows are cut into batches whose kernels alternate between two
 // compute streams (so the tail of one batch overlaps the head of the next) and whose device->host copies run on a third
 // stream as soon as the batch's kernel has finished.  All work is enqueued; the caller synchronises copy_stream.
 //   ev[0] start, ev[1] first kernel start, ev[2] last kernel end, ev[3] last copy end.
-int enqueue_pipelined(rthx_handle* h, const rthx_trace_args* a, int rank, int world, uint64_t* counts_out, bool with_rec, int n_slots,
-                      LaunchPlan* plan_out, int* n_launches) {
+int pipeline_launch(rthx_handle* h, const rthx_trace_args* a, int rank, int world, bool with_rec, int n_slots,
+                    LaunchPlan* plan_out, int* n_launches, int* n_batches_out) {
   const int N = h->N;
   const int n_owned = (N - rank + world - 1) / world;
   CU(h, ensure(&h->counts_dev, &h->counts_cap, (size_t)a->n_bins * (size_t)n_owned * N));
@@ -644,23 +650,94 @@ int enqueue_pipelined(rthx_handle* h, const rthx_trace_args* a, int rank, int wo
                            /*upload_bins=*/false);
     if (rc) return rc;
     CU(h, cudaEventRecord(h->bev[b], cs));
-    CU(h, cudaStreamWaitEvent(h->copy_stream, h->bev[b], 0));
-    if (y1 > y0)
-      for (int bin = 0; bin < a->n_bins; ++bin) {
-        const unsigned long long* src = h->counts_dev + ((size_t)bin * n_owned + y0) * N;
-        if (world == 1)
-          CU(h, cudaMemcpyAsync(counts_out + ((size_t)bin * N + y0) * N, src, sizeof(uint64_t) * (size_t)(y1 - y0) * N, cudaMemcpyDeviceToHost, h->copy_stream));
-        else
-          CU(h, cudaMemcpy2DAsync(counts_out + ((size_t)bin * N + rank + (size_t)y0 * world) * N, sizeof(uint64_t) * (size_t)world * N, src,
-                                  sizeof(uint64_t) * (size_t)N, sizeof(uint64_t) * (size_t)N, (size_t)(y1 - y0), cudaMemcpyDeviceToHost, h->copy_stream));
-      }
   }
   // last kernel end = both compute streams drained
   CU(h, cudaEventRecord(h->bev[16], h->stream2));
   CU(h, cudaStreamWaitEvent(h->stream, h->bev[16], 0));
   CU(h, cudaEventRecord(h->ev[2], h->stream));
-  CU(h, cudaStreamWaitEvent(h->copy_stream, h->ev[2], 0));
   *plan_out = pl;
+  *n_batches_out = n_batches;
+  return RTHX_OK;
+}
+
+void parallel_memcpy(void* dst, const void* src, size_t bytes) {
+  const int nt = bytes >= (size_t(16) << 20) ? 4 : 1;
+  if (nt == 1) { std::memcpy(dst, src, bytes); return; }
+  std::vector<std::thread> th;
+  const size_t per = ((bytes / nt) + 4095) & ~size_t(4095);
+  for (int t = 0; t < nt; ++t) {
+    const size_t off = (size_t)t * per;
+    if (off >= bytes) break;
+    const size_t n = std::min(per, bytes - off);
+    th.emplace_back([=] { std::memcpy((char*)dst + off, (const char*)src + off, n); });
+  }
+  for (auto& t : th) t.join();
+}
+
+// Second half of the pipeline: copy each batch's rows to the caller's matrix as soon as its kernel has finished.
+//   pinned / registered destination : cudaMemcpy(2D)Async straight into it on copy_stream (nothing blocks the host);
+//   pageable destination (e.g. a Julia Array): DMA into two pinned staging buffers, the host thread moves batch b-1 to
+//       the caller's memory while batch b is in flight (a pageable cudaMemcpyAsync would block the host per batch and
+//       crawl at ~4 GB/s).
+int pipeline_copy(rthx_handle* h, const rthx_trace_args* a, int rank, int world, uint64_t* counts_out, int n_batches) {
+  const int N = h->N;
+  const int n_owned = (N - rank + world - 1) / world;
+  cudaPointerAttributes pa;
+  bool pinned = cudaPointerGetAttributes(&pa, counts_out) == cudaSuccess && (pa.type == cudaMemoryTypeHost || pa.type == cudaMemoryTypeManaged);
+  cudaGetLastError();
+  if (const char* ev = std::getenv("RTHX_FORCE_STAGING")) { if (std::atoi(ev)) pinned = false; }
+  const size_t row_bytes = sizeof(uint64_t) * (size_t)N;
+  auto batch_rows = [&](int b, int& y0, int& y1) { y0 = (int)((long long)n_owned * b / n_batches); y1 = (int)((long long)n_owned * (b + 1) / n_batches); };
+  if (pinned) {
+    for (int b = 0; b < n_batches; ++b) {
+      int y0, y1; batch_rows(b, y0, y1);
+      CU(h, cudaStreamWaitEvent(h->copy_stream, h->bev[b], 0));
+      for (int bin = 0; bin < a->n_bins && y1 > y0; ++bin) {
+        const unsigned long long* src = h->counts_dev + ((size_t)bin * n_owned + y0) * N;
+        if (world == 1)
+          CU(h, cudaMemcpyAsync(counts_out + ((size_t)bin * N + y0) * N, src, row_bytes * (size_t)(y1 - y0), cudaMemcpyDeviceToHost, h->copy_stream));
+        else
+          CU(h, cudaMemcpy2DAsync(counts_out + ((size_t)bin * N + rank + (size_t)y0 * world) * N, row_bytes * world, src, row_bytes, row_bytes,
+                                  (size_t)(y1 - y0), cudaMemcpyDeviceToHost, h->copy_stream));
+      }
+    }
+    CU(h, cudaStreamWaitEvent(h->copy_stream, h->ev[2], 0));
+    return RTHX_OK;
+  }
+  // staged path
+  size_t max_rows = 0;
+  for (int b = 0; b < n_batches; ++b) { int y0, y1; batch_rows(b, y0, y1); max_rows = std::max(max_rows, (size_t)(y1 - y0)); }
+  const size_t stage_bytes = std::max<size_t>(1, max_rows * a->n_bins * row_bytes);
+  if (h->stage_cap < stage_bytes) {
+    for (auto& sp : h->stage) { if (sp) cudaFreeHost(sp); sp = nullptr; }
+    h->stage_cap = 0;
+    for (auto& sp : h->stage) CU(h, cudaMallocHost(&sp, stage_bytes));
+    h->stage_cap = stage_bytes;
+  }
+  auto unload = [&](int b) {   // staging[b&1] -> caller's matrix
+    int y0, y1; batch_rows(b, y0, y1);
+    const size_t rows = (size_t)(y1 - y0);
+    const char* st = (const char*)h->stage[b & 1];
+    for (int bin = 0; bin < a->n_bins && rows; ++bin) {
+      const char* src = st + (size_t)bin * rows * row_bytes;
+      if (world == 1) parallel_memcpy(counts_out + ((size_t)bin * N + y0) * N, src, rows * row_bytes);
+      else
+        for (size_t r = 0; r < rows; ++r) std::memcpy(counts_out + ((size_t)bin * N + rank + (size_t)(y0 + r) * world) * N, src + r * row_bytes, row_bytes);
+    }
+  };
+  for (int b = 0; b < n_batches; ++b) {
+    int y0, y1; batch_rows(b, y0, y1);
+    const size_t rows = (size_t)(y1 - y0);
+    CU(h, cudaStreamWaitEvent(h->copy_stream, h->bev[b], 0));
+    for (int bin = 0; bin < a->n_bins && rows; ++bin)
+      CU(h, cudaMemcpyAsync((char*)h->stage[b & 1] + (size_t)bin * rows * row_bytes, h->counts_dev + ((size_t)bin * n_owned + y0) * N, rows * row_bytes,
+                            cudaMemcpyDeviceToHost, h->copy_stream));
+    CU(h, cudaEventRecord(h->cev[b & 1], h->copy_stream));
+    if (b >= 1) { CU(h, cudaEventSynchronize(h->cev[(b - 1) & 1])); unload(b - 1); }
+  }
+  CU(h, cudaEventSynchronize(h->cev[(n_batches - 1) & 1]));
+  unload(n_batches - 1);
+  CU(h, cudaStreamWaitEvent(h->copy_stream, h->ev[2], 0));
   return RTHX_OK;
 }
 
@@ -718,7 +795,10 @@ extern "C" int rthx_trace_exchange(rthx_handle* h, const rthx_trace_args* a, uin
   if (rc) return rc;
   LaunchPlan pl{};
   if (a->emitter_world > 1) std::memset(counts_out, 0, sizeof(uint64_t) * (size_t)a->n_bins * N * N);   // rows of other ranks
-  rc = enqueue_pipelined(h, a, a->emitter_rank, a->emitter_world, counts_out, rec != nullptr, n_slots, &pl, &n_launches);
+  int n_batches = 1;
+  rc = pipeline_launch(h, a, a->emitter_rank, a->emitter_world, rec != nullptr, n_slots, &pl, &n_launches, &n_batches);
+  if (rc) return rc;
+  rc = pipeline_copy(h, a, a->emitter_rank, a->emitter_world, counts_out, n_batches);
   if (rc) return rc;
   std::vector<uint64_t> lost_host((size_t)a->n_bins * N);
   CU(h, cudaMemcpyAsync(lost_host.data(), h->lost_dev, sizeof(uint64_t) * lost_host.size(), cudaMemcpyDeviceToHost, h->copy_stream));
@@ -767,7 +847,7 @@ extern "C" int rthx_trace_exchange_multi(rthx_handle** hs, int n, const rthx_tra
   const int N = h0->N;
   for (int i = 0; i < n; ++i) if (!hs[i] || hs[i]->N != N || hs[i]->n_bands != h0->n_bands) return fail(h0, RTHX_ERR_ARG, "trace_multi: handles differ");
   std::vector<LaunchPlan> plans(n);
-  std::vector<int> slots(n, 0);
+  std::vector<int> slots(n, 0), batches(n, 1);
   int n_launches = 0;
   // enqueue on every device first, then drain: the devices run concurrently
   if (n > 1) std::memset(counts_out, 0, sizeof(uint64_t) * (size_t)a->n_bins * N * N);
@@ -777,7 +857,13 @@ extern "C" int rthx_trace_exchange_multi(rthx_handle** hs, int n, const rthx_tra
     CU(h0, cudaEventRecord(h->ev[0], h->stream));
     rc = prepare_recorder(h, a, rec, &slots[i], h->stream);
     if (rc) return fail(h0, rc, h->err);
-    rc = enqueue_pipelined(h, a, i, n, counts_out, rec != nullptr, slots[i], &plans[i], &n_launches);
+    rc = pipeline_launch(h, a, i, n, rec != nullptr, slots[i], &plans[i], &n_launches, &batches[i]);
+    if (rc) return fail(h0, rc, h->err);
+  }
+  for (int i = 0; i < n; ++i) {   // every device is busy by now: drain the copies device by device
+    rthx_handle* h = hs[i];
+    CU(h0, cudaSetDevice(h->device));
+    rc = pipeline_copy(h, a, i, n, counts_out, batches[i]);
     if (rc) return fail(h0, rc, h->err);
     CU(h0, cudaEventRecord(h->ev[3], h->copy_stream));
   }

@@ -93,6 +93,26 @@ __constant__ double c_log[9] = {    // fdlibm e_log.c: Lg1..Lg7, ln2_hi, ln2_lo
     1.818357216161805012e-01, 1.531383769920937332e-01, 1.479819860511658591e-01,
     6.93147180369123816490e-01, 1.90821492927058770002e-10};
 
+// sqrt(x) and a/b for well-scaled positive normal operands (variates in (0,1), geometric ratios): MUFU seed + Newton,
+// without libdevice's special-case branch (which splits the basic block and blocks instruction interleaving).
+// Both are accurate to <= 1 ulp; neither is used where x or b can be 0, Inf or subnormal.
+__device__ __forceinline__ double sqrt_pos(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double e = fma(-x, y * y, 1.0);                 // 1 - x y^2
+  y = fma(fma(e, 0.375, 0.5), y * e, y);                // y (1 + e/2 + 3 e^2/8)
+  const double g = x * y;
+  return fma(fma(-g, g, x), 0.5 * y, g);
+}
+__device__ __forceinline__ double div_pos(double a, double b) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+  r = fma(r, fma(-b, r, 1.0), r);
+  r = fma(r, fma(-b, r, 1.0), r);
+  const double q = a * r;
+  return fma(r, fma(-b, q, a), q);
+}
+
 // cos(2 pi R) for R in (0,1): with x = 2R - 1 in (-1,1), cos(2 pi R) = -cos(pi x) = sin(pi (|x| - 1/2)); branch-free.
 __device__ __forceinline__ double cos2pi_unit(double R) {
   const double z = fabs(fma(R, 2.0, -1.0)) - 0.5;
@@ -151,7 +171,7 @@ __device__ __forceinline__ double dist_fast(const CoarseDev& f, double px, doubl
     const bool take0 = ok0 & (!ok1 | (l < r) | ((l == r) & (e0 < e1)));
     k = take0 ? e0 : e1;
     const double an = take0 ? an0 : an1, ad = take0 ? ad0 : ad1;
-    return (ok0 | ok1) ? an / ad : CUDART_INF;
+    return (ok0 | ok1) ? div_pos(an, ad) : CUDART_INF;
   }
   double bn = 1.0, bd = 0.0;
   int bk = 0;
@@ -166,7 +186,7 @@ __device__ __forceinline__ double dist_fast(const CoarseDev& f, double px, doubl
     bk = better ? i : bk;
   }
   k = bk;
-  return bd > 0.0 ? bn / bd : CUDART_INF;
+  return bd > 0.0 ? div_pos(bn, bd) : CUDART_INF;
 }
 
 // Faithful distToSurface2D on an arbitrary polygon of the generic tables (used by the generic locator for the
@@ -340,7 +360,7 @@ __global__ void __launch_bounds__(256, MINB) trace_exchange_kernel(const __grid_
       // lambertSample2D: Float32 variates / sqrt / square, the rest in Float64
       const float cosT = __fsqrt_rn(u23(w0.y));
       const float cos2 = __fmul_rn(cosT, cosT);
-      const double sinT = sqrt(1.0 - (double)cos2);
+      const double sinT = FAST ? sqrt_pos(1.0 - (double)cos2) : sqrt(1.0 - (double)cos2);
       const double xdir = sinT * (FAST ? cos2pi_unit((double)u23(w0.z)) : cospi(2.0 * (double)u23(w0.z)));
       const double zdir = (double)cosT;
       dx = s_em[4] * xdir + s_em[6] * zdir;
@@ -348,7 +368,7 @@ __global__ void __launch_bounds__(256, MINB) trace_exchange_kernel(const __grid_
       R_S = u52(w1.x, w1.y, p.k_u52);
     } else {
       const double R1 = u32d(w0.x, p.k_u32), R2 = u32d(w0.y, p.k_u32);
-      const double sq = sqrt(R1);
+      const double sq = FAST ? sqrt_pos(R1) : sqrt(R1);
       // uniform point of triangle (V0,V1,V2): V0 + sqrt(R1)(1-R2)(V1-V0) + sqrt(R1) R2 (V2-V0), emitVolumeRay2D.jl:9,12
       const double* tri = s_em + ((u32d(w0.z, p.k_u32) < s_em[14]) ? 0 : 6);
       const double a2 = sq * R2, a1 = sq - a2;
@@ -356,7 +376,7 @@ __global__ void __launch_bounds__(256, MINB) trace_exchange_kernel(const __grid_
       py = fma(a2, tri[5], fma(a1, tri[3], tri[1]));
       // theta = acos(1-2R): cos(theta) = 1-2R, sin(theta) = 2 sqrt(R(1-R)) (algebraically identical)
       const double Rt = u52(w1.x, w1.y, p.k_u52);
-      const double sinT = 2.0 * sqrt(Rt * (1.0 - Rt));
+      const double sinT = 2.0 * (FAST ? sqrt_pos(Rt * (1.0 - Rt)) : sqrt(Rt * (1.0 - Rt)));
       const double phiR = u32d(w0.w, p.k_u32);
       dx = sinT * (FAST ? cos2pi_unit(phiR) : cospi(2.0 * phiR));
       dy = fma(Rt, -2.0, 1.0);
