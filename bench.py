@@ -49,6 +49,9 @@ def parse_args():
     return ap.parse_args()
 
 
+# DRAM bytes per launch of trace_exchange_kernel measured by ncu (profiles/r1d_trace_exchange_metrics.csv)
+NCU_DRAM_BYTES_PER_LAUNCH = {"cfg3": 895565312 + 833359872}
+
 DEFAULT_RAYS = {"cfg1": 1e6, "cfg2": 1e8, "cfg3": 1e10, "cfg4": 1e8, "cfg5": 1e9}
 
 
@@ -337,7 +340,11 @@ def main():
     achieved = kernel_rays_per_s * A / 1e12
     hbm_bytes_per_ray = 8.0 * N * N * nb / world / max(1, traced_per_step / world)
     roofline = {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                "frac": achieved / fp64_peak if fp64_peak else None, "traffic": None,
+                "frac": achieved / fp64_peak if fp64_peak else None,
+                "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(args.workload),
+                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture "
+                                "profiles/r1d_trace_exchange_metrics.csv (cfg3; the reductions read-modify-write the zeroed "
+                                "8*N*N-byte count matrix once, independent of the ray count)",
                 "kernel": "trace_exchange_kernel", "kernel_ms": kernel_ms, "kernel_rays_per_s": kernel_rays_per_s,
                 "flop_per_ray": A,
                 "peak_source": "FP64 DFMA-chain micro-benchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
