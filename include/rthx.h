@@ -46,7 +46,18 @@ enum {
 /* trace modes.  FIRST_INTERACTION is what method=:exchange computes (traceRay.jl:20-147): every ray
  * stops at its first gas-extinction event or solid-wall hit; albedo and wall reflectivity are applied
  * algebraically later by the unchanged host solver. */
-enum { RTHX_FIRST_INTERACTION = 0 };
+enum {
+  RTHX_FIRST_INTERACTION = 0,
+  /* Optional total-exchange mode (the analogue of method=:direct's traceSingleRay.jl:7-81 without re-emission): after
+   * every first interaction the ray is absorbed with probability 1 - omega (gas, omega = sigma_s/(kappa+sigma_s)) or
+   * epsilon (wall); otherwise it scatters isotropically (isotropicScatter2D.jl:1-4) or is reflected — diffusely about
+   * the inward wall normal, or specularly — and is traced on to its next interaction.  counts[i][j] then is the number
+   * of rays of emitter i finally ABSORBED by element j.  NOT what method=:exchange feeds to the host solver (that
+   * applies albedo and reflectivity algebraically); equals the closure (I - F B)^-1 F (I - B) of the first-interaction
+   * F up to discretisation.  Rays still alive after 1000 events face the reference's Russian roulette (:11). */
+  RTHX_MULTI_BOUNCE = 1,
+  RTHX_MULTI_BOUNCE_SPECULAR = 2
+};
 
 /* point-location strategy (rthx_trace_args.locator) */
 enum {
@@ -82,8 +93,8 @@ typedef struct rthx_mesh {
                                                      (surface_mapping of RayTracingDomain2D.jl:57-76) */
   const double*  kappa;         /* [n_bands*n_cells] kappa_g   */
   const double*  sigma_s;       /* [n_bands*n_cells] sigma_s_g */
-  const double*  epsilon;       /* [n_bands*n_surfaces] wall emissivity; may be NULL (unused by
-                                                     FIRST_INTERACTION) */
+  const double*  epsilon;       /* [n_bands*n_surfaces] wall emissivity; may be NULL (only MULTI_BOUNCE
+                                                     reads it) */
   const double*  uniform_beta;  /* [n_bands]         uniform_across_bin (validateDomainUniformity.jl:57-85):
                                                      common beta, or -1 when cells disagree */
 } rthx_mesh;
@@ -93,12 +104,14 @@ typedef struct rthx_mesh {
  * (getGlobalIndex2D.jl:5-12).  N = Ns + n_cells.
  *
  * RNG contract (the reference is unseeded; this is new): Philox4x32-10, key = seed,
- * counter = (ray_id lo, ray_id hi, emitter element index, (band << 8) | call#), ray_id in
+ * counter = (ray_id lo, ray_id hi, emitter element index, (band << 16) | call#), ray_id in
  * [ray_id_offset, ray_id_offset + rays_per_emitter); two calls per ray, words w0..w3 (call 0), w4..w7 (call 1).
  *   surface emitter: w0 position (32-bit uniform), w1 cos(theta) and w2 psi (23-bit Float32 uniforms, as
  *                    lambertSample2D.jl:2,5 quantises them), (w4,w5) free path (52-bit);
  *   volume emitter : w0 R_1, w1 R_2, w2 triangle selector (quads only), w3 phi (32-bit), (w4,w5) theta (52-bit),
  *                    (w6,w7) free path / optical depth (52-bit).
+ *   MULTI_BOUNCE event n (n = 0,1,...): calls 2+2n and 3+2n — decision, azimuth, cos(theta) (walls), roulette (32/23-bit),
+ *                    polar angle and next free path (52-bit).
  *   uniforms: (w + 0.5) 2^-32, ((w >> 9) + 0.5) 2^-23, ((hi:lo >> 12) + 0.5) 2^-52 — all in the open interval (0,1).
  * Results are a pure function of
  * (mesh, seed, ray_id range, nudge): independent of thread-block shape, chunking and GPU count.
@@ -110,7 +123,7 @@ typedef struct rthx_trace_args {
   double   nudge;               /* 1e4*eps(Float64) by default, multiDispatchRayTrace2D.jl:10 */
   int32_t  n_bins;              /* number of bands traced in this call (batched in the grid) */
   const int32_t* bins;          /* [n_bins] band indices */
-  int32_t  mode;                /* RTHX_FIRST_INTERACTION */
+  int32_t  mode;                /* RTHX_FIRST_INTERACTION (method=:exchange) | RTHX_MULTI_BOUNCE[_SPECULAR] */
   int32_t  locator;             /* RTHX_LOCATOR_* */
   int32_t  emitter_rank;        /* this call traces emitters e with e % emitter_world == emitter_rank; */
   int32_t  emitter_world;       /*   rows of other emitters are left zero.  (0,1) = all emitters */

@@ -65,11 +65,11 @@ def lib():
 
 
 def trace(flat, rays_per_emitter, seed=0x5EED0001, bins=(0,), nudge=None, n_threads=0, rec_ids=None, rec_bin=0,
-          ray_id_offset=0, emitter_rank=0, emitter_world=1):
+          ray_id_offset=0, emitter_rank=0, emitter_world=1, mode=0):
     """Run the oracle on a FlatMesh.  Returns dict(counts[nb,N,N] u64, lost[nb,N] u64, stats, origins, endpoints)."""
     args, keep = rthx.make_trace_args(rays_per_emitter, seed=seed, bins=bins, nudge=nudge, rec_ids=rec_ids,
                                       rec_bin=rec_bin, ray_id_offset=ray_id_offset, emitter_rank=emitter_rank,
-                                      emitter_world=emitter_world)
+                                      emitter_world=emitter_world, mode=mode)
     N = flat.n_elements
     nb = len(bins)
     counts = np.zeros((nb, N, N), np.uint64)

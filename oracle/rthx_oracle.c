@@ -83,8 +83,21 @@ static void draws_init(draws_t* d, uint64_t seed, uint64_t ray_id, uint32_t emit
   d->ctr[1] = (uint32_t)(ray_id >> 32);
   d->ctr[2] = emitter;
   for (int call = 0; call < ncalls; ++call) {
-    d->ctr[3] = (band << 8) | (uint32_t)call;
+    d->ctr[3] = (band << 16) | (uint32_t)call;
     rthx_oracle_philox4x32_10(d->ctr, d->key, d->w + 4 * call);
+  }
+}
+
+/* the two Philox calls of MULTI_BOUNCE event n: call# 2+2n and 3+2n */
+static void draws_event(draws_t* d, uint64_t seed, uint64_t ray_id, uint32_t emitter, uint32_t band, int event) {
+  d->key[0] = (uint32_t)seed;
+  d->key[1] = (uint32_t)(seed >> 32);
+  d->ctr[0] = (uint32_t)ray_id;
+  d->ctr[1] = (uint32_t)(ray_id >> 32);
+  d->ctr[2] = emitter;
+  for (int k = 0; k < 2; ++k) {
+    d->ctr[3] = (band << 16) | (uint32_t)(2 + 2 * event + k);
+    rthx_oracle_philox4x32_10(d->ctr, d->key, d->w + 4 * k);
   }
 }
 
@@ -479,24 +492,66 @@ static int shoot(const omesh_t* o, const double* beta_all, const rthx_trace_args
     R_S = rthx_oracle_u52(d.w[6], d.w[7]);
   }
   const double* beta_band = beta_all + (size_t)band * m->n_cells;
-  hit_t h;
-  if (m->uniform_beta[band] > -0.1) /* traceRay.jl:4-12: beta of fine_mesh[1][1] */
-    h = trace_uniform(o, r, beta_band[0], a->nudge, c, R_S);
-  else
-    h = trace_variable(o, r, beta_band, a->nudge, c, R_S);
+  const int uniform = m->uniform_beta[band] > -0.1; /* traceRay.jl:4-12: uniform bins use beta of fine_mesh[1][1] */
+  hit_t h = uniform ? trace_uniform(o, r, beta_band[0], a->nudge, c, R_S) : trace_variable(o, r, beta_band, a->nudge, c, R_S);
   if (ray_out) *ray_out = r;
-  if (hit_out) *hit_out = h;
-  if (!h.ok) return -1;
-  const int gh = m->fine_off[h.coarse] + h.fine;
-  if (h.wall > 0) return m->cell_surf_id[gh * 4 + (h.wall - 1)]; /* -1 if that fine wall is not solid */
-  return o->ns + gh;
+  int crossings = h.crossings;
+  /* RTHX_MULTI_BOUNCE: traceSingleRay.jl:7-81 without the re-emission branches — absorb, scatter or reflect at every
+   * interaction until the ray is absorbed. */
+  for (int event = 0;; ++event) {
+    if (!h.ok) { if (hit_out) { *hit_out = h; hit_out->crossings = crossings; } return -1; }
+    const int gh = m->fine_off[h.coarse] + h.fine;
+    const int absorber = h.wall > 0 ? m->cell_surf_id[gh * 4 + (h.wall - 1)] : o->ns + gh; /* getGlobalIndex2D.jl:1-14 */
+    if (hit_out) { *hit_out = h; hit_out->crossings = crossings; }
+    if (a->mode == RTHX_FIRST_INTERACTION || absorber < 0) return absorber; /* -1: that fine wall is not solid */
+    if (event >= 16000) return -1;
+    draws_event(&d, a->seed, ray_id, (uint32_t)e, (uint32_t)band, event);
+    if (event >= 1000 && rthx_oracle_u32(d.w[3]) > 0.8) return -1; /* Russian roulette, traceSingleRay.jl:11 */
+    const double dec = rthx_oracle_u32(d.w[0]);
+    ray_t r2;
+    r2.px = h.px; r2.py = h.py; /* origin = end_point (:45,:64) */
+    if (h.wall == 0) {
+      const size_t ib = (size_t)band * m->n_cells + gh;
+      const double beta = m->kappa[ib] + m->sigma_s[ib];
+      const double omega = beta > 0 ? m->sigma_s[ib] / beta : 0.0;
+      if (!(dec < omega)) return absorber; /* :61 */
+      /* isotropicScatter2D.jl:1-4 */
+      const double theta = acos(2 * rthx_oracle_u52(d.w[4], d.w[5]) - 1);
+      const double phi = (2.0 * M_PI) * rthx_oracle_u32(d.w[1]);
+      r2.dx = sin(theta) * cos(phi);
+      r2.dy = cos(theta);
+    } else {
+      const double eps = m->epsilon ? m->epsilon[(size_t)band * o->ns + absorber] : 1.0;
+      if (dec < eps) return absorber; /* :28 */
+      const poly_t* cell = &o->fine[h.coarse].faces[h.fine];
+      const double nx = -cell->nx[h.wall - 1], ny = -cell->ny[h.wall - 1]; /* inward normal of the wall */
+      if (a->mode == RTHX_MULTI_BOUNCE_SPECULAR) {
+        const double dn = r.dx * nx + r.dy * ny;
+        r2.dx = r.dx - 2 * dn * nx;
+        r2.dy = r.dy - 2 * dn * ny;
+      } else {
+        /* sampleReflectionDirection2D.jl:5-16 with lambertSample2D.jl:1-11: x-axis (n.y, -n.x), y-axis n */
+        const float cosTheta = sqrtf(rthx_oracle_u23(d.w[2]));
+        const float cos2 = cosTheta * cosTheta;
+        const double sinTheta = sqrt(1.0 - (double)cos2);
+        const double xdir = sinTheta * cos((2.0 * M_PI) * (double)rthx_oracle_u23(d.w[1]));
+        const double zdir = (double)cosTheta;
+        r2.dx = ny * xdir + nx * zdir;
+        r2.dy = -nx * xdir + ny * zdir;
+      }
+    }
+    r = r2;
+    R_S = rthx_oracle_u52(d.w[6], d.w[7]);
+    h = uniform ? trace_uniform(o, r, beta_band[0], a->nudge, h.coarse, R_S) : trace_variable(o, r, beta_band, a->nudge, h.coarse, R_S);
+    crossings += h.crossings;
+  }
 }
 
 static int check_args(const rthx_mesh* m, const rthx_trace_args* a) {
   if (!m || !a || a->rays_per_emitter < 0 || a->n_bins < 1 || !a->bins) return 1;
   for (int b = 0; b < a->n_bins; ++b) if (a->bins[b] < 0 || a->bins[b] >= m->n_bands) return 1;
   if (a->emitter_world < 1 || a->emitter_rank < 0 || a->emitter_rank >= a->emitter_world) return 1;
-  if (a->mode != RTHX_FIRST_INTERACTION) return 1;
+  if (a->mode != RTHX_FIRST_INTERACTION && a->mode != RTHX_MULTI_BOUNCE && a->mode != RTHX_MULTI_BOUNCE_SPECULAR) return 1;
   return 0;
 }
 

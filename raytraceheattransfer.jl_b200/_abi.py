@@ -5,6 +5,8 @@ import ctypes as C
 
 RTHX_OK = 0
 RTHX_FIRST_INTERACTION = 0
+RTHX_MULTI_BOUNCE = 1
+RTHX_MULTI_BOUNCE_SPECULAR = 2
 RTHX_LOCATOR_AUTO = 0
 RTHX_LOCATOR_GENERIC = 1
 RTHX_ZERO_NONE, RTHX_ZERO_ALL, RTHX_ZERO_OWN_ROWS = 0, 1, 2

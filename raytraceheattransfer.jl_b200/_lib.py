@@ -103,7 +103,8 @@ def load_library():
 def make_trace_args(rays_per_emitter: int, seed: int = DEFAULT_SEED, bins: Sequence[int] = (0,),
                     nudge: Optional[float] = None, rec_ids: Optional[Sequence[int]] = None, rec_bin: int = 0,
                     ray_id_offset: int = 0, emitter_rank: int = 0, emitter_world: int = 1,
-                    locator: int = RTHX_LOCATOR_AUTO, block_threads: int = 0, row_chunks: int = 0):
+                    locator: int = RTHX_LOCATOR_AUTO, block_threads: int = 0, row_chunks: int = 0,
+                    mode: int = RTHX_FIRST_INTERACTION):
     """Build an rthx_trace_args; returns (args, keepalive) — keep `keepalive` referenced during the call."""
     a = rthx_trace_args()
     a.rays_per_emitter = int(rays_per_emitter)
@@ -113,7 +114,7 @@ def make_trace_args(rays_per_emitter: int, seed: int = DEFAULT_SEED, bins: Seque
     bins_arr = np.ascontiguousarray(bins, dtype=np.int32)
     a.n_bins = len(bins_arr)
     a.bins = bins_arr.ctypes.data_as(c_i32p)
-    a.mode = RTHX_FIRST_INTERACTION
+    a.mode = int(mode)
     a.locator = int(locator)
     a.emitter_rank = int(emitter_rank)
     a.emitter_world = int(emitter_world)

@@ -44,6 +44,7 @@ struct rthx_handle : DevRes {
   cudaDeviceProp prop{};
   int n_coarse = 0, n_cells = 0, n_bands = 0, ns = 0, N = 0, n_affine = 0;
   bool coarse_fits_smem = false;
+  bool has_eps = false;
   bool fast_ok = false;        // every coarse face affine + complete neighbour table + descriptors fit in smem
   size_t mesh_bytes = 0;
   TraceParams base{};          // mesh pointers filled once
@@ -431,6 +432,11 @@ extern "C" int rthx_create(rthx_handle** out, const rthx_mesh* m, int device_id)
   std::vector<double> mid(m->cell_mid, m->cell_mid + 2 * (size_t)ncell), vol(m->cell_volume, m->cell_volume + ncell);
   std::vector<int32_t> surf(m->cell_surf_id, m->cell_surf_id + 4 * (size_t)ncell);
   if (lattice.empty()) lattice.push_back(-1);
+  // MULTI_BOUNCE properties: scattering albedo per (band, cell) — 0 where beta = 0 — and emissivity per (band, surface)
+  std::vector<double> omega((size_t)nb * ncell), epsv;
+  for (size_t i = 0; i < omega.size(); ++i) omega[i] = beta[i] > 0.0 ? m->sigma_s[i] / beta[i] : 0.0;
+  if (m->epsilon) epsv.assign(m->epsilon, m->epsilon + (size_t)nb * ns);
+  h->has_eps = m->epsilon != nullptr || ns == 0;
 
   TraceParams& P = h->base;
   std::memset(&P, 0, sizeof(P));
@@ -438,7 +444,7 @@ extern "C" int rthx_create(rthx_handle** out, const rthx_mesh* m, int device_id)
   const size_t o_coarse = A.add(coarse), o_sets = A.add(sets), o_bstart = A.add(bstart), o_bitems = A.add(bitems),
                o_nv = A.add(poly_nv), o_pvx = A.add(pvx), o_pvy = A.add(pvy), o_pnx = A.add(pnx), o_pny = A.add(pny),
                o_mid = A.add(mid), o_vol = A.add(vol), o_surf = A.add(surf), o_beta = A.add(beta), o_ub = A.add(ub),
-               o_lat = A.add(lattice), o_ec = A.add(em_cell), o_ew = A.add(em_wall), o_eco = A.add(em_coarse),
+               o_lat = A.add(lattice), o_omega = A.add(omega), o_eps = A.add(epsv), o_ec = A.add(em_cell), o_ew = A.add(em_wall), o_eco = A.add(em_coarse),
                o_bins = A.add(std::vector<int32_t>(), (size_t)nb * 4 + 16), o_rec = A.add(std::vector<int32_t>(), (size_t)N),
                o_lost = A.add(std::vector<unsigned long long>(), ((size_t)nb * 4 + 16) * (size_t)N);
   if (h->arena_cap < A.host.size()) {
@@ -459,6 +465,7 @@ extern "C" int rthx_create(rthx_handle** out, const rthx_mesh* m, int device_id)
   P.poly_nx = (const double*)(b8 + o_pnx); P.poly_ny = (const double*)(b8 + o_pny);
   P.cell_mid = (const double*)(b8 + o_mid); P.cell_volume = (const double*)(b8 + o_vol);
   P.cell_surf_id = (const int32_t*)(b8 + o_surf); P.beta = (const double*)(b8 + o_beta); P.uniform_beta = (const double*)(b8 + o_ub);
+  P.omega = (const double*)(b8 + o_omega); P.eps = (const double*)(b8 + o_eps);
   P.lattice = (const int32_t*)(b8 + o_lat); P.em_cell = (const int32_t*)(b8 + o_ec); P.em_wall = (const int32_t*)(b8 + o_ew);
   P.em_coarse = (const int32_t*)(b8 + o_eco);
   h->bins_dev = (int32_t*)(b8 + o_bins); h->bins_cap = (size_t)nb * 4 + 16;
@@ -488,14 +495,16 @@ extern "C" int rthx_get_info(const rthx_handle* h, rthx_info* info) {
 // ---------------------------------------------------------------------------------------------------------------
 namespace {
 
-struct LaunchPlan { int n_owned, n_blocks, block_threads, row_chunks, hist_in_smem, fast, minb; size_t smem_bytes; };
+struct LaunchPlan { int n_owned, n_blocks, block_threads, row_chunks, hist_in_smem, fast, minb, multi; size_t smem_bytes; };
 
 int check_args(rthx_handle* h, const rthx_trace_args* a) {
   if (!a) return fail(h, RTHX_ERR_ARG, "trace: args is NULL");
   if (a->rays_per_emitter < 0) return fail(h, RTHX_ERR_ARG, "trace: rays_per_emitter out of range");
   if (a->n_bins < 1 || !a->bins) return fail(h, RTHX_ERR_ARG, "trace: n_bins must be >= 1");
   for (int i = 0; i < a->n_bins; ++i) if (a->bins[i] < 0 || a->bins[i] >= h->n_bands) return fail(h, RTHX_ERR_ARG, "trace: band index out of range");
-  if (a->mode != RTHX_FIRST_INTERACTION) return fail(h, RTHX_ERR_ARG, "trace: unknown mode");
+  if (a->mode != RTHX_FIRST_INTERACTION && a->mode != RTHX_MULTI_BOUNCE && a->mode != RTHX_MULTI_BOUNCE_SPECULAR) return fail(h, RTHX_ERR_ARG, "trace: unknown mode");
+  if (a->mode != RTHX_FIRST_INTERACTION && !h->has_eps) return fail(h, RTHX_ERR_ARG, "trace: MULTI_BOUNCE needs rthx_mesh.epsilon");
+  if (a->mode != RTHX_FIRST_INTERACTION && h->n_bands > 65535) return fail(h, RTHX_ERR_ARG, "trace: too many bands");
   if (a->emitter_world < 1 || a->emitter_rank < 0 || a->emitter_rank >= a->emitter_world) return fail(h, RTHX_ERR_ARG, "trace: bad emitter_rank/world");
   if (a->n_rec_ids < 0 || (a->n_rec_ids > 0 && !a->rec_ids)) return fail(h, RTHX_ERR_ARG, "trace: bad recorder ids");
   if (a->block_threads != 0 && (a->block_threads < 32 || a->block_threads > 256 || a->block_threads % 32)) return fail(h, RTHX_ERR_ARG, "trace: block_threads must be a multiple of 32 in [32,256]");
@@ -509,7 +518,8 @@ LaunchPlan make_plan(const rthx_handle* h, const rthx_trace_args* a, int rank, i
   if (pl.n_owned < 0) pl.n_owned = 0;
   pl.block_threads = a->block_threads ? a->block_threads : 256;
   pl.fast = (h->fast_ok && a->locator != RTHX_LOCATOR_GENERIC) ? 1 : 0;
-  pl.minb = 4;
+  pl.multi = a->mode != RTHX_FIRST_INTERACTION ? 1 : 0;
+  pl.minb = pl.multi ? 2 : 4;
   if (const char* ev = std::getenv("RTHX_MINB")) { const int v = std::atoi(ev); if (v >= 2 && v <= 4) pl.minb = v; }   // tuning knob
   const size_t coarse_bytes = h->coarse_fits_smem ? sizeof(CoarseDev) * (size_t)h->n_coarse : 0;
   const size_t hist_bytes = sizeof(uint32_t) * (size_t)h->N, em_bytes = sizeof(double) * 16;
@@ -520,7 +530,7 @@ LaunchPlan make_plan(const rthx_handle* h, const rthx_trace_args* a, int rank, i
   long long chunks = a->row_chunks;
   if (chunks <= 0) {
     // enough blocks for ~32 waves of the resident set, but keep >= 2048 rays (and >= N/2, the flush scan) per block
-    const int per_sm = std::max(1, trace_kernel_max_blocks_per_sm(pl.block_threads, pl.smem_bytes, pl.hist_in_smem != 0, pl.fast != 0, pl.minb));
+    const int per_sm = std::max(1, trace_kernel_max_blocks_per_sm(pl.block_threads, pl.smem_bytes, pl.hist_in_smem != 0, pl.fast != 0, pl.minb, pl.multi != 0));
     const long long target = (long long)h->prop.multiProcessorCount * per_sm * 32;
     chunks = rows > 0 ? (target + rows - 1) / rows : 1;
     const long long min_rays = std::max<long long>(2048, h->N / 2);
@@ -547,6 +557,7 @@ void fill_params(const rthx_handle* h, const rthx_trace_args* a, const LaunchPla
   P.coarse_in_smem = h->coarse_fits_smem ? 1 : 0;
   P.hist_in_smem = pl.hist_in_smem;
   P.force_generic = a->locator == RTHX_LOCATOR_GENERIC ? 1 : 0;
+  P.multi_bounce = pl.multi; P.specular = a->mode == RTHX_MULTI_BOUNCE_SPECULAR ? 1 : 0;
   // a count matrix that lives on another GPU (fused peer flush) is updated with system-scope reductions
   P.flush_system = 0;
   cudaPointerAttributes pa;
@@ -631,7 +642,7 @@ int pipeline_launch(rthx_handle* h, const rthx_trace_args* a, int rank, int worl
   CU(h, ensure(&h->counts_dev, &h->counts_cap, (size_t)a->n_bins * (size_t)n_owned * N));
   LaunchPlan pl = make_plan(h, a, rank, world);
   // batches: >= ~6 waves of resident blocks each, at most 16
-  const int per_sm = std::max(1, trace_kernel_max_blocks_per_sm(pl.block_threads, pl.smem_bytes, pl.hist_in_smem != 0, pl.fast != 0, pl.minb));
+  const int per_sm = std::max(1, trace_kernel_max_blocks_per_sm(pl.block_threads, pl.smem_bytes, pl.hist_in_smem != 0, pl.fast != 0, pl.minb, pl.multi != 0));
   const long long resident = (long long)h->prop.multiProcessorCount * per_sm;
   int n_batches = (int)std::min<long long>(16, std::max<long long>(1, pl.n_blocks / (6 * resident)));
   n_batches = std::max(1, std::min(n_batches, n_owned));

@@ -55,6 +55,8 @@ struct TraceParams {
   const int32_t* cell_surf_id; // [n_cells*4]
   const double* beta;          // [n_bands*n_cells]
   const double* uniform_beta;  // [n_bands]
+  const double* omega;         // [n_bands*n_cells]    scattering albedo sigma_s/(kappa+sigma_s)   (MULTI_BOUNCE)
+  const double* eps;           // [n_bands*n_surfaces] wall emissivity                              (MULTI_BOUNCE)
   const int32_t* lattice;      // lattice -> local fine index tables (kind 2)
   const int32_t* em_cell;      // [N]
   const int32_t* em_wall;      // [N]  -1 for volume emitters
@@ -76,6 +78,8 @@ struct TraceParams {
   int32_t coarse_in_smem;
   int32_t hist_in_smem;
   int32_t force_generic;
+  int32_t multi_bounce;        // RTHX_MULTI_BOUNCE: follow scattering / reflection events until absorption
+  int32_t specular;            // MULTI_BOUNCE: mirror reflection instead of diffuse
   int32_t flush_system;        // 1: system-scope atomics for the flush (count matrix in peer memory)
   int32_t rec_bin;
   int64_t rays_per_emitter;
@@ -94,6 +98,6 @@ cudaError_t launch_trace_exchange(const TraceParams& p, int n_blocks, int block_
                                   cudaStream_t stream);
 cudaError_t configure_trace_kernel(size_t smem_bytes);
 cudaError_t launch_fp64_peak(double* out, int n_blocks, int block_threads, int iters, cudaStream_t stream);
-int trace_kernel_max_blocks_per_sm(int block_threads, size_t smem_bytes, bool hist, bool fast, int minb);
+int trace_kernel_max_blocks_per_sm(int block_threads, size_t smem_bytes, bool hist, bool fast, int minb, bool multi);
 
 }  // namespace rthx

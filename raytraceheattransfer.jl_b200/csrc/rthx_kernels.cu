@@ -270,7 +270,7 @@ __device__ __forceinline__ int locate_fine(const TraceParams& p, const CoarseDev
 //   both           : [12,13] cell midPoint
 constexpr int EM_DOUBLES = 16;
 
-template <bool HIST_SMEM, bool FAST, int MINB>
+template <bool HIST_SMEM, bool FAST, int MINB, bool MULTI>
 __global__ void __launch_bounds__(256, MINB) trace_exchange_kernel(const __grid_constant__ TraceParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   CoarseDev* s_coarse = reinterpret_cast<CoarseDev*>(smem_raw);
@@ -342,7 +342,7 @@ __global__ void __launch_bounds__(256, MINB) trace_exchange_kernel(const __grid_
 
   __syncthreads();
 
-  const uint32_t cw = ((uint32_t)band << 8);
+  const uint32_t cw = ((uint32_t)band << 16);
   unsigned int n_lost = 0;
 
   for (int64_t r = r_begin + threadIdx.x; r < r_end; r += blockDim.x) {
@@ -390,11 +390,17 @@ __global__ void __launch_bounds__(256, MINB) trace_exchange_kernel(const __grid_
     }
 
     // ---- stage 2: first-interaction traversal (traceRayUniform / traceRayVariable) --------------------------
-    const double neg_log = FAST ? neg_log_unit(R_S) : -log(R_S);
-    double S = uniform ? neg_log * inv_beta_u : 0.0;   // remaining free path (uniform); beta = 0 -> Inf
-    double acc = 0.0;                                  // accumulated tau (variable)
+    // MULTI (RTHX_MULTI_BOUNCE): the traversal is repeated from every scattering / reflection event until the ray is
+    // absorbed (traceSingleRay.jl:7-81 without the re-emission branches); otherwise the body runs exactly once.
+    double neg_log = FAST ? neg_log_unit(R_S) : -log(R_S);
     int c = c0;
     int absorber = -1;
+    double hit_nx = 0.0, hit_ny = 0.0;   // MULTI: outward unit normal of the wall that was hit
+#pragma unroll 1
+    for (int event = 0;; ++event) {
+    double S = uniform ? neg_log * inv_beta_u : 0.0;   // remaining free path (uniform); beta = 0 -> Inf
+    double acc = 0.0;                                  // accumulated tau (variable)
+    absorber = -1;
     for (int it = 0; it < 10000; ++it) {
       const CoarseDev& cf = coarse[c];
       const int kind = FAST ? cf.kind : (p.force_generic ? KIND_GENERIC : cf.kind);
@@ -429,13 +435,17 @@ __global__ void __launch_bounds__(256, MINB) trace_exchange_kernel(const __grid_
         int w;
         if (!FAST && kind == KIND_GENERIC) {
           w = wall_of_poly(p, gc, px, py, dx, dy);              // traceRay.jl:51
-        } else if (kind == KIND_AFFINE_QUAD) {
-          w = k;                                                // fine wall lying on coarse edge k
-        } else if (__ldg(p.poly_nv + gc) == 3) {
-          w = k;                                                // diagonal triangle cell: walls follow the coarse edges
+          if (MULTI) { hit_nx = p.poly_nx[4 * gc + w]; hit_ny = p.poly_ny[4 * gc + w]; }
         } else {
-          if (k == cf.diag) break;
-          w = (k < cf.diag) ? k : k + 1;                        // quad cell of a mirrored-triangle lattice
+          if (MULTI) { hit_nx = cf.nx[k]; hit_ny = cf.ny[k]; }  // fine walls on a coarse edge share its normal
+          if (kind == KIND_AFFINE_QUAD) {
+            w = k;                                              // fine wall lying on coarse edge k
+          } else if (__ldg(p.poly_nv + gc) == 3) {
+            w = k;                                              // diagonal triangle cell: walls follow the coarse edges
+          } else {
+            if (k == cf.diag) break;
+            w = (k < cf.diag) ? k : k + 1;                      // quad cell of a mirrored-triangle lattice
+          }
         }
         absorber = __ldg(p.cell_surf_id + 4 * gc + w);          // -1: fine wall not solid -> lost
         break;
@@ -453,6 +463,41 @@ __global__ void __launch_bounds__(256, MINB) trace_exchange_kernel(const __grid_
         if (nc < 0) break;
         c = nc;
       }
+    }
+    if (!MULTI || absorber < 0) break;
+    // ---- MULTI_BOUNCE: absorb, scatter or reflect (traceSingleRay.jl:24-79) ---------------------------------------
+    // two more Philox calls per event: call# 2+2*event (+1).  v0.x decision, v0.y azimuth / psi, v0.z cos-theta (walls),
+    // v0.w roulette, (v1.x,v1.y) polar angle (gas), (v1.z,v1.w) next free path
+    if (event >= 16000) { absorber = -1; break; }                // call# is a 16-bit field
+    const uint4 v0 = philox4x32_10_rk(make_uint4(c_lo, c_hi, (uint32_t)e, cw | (uint32_t)(2 + 2 * event)), p.rk);
+    const uint4 v1 = philox4x32_10_rk(make_uint4(c_lo, c_hi, (uint32_t)e, cw | (uint32_t)(3 + 2 * event)), p.rk);
+    if (event >= 1000 && u32d(v0.w, p.k_u32) > 0.8) { absorber = -1; break; }   // Russian roulette, traceSingleRay.jl:11
+    const double dec = u32d(v0.x, p.k_u32);
+    if (absorber >= p.n_surfaces) {
+      if (!(dec < p.omega[(size_t)band * p.n_cells + (absorber - p.n_surfaces)])) break;   // absorbed in the gas
+      // isotropicScatter2D.jl:1-4: theta = acos(2R-1), phi = 2 pi R
+      const double Rt = u52(v1.x, v1.y, p.k_u52);
+      const double sinT = 2.0 * sqrt(Rt * (1.0 - Rt));
+      dx = sinT * cospi(2.0 * u32d(v0.y, p.k_u32));
+      dy = fma(Rt, 2.0, -1.0);
+    } else {
+      if (dec < p.eps[(size_t)band * p.n_surfaces + absorber]) break;                       // absorbed by the wall
+      if (p.specular) {
+        const double dn = dx * hit_nx + dy * hit_ny;            // mirror the in-plane components; the axial one is unchanged
+        dx = fma(-2.0 * dn, hit_nx, dx);
+        dy = fma(-2.0 * dn, hit_ny, dy);
+      } else {
+        // diffuse: Lambert about the inward normal n = -hit_n with x-axis (n.y, -n.x) (sampleReflectionDirection2D.jl:5-16)
+        const float cosT = __fsqrt_rn(u23(v0.z));
+        const float cos2 = __fmul_rn(cosT, cosT);
+        const double xdir = sqrt(1.0 - (double)cos2) * cospi(2.0 * (double)u23(v0.y));
+        const double zdir = (double)cosT;
+        const double nxi = -hit_nx, nyi = -hit_ny;
+        dx = nyi * xdir + nxi * zdir;
+        dy = -nxi * xdir + nyi * zdir;
+      }
+    }
+    neg_log = -log(u52(v1.z, v1.w, p.k_u52));
     }
 
     // ---- stage 3/4: tally (+ record) -------------------------------------------------------------------------
@@ -489,38 +534,43 @@ __global__ void __launch_bounds__(256, MINB) trace_exchange_kernel(const __grid_
   }
 }
 
-// kernel variants: [hist_in_smem][fast][minb - 2]
+// kernel variants: hist_in_smem x fast x multi; the register bound MINB only varies for the hot FIRST_INTERACTION FAST kernel
 typedef void (*TraceKernel)(const TraceParams);
-static TraceKernel kernel_variant(bool hist, bool fast, int minb) {
-  if (!hist) return fast ? (TraceKernel)trace_exchange_kernel<false, true, 2> : (TraceKernel)trace_exchange_kernel<false, false, 2>;
-  if (!fast) return (TraceKernel)trace_exchange_kernel<true, false, 2>;
+static TraceKernel kernel_variant(bool hist, bool fast, int minb, bool multi) {
+  if (multi) {
+    if (hist) return fast ? (TraceKernel)trace_exchange_kernel<true, true, 2, true> : (TraceKernel)trace_exchange_kernel<true, false, 2, true>;
+    return fast ? (TraceKernel)trace_exchange_kernel<false, true, 2, true> : (TraceKernel)trace_exchange_kernel<false, false, 2, true>;
+  }
+  if (!hist) return fast ? (TraceKernel)trace_exchange_kernel<false, true, 2, false> : (TraceKernel)trace_exchange_kernel<false, false, 2, false>;
+  if (!fast) return (TraceKernel)trace_exchange_kernel<true, false, 2, false>;
   switch (minb) {
-    case 3: return (TraceKernel)trace_exchange_kernel<true, true, 3>;
-    case 4: return (TraceKernel)trace_exchange_kernel<true, true, 4>;
-    default: return (TraceKernel)trace_exchange_kernel<true, true, 2>;
+    case 3: return (TraceKernel)trace_exchange_kernel<true, true, 3, false>;
+    case 4: return (TraceKernel)trace_exchange_kernel<true, true, 4, false>;
+    default: return (TraceKernel)trace_exchange_kernel<true, true, 2, false>;
   }
 }
 
 cudaError_t configure_trace_kernel(size_t smem_bytes) {
-  for (int hist = 0; hist < 2; ++hist)
-    for (int fast = 0; fast < 2; ++fast)
-      for (int minb = 2; minb <= 4; ++minb) {
-        cudaError_t e = cudaFuncSetAttribute((const void*)kernel_variant(hist, fast, minb), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-        if (e != cudaSuccess) return e;
-      }
+  for (int multi = 0; multi < 2; ++multi)
+    for (int hist = 0; hist < 2; ++hist)
+      for (int fast = 0; fast < 2; ++fast)
+        for (int minb = 2; minb <= 4; ++minb) {
+          cudaError_t e = cudaFuncSetAttribute((const void*)kernel_variant(hist, fast, minb, multi), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+          if (e != cudaSuccess) return e;
+        }
   return cudaSuccess;
 }
 
-int trace_kernel_max_blocks_per_sm(int block_threads, size_t smem_bytes, bool hist, bool fast, int minb) {
+int trace_kernel_max_blocks_per_sm(int block_threads, size_t smem_bytes, bool hist, bool fast, int minb, bool multi) {
   int n = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, (const void*)kernel_variant(hist, fast, minb), block_threads, smem_bytes) != cudaSuccess) return 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, (const void*)kernel_variant(hist, fast, minb, multi), block_threads, smem_bytes) != cudaSuccess) return 0;
   return n;
 }
 
 cudaError_t launch_trace_exchange(const TraceParams& p, int n_blocks, int block_threads, size_t smem_bytes, bool fast, int minb,
                                   cudaStream_t stream) {
   if (n_blocks <= 0) return cudaSuccess;
-  TraceKernel k = kernel_variant(p.hist_in_smem != 0, fast, minb);
+  TraceKernel k = kernel_variant(p.hist_in_smem != 0, fast, minb, p.multi_bounce != 0);
   void* args[] = {(void*)&p};
   return cudaLaunchKernel((const void*)k, dim3(n_blocks), dim3(block_threads), args, smem_bytes, stream);
 }

@@ -1,0 +1,111 @@
+"""RTHX_MULTI_BOUNCE: absorption-to-absorption tallies with scattering and wall reflection — the
+analogue of method=:direct's traceSingleRay.jl.  Checked against the algebraic closure of the first-interaction F that
+the unchanged host solver applies: T = (I - F B)^-1 F (I - B), B = diag(b) (smoothExchangeFactors.jl:343-357)."""
+import numpy as np
+import pytest
+
+MULTI, SPECULAR = 1, 2
+
+
+def domain(rthx, Ndim=9, kappa=0.6, sigma_s=0.9, eps=(0.3, 0.6, 0.9, 0.5)):
+    return rthx.meshes.square_domain(Ndim, kappa=kappa, sigma_s=sigma_s, epsilon=eps)
+
+
+def test_black_nonscattering_equals_first_interaction(oracle_mod, rthx_mod):
+    rtm = rthx_mod.meshes.cfg1()                                   # eps = 1, sigma_s = 0
+    flat = rthx_mod.flatten_domain(rtm)
+    a = oracle_mod.trace(flat, 2000, seed=3)
+    b = oracle_mod.trace(flat, 2000, seed=3, mode=MULTI)
+    c = oracle_mod.trace(flat, 2000, seed=3, mode=SPECULAR)
+    assert np.array_equal(a["counts"], b["counts"]) and np.array_equal(a["counts"], c["counts"])
+
+
+def test_rows_conserve_rays_and_reciprocity(oracle_mod, rthx_mod):
+    rtm = domain(rthx_mod)
+    flat = rthx_mod.flatten_domain(rtm)
+    rpe = 30_000
+    w = rthx_mod.get_w(rtm)
+    b = rthx_mod.get_b(rtm)[:, 0]
+    for mode in (MULTI, SPECULAR):
+        out = oracle_mod.trace(flat, rpe, seed=4, mode=mode)
+        c = out["counts"][0]
+        assert np.all(c.sum(axis=1) + out["lost"][0] == rpe) and out["lost"].sum() == 0
+        T = c / float(rpe)
+        X = (w * (1 - b))[:, None] * T                             # total exchange areas: eps_i A_i T_ij, 4 kappa_i V_i T_ij
+        sel = (c > 300) & (c.T > 300)
+        rel = np.abs(X - X.T)[sel] / (0.5 * (X + X.T)[sel])
+        assert sel.sum() > 500 and np.median(rel) < 0.06 and rel.max() < 0.5
+
+
+def test_matches_algebraic_closure_of_first_interaction_F(oracle_mod, rthx_mod):
+    """Diffuse walls + isotropic scattering: multi-bounce tallies vs (I - F B)^-1 F (I - B).  The closure assumes
+    element-wise uniform re-emission, so agreement is up to the mesh discretisation (a few %) on aggregated blocks."""
+    rtm = domain(rthx_mod, Ndim=13)
+    flat = rthx_mod.flatten_domain(rtm)
+    ns, N = flat.n_surfaces, flat.n_elements
+    rpe = 40_000
+    F = oracle_mod.trace(flat, rpe, seed=5)["counts"][0] / float(rpe)
+    T = oracle_mod.trace(flat, rpe, seed=6, mode=MULTI)["counts"][0] / float(rpe)
+    b = rthx_mod.get_b(rtm)[:, 0]
+    T_alg = np.linalg.solve(np.eye(N) - F * b[None, :], F * (1 - b)[None, :])
+    assert np.allclose(T_alg.sum(axis=1), 1.0, atol=1e-9)
+    sides = {k: [] for k in (1, 2, 3, 4)}
+    for (c, f, wl), s in rtm.surface_mapping.items():
+        sides[wl].append(s - 1)
+    # emitter groups x absorber groups: four walls + gas
+    groups = [sides[1], sides[2], sides[3], sides[4], list(range(ns, N))]
+    for gi in groups:
+        for gj in groups:
+            a = T[np.ix_(gi, gj)].sum() / len(gi)
+            e = T_alg[np.ix_(gi, gj)].sum() / len(gi)
+            assert abs(a - e) < 0.02 * max(e, 0.05), (a, e)
+
+
+def test_specular_mirror_symmetry(oracle_mod, rthx_mod):
+    """Transparent square, left/right walls perfect specular mirrors (eps = 0), top black: rays from the bottom wall
+    either return to the bottom or reach the top — the mirrors fold the enclosure into infinite parallel plates, for
+    which F(bottom -> top) = 1 exactly."""
+    rtm = rthx_mod.meshes.square_domain(5, kappa=0.0, epsilon=(1.0, 0.0, 1.0, 0.0))
+    flat = rthx_mod.flatten_domain(rtm)
+    out = oracle_mod.trace(flat, 20_000, seed=7, mode=SPECULAR)
+    c = out["counts"][0]
+    bottom = [s - 1 for (cc, f, w), s in rtm.surface_mapping.items() if w == 1]
+    top = [s - 1 for (cc, f, w), s in rtm.surface_mapping.items() if w == 3]
+    rows = c[bottom].sum(axis=0)
+    assert rows[top].sum() == rows.sum()
+    # near-horizontal rays need > 1000 mirror bounces and meet the Russian roulette (traceSingleRay.jl:11): a few are lost
+    assert out["lost"][0][bottom].sum() <= 0.002 * 20_000 * len(bottom)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", [MULTI, SPECULAR])
+def test_gpu_parity_multi_bounce(oracle_mod, rthx_mod, cuda_lib, mode):
+    from helpers import n_differing_rays
+    cases = [domain(rthx_mod), rthx_mod.meshes.two_quads_domain(kappa=(0.5, 3.0)),
+             rthx_mod.meshes.circle_domain(16, 5)]
+    cases[1].coarse_mesh[0].epsilon = [0.5] * 4
+    for rtm in cases:
+        for fine in rtm.fine_mesh:                                  # grey walls + scattering everywhere
+            for cell in fine:
+                cell.epsilon = [0.4] * len(cell.vertices)
+                cell.sigma_s_g = 0.7
+        rtm.refresh_spectral_flags()
+        flat = rthx_mod.flatten_domain(rtm)
+        tr = rthx_mod.DeviceTracer(flat, device=0)
+        rpe = 6000
+        ref = oracle_mod.trace(flat, rpe, seed=8, mode=mode)
+        for loc in (0, 1):
+            got = tr.trace(rpe, seed=8, mode=mode, locator=loc)
+            assert np.all(got["counts"].sum(axis=2) + got["lost"] == rpe)
+            nd = n_differing_rays(got["counts"], ref["counts"])
+            total = int(ref["counts"].sum())
+            assert nd <= max(2, int((2e-6 if loc == 1 else 3e-4) * total)), (nd, total, loc)
+
+
+@pytest.mark.gpu
+def test_gpu_multi_bounce_reduces_to_first_interaction(rthx_mod, cuda_lib):
+    flat = rthx_mod.flatten_domain(rthx_mod.meshes.cfg1())
+    tr = rthx_mod.DeviceTracer(flat, device=0)
+    a = tr.trace(3000, seed=9)
+    b = tr.trace(3000, seed=9, mode=MULTI)
+    assert np.array_equal(a["counts"], b["counts"])
