@@ -42,6 +42,7 @@ def parse_args():
     ap.add_argument("--cpu-sample-rays", type=float, default=1.5e8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-smoothing", action="store_true")
     ap.add_argument("--block-threads", type=int, default=0)
     ap.add_argument("--row-chunks", type=int, default=0)
     ap.add_argument("--reduce", default="fused", choices=["fused", "nccl"],
@@ -326,6 +327,26 @@ def main():
             dist.destroy_process_group()
         return 0
 
+    # ---- next-stage kernel: dense reciprocity smoothing of the traced matrix on the device (HBM-bound) -----------
+    smoothing = None
+    if world == 1 and not args.no_smoothing:
+        try:
+            hbm_peak = json.load(open(os.path.join(_ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+            peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth of this pool's B200)"
+        except Exception:
+            hbm_peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+        tr = rthx.DeviceTracer(flat, device=local_rank)
+        tr.trace(max(1, rpe // 10), counts_out=counts_host.numpy().view(np.uint64) if not args.no_e2e else None, seed=4000, **kw)
+        w = rthx.get_w(rtm)
+        F_host = torch.empty((N, N), dtype=torch.float64, pin_memory=True)
+        _, ss = tr.smooth(w / w.min(), max_iters=1000, measure_pass=True, out=F_host.numpy())
+        tr.close()
+        smoothing = {"kernel": "scale_rows_kernel (one alternating-projection iteration: X *= (u_i+u_j)/2 with fused row sums)",
+                     "bound": "hbm", "achieved": ss["pass_gbs"], "peak": hbm_peak, "unit": "GB/s",
+                     "frac": ss["pass_gbs"] / hbm_peak, "bytes_per_pass": 16 * N * N, "pass_ms": ss["pass_ms"],
+                     "iterations": ss["iterations"], "delta_init": ss["delta_init"], "delta": ss["delta"],
+                     "total_ms": ss["total_ms"], "peak_source": peak_src}
+
     # ---- roofline (FP64 pipe) and CPU baseline ---------------------------------------------------------------
     fp64_peak = sh.tracer.measure_fp64_peak()
     cpu = None
@@ -362,7 +383,7 @@ def main():
                                  "one NCCL reduce of the u64 count matrix to rank 0" if sh.mode == "nccl" else "single GPU")),
                    "l2": "count matrix (8*N*N bytes) exceeds the 126 MB L2 for cfg3; a fresh Philox seed every step",
                    "launch": {k: st[k] for k in ("n_blocks", "block_threads", "row_chunks", "smem_bytes", "hist_in_smem")}},
-        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps * world,
+        "roofline": roofline, "smoothing": smoothing, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps * world,
         "clocks": sampler.summary() if sampler else None,
         "check": {"tallied_last_step": tallied, "lost_last_step": lost_total},
     }

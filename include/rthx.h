@@ -208,6 +208,29 @@ int rthx_trace_exchange_multi(rthx_handle** hs, int n, const rthx_trace_args* ar
                               uint64_t* counts_out, uint64_t* lost_out,
                               rthx_rec_out* rec, rthx_stats* stats);
 
+/* Reciprocity smoothing of a dense exchange-factor matrix on the device (next-stage row of the hot path; restates the
+ * dense alternating projection of src/HeatTransfer/exchangeFactorSmoothing/smoothExchangeFactors.jl:412-612: build_X,
+ * hunger!, scale!, delta_R_X, recover_F).  Returns F_smooth with rows summing to 1 and w_i F_ij = w_j F_ji.
+ *   source RTHX_SMOOTH_FROM_LAST_TRACE: the UInt64 counts of traced bin `bin` still resident on the device from the
+ *          last rthx_trace_exchange on this handle (no host round trip); n <= N crops to the leading n x n block
+ *          (the surfaces-only crop of exchangeRayTracing.jl:9-11);
+ *   source RTHX_SMOOTH_FROM_COUNTS / _FROM_F: src_host is a host UInt64 / Float64 [n][n] matrix.
+ *   w: [n] reciprocity weights, already renormalised by the caller (smooth_F :452-456); target <= 0 means 8 eps.
+ *   measure_pass != 0 additionally times the scaling pass alone (stats->pass_ms / pass_gbs: 16 n^2 bytes per pass). */
+enum { RTHX_SMOOTH_FROM_LAST_TRACE = 0, RTHX_SMOOTH_FROM_COUNTS = 1, RTHX_SMOOTH_FROM_F = 2 };
+typedef struct rthx_smooth_stats {
+  int32_t iterations;
+  int32_t launches;
+  double  delta_init;           /* delta_R after the first reciprocity projection */
+  double  delta;                /* final delta_R */
+  double  total_ms;             /* device time: build X + iterations + recover */
+  double  ms_per_iteration;
+  double  pass_ms;              /* one scaling pass (read + write of X, fused row sums) */
+  double  pass_gbs;             /* 16 n^2 bytes / pass_ms */
+} rthx_smooth_stats;
+int rthx_smooth_F(rthx_handle* h, int source, const void* src_host, int bin, int n, const double* w, int max_iters,
+                  double target, int measure_pass, double* F_out, rthx_smooth_stats* stats);
+
 /* Peer-memory plumbing for the fused flush in one-process-per-GPU runs: rank 0 allocates the UInt64 count matrix
  * with rthx_shared_alloc and publishes the 64-byte CUDA IPC handle; every other rank maps it with rthx_shared_open
  * (peer access over NVLink is enabled lazily) and passes the mapped pointer as `counts_dev` to

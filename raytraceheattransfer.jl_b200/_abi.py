@@ -55,6 +55,17 @@ class rthx_stats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class rthx_smooth_stats(C.Structure):
+    _fields_ = [("iterations", C.c_int32), ("launches", C.c_int32), ("delta_init", C.c_double), ("delta", C.c_double),
+                ("total_ms", C.c_double), ("ms_per_iteration", C.c_double), ("pass_ms", C.c_double), ("pass_gbs", C.c_double)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+RTHX_SMOOTH_FROM_LAST_TRACE, RTHX_SMOOTH_FROM_COUNTS, RTHX_SMOOTH_FROM_F = 0, 1, 2
+
+
 class rthx_info(C.Structure):
     _fields_ = [
         ("n_elements", C.c_int32), ("n_surfaces", C.c_int32), ("n_cells", C.c_int32), ("n_coarse", C.c_int32),
@@ -71,4 +82,5 @@ EXPORTED_SYMBOLS = (
     "rthx_create", "rthx_destroy", "rthx_get_info", "rthx_trace_exchange", "rthx_trace_exchange_device",
     "rthx_trace_exchange_multi", "rthx_measure_fp64_peak", "rthx_last_error", "rthx_version",
     "rthx_shared_alloc", "rthx_shared_open", "rthx_shared_close", "rthx_shared_free", "rthx_release_cached",
+    "rthx_smooth_F",
 )

@@ -13,7 +13,8 @@ from typing import Optional, Sequence
 
 import numpy as np
 
-from ._abi import (rthx_mesh, rthx_trace_args, rthx_rec_out, rthx_stats, rthx_info, c_i32p, c_f64p, c_u64p,
+from ._abi import (rthx_mesh, rthx_trace_args, rthx_rec_out, rthx_stats, rthx_info, rthx_smooth_stats, c_i32p, c_f64p, c_u64p,
+                   RTHX_SMOOTH_FROM_LAST_TRACE, RTHX_SMOOTH_FROM_COUNTS, RTHX_SMOOTH_FROM_F,
                    RTHX_FIRST_INTERACTION, RTHX_LOCATOR_AUTO, RTHX_LOCATOR_GENERIC, EXPORTED_SYMBOLS)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -90,6 +91,11 @@ def load_library():
     L.rthx_shared_close.argtypes = [C.c_int, C.c_void_p]
     L.rthx_shared_free.restype = C.c_int
     L.rthx_shared_free.argtypes = [C.c_int, C.c_void_p]
+    L.rthx_smooth_F.restype = C.c_int
+    L.rthx_smooth_F.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, c_f64p, C.c_int, C.c_double, C.c_int,
+                                c_f64p, C.POINTER(rthx_smooth_stats)]
+    L.rthx_release_cached.restype = C.c_int
+    L.rthx_release_cached.argtypes = []
     L.rthx_measure_fp64_peak.restype = C.c_int
     L.rthx_measure_fp64_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     L.rthx_last_error.restype = C.c_char_p
@@ -197,6 +203,30 @@ class DeviceTracer:
                                                        C.c_void_p(lost_ptr), C.c_void_p(stream),
                                                        int(zero_first), C.byref(st)))
         return st.as_dict()
+
+    def smooth(self, w, n: Optional[int] = None, counts: Optional[np.ndarray] = None, F: Optional[np.ndarray] = None,
+               bin: int = 0, max_iters: int = 1000, target: float = 0.0, measure_pass: bool = False,
+               out: Optional[np.ndarray] = None):
+        """Dense reciprocity smoothing on the device (rthx_smooth_F).  Source: `counts` (u64 [n,n]) or `F` (f64 [n,n])
+        from the host, or — with neither — the counts of traced bin `bin` still resident from the last `trace()`.
+        `w` must already be renormalised (w / min(w)).  Returns (F_smooth [n,n] f64, stats dict)."""
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        n = len(w) if n is None else int(n)
+        assert len(w) == n
+        if counts is not None:
+            src = np.ascontiguousarray(counts, dtype=np.uint64); assert src.shape == (n, n)
+            source, ptr = RTHX_SMOOTH_FROM_COUNTS, src.ctypes.data_as(C.c_void_p)
+        elif F is not None:
+            src = np.ascontiguousarray(F, dtype=np.float64); assert src.shape == (n, n)
+            source, ptr = RTHX_SMOOTH_FROM_F, src.ctypes.data_as(C.c_void_p)
+        else:
+            src, source, ptr = None, RTHX_SMOOTH_FROM_LAST_TRACE, None
+        F_out = out if out is not None else np.empty((n, n), np.float64)
+        assert F_out.dtype == np.float64 and F_out.size == n * n and F_out.flags["C_CONTIGUOUS"]
+        st = rthx_smooth_stats()
+        self._check(self._L.rthx_smooth_F(self._h, source, ptr, int(bin), n, w.ctypes.data_as(c_f64p), int(max_iters),
+                                          float(target), 1 if measure_pass else 0, F_out.ctypes.data_as(c_f64p), C.byref(st)))
+        return F_out.reshape(n, n), st.as_dict()
 
     def measure_fp64_peak(self) -> float:
         v = C.c_double(0.0)

@@ -34,6 +34,9 @@ struct DevRes {
   double* rec_pts_dev = nullptr;            size_t rec_pts_cap = 0;
   uint8_t* rec_valid_dev = nullptr;         size_t rec_valid_cap = 0;
   double* peak_dev = nullptr;
+  double* smooth_X = nullptr;               size_t smooth_cap = 0;     // n*n doubles of the smoothing iterate
+  double* smooth_vec = nullptr;             size_t smooth_vec_cap = 0; // w, rs, r, u, part (5 n doubles)
+  void* smooth_src = nullptr;               size_t smooth_src_cap = 0; // staged host matrix (FROM_COUNTS / FROM_F)
   void* stage[2] = {nullptr, nullptr};      size_t stage_cap = 0;      // pinned staging for pageable destinations
   cudaEvent_t cev[2] = {nullptr, nullptr};
   bool valid = false;
@@ -48,6 +51,7 @@ struct rthx_handle : DevRes {
   bool fast_ok = false;        // every coarse face affine + complete neighbour table + descriptors fit in smem
   size_t mesh_bytes = 0;
   TraceParams base{};          // mesh pointers filled once
+  int last_trace_bins = 0; size_t last_trace_rows = 0;   // layout of counts_dev left by the last host-output trace
   // views into the arena
   unsigned long long* lost_dev = nullptr;   size_t lost_cap = 0;
   int32_t* bins_dev = nullptr;              size_t bins_cap = 0;
@@ -64,6 +68,7 @@ cudaDeviceProp g_prop[64];
 bool g_prop_ok[64] = {};
 
 void devres_free(DevRes& r) {
+  cudaFree(r.smooth_X); cudaFree(r.smooth_vec); cudaFree(r.smooth_src);
   cudaFree(r.arena); cudaFree(r.counts_dev); cudaFree(r.rec_pts_dev); cudaFree(r.rec_valid_dev); cudaFree(r.peak_dev);
   for (auto& e : r.ev) if (e) cudaEventDestroy(e);
   for (auto& e : r.bev) if (e) cudaEventDestroy(e);
@@ -811,6 +816,8 @@ extern "C" int rthx_trace_exchange(rthx_handle* h, const rthx_trace_args* a, uin
   if (rc) return rc;
   rc = pipeline_copy(h, a, a->emitter_rank, a->emitter_world, counts_out, n_batches);
   if (rc) return rc;
+  h->last_trace_bins = a->emitter_world == 1 ? a->n_bins : 0;
+  h->last_trace_rows = (size_t)N;
   std::vector<uint64_t> lost_host((size_t)a->n_bins * N);
   CU(h, cudaMemcpyAsync(lost_host.data(), h->lost_dev, sizeof(uint64_t) * lost_host.size(), cudaMemcpyDeviceToHost, h->copy_stream));
   CU(h, cudaEventRecord(h->ev[3], h->copy_stream));
@@ -987,6 +994,68 @@ extern "C" int rthx_shared_free(int device_id, void* dev_ptr) {
   if (!dev_ptr) return RTHX_OK;
   CUG(cudaSetDevice(device_id));
   CUG(cudaFree(dev_ptr));
+  return RTHX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// reciprocity smoothing on the device
+// ---------------------------------------------------------------------------------------------------------------
+namespace rthx {
+struct SmoothResult { int iters; double delta, delta_init; double ms_total, ms_per_iter; int launches; };
+cudaError_t run_ap(const unsigned long long* src_counts, const double* src_F, size_t ld, const double* w_dev, int n, size_t ldx, int max_iters, double target,
+                   double* X, double* rs, double* r, double* u, double* part, std::vector<double>& part_host, cudaStream_t st, cudaEvent_t e0,
+                   cudaEvent_t e1, SmoothResult* out);
+cudaError_t time_scale_pass(double* X, double* u, double* r, int n, size_t ldx, int reps, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1, double* ms_per_pass);
+}  // namespace rthx
+
+extern "C" int rthx_smooth_F(rthx_handle* h, int source, const void* src_host, int bin, int n, const double* w, int max_iters, double target,
+                             int measure_pass, double* F_out, rthx_smooth_stats* st) {
+  if (!h) return RTHX_ERR_ARG;
+  if (n < 1 || !w || !F_out || max_iters < 0) return fail(h, RTHX_ERR_ARG, "smooth: bad argument");
+  CU(h, cudaSetDevice(h->device));
+  const size_t nn = (size_t)n * n;
+  const unsigned long long* src_counts = nullptr;
+  const double* src_F = nullptr;
+  size_t ld = (size_t)n;
+  if (source == RTHX_SMOOTH_FROM_LAST_TRACE) {
+    if (bin < 0 || bin >= h->last_trace_bins || !h->counts_dev || n > h->N) return fail(h, RTHX_ERR_ARG, "smooth: no resident counts for that bin (run rthx_trace_exchange on all emitters first)");
+    src_counts = h->counts_dev + (size_t)bin * h->last_trace_rows * h->N;
+    ld = (size_t)h->N;
+  } else if (source == RTHX_SMOOTH_FROM_COUNTS || source == RTHX_SMOOTH_FROM_F) {
+    if (!src_host) return fail(h, RTHX_ERR_ARG, "smooth: src_host is NULL");
+    if (h->smooth_src_cap < nn * 8) {
+      cudaFree(h->smooth_src); h->smooth_src = nullptr; h->smooth_src_cap = 0;
+      CU(h, cudaMalloc(&h->smooth_src, nn * 8));
+      h->smooth_src_cap = nn * 8;
+    }
+    CU(h, cudaMemcpyAsync(h->smooth_src, src_host, nn * 8, cudaMemcpyHostToDevice, h->stream));
+    if (source == RTHX_SMOOTH_FROM_COUNTS) src_counts = (const unsigned long long*)h->smooth_src; else src_F = (const double*)h->smooth_src;
+  } else {
+    return fail(h, RTHX_ERR_ARG, "smooth: unknown source");
+  }
+  const size_t ldx = ((size_t)n + 15) & ~size_t(15);      // rows padded to 128 bytes
+  CU(h, ensure(&h->smooth_X, &h->smooth_cap, (size_t)n * ldx));
+  CU(h, ensure(&h->smooth_vec, &h->smooth_vec_cap, (size_t)5 * ldx));
+  double *w_dev = h->smooth_vec, *rs = w_dev + ldx, *r = rs + ldx, *u = r + ldx, *part = u + ldx;
+  CU(h, cudaMemcpyAsync(w_dev, w, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+  std::vector<double> part_host(n);
+  rthx::SmoothResult res{};
+  const double tgt = target > 0 ? target : 8 * 2.220446049250313e-16;
+  CU(h, rthx::run_ap(src_counts, src_F, ld, w_dev, n, ldx, max_iters, tgt, h->smooth_X, rs, r, u, part, part_host, h->stream, h->ev[0], h->ev[1], &res));
+  CU(h, cudaMemcpy2DAsync(F_out, sizeof(double) * (size_t)n, h->smooth_X, sizeof(double) * ldx, sizeof(double) * (size_t)n, (size_t)n,
+                          cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  double pass_ms = 0;
+  if (measure_pass) {
+    std::vector<double> ones(ldx, 1.0);
+    CU(h, cudaMemcpyAsync(u, ones.data(), sizeof(double) * ldx, cudaMemcpyHostToDevice, h->stream));
+    CU(h, rthx::time_scale_pass(h->smooth_X, u, r, n, ldx, 20, h->stream, h->ev[0], h->ev[1], &pass_ms));
+  }
+  if (st) {
+    st->iterations = res.iters; st->launches = res.launches; st->delta_init = res.delta_init; st->delta = res.delta;
+    st->total_ms = res.ms_total; st->ms_per_iteration = res.ms_per_iter; st->pass_ms = pass_ms;
+    st->pass_gbs = pass_ms > 0 ? 16.0 * (double)nn / (pass_ms * 1e-3) / 1e9 : 0.0;
+  }
   return RTHX_OK;
 }
 

@@ -1,0 +1,214 @@
+// rthx_smooth.cu — reciprocity smoothing of a dense exchange-factor matrix on the device.
+//
+// After the trace takes ~0.2 s, the host-side alternating projection of the reference on a 10 605 x 10 605 dense matrix
+// (900 MB of Float64, seconds per iteration on the CPU) dominates `mesh(N; method=:exchange)`.  This file restates the
+// dense branch of src/HeatTransfer/exchangeFactorSmoothing/smoothExchangeFactors.jl on the GPU:
+//   build_X    :474-490   X = (W F + (W F)')/2                         -> build_x_kernel (tile transpose, counts in)
+//   hunger!    :492-499   r = X 1, u = w ./ r                           -> row sums fused into the scaling pass + u_kernel
+//   scale!     :512-521   X_ij *= (u_i + u_j)/2                         -> scale_rows_kernel (one HBM pass per iteration)
+//   delta_R_X  :100-118   sqrt(sum_{i<j} (X_ij (u_i-u_j))^2/(w_i^2+w_j^2)) -> delta_kernel (read-only pass, on check iterations)
+//   recover_F  :546       F = X ./ r                                    -> recover_kernel
+//   AP loop    :548-612   target 8 eps, floor acceptance when the contraction stalls
+// Every pass is HBM-bound: 16 B per matrix element per iteration (read + write of X), 8 B for a delta check.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "rthx_internal.h"
+
+namespace rthx {
+
+// counts (u64, row-major [N][ld]) -> row sums as doubles; one warp per row
+__global__ void __launch_bounds__(256) count_rowsum_kernel(const unsigned long long* __restrict__ c, int n, size_t ld, double* __restrict__ rs) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= n) return;
+  unsigned long long s = 0;
+  for (int j = lane; j < n; j += 32) s += c[(size_t)row * ld + j];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+  if (lane == 0) rs[row] = (double)s;
+}
+
+// X_ij = (w_i F_ij + w_j F_ji)/2 with F = counts / rowsum (rows with no tallies stay zero), 32x32 tiles through smem
+// so both the (I,J) and the transposed (J,I) reads are coalesced.  F may also be given directly as doubles.
+template <class T>
+__global__ void __launch_bounds__(256) build_x_kernel(const T* __restrict__ src, size_t ld, const double* __restrict__ rs,
+                                                      const double* __restrict__ w, int n, size_t ldx, double* __restrict__ X) {
+  __shared__ double t[32][33];
+  const int bi = blockIdx.y * 32, bj = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  // transposed tile: element (bj + r, bi + c) -> t[r][c]
+  for (int r = ty; r < 32; r += 8) {
+    const int i = bj + r, j = bi + tx;
+    double v = 0.0;
+    if (i < n && j < n) {
+      const double d = rs ? rs[i] : 1.0;
+      v = d > 0.0 ? w[i] * ((double)src[(size_t)i * ld + j] / d) : 0.0;
+    }
+    t[r][tx] = v;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int i = bi + r, j = bj + tx;
+    if (i < n && j < n) {
+      const double d = rs ? rs[i] : 1.0;
+      const double a = d > 0.0 ? w[i] * ((double)src[(size_t)i * ld + j] / d) : 0.0;
+      X[(size_t)i * ldx + j] = 0.5 * (a + t[tx][r]);
+    } else if (i < n && (size_t)j < ldx) {
+      X[(size_t)i * ldx + j] = 0.0;                        // row padding (columns n..ldx-1) stays zero for ever
+    }
+  }
+}
+
+// Rows of X are padded to ldx = 16-double multiples (128-byte aligned rows; the padding holds zeros and u is padded
+// with ones), so every pass streams X with aligned 16-byte accesses.  One 1024-thread block per row: 96 % of the
+// measured copy bandwidth in isolation (tools/microbench/scale_pass.cu); an unpadded odd n (10 605) forces 8-byte
+// accesses on misaligned rows and drops to 69 %.
+constexpr int ROW_THREADS = 1024;
+
+__device__ __forceinline__ double block_sum(double s, double* red) {
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  double a = 0.0;
+  if (threadIdx.x == 0) for (int k = 0; k < (int)(blockDim.x >> 5); ++k) a += red[k];
+  return a;
+}
+
+// plain row sums of X (first hunger!): one block per row
+__global__ void __launch_bounds__(ROW_THREADS) rowsum_kernel(const double* __restrict__ X, size_t ldx, double* __restrict__ r) {
+  __shared__ double red[32];
+  const double2* x2 = reinterpret_cast<const double2*>(X + (size_t)blockIdx.x * ldx);
+  double s = 0.0;
+  for (int j = threadIdx.x; j < (int)(ldx >> 1); j += ROW_THREADS) { const double2 v = x2[j]; s += v.x + v.y; }
+  const double a = block_sum(s, red);
+  if (threadIdx.x == 0) r[blockIdx.x] = a;
+}
+
+// u = w ./ r on [0,n), 1 on the padding [n, ldx)
+__global__ void u_kernel(const double* __restrict__ w, const double* __restrict__ r, int n, int ldx, double* __restrict__ u) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) u[i] = r[i] > 0.0 ? w[i] / r[i] : 1.0;
+  else if (i < ldx) u[i] = 1.0;
+}
+
+// One AP iteration in ONE pass over HBM: X_ij *= (u_i + u_j)/2 and the new row sums r_i = sum_j X_ij.
+__global__ void __launch_bounds__(ROW_THREADS) scale_rows_kernel(double* __restrict__ X, const double* __restrict__ u, size_t ldx, double* __restrict__ r) {
+  __shared__ double red[32];
+  const size_t row = blockIdx.x;
+  const double hui = 0.5 * u[row];
+  double2* x2 = reinterpret_cast<double2*>(X + row * ldx);
+  const double2* u2 = reinterpret_cast<const double2*>(u);
+  double s = 0.0;
+  for (int j = threadIdx.x; j < (int)(ldx >> 1); j += ROW_THREADS) {
+    double2 v = x2[j];
+    const double2 uj = u2[j];
+    v.x *= fma(0.5, uj.x, hui);
+    v.y *= fma(0.5, uj.y, hui);
+    x2[j] = v;
+    s += v.x + v.y;
+  }
+  const double a = block_sum(s, red);
+  if (threadIdx.x == 0) r[row] = a;
+}
+
+// delta_R^2 partial sums: sum_{j>i} (X_ij (u_i - u_j))^2 / (w_i^2 + w_j^2), one block per row -> part[row]
+__global__ void __launch_bounds__(256) delta_kernel(const double* __restrict__ X, const double* __restrict__ u, const double* __restrict__ w,
+                                                    int n, size_t ldx, double* __restrict__ part) {
+  __shared__ double red[32];
+  const size_t row = blockIdx.x;
+  const double ui = u[row], wi2 = w[row] * w[row];
+  double s = 0.0;
+  for (int j = (int)row + 1 + threadIdx.x; j < n; j += blockDim.x) {
+    const double d = X[row * ldx + j] * (ui - u[j]);
+    s += d * d / (wi2 + w[j] * w[j]);
+  }
+  const double a = block_sum(s, red);
+  if (threadIdx.x == 0) part[row] = a;
+}
+
+__global__ void __launch_bounds__(ROW_THREADS) recover_kernel(double* __restrict__ X, const double* __restrict__ r, size_t ldx) {
+  const size_t row = blockIdx.x;
+  const double inv = r[row] > 0.0 ? 1.0 / r[row] : 0.0;
+  double2* x2 = reinterpret_cast<double2*>(X + row * ldx);
+  for (int j = threadIdx.x; j < (int)(ldx >> 1); j += ROW_THREADS) { double2 v = x2[j]; v.x *= inv; v.y *= inv; x2[j] = v; }
+}
+
+struct SmoothResult { int iters; double delta, delta_init; double ms_total, ms_per_iter; int launches; };
+
+// Runs AP on the device.  `src_counts` (u64, leading dimension ld) or `src_F` (doubles) is a DEVICE pointer; X (n*n
+// doubles) and the work vectors are device scratch owned by the caller.  On return X holds F_smooth.
+cudaError_t run_ap(const unsigned long long* src_counts, const double* src_F, size_t ld, const double* w_dev, int n, size_t ldx, int max_iters, double target,
+                   double* X, double* rs, double* r, double* u, double* part, std::vector<double>& part_host, cudaStream_t st, cudaEvent_t e0,
+                   cudaEvent_t e1, SmoothResult* out) {
+  cudaError_t e;
+  int launches = 0;
+  const dim3 tg((unsigned)((ldx + 31) / 32), (n + 31) / 32);   // x covers the row padding too
+  if ((e = cudaEventRecord(e0, st)) != cudaSuccess) return e;
+  if (src_counts) {
+    count_rowsum_kernel<<<(n + 7) / 8, 256, 0, st>>>(src_counts, n, ld, rs);
+    build_x_kernel<unsigned long long><<<tg, 256, 0, st>>>(src_counts, ld, rs, w_dev, n, ldx, X);
+    launches += 2;
+  } else {
+    build_x_kernel<double><<<tg, 256, 0, st>>>(src_F, ld, nullptr, w_dev, n, ldx, X);
+    launches += 1;
+  }
+  rowsum_kernel<<<n, ROW_THREADS, 0, st>>>(X, ldx, r);
+  u_kernel<<<(unsigned)((ldx + 255) / 256), 256, 0, st>>>(w_dev, r, n, (int)ldx, u);
+  launches += 2;
+  auto delta_now = [&](double* d) -> cudaError_t {
+    delta_kernel<<<n, 256, 0, st>>>(X, u, w_dev, n, ldx, part);
+    ++launches;
+    cudaError_t ee = cudaMemcpyAsync(part_host.data(), part, sizeof(double) * n, cudaMemcpyDeviceToHost, st);
+    if (ee != cudaSuccess) return ee;
+    if ((ee = cudaStreamSynchronize(st)) != cudaSuccess) return ee;
+    double s = 0;
+    for (int i = 0; i < n; ++i) s += part_host[i];
+    *d = std::sqrt(s);
+    return cudaSuccess;
+  };
+  double delta = 0;
+  if ((e = delta_now(&delta)) != cudaSuccess) return e;
+  const double delta_init = delta;
+  double best = delta;
+  int k = 0, k_next = 1, flat = 0;
+  while (k < max_iters && delta > target) {
+    scale_rows_kernel<<<n, ROW_THREADS, 0, st>>>(X, u, ldx, r);
+    u_kernel<<<(unsigned)((ldx + 255) / 256), 256, 0, st>>>(w_dev, r, n, (int)ldx, u);
+    launches += 2;
+    ++k;
+    if (k >= k_next || k == max_iters) {
+      if ((e = delta_now(&delta)) != cudaSuccess) return e;
+      flat = delta >= best * (1 - 1e-3) ? flat + 1 : 0;      // smoothExchangeFactors.jl:582: contraction exhausted
+      best = std::min(best, delta);
+      if (flat >= 3) break;
+      k_next = k + std::min(32, std::max(1, k));             // 1,2,4,...,32 then every 32 iterations
+    }
+  }
+  recover_kernel<<<n, ROW_THREADS, 0, st>>>(X, r, ldx);
+  ++launches;
+  if ((e = cudaEventRecord(e1, st)) != cudaSuccess) return e;
+  if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  out->iters = k; out->delta = delta; out->delta_init = delta_init; out->ms_total = ms;
+  out->ms_per_iter = k > 0 ? ms / k : 0.0; out->launches = launches;
+  return cudaGetLastError();
+}
+
+// timing helper for the roofline: `reps` back-to-back scaling passes with u = 1 (X unchanged), returns ms per pass
+cudaError_t time_scale_pass(double* X, double* u, double* r, int n, size_t ldx, int reps, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1, double* ms_per_pass) {
+  cudaError_t e;
+  scale_rows_kernel<<<n, ROW_THREADS, 0, st>>>(X, u, ldx, r);
+  if ((e = cudaEventRecord(e0, st)) != cudaSuccess) return e;
+  for (int i = 0; i < reps; ++i) scale_rows_kernel<<<n, ROW_THREADS, 0, st>>>(X, u, ldx, r);
+  if ((e = cudaEventRecord(e1, st)) != cudaSuccess) return e;
+  if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  *ms_per_pass = ms / reps;
+  return cudaGetLastError();
+}
+
+}  // namespace rthx

@@ -160,6 +160,22 @@ def get_b(rtm) -> np.ndarray:
     return b
 
 
+def _smooth_on_device(rtm, F_raw, w, ns: int, max_iters: int, verbose: bool):
+    """Dense branch of smooth_F (density > 0.25, smoothExchangeFactors.jl:432-434) on the GPU, straight from the counts
+    that the trace left on the device; returns None when the sparse host path applies (sparsity must be preserved)."""
+    tr = getattr(rtm, "_device", None)
+    n = F_raw.shape[0]
+    if tr is None or max_iters <= 0 or F_raw.nnz / float(n * n) <= 0.25:
+        return None
+    wn = w[:n] / np.min(w[:n])
+    verbose and print(f"Matrix size: {n}x{n}; dense alternating projection on the device")
+    F_smooth, st = tr.smooth(wn, n=n, max_iters=max_iters)
+    rtm.last_smooth_stats = st
+    verbose and print(f"AP: {st['iterations']} iterations, delta_R {st['delta_init']:.3e} -> {st['delta']:.3e}, "
+                      f"{st['total_ms']:.1f} ms on the device")
+    return F_smooth
+
+
 def exchangeRayTracing(rtm, rays_tot: int, nudge: float, max_iters: int, k_dykstra, verbose: bool, rec,
                        seed: Optional[int] = None, device: int = 0, locator: int = RTHX_LOCATOR_AUTO,
                        smooth: bool = True):
@@ -187,8 +203,10 @@ def exchangeRayTracing(rtm, rays_tot: int, nudge: float, max_iters: int, k_dykst
             for j in g:
                 F_smooth[j - 1] = Fs
     else:
-        F_smooth = smooth_F(F_raw, get_w(rtm), ns, max_iters=max_iters, k_dykstra=k_dykstra, verbose=verbose,
-                            smooth_surfaces_only=rtm.surfaces_only)
+        F_smooth = _smooth_on_device(rtm, F_raw, get_w(rtm), ns, max_iters, verbose)
+        if F_smooth is None:
+            F_smooth = smooth_F(F_raw, get_w(rtm), ns, max_iters=max_iters, k_dykstra=k_dykstra, verbose=verbose,
+                                smooth_surfaces_only=rtm.surfaces_only)
     rtm.F_raw = F_raw
     rtm.F_smooth = F_smooth
     return F_smooth

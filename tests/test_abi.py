@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_header_symbols_all_exported(cuda_lib, rthx_mod):
     from rthx._abi import EXPORTED_SYMBOLS
     header = open(os.path.join(ROOT, "include", "rthx.h")).read()
-    declared = set(re.findall(r"\b(rthx_[a-z0-9_]+)\s*\(", header))
+    declared = set(re.findall(r"\b(rthx_[A-Za-z0-9_]+)\s*\(", header))
     assert declared == set(EXPORTED_SYMBOLS)
     for name in declared:
         assert getattr(cuda_lib, name) is not None
