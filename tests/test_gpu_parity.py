@@ -262,3 +262,58 @@ def test_open_boundary_loses_rays_like_the_reference(rthx_mod, oracle_mod, cuda_
         got = tr.trace(10000, seed=33, locator=loc)
         check_exact(got, ref, 10000)
         assert n_differing_rays(got["lost"], ref["lost"]) <= 2
+
+
+def test_edge_cases_empty_and_extreme_arguments(rthx_mod, oracle_mod, cuda_lib):
+    flat, tr = tracer(rthx_mod, cuda_lib, rthx_mod.meshes.square_domain(4))
+    N = tr.n_elements
+    z = tr.trace(0, seed=1)                                            # no rays at all
+    assert z["counts"].shape == (1, N, N) and z["counts"].sum() == 0 and z["lost"].sum() == 0
+    one = tr.trace(1, seed=1)                                          # one ray per emitter
+    assert np.all(one["counts"].sum(axis=2) + one["lost"] == 1)
+    assert np.array_equal(one["counts"], oracle_mod.trace(flat, 1, seed=1)["counts"])
+    big = 2 ** 40 + 12345                                              # ray ids beyond 32 bits, all-ones seed
+    got = tr.trace(700, seed=2 ** 64 - 1, ray_id_offset=big)
+    ref = oracle_mod.trace(flat, 700, seed=2 ** 64 - 1, ray_id_offset=big)
+    assert np.array_equal(got["counts"], ref["counts"])
+    rep = tr.trace(500, seed=3, bins=[0, 0, 0])                        # the same band three times: identical slabs
+    assert np.array_equal(rep["counts"][0], rep["counts"][1]) and np.array_equal(rep["counts"][0], rep["counts"][2])
+    with pytest.raises(rthx_mod.RthxError):
+        tr.trace(10, bins=[1])                                         # band out of range
+    with pytest.raises(rthx_mod.RthxError):
+        tr.trace(10, emitter_rank=2, emitter_world=2)
+    with pytest.raises(rthx_mod.RthxError):
+        tr.trace(10, mode=7)
+    more = tr.trace(50, emitter_rank=N + 3, emitter_world=N + 5)       # a shard that owns no emitter
+    assert more["counts"].sum() == 0
+
+
+def test_cellwise_variable_extinction_inside_one_face(rthx_mod, oracle_mod, cuda_lib):
+    """User-edited per-cell kappa inside a single coarse face: uniform_across_bin = -1, so traceRayVariable runs and —
+    faithful to traceRay.jl:87-103 — takes beta of the fine cell at the entry point for the whole coarse-face visit."""
+    rtm = rthx_mod.meshes.square_domain(8, kappa=1.0)
+    for f, cell in enumerate(rtm.fine_mesh[0]):
+        cell.kappa_g = 0.2 + 0.15 * (f % 7)
+    rtm.refresh_spectral_flags()
+    assert rtm.uniform_across_bin == [-1.0]
+    flat, tr = tracer(rthx_mod, cuda_lib, rtm)
+    ref = oracle_mod.trace(flat, 15000, seed=21)
+    check_exact(tr.trace(15000, seed=21), ref, 15000)
+    check_exact(tr.trace(15000, seed=21, locator=GENERIC), ref, 15000)
+    # rows of cells with different kappa really differ in their self-absorption
+    c = ref["counts"][0]
+    ns = flat.n_surfaces
+    self_abs = np.array([c[ns + f, ns + f] for f in range(64)]) / 15000.0
+    assert self_abs[6] > 1.5 * self_abs[0]
+
+
+def test_recorder_on_spectral_bin(rthx_mod, oracle_mod, cuda_lib):
+    """RayRecorder(ids; bin): only rays of that band are recorded (parallelRayTracing.jl:108)."""
+    rtm = rthx_mod.meshes.cfg4(Ndim=9, n_bins=3)
+    flat, tr = tracer(rthx_mod, cuda_lib, rtm)
+    got = tr.trace(400, seed=22, bins=[0, 1, 2], rec_ids=[5, 40], rec_bin=1)
+    ref = oracle_mod.trace(flat, 400, seed=22, bins=[0, 1, 2], rec_ids=[5, 40], rec_bin=1)
+    assert got["origins"].shape == ref["origins"].shape == (800, 2)
+    assert np.allclose(got["origins"], ref["origins"], atol=1e-13) and np.allclose(got["endpoints"], ref["endpoints"], atol=1e-9)
+    none = tr.trace(400, seed=22, bins=[0, 2], rec_ids=[5, 40], rec_bin=1)   # the recorded band is not traced
+    assert none["origins"].shape == (0, 2)
