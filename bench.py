@@ -270,13 +270,13 @@ def main():
     # ---- end-to-end through the C ABI with host buffers ------------------------------------------------------
     e2e = None
     if not args.no_e2e:
-        counts_host = torch.empty((nb, N, N), dtype=torch.int64, pin_memory=True)
+        counts_host = torch.empty((nb, N, N), dtype=torch.int64, pin_memory=True) if world == 1 else None
         mesh_bytes = sum(getattr(flat, n).nbytes for n in (
             "coarse_nv", "coarse_vx", "coarse_vy", "coarse_solid", "fine_off", "cell_nv", "cell_vx", "cell_vy", "cell_mid",
             "cell_volume", "cell_surf_id", "kappa", "sigma_s", "epsilon", "uniform_beta"))
 
         e2e_dev_ms = []
-        e2e_phases = []   # N > 1: [create, trace+finish, d2h+sync, close] ms per step
+        e2e_phases = []   # N > 1: [create, trace + own-row D2H, barrier, close] ms per step
 
         def e2e_step(seed):
             if world == 1:
@@ -285,22 +285,29 @@ def main():
                 tr.close()
                 e2e_dev_ms.append((out["stats"]["kernel_ms"], out["stats"]["total_ms"]))
                 return int(out["lost"].sum())
+            # N > 1: every rank re-uploads the mesh and copies ITS rows into one page-locked matrix in POSIX shared
+            # memory over its own PCIe link (overlapped with tracing); a barrier makes the matrix complete on rank 0.
             tp = [time.perf_counter()]
-            old = sh.tracer
-            sh.tracer = rthx.DeviceTracer(flat, device=local_rank)    # this step's mesh -> device (H2D)
+            tr = rthx.DeviceTracer(flat, device=local_rank)
             tp.append(time.perf_counter())
-            sh.trace(rpe, seed=seed, **kw)
+            tr.trace(rpe, counts_out=shared_host.array, seed=seed, emitter_rank=rank, emitter_world=world, **kw)
             tp.append(time.perf_counter())
-            if rank == 0:
-                counts_host.copy_(sh.counts, non_blocking=True)
-            torch.cuda.synchronize(dev)
+            dist.barrier(device_ids=[local_rank])
             tp.append(time.perf_counter())
-            tp.append(time.perf_counter())
-            old.close()
+            tr.close()
             tp.append(time.perf_counter())
             e2e_phases.append([1e3 * (b - a) for a, b in zip(tp[:-1], tp[1:])])
             return 0
 
+        shared_host = None
+        if world > 1:
+            from rthx._lib import SharedHostMatrix
+            shm_name = f"rthx_bench_{os.environ.get('MASTER_PORT', '0')}"
+            if rank == 0:
+                shared_host = SharedHostMatrix(shm_name, (nb, N, N), create=True)
+            dist.barrier(device_ids=[local_rank])
+            if rank != 0:
+                shared_host = SharedHostMatrix(shm_name, (nb, N, N), create=False)
         e2e_step(3000)
         barrier()
         t0 = time.perf_counter()
@@ -320,7 +327,11 @@ def main():
                                       "zero+kernel+d2h": float(np.mean([b for _, b in e2e_dev_ms[1:]]))} if e2e_dev_ms else None,
                "phases_ms": [float(x) for x in np.mean(np.array(e2e_phases[1:]), axis=0)] if len(e2e_phases) > 1 else None,
                "path": "rthx_create + rthx_trace_exchange (pinned host count matrix)" if world == 1 else
-                       f"rthx_create + rthx_trace_exchange_device ({args.reduce}) + D2H of the matrix on rank 0"}
+                       "per rank: rthx_create + rthx_trace_exchange(own rows -> page-locked shared host matrix); barrier"}
+        if world > 1:
+            e2e["check_total"] = int(shared_host.array.sum()) if rank == 0 else None
+            dist.barrier(device_ids=[local_rank])
+            shared_host.close()
 
     if rank != 0:
         if world > 1:

@@ -185,7 +185,10 @@ int rthx_get_info(const rthx_handle* h, rthx_info* info);
  * for all `bins` at once: counts_out[b][i][j] = number of rays of emitter i whose first interaction is
  * element j; lost_out[b][i] = rays dropped.  The caller forms F = counts / rowsum exactly as
  * parallelRayTracing.jl:144-146 + row_normalize! :161-169 compose.
- *   counts_out: [n_bins*N*N] uint64, lost_out: [n_bins*N] uint64 (may be NULL), rec / stats may be NULL. */
+ *   counts_out: [n_bins*N*N] uint64, lost_out: [n_bins*N] uint64 (may be NULL), rec / stats may be NULL.
+ * With emitter_world > 1 only the rows this call owns are written; the other rows of counts_out are NOT touched, so
+ * several ranks (processes) can fill one matrix in shared host memory, each copying its rows over its own PCIe link.
+ * Pinned / registered destinations are written by DMA directly; pageable ones go through internal pinned staging. */
 int rthx_trace_exchange(rthx_handle* h, const rthx_trace_args* args,
                         uint64_t* counts_out, uint64_t* lost_out,
                         rthx_rec_out* rec, rthx_stats* stats);
@@ -241,6 +244,11 @@ int rthx_shared_alloc(int device_id, uint64_t bytes, void** dev_ptr, unsigned ch
 int rthx_shared_open(int device_id, const unsigned char ipc_handle[64], void** dev_ptr);
 int rthx_shared_close(int device_id, void* dev_ptr);
 int rthx_shared_free(int device_id, void* dev_ptr);
+
+/* Page-lock a caller-owned host buffer (e.g. a matrix in POSIX shared memory that several ranks fill) so the
+ * pipelined device->host copies of rthx_trace_exchange run at full PCIe speed and overlap with tracing. */
+int rthx_host_register(void* ptr, uint64_t bytes);
+int rthx_host_unregister(void* ptr);
 
 /* FP64 FMA-chain micro-benchmark on the handle's device: the denominator of the FP64 roofline
  * (MEASURED_PEAKS.json has no FP64 entry).  Returns TFLOP/s (2 flop per DFMA). */

@@ -96,6 +96,10 @@ def load_library():
                                 c_f64p, C.POINTER(rthx_smooth_stats)]
     L.rthx_release_cached.restype = C.c_int
     L.rthx_release_cached.argtypes = []
+    L.rthx_host_register.restype = C.c_int
+    L.rthx_host_register.argtypes = [C.c_void_p, C.c_uint64]
+    L.rthx_host_unregister.restype = C.c_int
+    L.rthx_host_unregister.argtypes = [C.c_void_p]
     L.rthx_measure_fp64_peak.restype = C.c_int
     L.rthx_measure_fp64_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     L.rthx_last_error.restype = C.c_char_p
@@ -173,7 +177,10 @@ class DeviceTracer:
         rec_ids = kw.get("rec_ids")
         args, keep = make_trace_args(rays_per_emitter, **kw)
         N, nb = self.n_elements, args.n_bins
-        counts = counts_out if counts_out is not None else np.empty((nb, N, N), np.uint64)
+        if counts_out is not None:
+            counts = counts_out
+        else:   # rows of other ranks are left untouched by the library: start from zeros when sharded
+            counts = (np.zeros if args.emitter_world > 1 else np.empty)((nb, N, N), np.uint64)
         assert counts.dtype == np.uint64 and counts.size == nb * N * N and counts.flags["C_CONTIGUOUS"]
         lost = np.empty((nb, N), np.uint64)
         st = rthx_stats()
@@ -298,3 +305,31 @@ class SharedDeviceBuffer:
             self.close()
         except Exception:
             pass
+
+
+class SharedHostMatrix:
+    """A UInt64 count matrix in POSIX shared memory, page-locked in every process that maps it: each rank's
+    `DeviceTracer.trace(..., counts_out=m.array, emitter_rank=r, emitter_world=W)` copies its own rows over its own PCIe
+    link, overlapped with tracing, and rank 0 reads the assembled matrix after a barrier — no device-side gather."""
+
+    def __init__(self, name: str, shape, create: bool):
+        from multiprocessing import shared_memory
+        nbytes = int(np.prod(shape)) * 8
+        self.shm = shared_memory.SharedMemory(name=name, create=create, size=nbytes)
+        self.owner = create
+        self.array = np.ndarray(shape, dtype=np.uint64, buffer=self.shm.buf)
+        L = load_library()
+        rc = L.rthx_host_register(C.c_void_p(self.array.ctypes.data), nbytes)
+        if rc != 0:
+            msg = L.rthx_last_error(None)
+            raise RthxError(f"rthx_host_register failed ({rc}): {msg.decode() if msg else ''}")
+        self._L = L
+
+    def close(self):
+        if getattr(self, "shm", None) is not None:
+            self._L.rthx_host_unregister(C.c_void_p(self.array.ctypes.data))
+            self.array = None
+            self.shm.close()
+            if self.owner:
+                self.shm.unlink()
+            self.shm = None

@@ -810,7 +810,6 @@ extern "C" int rthx_trace_exchange(rthx_handle* h, const rthx_trace_args* a, uin
   rc = prepare_recorder(h, a, rec, &n_slots, h->stream);
   if (rc) return rc;
   LaunchPlan pl{};
-  if (a->emitter_world > 1) std::memset(counts_out, 0, sizeof(uint64_t) * (size_t)a->n_bins * N * N);   // rows of other ranks
   int n_batches = 1;
   rc = pipeline_launch(h, a, a->emitter_rank, a->emitter_world, rec != nullptr, n_slots, &pl, &n_launches, &n_batches);
   if (rc) return rc;
@@ -957,6 +956,18 @@ extern "C" int rthx_trace_exchange_multi(rthx_handle** hs, int n, const rthx_tra
     cudaError_t e_ = (call);                                                                          \
     if (e_ != cudaSuccess) return fail(nullptr, RTHX_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
   } while (0)
+
+extern "C" int rthx_host_register(void* ptr, uint64_t bytes) {
+  if (!ptr || bytes == 0) return fail(nullptr, RTHX_ERR_ARG, "rthx_host_register: bad argument");
+  CUG(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable));
+  return RTHX_OK;
+}
+
+extern "C" int rthx_host_unregister(void* ptr) {
+  if (!ptr) return RTHX_OK;
+  CUG(cudaHostUnregister(ptr));
+  return RTHX_OK;
+}
 
 extern "C" int rthx_shared_alloc(int device_id, uint64_t bytes, void** dev_ptr, unsigned char ipc_handle[64]) {
   if (!dev_ptr || !ipc_handle || bytes == 0) return fail(nullptr, RTHX_ERR_ARG, "rthx_shared_alloc: bad argument");

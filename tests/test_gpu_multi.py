@@ -36,6 +36,24 @@ def _worker(rank, world, port, out_dir):
             np.save(os.path.join(out_dir, f"{mode}_counts.npy"), sh.counts.cpu().numpy().view(np.uint64))
             np.save(os.path.join(out_dir, f"{mode}_lost.npy"), sh.lost.cpu().numpy().view(np.uint64))
         sh.close()
+    # host-output sharding: every rank copies its own rows into one page-locked matrix in POSIX shared memory
+    from rthx._lib import SharedHostMatrix
+    N = flat.n_elements
+    name = f"rthx_test_{port}"
+    m = SharedHostMatrix(name, (3, N, N), create=True) if rank == 0 else None
+    dist.barrier()
+    if rank != 0:
+        m = SharedHostMatrix(name, (3, N, N), create=False)
+    if rank == 0:
+        m.array[:] = 7                                            # stale contents must be overwritten row by row
+    dist.barrier()
+    tr = rthx.DeviceTracer(flat, device=rank)
+    tr.trace(4000, counts_out=m.array, seed=21, bins=bins, emitter_rank=rank, emitter_world=world)
+    dist.barrier()
+    if rank == 0:
+        np.save(os.path.join(out_dir, "hostshared_counts.npy"), np.array(m.array))
+    dist.barrier()
+    m.close()
     dist.barrier()
     dist.destroy_process_group()
 
@@ -51,3 +69,4 @@ def test_fused_peer_flush_equals_nccl_reduce_equals_single_gpu(tmp_path, rthx_mo
         l = np.load(tmp_path / f"{mode}_lost.npy")
         assert np.array_equal(c, one["counts"]), mode
         assert np.array_equal(l, one["lost"]), mode
+    assert np.array_equal(np.load(tmp_path / "hostshared_counts.npy"), one["counts"])
