@@ -48,6 +48,8 @@ struct rthx_handle : DevRes {
   int n_coarse = 0, n_cells = 0, n_bands = 0, ns = 0, N = 0, n_affine = 0;
   bool coarse_fits_smem = false;
   bool has_eps = false;
+  bool single_quad = false;    // one parallelogram coarse face: SQ kernel
+  CoarseDev face0{};
   bool fast_ok = false;        // every coarse face affine + complete neighbour table + descriptors fit in smem
   size_t mesh_bytes = 0;
   TraceParams base{};          // mesh pointers filled once
@@ -478,6 +480,8 @@ extern "C" int rthx_create(rthx_handle** out, const rthx_mesh* m, int device_id)
   h->lost_dev = (unsigned long long*)(b8 + o_lost); h->lost_cap = ((size_t)nb * 4 + 16) * (size_t)N;
   P.n_coarse = nc; P.n_cells = ncell; P.n_surfaces = ns; P.N = N;
   h->coarse_fits_smem = sizeof(CoarseDev) * (size_t)nc <= 32 * 1024;
+  h->face0 = coarse[0];
+  h->single_quad = nc == 1 && coarse[0].kind == KIND_AFFINE_QUAD;
   h->fast_ok = h->coarse_fits_smem && h->n_affine == nc;
   for (int c = 0; c < nc && h->fast_ok; ++c)
     for (int k = 0; k < coarse[c].nv; ++k)
@@ -500,7 +504,7 @@ extern "C" int rthx_get_info(const rthx_handle* h, rthx_info* info) {
 // ---------------------------------------------------------------------------------------------------------------
 namespace {
 
-struct LaunchPlan { int n_owned, n_blocks, block_threads, row_chunks, hist_in_smem, fast, minb, multi; size_t smem_bytes; };
+struct LaunchPlan { int n_owned, n_blocks, block_threads, row_chunks, hist_in_smem, fast, minb, multi, sq; size_t smem_bytes; };
 
 int check_args(rthx_handle* h, const rthx_trace_args* a) {
   if (!a) return fail(h, RTHX_ERR_ARG, "trace: args is NULL");
@@ -530,12 +534,15 @@ LaunchPlan make_plan(const rthx_handle* h, const rthx_trace_args* a, int rank, i
   const size_t hist_bytes = sizeof(uint32_t) * (size_t)h->N, em_bytes = sizeof(double) * 16;
   pl.hist_in_smem = (coarse_bytes + em_bytes + hist_bytes <= h->prop.sharedMemPerBlockOptin) ? 1 : 0;
   if (const char* ev = std::getenv("RTHX_FORCE_GLOBAL_TALLY")) { if (std::atoi(ev)) pl.hist_in_smem = 0; }   // test knob: the N > ~57k path
+  pl.sq = (h->single_quad && a->locator != RTHX_LOCATOR_GENERIC && !pl.multi && pl.hist_in_smem) ? 1 : 0;
+  if (const char* ev = std::getenv("RTHX_NO_SQ")) { if (std::atoi(ev)) pl.sq = 0; }   // test / tuning knob
+  if (pl.sq) { pl.fast = 1; pl.minb = 4; }
   pl.smem_bytes = coarse_bytes + em_bytes + (pl.hist_in_smem ? hist_bytes : 0);
   const long long rows = (long long)pl.n_owned * a->n_bins;
   long long chunks = a->row_chunks;
   if (chunks <= 0) {
     // enough blocks for ~32 waves of the resident set, but keep >= 2048 rays (and >= N/2, the flush scan) per block
-    const int per_sm = std::max(1, trace_kernel_max_blocks_per_sm(pl.block_threads, pl.smem_bytes, pl.hist_in_smem != 0, pl.fast != 0, pl.minb, pl.multi != 0));
+    const int per_sm = std::max(1, trace_kernel_max_blocks_per_sm(pl.block_threads, pl.smem_bytes, pl.hist_in_smem != 0, pl.fast != 0, pl.minb, pl.multi != 0, pl.sq != 0));
     const long long target = (long long)h->prop.multiProcessorCount * per_sm * 32;
     chunks = rows > 0 ? (target + rows - 1) / rows : 1;
     const long long min_rays = std::max<long long>(2048, h->N / 2);
@@ -575,6 +582,7 @@ void fill_params(const rthx_handle* h, const rthx_trace_args* a, const LaunchPla
   P.seed = a->seed;
   P.nudge = a->nudge;
   P.rec_slot = nullptr; P.rec_pts = nullptr; P.rec_valid = nullptr;
+  P.face0 = h->face0;
   P.k_u52 = 1.0 - 0x1p-53; P.k_u32 = 1.0 - 0x1p-33; P.k_eps = 1e-10;
   uint32_t k0 = (uint32_t)a->seed, k1 = (uint32_t)(a->seed >> 32);
   for (int r = 0; r < 10; ++r) { P.rk[2 * r] = k0; P.rk[2 * r + 1] = k1; k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
@@ -630,7 +638,7 @@ int enqueue_trace(rthx_handle* h, const rthx_trace_args* a, int rank, int world,
   if (y1 < 0) y1 = pl.n_owned;
   P.y_offset = y0;
   const long long nb = (long long)(y1 - y0) * a->n_bins * pl.row_chunks;
-  CU(h, launch_trace_exchange(P, (int)nb, pl.block_threads, pl.smem_bytes, pl.fast != 0, pl.minb, stream));
+  CU(h, launch_trace_exchange(P, (int)nb, pl.block_threads, pl.smem_bytes, pl.fast != 0, pl.minb, pl.sq != 0, stream));
   if (nb > 0) *n_launches += 1;
   *plan_out = pl;
   return RTHX_OK;
@@ -647,7 +655,7 @@ int pipeline_launch(rthx_handle* h, const rthx_trace_args* a, int rank, int worl
   CU(h, ensure(&h->counts_dev, &h->counts_cap, (size_t)a->n_bins * (size_t)n_owned * N));
   LaunchPlan pl = make_plan(h, a, rank, world);
   // batches: >= ~6 waves of resident blocks each, at most 16
-  const int per_sm = std::max(1, trace_kernel_max_blocks_per_sm(pl.block_threads, pl.smem_bytes, pl.hist_in_smem != 0, pl.fast != 0, pl.minb, pl.multi != 0));
+  const int per_sm = std::max(1, trace_kernel_max_blocks_per_sm(pl.block_threads, pl.smem_bytes, pl.hist_in_smem != 0, pl.fast != 0, pl.minb, pl.multi != 0, pl.sq != 0));
   const long long resident = (long long)h->prop.multiProcessorCount * per_sm;
   int n_batches = (int)std::min<long long>(16, std::max<long long>(1, pl.n_blocks / (6 * resident)));
   n_batches = std::max(1, std::min(n_batches, n_owned));

@@ -91,13 +91,14 @@ struct TraceParams {
   double k_u32;   // 1 - 2^-33
   double k_eps;   // 1e-10, the near-parallel threshold of distToSurface2D.jl:10
   uint32_t rk[20];  // Philox round keys (key + r*W), two per round
+  CoarseDev face0;  // SQ kernels: the single coarse face, read from the parameter bank
 };
 
 // launchers implemented in rthx_kernels.cu
-cudaError_t launch_trace_exchange(const TraceParams& p, int n_blocks, int block_threads, size_t smem_bytes, bool fast, int minb,
+cudaError_t launch_trace_exchange(const TraceParams& p, int n_blocks, int block_threads, size_t smem_bytes, bool fast, int minb, bool sq,
                                   cudaStream_t stream);
 cudaError_t configure_trace_kernel(size_t smem_bytes);
 cudaError_t launch_fp64_peak(double* out, int n_blocks, int block_threads, int iters, cudaStream_t stream);
-int trace_kernel_max_blocks_per_sm(int block_threads, size_t smem_bytes, bool hist, bool fast, int minb, bool multi);
+int trace_kernel_max_blocks_per_sm(int block_threads, size_t smem_bytes, bool hist, bool fast, int minb, bool multi, bool sq);
 
 }  // namespace rthx

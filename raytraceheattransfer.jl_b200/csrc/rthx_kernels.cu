@@ -157,22 +157,24 @@ __device__ __forceinline__ double neg_log_unit(double x) {
 //                           axis instead of four per edge, and the sign of d·n picks the edge of each pair;
 //   triangles             : three edges.
 // The argmin runs on cross-multiplied fractions (first index on ties), one division at the end.
+__device__ __forceinline__ double dist_quad(const CoarseDev& f, double px, double py, double dx, double dy, double eps, int& k) {
+  const double n0x = f.nx[0], n0y = f.ny[0], n1x = f.nx[1], n1y = f.ny[1];
+  const double den0 = dx * n0x + dy * n0y, q0 = px * n0x + py * n0y;
+  const double den1 = dx * n1x + dy * n1y, q1 = px * n1x + py * n1y;
+  const bool p0 = den0 > 0.0, p1 = den1 > 0.0;
+  const double an0 = p0 ? f.h[0] - q0 : q0 - f.h[2], ad0 = fabs(den0);
+  const double an1 = p1 ? f.h[1] - q1 : q1 - f.h[3], ad1 = fabs(den1);
+  const int e0 = p0 ? 0 : 2, e1 = p1 ? 1 : 3;
+  const bool ok0 = (ad0 >= eps) & (an0 > 0.0), ok1 = (ad1 >= eps) & (an1 > 0.0);
+  const double l = an0 * ad1, r = an1 * ad0;
+  const bool take0 = ok0 & (!ok1 | (l < r) | ((l == r) & (e0 < e1)));
+  k = take0 ? e0 : e1;
+  const double an = take0 ? an0 : an1, ad = take0 ? ad0 : ad1;
+  return (ok0 | ok1) ? div_pos(an, ad) : CUDART_INF;
+}
+
 __device__ __forceinline__ double dist_fast(const CoarseDev& f, double px, double py, double dx, double dy, double eps, int& k) {
-  if (f.kind == KIND_AFFINE_QUAD) {
-    const double n0x = f.nx[0], n0y = f.ny[0], n1x = f.nx[1], n1y = f.ny[1];
-    const double den0 = dx * n0x + dy * n0y, q0 = px * n0x + py * n0y;
-    const double den1 = dx * n1x + dy * n1y, q1 = px * n1x + py * n1y;
-    const bool p0 = den0 > 0.0, p1 = den1 > 0.0;
-    const double an0 = p0 ? f.h[0] - q0 : q0 - f.h[2], ad0 = fabs(den0);
-    const double an1 = p1 ? f.h[1] - q1 : q1 - f.h[3], ad1 = fabs(den1);
-    const int e0 = p0 ? 0 : 2, e1 = p1 ? 1 : 3;
-    const bool ok0 = (ad0 >= eps) & (an0 > 0.0), ok1 = (ad1 >= eps) & (an1 > 0.0);
-    const double l = an0 * ad1, r = an1 * ad0;
-    const bool take0 = ok0 & (!ok1 | (l < r) | ((l == r) & (e0 < e1)));
-    k = take0 ? e0 : e1;
-    const double an = take0 ? an0 : an1, ad = take0 ? ad0 : ad1;
-    return (ok0 | ok1) ? div_pos(an, ad) : CUDART_INF;
-  }
+  if (f.kind == KIND_AFFINE_QUAD) return dist_quad(f, px, py, dx, dy, eps, k);
   double bn = 1.0, bd = 0.0;
   int bk = 0;
 #pragma unroll
@@ -251,6 +253,15 @@ __device__ __forceinline__ int locate_affine(const TraceParams& p, const CoarseD
   return __ldg(p.lattice + cf.lat_off + cell);
 }
 
+// the same for a face known to be a parallelogram lattice (fine index = n + m Nx, meshQuad.jl:139,151)
+__device__ __forceinline__ int locate_quad(const CoarseDev& cf, double px, double py) {
+  const double rx = px - cf.ax, ry = py - cf.ay;
+  const double s = rx * cf.g1x + ry * cf.g1y, t = rx * cf.g2x + ry * cf.g2y;
+  const int n = __double2int_rd(s), m = __double2int_rd(t);
+  if (!((s >= 0.0) & (t >= 0.0) & (n < cf.Nx) & (m < cf.Ny))) return -1;
+  return n + m * cf.Nx;
+}
+
 template <bool FAST>
 __device__ __forceinline__ int locate_fine(const TraceParams& p, const CoarseDev& cf, int c, int kind, double px, double py) {
   if (!FAST && kind == KIND_GENERIC) return find_face_generic(p, 1 + c, px, py);
@@ -270,11 +281,15 @@ __device__ __forceinline__ int locate_fine(const TraceParams& p, const CoarseDev
 //   both           : [12,13] cell midPoint
 constexpr int EM_DOUBLES = 16;
 
-template <bool HIST_SMEM, bool FAST, int MINB, bool MULTI>
+//   MULTI    : RTHX_MULTI_BOUNCE event loop
+//   SQ       : the whole domain is ONE parallelogram coarse face (every square / rectangular enclosure): its descriptor
+//              is read from the kernel-parameter bank (FP64 instructions take c[0][..] operands: no LDS, no address
+//              arithmetic), there is no coarse-face loop and no per-face kind dispatch
+template <bool HIST_SMEM, bool FAST, int MINB, bool MULTI, bool SQ>
 __global__ void __launch_bounds__(256, MINB) trace_exchange_kernel(const __grid_constant__ TraceParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   CoarseDev* s_coarse = reinterpret_cast<CoarseDev*>(smem_raw);
-  const bool coarse_smem = FAST || p.coarse_in_smem;
+  const bool coarse_smem = !SQ && (FAST || p.coarse_in_smem);
   const size_t coarse_bytes = coarse_smem ? sizeof(CoarseDev) * (size_t)p.n_coarse : 0;
   double* s_em = reinterpret_cast<double*>(smem_raw + coarse_bytes);
   uint32_t* hist = reinterpret_cast<uint32_t*>(smem_raw + coarse_bytes + sizeof(double) * EM_DOUBLES);
@@ -395,6 +410,34 @@ __global__ void __launch_bounds__(256, MINB) trace_exchange_kernel(const __grid_
     double neg_log = FAST ? neg_log_unit(R_S) : -log(R_S);
     int c = c0;
     int absorber = -1;
+    if constexpr (SQ) {
+      // single parallelogram face: one distToSurface2D, one decision, one fine-cell location (traceRay.jl:27-52)
+      const CoarseDev& cf = p.face0;
+      int k;
+      const double u = dist_quad(cf, px, py, dx, dy, p.k_eps, k);
+      double S = neg_log * inv_beta_u;
+      bool gas = S < u, ok = true;
+      if (!uniform) {
+        const int f0 = locate_quad(cf, px, py);              // traceRay.jl:87-100
+        ok = f0 >= 0;
+        const double local_beta = ok ? beta_band[f0] : 0.0;
+        gas = local_beta * u >= neg_log;
+        S = neg_log / local_beta;
+      }
+      if (ok) {
+        if (gas) {
+          px = fma(S - p.nudge, dx, px);
+          py = fma(S - p.nudge, dy, py);
+          const int f = locate_quad(cf, px, py);
+          if (f >= 0) absorber = p.n_surfaces + f;
+        } else if ((u < CUDART_INF) && cf.solid[k]) {        // an open edge has no neighbour face: the ray is lost
+          px = fma(u - p.nudge, dx, px);
+          py = fma(u - p.nudge, dy, py);
+          const int f = locate_quad(cf, px, py);
+          if (f >= 0) absorber = __ldg(p.cell_surf_id + 4 * f + k);
+        }
+      }
+    } else {
     double hit_nx = 0.0, hit_ny = 0.0;   // MULTI: outward unit normal of the wall that was hit
 #pragma unroll 1
     for (int event = 0;; ++event) {
@@ -499,6 +542,7 @@ __global__ void __launch_bounds__(256, MINB) trace_exchange_kernel(const __grid_
     }
     neg_log = -log(u52(v1.z, v1.w, p.k_u52));
     }
+    }
 
     // ---- stage 3/4: tally (+ record) -------------------------------------------------------------------------
     if (absorber >= 0) {
@@ -536,41 +580,43 @@ __global__ void __launch_bounds__(256, MINB) trace_exchange_kernel(const __grid_
 
 // kernel variants: hist_in_smem x fast x multi; the register bound MINB only varies for the hot FIRST_INTERACTION FAST kernel
 typedef void (*TraceKernel)(const TraceParams);
-static TraceKernel kernel_variant(bool hist, bool fast, int minb, bool multi) {
+static TraceKernel kernel_variant(bool hist, bool fast, int minb, bool multi, bool sq) {
+  if (sq && hist && fast && !multi) return (TraceKernel)trace_exchange_kernel<true, true, 4, false, true>;
   if (multi) {
-    if (hist) return fast ? (TraceKernel)trace_exchange_kernel<true, true, 2, true> : (TraceKernel)trace_exchange_kernel<true, false, 2, true>;
-    return fast ? (TraceKernel)trace_exchange_kernel<false, true, 2, true> : (TraceKernel)trace_exchange_kernel<false, false, 2, true>;
+    if (hist) return fast ? (TraceKernel)trace_exchange_kernel<true, true, 2, true, false> : (TraceKernel)trace_exchange_kernel<true, false, 2, true, false>;
+    return fast ? (TraceKernel)trace_exchange_kernel<false, true, 2, true, false> : (TraceKernel)trace_exchange_kernel<false, false, 2, true, false>;
   }
-  if (!hist) return fast ? (TraceKernel)trace_exchange_kernel<false, true, 2, false> : (TraceKernel)trace_exchange_kernel<false, false, 2, false>;
-  if (!fast) return (TraceKernel)trace_exchange_kernel<true, false, 2, false>;
+  if (!hist) return fast ? (TraceKernel)trace_exchange_kernel<false, true, 2, false, false> : (TraceKernel)trace_exchange_kernel<false, false, 2, false, false>;
+  if (!fast) return (TraceKernel)trace_exchange_kernel<true, false, 2, false, false>;
   switch (minb) {
-    case 3: return (TraceKernel)trace_exchange_kernel<true, true, 3, false>;
-    case 4: return (TraceKernel)trace_exchange_kernel<true, true, 4, false>;
-    default: return (TraceKernel)trace_exchange_kernel<true, true, 2, false>;
+    case 3: return (TraceKernel)trace_exchange_kernel<true, true, 3, false, false>;
+    case 4: return (TraceKernel)trace_exchange_kernel<true, true, 4, false, false>;
+    default: return (TraceKernel)trace_exchange_kernel<true, true, 2, false, false>;
   }
 }
 
 cudaError_t configure_trace_kernel(size_t smem_bytes) {
-  for (int multi = 0; multi < 2; ++multi)
-    for (int hist = 0; hist < 2; ++hist)
-      for (int fast = 0; fast < 2; ++fast)
-        for (int minb = 2; minb <= 4; ++minb) {
-          cudaError_t e = cudaFuncSetAttribute((const void*)kernel_variant(hist, fast, minb, multi), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-          if (e != cudaSuccess) return e;
-        }
+  for (int sq = 0; sq < 2; ++sq)
+    for (int multi = 0; multi < 2; ++multi)
+      for (int hist = 0; hist < 2; ++hist)
+        for (int fast = 0; fast < 2; ++fast)
+          for (int minb = 2; minb <= 4; ++minb) {
+            cudaError_t e = cudaFuncSetAttribute((const void*)kernel_variant(hist, fast, minb, multi, sq), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+            if (e != cudaSuccess) return e;
+          }
   return cudaSuccess;
 }
 
-int trace_kernel_max_blocks_per_sm(int block_threads, size_t smem_bytes, bool hist, bool fast, int minb, bool multi) {
+int trace_kernel_max_blocks_per_sm(int block_threads, size_t smem_bytes, bool hist, bool fast, int minb, bool multi, bool sq) {
   int n = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, (const void*)kernel_variant(hist, fast, minb, multi), block_threads, smem_bytes) != cudaSuccess) return 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, (const void*)kernel_variant(hist, fast, minb, multi, sq), block_threads, smem_bytes) != cudaSuccess) return 0;
   return n;
 }
 
-cudaError_t launch_trace_exchange(const TraceParams& p, int n_blocks, int block_threads, size_t smem_bytes, bool fast, int minb,
+cudaError_t launch_trace_exchange(const TraceParams& p, int n_blocks, int block_threads, size_t smem_bytes, bool fast, int minb, bool sq,
                                   cudaStream_t stream) {
   if (n_blocks <= 0) return cudaSuccess;
-  TraceKernel k = kernel_variant(p.hist_in_smem != 0, fast, minb, p.multi_bounce != 0);
+  TraceKernel k = kernel_variant(p.hist_in_smem != 0, fast, minb, p.multi_bounce != 0, sq);
   void* args[] = {(void*)&p};
   return cudaLaunchKernel((const void*)k, dim3(n_blocks), dim3(block_threads), args, smem_bytes, stream);
 }
