@@ -10,7 +10,7 @@ namespace rthx {
 enum : int { KIND_GENERIC = 0, KIND_AFFINE_QUAD = 1, KIND_AFFINE_TRI = 2 };
 
 // One coarse face (user polygon).  Staged in shared memory by every thread block when the whole array fits.
-struct CoarseDev {
+struct alignas(16) CoarseDev {
   double vx[4], vy[4];   // CCW vertices
   double nx[4], ny[4];   // unit outward edge normals (the reference's `inwardNormals`, calculateInwardNormal.jl:1-12)
   double h[4];           // plane offsets: quads h0 = v0·n0, h1 = v1·n1, h2 = v2·n0, h3 = v3·n1 (slab form); else h_i = v_i·n_i
@@ -26,7 +26,7 @@ struct CoarseDev {
   uint8_t solid[4];
   int32_t pad_;
 };
-static_assert(sizeof(CoarseDev) % 8 == 0, "CoarseDev must stay 8-byte sized");
+static_assert(sizeof(CoarseDev) % 16 == 0, "CoarseDev must stay a multiple of 16 bytes (shared-memory layout behind it)");
 
 // Uniform-grid face set for the reference-faithful locator (spatialAccelerations.jl:2-59).
 // Set 0 = coarse mesh, set 1+c = fine cells of coarse face c.

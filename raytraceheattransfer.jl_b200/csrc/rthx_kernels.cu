@@ -123,6 +123,88 @@ __device__ __forceinline__ double cos2pi_unit(double R) {
   return z * p;
 }
 
+// -log(x) by table: x = 2^e m, m in [1,2) falls in one of 64 intervals with midpoint c_i; with r = m/c_i - 1 (|r| <= 2^-7)
+//   log x = e ln2 + log c_i + log1p(r),   log1p(r) = r - r^2/2 + ... + r^7/7   (truncation < 2^-59)
+// 11 FP64 instructions instead of ~30 for the fdlibm form below (the FP64 pipe is the busiest unit of the kernel).
+// Absolute error <= 2e-15 on -log x <= 37 (relative <= 1e-16 except within 1e-10 of x = 1, where the free path itself
+// is ~1e-10 and an absolute 1e-16 is immaterial).  The (1/c_i, log c_i) pairs are staged into shared memory per block.
+__constant__ double2 c_logtab[64] = {
+    {0x1.fc07f01fc07f0p-1, 0x1.fe02a6b106789p-8},
+    {0x1.f44659e4a4271p-1, 0x1.7b91b07d5b11bp-6},
+    {0x1.ecc07b301ecc0p-1, 0x1.39e87b9febd60p-5},
+    {0x1.e573ac901e574p-1, 0x1.b42dd711971bfp-5},
+    {0x1.de5d6e3f8868ap-1, 0x1.16536eea37ae1p-4},
+    {0x1.d77b654b82c34p-1, 0x1.51b073f06183fp-4},
+    {0x1.d0cb58f6ec074p-1, 0x1.8c345d6319b21p-4},
+    {0x1.ca4b3055ee191p-1, 0x1.c5e548f5bc743p-4},
+    {0x1.c3f8f01c3f8f0p-1, 0x1.fec9131dbeabbp-4},
+    {0x1.bdd2b899406f7p-1, 0x1.1b72ad52f67a0p-3},
+    {0x1.b7d6c3dda338bp-1, 0x1.371fc201e8f74p-3},
+    {0x1.b2036406c80d9p-1, 0x1.526e5e3a1b438p-3},
+    {0x1.ac5701ac5701bp-1, 0x1.6d60fe719d21dp-3},
+    {0x1.a6d01a6d01a6dp-1, 0x1.87fa06520c911p-3},
+    {0x1.a16d3f97a4b02p-1, 0x1.a23bc1fe2b563p-3},
+    {0x1.9c2d14ee4a102p-1, 0x1.bc286742d8cd6p-3},
+    {0x1.970e4f80cb872p-1, 0x1.d5c216b4fbb91p-3},
+    {0x1.920fb49d0e229p-1, 0x1.ef0adcbdc5936p-3},
+    {0x1.8d3018d3018d3p-1, 0x1.0402594b4d041p-2},
+    {0x1.886e5f0abb04ap-1, 0x1.1058bf9ae4ad5p-2},
+    {0x1.83c977ab2beddp-1, 0x1.1c898c16999fbp-2},
+    {0x1.7f405fd017f40p-1, 0x1.2895a13de86a3p-2},
+    {0x1.7ad2208e0ecc3p-1, 0x1.347dd9a987d55p-2},
+    {0x1.767dce434a9b1p-1, 0x1.404308686a7e4p-2},
+    {0x1.724287f46debcp-1, 0x1.4be5f957778a1p-2},
+    {0x1.6e1f76b4337c7p-1, 0x1.5767717455a6cp-2},
+    {0x1.6a13cd1537290p-1, 0x1.62c82f2b9c795p-2},
+    {0x1.661ec6a5122f9p-1, 0x1.6e08eaa2ba1e4p-2},
+    {0x1.623fa77016240p-1, 0x1.792a55fdd47a2p-2},
+    {0x1.5e75bb8d015e7p-1, 0x1.842d1da1e8b17p-2},
+    {0x1.5ac056b015ac0p-1, 0x1.8f11e873662c7p-2},
+    {0x1.571ed3c506b3ap-1, 0x1.99d958117e08bp-2},
+    {0x1.5390948f40febp-1, 0x1.a484090e5bb0ap-2},
+    {0x1.5015015015015p-1, 0x1.af1293247786bp-2},
+    {0x1.4cab88725af6ep-1, 0x1.b9858969310fbp-2},
+    {0x1.49539e3b2d067p-1, 0x1.c3dd7a7cdad4dp-2},
+    {0x1.460cbc7f5cf9ap-1, 0x1.ce1af0b85f3ebp-2},
+    {0x1.42d6625d51f87p-1, 0x1.d83e7258a2f3ep-2},
+    {0x1.3fb013fb013fbp-1, 0x1.e24881a7c6c26p-2},
+    {0x1.3c995a47babe7p-1, 0x1.ec399d2468cc0p-2},
+    {0x1.3991c2c187f63p-1, 0x1.f6123fa7028acp-2},
+    {0x1.3698df3de0748p-1, 0x1.ffd2e0857f498p-2},
+    {0x1.33ae45b57bcb2p-1, 0x1.04bdf9da926d2p-1},
+    {0x1.30d190130d190p-1, 0x1.0986f4f573521p-1},
+    {0x1.2e025c04b8097p-1, 0x1.0e44985d1cc8cp-1},
+    {0x1.2b404ad012b40p-1, 0x1.12f719593efbcp-1},
+    {0x1.288b01288b013p-1, 0x1.179eabbd899a1p-1},
+    {0x1.25e22708092f1p-1, 0x1.1c3b81f713c25p-1},
+    {0x1.23456789abcdfp-1, 0x1.20cdcd192ab6ep-1},
+    {0x1.20b470c67c0d9p-1, 0x1.2555bce98f7cbp-1},
+    {0x1.1e2ef3b3fb874p-1, 0x1.29d37fec2b08bp-1},
+    {0x1.1bb4a4046ed29p-1, 0x1.2e47436e40268p-1},
+    {0x1.19453808ca29cp-1, 0x1.32b1339121d71p-1},
+    {0x1.16e0689427379p-1, 0x1.37117b54747b6p-1},
+    {0x1.1485f0e0acd3bp-1, 0x1.3b68449fffc23p-1},
+    {0x1.12358e75d3033p-1, 0x1.3fb5b84d16f42p-1},
+    {0x1.0fef010fef011p-1, 0x1.43f9fe2f9ce67p-1},
+    {0x1.0db20a88f4696p-1, 0x1.48353d1ea88dfp-1},
+    {0x1.0b7e6ec259dc8p-1, 0x1.4c679afccee3ap-1},
+    {0x1.0953f39010954p-1, 0x1.50913cc01686bp-1},
+    {0x1.073260a47f7c6p-1, 0x1.54b2467999498p-1},
+    {0x1.05197f7d73404p-1, 0x1.58cadb5cd7989p-1},
+    {0x1.03091b51f5e1ap-1, 0x1.5cdb1dc6c1765p-1},
+    {0x1.0101010101010p-1, 0x1.60e32f44788d9p-1}};
+
+__device__ __forceinline__ double neg_log_table(double x, const double2* __restrict__ tab) {
+  const int hi = __double2hiint(x), lo = __double2loint(x);
+  const int e = (hi >> 20) - 1023;
+  const double m = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, lo);
+  const double2 t = tab[(hi >> 14) & 63];
+  const double r = fma(m, t.x, -1.0);
+  const double P = fma(r, fma(r, fma(r, fma(r, fma(r, 0x1.2492492492492p-3, -0x1.5555555555555p-3), 0x1.999999999999ap-3), -0.25),
+                              0x1.5555555555555p-2), -0.5);
+  return -(fma((double)e, 0x1.62e42fefa39efp-1, t.y) + fma(r * r, P, r));
+}
+
 // -log(x) for a normal double x in (0,1) (the uniforms of the RNG contract are >= 2^-53): fdlibm's algorithm without
 // the subnormal / special-case branches; s = f/(2+f) by MUFU.RCP64H + two Newton steps.  Error < 2 ulp.
 __device__ __forceinline__ double neg_log_unit(double x) {
@@ -292,7 +374,8 @@ __global__ void __launch_bounds__(256, MINB) trace_exchange_kernel(const __grid_
   const bool coarse_smem = !SQ && (FAST || p.coarse_in_smem);
   const size_t coarse_bytes = coarse_smem ? sizeof(CoarseDev) * (size_t)p.n_coarse : 0;
   double* s_em = reinterpret_cast<double*>(smem_raw + coarse_bytes);
-  uint32_t* hist = reinterpret_cast<uint32_t*>(smem_raw + coarse_bytes + sizeof(double) * EM_DOUBLES);
+  double2* s_log = reinterpret_cast<double2*>(smem_raw + coarse_bytes + sizeof(double) * EM_DOUBLES);
+  uint32_t* hist = reinterpret_cast<uint32_t*>(smem_raw + coarse_bytes + sizeof(double) * EM_DOUBLES + sizeof(double2) * 64);
 
   // block -> (owned emitter ordinal y, traced bin bi, ray chunk)
   const unsigned bid = blockIdx.x;
@@ -313,6 +396,7 @@ __global__ void __launch_bounds__(256, MINB) trace_exchange_kernel(const __grid_
   }
   if (HIST_SMEM)
     for (int i = threadIdx.x; i < N; i += blockDim.x) hist[i] = 0u;
+  if (FAST && threadIdx.x < 64) s_log[threadIdx.x] = c_logtab[threadIdx.x];
   // FAST: a plain shared-memory pointer (LDS); otherwise a generic pointer that may be shared or global
   const CoarseDev* coarse = FAST ? s_coarse : (p.coarse_in_smem ? s_coarse : p.coarse);
 
@@ -407,7 +491,7 @@ __global__ void __launch_bounds__(256, MINB) trace_exchange_kernel(const __grid_
     // ---- stage 2: first-interaction traversal (traceRayUniform / traceRayVariable) --------------------------
     // MULTI (RTHX_MULTI_BOUNCE): the traversal is repeated from every scattering / reflection event until the ray is
     // absorbed (traceSingleRay.jl:7-81 without the re-emission branches); otherwise the body runs exactly once.
-    double neg_log = FAST ? neg_log_unit(R_S) : -log(R_S);
+    double neg_log = FAST ? neg_log_table(R_S, s_log) : -log(R_S);
     int c = c0;
     int absorber = -1;
     if constexpr (SQ) {
