@@ -88,29 +88,23 @@ __device__ __forceinline__ double dist_to_coarse(const CoarseDev& f, double px, 
 __constant__ double c_sinpi[9] = {  // sin(pi z) = z * P(z^2), |z| <= 1/2, max abs error 2.2e-16 (Chebyshev fit, mpmath)
     0x1.921fb54442d18p+1, -0x1.4abbce625be52p+2, 0x1.466bc6775aa7dp+1, -0x1.32d2cce627c86p-1, 0x1.5078348551854p-4,
     -0x1.e3074dfaf87afp-8, 0x1.e8f3675ee37ddp-12, -0x1.6f7acdb8f6580p-16, 0x1.9d462020fcc78p-21};
-__constant__ double c_log[9] = {    // fdlibm e_log.c: Lg1..Lg7, ln2_hi, ln2_lo
-    6.666666666666735130e-01, 3.999999999940941908e-01, 2.857142874366239149e-01, 2.222219843214978396e-01,
-    1.818357216161805012e-01, 1.531383769920937332e-01, 1.479819860511658591e-01,
-    6.93147180369123816490e-01, 1.90821492927058770002e-10};
 
 // sqrt(x) and a/b for well-scaled positive normal operands (variates in (0,1), geometric ratios): MUFU seed + Newton,
 // without libdevice's special-case branch (which splits the basic block and blocks instruction interleaving).
-// Both are accurate to <= 1 ulp; neither is used where x or b can be 0, Inf or subnormal.
+// Accurate to <= 2 ulp (sqrt) / 1 ulp (div); neither is used where x or b can be 0, Inf or subnormal.
 __device__ __forceinline__ double sqrt_pos(double x) {
   double y;
-  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  const double e = fma(-x, y * y, 1.0);                 // 1 - x y^2
-  y = fma(fma(e, 0.375, 0.5), y * e, y);                // y (1 + e/2 + 3 e^2/8)
-  const double g = x * y;
-  return fma(fma(-g, g, x), 0.5 * y, g);
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));   // MUFU.RSQ64H: ~2^-20 relative
+  const double e = fma(-x, y * y, 1.0);                     // 1 - x y^2
+  y = fma(fma(e, 0.375, 0.5), y * e, y);                    // y (1 + e/2 + 3 e^2/8): ~2^-58
+  return x * y;
 }
 __device__ __forceinline__ double div_pos(double a, double b) {
   double r;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
-  r = fma(r, fma(-b, r, 1.0), r);
-  r = fma(r, fma(-b, r, 1.0), r);
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));     // MUFU.RCP64H: ~2^-20 relative
+  r = fma(r, fma(-b, r, 1.0), r);                           // ~2^-40
   const double q = a * r;
-  return fma(r, fma(-b, q, a), q);
+  return fma(r, fma(-b, q, a), q);                          // residual correction: <= 1 ulp
 }
 
 // cos(2 pi R) for R in (0,1): with x = 2R - 1 in (-1,1), cos(2 pi R) = -cos(pi x) = sin(pi (|x| - 1/2)); branch-free.
@@ -203,34 +197,6 @@ __device__ __forceinline__ double neg_log_table(double x, const double2* __restr
   const double P = fma(r, fma(r, fma(r, fma(r, fma(r, 0x1.2492492492492p-3, -0x1.5555555555555p-3), 0x1.999999999999ap-3), -0.25),
                               0x1.5555555555555p-2), -0.5);
   return -(fma((double)e, 0x1.62e42fefa39efp-1, t.y) + fma(r * r, P, r));
-}
-
-// -log(x) for a normal double x in (0,1) (the uniforms of the RNG contract are >= 2^-53): fdlibm's algorithm without
-// the subnormal / special-case branches; s = f/(2+f) by MUFU.RCP64H + two Newton steps.  Error < 2 ulp.
-__device__ __forceinline__ double neg_log_unit(double x) {
-  int hi = __double2hiint(x);
-  const int lo = __double2loint(x);
-  int e = (hi >> 20) - 1023;
-  hi = (hi & 0x000FFFFF) | 0x3FF00000;
-  const bool big = hi >= 0x3FF6A09F;        // m > sqrt(2): halve it
-  hi = big ? hi - 0x00100000 : hi;
-  e = big ? e + 1 : e;
-  const double m = __hiloint2double(hi, lo);
-  const double f = m - 1.0, d = m + 1.0;
-  double r;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
-  r = fma(r, fma(-d, r, 1.0), r);
-  r = fma(r, fma(-d, r, 1.0), r);
-  double sq = f * r;
-  sq = fma(r, fma(-d, sq, f), sq);          // s = f/d, correctly rounded to ~1 ulp
-  const double z = sq * sq, w = z * z;
-  const double t1 = w * fma(w, fma(w, c_log[5], c_log[3]), c_log[1]);
-  const double t2 = z * fma(w, fma(w, fma(w, c_log[6], c_log[4]), c_log[2]), c_log[0]);
-  const double R = t2 + t1;
-  const double hfsq = 0.5 * f * f;
-  const double dk = (double)e;
-  // log(x) = dk*ln2_hi - ((hfsq - (s*(hfsq+R) + dk*ln2_lo)) - f)
-  return fma(-dk, c_log[7], (hfsq - fma(sq, hfsq + R, dk * c_log[8])) - f);
 }
 
 // distToSurface2D on a coarse face, FAST path.  The emission / crossing point is inside the face, so edge i can
