@@ -33,7 +33,7 @@ FLOP_SG, FLOP_SW, FLOP_VG, FLOP_VW, FLOP_CROSS = 90.0, 138.0, 98.0, 146.0, 65.0
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="rthx", choices=["rthx", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
@@ -120,7 +120,7 @@ class ClockSampler(threading.Thread):
             for line in self.proc.stdout:
                 if self._stop.is_set():
                     break
-                self.rows.append([x.strip() for x in line.split(",")])
+                self.rows.append((time.monotonic(), [x.strip() for x in line.split(",")]))
         except Exception:
             pass
 
@@ -132,10 +132,13 @@ class ClockSampler(threading.Thread):
             except Exception:
                 pass
 
-    def summary(self):
+    def summary(self, t0=None, t1=None):
+        """Median SM clock and active throttle reasons over the samples taken inside [t0, t1] (the timed region)."""
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for ts, r in self.rows:
+            if (t0 is not None and ts < t0) or (t1 is not None and ts > t1):
+                continue
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
                 for nm, v in zip(names, r[3:7]):
@@ -240,21 +243,24 @@ def main():
         torch.cuda.synchronize(dev)
 
     # ---- device-resident timing ------------------------------------------------------------------------------
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()                      # nvidia-smi needs ~0.5 s to deliver its first sample: start before warm-up
     for w in range(args.warmup):
         st = step(1000 + w)
     barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    if sampler:
-        sampler.start()
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_win0 = time.monotonic()
     e0.record(stream)
     for s in range(args.steps):
         st = step(2000 + s, kev[s])
     e1.record(stream)
     barrier()
+    t_win1 = time.monotonic()
     if sampler:
+        time.sleep(0.15)
         sampler.stop()
     total_ms = e0.elapsed_time(e1)
     kernel_ms = sum(a.elapsed_time(b) for a, b in kev) / max(1, args.steps)
@@ -395,7 +401,7 @@ def main():
                    "l2": "count matrix (8*N*N bytes) exceeds the 126 MB L2 for cfg3; a fresh Philox seed every step",
                    "launch": {k: st[k] for k in ("n_blocks", "block_threads", "row_chunks", "smem_bytes", "hist_in_smem")}},
         "roofline": roofline, "smoothing": smoothing, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps * world,
-        "clocks": sampler.summary() if sampler else None,
+        "clocks": sampler.summary(t_win0, t_win1 + 0.1) if sampler else None,
         "check": {"tallied_last_step": tallied, "lost_last_step": lost_total},
     }
     print(json.dumps(line))

@@ -188,15 +188,17 @@ __constant__ double2 c_logtab[64] = {
     {0x1.03091b51f5e1ap-1, 0x1.5cdb1dc6c1765p-1},
     {0x1.0101010101010p-1, 0x1.60e32f44788d9p-1}};
 
+__constant__ double c_l1p[6] = {0x1.2492492492492p-3 /* 1/7 */, -0x1.5555555555555p-3 /* -1/6 */, 0x1.999999999999ap-3 /* 1/5 */,
+                                0x1.5555555555555p-2 /* 1/3 */, 0x1.62e42fefa39efp-1 /* ln 2 */, 0.0};
+
 __device__ __forceinline__ double neg_log_table(double x, const double2* __restrict__ tab) {
   const int hi = __double2hiint(x), lo = __double2loint(x);
   const int e = (hi >> 20) - 1023;
   const double m = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, lo);
   const double2 t = tab[(hi >> 14) & 63];
   const double r = fma(m, t.x, -1.0);
-  const double P = fma(r, fma(r, fma(r, fma(r, fma(r, 0x1.2492492492492p-3, -0x1.5555555555555p-3), 0x1.999999999999ap-3), -0.25),
-                              0x1.5555555555555p-2), -0.5);
-  return -(fma((double)e, 0x1.62e42fefa39efp-1, t.y) + fma(r * r, P, r));
+  const double P = fma(r, fma(r, fma(r, fma(r, fma(r, c_l1p[0], c_l1p[1]), c_l1p[2]), -0.25), c_l1p[3]), -0.5);
+  return -(fma((double)e, c_l1p[4], t.y) + fma(r * r, P, r));
 }
 
 // distToSurface2D on a coarse face, FAST path.  The emission / crossing point is inside the face, so edge i can
