@@ -313,23 +313,36 @@ class SharedHostMatrix:
     link, overlapped with tracing, and rank 0 reads the assembled matrix after a barrier — no device-side gather."""
 
     def __init__(self, name: str, shape, create: bool):
-        from multiprocessing import shared_memory
+        from multiprocessing import shared_memory, resource_tracker
         nbytes = int(np.prod(shape)) * 8
+        if create:
+            try:                                   # a stale segment of a crashed run
+                old = shared_memory.SharedMemory(name=name, create=False)
+                old.close(); old.unlink()
+            except FileNotFoundError:
+                pass
         self.shm = shared_memory.SharedMemory(name=name, create=create, size=nbytes)
+        if not create:
+            try:                                   # Python < 3.13 would unlink the segment when an attaching process exits
+                resource_tracker.unregister(self.shm._name, "shared_memory")
+            except Exception:
+                pass
         self.owner = create
         self.array = np.ndarray(shape, dtype=np.uint64, buffer=self.shm.buf)
         L = load_library()
-        rc = L.rthx_host_register(C.c_void_p(self.array.ctypes.data), nbytes)
-        if rc != 0:
-            msg = L.rthx_last_error(None)
-            raise RthxError(f"rthx_host_register failed ({rc}): {msg.decode() if msg else ''}")
         self._L = L
+        self.registered = L.rthx_host_register(C.c_void_p(self.array.ctypes.data), nbytes) == 0
+        # not page-locked (e.g. locked-memory limit): the library's pinned staging path still serves it
 
     def close(self):
         if getattr(self, "shm", None) is not None:
-            self._L.rthx_host_unregister(C.c_void_p(self.array.ctypes.data))
+            if self.registered:
+                self._L.rthx_host_unregister(C.c_void_p(self.array.ctypes.data))
             self.array = None
             self.shm.close()
             if self.owner:
-                self.shm.unlink()
+                try:
+                    self.shm.unlink()
+                except FileNotFoundError:
+                    pass
             self.shm = None
