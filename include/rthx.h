@@ -185,7 +185,8 @@ int rthx_get_info(const rthx_handle* h, rthx_info* info);
  * for all `bins` at once: counts_out[b][i][j] = number of rays of emitter i whose first interaction is
  * element j; lost_out[b][i] = rays dropped.  The caller forms F = counts / rowsum exactly as
  * parallelRayTracing.jl:144-146 + row_normalize! :161-169 compose.
- *   counts_out: [n_bins*N*N] uint64, lost_out: [n_bins*N] uint64 (may be NULL), rec / stats may be NULL.
+ *   counts_out: [n_bins*N*N] uint64 (NULL: leave the counts on the device for rthx_counts_csr / rthx_smooth_F),
+ *   lost_out: [n_bins*N] uint64 (may be NULL), rec / stats may be NULL.
  * With emitter_world > 1 only the rows this call owns are written; the other rows of counts_out are NOT touched, so
  * several ranks (processes) can fill one matrix in shared host memory, each copying its rows over its own PCIe link.
  * Pinned / registered destinations are written by DMA directly; pageable ones go through internal pinned staging. */
@@ -233,6 +234,17 @@ typedef struct rthx_smooth_stats {
 } rthx_smooth_stats;
 int rthx_smooth_F(rthx_handle* h, int source, const void* src_host, int bin, int n, const double* w, int max_iters,
                   double target, int measure_pass, double* F_out, rthx_smooth_stats* stats);
+
+/* Sparse (CSR) read-out of the counts still resident on the device from the last rthx_trace_exchange on this handle
+ * (all emitters): per row the non-zero absorber columns in ascending order — exactly the triplets the reference
+ * feeds to sparse(I, J, V) (parallelRayTracing.jl:144-154) — compacted on the device, so optically thick meshes
+ * (test/test_2d_diffusion.jl:64) never move their N^2 zeros.  rthx_trace_exchange accepts counts_out == NULL for
+ * callers that only want this view.
+ *   rthx_counts_nnz : number of non-zeros of traced bin `bin` (also prepares the row pointers on the device);
+ *   rthx_counts_csr : row_ptr [N+1], cols [nnz], vals [nnz] (may be NULL), F_vals [nnz] = count / row total (may be
+ *                     NULL; this is the row-normalised F of row_normalize!, :161-169), row_lost not included. */
+int rthx_counts_nnz(rthx_handle* h, int bin, int64_t* nnz_out);
+int rthx_counts_csr(rthx_handle* h, int bin, int64_t* row_ptr, int32_t* cols, uint64_t* vals, double* F_vals);
 
 /* Peer-memory plumbing for the fused flush in one-process-per-GPU runs: rank 0 allocates the UInt64 count matrix
  * with rthx_shared_alloc and publishes the 64-byte CUDA IPC handle; every other rank maps it with rthx_shared_open

@@ -82,5 +82,5 @@ EXPORTED_SYMBOLS = (
     "rthx_create", "rthx_destroy", "rthx_get_info", "rthx_trace_exchange", "rthx_trace_exchange_device",
     "rthx_trace_exchange_multi", "rthx_measure_fp64_peak", "rthx_last_error", "rthx_version",
     "rthx_shared_alloc", "rthx_shared_open", "rthx_shared_close", "rthx_shared_free", "rthx_release_cached",
-    "rthx_smooth_F", "rthx_host_register", "rthx_host_unregister",
+    "rthx_smooth_F", "rthx_host_register", "rthx_host_unregister", "rthx_counts_nnz", "rthx_counts_csr",
 )

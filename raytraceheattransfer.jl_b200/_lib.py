@@ -96,6 +96,10 @@ def load_library():
                                 c_f64p, C.POINTER(rthx_smooth_stats)]
     L.rthx_release_cached.restype = C.c_int
     L.rthx_release_cached.argtypes = []
+    L.rthx_counts_nnz.restype = C.c_int
+    L.rthx_counts_nnz.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int64)]
+    L.rthx_counts_csr.restype = C.c_int
+    L.rthx_counts_csr.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int64), c_i32p, c_u64p, c_f64p]
     L.rthx_host_register.restype = C.c_int
     L.rthx_host_register.argtypes = [C.c_void_p, C.c_uint64]
     L.rthx_host_unregister.restype = C.c_int
@@ -171,17 +175,20 @@ class DeviceTracer:
         except Exception:
             pass
 
-    def trace(self, rays_per_emitter: int, counts_out: Optional[np.ndarray] = None, **kw):
+    def trace(self, rays_per_emitter: int, counts_out: Optional[np.ndarray] = None, dense: bool = True, **kw):
         """Blocking trace with host outputs (rthx_trace_exchange).  Returns a dict with counts [nb,N,N] u64,
-        lost [nb,N] u64, stats, and origins/endpoints when rec_ids is given."""
+        lost [nb,N] u64, stats, and origins/endpoints when rec_ids is given.  dense=False leaves the counts on the
+        device (counts is None): read them with `counts_csr()` or smooth them with `smooth()`."""
         rec_ids = kw.get("rec_ids")
         args, keep = make_trace_args(rays_per_emitter, **kw)
         N, nb = self.n_elements, args.n_bins
-        if counts_out is not None:
+        if not dense:
+            counts = None
+        elif counts_out is not None:
             counts = counts_out
         else:   # rows of other ranks are left untouched by the library: start from zeros when sharded
             counts = (np.zeros if args.emitter_world > 1 else np.empty)((nb, N, N), np.uint64)
-        assert counts.dtype == np.uint64 and counts.size == nb * N * N and counts.flags["C_CONTIGUOUS"]
+        assert counts is None or (counts.dtype == np.uint64 and counts.size == nb * N * N and counts.flags["C_CONTIGUOUS"])
         lost = np.empty((nb, N), np.uint64)
         st = rthx_stats()
         rec = None
@@ -191,10 +198,10 @@ class DeviceTracer:
             origins = np.zeros((max(cap, 1), 2))
             endpoints = np.zeros((max(cap, 1), 2))
             rec = rthx_rec_out(cap, origins.ctypes.data_as(c_f64p), endpoints.ctypes.data_as(c_f64p), 0)
-        self._check(self._L.rthx_trace_exchange(self._h, C.byref(args), counts.ctypes.data_as(c_u64p),
+        self._check(self._L.rthx_trace_exchange(self._h, C.byref(args), counts.ctypes.data_as(c_u64p) if counts is not None else None,
                                                 lost.ctypes.data_as(c_u64p), C.byref(rec) if rec else None,
                                                 C.byref(st)))
-        out = dict(counts=counts.reshape(nb, N, N), lost=lost, stats=st.as_dict())
+        out = dict(counts=counts.reshape(nb, N, N) if counts is not None else None, lost=lost, stats=st.as_dict())
         if rec is not None:
             out["origins"] = origins[: rec.n_recorded].copy()
             out["endpoints"] = endpoints[: rec.n_recorded].copy()
@@ -210,6 +217,22 @@ class DeviceTracer:
                                                        C.c_void_p(lost_ptr), C.c_void_p(stream),
                                                        int(zero_first), C.byref(st)))
         return st.as_dict()
+
+    def counts_csr(self, bin: int = 0, values: bool = True, normalised: bool = True):
+        """CSR read-out of the counts resident on the device (rthx_counts_nnz / rthx_counts_csr): returns
+        (row_ptr [N+1] i64, cols [nnz] i32, counts [nnz] u64 or None, F_vals [nnz] f64 = count/row total or None)."""
+        nnz = C.c_int64(0)
+        self._check(self._L.rthx_counts_nnz(self._h, int(bin), C.byref(nnz)))
+        N, k = self.n_elements, max(1, nnz.value)
+        row_ptr = np.empty(N + 1, np.int64)
+        cols = np.empty(k, np.int32)
+        vals = np.empty(k, np.uint64) if values else None
+        fv = np.empty(k, np.float64) if normalised else None
+        self._check(self._L.rthx_counts_csr(self._h, int(bin), row_ptr.ctypes.data_as(C.POINTER(C.c_int64)), cols.ctypes.data_as(c_i32p),
+                                            vals.ctypes.data_as(c_u64p) if values else None,
+                                            fv.ctypes.data_as(c_f64p) if normalised else None))
+        n = nnz.value
+        return row_ptr, cols[:n], (vals[:n] if values else None), (fv[:n] if normalised else None)
 
     def smooth(self, w, n: Optional[int] = None, counts: Optional[np.ndarray] = None, F: Optional[np.ndarray] = None,
                bin: int = 0, max_iters: int = 1000, target: float = 0.0, measure_pass: bool = False,

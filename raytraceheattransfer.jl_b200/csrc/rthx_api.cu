@@ -34,6 +34,9 @@ struct DevRes {
   double* rec_pts_dev = nullptr;            size_t rec_pts_cap = 0;
   uint8_t* rec_valid_dev = nullptr;         size_t rec_valid_cap = 0;
   double* peak_dev = nullptr;
+  int* csr_nnz = nullptr;                   size_t csr_cap = 0;        // per-row nnz (int), row totals, row pointers
+  unsigned long long* csr_rowsum = nullptr; long long* csr_rowptr = nullptr;
+  void* csr_out = nullptr;                  size_t csr_out_cap = 0;    // compacted cols / vals / F_vals
   double* smooth_X = nullptr;               size_t smooth_cap = 0;     // n*n doubles of the smoothing iterate
   double* smooth_vec = nullptr;             size_t smooth_vec_cap = 0; // w, rs, r, u, part (5 n doubles)
   void* smooth_src = nullptr;               size_t smooth_src_cap = 0; // staged host matrix (FROM_COUNTS / FROM_F)
@@ -53,7 +56,8 @@ struct rthx_handle : DevRes {
   bool fast_ok = false;        // every coarse face affine + complete neighbour table + descriptors fit in smem
   size_t mesh_bytes = 0;
   TraceParams base{};          // mesh pointers filled once
-  int last_trace_bins = 0; size_t last_trace_rows = 0;   // layout of counts_dev left by the last host-output trace
+  int last_trace_bins = 0; size_t last_trace_rows = 0;
+  int csr_bin = -1; long long csr_total = 0;              // bin whose row pointers are prepared on the device   // layout of counts_dev left by the last host-output trace
   // views into the arena
   unsigned long long* lost_dev = nullptr;   size_t lost_cap = 0;
   int32_t* bins_dev = nullptr;              size_t bins_cap = 0;
@@ -71,6 +75,7 @@ bool g_prop_ok[64] = {};
 
 void devres_free(DevRes& r) {
   cudaFree(r.smooth_X); cudaFree(r.smooth_vec); cudaFree(r.smooth_src);
+  cudaFree(r.csr_nnz); cudaFree(r.csr_rowsum); cudaFree(r.csr_rowptr); cudaFree(r.csr_out);
   cudaFree(r.arena); cudaFree(r.counts_dev); cudaFree(r.rec_pts_dev); cudaFree(r.rec_valid_dev); cudaFree(r.peak_dev);
   for (auto& e : r.ev) if (e) cudaEventDestroy(e);
   for (auto& e : r.bev) if (e) cudaEventDestroy(e);
@@ -810,7 +815,6 @@ extern "C" int rthx_trace_exchange(rthx_handle* h, const rthx_trace_args* a, uin
   if (!h) return RTHX_ERR_ARG;
   int rc = check_args(h, a);
   if (rc) return rc;
-  if (!counts_out) return fail(h, RTHX_ERR_ARG, "trace: counts_out is NULL");
   CU(h, cudaSetDevice(h->device));
   const int N = h->N;
   int n_slots = 0, n_launches = 0;
@@ -821,10 +825,15 @@ extern "C" int rthx_trace_exchange(rthx_handle* h, const rthx_trace_args* a, uin
   int n_batches = 1;
   rc = pipeline_launch(h, a, a->emitter_rank, a->emitter_world, rec != nullptr, n_slots, &pl, &n_launches, &n_batches);
   if (rc) return rc;
-  rc = pipeline_copy(h, a, a->emitter_rank, a->emitter_world, counts_out, n_batches);
-  if (rc) return rc;
+  if (counts_out) {
+    rc = pipeline_copy(h, a, a->emitter_rank, a->emitter_world, counts_out, n_batches);
+    if (rc) return rc;
+  } else {
+    CU(h, cudaStreamWaitEvent(h->copy_stream, h->ev[2], 0));
+  }
   h->last_trace_bins = a->emitter_world == 1 ? a->n_bins : 0;
   h->last_trace_rows = (size_t)N;
+  h->csr_bin = -1;
   std::vector<uint64_t> lost_host((size_t)a->n_bins * N);
   CU(h, cudaMemcpyAsync(lost_host.data(), h->lost_dev, sizeof(uint64_t) * lost_host.size(), cudaMemcpyDeviceToHost, h->copy_stream));
   CU(h, cudaEventRecord(h->ev[3], h->copy_stream));
@@ -1013,6 +1022,69 @@ extern "C" int rthx_shared_free(int device_id, void* dev_ptr) {
   if (!dev_ptr) return RTHX_OK;
   CUG(cudaSetDevice(device_id));
   CUG(cudaFree(dev_ptr));
+  return RTHX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// sparse read-out of the resident counts
+// ---------------------------------------------------------------------------------------------------------------
+namespace rthx {
+cudaError_t launch_row_nnz(const unsigned long long* c, int n, size_t ld, int* nnz, unsigned long long* rowsum, cudaStream_t st);
+cudaError_t launch_row_fill(const unsigned long long* c, int n, size_t ld, const long long* row_ptr, const unsigned long long* rowsum, int* cols,
+                            unsigned long long* vals, double* fvals, cudaStream_t st);
+}  // namespace rthx
+
+extern "C" int rthx_counts_nnz(rthx_handle* h, int bin, int64_t* nnz_out) {
+  if (!h || !nnz_out) return RTHX_ERR_ARG;
+  if (bin < 0 || bin >= h->last_trace_bins || !h->counts_dev) return fail(h, RTHX_ERR_ARG, "counts_nnz: no resident counts for that bin (run rthx_trace_exchange on all emitters first)");
+  CU(h, cudaSetDevice(h->device));
+  const int N = h->N;
+  if (h->csr_cap < (size_t)N + 1) {
+    cudaFree(h->csr_nnz); cudaFree(h->csr_rowsum); cudaFree(h->csr_rowptr);
+    h->csr_nnz = nullptr; h->csr_rowsum = nullptr; h->csr_rowptr = nullptr; h->csr_cap = 0;
+    CU(h, cudaMalloc(&h->csr_nnz, sizeof(int) * ((size_t)N + 1)));
+    CU(h, cudaMalloc(&h->csr_rowsum, sizeof(unsigned long long) * ((size_t)N + 1)));
+    CU(h, cudaMalloc(&h->csr_rowptr, sizeof(long long) * ((size_t)N + 1)));
+    h->csr_cap = (size_t)N + 1;
+  }
+  const unsigned long long* c = h->counts_dev + (size_t)bin * h->last_trace_rows * N;
+  CU(h, rthx::launch_row_nnz(c, N, (size_t)N, h->csr_nnz, h->csr_rowsum, h->stream));
+  std::vector<int> nnz(N);
+  CU(h, cudaMemcpyAsync(nnz.data(), h->csr_nnz, sizeof(int) * N, cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  std::vector<long long> rp((size_t)N + 1, 0);
+  for (int i = 0; i < N; ++i) rp[i + 1] = rp[i] + nnz[i];
+  CU(h, cudaMemcpyAsync(h->csr_rowptr, rp.data(), sizeof(long long) * ((size_t)N + 1), cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  h->csr_bin = bin; h->csr_total = rp[N];
+  *nnz_out = rp[N];
+  return RTHX_OK;
+}
+
+extern "C" int rthx_counts_csr(rthx_handle* h, int bin, int64_t* row_ptr, int32_t* cols, uint64_t* vals, double* F_vals) {
+  if (!h || !row_ptr || !cols) return RTHX_ERR_ARG;
+  if (h->csr_bin != bin) { int64_t dummy; int rc = rthx_counts_nnz(h, bin, &dummy); if (rc) return rc; }
+  CU(h, cudaSetDevice(h->device));
+  const int N = h->N;
+  const size_t nnz = (size_t)h->csr_total;
+  const size_t need = std::max<size_t>(1, nnz) * (sizeof(int) + sizeof(unsigned long long) + sizeof(double));
+  if (h->csr_out_cap < need) {
+    cudaFree(h->csr_out); h->csr_out = nullptr; h->csr_out_cap = 0;
+    CU(h, cudaMalloc(&h->csr_out, need));
+    h->csr_out_cap = need;
+  }
+  unsigned long long* d_vals = (unsigned long long*)h->csr_out;
+  double* d_f = (double*)(d_vals + std::max<size_t>(1, nnz));
+  int* d_cols = (int*)(d_f + std::max<size_t>(1, nnz));
+  const unsigned long long* c = h->counts_dev + (size_t)bin * h->last_trace_rows * N;
+  CU(h, rthx::launch_row_fill(c, N, (size_t)N, h->csr_rowptr, h->csr_rowsum, d_cols, d_vals, F_vals ? d_f : nullptr, h->stream));
+  CU(h, cudaMemcpyAsync(row_ptr, h->csr_rowptr, sizeof(long long) * ((size_t)N + 1), cudaMemcpyDeviceToHost, h->stream));
+  if (nnz) {
+    CU(h, cudaMemcpyAsync(cols, d_cols, sizeof(int) * nnz, cudaMemcpyDeviceToHost, h->stream));
+    if (vals) CU(h, cudaMemcpyAsync(vals, d_vals, sizeof(unsigned long long) * nnz, cudaMemcpyDeviceToHost, h->stream));
+    if (F_vals) CU(h, cudaMemcpyAsync(F_vals, d_f, sizeof(double) * nnz, cudaMemcpyDeviceToHost, h->stream));
+  }
+  CU(h, cudaStreamSynchronize(h->stream));
   return RTHX_OK;
 }
 

@@ -135,6 +135,53 @@ __global__ void __launch_bounds__(ROW_THREADS) recover_kernel(double* __restrict
   for (int j = threadIdx.x; j < (int)(ldx >> 1); j += ROW_THREADS) { double2 v = x2[j]; v.x *= inv; v.y *= inv; x2[j] = v; }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// sparse (CSR) view of a count matrix: feeds sparse(I, J, V) without moving the zeros
+// ---------------------------------------------------------------------------------------------------------------
+// one warp per row: number of non-zero tallies and the row total
+__global__ void __launch_bounds__(256) row_nnz_kernel(const unsigned long long* __restrict__ c, int n, size_t ld, int* __restrict__ nnz,
+                                                      unsigned long long* __restrict__ rowsum) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= n) return;
+  int cnt = 0;
+  unsigned long long s = 0;
+  for (int j = lane; j < n; j += 32) { const unsigned long long v = c[(size_t)row * ld + j]; cnt += v != 0; s += v; }
+  for (int o = 16; o > 0; o >>= 1) { cnt += __shfl_down_sync(0xffffffffu, cnt, o); s += __shfl_down_sync(0xffffffffu, s, o); }
+  if (lane == 0) { nnz[row] = cnt; rowsum[row] = s; }
+}
+
+// one warp per row: write (column, count, count / rowsum) of the non-zeros in ascending column order at row_ptr[row]
+__global__ void __launch_bounds__(256) row_fill_kernel(const unsigned long long* __restrict__ c, int n, size_t ld, const long long* __restrict__ row_ptr,
+                                                       const unsigned long long* __restrict__ rowsum, int* __restrict__ cols,
+                                                       unsigned long long* __restrict__ vals, double* __restrict__ fvals) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= n) return;
+  long long base = row_ptr[row];
+  const double inv = rowsum[row] ? 1.0 / (double)rowsum[row] : 0.0;
+  for (int j0 = 0; j0 < n; j0 += 32) {
+    const int j = j0 + lane;
+    const unsigned long long v = j < n ? c[(size_t)row * ld + j] : 0ull;
+    const unsigned m = __ballot_sync(0xffffffffu, v != 0);
+    if (v != 0) {
+      const long long k = base + __popc(m & ((1u << lane) - 1u));
+      cols[k] = j;
+      vals[k] = v;
+      if (fvals) fvals[k] = (double)v * inv;
+    }
+    base += __popc(m);
+  }
+}
+
+cudaError_t launch_row_nnz(const unsigned long long* c, int n, size_t ld, int* nnz, unsigned long long* rowsum, cudaStream_t st) {
+  row_nnz_kernel<<<(n + 7) / 8, 256, 0, st>>>(c, n, ld, nnz, rowsum);
+  return cudaGetLastError();
+}
+cudaError_t launch_row_fill(const unsigned long long* c, int n, size_t ld, const long long* row_ptr, const unsigned long long* rowsum, int* cols,
+                            unsigned long long* vals, double* fvals, cudaStream_t st) {
+  row_fill_kernel<<<(n + 7) / 8, 256, 0, st>>>(c, n, ld, row_ptr, rowsum, cols, vals, fvals);
+  return cudaGetLastError();
+}
+
 struct SmoothResult { int iters; double delta, delta_init; double ms_total, ms_per_iter; int launches; };
 
 // Runs AP on the device.  `src_counts` (u64, leading dimension ld) or `src_F` (doubles) is a DEVICE pointer; X (n*n

@@ -82,16 +82,24 @@ def computeExchangeFactorsBins(rtm, rays_per_emitter: int, nudge: float, spectra
     rec_ids = [i - 1 for i in rec.ids] if rec is not None else None
     rec_bin = (rec.bin - 1) if rec is not None else 0
     verbose and print(f"  Using CUDA device {device} for spectral bins {list(spectral_bins)}")
-    out = tr.trace(rays_per_emitter, seed=seed, bins=[b - 1 for b in spectral_bins], nudge=nudge,
+    # the counts stay on the device; only their non-zeros come back, already row-normalised, as CSR triplets
+    # (parallelRayTracing.jl:144-154 + row_normalize! :161-169) — no N^2 host traffic, no host-side compaction
+    out = tr.trace(rays_per_emitter, dense=False, seed=seed, bins=[b - 1 for b in spectral_bins], nudge=nudge,
                    rec_ids=rec_ids, rec_bin=rec_bin, locator=locator)
     rtm.last_trace_stats = out["stats"]
-    rtm.last_counts = out["counts"]
     rtm.last_lost = out["lost"]
     if rec is not None and "origins" in out:
         # parallelRayTracing.jl:120-123 push into rec.origins[tid]; any slot works for collect_rays
         rec.origins[0] = np.concatenate([rec.origins[0], out["origins"]], axis=0)
         rec.endpoints[0] = np.concatenate([rec.endpoints[0], out["endpoints"]], axis=0)
-    return [counts_to_F(out["counts"][k], rays_per_emitter) for k in range(len(spectral_bins))]
+    N = tr.n_elements
+    mats = []
+    for k in range(len(spectral_bins)):
+        row_ptr, cols, _, fvals = tr.counts_csr(k, values=False, normalised=True)
+        max_loss = int(out["lost"][k].max()) if N else 0
+        print(f"Maximum ray tracing ray loss per emitter: {max_loss}/{rays_per_emitter}")   # unconditional, :163
+        mats.append(sp.csr_matrix((fvals, cols, row_ptr), shape=(N, N)).tocsc())
+    return mats
 
 
 def computeExchangeFactorsBin(rtm, rays_per_emitter: int, nudge: float, spectral_bin: int, verbose: bool = False,
