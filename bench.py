@@ -151,6 +151,33 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def run_julia_reference(args, sample):
+    """If a `julia` binary and baseline/_ref exist, time the UNMODIFIED reference (baseline/run_julia_ref.jl).
+    Neither exists in this image, so this returns None and the oracle port is timed instead."""
+    import shutil
+    julia = shutil.which("julia")
+    ref = os.path.join(_ROOT, "baseline", "_ref")
+    if julia is None or not os.path.isdir(ref):
+        return None
+    ndim, kappa, sig = {"cfg1": (11, 1.0, 0.0), "cfg2": (41, 1.0, 0.0), "cfg3": (101, 0.5, 0.5)}[args.workload]
+    try:
+        r = subprocess.run([julia, "-t", "auto", f"--project={ref}", os.path.join(_ROOT, "baseline", "run_julia_ref.jl"),
+                            str(ndim), str(kappa), str(sig), str(int(sample)), str(args.steps)],
+                           capture_output=True, text=True, timeout=1500)
+        line = next(l for l in r.stdout.splitlines() if l.startswith("RTHX_JULIA_REF"))
+        kv = dict(x.split("=") for x in line.split()[1:])
+    except Exception:
+        return None
+    value = float(kv["rays_per_s"])
+    return {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": float(kv["rays"]) / value * 1e3, "higher_is_better": True,
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {workload_desc(args.workload)}"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": int(kv["threads"]), "kind": "reference",
+                             "sample": f"{kv['rays']} rays per step, parallelRayTracing of the unmodified Julia reference"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+
+
 def main_reference(args):
     """Reference arm: the reference's own algorithm on the host cores.  Julia is absent from the image, so this is
     the CPU oracle (oracle/rthx_oracle.c, kind "port") with every host thread, on a bounded sample per step."""
@@ -159,6 +186,10 @@ def main_reference(args):
         return 0
     rtm, flat, bins = build_workload(args.workload)
     sample = args.cpu_sample_rays / 5.0
+    julia_line = run_julia_reference(args, sample) if args.workload in ("cfg1", "cfg2", "cfg3") else None
+    if julia_line is not None:
+        print(json.dumps(julia_line))
+        return 0
     for _ in range(max(0, args.warmup)):
         run_oracle_sample(flat, bins, sample / 10.0, seed=7)
     t0 = time.perf_counter()
