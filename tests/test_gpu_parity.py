@@ -339,3 +339,24 @@ def test_statistical_parity_cfg2_full_size(rthx_mod, oracle_mod, cuda_lib):
     dof = keep.sum(axis=1)
     zrow = (chi2 - dof) / np.sqrt(2 * np.maximum(dof, 1))
     assert np.abs(zrow).max() < 6 and abs(zrow.mean()) < 0.2
+
+
+def test_full_size_cfg3_reproduces_crosbie_schrenker(rthx_mod, cuda_lib):
+    """The north-star acceptance at the NAMED configuration: 101x101 grey absorbing+scattering enclosure (kappa =
+    sigma_s = 0.5, tau = 1), 1e10 rays through the public call (trace + CSR read-out + device-side smoothing), then the
+    grey equilibrium solve -> centre-line S(tau) against the Crosbie & Schrenker (1984) table of test_2d_grey.jl:25-33.
+    In radiative equilibrium the scattering albedo drops out, so the table for tau = 1 applies."""
+    from oracle import grey_solver as gs
+    rtm = rthx_mod.meshes.cfg3()
+    rtm(10_000_000_000, method="exchange", verbose=False, seed=0x5EED0001)
+    st = rtm.last_trace_stats
+    assert st["rays_traced"] == 942951 * 10605 and st["rays_lost"] <= 10
+    assert isinstance(rtm.F_smooth, np.ndarray) and rtm.F_smooth.shape == (10605, 10605)      # dense branch, on the device
+    assert rtm.last_smooth_stats["delta"] < 1e-14
+    res = gs.solve_grey(rtm, rtm.F_smooth)
+    S = gs.centerline_source_function(rtm, 101, 1000.0)
+    A = gs.analytical_centerline(101)
+    rel = np.linalg.norm(S - A) / max(np.linalg.norm(S), np.linalg.norm(A))
+    assert rel <= 0.05                                            # the reference's own tolerance (test_2d_grey.jl:216)
+    assert rel <= 0.01 and np.abs(S - A).max() < 0.01             # what 1e10 rays on 101x101 actually deliver
+    assert abs(res["energy_error"]) < 1e-4
