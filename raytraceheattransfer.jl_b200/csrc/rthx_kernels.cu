@@ -476,18 +476,15 @@ __global__ void __launch_bounds__(256, MINB) trace_exchange_kernel(const __grid_
         gas = local_beta * u >= neg_log;
         S = neg_log / local_beta;
       }
-      if (ok) {
-        if (gas) {
-          px = fma(S - p.nudge, dx, px);
-          py = fma(S - p.nudge, dy, py);
-          const int f = locate_quad(cf, px, py);
-          if (f >= 0) absorber = p.n_surfaces + f;
-        } else if ((u < CUDART_INF) && cf.solid[k]) {        // an open edge has no neighbour face: the ray is lost
-          px = fma(u - p.nudge, dx, px);
-          py = fma(u - p.nudge, dy, py);
-          const int f = locate_quad(cf, px, py);
-          if (f >= 0) absorber = __ldg(p.cell_surf_id + 4 * f + k);
-        }
+      // Gas and wall endings share one advance + one fine-cell location (same arithmetic as the two branches of
+      // traceRay.jl:31-52, selected per lane): a warp with both kinds of ray no longer issues the tail twice.
+      const bool hit = !gas & (u < CUDART_INF) & (cf.solid[k] != 0);   // an open edge has no neighbour face: the ray is lost
+      if (ok & (gas | hit)) {
+        const double adv = (gas ? S : u) - p.nudge;
+        px = fma(adv, dx, px);
+        py = fma(adv, dy, py);
+        const int f = locate_quad(cf, px, py);
+        if (f >= 0) absorber = gas ? p.n_surfaces + f : __ldg(p.cell_surf_id + 4 * f + k);
       }
     } else {
     double hit_nx = 0.0, hit_ny = 0.0;   // MULTI: outward unit normal of the wall that was hit
