@@ -401,7 +401,7 @@ def main():
         return 0
 
     # ---- next-stage kernel: dense reciprocity smoothing of the traced matrix on the device (HBM-bound) -----------
-    smoothing = None
+    smoothing = solve = None
     if world == 1 and not args.no_smoothing:
         try:
             hbm_peak = json.load(open(os.path.join(_ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
@@ -413,6 +413,16 @@ def main():
         w = rthx.get_w(rtm)
         F_host = torch.empty((N, N), dtype=torch.float64, pin_memory=True)
         _, ss = tr.smooth(w / w.min(), max_iters=1000, measure_pass=True, out=F_host.numpy())
+        # grey equilibrium solve on the F_smooth that is still resident on the device (equilibriumGrey2D.jl:148-194)
+        from rthx import equilibrium as _eq
+        _, _b, coeff, h = _eq._system_vectors(rtm, _eq.populateWorkspace(rtm))
+        _, _, sv = tr.solve_grey(coeff, h, measure_pass=True)
+        solve = {"kernel": "matvec_t_partial_kernel (y = F'x on the resident dense F_smooth: one read of F per Krylov step)",
+                 "bound": "hbm", "achieved": sv["matvec_gbs"], "peak": hbm_peak, "unit": "GB/s",
+                 "frac": sv["matvec_gbs"] / hbm_peak, "bytes_per_pass": sv["matvec_bytes"], "pass_ms": sv["matvec_ms"],
+                 "iterations": sv["iterations"], "restarts": sv["restarts"], "matvecs": sv["matvecs"],
+                 "converged": sv["converged"], "residual": sv["residual"], "rhs_norm": sv["rhs_norm"],
+                 "total_ms": sv["total_ms"], "launches": sv["launches"], "peak_source": peak_src}
         tr.close()
         smoothing = {"kernel": "scale_rows_kernel (one alternating-projection iteration: X *= (u_i+u_j)/2 with fused row sums)",
                      "bound": "hbm", "achieved": ss["pass_gbs"], "peak": hbm_peak, "unit": "GB/s",
@@ -456,7 +466,7 @@ def main():
                                  "one NCCL reduce of the u64 count matrix to rank 0" if sh.mode == "nccl" else "single GPU")),
                    "l2": "count matrix (8*N*N bytes) exceeds the 126 MB L2 for cfg3; a fresh Philox seed every step",
                    "launch": {k: st[k] for k in ("n_blocks", "block_threads", "row_chunks", "smem_bytes", "hist_in_smem")}},
-        "roofline": roofline, "smoothing": smoothing, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps * world,
+        "roofline": roofline, "smoothing": smoothing, "solve": solve, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps * world,
         "clocks": sampler.summary(t_win0, t_win1 + 0.1) if sampler else None,
         "check": {"tallied_last_step": tallied, "lost_last_step": lost_total},
     }

@@ -235,6 +235,56 @@ typedef struct rthx_smooth_stats {
 int rthx_smooth_F(rthx_handle* h, int source, const void* src_host, int bin, int n, const double* w, int max_iters,
                   double target, int measure_pass, double* F_out, rthx_smooth_stats* stats);
 
+/* Grey GERT equilibrium solve on the device (next-stage row of the hot path: the consumer of F).  Restates the
+ * linear-algebra core of src/HeatTransfer/equilibrium/equilibriumGrey2D.jl:80-211:
+ *     M = I - Diagonal(coeff) * F'   (:148-149; coeff = ifelse(Q_known, 1, b), never formed explicitly)
+ *     j = M \ h                      (:152-158; restarted GMRES(memory), stop at |r| <= atol + rtol*|h| like
+ *                                     Krylov.jl's gmres!(...; memory = 50, restart = true, rtol = 1e-12))
+ *     g_i = sum_k F[k,i] j[k]        (:168-194; the caller forms r = b.*g and Abs = (1-b).*g)
+ * A caller replaces exactly those lines and keeps populateWorkspace!, the boundary-condition vectors, the
+ * temperature recovery and the write-back unchanged on the host.
+ *   source RTHX_SOLVE_FROM_LAST_SMOOTH: the n x n F_smooth still resident on the device from the last rthx_smooth_F
+ *          on this handle (trace -> smooth -> solve without moving F over PCIe); `n` must match that call;
+ *   source RTHX_SOLVE_FROM_DENSE: F_dense is a host [n*n] Float64 matrix, layout RTHX_ROW_MAJOR (C / numpy:
+ *          F[i][j] at i*n + j) or RTHX_COL_MAJOR (a Julia `Matrix` as it lies in memory);
+ *   source RTHX_SOLVE_FROM_CSC: colptr [n+1] / rowval [nnz] / nzval [nnz], the fields of a SparseMatrixCSC, 0-based.
+ *   coeff, rhs: [n].  memory <= 0 -> 50; max_iters <= 0 -> 2n (Krylov.jl's itmax); rtol <= 0 -> 1e-12;
+ *   atol < 0 -> sqrt(eps) (Krylov.jl's default).  j_out [n]; g_out [n] may be NULL.
+ *   measure_pass != 0 additionally times the product y = F'x alone (stats->matvec_ms / matvec_gbs). */
+enum { RTHX_SOLVE_FROM_LAST_SMOOTH = 0, RTHX_SOLVE_FROM_DENSE = 1, RTHX_SOLVE_FROM_CSC = 2 };
+enum { RTHX_ROW_MAJOR = 0, RTHX_COL_MAJOR = 1 };
+typedef struct rthx_solve_args {
+  int32_t n;
+  int32_t source;               /* RTHX_SOLVE_FROM_* */
+  int32_t layout;               /* FROM_DENSE: RTHX_ROW_MAJOR | RTHX_COL_MAJOR */
+  int32_t memory;               /* Krylov subspace cap per restart cycle */
+  int32_t max_iters;            /* cap on the total number of inner iterations */
+  int32_t measure_pass;
+  const double*  F_dense;       /* FROM_DENSE */
+  const int64_t* colptr;        /* FROM_CSC */
+  const int32_t* rowval;
+  const double*  nzval;
+  const double*  coeff;         /* [n] */
+  const double*  rhs;           /* [n] h */
+  double rtol;
+  double atol;
+} rthx_solve_args;
+typedef struct rthx_solve_stats {
+  int32_t iterations;           /* inner (Arnoldi) iterations */
+  int32_t restarts;
+  int32_t launches;
+  int32_t converged;            /* 1: true residual |h - M j| <= atol + rtol*|h| */
+  int32_t matvecs;              /* products with F' (one read of F each) */
+  int32_t pad_;
+  double  residual;             /* final true residual norm */
+  double  rhs_norm;
+  double  total_ms;             /* device time of the whole solve */
+  double  matvec_ms;            /* one product y = F'x (measure_pass) */
+  double  matvec_gbs;           /* matvec_bytes / matvec_ms */
+  int64_t matvec_bytes;         /* algorithmic bytes of one product: 8 n^2 (dense) or 12 nnz + 8 (n+1) (CSC) */
+} rthx_solve_stats;
+int rthx_solve_grey(rthx_handle* h, const rthx_solve_args* args, double* j_out, double* g_out, rthx_solve_stats* stats);
+
 /* Sparse (CSR) read-out of the counts still resident on the device from the last rthx_trace_exchange on this handle
  * (all emitters): per row the non-zero absorber columns in ascending order — exactly the triplets the reference
  * feeds to sparse(I, J, V) (parallelRayTracing.jl:144-154) — compacted on the device, so optically thick meshes

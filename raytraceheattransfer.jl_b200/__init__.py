@@ -10,6 +10,7 @@ from .flatten import flatten_domain, FlatMesh
 from ._lib import (make_trace_args, load_library, library_path, build_library, DeviceTracer, RthxError)
 from .tracing import (parallelRayTracing, exchangeRayTracing, computeExchangeFactorsBin, group_uniform_bins,
                       counts_to_F, get_w, get_b)
+from .equilibrium import solveEquilibrium, equilibriumGrey2D, buildSystemMatrix
 from . import meshes, smoothing
 
 __all__ = [
@@ -17,4 +18,5 @@ __all__ = [
     "flatten_domain", "FlatMesh", "make_trace_args", "load_library", "library_path", "build_library",
     "DeviceTracer", "RthxError", "parallelRayTracing", "exchangeRayTracing", "computeExchangeFactorsBin",
     "group_uniform_bins", "counts_to_F", "get_w", "get_b", "meshes",
+    "solveEquilibrium", "equilibriumGrey2D", "buildSystemMatrix",
 ]

@@ -64,6 +64,26 @@ class rthx_smooth_stats(C.Structure):
 
 
 RTHX_SMOOTH_FROM_LAST_TRACE, RTHX_SMOOTH_FROM_COUNTS, RTHX_SMOOTH_FROM_F = 0, 1, 2
+RTHX_SOLVE_FROM_LAST_SMOOTH, RTHX_SOLVE_FROM_DENSE, RTHX_SOLVE_FROM_CSC = 0, 1, 2
+RTHX_ROW_MAJOR, RTHX_COL_MAJOR = 0, 1
+c_i64p = C.POINTER(C.c_int64)
+
+
+class rthx_solve_args(C.Structure):
+    _fields_ = [("n", C.c_int32), ("source", C.c_int32), ("layout", C.c_int32), ("memory", C.c_int32),
+                ("max_iters", C.c_int32), ("measure_pass", C.c_int32),
+                ("F_dense", c_f64p), ("colptr", c_i64p), ("rowval", c_i32p), ("nzval", c_f64p),
+                ("coeff", c_f64p), ("rhs", c_f64p), ("rtol", C.c_double), ("atol", C.c_double)]
+
+
+class rthx_solve_stats(C.Structure):
+    _fields_ = [("iterations", C.c_int32), ("restarts", C.c_int32), ("launches", C.c_int32), ("converged", C.c_int32),
+                ("matvecs", C.c_int32), ("pad_", C.c_int32),
+                ("residual", C.c_double), ("rhs_norm", C.c_double), ("total_ms", C.c_double),
+                ("matvec_ms", C.c_double), ("matvec_gbs", C.c_double), ("matvec_bytes", C.c_int64)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if k != "pad_"}
 
 
 class rthx_info(C.Structure):
@@ -82,5 +102,5 @@ EXPORTED_SYMBOLS = (
     "rthx_create", "rthx_destroy", "rthx_get_info", "rthx_trace_exchange", "rthx_trace_exchange_device",
     "rthx_trace_exchange_multi", "rthx_measure_fp64_peak", "rthx_last_error", "rthx_version",
     "rthx_shared_alloc", "rthx_shared_open", "rthx_shared_close", "rthx_shared_free", "rthx_release_cached",
-    "rthx_smooth_F", "rthx_host_register", "rthx_host_unregister", "rthx_counts_nnz", "rthx_counts_csr",
+    "rthx_smooth_F", "rthx_solve_grey", "rthx_host_register", "rthx_host_unregister", "rthx_counts_nnz", "rthx_counts_csr",
 )

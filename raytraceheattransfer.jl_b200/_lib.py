@@ -14,7 +14,9 @@ from typing import Optional, Sequence
 import numpy as np
 
 from ._abi import (rthx_mesh, rthx_trace_args, rthx_rec_out, rthx_stats, rthx_info, rthx_smooth_stats, c_i32p, c_f64p, c_u64p,
+                   rthx_solve_args, rthx_solve_stats, c_i64p,
                    RTHX_SMOOTH_FROM_LAST_TRACE, RTHX_SMOOTH_FROM_COUNTS, RTHX_SMOOTH_FROM_F,
+                   RTHX_SOLVE_FROM_LAST_SMOOTH, RTHX_SOLVE_FROM_DENSE, RTHX_SOLVE_FROM_CSC, RTHX_ROW_MAJOR, RTHX_COL_MAJOR,
                    RTHX_FIRST_INTERACTION, RTHX_LOCATOR_AUTO, RTHX_LOCATOR_GENERIC, EXPORTED_SYMBOLS)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -94,6 +96,8 @@ def load_library():
     L.rthx_smooth_F.restype = C.c_int
     L.rthx_smooth_F.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, c_f64p, C.c_int, C.c_double, C.c_int,
                                 c_f64p, C.POINTER(rthx_smooth_stats)]
+    L.rthx_solve_grey.restype = C.c_int
+    L.rthx_solve_grey.argtypes = [C.c_void_p, C.POINTER(rthx_solve_args), c_f64p, c_f64p, C.POINTER(rthx_solve_stats)]
     L.rthx_release_cached.restype = C.c_int
     L.rthx_release_cached.argtypes = []
     L.rthx_counts_nnz.restype = C.c_int
@@ -243,6 +247,7 @@ class DeviceTracer:
         w = np.ascontiguousarray(w, dtype=np.float64)
         n = len(w) if n is None else int(n)
         assert len(w) == n
+        self._resident_F = None        # whatever F_smooth an earlier call left on the device is about to be replaced
         if counts is not None:
             src = np.ascontiguousarray(counts, dtype=np.uint64); assert src.shape == (n, n)
             source, ptr = RTHX_SMOOTH_FROM_COUNTS, src.ctypes.data_as(C.c_void_p)
@@ -257,6 +262,44 @@ class DeviceTracer:
         self._check(self._L.rthx_smooth_F(self._h, source, ptr, int(bin), n, w.ctypes.data_as(c_f64p), int(max_iters),
                                           float(target), 1 if measure_pass else 0, F_out.ctypes.data_as(c_f64p), C.byref(st)))
         return F_out.reshape(n, n), st.as_dict()
+
+    def solve_grey(self, coeff, rhs, F=None, col_major: bool = False, memory: int = 50, max_iters: int = 0,
+                   rtol: float = 1e-12, atol: float = -1.0, measure_pass: bool = False):
+        """(I - diag(coeff) F') j = rhs by restarted GMRES on the device (rthx_solve_grey).  `F`: None — the F_smooth
+        still resident on the device from the last `smooth()`; a dense [n,n] float64 array (C order, or the memory of a
+        column-major matrix with col_major=True); or a scipy.sparse matrix (converted to CSC, the reference's
+        SparseMatrixCSC).  Returns (j [n], g = F'j [n], stats dict)."""
+        import scipy.sparse as sp
+        coeff = np.ascontiguousarray(coeff, dtype=np.float64)
+        rhs = np.ascontiguousarray(rhs, dtype=np.float64)
+        n = len(rhs)
+        assert len(coeff) == n
+        a = rthx_solve_args()
+        a.n, a.memory, a.max_iters, a.measure_pass = n, int(memory), int(max_iters), 1 if measure_pass else 0
+        a.rtol, a.atol = float(rtol), float(atol)
+        a.coeff, a.rhs = coeff.ctypes.data_as(c_f64p), rhs.ctypes.data_as(c_f64p)
+        keep = None
+        if F is None:
+            a.source = RTHX_SOLVE_FROM_LAST_SMOOTH
+        elif sp.issparse(F):
+            Fc = F.tocsc()
+            Fc.sort_indices()
+            assert Fc.shape == (n, n)
+            keep = (np.ascontiguousarray(Fc.indptr, dtype=np.int64), np.ascontiguousarray(Fc.indices, dtype=np.int32),
+                    np.ascontiguousarray(Fc.data, dtype=np.float64))
+            a.source = RTHX_SOLVE_FROM_CSC
+            a.colptr, a.rowval, a.nzval = (keep[0].ctypes.data_as(c_i64p), keep[1].ctypes.data_as(c_i32p),
+                                           keep[2].ctypes.data_as(c_f64p))
+        else:
+            keep = np.ascontiguousarray(F, dtype=np.float64)
+            assert keep.shape == (n, n)
+            a.source, a.layout = RTHX_SOLVE_FROM_DENSE, (RTHX_COL_MAJOR if col_major else RTHX_ROW_MAJOR)
+            a.F_dense = keep.ctypes.data_as(c_f64p)
+        j = np.empty(n)
+        g = np.empty(n)
+        st = rthx_solve_stats()
+        self._check(self._L.rthx_solve_grey(self._h, C.byref(a), j.ctypes.data_as(c_f64p), g.ctypes.data_as(c_f64p), C.byref(st)))
+        return j, g, st.as_dict()
 
     def measure_fp64_peak(self) -> float:
         v = C.c_double(0.0)

@@ -40,6 +40,8 @@ struct DevRes {
   double* smooth_X = nullptr;               size_t smooth_cap = 0;     // n*n doubles of the smoothing iterate
   double* smooth_vec = nullptr;             size_t smooth_vec_cap = 0; // w, rs, r, u, part (5 n doubles)
   void* smooth_src = nullptr;               size_t smooth_src_cap = 0; // staged host matrix (FROM_COUNTS / FROM_F)
+  double* solve_buf = nullptr;              size_t solve_cap = 0;      // Krylov basis + work vectors + matvec partials
+  double* solve_mat = nullptr;              size_t solve_mat_cap = 0;  // staged host F of rthx_solve_grey (dense padded / CSC)
   void* stage[2] = {nullptr, nullptr};      size_t stage_cap = 0;      // pinned staging for pageable destinations
   cudaEvent_t cev[2] = {nullptr, nullptr};
   bool valid = false;
@@ -57,6 +59,7 @@ struct rthx_handle : DevRes {
   size_t mesh_bytes = 0;
   TraceParams base{};          // mesh pointers filled once
   int last_trace_bins = 0; size_t last_trace_rows = 0;
+  int smooth_n = 0; size_t smooth_ldx = 0;                // F_smooth resident in smooth_X after rthx_smooth_F (0: none)
   int csr_bin = -1; long long csr_total = 0;              // bin whose row pointers are prepared on the device   // layout of counts_dev left by the last host-output trace
   // views into the arena
   unsigned long long* lost_dev = nullptr;   size_t lost_cap = 0;
@@ -74,7 +77,7 @@ cudaDeviceProp g_prop[64];
 bool g_prop_ok[64] = {};
 
 void devres_free(DevRes& r) {
-  cudaFree(r.smooth_X); cudaFree(r.smooth_vec); cudaFree(r.smooth_src);
+  cudaFree(r.smooth_X); cudaFree(r.smooth_vec); cudaFree(r.smooth_src); cudaFree(r.solve_buf); cudaFree(r.solve_mat);
   cudaFree(r.csr_nnz); cudaFree(r.csr_rowsum); cudaFree(r.csr_rowptr); cudaFree(r.csr_out);
   cudaFree(r.arena); cudaFree(r.counts_dev); cudaFree(r.rec_pts_dev); cudaFree(r.rec_valid_dev); cudaFree(r.peak_dev);
   for (auto& e : r.ev) if (e) cudaEventDestroy(e);
@@ -1125,6 +1128,7 @@ extern "C" int rthx_smooth_F(rthx_handle* h, int source, const void* src_host, i
     return fail(h, RTHX_ERR_ARG, "smooth: unknown source");
   }
   const size_t ldx = ((size_t)n + 15) & ~size_t(15);      // rows padded to 128 bytes
+  h->smooth_n = 0;
   CU(h, ensure(&h->smooth_X, &h->smooth_cap, (size_t)n * ldx));
   CU(h, ensure(&h->smooth_vec, &h->smooth_vec_cap, (size_t)5 * ldx));
   double *w_dev = h->smooth_vec, *rs = w_dev + ldx, *r = rs + ldx, *u = r + ldx, *part = u + ldx;
@@ -1136,6 +1140,7 @@ extern "C" int rthx_smooth_F(rthx_handle* h, int source, const void* src_host, i
   CU(h, cudaMemcpy2DAsync(F_out, sizeof(double) * (size_t)n, h->smooth_X, sizeof(double) * ldx, sizeof(double) * (size_t)n, (size_t)n,
                           cudaMemcpyDeviceToHost, h->stream));
   CU(h, cudaStreamSynchronize(h->stream));
+  h->smooth_n = n; h->smooth_ldx = ldx;
   double pass_ms = 0;
   if (measure_pass) {
     std::vector<double> ones(ldx, 1.0);
@@ -1146,6 +1151,70 @@ extern "C" int rthx_smooth_F(rthx_handle* h, int source, const void* src_host, i
     st->iterations = res.iters; st->launches = res.launches; st->delta_init = res.delta_init; st->delta = res.delta;
     st->total_ms = res.ms_total; st->ms_per_iteration = res.ms_per_iter; st->pass_ms = pass_ms;
     st->pass_gbs = pass_ms > 0 ? 16.0 * (double)nn / (pass_ms * 1e-3) / 1e9 : 0.0;
+  }
+  return RTHX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// rthx_solve_grey: (I - diag(coeff) F') j = h by restarted GMRES on the device (kernels in rthx_solve.cu)
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int rthx_solve_grey(rthx_handle* h, const rthx_solve_args* a, double* j_out, double* g_out, rthx_solve_stats* st) {
+  if (!h) return RTHX_ERR_ARG;
+  if (!a || !j_out || a->n < 1 || !a->coeff || !a->rhs) return fail(h, RTHX_ERR_ARG, "solve: bad argument");
+  CU(h, cudaSetDevice(h->device));
+  const int n = a->n;
+  const int m = std::max(1, std::min(a->memory > 0 ? a->memory : 50, n));
+  const int max_iters = a->max_iters > 0 ? a->max_iters : 2 * n;
+  const double rtol = a->rtol > 0 ? a->rtol : 1e-12;
+  const double atol = a->atol >= 0 ? a->atol : 1.4901161193847656e-08;   // sqrt(eps(Float64))
+  const size_t nl = ((size_t)n + 15) & ~size_t(15);
+  rthx::SolveMatrix A;
+  if (a->source == RTHX_SOLVE_FROM_LAST_SMOOTH) {
+    if (h->smooth_n != n || !h->smooth_X) return fail(h, RTHX_ERR_ARG, "solve: no resident F_smooth of that size (run rthx_smooth_F on this handle first)");
+    A.kind = 0; A.dense = h->smooth_X; A.ld = h->smooth_ldx;
+  } else if (a->source == RTHX_SOLVE_FROM_DENSE) {
+    if (!a->F_dense || (a->layout != RTHX_ROW_MAJOR && a->layout != RTHX_COL_MAJOR)) return fail(h, RTHX_ERR_ARG, "solve: F_dense is NULL or unknown layout");
+    CU(h, ensure(&h->solve_mat, &h->solve_mat_cap, (size_t)n * nl));
+    CU(h, cudaMemsetAsync(h->solve_mat, 0, sizeof(double) * (size_t)n * nl, h->stream));      // row padding must read as zeros
+    CU(h, cudaMemcpy2DAsync(h->solve_mat, sizeof(double) * nl, a->F_dense, sizeof(double) * (size_t)n, sizeof(double) * (size_t)n, (size_t)n,
+                            cudaMemcpyHostToDevice, h->stream));
+    A.kind = a->layout == RTHX_ROW_MAJOR ? 0 : 1; A.dense = h->solve_mat; A.ld = nl;
+  } else if (a->source == RTHX_SOLVE_FROM_CSC) {
+    if (!a->colptr || (!a->rowval && a->colptr[n] > 0) || (!a->nzval && a->colptr[n] > 0)) return fail(h, RTHX_ERR_ARG, "solve: CSC arrays missing");
+    const long long nnz = a->colptr[n];
+    if (nnz < 0 || a->colptr[0] != 0) return fail(h, RTHX_ERR_ARG, "solve: colptr must be 0-based and non-decreasing");
+    // one buffer: nzval [nnz] doubles | colptr [n+1] i64 | rowval [nnz] i32
+    const size_t need = (size_t)std::max<long long>(nnz, 1) + (size_t)(n + 1) + ((size_t)std::max<long long>(nnz, 1) + 1) / 2 + 4;
+    CU(h, ensure(&h->solve_mat, &h->solve_mat_cap, need));
+    double* nz = h->solve_mat;
+    long long* cp = reinterpret_cast<long long*>(nz + std::max<long long>(nnz, 1));
+    int* rv = reinterpret_cast<int*>(cp + (n + 1));
+    if (nnz > 0) {
+      CU(h, cudaMemcpyAsync(nz, a->nzval, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, h->stream));
+      CU(h, cudaMemcpyAsync(rv, a->rowval, sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice, h->stream));
+    }
+    CU(h, cudaMemcpyAsync(cp, a->colptr, sizeof(long long) * (size_t)(n + 1), cudaMemcpyHostToDevice, h->stream));
+    A.kind = 2; A.colptr = cp; A.rowval = rv; A.nzval = nz; A.nnz = nnz;
+  } else {
+    return fail(h, RTHX_ERR_ARG, "solve: unknown source");
+  }
+  const size_t vec = rthx::solve_vec_doubles(nl, m);
+  const size_t part = A.kind == 0 ? rthx::solve_part_doubles(n, A.ld) : 0;
+  CU(h, ensure(&h->solve_buf, &h->solve_cap, vec + part));
+  CU(h, cudaMemsetAsync(h->solve_buf, 0, sizeof(double) * vec, h->stream));
+  double* coeff_dev = h->solve_buf + (size_t)(m + 4) * nl;     // layout of run_gmres: V[(m+1)] | w | x | r | coeff | rhs | d
+  double* rhs_dev = coeff_dev + nl;
+  CU(h, cudaMemcpyAsync(coeff_dev, a->coeff, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaMemcpyAsync(rhs_dev, a->rhs, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+  rthx::SolveResult res{};
+  CU(h, rthx::run_gmres(A, n, nl, m, max_iters, rtol, atol, h->solve_buf, h->solve_buf + vec, j_out, g_out, h->stream, h->ev[0], h->ev[1], &res));
+  double mv_ms = 0;
+  if (a->measure_pass) CU(h, rthx::time_matvec(A, n, nl, m, h->solve_buf, h->solve_buf + vec, 20, h->stream, h->ev[0], h->ev[1], &mv_ms));
+  if (st) {
+    std::memset(st, 0, sizeof(*st));
+    st->iterations = res.iterations; st->restarts = res.restarts; st->launches = res.launches; st->converged = res.converged; st->matvecs = res.matvecs;
+    st->residual = res.residual; st->rhs_norm = res.rhs_norm; st->total_ms = res.total_ms; st->matvec_bytes = res.matvec_bytes;
+    st->matvec_ms = mv_ms; st->matvec_gbs = mv_ms > 0 ? (double)res.matvec_bytes / (mv_ms * 1e-3) / 1e9 : 0.0;
   }
   return RTHX_OK;
 }

@@ -101,4 +101,28 @@ cudaError_t configure_trace_kernel(size_t smem_bytes);
 cudaError_t launch_fp64_peak(double* out, int n_blocks, int block_threads, int iters, cudaStream_t stream);
 int trace_kernel_max_blocks_per_sm(int block_threads, size_t smem_bytes, bool hist, bool fast, int minb, bool multi, bool sq);
 
+// ---- grey equilibrium solve (rthx_solve.cu) ---------------------------------------------------------------------
+struct SolveMatrix {
+  int kind = 0;                      // 0 dense row-major F, 1 dense col-major F (= F' row-major), 2 CSC
+  const double* dense = nullptr;     // device
+  size_t ld = 0;
+  const long long* colptr = nullptr; // device
+  const int* rowval = nullptr;
+  const double* nzval = nullptr;
+  long long nnz = 0;
+};
+
+struct SolveResult {
+  int iterations = 0, restarts = 0, launches = 0, converged = 0, matvecs = 0;
+  double residual = 0, rhs_norm = 0, total_ms = 0, matvec_ms = 0;
+  long long matvec_bytes = 0;
+};
+
+size_t solve_part_doubles(int n, size_t ld);
+size_t solve_vec_doubles(size_t nl, int m);
+cudaError_t run_gmres(const SolveMatrix& A, int n, size_t nl, int m, int max_iters, double rtol, double atol, double* buf, double* part, double* j_host,
+                      double* g_host, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1, SolveResult* out);
+cudaError_t time_matvec(const SolveMatrix& A, int n, size_t nl, int m, double* buf, double* part, int reps, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1,
+                        double* ms_per_pass);
+
 }  // namespace rthx

@@ -35,7 +35,10 @@ class PolyVolume2D:
 
     __slots__ = ("vertices", "solidWalls", "midPoint", "volume", "area", "subVolumes",
                  "n_spectral_bins", "kappa_g", "sigma_s_g", "epsilon",
-                 "T_in_w", "T_in_g", "q_in_g", "q_in_w", "T_g", "T_w")
+                 "T_in_w", "T_in_g", "q_in_g", "q_in_w", "T_g", "T_w",
+                 # result fields written by solveEquilibrium (DomainStructs.jl:22-43)
+                 "j_g", "g_a_g", "e_g", "r_g", "g_g", "i_g", "q_g",
+                 "j_w", "g_a_w", "e_w", "r_w", "g_w", "i_w", "q_w")
 
     def __init__(self, vertices, solidWalls, n_spectral_bins: int = 1,
                  kappa_default: float = 0.0, sigma_s_default: float = 0.0):
@@ -79,6 +82,9 @@ class PolyVolume2D:
         self.q_in_g = 0.0
         self.T_g = 0.0
         self.T_w = [0.0] * n
+        self.j_g = self.g_a_g = self.e_g = self.r_g = self.g_g = self.i_g = self.q_g = 0.0
+        self.j_w, self.g_a_w, self.e_w, self.r_w = [0.0] * n, [0.0] * n, [0.0] * n, [0.0] * n
+        self.g_w, self.i_w, self.q_w = [0.0] * n, [0.0] * n, [0.0] * n
 
     # -- helpers -------------------------------------------------------------------------------
     def beta(self, band: int = 0) -> float:

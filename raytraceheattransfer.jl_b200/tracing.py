@@ -179,6 +179,9 @@ def _smooth_on_device(rtm, F_raw, w, ns: int, max_iters: int, verbose: bool):
     verbose and print(f"Matrix size: {n}x{n}; dense alternating projection on the device")
     F_smooth, st = tr.smooth(wn, n=n, max_iters=max_iters)
     rtm.last_smooth_stats = st
+    # the smoothed matrix also stays on the device: solveEquilibrium reads it there when handed this very array
+    from .equilibrium import _sample_of
+    tr._resident_F = (F_smooth, _sample_of(F_smooth))
     verbose and print(f"AP: {st['iterations']} iterations, delta_R {st['delta_init']:.3e} -> {st['delta']:.3e}, "
                       f"{st['total_ms']:.1f} ms on the device")
     return F_smooth

@@ -32,6 +32,8 @@ int main(void) {
   printf("%zu %zu %zu %zu %zu\n", sizeof(rthx_mesh), sizeof(rthx_trace_args), sizeof(rthx_rec_out), sizeof(rthx_stats), sizeof(rthx_info));
   printf("%zu %zu %zu %zu\n", offsetof(rthx_trace_args, nudge), offsetof(rthx_trace_args, bins), offsetof(rthx_trace_args, rec_ids), offsetof(rthx_trace_args, row_chunks));
   printf("%zu %zu\n", offsetof(rthx_mesh, uniform_beta), offsetof(rthx_stats, n_launches));
+  printf("%zu %zu %zu %zu %zu %zu\n", sizeof(rthx_solve_args), sizeof(rthx_solve_stats), sizeof(rthx_smooth_stats),
+         offsetof(rthx_solve_args, F_dense), offsetof(rthx_solve_args, atol), offsetof(rthx_solve_stats, matvec_bytes));
   return 0;
 }'''
     with tempfile.TemporaryDirectory() as d:
@@ -42,7 +44,9 @@ int main(void) {
     A = _abi.rthx_trace_args
     want = [C.sizeof(_abi.rthx_mesh), C.sizeof(A), C.sizeof(_abi.rthx_rec_out), C.sizeof(_abi.rthx_stats), C.sizeof(_abi.rthx_info),
             A.nudge.offset, A.bins.offset, A.rec_ids.offset, A.row_chunks.offset,
-            _abi.rthx_mesh.uniform_beta.offset, _abi.rthx_stats.n_launches.offset]
+            _abi.rthx_mesh.uniform_beta.offset, _abi.rthx_stats.n_launches.offset,
+            C.sizeof(_abi.rthx_solve_args), C.sizeof(_abi.rthx_solve_stats), C.sizeof(_abi.rthx_smooth_stats),
+            _abi.rthx_solve_args.F_dense.offset, _abi.rthx_solve_args.atol.offset, _abi.rthx_solve_stats.matvec_bytes.offset]
     assert got == want
 
 
@@ -56,6 +60,9 @@ def test_no_gpu_fails_loudly(cuda_lib, rthx_mod):
     rtm = rthx_mod.meshes.square_domain(3)
     with pytest.raises(rthx_mod.RthxError):
         rtm(1000, method="exchange", verbose=False)               # the public call has no CPU fallback either
+    import numpy as np
+    with pytest.raises(rthx_mod.RthxError):
+        rthx_mod.solveEquilibrium(rtm, np.eye(rtm.num_elements), verbose=False)   # nor has the equilibrium solve
 
 
 def test_bad_mesh_rejected_before_touching_the_device(cuda_lib, rthx_mod):

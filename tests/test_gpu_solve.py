@@ -1,0 +1,161 @@
+"""GPU grey equilibrium solve (rthx_solve_grey) against the numpy restatement of the reference's `M \\ h`
+(oracle/grey_solver.py, equilibriumGrey2D.jl:80-211).  Tolerance: the solve stops at a relative residual of 1e-12
+(the reference's own GMRES setting, :154), so j is compared to the LU answer at 1e-9 relative, temperatures through T^4 at 1e-9 of T_hot^4."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+pytestmark = pytest.mark.gpu
+
+
+def _system(n, seed, density=1.0):
+    rng = np.random.default_rng(seed)
+    F = rng.random((n, n))
+    if density < 1.0:
+        F *= rng.random((n, n)) < density
+        F[np.arange(n), rng.integers(0, n, n)] += 0.1          # no empty rows
+    F /= F.sum(axis=1, keepdims=True)
+    coeff = rng.random(n) * 0.9
+    coeff[rng.random(n) < 0.3] = 1.0                            # elements with prescribed flux (Q known)
+    coeff[: max(2, n // 10)] = 0.0                              # black walls at prescribed temperature close the system
+    h = rng.random(n) * 1e3
+    return F, coeff, h
+
+
+def _tracer(rthx_mod):
+    rtm = rthx_mod.meshes.square_domain(3)
+    return rthx_mod.DeviceTracer(rthx_mod.flatten_domain(rtm), device=0)
+
+
+@pytest.mark.parametrize("n", [1, 7, 165, 1000, 1845])
+def test_dense_sources_match_numpy(rthx_mod, cuda_lib, n):
+    F, coeff, h = _system(n, 100 + n)
+    M = np.eye(n) - coeff[:, None] * F.T
+    j_ref = np.linalg.solve(M, h)
+    g_ref = F.T @ j_ref
+    tr = _tracer(rthx_mod)
+    scale = np.abs(j_ref).max()
+    ja, ga, sa = tr.solve_grey(coeff, h, F=F)                                     # row-major (numpy)
+    jb, gb, sb = tr.solve_grey(coeff, h, F=np.asfortranarray(F).T, col_major=True)  # the memory of a Julia Matrix
+    jc, gc, sc = tr.solve_grey(coeff, h, F=sp.csc_matrix(F))                      # SparseMatrixCSC
+    for j, g, st in ((ja, ga, sa), (jb, gb, sb), (jc, gc, sc)):
+        assert st["converged"] == 1 and st["residual"] <= 1.5e-8 + 1e-12 * st["rhs_norm"]
+        assert np.abs(j - j_ref).max() <= 1e-9 * scale
+        assert np.abs(g - g_ref).max() <= 1e-9 * scale
+    tr.close()
+
+
+def test_restarts_and_iteration_cap(rthx_mod, cuda_lib):
+    n = 400
+    F, coeff, h = _system(n, 7)
+    j_ref = np.linalg.solve(np.eye(n) - coeff[:, None] * F.T, h)
+    tr = _tracer(rthx_mod)
+    j, g, st = tr.solve_grey(coeff, h, F=F, memory=4)          # GMRES(4): many restart cycles, same answer
+    assert st["restarts"] > 0 and st["converged"] == 1
+    assert np.abs(j - j_ref).max() <= 1e-9 * np.abs(j_ref).max()
+    j2, g2, st2 = tr.solve_grey(coeff, h, F=F, max_iters=3)    # capped: reports non-convergence instead of lying
+    assert st2["converged"] == 0 and st2["iterations"] == 3 and st2["residual"] > 1e-8
+    # bit-reproducible
+    j3, _, _ = tr.solve_grey(coeff, h, F=F, memory=4)
+    assert np.array_equal(j, j3)
+    tr.close()
+
+
+def test_sparse_matrix_and_zero_rhs(rthx_mod, cuda_lib):
+    n = 600
+    F, coeff, h = _system(n, 11, density=0.02)
+    Fs = sp.csc_matrix(F)
+    assert Fs.nnz < 0.05 * n * n
+    tr = _tracer(rthx_mod)
+    j, g, st = tr.solve_grey(coeff, h, F=Fs, measure_pass=True)
+    j_ref = np.linalg.solve(np.eye(n) - coeff[:, None] * F.T, h)
+    assert st["converged"] == 1 and np.abs(j - j_ref).max() <= 1e-9 * np.abs(j_ref).max()
+    assert st["matvec_bytes"] == 12 * Fs.nnz + 8 * (n + 1) and st["matvec_gbs"] > 0
+    jz, gz, stz = tr.solve_grey(coeff, np.zeros(n), F=Fs)
+    assert stz["converged"] == 1 and stz["iterations"] == 0 and not jz.any() and not gz.any()
+    tr.close()
+
+
+def test_resident_smoothed_matrix_and_errors(rthx_mod, cuda_lib):
+    """trace -> smooth -> solve with F never leaving the device; the result equals the solve of the returned matrix."""
+    rtm = rthx_mod.meshes.square_domain(9, kappa=0.5, sigma_s=0.5)
+    flat = rthx_mod.flatten_domain(rtm)
+    tr = rthx_mod.DeviceTracer(flat, device=0)
+    n = flat.n_elements
+    _, coeff, h = _system(n, 5)
+    with pytest.raises(rthx_mod.RthxError):
+        tr.solve_grey(coeff, h)                                 # nothing resident yet
+    tr.trace(20000, seed=3, dense=False)
+    w = rthx_mod.get_w(rtm)
+    Fs, _ = tr.smooth(w / w.min())
+    j, g, st = tr.solve_grey(coeff, h, measure_pass=True)
+    j2, g2, _ = tr.solve_grey(coeff, h, F=Fs)
+    assert np.array_equal(j, j2) and np.array_equal(g, g2)      # same kernel, same summation order
+    j_ref = np.linalg.solve(np.eye(n) - coeff[:, None] * Fs.T, h)
+    assert np.abs(j - j_ref).max() <= 1e-9 * np.abs(j_ref).max()
+    assert st["matvec_bytes"] == 8 * n * n and st["matvec_ms"] > 0
+    with pytest.raises(rthx_mod.RthxError):
+        tr.solve_grey(coeff[:-1], h[:-1])                       # size mismatch with the resident matrix
+    tr.close()
+
+
+@pytest.mark.parametrize("case", ["black_scattering", "reflecting_walls", "flux_wall"])
+def test_public_solve_matches_reference_restatement(rthx_mod, cuda_lib, case):
+    """mesh(N) then solveEquilibrium!(mesh, mesh.F_smooth): every field the reference writes agrees with the numpy
+    restatement of equilibriumGrey2D.jl run on the same F."""
+    from oracle import grey_solver as gs
+    if case == "black_scattering":
+        rtm = rthx_mod.meshes.square_domain(11, kappa=0.5, sigma_s=0.5)
+    elif case == "reflecting_walls":
+        rtm = rthx_mod.meshes.square_domain(9, kappa=1.0, epsilon=(1.0, 0.5, 0.5, 0.5))
+    else:
+        rtm = rthx_mod.meshes.square_domain(9, kappa=1.0)
+        for cell in rtm.fine_mesh[0]:
+            for w, solid in enumerate(cell.solidWalls):
+                if solid and w == 2:                             # top wall: prescribed flux instead of temperature
+                    cell.T_in_w[w] = -1.0
+                    cell.q_in_w[w] = 25.0 * cell.area[w]
+    F = rtm(400_000, method="exchange", verbose=False, seed=77)
+    rthx_mod.solveEquilibrium(rtm, F, verbose=False)
+    st = rtm.last_solve_stats
+    assert st["converged"] == 1
+    got_Tg = np.array([c.T_g for c in rtm.fine_mesh[0]])
+    got_Tw = np.array([c.T_w[w] for c in rtm.fine_mesh[0] for w, s in enumerate(c.solidWalls) if s])
+    got_qw = np.array([c.q_w[w] for c in rtm.fine_mesh[0] for w, s in enumerate(c.solidWalls) if s])
+    got_err = rtm.energy_error
+    ref = gs.solve_grey(rtm, F)            # (overwrites the T fields of rtm: the GPU results were read out above)
+    # temperatures are compared through T^4 (emissive power): a cold wall with eps < 1 has T = (rounding noise)^(1/4),
+    # which turns residuals of 1e-9 into ~1 K in either solver
+    T4 = 1000.0 ** 4
+    assert np.abs(got_Tg ** 4 - ref["T_g"] ** 4).max() < 1e-9 * T4
+    assert np.abs(got_Tw ** 4 - ref["T_w"] ** 4).max() < 1e-9 * T4
+    assert abs(got_err) < 1e-4 and abs(got_err - ref["energy_error"]) < 1e-6
+    assert np.isfinite(got_qw).all()
+    # a fresh copy of F (not the resident array) takes the upload path and gives the same temperatures
+    rthx_mod.solveEquilibrium(rtm, F.copy(), verbose=False)
+    assert np.abs(np.array([c.T_g for c in rtm.fine_mesh[0]]) ** 4 - got_Tg ** 4).max() < 1e-9 * T4
+
+
+def test_crosbie_schrenker_end_to_end_on_device(rthx_mod, cuda_lib):
+    """trace + smooth + solve all on the GPU (cfg1, README Example 1) -> Crosbie & Schrenker centre-line within the
+    reference's own acceptance (test/test_2d_grey.jl:216 rtol = 0.05, :220 energy error < 1e-4)."""
+    from oracle import grey_solver as gs
+    rtm = rthx_mod.meshes.cfg1()
+    F = rtm(1_000_000, method="exchange", verbose=False, seed=2024)
+    rthx_mod.solveEquilibrium(rtm, F, verbose=False)
+    S = gs.centerline_source_function(rtm, 11, 1000.0)
+    A = gs.analytical_centerline(11)
+    assert np.linalg.norm(S - A) <= 0.05 * max(np.linalg.norm(S), np.linalg.norm(A))
+    assert abs(rtm.energy_error) < 1e-4
+
+
+def test_sparse_public_path_diffusion_mesh(rthx_mod, cuda_lib):
+    """An optically thick mesh keeps F sparse (test/test_2d_diffusion.jl:57-65): the solve takes the CSC path."""
+    from oracle import grey_solver as gs
+    rtm = rthx_mod.meshes.square_domain(15, kappa=40.0)
+    F = rtm(600_000, method="exchange", verbose=False, seed=5)
+    assert sp.issparse(F)
+    rthx_mod.solveEquilibrium(rtm, F, verbose=False)
+    got = np.array([c.T_g for c in rtm.fine_mesh[0]])
+    ref = gs.solve_grey(rtm, F)
+    assert np.abs(got ** 4 - ref["T_g"] ** 4).max() < 1e-9 * 1000.0 ** 4 and rtm.last_solve_stats["matvec_bytes"] == 12 * F.nnz + 8 * (F.shape[0] + 1)

@@ -126,3 +126,49 @@ def test_unknown_method_raises(rthx_mod):
     rtm = rthx_mod.meshes.square_domain(3)
     with pytest.raises(ValueError, match="Unknown ray tracing method"):
         rtm(1000, method="bogus")
+
+
+def test_equilibrium_host_vectors_match_the_numpy_restatement(rthx_mod):
+    """populateWorkspace! / emissive powers / coeff / h of the package mirror (equilibrium.py) against the independent
+    numpy restatement used by the tests (oracle/grey_solver.py), on a mesh with reflecting walls, scattering gas, a flux
+    wall and a prescribed-temperature gas cell."""
+    from rthx import equilibrium as eq
+    rtm = rthx_mod.meshes.square_domain(5, kappa=0.7, sigma_s=0.3, epsilon=(1.0, 0.5, 0.8, 0.5))
+    cells = rtm.fine_mesh[0]
+    cells[7].T_in_g = 650.0                                     # one gas cell at prescribed temperature
+    for cell in cells:
+        for w, solid in enumerate(cell.solidWalls):
+            if solid and w == 2:
+                cell.T_in_w[w] = -1.0; cell.q_in_w[w] = 3.0     # flux-specified top wall
+    ws = eq.populateWorkspace(rtm)
+    Qk, b, coeff, h = eq._system_vectors(rtm, ws)
+    ns, nv = rtm.num_surfaces, rtm.num_volumes
+    assert len(h) == ns + nv and Qk[:ns].sum() == 5 and Qk[ns:].sum() == nv - 1
+    assert np.allclose(b, rthx_mod.get_b(rtm)[:, 0])
+    assert np.array_equal(coeff, np.where(Qk, 1.0, b))
+    # surfaces in mapping order
+    for (c, f, w), s in rtm.surface_mapping.items():
+        cell = rtm.fine_mesh[c - 1][f - 1]
+        assert ws["Area"][s - 1] == cell.area[w - 1] and ws["epsw"][s - 1] == cell.eps(w - 1)
+        want = cell.q_in_w[w - 1] if cell.T_in_w[w - 1] < 0 else cell.eps(w - 1) * eq.STEFAN_BOLTZMANN * cell.area[w - 1] * cell.T_in_w[w - 1] ** 4
+        assert h[s - 1] == pytest.approx(want, rel=1e-15)
+    v = rtm.volume_mapping[(1, 8)]
+    assert h[ns + v - 1] == pytest.approx(4 * 0.7 * eq.STEFAN_BOLTZMANN * cells[7].volume * 650.0 ** 4, rel=1e-15)
+    # buildSystemMatrix.jl: M = I - Diagonal(coeff) F'
+    rng = np.random.default_rng(0)
+    F = rng.random((ns + nv, ns + nv)); F /= F.sum(axis=1, keepdims=True)
+    M = rthx_mod.buildSystemMatrix(rtm, sp.csc_matrix(F))
+    assert np.allclose(M, np.eye(ns + nv) - coeff[:, None] * F.T, atol=1e-15)
+
+
+def test_solve_equilibrium_dispatch(rthx_mod):
+    rtm = rthx_mod.meshes.cfg4(Ndim=3, n_bins=2)
+    with pytest.raises(NotImplementedError):
+        rthx_mod.solveEquilibrium(rtm, [None, None])
+    rtm = rthx_mod.meshes.square_domain(3)
+    rtm.spectral_mode = "nonsense"
+    with pytest.raises(ValueError, match="Unknown spectral mode"):
+        rthx_mod.solveEquilibrium(rtm, np.eye(rtm.num_elements))
+    rtm.spectral_mode = "grey"
+    with pytest.raises(ValueError, match="expected"):
+        rthx_mod.solveEquilibrium(rtm, np.eye(3), verbose=False)
