@@ -544,7 +544,10 @@ LaunchPlan make_plan(const rthx_handle* h, const rthx_trace_args* a, int rank, i
   if (const char* ev = std::getenv("RTHX_FORCE_GLOBAL_TALLY")) { if (std::atoi(ev)) pl.hist_in_smem = 0; }   // test knob: the N > ~57k path
   pl.sq = (h->single_quad && a->locator != RTHX_LOCATOR_GENERIC && !pl.multi && pl.hist_in_smem) ? 1 : 0;
   if (const char* ev = std::getenv("RTHX_NO_SQ")) { if (std::atoi(ev)) pl.sq = 0; }   // test / tuning knob
-  if (pl.sq) { pl.fast = 1; pl.minb = 4; }
+  if (pl.sq) {
+    pl.fast = 1; pl.minb = 4;
+    if (const char* ev = std::getenv("RTHX_MINB")) { if (std::atoi(ev) == 5) pl.minb = 5; }   // tuning knob: 48 registers, 5 blocks / SM
+  }
   pl.smem_bytes = coarse_bytes + em_bytes + (pl.hist_in_smem ? hist_bytes : 0);
   const long long rows = (long long)pl.n_owned * a->n_bins;
   long long chunks = a->row_chunks;

@@ -630,7 +630,8 @@ __global__ void __launch_bounds__(256, MINB) trace_exchange_kernel(const __grid_
 // kernel variants: hist_in_smem x fast x multi; the register bound MINB only varies for the hot FIRST_INTERACTION FAST kernel
 typedef void (*TraceKernel)(const TraceParams);
 static TraceKernel kernel_variant(bool hist, bool fast, int minb, bool multi, bool sq) {
-  if (sq && hist && fast && !multi) return (TraceKernel)trace_exchange_kernel<true, true, 4, false, true>;
+  if (sq && hist && fast && !multi)
+    return minb == 5 ? (TraceKernel)trace_exchange_kernel<true, true, 5, false, true> : (TraceKernel)trace_exchange_kernel<true, true, 4, false, true>;
   if (multi) {
     if (hist) return fast ? (TraceKernel)trace_exchange_kernel<true, true, 2, true, false> : (TraceKernel)trace_exchange_kernel<true, false, 2, true, false>;
     return fast ? (TraceKernel)trace_exchange_kernel<false, true, 2, true, false> : (TraceKernel)trace_exchange_kernel<false, false, 2, true, false>;
@@ -649,7 +650,7 @@ cudaError_t configure_trace_kernel(size_t smem_bytes) {
     for (int multi = 0; multi < 2; ++multi)
       for (int hist = 0; hist < 2; ++hist)
         for (int fast = 0; fast < 2; ++fast)
-          for (int minb = 2; minb <= 4; ++minb) {
+          for (int minb = 2; minb <= 5; ++minb) {
             cudaError_t e = cudaFuncSetAttribute((const void*)kernel_variant(hist, fast, minb, multi, sq), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
             if (e != cudaSuccess) return e;
           }

@@ -169,12 +169,21 @@ __global__ void __launch_bounds__(256) residual_kernel(const double* __restrict_
 // ---------------------------------------------------------------------------------------------------------------
 // host driver
 // ---------------------------------------------------------------------------------------------------------------
-// row tiling of the dense transposed product: a function of n only, so the summation order — and with it every bit of the
-// result — is the same on every device
+// Row tiling of the dense transposed product: column strips x row tiles fill exactly ONE wave of resident blocks
+// (SM count x occupancy of matvec_t_partial_kernel), so no block waits for a slot and no tail wave runs half empty.
+// The tiling fixes the summation order; it depends on n and the device model only (results are bit-reproducible on B200).
 static int mv_row_tiles(int n, size_t ld) {
+  static int slots = 0;
+  if (slots == 0) {
+    int dev = 0, sms = 148, occ = 6;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, matvec_t_partial_kernel, MV_THREADS, 0) != cudaSuccess || occ < 1) occ = 6;
+    slots = sms * occ;
+  }
   const int col_blocks = (int)(((ld >> 1) + MV_THREADS - 1) / MV_THREADS);
-  int tiles = (1184 + col_blocks - 1) / col_blocks;          // ~8 blocks per SM on 148 SMs
-  tiles = std::max(1, std::min(tiles, std::min(64, (n + 31) / 32)));
+  int tiles = slots / col_blocks;
+  tiles = std::max(1, std::min(tiles, std::min(256, (n + 15) / 16)));
   return tiles;
 }
 
