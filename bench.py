@@ -51,7 +51,7 @@ def parse_args():
 
 
 # DRAM bytes per launch of trace_exchange_kernel measured by ncu (profiles/r1d_trace_exchange_metrics.csv)
-NCU_DRAM_BYTES_PER_LAUNCH = {"cfg3": 895565312 + 833359872}
+NCU_DRAM_BYTES_PER_LAUNCH = {"cfg3": 894779904 + 835332096}   # profiles/r1g_trace_exchange_metrics.csv
 
 DEFAULT_RAYS = {"cfg1": 1e6, "cfg2": 1e8, "cfg3": 1e10, "cfg4": 1e8, "cfg5": 1e9}
 
@@ -422,7 +422,9 @@ def main():
                  "frac": sv["matvec_gbs"] / hbm_peak, "bytes_per_pass": sv["matvec_bytes"], "pass_ms": sv["matvec_ms"],
                  "iterations": sv["iterations"], "restarts": sv["restarts"], "matvecs": sv["matvecs"],
                  "converged": sv["converged"], "residual": sv["residual"], "rhs_norm": sv["rhs_norm"],
-                 "total_ms": sv["total_ms"], "launches": sv["launches"], "peak_source": peak_src}
+                 "total_ms": sv["total_ms"], "launches": sv["launches"], "peak_source": peak_src,
+                 "traffic": 900086016 + 6328576,
+                 "traffic_note": "dram bytes read + written per launch, ncu --set full, profiles/r1g_solve_matvec_metrics.csv"}
         tr.close()
         smoothing = {"kernel": "scale_rows_kernel (one alternating-projection iteration: X *= (u_i+u_j)/2 with fused row sums)",
                      "bound": "hbm", "achieved": ss["pass_gbs"], "peak": hbm_peak, "unit": "GB/s",
@@ -447,7 +449,7 @@ def main():
                 "frac": achieved / fp64_peak if fp64_peak else None,
                 "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(args.workload),
                 "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture "
-                                "profiles/r1d_trace_exchange_metrics.csv (cfg3; the reductions read-modify-write the zeroed "
+                                "profiles/r1g_trace_exchange_metrics.csv (cfg3; the reductions read-modify-write the zeroed "
                                 "8*N*N-byte count matrix once, independent of the ray count)",
                 "kernel": "trace_exchange_kernel", "kernel_ms": kernel_ms, "kernel_rays_per_s": kernel_rays_per_s,
                 "flop_per_ray": A,

@@ -231,9 +231,21 @@ typedef struct rthx_smooth_stats {
   double  ms_per_iteration;
   double  pass_ms;              /* one scaling pass (read + write of X, fused row sums) */
   double  pass_gbs;             /* 16 n^2 bytes / pass_ms */
+  int32_t dykstra_rounds;       /* rthx_smooth_DkAP: rounds executed */
+  int32_t pcg_iterations;       /* total PCG iterations of the dual solves inside the rounds */
+  double  dykstra_delta;        /* delta_perp after the last checked round (delta_perp :DYK, :136-142) */
+  double  dykstra_ms;           /* device time of the rounds */
 } rthx_smooth_stats;
 int rthx_smooth_F(rthx_handle* h, int source, const void* src_host, int bin, int n, const double* w, int max_iters,
                   double target, int measure_pass, double* F_out, rthx_smooth_stats* stats);
+/* The same with `k_dykstra` Dykstra rounds in front of the alternating projection — DkAP, smoothExchangeFactors.jl:299-318:
+ * each round is the orthogonal projection OP (:292-297) onto {reciprocal, unit row sums} through the dual system
+ * R lambda = b (Jacobi-PCG, :15-37; the reduced-mass weights Y are formed on the fly, never stored), followed by
+ * max(., 0) with the Dykstra correction; the rows are then renormalised and polished by AP.  The reference's own
+ * default for a dense F is k_dykstra = 1 when the surface-gas cross-coupling chi >= 0.4, else 0 (:441-450); the caller
+ * makes that choice (cross_coupling_chi :215-241 is O(nnz) on the host).  k_dykstra = 0 is rthx_smooth_F. */
+int rthx_smooth_DkAP(rthx_handle* h, int source, const void* src_host, int bin, int n, const double* w, int k_dykstra,
+                     int max_iters, double target, int measure_pass, double* F_out, rthx_smooth_stats* stats);
 
 /* Grey GERT equilibrium solve on the device (next-stage row of the hot path: the consumer of F).  Restates the
  * linear-algebra core of src/HeatTransfer/equilibrium/equilibriumGrey2D.jl:80-211:

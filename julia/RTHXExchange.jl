@@ -184,4 +184,59 @@ function RayTraceHeatTransfer.parallelRayTracing(rtm::RayTracingDomain2D, rays_t
     return trace_bins(rtm, rays_per_emitter, Float64(nudge), [1], rec)[1], rays_per_emitter
 end
 
+# ---- optional: the linear solve of equilibriumGrey2D! on the device (rthx_solve_grey, include/rthx.h) ----------------
+struct RthxSolveArgs
+    n::Int32; source::Int32; layout::Int32; memory::Int32; max_iters::Int32; measure_pass::Int32
+    F_dense::Ptr{Float64}; colptr::Ptr{Int64}; rowval::Ptr{Int32}; nzval::Ptr{Float64}
+    coeff::Ptr{Float64}; rhs::Ptr{Float64}; rtol::Float64; atol::Float64
+end
+
+mutable struct RthxSolveStats
+    iterations::Int32; restarts::Int32; launches::Int32; converged::Int32; matvecs::Int32; pad_::Int32
+    residual::Float64; rhs_norm::Float64; total_ms::Float64; matvec_ms::Float64; matvec_gbs::Float64; matvec_bytes::Int64
+    RthxSolveStats() = new(0, 0, 0, 0, 0, 0, 0.0, 0.0, 0.0, 0.0, 0.0, 0)
+end
+
+"""
+    solve_grey(rtm, F, coeff, h; memory = 50, rtol = 1e-12) -> (j, g, stats)
+
+Solves `(I - Diagonal(coeff) * F') * j = h` on the GPU and returns the incident power `g = F' * j` with it: the two
+O(N^2) steps of `equilibriumGrey2D!` (src/HeatTransfer/equilibrium/equilibriumGrey2D.jl:148-158 and :168-194).
+A `Matrix{Float64}` is handed over as it lies in memory (column-major), a `SparseMatrixCSC` by its three fields.
+In `equilibriumGrey2D!` the maintainer replaces
+    M = I - Diagonal(coeff) * permutedims(F); j = F isa SparseMatrixCSC ? gmres(...) : M \ h      (:149-158)
+    the two receiver loops                                                                          (:168-194)
+by
+    j, g, _ = RTHXExchange.solve_grey(mesh, F, coeff, h);  r .= b .* g;  Abs .= (1 .- b) .* g
+"""
+function solve_grey(rtm::RayTracingDomain2D, F::AbstractMatrix, coeff::Vector{Float64}, h::Vector{Float64};
+                    memory::Integer = 50, rtol::Float64 = 1e-12)
+    n = length(h)
+    size(F) == (n, n) && length(coeff) == n || error("solve_grey: size mismatch")
+    mesh, arrays = flatten(rtm)
+    j = zeros(n); g = zeros(n); stats = RthxSolveStats()
+    hd = Ref{Ptr{Cvoid}}(C_NULL)
+    if F isa SparseMatrixCSC
+        colptr = Int64.(F.colptr .- 1); rowval = Int32.(F.rowval .- 1); nzval = Vector{Float64}(F.nzval)
+        Fd = Float64[]
+    else
+        colptr = Int64[]; rowval = Int32[]; nzval = Float64[]
+        Fd = Matrix{Float64}(F)
+    end
+    GC.@preserve arrays colptr rowval nzval Fd coeff h j g begin
+        check(ccall((:rthx_create, LIB), Cint, (Ref{Ptr{Cvoid}}, Ref{RthxMesh}, Cint), hd, mesh, DEVICES[][1]), C_NULL)
+        args = F isa SparseMatrixCSC ?
+            RthxSolveArgs(n, 2, 0, memory, 0, 0, C_NULL, pointer(colptr), pointer(rowval), pointer(nzval),
+                          pointer(coeff), pointer(h), rtol, -1.0) :
+            RthxSolveArgs(n, 1, 1, memory, 0, 0, pointer(Fd), C_NULL, C_NULL, C_NULL,        # RTHX_COL_MAJOR
+                          pointer(coeff), pointer(h), rtol, -1.0)
+        rc = ccall((:rthx_solve_grey, LIB), Cint, (Ptr{Cvoid}, Ref{RthxSolveArgs}, Ptr{Float64}, Ptr{Float64}, Ref{RthxSolveStats}),
+                   hd[], args, j, g, stats)
+        check(rc, hd[])
+        ccall((:rthx_destroy, LIB), Cint, (Ptr{Cvoid},), hd[])
+    end
+    stats.converged == 1 || @warn "rthx_solve_grey: residual $(stats.residual) after $(stats.iterations) iterations"
+    return j, g, stats
+end
+
 end # module

@@ -96,6 +96,9 @@ def load_library():
     L.rthx_smooth_F.restype = C.c_int
     L.rthx_smooth_F.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, c_f64p, C.c_int, C.c_double, C.c_int,
                                 c_f64p, C.POINTER(rthx_smooth_stats)]
+    L.rthx_smooth_DkAP.restype = C.c_int
+    L.rthx_smooth_DkAP.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, c_f64p, C.c_int, C.c_int, C.c_double, C.c_int,
+                                   c_f64p, C.POINTER(rthx_smooth_stats)]
     L.rthx_solve_grey.restype = C.c_int
     L.rthx_solve_grey.argtypes = [C.c_void_p, C.POINTER(rthx_solve_args), c_f64p, c_f64p, C.POINTER(rthx_solve_stats)]
     L.rthx_release_cached.restype = C.c_int
@@ -240,8 +243,8 @@ class DeviceTracer:
 
     def smooth(self, w, n: Optional[int] = None, counts: Optional[np.ndarray] = None, F: Optional[np.ndarray] = None,
                bin: int = 0, max_iters: int = 1000, target: float = 0.0, measure_pass: bool = False,
-               out: Optional[np.ndarray] = None):
-        """Dense reciprocity smoothing on the device (rthx_smooth_F).  Source: `counts` (u64 [n,n]) or `F` (f64 [n,n])
+               out: Optional[np.ndarray] = None, k_dykstra: int = 0):
+        """Dense reciprocity smoothing on the device (rthx_smooth_DkAP: `k_dykstra` Dykstra rounds, then AP).  Source: `counts` (u64 [n,n]) or `F` (f64 [n,n])
         from the host, or — with neither — the counts of traced bin `bin` still resident from the last `trace()`.
         `w` must already be renormalised (w / min(w)).  Returns (F_smooth [n,n] f64, stats dict)."""
         w = np.ascontiguousarray(w, dtype=np.float64)
@@ -259,8 +262,9 @@ class DeviceTracer:
         F_out = out if out is not None else np.empty((n, n), np.float64)
         assert F_out.dtype == np.float64 and F_out.size == n * n and F_out.flags["C_CONTIGUOUS"]
         st = rthx_smooth_stats()
-        self._check(self._L.rthx_smooth_F(self._h, source, ptr, int(bin), n, w.ctypes.data_as(c_f64p), int(max_iters),
-                                          float(target), 1 if measure_pass else 0, F_out.ctypes.data_as(c_f64p), C.byref(st)))
+        self._check(self._L.rthx_smooth_DkAP(self._h, source, ptr, int(bin), n, w.ctypes.data_as(c_f64p), int(k_dykstra),
+                                             int(max_iters), float(target), 1 if measure_pass else 0,
+                                             F_out.ctypes.data_as(c_f64p), C.byref(st)))
         return F_out.reshape(n, n), st.as_dict()
 
     def solve_grey(self, coeff, rhs, F=None, col_major: bool = False, memory: int = 50, max_iters: int = 0,

@@ -40,6 +40,7 @@ struct DevRes {
   double* smooth_X = nullptr;               size_t smooth_cap = 0;     // n*n doubles of the smoothing iterate
   double* smooth_vec = nullptr;             size_t smooth_vec_cap = 0; // w, rs, r, u, part (5 n doubles)
   void* smooth_src = nullptr;               size_t smooth_src_cap = 0; // staged host matrix (FROM_COUNTS / FROM_F)
+  double* dyk_buf = nullptr;                size_t dyk_cap = 0;        // Dykstra rounds: Xbar / F iterate (+ second iterate and P for k > 1)
   double* solve_buf = nullptr;              size_t solve_cap = 0;      // Krylov basis + work vectors + matvec partials
   double* solve_mat = nullptr;              size_t solve_mat_cap = 0;  // staged host F of rthx_solve_grey (dense padded / CSC)
   void* stage[2] = {nullptr, nullptr};      size_t stage_cap = 0;      // pinned staging for pageable destinations
@@ -77,7 +78,7 @@ cudaDeviceProp g_prop[64];
 bool g_prop_ok[64] = {};
 
 void devres_free(DevRes& r) {
-  cudaFree(r.smooth_X); cudaFree(r.smooth_vec); cudaFree(r.smooth_src); cudaFree(r.solve_buf); cudaFree(r.solve_mat);
+  cudaFree(r.smooth_X); cudaFree(r.smooth_vec); cudaFree(r.smooth_src); cudaFree(r.solve_buf); cudaFree(r.solve_mat); cudaFree(r.dyk_buf);
   cudaFree(r.csr_nnz); cudaFree(r.csr_rowsum); cudaFree(r.csr_rowptr); cudaFree(r.csr_out);
   cudaFree(r.arena); cudaFree(r.counts_dev); cudaFree(r.rec_pts_dev); cudaFree(r.rec_valid_dev); cudaFree(r.peak_dev);
   for (auto& e : r.ev) if (e) cudaEventDestroy(e);
@@ -1099,16 +1100,25 @@ extern "C" int rthx_counts_csr(rthx_handle* h, int bin, int64_t* row_ptr, int32_
 // ---------------------------------------------------------------------------------------------------------------
 namespace rthx {
 struct SmoothResult { int iters; double delta, delta_init; double ms_total, ms_per_iter; int launches; };
-cudaError_t run_ap(const unsigned long long* src_counts, const double* src_F, size_t ld, const double* w_dev, int n, size_t ldx, int max_iters, double target,
-                   double* X, double* rs, double* r, double* u, double* part, std::vector<double>& part_host, cudaStream_t st, cudaEvent_t e0,
-                   cudaEvent_t e1, SmoothResult* out);
+cudaError_t run_ap(const unsigned long long* src_counts, const double* src_F, const double* src_rs, size_t ld, const double* w_dev, int n, size_t ldx,
+                   int max_iters, double target, double* X, double* rs, double* r, double* u, double* part, std::vector<double>& part_host, cudaStream_t st,
+                   cudaEvent_t e0, cudaEvent_t e1, SmoothResult* out);
+struct DykstraResult { int rounds; int pcg_iters; double delta; double ms; int launches; };
+cudaError_t run_dykstra(const unsigned long long* src_counts, const double* src_F, size_t ld, const double* w_dev, int n, size_t ldx, int k_dykstra,
+                        double* B, double* C, double* P, double* vec, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1, double** F_out, double** rs_out,
+                        DykstraResult* out);
 cudaError_t time_scale_pass(double* X, double* u, double* r, int n, size_t ldx, int reps, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1, double* ms_per_pass);
 }  // namespace rthx
 
 extern "C" int rthx_smooth_F(rthx_handle* h, int source, const void* src_host, int bin, int n, const double* w, int max_iters, double target,
                              int measure_pass, double* F_out, rthx_smooth_stats* st) {
+  return rthx_smooth_DkAP(h, source, src_host, bin, n, w, 0, max_iters, target, measure_pass, F_out, st);
+}
+
+extern "C" int rthx_smooth_DkAP(rthx_handle* h, int source, const void* src_host, int bin, int n, const double* w, int k_dykstra, int max_iters,
+                                double target, int measure_pass, double* F_out, rthx_smooth_stats* st) {
   if (!h) return RTHX_ERR_ARG;
-  if (n < 1 || !w || !F_out || max_iters < 0) return fail(h, RTHX_ERR_ARG, "smooth: bad argument");
+  if (n < 1 || !w || !F_out || max_iters < 0 || k_dykstra < 0) return fail(h, RTHX_ERR_ARG, "smooth: bad argument");
   CU(h, cudaSetDevice(h->device));
   const size_t nn = (size_t)n * n;
   const unsigned long long* src_counts = nullptr;
@@ -1133,13 +1143,26 @@ extern "C" int rthx_smooth_F(rthx_handle* h, int source, const void* src_host, i
   const size_t ldx = ((size_t)n + 15) & ~size_t(15);      // rows padded to 128 bytes
   h->smooth_n = 0;
   CU(h, ensure(&h->smooth_X, &h->smooth_cap, (size_t)n * ldx));
-  CU(h, ensure(&h->smooth_vec, &h->smooth_vec_cap, (size_t)5 * ldx));
+  CU(h, ensure(&h->smooth_vec, &h->smooth_vec_cap, (size_t)16 * ldx + 8));   // AP: w, rs, r, u, part; Dykstra: 10 vectors + 8 scalars
   double *w_dev = h->smooth_vec, *rs = w_dev + ldx, *r = rs + ldx, *u = r + ldx, *part = u + ldx;
   CU(h, cudaMemcpyAsync(w_dev, w, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
   std::vector<double> part_host(n);
   rthx::SmoothResult res{};
+  rthx::DykstraResult dres{};
   const double tgt = target > 0 ? target : 8 * 2.220446049250313e-16;
-  CU(h, rthx::run_ap(src_counts, src_F, ld, w_dev, n, ldx, max_iters, tgt, h->smooth_X, rs, r, u, part, part_host, h->stream, h->ev[0], h->ev[1], &res));
+  const double* src_rs = nullptr;
+  if (k_dykstra > 0) {
+    // Dykstra rounds (DkAP, smoothExchangeFactors.jl:299-318) write into their own buffers; AP then builds X from the result
+    const size_t mats = k_dykstra > 1 ? 3 : 1;
+    CU(h, ensure(&h->dyk_buf, &h->dyk_cap, mats * (size_t)n * ldx));
+    double* B = h->dyk_buf;
+    double* Cb = mats > 1 ? B + (size_t)n * ldx : nullptr;
+    double* Pb = mats > 1 ? Cb + (size_t)n * ldx : nullptr;
+    double *Fd = nullptr, *rsd = nullptr;
+    CU(h, rthx::run_dykstra(src_counts, src_F, ld, w_dev, n, ldx, k_dykstra, B, Cb, Pb, h->smooth_vec + 5 * ldx, h->stream, h->ev[2], h->ev[3], &Fd, &rsd, &dres));
+    src_counts = nullptr; src_F = Fd; src_rs = rsd; ld = ldx;
+  }
+  CU(h, rthx::run_ap(src_counts, src_F, src_rs, ld, w_dev, n, ldx, max_iters, tgt, h->smooth_X, rs, r, u, part, part_host, h->stream, h->ev[0], h->ev[1], &res));
   CU(h, cudaMemcpy2DAsync(F_out, sizeof(double) * (size_t)n, h->smooth_X, sizeof(double) * ldx, sizeof(double) * (size_t)n, (size_t)n,
                           cudaMemcpyDeviceToHost, h->stream));
   CU(h, cudaStreamSynchronize(h->stream));
@@ -1154,6 +1177,8 @@ extern "C" int rthx_smooth_F(rthx_handle* h, int source, const void* src_host, i
     st->iterations = res.iters; st->launches = res.launches; st->delta_init = res.delta_init; st->delta = res.delta;
     st->total_ms = res.ms_total; st->ms_per_iteration = res.ms_per_iter; st->pass_ms = pass_ms;
     st->pass_gbs = pass_ms > 0 ? 16.0 * (double)nn / (pass_ms * 1e-3) / 1e9 : 0.0;
+    st->dykstra_rounds = dres.rounds; st->pcg_iterations = dres.pcg_iters; st->dykstra_delta = dres.rounds ? dres.delta : 0.0; st->dykstra_ms = dres.ms;
+    st->launches += dres.launches;
   }
   return RTHX_OK;
 }

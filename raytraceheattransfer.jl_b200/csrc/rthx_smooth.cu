@@ -9,6 +9,10 @@
 //   delta_R_X  :100-118   sqrt(sum_{i<j} (X_ij (u_i-u_j))^2/(w_i^2+w_j^2)) -> delta_kernel (read-only pass, on check iterations)
 //   recover_F  :546       F = X ./ r                                    -> recover_kernel
 //   AP loop    :548-612   target 8 eps, floor acceptance when the contraction stalls
+//   OP / DkAP  :292-318   Dykstra rounds in front of AP (the reference's default for a dense F with cross-coupling
+//                         chi >= 0.4, :441-450): orthogonal projection onto {reciprocal, unit row sums} through the dual
+//                         system R lambda = b (DualSolver :1-37, Jacobi-PCG, rtol 1e-14), then max(., 0) with the
+//                         Dykstra correction P                         -> op_xbar / y_matvec / pcg_* / op_finalize kernels
 // Every pass is HBM-bound: 16 B per matrix element per iteration (read + write of X), 8 B for a delta check.
 #include <algorithm>
 #include <cmath>
@@ -31,8 +35,11 @@ __global__ void __launch_bounds__(256) count_rowsum_kernel(const unsigned long l
 }
 
 // X_ij = (w_i F_ij + w_j F_ji)/2 with F = counts / rowsum (rows with no tallies stay zero), 32x32 tiles through smem
-// so both the (I,J) and the transposed (J,I) reads are coalesced.  F may also be given directly as doubles.
-template <class T>
+// so both the (I,J) and the transposed (J,I) reads are coalesced.  F may also be given directly as doubles (rs == nullptr,
+// or rs = its row sums when it still has to be row-normalised).
+// XBAR: the OP form instead (Xbar_b :261-281): Xbar_ij = Y_ij (F_ij / w_i + F_ji / w_j), Y_ij = w_i^2 w_j^2 / (w_i^2 + w_j^2)
+// = 1 / (a_i + a_j) with a = 1 / w^2 (reduced-mass weights, Y_mat :243-259).
+template <class T, bool XBAR>
 __global__ void __launch_bounds__(256) build_x_kernel(const T* __restrict__ src, size_t ld, const double* __restrict__ rs,
                                                       const double* __restrict__ w, int n, size_t ldx, double* __restrict__ X) {
   __shared__ double t[32][33];
@@ -44,7 +51,8 @@ __global__ void __launch_bounds__(256) build_x_kernel(const T* __restrict__ src,
     double v = 0.0;
     if (i < n && j < n) {
       const double d = rs ? rs[i] : 1.0;
-      v = d > 0.0 ? w[i] * ((double)src[(size_t)i * ld + j] / d) : 0.0;
+      const double f = d > 0.0 ? (double)src[(size_t)i * ld + j] / d : 0.0;
+      v = XBAR ? f / w[i] : w[i] * f;
     }
     t[r][tx] = v;
   }
@@ -53,8 +61,14 @@ __global__ void __launch_bounds__(256) build_x_kernel(const T* __restrict__ src,
     const int i = bi + r, j = bj + tx;
     if (i < n && j < n) {
       const double d = rs ? rs[i] : 1.0;
-      const double a = d > 0.0 ? w[i] * ((double)src[(size_t)i * ld + j] / d) : 0.0;
-      X[(size_t)i * ldx + j] = 0.5 * (a + t[tx][r]);
+      const double f = d > 0.0 ? (double)src[(size_t)i * ld + j] / d : 0.0;
+      if (XBAR) {
+        const double wi = w[i], wj = w[j];
+        const double y = 1.0 / (1.0 / (wi * wi) + 1.0 / (wj * wj));
+        X[(size_t)i * ldx + j] = y * (f / wi + t[tx][r]);
+      } else {
+        X[(size_t)i * ldx + j] = 0.5 * (w[i] * f + t[tx][r]);
+      }
     } else if (i < n && (size_t)j < ldx) {
       X[(size_t)i * ldx + j] = 0.0;                        // row padding (columns n..ldx-1) stays zero for ever
     }
@@ -184,9 +198,10 @@ cudaError_t launch_row_fill(const unsigned long long* c, int n, size_t ld, const
 
 struct SmoothResult { int iters; double delta, delta_init; double ms_total, ms_per_iter; int launches; };
 
-// Runs AP on the device.  `src_counts` (u64, leading dimension ld) or `src_F` (doubles) is a DEVICE pointer; X (n*n
-// doubles) and the work vectors are device scratch owned by the caller.  On return X holds F_smooth.
-cudaError_t run_ap(const unsigned long long* src_counts, const double* src_F, size_t ld, const double* w_dev, int n, size_t ldx, int max_iters, double target,
+// Runs AP on the device.  `src_counts` (u64, leading dimension ld) or `src_F` (doubles; `src_rs` = its row sums when it
+// still has to be row-normalised, else nullptr) is a DEVICE pointer; X (n*ldx doubles) and the work vectors are device
+// scratch owned by the caller.  On return X holds F_smooth.
+cudaError_t run_ap(const unsigned long long* src_counts, const double* src_F, const double* src_rs, size_t ld, const double* w_dev, int n, size_t ldx, int max_iters, double target,
                    double* X, double* rs, double* r, double* u, double* part, std::vector<double>& part_host, cudaStream_t st, cudaEvent_t e0,
                    cudaEvent_t e1, SmoothResult* out) {
   cudaError_t e;
@@ -195,10 +210,10 @@ cudaError_t run_ap(const unsigned long long* src_counts, const double* src_F, si
   if ((e = cudaEventRecord(e0, st)) != cudaSuccess) return e;
   if (src_counts) {
     count_rowsum_kernel<<<(n + 7) / 8, 256, 0, st>>>(src_counts, n, ld, rs);
-    build_x_kernel<unsigned long long><<<tg, 256, 0, st>>>(src_counts, ld, rs, w_dev, n, ldx, X);
+    build_x_kernel<unsigned long long, false><<<tg, 256, 0, st>>>(src_counts, ld, rs, w_dev, n, ldx, X);
     launches += 2;
   } else {
-    build_x_kernel<double><<<tg, 256, 0, st>>>(src_F, ld, nullptr, w_dev, n, ldx, X);
+    build_x_kernel<double, false><<<tg, 256, 0, st>>>(src_F, ld, src_rs, w_dev, n, ldx, X);
     launches += 1;
   }
   rowsum_kernel<<<n, ROW_THREADS, 0, st>>>(X, ldx, r);
@@ -241,6 +256,213 @@ cudaError_t run_ap(const unsigned long long* src_counts, const double* src_F, si
   cudaEventElapsedTime(&ms, e0, e1);
   out->iters = k; out->delta = delta; out->delta_init = delta_init; out->ms_total = ms;
   out->ms_per_iter = k > 0 ? ms / k : 0.0; out->launches = launches;
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Dykstra rounds (OP) in front of AP — smoothExchangeFactors.jl:1-37 (DualSolver, solve_R), :261-318 (Xbar_b, OP, DkAP)
+// ---------------------------------------------------------------------------------------------------------------
+// a = 1 / w^2 on [0,n)
+__global__ void inv_sq_kernel(const double* __restrict__ w, int n, double* __restrict__ a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] = 1.0 / (w[i] * w[i]);
+}
+
+// out_i = sum_j Y_ij v_j (+ rowsumY_i v_i when rowsumY != nullptr: R = Y + Diagonal(Y 1), Rmul! :13), Y_ij = 1/(a_i + a_j)
+// formed on the fly — no N^2 matrix is stored or streamed.  v == nullptr means v = 1 (the row sums of Y).
+__global__ void __launch_bounds__(256) y_matvec_kernel(const double* __restrict__ a, const double* __restrict__ v, const double* __restrict__ rowsumY,
+                                                       int n, double* __restrict__ out) {
+  __shared__ double red[32];
+  const int i = blockIdx.x;
+  const double ai = a[i];
+  double s = 0.0;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) s += (v ? v[j] : 1.0) / (ai + a[j]);
+  const double t = block_sum(s, red);
+  if (threadIdx.x == 0) out[i] = rowsumY ? fma(rowsumY[i], v[i], t) : t;
+}
+
+// 1024-thread single-block reductions for the PCG scalars (fixed order: bit-reproducible)
+__device__ __forceinline__ double block_allsum_1024(double s, double* red) {
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+  __syncthreads();                                     // red may still be read from the previous reduction
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  double a = 0.0;
+  for (int k = 0; k < 32; ++k) a += red[k];
+  return a;
+}
+
+// dinv = 1 / (Y_ii + rowsumY_i), Y_ii = w_i^2 / 2 = 1 / (2 a_i)   (DualSolver :7-11)
+__global__ void dinv_kernel(const double* __restrict__ a, const double* __restrict__ rowsumY, int n, double* __restrict__ dinv) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dinv[i] = 1.0 / (0.5 / a[i] + rowsumY[i]);
+}
+
+// b = rowsum - w (OP right-hand side, Xbar_b) or b = w .* (rowsum - 1) (delta_perp :DYK, :139)
+__global__ void op_rhs_kernel(const double* __restrict__ rowsum, const double* __restrict__ w, int n, int dyk, double* __restrict__ b) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) b[i] = dyk ? w[i] * (rowsum[i] - 1.0) : rowsum[i] - w[i];
+}
+
+// solve_R :15-37 — x = 0, r = b, z = dinv r, p = z; sc[0] = r.z, sc[1] = |r|^2, sc[3] = |b|^2
+__global__ void __launch_bounds__(1024) pcg_init_kernel(int n, const double* __restrict__ b, const double* __restrict__ dinv, double* __restrict__ x,
+                                                        double* __restrict__ r, double* __restrict__ z, double* __restrict__ p, double* __restrict__ sc) {
+  __shared__ double red[32];
+  double rz = 0.0, bb = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double bi = b[i], zi = dinv[i] * bi;
+    x[i] = 0.0; r[i] = bi; z[i] = zi; p[i] = zi;
+    rz = fma(bi, zi, rz); bb = fma(bi, bi, bb);
+  }
+  rz = block_allsum_1024(rz, red);
+  bb = block_allsum_1024(bb, red);
+  if (threadIdx.x == 0) { sc[0] = rz; sc[1] = bb; sc[3] = bb; }
+}
+
+// one PCG iteration after Ap = R p: alpha = rz / p.Ap; x += alpha p; r -= alpha Ap; z = dinv r; beta = r.z / rz; p = z + beta p
+__global__ void __launch_bounds__(1024) pcg_step_kernel(int n, const double* __restrict__ dinv, const double* __restrict__ Ap, double* __restrict__ x,
+                                                        double* __restrict__ r, double* __restrict__ z, double* __restrict__ p, double* __restrict__ sc) {
+  __shared__ double red[32];
+  double pap = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) pap = fma(p[i], Ap[i], pap);
+  pap = block_allsum_1024(pap, red);
+  const double rz = sc[0];
+  const double alpha = rz / pap;
+  double rn = 0.0, rzn = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    x[i] = fma(alpha, p[i], x[i]);
+    const double ri = fma(-alpha, Ap[i], r[i]);
+    const double zi = dinv[i] * ri;
+    r[i] = ri; z[i] = zi;
+    rn = fma(ri, ri, rn); rzn = fma(ri, zi, rzn);
+  }
+  rn = block_allsum_1024(rn, red);
+  rzn = block_allsum_1024(rzn, red);
+  const double beta = rzn / rz;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) p[i] = fma(beta, p[i], z[i]);
+  __syncthreads();
+  if (threadIdx.x == 0) { sc[0] = rzn; sc[1] = rn; }
+}
+
+// sc[2] = u . v (single block)
+__global__ void __launch_bounds__(1024) dot_kernel(int n, const double* __restrict__ u, const double* __restrict__ v, double* __restrict__ sc) {
+  __shared__ double red[32];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s = fma(u[i], v[i], s);
+  s = block_allsum_1024(s, red);
+  if (threadIdx.x == 0) sc[2] = s;
+}
+
+// OP :292-297 + the Dykstra update of DkAP :306-313, in place on the Xbar buffer, one block per row:
+//   G = (Xbar - Y .* (lambda_i + lambda_j)) / w_i;  F = max(G + P, 0);  P = G + P - F;  rs_i = sum_j F_ij
+__global__ void __launch_bounds__(ROW_THREADS) op_finalize_kernel(double* __restrict__ Xb, double* __restrict__ P, const double* __restrict__ w,
+                                                                  const double* __restrict__ a, const double* __restrict__ lam, int n, size_t ldx,
+                                                                  double* __restrict__ rs) {
+  __shared__ double red[32];
+  const size_t row = blockIdx.x;
+  const double ai = a[row], li = lam[row], inv_wi = 1.0 / w[row];
+  double s = 0.0;
+  for (int j = threadIdx.x; j < n; j += ROW_THREADS) {
+    const double y = 1.0 / (ai + a[j]);
+    const double g = (Xb[row * ldx + j] - y * (li + lam[j])) * inv_wi;
+    const double t = P ? g + P[row * ldx + j] : g;
+    const double f = fmax(t, 0.0);
+    if (P) P[row * ldx + j] = t - f;
+    Xb[row * ldx + j] = f;
+    s += f;
+  }
+  const double tot = block_sum(s, red);
+  if (threadIdx.x == 0) rs[row] = tot;
+}
+
+struct DykstraResult { int rounds; int pcg_iters; double delta; double ms; int launches; };
+
+// Jacobi-PCG on R lambda = b (solve_R :15-37: rtol 1e-14, maxiter 200).  vec: a, rowsumY, dinv, b, x, r, z, p, Ap
+static cudaError_t pcg_solve(int n, const double* a, const double* rowsumY, const double* dinv, const double* b, double* x, double* r, double* z,
+                             double* p, double* Ap, double* sc, cudaStream_t st, int* iters, int* launches) {
+  cudaError_t e;
+  pcg_init_kernel<<<1, 1024, 0, st>>>(n, b, dinv, x, r, z, p, sc);
+  ++*launches;
+  double h[4];
+  if ((e = cudaMemcpyAsync(h, sc, sizeof(h), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
+  if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
+  const double bn = std::sqrt(h[3]);
+  *iters = 0;
+  if (bn == 0.0) return cudaSuccess;
+  for (int it = 1; it <= 200; ++it) {
+    y_matvec_kernel<<<n, 256, 0, st>>>(a, p, rowsumY, n, Ap);
+    pcg_step_kernel<<<1, 1024, 0, st>>>(n, dinv, Ap, x, r, z, p, sc);
+    *launches += 2;
+    *iters = it;
+    if ((e = cudaMemcpyAsync(h, sc, sizeof(double) * 2, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
+    if (std::sqrt(h[1]) <= 1e-14 * bn) break;
+  }
+  return cudaGetLastError();
+}
+
+// k_dykstra rounds of OP + clipping.  Source as in run_ap.  B (and C, P when k_dykstra > 1) are n*ldx device buffers;
+// vec holds 10 vectors of ldx doubles + 8 scalars.  On return *F_out (B or C) holds the clipped iterate and rs_out its row
+// sums; the caller hands both to run_ap, which renormalises the rows (DkAP :316) and polishes with AP (:317).
+cudaError_t run_dykstra(const unsigned long long* src_counts, const double* src_F, size_t ld, const double* w_dev, int n, size_t ldx, int k_dykstra,
+                        double* B, double* C, double* P, double* vec, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1, double** F_out, double** rs_out,
+                        DykstraResult* out) {
+  cudaError_t e;
+  double *a = vec, *rowsumY = a + ldx, *dinv = rowsumY + ldx, *b = dinv + ldx, *lam = b + ldx, *r = lam + ldx, *z = r + ldx, *p = z + ldx,
+         *Ap = p + ldx, *rs = Ap + ldx, *sc = rs + ldx;
+  int launches = 0, pcg_total = 0;
+  const int vb = (n + 255) / 256;
+  const dim3 tg((unsigned)((ldx + 31) / 32), (n + 31) / 32);
+  if ((e = cudaEventRecord(e0, st)) != cudaSuccess) return e;
+  inv_sq_kernel<<<vb, 256, 0, st>>>(w_dev, n, a);
+  y_matvec_kernel<<<n, 256, 0, st>>>(a, nullptr, nullptr, n, rowsumY);
+  dinv_kernel<<<vb, 256, 0, st>>>(a, rowsumY, n, dinv);
+  launches += 3;
+  if (P && (e = cudaMemsetAsync(P, 0, sizeof(double) * (size_t)n * ldx, st)) != cudaSuccess) return e;
+  double delta = INFINITY;
+  double* cur = nullptr;
+  int k = 1;
+  for (; k <= k_dykstra; ++k) {
+    double* dst = (k & 1) ? B : C;
+    if (k == 1 && src_counts) {
+      count_rowsum_kernel<<<(n + 7) / 8, 256, 0, st>>>(src_counts, n, ld, rs);
+      build_x_kernel<unsigned long long, true><<<tg, 256, 0, st>>>(src_counts, ld, rs, w_dev, n, ldx, dst);
+      launches += 2;
+    } else if (k == 1) {
+      build_x_kernel<double, true><<<tg, 256, 0, st>>>(src_F, ld, nullptr, w_dev, n, ldx, dst);
+      ++launches;
+    } else {
+      build_x_kernel<double, true><<<tg, 256, 0, st>>>(cur, ldx, nullptr, w_dev, n, ldx, dst);
+      ++launches;
+    }
+    rowsum_kernel<<<n, ROW_THREADS, 0, st>>>(dst, ldx, rs);
+    op_rhs_kernel<<<vb, 256, 0, st>>>(rs, w_dev, n, 0, b);
+    launches += 2;
+    int it = 0;
+    if ((e = pcg_solve(n, a, rowsumY, dinv, b, lam, r, z, p, Ap, sc, st, &it, &launches)) != cudaSuccess) return e;
+    pcg_total += it;
+    op_finalize_kernel<<<n, ROW_THREADS, 0, st>>>(dst, k_dykstra > 1 ? P : nullptr, w_dev, a, lam, n, ldx, rs);
+    ++launches;
+    cur = dst;
+    if (k % 5 == 0 || k == k_dykstra) {                        // delta_perp(:DYK) :136-142
+      op_rhs_kernel<<<vb, 256, 0, st>>>(rs, w_dev, n, 1, b);
+      ++launches;
+      if ((e = pcg_solve(n, a, rowsumY, dinv, b, lam, r, z, p, Ap, sc, st, &it, &launches)) != cudaSuccess) return e;
+      dot_kernel<<<1, 1024, 0, st>>>(n, b, lam, sc);
+      ++launches;
+      double d2 = 0;
+      if ((e = cudaMemcpyAsync(&d2, sc + 2, sizeof(double), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
+      if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
+      delta = std::sqrt(std::max(d2, 0.0));
+    }
+    if (delta < 8 * 2.220446049250313e-16) { ++k; break; }
+  }
+  if ((e = cudaEventRecord(e1, st)) != cudaSuccess) return e;
+  if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  *F_out = cur; *rs_out = rs;
+  out->rounds = k - 1; out->pcg_iters = pcg_total; out->delta = delta; out->ms = ms; out->launches = launches;
   return cudaGetLastError();
 }
 

@@ -168,7 +168,7 @@ def get_b(rtm) -> np.ndarray:
     return b
 
 
-def _smooth_on_device(rtm, F_raw, w, ns: int, max_iters: int, verbose: bool):
+def _smooth_on_device(rtm, F_raw, w, ns: int, max_iters: int, verbose: bool, k_dykstra=None):
     """Dense branch of smooth_F (density > 0.25, smoothExchangeFactors.jl:432-434) on the GPU, straight from the counts
     that the trace left on the device; returns None when the sparse host path applies (sparsity must be preserved)."""
     tr = getattr(rtm, "_device", None)
@@ -176,8 +176,11 @@ def _smooth_on_device(rtm, F_raw, w, ns: int, max_iters: int, verbose: bool):
     if tr is None or max_iters <= 0 or F_raw.nnz / float(n * n) <= 0.25:
         return None
     wn = w[:n] / np.min(w[:n])
-    verbose and print(f"Matrix size: {n}x{n}; dense alternating projection on the device")
-    F_smooth, st = tr.smooth(wn, n=n, max_iters=max_iters)
+    if k_dykstra is None:       # smooth_F :441-450: one Dykstra round when surfaces and gas are strongly coupled, else AP only
+        from .smoothing import default_k_dykstra
+        k_dykstra = default_k_dykstra(F_raw, ns, smooth_surfaces_only=rtm.surfaces_only)
+    verbose and print(f"Matrix size: {n}x{n}; dense smoothing on the device ({k_dykstra} Dykstra rounds + AP)")
+    F_smooth, st = tr.smooth(wn, n=n, max_iters=max_iters, k_dykstra=int(k_dykstra))
     rtm.last_smooth_stats = st
     # the smoothed matrix also stays on the device: solveEquilibrium reads it there when handed this very array
     from .equilibrium import _sample_of
@@ -214,7 +217,7 @@ def exchangeRayTracing(rtm, rays_tot: int, nudge: float, max_iters: int, k_dykst
             for j in g:
                 F_smooth[j - 1] = Fs
     else:
-        F_smooth = _smooth_on_device(rtm, F_raw, get_w(rtm), ns, max_iters, verbose)
+        F_smooth = _smooth_on_device(rtm, F_raw, get_w(rtm), ns, max_iters, verbose, k_dykstra=k_dykstra)
         if F_smooth is None:
             F_smooth = smooth_F(F_raw, get_w(rtm), ns, max_iters=max_iters, k_dykstra=k_dykstra, verbose=verbose,
                                 smooth_surfaces_only=rtm.surfaces_only)

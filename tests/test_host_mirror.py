@@ -172,3 +172,35 @@ def test_solve_equilibrium_dispatch(rthx_mod):
     rtm.spectral_mode = "grey"
     with pytest.raises(ValueError, match="expected"):
         rthx_mod.solveEquilibrium(rtm, np.eye(3), verbose=False)
+
+
+def test_dykstra_restatement_properties(rthx_mod):
+    """numpy DkAP (smoothExchangeFactors.jl:292-318): one OP round is the exact projection onto {reciprocal, unit row
+    sums}; the full DkAP result is in addition non-negative and no farther from F_raw (Frobenius norm) than AP alone."""
+    from rthx import smoothing as sm
+    rng = np.random.default_rng(0)
+    n, ns = 60, 12
+    w = np.concatenate([np.full(ns, 0.1), np.full(n - ns, 0.04)])
+    w = w / w.min()
+    S = rng.random((n, n)); S = S + S.T
+    F = S / w[:, None]; F /= F.sum(axis=1, keepdims=True)
+    Fn = np.abs(F * (1 + 0.05 * rng.standard_normal((n, n)))); Fn /= Fn.sum(axis=1, keepdims=True)
+    w2 = w * w
+    Y = (w2[:, None] * w2[None, :]) / (w2[:, None] + w2[None, :])
+    rs = Y.sum(axis=1)
+    Z = Fn / w[:, None]; Xbar = Y * (Z + Z.T)
+    lam, it = sm._solve_R(Y, rs, 1 / (np.diag(Y) + rs), Xbar.sum(axis=1) - w)
+    G = (Xbar - Y * (lam[:, None] + lam[None, :])) / w[:, None]
+    assert it < 50 and np.abs(w[:, None] * G - (w[:, None] * G).T).max() < 1e-14 and np.abs(G.sum(axis=1) - 1).max() < 1e-13
+    for k in (1, 4):
+        Fd = sm.DkAP(Fn, w, ns, k_dykstra=k)
+        WF = w[:, None] * Fd
+        assert np.abs(WF - WF.T).max() < 1e-13 and np.abs(Fd.sum(axis=1) - 1).max() < 1e-13 and Fd.min() >= 0
+    Fa = sm.AP(Fn, w, ns)
+    wd = lambda A: np.linalg.norm(A - Fn)          # OP is orthogonal in the Frobenius norm of F
+    assert wd(sm.DkAP(Fn, w, ns, k_dykstra=1)) <= wd(Fa)
+    # the default rule of smooth_F :441-450
+    assert sm.default_k_dykstra(Fn, ns) == (1 if sm.cross_coupling_chi(Fn, ns) >= 0.4 else 0)
+    assert sm.default_k_dykstra(sp.csc_matrix(np.eye(n)), ns) == 0 and sm.default_k_dykstra(Fn, ns, smooth_surfaces_only=True) == 0
+    strong = np.zeros((n, n)); strong[:ns, ns:] = 1.0 / (n - ns); strong[ns:, :ns] = 1.0 / ns
+    assert sm.cross_coupling_chi(strong, ns) == pytest.approx(1.0) and sm.default_k_dykstra(strong, ns) == 1
