@@ -547,7 +547,8 @@ LaunchPlan make_plan(const rthx_handle* h, const rthx_trace_args* a, int rank, i
   if (const char* ev = std::getenv("RTHX_NO_SQ")) { if (std::atoi(ev)) pl.sq = 0; }   // test / tuning knob
   if (pl.sq) {
     pl.fast = 1; pl.minb = 4;
-    if (const char* ev = std::getenv("RTHX_MINB")) { if (std::atoi(ev) == 5) pl.minb = 5; }   // tuning knob: 48 registers, 5 blocks / SM
+    // tuning knobs: 5 = 48 registers, 5 blocks / SM; 3 = the shared-loop SQ branch of the general kernel (A/B reference)
+    if (const char* ev = std::getenv("RTHX_MINB")) { const int v = std::atoi(ev); if (v == 5 || v == 3) pl.minb = v; }
   }
   pl.smem_bytes = coarse_bytes + em_bytes + (pl.hist_in_smem ? hist_bytes : 0);
   const long long rows = (long long)pl.n_owned * a->n_bins;

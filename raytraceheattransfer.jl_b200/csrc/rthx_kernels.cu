@@ -364,7 +364,8 @@ __global__ void __launch_bounds__(256, MINB) trace_exchange_kernel(const __grid_
   }
   if (HIST_SMEM)
     for (int i = threadIdx.x; i < N; i += blockDim.x) hist[i] = 0u;
-  if (FAST && threadIdx.x < 64) s_log[threadIdx.x] = c_logtab[threadIdx.x];
+  if (FAST)
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) s_log[i] = c_logtab[i];
   // FAST: a plain shared-memory pointer (LDS); otherwise a generic pointer that may be shared or global
   const CoarseDev* coarse = FAST ? s_coarse : (p.coarse_in_smem ? s_coarse : p.coarse);
 
@@ -627,11 +628,216 @@ __global__ void __launch_bounds__(256, MINB) trace_exchange_kernel(const __grid_
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// K1-SQ: the fused kernel for domains that are ONE parallelogram coarse face (every square / rectangular enclosure:
+// cfg1-4).  Same arithmetic as the SQ branch of trace_exchange_kernel; what differs is the code shape:
+//   * the three block-uniform decisions — surface or volume emitter, uniform or cell-wise beta, recorder on or off —
+//     are taken ONCE, outside the ray loop, into eight specialised loop bodies.  Each loop keeps only its own
+//     constants live, so the uniform-register file no longer overflows (the single shared loop spent ~40 of 327 warp
+//     instructions per 32 rays on LDCU / R2UR / MOV.SPILL / UMOV / S2UR constant shuffling) and carries no dead branches;
+//   * 32-bit loop counter relative to the block's first ray;
+//   * the lattice inverse and the emission nudge use pre-folded constants (s = p.g1 + c1 instead of (p - a).g1; p(1-nudge) +
+//     mid nudge instead of p + (mid - p) nudge): 4 FP64 instructions fewer, results equal to 1 ulp of the coordinates.
+// ------------------------------------------------------------------------------------------------------------
+struct SqBlock {            // block-uniform state of one (emitter row, band, chunk)
+  const double* s_em;       // emitter description (shared memory, EM_DOUBLES)
+  const double2* s_log;     // -log table (shared memory)
+  uint32_t* hist;           // row histogram (shared memory)
+  const double* beta_band;  // per-cell beta of the band (non-uniform bins)
+  double inv_beta_u;
+  double c1, c2;            // folded lattice-inverse offsets: s = px g1x + py g1y + c1, t = px g2x + py g2y + c2
+  double one_m_nudge, midx_n, midy_n;
+  uint32_t e, cw;
+  int64_t ray0;             // ray id of the block's first ray
+  uint32_t n_rays;          // rays of this block
+  size_t rec_base;          // recorder slot of the block's first ray
+};
+
+__device__ __forceinline__ int locate_sq(const CoarseDev& cf, double c1, double c2, double px, double py) {
+  const double s = fma(px, cf.g1x, fma(py, cf.g1y, c1)), t = fma(px, cf.g2x, fma(py, cf.g2y, c2));
+  const int n = __double2int_rd(s), m = __double2int_rd(t);
+  if (!((s >= 0.0) & (t >= 0.0) & (n < cf.Nx) & (m < cf.Ny))) return -1;
+  return n + m * cf.Nx;
+}
+
+template <bool SURF, bool UNIFORM, bool REC>
+__device__ __forceinline__ unsigned int sq_ray_loop(const TraceParams& p, const SqBlock& b) {
+  const CoarseDev& cf = p.face0;
+  unsigned int n_lost = 0;
+  for (uint32_t i = threadIdx.x; i < b.n_rays; i += blockDim.x) {
+    const uint64_t ray_id = (uint64_t)(b.ray0 + (int64_t)i);
+    const uint32_t c_lo = (uint32_t)ray_id, c_hi = (uint32_t)(ray_id >> 32);
+    const uint4 w0 = philox4x32_10_rk(make_uint4(c_lo, c_hi, b.e, b.cw | 0u), p.rk);
+    const uint4 w1 = philox4x32_10_rk(make_uint4(c_lo, c_hi, b.e, b.cw | 1u), p.rk);
+    double px, py, dx, dy, R_S;
+    if (SURF) {
+      const double R = u32d(w0.x, p.k_u32);
+      px = fma(b.s_em[2], R, b.s_em[0]);
+      py = fma(b.s_em[3], R, b.s_em[1]);
+      const float cosT = __fsqrt_rn(u23(w0.y));
+      const float cos2 = __fmul_rn(cosT, cosT);
+      const double sinT = sqrt_pos(1.0 - (double)cos2);
+      const double xdir = sinT * cos2pi_unit((double)u23(w0.z));
+      const double zdir = (double)cosT;
+      dx = b.s_em[4] * xdir + b.s_em[6] * zdir;
+      dy = b.s_em[5] * xdir + b.s_em[7] * zdir;
+      R_S = u52(w1.x, w1.y, p.k_u52);
+    } else {
+      const double R1 = u32d(w0.x, p.k_u32), R2 = u32d(w0.y, p.k_u32);
+      const double sq = sqrt_pos(R1);
+      const double* tri = b.s_em + ((u32d(w0.z, p.k_u32) < b.s_em[14]) ? 0 : 6);
+      const double a2 = sq * R2, a1 = sq - a2;
+      px = fma(a2, tri[4], fma(a1, tri[2], tri[0]));
+      py = fma(a2, tri[5], fma(a1, tri[3], tri[1]));
+      const double Rt = u52(w1.x, w1.y, p.k_u52);
+      const double sinT = 2.0 * sqrt_pos(Rt * (1.0 - Rt));
+      dx = sinT * cos2pi_unit(u32d(w0.w, p.k_u32));
+      dy = fma(Rt, -2.0, 1.0);
+      R_S = u52(w1.z, w1.w, p.k_u52);
+    }
+    px = fma(px, b.one_m_nudge, b.midx_n);      // p + (mid - p) nudge  (emitSurfaceRay2D.jl:10, emitVolumeRay2D.jl:22)
+    py = fma(py, b.one_m_nudge, b.midy_n);
+    if (REC) {
+      double* o = p.rec_pts + 4 * (b.rec_base + i);
+      o[0] = px; o[1] = py;
+    }
+    const double neg_log = neg_log_table(R_S, b.s_log);
+    int k;
+    const double u = dist_quad(cf, px, py, dx, dy, p.k_eps, k);
+    double S;
+    bool gas, ok = true;
+    if (UNIFORM) {
+      S = neg_log * b.inv_beta_u;
+      gas = S < u;
+    } else {
+      const int f0 = locate_sq(cf, b.c1, b.c2, px, py);        // traceRay.jl:87-100
+      ok = f0 >= 0;
+      const double local_beta = ok ? b.beta_band[f0] : 0.0;
+      gas = local_beta * u >= neg_log;
+      S = neg_log / local_beta;
+    }
+    int absorber = -1;
+    const bool hit = !gas & (u < CUDART_INF) & (cf.solid[k] != 0);   // an open edge has no neighbour face: the ray is lost
+    if (ok & (gas | hit)) {
+      const double adv = (gas ? S : u) - p.nudge;
+      px = fma(adv, dx, px);
+      py = fma(adv, dy, py);
+      const int f = locate_sq(cf, b.c1, b.c2, px, py);
+      if (f >= 0) absorber = gas ? p.n_surfaces + f : __ldg(p.cell_surf_id + 4 * f + k);
+    }
+    if (absorber >= 0) {
+      atomicAdd(&b.hist[absorber], 1u);
+      if (REC) {
+        const size_t sl = b.rec_base + i;
+        double* o = p.rec_pts + 4 * sl;
+        o[2] = px; o[3] = py;
+        p.rec_valid[sl] = 1;
+      }
+    } else {
+      ++n_lost;
+    }
+  }
+  return n_lost;
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) trace_exchange_sq_kernel(const __grid_constant__ TraceParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* s_em = reinterpret_cast<double*>(smem_raw);
+  double2* s_log = reinterpret_cast<double2*>(smem_raw + sizeof(double) * EM_DOUBLES);
+  uint32_t* hist = reinterpret_cast<uint32_t*>(smem_raw + sizeof(double) * EM_DOUBLES + sizeof(double2) * 64);
+
+  const unsigned bid = blockIdx.x;
+  const int chunk = (int)(bid % (unsigned)p.row_chunks);
+  const unsigned t1 = bid / (unsigned)p.row_chunks;
+  const int bi = (int)(t1 % (unsigned)p.n_bins);
+  const int y = p.y_offset + (int)(t1 / (unsigned)p.n_bins);
+  const int e = p.emitter_rank + y * p.emitter_world;
+  const int band = p.bins[bi];
+  const int N = p.N;
+
+  for (int i = threadIdx.x; i < N; i += blockDim.x) hist[i] = 0u;
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) s_log[i] = c_logtab[i];
+  const int g = p.em_cell[e];
+  const int wall = p.em_wall[e];
+  const bool is_surface = wall >= 0;
+  if (threadIdx.x == 0) {
+    const int em_nv = p.poly_nv[g];
+    const double* vx = p.poly_vx + 4 * g;
+    const double* vy = p.poly_vy + 4 * g;
+    if (is_surface) {
+      const int j = (wall + 1 == em_nv) ? 0 : wall + 1;
+      const double ex = vx[j] - vx[wall], ey = vy[j] - vy[wall];
+      const double len = sqrt(ex * ex + ey * ey);
+      s_em[0] = vx[wall]; s_em[1] = vy[wall]; s_em[2] = ex; s_em[3] = ey;
+      s_em[4] = ex / len; s_em[5] = ey / len;
+      s_em[6] = -(ey / len); s_em[7] = ex / len;
+    } else {
+      s_em[0] = vx[0]; s_em[1] = vy[0]; s_em[2] = vx[1] - vx[0]; s_em[3] = vy[1] - vy[0]; s_em[4] = vx[2] - vx[0]; s_em[5] = vy[2] - vy[0];
+      s_em[6] = vx[2]; s_em[7] = vy[2]; s_em[8] = vx[3] - vx[2]; s_em[9] = vy[3] - vy[2]; s_em[10] = vx[0] - vx[2]; s_em[11] = vy[0] - vy[2];
+      s_em[14] = em_nv == 3 ? 2.0 : 0.5 * (vx[0] * (vy[1] - vy[2]) + vx[1] * (vy[2] - vy[0]) + vx[2] * (vy[0] - vy[1])) / p.cell_volume[g];
+    }
+    s_em[12] = p.cell_mid[2 * g] * p.nudge; s_em[13] = p.cell_mid[2 * g + 1] * p.nudge;
+  }
+
+  const int64_t per = (p.rays_per_emitter + p.row_chunks - 1) / p.row_chunks;
+  const int64_t r_begin = (int64_t)chunk * per;
+  int64_t r_end = r_begin + per;
+  if (r_end > p.rays_per_emitter) r_end = p.rays_per_emitter;
+
+  const double ub = p.uniform_beta[band];
+  const bool uniform = ub > -0.1;                      // traceRay.jl:4
+  const double* beta_band = p.beta + (size_t)band * p.n_cells;
+  const double beta_u = beta_band[0];                  // traceRay.jl:6-11: beta of fine_mesh[1][1]
+  const int rec_slot = (p.rec_slot != nullptr && band == p.rec_bin) ? p.rec_slot[e] : -1;
+  unsigned long long* count_row = p.counts + (p.compact_rows ? ((size_t)bi * p.n_owned + y) : ((size_t)bi * N + e)) * (size_t)N;
+
+  __syncthreads();
+
+  SqBlock b;
+  b.s_em = s_em; b.s_log = s_log; b.hist = hist; b.beta_band = beta_band;
+  b.inv_beta_u = beta_u > 0.0 ? 1.0 / beta_u : CUDART_INF;
+  b.c1 = -(p.face0.ax * p.face0.g1x + p.face0.ay * p.face0.g1y);
+  b.c2 = -(p.face0.ax * p.face0.g2x + p.face0.ay * p.face0.g2y);
+  b.one_m_nudge = 1.0 - p.nudge; b.midx_n = s_em[12]; b.midy_n = s_em[13];
+  b.e = (uint32_t)e; b.cw = ((uint32_t)band << 16);
+  b.ray0 = p.ray_id_offset + r_begin;
+  b.n_rays = r_end > r_begin ? (uint32_t)(r_end - r_begin) : 0u;
+  b.rec_base = rec_slot >= 0 ? (size_t)rec_slot * (size_t)p.rays_per_emitter + (size_t)r_begin : 0;
+
+  unsigned int n_lost;
+  const bool rec = rec_slot >= 0;
+  if (is_surface) {
+    if (uniform) n_lost = rec ? sq_ray_loop<true, true, true>(p, b) : sq_ray_loop<true, true, false>(p, b);
+    else         n_lost = rec ? sq_ray_loop<true, false, true>(p, b) : sq_ray_loop<true, false, false>(p, b);
+  } else {
+    if (uniform) n_lost = rec ? sq_ray_loop<false, true, true>(p, b) : sq_ray_loop<false, true, false>(p, b);
+    else         n_lost = rec ? sq_ray_loop<false, false, true>(p, b) : sq_ray_loop<false, false, false>(p, b);
+  }
+
+  for (int off = 16; off > 0; off >>= 1) n_lost += __shfl_down_sync(0xffffffffu, n_lost, off);
+  if ((threadIdx.x & 31) == 0 && n_lost) {
+    if (p.flush_system) atomicAdd_system(&p.lost[(size_t)bi * N + e], (unsigned long long)n_lost);
+    else atomicAdd(&p.lost[(size_t)bi * N + e], (unsigned long long)n_lost);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const uint32_t v = hist[i];
+    if (v) {
+      if (p.flush_system) atomicAdd_system(&count_row[i], (unsigned long long)v);
+      else atomicAdd(&count_row[i], (unsigned long long)v);
+    }
+  }
+}
+
 // kernel variants: hist_in_smem x fast x multi; the register bound MINB only varies for the hot FIRST_INTERACTION FAST kernel
 typedef void (*TraceKernel)(const TraceParams);
 static TraceKernel kernel_variant(bool hist, bool fast, int minb, bool multi, bool sq) {
-  if (sq && hist && fast && !multi)
-    return minb == 5 ? (TraceKernel)trace_exchange_kernel<true, true, 5, false, true> : (TraceKernel)trace_exchange_kernel<true, true, 4, false, true>;
+  if (sq && hist && fast && !multi) {
+    if (minb == 5) return (TraceKernel)trace_exchange_sq_kernel<5>;
+    if (minb == 3) return (TraceKernel)trace_exchange_kernel<true, true, 4, false, true>;   // the shared-loop form (RTHX_MINB=3: A/B knob)
+    return (TraceKernel)trace_exchange_sq_kernel<4>;
+  }
   if (multi) {
     if (hist) return fast ? (TraceKernel)trace_exchange_kernel<true, true, 2, true, false> : (TraceKernel)trace_exchange_kernel<true, false, 2, true, false>;
     return fast ? (TraceKernel)trace_exchange_kernel<false, true, 2, true, false> : (TraceKernel)trace_exchange_kernel<false, false, 2, true, false>;
