@@ -513,7 +513,7 @@ extern "C" int rthx_get_info(const rthx_handle* h, rthx_info* info) {
 // ---------------------------------------------------------------------------------------------------------------
 namespace {
 
-struct LaunchPlan { int n_owned, n_blocks, block_threads, row_chunks, hist_in_smem, fast, minb, multi, sq; size_t smem_bytes; };
+struct LaunchPlan { int n_owned, n_blocks, block_threads, row_chunks, hist_in_smem, fast, minb, multi, sq, queue_depth; size_t smem_bytes; };
 
 int check_args(rthx_handle* h, const rthx_trace_args* a) {
   if (!a) return fail(h, RTHX_ERR_ARG, "trace: args is NULL");
@@ -551,6 +551,18 @@ LaunchPlan make_plan(const rthx_handle* h, const rthx_trace_args* a, int rank, i
     if (const char* ev = std::getenv("RTHX_MINB")) { const int v = std::atoi(ev); if (v == 5 || v == 3) pl.minb = v; }
   }
   pl.smem_bytes = coarse_bytes + em_bytes + (pl.hist_in_smem ? hist_bytes : 0);
+  // Multi-face FAST meshes: the queue kernel (per-warp ray queue in shared memory, 40 bytes per parked ray).  Depth = as many
+  // rays per lane as still leave 4 resident blocks per SM, at most 8; RTHX_QUEUE_DEPTH overrides (0 = the lock-step kernel).
+  if (pl.fast && !pl.multi && !pl.sq && pl.hist_in_smem && h->coarse_fits_smem && h->n_coarse > 1 && pl.block_threads == 256) {
+    const size_t base = (pl.smem_bytes + 15) & ~size_t(15);
+    const size_t per_depth = (size_t)pl.block_threads * 40;
+    const size_t budget = (size_t)h->prop.sharedMemPerMultiprocessor / 4 - 1024;
+    int depth = base < budget ? (int)std::min<size_t>(8, (budget - base) / per_depth) : 0;
+    if (const char* ev = std::getenv("RTHX_QUEUE_DEPTH")) { const int v = std::atoi(ev); if (v >= 0 && v <= 16) depth = v; }
+    if (depth >= 1 && base + depth * per_depth <= h->prop.sharedMemPerBlockOptin) {
+      pl.minb = 6; pl.queue_depth = depth; pl.smem_bytes = base + depth * per_depth;
+    }
+  }
   const long long rows = (long long)pl.n_owned * a->n_bins;
   long long chunks = a->row_chunks;
   if (chunks <= 0) {
@@ -579,6 +591,7 @@ void fill_params(const rthx_handle* h, const rthx_trace_args* a, const LaunchPla
   P.emitter_rank = rank; P.emitter_world = world; P.n_owned = pl.n_owned; P.y_offset = 0;
   P.compact_rows = compact ? 1 : 0;
   P.row_chunks = pl.row_chunks;
+  P.queue_depth = pl.queue_depth;
   P.coarse_in_smem = h->coarse_fits_smem ? 1 : 0;
   P.hist_in_smem = pl.hist_in_smem;
   P.force_generic = a->locator == RTHX_LOCATOR_GENERIC ? 1 : 0;

@@ -664,11 +664,18 @@ template <bool SURF, bool UNIFORM, bool REC>
 __device__ __forceinline__ unsigned int sq_ray_loop(const TraceParams& p, const SqBlock& b) {
   const CoarseDev& cf = p.face0;
   unsigned int n_lost = 0;
+  // The Philox words of a thread's NEXT ray are computed at the end of the loop body, behind the tally: measured 3 %
+  // faster than generating them at the top (11.25 vs 11.53 ms per 1e9 rays) — the integer burst then overlaps the
+  // shared-memory atomic and the FP64 tail of the other warps.  (Generating them in the same basic block as the FP64
+  // geometry of the current ray, a software pipeline, costs 8 live registers and was slower: 11.62 ms.)
+  uint4 w0n, w1n;
+  {
+    const uint64_t ray_id = (uint64_t)(b.ray0 + (int64_t)threadIdx.x);
+    w0n = philox4x32_10_rk(make_uint4((uint32_t)ray_id, (uint32_t)(ray_id >> 32), b.e, b.cw | 0u), p.rk);
+    w1n = philox4x32_10_rk(make_uint4((uint32_t)ray_id, (uint32_t)(ray_id >> 32), b.e, b.cw | 1u), p.rk);
+  }
   for (uint32_t i = threadIdx.x; i < b.n_rays; i += blockDim.x) {
-    const uint64_t ray_id = (uint64_t)(b.ray0 + (int64_t)i);
-    const uint32_t c_lo = (uint32_t)ray_id, c_hi = (uint32_t)(ray_id >> 32);
-    const uint4 w0 = philox4x32_10_rk(make_uint4(c_lo, c_hi, b.e, b.cw | 0u), p.rk);
-    const uint4 w1 = philox4x32_10_rk(make_uint4(c_lo, c_hi, b.e, b.cw | 1u), p.rk);
+    const uint4 w0 = w0n, w1 = w1n;
     double px, py, dx, dy, R_S;
     if (SURF) {
       const double R = u32d(w0.x, p.k_u32);
@@ -735,6 +742,11 @@ __device__ __forceinline__ unsigned int sq_ray_loop(const TraceParams& p, const 
       }
     } else {
       ++n_lost;
+    }
+    {
+      const uint64_t ray_id = (uint64_t)(b.ray0 + (int64_t)(i + blockDim.x));
+      w0n = philox4x32_10_rk(make_uint4((uint32_t)ray_id, (uint32_t)(ray_id >> 32), b.e, b.cw | 0u), p.rk);
+      w1n = philox4x32_10_rk(make_uint4((uint32_t)ray_id, (uint32_t)(ray_id >> 32), b.e, b.cw | 1u), p.rk);
     }
   }
   return n_lost;
@@ -830,14 +842,293 @@ __global__ void __launch_bounds__(256, MINB) trace_exchange_sq_kernel(const __gr
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// K1-Q: the fused kernel for multi-face FAST meshes (cfg5: 16 wedges with transparent interfaces and triangle sub-meshes).
+// A ray crosses 3-4 coarse faces on average but up to ~10, and in trace_exchange_kernel a warp waits for its longest
+// ray: 13.6 of 32 lanes are active on average (ncu), 10.7 in the traversal loop.  Here every warp owns a ray QUEUE in
+// shared memory:
+//   emission  : each lane emits `depth` rays at full occupancy (Philox + FP64 sampling) and parks their state
+//               (p, d, -log R: 40 bytes) in the warp's queue;
+//   traversal : one coarse-face step per loop iteration for every lane that holds a ray; lanes whose ray ended take the
+//               next unprocessed queue slot — slots are handed out with __ballot_sync + __popc (match / vote, no atomics)
+//               — so the warp stays full until its queue runs dry.
+// Which lane traces which ray does not matter: tallies are integers keyed by the ray's own Philox counter, so the counts
+// stay bit-identical to every other kernel variant, block shape and GPU count.
+// ------------------------------------------------------------------------------------------------------------
+struct QueueBlock {          // block-uniform state of one (emitter row, band, chunk) in the queue kernel
+  const CoarseDev* coarse;   // shared memory
+  const double* s_em;
+  const double2* s_log;
+  uint32_t* hist;
+  double* q;                 // this warp's queue: px | py | dx | dy | -log R, `wq` doubles each
+  const double* beta_band;
+  double inv_beta_u;
+  int64_t r_begin, r_end;    // ray range of the block
+  size_t rec_row;            // first recorder slot of the emitter row
+  uint32_t e, cw;
+  int c0, wq, n_warps, warp, lane, is_surface;
+};
+
+template <bool UNIFORM, bool REC>
+__device__ __forceinline__ unsigned int queue_ray_loop(const TraceParams& p, const QueueBlock& b) {
+  const int wq = b.wq, lane = b.lane;
+  double* q_px = b.q;
+  double* q_py = q_px + wq;
+  double* q_dx = q_py + wq;
+  double* q_dy = q_dx + wq;
+  double* q_nl = q_dy + wq;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  unsigned int n_lost = 0;
+  // in-flight ray of this lane (lives in registers across queue refills)
+  bool active = false;
+  double px = 0.0, py = 0.0, dx = 0.0, dy = 0.0, neg_log = 0.0, S = 0.0, acc = 0.0;
+  int c = b.c0, it = 0;
+  int64_t r_cur = 0;                                   // ray index of the in-flight ray (recorder slot)
+  // the warp's rays: batch j of the block covers [r_begin + j*n_warps*wq, ...), this warp takes its wq-slice of every batch
+  int64_t rb = b.r_begin + (int64_t)b.warp * wq;
+  const int64_t stride = (int64_t)b.n_warps * wq;
+  while (true) {
+    // ---- stage 1: emission at full occupancy into the warp's queue ----------------------------------------------------
+    const int n_valid = rb < b.r_end ? (int)min((int64_t)wq, b.r_end - rb) : 0;
+    for (int s = lane; s < n_valid; s += 32) {
+      const uint64_t ray_id = (uint64_t)(p.ray_id_offset + rb + s);
+      const uint32_t c_lo = (uint32_t)ray_id, c_hi = (uint32_t)(ray_id >> 32);
+      const uint4 w0 = philox4x32_10_rk(make_uint4(c_lo, c_hi, b.e, b.cw | 0u), p.rk);
+      const uint4 w1 = philox4x32_10_rk(make_uint4(c_lo, c_hi, b.e, b.cw | 1u), p.rk);
+      double ex, ey, fx, fy, R_S;
+      if (b.is_surface) {
+        const double R = u32d(w0.x, p.k_u32);
+        ex = fma(b.s_em[2], R, b.s_em[0]);
+        ey = fma(b.s_em[3], R, b.s_em[1]);
+        const float cosT = __fsqrt_rn(u23(w0.y));
+        const float cos2 = __fmul_rn(cosT, cosT);
+        const double sinT = sqrt_pos(1.0 - (double)cos2);
+        const double xdir = sinT * cos2pi_unit((double)u23(w0.z));
+        const double zdir = (double)cosT;
+        fx = b.s_em[4] * xdir + b.s_em[6] * zdir;
+        fy = b.s_em[5] * xdir + b.s_em[7] * zdir;
+        R_S = u52(w1.x, w1.y, p.k_u52);
+      } else {
+        const double R1 = u32d(w0.x, p.k_u32), R2 = u32d(w0.y, p.k_u32);
+        const double sq = sqrt_pos(R1);
+        const double* tri = b.s_em + ((u32d(w0.z, p.k_u32) < b.s_em[14]) ? 0 : 6);
+        const double a2 = sq * R2, a1 = sq - a2;
+        ex = fma(a2, tri[4], fma(a1, tri[2], tri[0]));
+        ey = fma(a2, tri[5], fma(a1, tri[3], tri[1]));
+        const double Rt = u52(w1.x, w1.y, p.k_u52);
+        const double sinT = 2.0 * sqrt_pos(Rt * (1.0 - Rt));
+        fx = sinT * cos2pi_unit(u32d(w0.w, p.k_u32));
+        fy = fma(Rt, -2.0, 1.0);
+        R_S = u52(w1.z, w1.w, p.k_u52);
+      }
+      ex = fma(b.s_em[12] - ex, p.nudge, ex);
+      ey = fma(b.s_em[13] - ey, p.nudge, ey);
+      if (REC) {
+        double* o = p.rec_pts + 4 * (b.rec_row + (size_t)(rb + s));
+        o[0] = ex; o[1] = ey;
+      }
+      q_px[s] = ex; q_py[s] = ey; q_dx[s] = fx; q_dy[s] = fy; q_nl[s] = neg_log_table(R_S, b.s_log);
+    }
+    __syncwarp();
+    const bool last_batch = rb + stride >= b.r_end;    // nothing left to emit after this queue
+    // ---- stage 2: traversal; idle lanes take queue slots by warp vote --------------------------------------------------
+    int next = 0;
+    while (true) {
+      // refill: every lane without a ray takes the next unprocessed slot
+      const unsigned need = __ballot_sync(0xffffffffu, !active);
+      if (!active) {
+        const int idx = next + __popc(need & lt_mask);
+        if (idx < n_valid) {
+          px = q_px[idx]; py = q_py[idx]; dx = q_dx[idx]; dy = q_dy[idx]; neg_log = q_nl[idx];
+          S = UNIFORM ? neg_log * b.inv_beta_u : 0.0;
+          acc = 0.0; c = b.c0; it = 0; r_cur = rb + idx;
+          active = true;
+        }
+      }
+      next += __popc(need);
+      const unsigned busy = __ballot_sync(0xffffffffu, active);
+      if (busy == 0u) break;                                           // queue dry and nothing in flight
+      if (next >= n_valid && !last_batch && __popc(busy) <= 16) break; // queue dry: emit the next batch at full occupancy,
+                                                                       // the in-flight rays stay in their lanes
+      // one step = distToSurface2D on the current coarse face + ONE advance shared by the three outcomes (gas event, solid
+      // wall, crossing: only the advance length differs); the only divergent region is "this ray ended"
+      if (active) {
+        const CoarseDev& cf = b.coarse[c];
+        int k;
+        const double u = dist_fast(cf, px, py, dx, dy, p.k_eps, k);
+        bool gas, ok = true;
+        double tau_b = 0.0;
+        if (UNIFORM) {
+          gas = S < u;
+        } else {
+          const int f0 = locate_affine(p, cf, px, py);                  // traceRay.jl:87-100
+          ok = f0 >= 0;
+          const double local_beta = ok ? b.beta_band[cf.fine_off + f0] : 0.0;
+          tau_b = local_beta * u;
+          gas = acc + tau_b >= neg_log;
+          if (gas) S = (neg_log - acc) / local_beta;
+        }
+        const bool edge = u < CUDART_INF;                               // an edge lies ahead
+        const bool solid = cf.solid[k] != 0;
+        const int nc = cf.nbr[k];
+        const bool cross = ok & !gas & edge & !solid & (nc >= 0) & (it < 9999);
+        const bool tallied = ok & (gas | (edge & solid));               // ends in an element (unless the location fails)
+        // traceRay.jl:33,44,56: gas S - nudge, solid wall u - nudge, crossing u + nudge
+        const double adv = gas ? S - p.nudge : (solid ? u - p.nudge : u + p.nudge);
+        if (cross | tallied) {
+          px = fma(adv, dx, px);
+          py = fma(adv, dy, py);
+        }
+        if (cross) {
+          if (UNIFORM) S -= u; else acc += tau_b;
+          c = nc;
+          ++it;
+        } else {
+          active = false;
+          int absorber = -1;
+          if (tallied) {
+            const int f = locate_affine(p, cf, px, py);
+            if (f >= 0) {
+              const int gc = cf.fine_off + f;
+              if (gas) {
+                absorber = p.n_surfaces + gc;
+              } else {
+                int w = k;                                               // fine wall lying on coarse edge k
+                bool on_cut = false;
+                if (cf.kind != KIND_AFFINE_QUAD && __ldg(p.poly_nv + gc) != 3) {
+                  on_cut = k == cf.diag;                                 // quad cell of a mirrored-triangle lattice
+                  w = (k < cf.diag) ? k : k + 1;
+                }
+                if (!on_cut) absorber = __ldg(p.cell_surf_id + 4 * gc + w);   // -1: fine wall not solid -> lost
+              }
+            }
+          }
+          if (absorber >= 0) {
+            atomicAdd(&b.hist[absorber], 1u);
+            if (REC) {
+              const size_t sl = b.rec_row + (size_t)r_cur;
+              double* o = p.rec_pts + 4 * sl;
+              o[2] = px; o[3] = py;
+              p.rec_valid[sl] = 1;
+            }
+          } else {
+            ++n_lost;
+          }
+        }
+      }
+    }
+    __syncwarp();
+    if (last_batch) break;                             // the inner loop only leaves the last batch with nothing in flight
+    rb += stride;
+  }
+  return n_lost;
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) trace_exchange_queue_kernel(const __grid_constant__ TraceParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const size_t coarse_bytes = sizeof(CoarseDev) * (size_t)p.n_coarse;
+  double* s_em = reinterpret_cast<double*>(smem_raw + coarse_bytes);
+  double2* s_log = reinterpret_cast<double2*>(smem_raw + coarse_bytes + sizeof(double) * EM_DOUBLES);
+  uint32_t* hist = reinterpret_cast<uint32_t*>(smem_raw + coarse_bytes + sizeof(double) * EM_DOUBLES + sizeof(double2) * 64);
+  const int N = p.N;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+  const int wq = 32 * p.queue_depth;                           // queue slots per warp
+  double* queue = reinterpret_cast<double*>(smem_raw + ((coarse_bytes + sizeof(double) * EM_DOUBLES + sizeof(double2) * 64 + sizeof(uint32_t) * (size_t)N + 15) & ~size_t(15)));
+
+  const unsigned bid = blockIdx.x;
+  const int chunk = (int)(bid % (unsigned)p.row_chunks);
+  const unsigned t1 = bid / (unsigned)p.row_chunks;
+  const int bi = (int)(t1 % (unsigned)p.n_bins);
+  const int y = p.y_offset + (int)(t1 / (unsigned)p.n_bins);
+  const int e = p.emitter_rank + y * p.emitter_world;
+  const int band = p.bins[bi];
+
+  {
+    const int nw = (int)(coarse_bytes / 8);
+    const double* src = reinterpret_cast<const double*>(p.coarse);
+    double* dst = reinterpret_cast<double*>(smem_raw);
+    for (int i = threadIdx.x; i < nw; i += blockDim.x) dst[i] = src[i];
+  }
+  for (int i = threadIdx.x; i < N; i += blockDim.x) hist[i] = 0u;
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) s_log[i] = c_logtab[i];
+
+  const int g = p.em_cell[e];
+  const int wall = p.em_wall[e];
+  const bool is_surface = wall >= 0;
+  if (threadIdx.x == 0) {
+    const int em_nv = p.poly_nv[g];
+    const double* vx = p.poly_vx + 4 * g;
+    const double* vy = p.poly_vy + 4 * g;
+    if (is_surface) {
+      const int j = (wall + 1 == em_nv) ? 0 : wall + 1;
+      const double ex = vx[j] - vx[wall], ey = vy[j] - vy[wall];
+      const double len = sqrt(ex * ex + ey * ey);
+      s_em[0] = vx[wall]; s_em[1] = vy[wall]; s_em[2] = ex; s_em[3] = ey;
+      s_em[4] = ex / len; s_em[5] = ey / len;
+      s_em[6] = -(ey / len); s_em[7] = ex / len;
+    } else {
+      s_em[0] = vx[0]; s_em[1] = vy[0]; s_em[2] = vx[1] - vx[0]; s_em[3] = vy[1] - vy[0]; s_em[4] = vx[2] - vx[0]; s_em[5] = vy[2] - vy[0];
+      s_em[6] = vx[2]; s_em[7] = vy[2]; s_em[8] = vx[3] - vx[2]; s_em[9] = vy[3] - vy[2]; s_em[10] = vx[0] - vx[2]; s_em[11] = vy[0] - vy[2];
+      s_em[14] = em_nv == 3 ? 2.0 : 0.5 * (vx[0] * (vy[1] - vy[2]) + vx[1] * (vy[2] - vy[0]) + vx[2] * (vy[0] - vy[1])) / p.cell_volume[g];
+    }
+    s_em[12] = p.cell_mid[2 * g]; s_em[13] = p.cell_mid[2 * g + 1];
+  }
+
+  const int64_t per = (p.rays_per_emitter + p.row_chunks - 1) / p.row_chunks;
+  const int64_t r_begin = (int64_t)chunk * per;
+  int64_t r_end = r_begin + per;
+  if (r_end > p.rays_per_emitter) r_end = p.rays_per_emitter;
+
+  const double ub = p.uniform_beta[band];
+  const bool uniform = ub > -0.1;                      // traceRay.jl:4
+  const double* beta_band = p.beta + (size_t)band * p.n_cells;
+  const double beta_u = beta_band[0];                  // traceRay.jl:6-11: beta of fine_mesh[1][1]
+  const int rec_slot = (p.rec_slot != nullptr && band == p.rec_bin) ? p.rec_slot[e] : -1;
+  unsigned long long* count_row = p.counts + (p.compact_rows ? ((size_t)bi * p.n_owned + y) : ((size_t)bi * N + e)) * (size_t)N;
+
+  __syncthreads();
+
+  QueueBlock b;
+  b.coarse = reinterpret_cast<const CoarseDev*>(smem_raw);
+  b.s_em = s_em; b.s_log = s_log; b.hist = hist;
+  b.q = queue + (size_t)warp * 5 * wq;
+  b.beta_band = beta_band;
+  b.inv_beta_u = beta_u > 0.0 ? 1.0 / beta_u : CUDART_INF;
+  b.r_begin = r_begin; b.r_end = r_end;
+  b.rec_row = rec_slot >= 0 ? (size_t)rec_slot * (size_t)p.rays_per_emitter : 0;
+  b.e = (uint32_t)e; b.cw = ((uint32_t)band << 16);
+  b.c0 = p.em_coarse[e]; b.wq = wq; b.n_warps = n_warps; b.warp = warp; b.lane = lane; b.is_surface = is_surface ? 1 : 0;
+
+  unsigned int n_lost;
+  if (uniform) n_lost = rec_slot >= 0 ? queue_ray_loop<true, true>(p, b) : queue_ray_loop<true, false>(p, b);
+  else         n_lost = rec_slot >= 0 ? queue_ray_loop<false, true>(p, b) : queue_ray_loop<false, false>(p, b);
+
+  // ---- flush --------------------------------------------------------------------------------------------------
+  for (int off = 16; off > 0; off >>= 1) n_lost += __shfl_down_sync(0xffffffffu, n_lost, off);
+  if (lane == 0 && n_lost) {
+    if (p.flush_system) atomicAdd_system(&p.lost[(size_t)bi * N + e], (unsigned long long)n_lost);
+    else atomicAdd(&p.lost[(size_t)bi * N + e], (unsigned long long)n_lost);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const uint32_t v = hist[i];
+    if (v) {
+      if (p.flush_system) atomicAdd_system(&count_row[i], (unsigned long long)v);
+      else atomicAdd(&count_row[i], (unsigned long long)v);
+    }
+  }
+}
+
 // kernel variants: hist_in_smem x fast x multi; the register bound MINB only varies for the hot FIRST_INTERACTION FAST kernel
 typedef void (*TraceKernel)(const TraceParams);
 static TraceKernel kernel_variant(bool hist, bool fast, int minb, bool multi, bool sq) {
   if (sq && hist && fast && !multi) {
-    if (minb == 5) return (TraceKernel)trace_exchange_sq_kernel<5>;
-    if (minb == 3) return (TraceKernel)trace_exchange_kernel<true, true, 4, false, true>;   // the shared-loop form (RTHX_MINB=3: A/B knob)
+    if (minb == 5) return (TraceKernel)trace_exchange_sq_kernel<5>;                         // RTHX_MINB=5: 48 registers, 5 blocks / SM (A/B knob)
+    if (minb == 3) return (TraceKernel)trace_exchange_kernel<true, true, 4, false, true>;   // RTHX_MINB=3: the shared-loop form (A/B knob)
     return (TraceKernel)trace_exchange_sq_kernel<4>;
   }
+  if (minb == 6 && hist && fast && !multi && !sq) return (TraceKernel)trace_exchange_queue_kernel<4>;   // per-warp ray queue (multi-face meshes)
   if (multi) {
     if (hist) return fast ? (TraceKernel)trace_exchange_kernel<true, true, 2, true, false> : (TraceKernel)trace_exchange_kernel<true, false, 2, true, false>;
     return fast ? (TraceKernel)trace_exchange_kernel<false, true, 2, true, false> : (TraceKernel)trace_exchange_kernel<false, false, 2, true, false>;
@@ -856,7 +1147,7 @@ cudaError_t configure_trace_kernel(size_t smem_bytes) {
     for (int multi = 0; multi < 2; ++multi)
       for (int hist = 0; hist < 2; ++hist)
         for (int fast = 0; fast < 2; ++fast)
-          for (int minb = 2; minb <= 5; ++minb) {
+          for (int minb = 2; minb <= 6; ++minb) {
             cudaError_t e = cudaFuncSetAttribute((const void*)kernel_variant(hist, fast, minb, multi, sq), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
             if (e != cudaSuccess) return e;
           }
