@@ -592,6 +592,8 @@ void fill_params(const rthx_handle* h, const rthx_trace_args* a, const LaunchPla
   P.compact_rows = compact ? 1 : 0;
   P.row_chunks = pl.row_chunks;
   P.queue_depth = pl.queue_depth;
+  P.queue_refill = 24;
+  if (const char* ev = std::getenv("RTHX_QUEUE_REFILL")) { const int v = std::atoi(ev); if (v >= 0 && v <= 32) P.queue_refill = v; }   // tuning knob
   P.coarse_in_smem = h->coarse_fits_smem ? 1 : 0;
   P.hist_in_smem = pl.hist_in_smem;
   P.force_generic = a->locator == RTHX_LOCATOR_GENERIC ? 1 : 0;

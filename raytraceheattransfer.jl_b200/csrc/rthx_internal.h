@@ -82,6 +82,7 @@ struct TraceParams {
   int32_t specular;            // MULTI_BOUNCE: mirror reflection instead of diffuse
   int32_t flush_system;        // 1: system-scope atomics for the flush (count matrix in peer memory)
   int32_t rec_bin;
+  int32_t queue_refill;        // queue kernel: with the queue dry, emit the next batch once <= this many lanes still hold a ray
   int32_t queue_depth;         // queue kernel: rays parked per lane and batch (queue slots per warp = 32 * queue_depth)
   int64_t rays_per_emitter;
   int64_t ray_id_offset;

@@ -948,7 +948,7 @@ __device__ __forceinline__ unsigned int queue_ray_loop(const TraceParams& p, con
       next += __popc(need);
       const unsigned busy = __ballot_sync(0xffffffffu, active);
       if (busy == 0u) break;                                           // queue dry and nothing in flight
-      if (next >= n_valid && !last_batch && __popc(busy) <= 16) break; // queue dry: emit the next batch at full occupancy,
+      if (next >= n_valid && !last_batch && __popc(busy) <= p.queue_refill) break; // queue dry: emit the next batch at full occupancy,
                                                                        // the in-flight rays stay in their lanes
       // one step = distToSurface2D on the current coarse face + ONE advance shared by the three outcomes (gas event, solid
       // wall, crossing: only the advance length differs); the only divergent region is "this ray ended"
