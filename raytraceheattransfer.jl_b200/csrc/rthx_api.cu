@@ -540,7 +540,7 @@ LaunchPlan make_plan(const rthx_handle* h, const rthx_trace_args* a, int rank, i
   pl.minb = pl.multi ? 2 : 4;
   if (const char* ev = std::getenv("RTHX_MINB")) { const int v = std::atoi(ev); if (v >= 2 && v <= 4) pl.minb = v; }   // tuning knob
   const size_t coarse_bytes = h->coarse_fits_smem ? sizeof(CoarseDev) * (size_t)h->n_coarse : 0;
-  const size_t hist_bytes = sizeof(uint32_t) * (size_t)h->N, em_bytes = sizeof(double) * 16 + 16 * 64;   // emitter block + log table
+  const size_t hist_bytes = sizeof(uint32_t) * (size_t)h->N, em_bytes = sizeof(double) * 16 + 16 * 256;   // emitter block + log table (LOGTAB_N entries)
   pl.hist_in_smem = (coarse_bytes + em_bytes + hist_bytes <= h->prop.sharedMemPerBlockOptin) ? 1 : 0;
   if (const char* ev = std::getenv("RTHX_FORCE_GLOBAL_TALLY")) { if (std::atoi(ev)) pl.hist_in_smem = 0; }   // test knob: the N > ~57k path
   pl.sq = (h->single_quad && a->locator != RTHX_LOCATOR_GENERIC && !pl.multi && pl.hist_in_smem) ? 1 : 0;
@@ -612,6 +612,24 @@ void fill_params(const rthx_handle* h, const rthx_trace_args* a, const LaunchPla
   P.rec_slot = nullptr; P.rec_pts = nullptr; P.rec_valid = nullptr;
   P.face0 = h->face0;
   P.k_u52 = 1.0 - 0x1p-53; P.k_u32 = 1.0 - 0x1p-33; P.k_eps = 1e-10;
+  P.k_u52c = 1.5 - 0x1p-53; P.k_u32c = 1.5 - 0x1p-33;
+  {
+    // SQ kernels: slab form of distToSurface2D on the single parallelogram — centre line and half width of each edge pair
+    // (h0 - q = hw - (q - cen), q - h2 = hw + (q - cen)), the folded lattice-inverse offsets, and the axis-aligned special case
+    // (n0 = (0, +-1), n1 = (+-1, 0), lattice axes along x and y, all exact: every product with a zero component vanishes exactly,
+    // so the shortened arithmetic is bit-identical to the general form).
+    const CoarseDev& f = h->face0;
+    P.sq_cen0 = 0.5 * (f.h[0] + f.h[2]); P.sq_hw0 = 0.5 * (f.h[0] - f.h[2]);
+    P.sq_cen1 = 0.5 * (f.h[1] + f.h[3]); P.sq_hw1 = 0.5 * (f.h[1] - f.h[3]);
+    P.sq_lc1 = -(f.ax * f.g1x + f.ay * f.g1y);
+    P.sq_lc2 = -(f.ax * f.g2x + f.ay * f.g2y);
+    P.sq_one_m_nudge = 1.0 - a->nudge;
+    const bool axis = f.nx[0] == 0.0 && std::fabs(f.ny[0]) == 1.0 && std::fabs(f.nx[1]) == 1.0 && f.ny[1] == 0.0 && f.g1y == 0.0 && f.g2x == 0.0;
+    P.sq_axis = axis ? 1 : 0;
+    if (const char* ev = std::getenv("RTHX_NO_AXIS")) { if (std::atoi(ev)) P.sq_axis = 0; }   // test knob: the general SQ loop
+    P.sq_cy = f.ny[0] * P.sq_cen0; P.sq_cx = f.nx[1] * P.sq_cen1;
+    P.sq_flip0 = f.ny[0] < 0.0 ? 0x80000000u : 0u; P.sq_flip1 = f.nx[1] < 0.0 ? 0x80000000u : 0u;
+  }
   uint32_t k0 = (uint32_t)a->seed, k1 = (uint32_t)(a->seed >> 32);
   for (int r = 0; r < 10; ++r) { P.rk[2 * r] = k0; P.rk[2 * r + 1] = k1; k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
 }

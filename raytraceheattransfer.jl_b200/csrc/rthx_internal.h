@@ -92,6 +92,15 @@ struct TraceParams {
   double k_u52;   // 1 - 2^-53
   double k_u32;   // 1 - 2^-33
   double k_eps;   // 1e-10, the near-parallel threshold of distToSurface2D.jl:10
+  double k_u52c;  // 3/2 - 2^-53: mantissa injection minus this = uniform - 1/2
+  double k_u32c;  // 3/2 - 2^-33
+  // SQ kernels (single parallelogram face): slab centre lines / half widths, folded lattice offsets, axis-aligned special case
+  double sq_cen0, sq_hw0, sq_cen1, sq_hw1;
+  double sq_lc1, sq_lc2, sq_one_m_nudge;
+  double sq_cy, sq_cx;         // axis-aligned: n0y * cen0, n1x * cen1
+  uint32_t sq_flip0, sq_flip1; // axis-aligned: sign bit of n0y / n1x
+  int32_t sq_axis;
+  int32_t sq_pad_;
   uint32_t rk[20];  // Philox round keys (key + r*W), two per round
   CoarseDev face0;  // SQ kernels: the single coarse face, read from the parameter bank
 };

@@ -95,9 +95,9 @@ __constant__ double c_sinpi[9] = {  // sin(pi z) = z * P(z^2), |z| <= 1/2, max a
 __device__ __forceinline__ double sqrt_pos(double x) {
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));   // MUFU.RSQ64H: ~2^-20 relative
-  const double e = fma(-x, y * y, 1.0);                     // 1 - x y^2
-  y = fma(fma(e, 0.375, 0.5), y * e, y);                    // y (1 + e/2 + 3 e^2/8): ~2^-58
-  return x * y;
+  const double g = x * y;                                   // sqrt(x) sqrt(1 - e),  e = 1 - x y^2
+  const double e = fma(-g, y, 1.0);
+  return fma(fma(e, 0.375, 0.5), g * e, g);                 // g (1 + e/2 + 3 e^2/8): ~2^-58; 5 FP64 instructions
 }
 __device__ __forceinline__ double div_pos(double a, double b) {
   double r;
@@ -105,6 +105,26 @@ __device__ __forceinline__ double div_pos(double a, double b) {
   r = fma(r, fma(-b, r, 1.0), r);                           // ~2^-40
   const double q = a * r;
   return fma(r, fma(-b, q, a), q);                          // residual correction: <= 1 ulp
+}
+
+// The same polynomial for the argument y = R - 1/2 (what the mantissa injection delivers in ONE DADD): with z' = |y| - 1/4 = z/2,
+// sin(pi z) = z' * P'(z'^2), P'_k = 2 * 4^k * P_k.  Scaling by powers of two is exact, so the result is bit-identical to
+// cos2pi_unit(R) — it only drops the DFMA 2R-1 and the two IMAD.MOVs that materialise its 2.0.
+__constant__ double c_sinpi2[9] = {
+    0x1.921fb54442d18p+1 * 0x1p1, -0x1.4abbce625be52p+2 * 0x1p3, 0x1.466bc6775aa7dp+1 * 0x1p5, -0x1.32d2cce627c86p-1 * 0x1p7,
+    0x1.5078348551854p-4 * 0x1p9, -0x1.e3074dfaf87afp-8 * 0x1p11, 0x1.e8f3675ee37ddp-12 * 0x1p13, -0x1.6f7acdb8f6580p-16 * 0x1p15,
+    0x1.9d462020fcc78p-21 * 0x1p17};
+__device__ __forceinline__ double cos2pi_centered(double y) {
+  const double z = fabs(y) - 0.25;
+  const double w = z * z;
+  double p = c_sinpi2[8];
+#pragma unroll
+  for (int k = 7; k >= 0; --k) p = fma(p, w, c_sinpi2[k]);
+  return z * p;
+}
+// u32 uniform minus 1/2, exact: [1,2) - (3/2 - 2^-33)
+__device__ __forceinline__ double u32d_centered(uint32_t w, double k_u32c) {
+  return __hiloint2double((int)(0x3FF00000u | (w >> 12)), (int)(w << 20)) - k_u32c;
 }
 
 // cos(2 pi R) for R in (0,1): with x = 2R - 1 in (-1,1), cos(2 pi R) = -cos(pi x) = sin(pi (|x| - 1/2)); branch-free.
@@ -117,88 +137,24 @@ __device__ __forceinline__ double cos2pi_unit(double R) {
   return z * p;
 }
 
-// -log(x) by table: x = 2^e m, m in [1,2) falls in one of 64 intervals with midpoint c_i; with r = m/c_i - 1 (|r| <= 2^-7)
-//   log x = e ln2 + log c_i + log1p(r),   log1p(r) = r - r^2/2 + ... + r^7/7   (truncation < 2^-59)
-// 11 FP64 instructions instead of ~30 for the fdlibm form below (the FP64 pipe is the busiest unit of the kernel).
-// Absolute error <= 2e-15 on -log x <= 37 (relative <= 1e-16 except within 1e-10 of x = 1, where the free path itself
-// is ~1e-10 and an absolute 1e-16 is immaterial).  The (1/c_i, log c_i) pairs are staged into shared memory per block.
-__constant__ double2 c_logtab[64] = {
-    {0x1.fc07f01fc07f0p-1, 0x1.fe02a6b106789p-8},
-    {0x1.f44659e4a4271p-1, 0x1.7b91b07d5b11bp-6},
-    {0x1.ecc07b301ecc0p-1, 0x1.39e87b9febd60p-5},
-    {0x1.e573ac901e574p-1, 0x1.b42dd711971bfp-5},
-    {0x1.de5d6e3f8868ap-1, 0x1.16536eea37ae1p-4},
-    {0x1.d77b654b82c34p-1, 0x1.51b073f06183fp-4},
-    {0x1.d0cb58f6ec074p-1, 0x1.8c345d6319b21p-4},
-    {0x1.ca4b3055ee191p-1, 0x1.c5e548f5bc743p-4},
-    {0x1.c3f8f01c3f8f0p-1, 0x1.fec9131dbeabbp-4},
-    {0x1.bdd2b899406f7p-1, 0x1.1b72ad52f67a0p-3},
-    {0x1.b7d6c3dda338bp-1, 0x1.371fc201e8f74p-3},
-    {0x1.b2036406c80d9p-1, 0x1.526e5e3a1b438p-3},
-    {0x1.ac5701ac5701bp-1, 0x1.6d60fe719d21dp-3},
-    {0x1.a6d01a6d01a6dp-1, 0x1.87fa06520c911p-3},
-    {0x1.a16d3f97a4b02p-1, 0x1.a23bc1fe2b563p-3},
-    {0x1.9c2d14ee4a102p-1, 0x1.bc286742d8cd6p-3},
-    {0x1.970e4f80cb872p-1, 0x1.d5c216b4fbb91p-3},
-    {0x1.920fb49d0e229p-1, 0x1.ef0adcbdc5936p-3},
-    {0x1.8d3018d3018d3p-1, 0x1.0402594b4d041p-2},
-    {0x1.886e5f0abb04ap-1, 0x1.1058bf9ae4ad5p-2},
-    {0x1.83c977ab2beddp-1, 0x1.1c898c16999fbp-2},
-    {0x1.7f405fd017f40p-1, 0x1.2895a13de86a3p-2},
-    {0x1.7ad2208e0ecc3p-1, 0x1.347dd9a987d55p-2},
-    {0x1.767dce434a9b1p-1, 0x1.404308686a7e4p-2},
-    {0x1.724287f46debcp-1, 0x1.4be5f957778a1p-2},
-    {0x1.6e1f76b4337c7p-1, 0x1.5767717455a6cp-2},
-    {0x1.6a13cd1537290p-1, 0x1.62c82f2b9c795p-2},
-    {0x1.661ec6a5122f9p-1, 0x1.6e08eaa2ba1e4p-2},
-    {0x1.623fa77016240p-1, 0x1.792a55fdd47a2p-2},
-    {0x1.5e75bb8d015e7p-1, 0x1.842d1da1e8b17p-2},
-    {0x1.5ac056b015ac0p-1, 0x1.8f11e873662c7p-2},
-    {0x1.571ed3c506b3ap-1, 0x1.99d958117e08bp-2},
-    {0x1.5390948f40febp-1, 0x1.a484090e5bb0ap-2},
-    {0x1.5015015015015p-1, 0x1.af1293247786bp-2},
-    {0x1.4cab88725af6ep-1, 0x1.b9858969310fbp-2},
-    {0x1.49539e3b2d067p-1, 0x1.c3dd7a7cdad4dp-2},
-    {0x1.460cbc7f5cf9ap-1, 0x1.ce1af0b85f3ebp-2},
-    {0x1.42d6625d51f87p-1, 0x1.d83e7258a2f3ep-2},
-    {0x1.3fb013fb013fbp-1, 0x1.e24881a7c6c26p-2},
-    {0x1.3c995a47babe7p-1, 0x1.ec399d2468cc0p-2},
-    {0x1.3991c2c187f63p-1, 0x1.f6123fa7028acp-2},
-    {0x1.3698df3de0748p-1, 0x1.ffd2e0857f498p-2},
-    {0x1.33ae45b57bcb2p-1, 0x1.04bdf9da926d2p-1},
-    {0x1.30d190130d190p-1, 0x1.0986f4f573521p-1},
-    {0x1.2e025c04b8097p-1, 0x1.0e44985d1cc8cp-1},
-    {0x1.2b404ad012b40p-1, 0x1.12f719593efbcp-1},
-    {0x1.288b01288b013p-1, 0x1.179eabbd899a1p-1},
-    {0x1.25e22708092f1p-1, 0x1.1c3b81f713c25p-1},
-    {0x1.23456789abcdfp-1, 0x1.20cdcd192ab6ep-1},
-    {0x1.20b470c67c0d9p-1, 0x1.2555bce98f7cbp-1},
-    {0x1.1e2ef3b3fb874p-1, 0x1.29d37fec2b08bp-1},
-    {0x1.1bb4a4046ed29p-1, 0x1.2e47436e40268p-1},
-    {0x1.19453808ca29cp-1, 0x1.32b1339121d71p-1},
-    {0x1.16e0689427379p-1, 0x1.37117b54747b6p-1},
-    {0x1.1485f0e0acd3bp-1, 0x1.3b68449fffc23p-1},
-    {0x1.12358e75d3033p-1, 0x1.3fb5b84d16f42p-1},
-    {0x1.0fef010fef011p-1, 0x1.43f9fe2f9ce67p-1},
-    {0x1.0db20a88f4696p-1, 0x1.48353d1ea88dfp-1},
-    {0x1.0b7e6ec259dc8p-1, 0x1.4c679afccee3ap-1},
-    {0x1.0953f39010954p-1, 0x1.50913cc01686bp-1},
-    {0x1.073260a47f7c6p-1, 0x1.54b2467999498p-1},
-    {0x1.05197f7d73404p-1, 0x1.58cadb5cd7989p-1},
-    {0x1.03091b51f5e1ap-1, 0x1.5cdb1dc6c1765p-1},
-    {0x1.0101010101010p-1, 0x1.60e32f44788d9p-1}};
+// -log(x) by table: x = 2^e m, m in [1,2) falls in one of 256 intervals with midpoint c_i; with r = m/c_i - 1 (|r| <= 2^-9)
+//   log x = e ln2 + log c_i + log1p(r),   log1p(r) = r - r^2/2 + r^3/3 - r^4/4 + r^5/5   (truncation r^6/6 < 2^-56)
+// 8 FP64 instructions instead of ~30 for the fdlibm form (FP64 instructions are the expensive ones of this kernel: the pipe
+// takes a warp every other cycle).  Absolute error <= 1e-15 on -log x <= 37 (relative <= 1e-16 except within 1e-10 of x = 1,
+// where the free path itself is ~1e-10 and an absolute 1e-16 is immaterial).  The (1/c_i, log c_i) pairs (tools/gen_logtab.py)
+// are staged into shared memory per block (4 KB).
+#include "rthx_logtab.h"
 
-__constant__ double c_l1p[6] = {0x1.2492492492492p-3 /* 1/7 */, -0x1.5555555555555p-3 /* -1/6 */, 0x1.999999999999ap-3 /* 1/5 */,
-                                0x1.5555555555555p-2 /* 1/3 */, 0x1.62e42fefa39efp-1 /* ln 2 */, 0.0};
+__constant__ double c_l1p[4] = {0x1.999999999999ap-3 /* 1/5 */, 0x1.5555555555555p-2 /* 1/3 */, 0x1.62e42fefa39efp-1 /* ln 2 */, 0.0};
 
 __device__ __forceinline__ double neg_log_table(double x, const double2* __restrict__ tab) {
   const int hi = __double2hiint(x), lo = __double2loint(x);
   const int e = (hi >> 20) - 1023;
   const double m = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, lo);
-  const double2 t = tab[(hi >> 14) & 63];
+  const double2 t = tab[(hi >> 12) & (LOGTAB_N - 1)];
   const double r = fma(m, t.x, -1.0);
-  const double P = fma(r, fma(r, fma(r, fma(r, fma(r, c_l1p[0], c_l1p[1]), c_l1p[2]), -0.25), c_l1p[3]), -0.5);
-  return -(fma((double)e, c_l1p[4], t.y) + fma(r * r, P, r));
+  const double P = fma(r, fma(r, fma(r, c_l1p[0], -0.25), c_l1p[1]), -0.5);
+  return -(fma((double)e, c_l1p[2], t.y) + fma(r * r, P, r));
 }
 
 // distToSurface2D on a coarse face, FAST path.  The emission / crossing point is inside the face, so edge i can
@@ -343,7 +299,7 @@ __global__ void __launch_bounds__(256, MINB) trace_exchange_kernel(const __grid_
   const size_t coarse_bytes = coarse_smem ? sizeof(CoarseDev) * (size_t)p.n_coarse : 0;
   double* s_em = reinterpret_cast<double*>(smem_raw + coarse_bytes);
   double2* s_log = reinterpret_cast<double2*>(smem_raw + coarse_bytes + sizeof(double) * EM_DOUBLES);
-  uint32_t* hist = reinterpret_cast<uint32_t*>(smem_raw + coarse_bytes + sizeof(double) * EM_DOUBLES + sizeof(double2) * 64);
+  uint32_t* hist = reinterpret_cast<uint32_t*>(smem_raw + coarse_bytes + sizeof(double) * EM_DOUBLES + sizeof(double2) * LOGTAB_N);
 
   // block -> (owned emitter ordinal y, traced bin bi, ray chunk)
   const unsigned bid = blockIdx.x;
@@ -365,7 +321,7 @@ __global__ void __launch_bounds__(256, MINB) trace_exchange_kernel(const __grid_
   if (HIST_SMEM)
     for (int i = threadIdx.x; i < N; i += blockDim.x) hist[i] = 0u;
   if (FAST)
-    for (int i = threadIdx.x; i < 64; i += blockDim.x) s_log[i] = c_logtab[i];
+    for (int i = threadIdx.x; i < LOGTAB_N; i += blockDim.x) s_log[i] = c_logtab[i];
   // FAST: a plain shared-memory pointer (LDS); otherwise a generic pointer that may be shared or global
   const CoarseDev* coarse = FAST ? s_coarse : (p.coarse_in_smem ? s_coarse : p.coarse);
 
@@ -639,28 +595,81 @@ __global__ void __launch_bounds__(256, MINB) trace_exchange_kernel(const __grid_
 //   * the lattice inverse and the emission nudge use pre-folded constants (s = p.g1 + c1 instead of (p - a).g1; p(1-nudge) +
 //     mid nudge instead of p + (mid - p) nudge): 4 FP64 instructions fewer, results equal to 1 ulp of the coordinates.
 // ------------------------------------------------------------------------------------------------------------
+// The triangle selector of emitVolumeRay2D.jl:7 as an integer compare:  (w + 1/2) 2^-32 < a  <=>  w < ceil(a 2^32 - 1/2)  (all
+// operations exact in double for a 2^32 < 2^52).  Returns the largest word that still selects triangle ABC; a >= 1 (triangular
+// cells: a = 2) selects it always.  (a <= 2^-33, a degenerate ABC, would select it for w = 0 only instead of never.)
+__device__ __forceinline__ uint32_t selector_threshold(double a) {
+  double t = ceil(a * 4294967296.0 - 0.5);
+  t = fmin(fmax(t, 1.0), 4294967296.0);
+  return (uint32_t)((unsigned long long)t - 1ull);
+}
+
 struct SqBlock {            // block-uniform state of one (emitter row, band, chunk)
   const double* s_em;       // emitter description (shared memory, EM_DOUBLES)
   const double2* s_log;     // -log table (shared memory)
   uint32_t* hist;           // row histogram (shared memory)
   const double* beta_band;  // per-cell beta of the band (non-uniform bins)
   double inv_beta_u;
-  double c1, c2;            // folded lattice-inverse offsets: s = px g1x + py g1y + c1, t = px g2x + py g2y + c2
-  double one_m_nudge, midx_n, midy_n;
+  double midx_n, midy_n;    // cell midPoint * nudge
+  uint32_t sel_thr;         // volume emitters: take triangle ABC iff Philox word <= sel_thr
   uint32_t e, cw;
   int64_t ray0;             // ray id of the block's first ray
   uint32_t n_rays;          // rays of this block
   size_t rec_base;          // recorder slot of the block's first ray
 };
 
-__device__ __forceinline__ int locate_sq(const CoarseDev& cf, double c1, double c2, double px, double py) {
-  const double s = fma(px, cf.g1x, fma(py, cf.g1y, c1)), t = fma(px, cf.g2x, fma(py, cf.g2y, c2));
+// Fine-cell index on the single lattice.  One unsigned compare per axis covers both ends of the range: a negative
+// coordinate floors to a negative integer (out of range as unsigned), an overflow saturates to INT_MIN/INT_MAX; s, t are finite
+// here (the advance length is finite whenever this is reached), so no NaN -> 0 alias can occur.
+template <bool AXIS>
+__device__ __forceinline__ int locate_sq(const TraceParams& p, double px, double py) {
+  const CoarseDev& cf = p.face0;
+  const double s = AXIS ? fma(px, cf.g1x, p.sq_lc1) : fma(px, cf.g1x, fma(py, cf.g1y, p.sq_lc1));
+  const double t = AXIS ? fma(py, cf.g2y, p.sq_lc2) : fma(px, cf.g2x, fma(py, cf.g2y, p.sq_lc2));
   const int n = __double2int_rd(s), m = __double2int_rd(t);
-  if (!((s >= 0.0) & (t >= 0.0) & (n < cf.Nx) & (m < cf.Ny))) return -1;
-  return n + m * cf.Nx;
+  return (((unsigned)n < (unsigned)cf.Nx) & ((unsigned)m < (unsigned)cf.Ny)) ? n + m * cf.Nx : -1;
 }
 
-template <bool SURF, bool UNIFORM, bool REC>
+__device__ __forceinline__ double flip_sign(double x, int sign_src_hi) {   // x with its sign bit xor-ed by the sign bit of a high word
+  return __hiloint2double(__double2hiint(x) ^ (sign_src_hi & (int)0x80000000), __double2loint(x));
+}
+
+// distToSurface2D on the single parallelogram, slab form about the centre lines: with t_a = p.n_a - cen_a, the plane distance
+// along the pair of edges with normal +-n_a is  hw_a - sign(d.n_a) t_a  (edge a if d.n_a > 0, edge a+2 otherwise).  Signs are
+// read from the high words (integer pipe), the argmin runs on cross-multiplied fractions, one division at the end.
+// AXIS: n0 = (0, +-1), n1 = (+-1, 0): d.n0 = +-dy, p.n0 = +-py — the four dot products disappear (bit-identical results).
+// Returns false when no edge lies ahead (the reference's u = Inf).
+template <bool AXIS>
+__device__ __forceinline__ bool dist_sq(const TraceParams& p, double px, double py, double dx, double dy, double& u, int& k) {
+  const CoarseDev& f = p.face0;
+  double ad0, ad1, tf0, tf1;
+  int s0, s1;                                     // high words carrying the sign of d.n0, d.n1
+  if (AXIS) {
+    s0 = __double2hiint(dy) ^ (int)p.sq_flip0; s1 = __double2hiint(dx) ^ (int)p.sq_flip1;
+    ad0 = fabs(dy); ad1 = fabs(dx);
+    tf0 = flip_sign(py - p.sq_cy, __double2hiint(dy));    // sign(d.n0) (p.n0 - cen0) = sign(dy) (py - n0y cen0)
+    tf1 = flip_sign(px - p.sq_cx, __double2hiint(dx));
+  } else {
+    const double den0 = fma(dx, f.nx[0], dy * f.ny[0]), den1 = fma(dx, f.nx[1], dy * f.ny[1]);
+    s0 = __double2hiint(den0); s1 = __double2hiint(den1);
+    ad0 = fabs(den0); ad1 = fabs(den1);
+    tf0 = flip_sign(fma(px, f.nx[0], fma(py, f.ny[0], -p.sq_cen0)), s0);
+    tf1 = flip_sign(fma(px, f.nx[1], fma(py, f.ny[1], -p.sq_cen1)), s1);
+  }
+  const double an0 = p.sq_hw0 - tf0, an1 = p.sq_hw1 - tf1;
+  // an > 0 by the high word: exact except for 0 < an < 2^-1022
+  const bool ok0 = (ad0 >= p.k_eps) & (__double2hiint(an0) > 0), ok1 = (ad1 >= p.k_eps) & (__double2hiint(an1) > 0);
+  const int e0 = s0 < 0 ? 2 : 0, e1 = s1 < 0 ? 3 : 1;
+  const double l = an0 * ad1, r = an1 * ad0;
+  const bool take0 = ok0 & (!ok1 | (l < r) | ((l == r) & (e0 < e1)));
+  k = take0 ? e0 : e1;
+  const double an = take0 ? an0 : an1, ad = take0 ? ad0 : ad1;
+  const bool any = ok0 | ok1;
+  u = any ? div_pos(an, ad) : CUDART_INF;
+  return any;
+}
+
+template <bool SURF, bool UNIFORM, bool REC, bool AXIS>
 __device__ __forceinline__ unsigned int sq_ray_loop(const TraceParams& p, const SqBlock& b) {
   const CoarseDev& cf = p.face0;
   unsigned int n_lost = 0;
@@ -684,7 +693,7 @@ __device__ __forceinline__ unsigned int sq_ray_loop(const TraceParams& p, const 
       const float cosT = __fsqrt_rn(u23(w0.y));
       const float cos2 = __fmul_rn(cosT, cosT);
       const double sinT = sqrt_pos(1.0 - (double)cos2);
-      const double xdir = sinT * cos2pi_unit((double)u23(w0.z));
+      const double xdir = sinT * cos2pi_centered((double)u23(w0.z) - 0.5);
       const double zdir = (double)cosT;
       dx = b.s_em[4] * xdir + b.s_em[6] * zdir;
       dy = b.s_em[5] * xdir + b.s_em[7] * zdir;
@@ -692,44 +701,48 @@ __device__ __forceinline__ unsigned int sq_ray_loop(const TraceParams& p, const 
     } else {
       const double R1 = u32d(w0.x, p.k_u32), R2 = u32d(w0.y, p.k_u32);
       const double sq = sqrt_pos(R1);
-      const double* tri = b.s_em + ((u32d(w0.z, p.k_u32) < b.s_em[14]) ? 0 : 6);
+      // triangle ABC or CDA (emitVolumeRay2D.jl:7): (w + 1/2) 2^-32 < area(ABC)/area  <=>  w <= thr, an integer compare
+      const double* tri = b.s_em + ((w0.z <= b.sel_thr) ? 0 : 6);
       const double a2 = sq * R2, a1 = sq - a2;
       px = fma(a2, tri[4], fma(a1, tri[2], tri[0]));
       py = fma(a2, tri[5], fma(a1, tri[3], tri[1]));
-      const double Rt = u52(w1.x, w1.y, p.k_u52);
-      const double sinT = 2.0 * sqrt_pos(Rt * (1.0 - Rt));
-      dx = sinT * cos2pi_unit(u32d(w0.w, p.k_u32));
-      dy = fma(Rt, -2.0, 1.0);
+      // theta = acos(1 - 2R): with c = R - 1/2 (one DADD from the mantissa injection), cos = -2c and sin = 2 sqrt(1/4 - c^2);
+      // 1/4 - c^2 = R (1 - R) exactly, so one fma rounds to the same double as the product did
+      const double c = __hiloint2double((int)(0x3FF00000u | (w1.y >> 12)), (int)((w1.y << 20) | (w1.x >> 12))) - p.k_u52c;
+      const double sinH = sqrt_pos(fma(-c, c, 0.25));
+      dx = (sinH + sinH) * cos2pi_centered(u32d_centered(w0.w, p.k_u32c));
+      dy = -(c + c);
       R_S = u52(w1.z, w1.w, p.k_u52);
     }
-    px = fma(px, b.one_m_nudge, b.midx_n);      // p + (mid - p) nudge  (emitSurfaceRay2D.jl:10, emitVolumeRay2D.jl:22)
-    py = fma(py, b.one_m_nudge, b.midy_n);
+    px = fma(px, p.sq_one_m_nudge, b.midx_n);      // p + (mid - p) nudge  (emitSurfaceRay2D.jl:10, emitVolumeRay2D.jl:22)
+    py = fma(py, p.sq_one_m_nudge, b.midy_n);
     if (REC) {
       double* o = p.rec_pts + 4 * (b.rec_base + i);
       o[0] = px; o[1] = py;
     }
     const double neg_log = neg_log_table(R_S, b.s_log);
     int k;
-    const double u = dist_quad(cf, px, py, dx, dy, p.k_eps, k);
+    double u;
+    const bool edge = dist_sq<AXIS>(p, px, py, dx, dy, u, k);
     double S;
     bool gas, ok = true;
     if (UNIFORM) {
       S = neg_log * b.inv_beta_u;
       gas = S < u;
     } else {
-      const int f0 = locate_sq(cf, b.c1, b.c2, px, py);        // traceRay.jl:87-100
+      const int f0 = locate_sq<AXIS>(p, px, py);               // traceRay.jl:87-100
       ok = f0 >= 0;
       const double local_beta = ok ? b.beta_band[f0] : 0.0;
       gas = local_beta * u >= neg_log;
       S = neg_log / local_beta;
     }
     int absorber = -1;
-    const bool hit = !gas & (u < CUDART_INF) & (cf.solid[k] != 0);   // an open edge has no neighbour face: the ray is lost
+    const bool hit = !gas & edge & (cf.solid[k] != 0);         // an open edge has no neighbour face: the ray is lost
     if (ok & (gas | hit)) {
       const double adv = (gas ? S : u) - p.nudge;
       px = fma(adv, dx, px);
       py = fma(adv, dy, py);
-      const int f = locate_sq(cf, b.c1, b.c2, px, py);
+      const int f = locate_sq<AXIS>(p, px, py);
       if (f >= 0) absorber = gas ? p.n_surfaces + f : __ldg(p.cell_surf_id + 4 * f + k);
     }
     if (absorber >= 0) {
@@ -752,12 +765,18 @@ __device__ __forceinline__ unsigned int sq_ray_loop(const TraceParams& p, const 
   return n_lost;
 }
 
+template <bool SURF, bool AXIS>
+__device__ __forceinline__ unsigned int sq_dispatch(const TraceParams& p, const SqBlock& b, bool uniform, bool rec) {
+  if (uniform) return rec ? sq_ray_loop<SURF, true, true, AXIS>(p, b) : sq_ray_loop<SURF, true, false, AXIS>(p, b);
+  return rec ? sq_ray_loop<SURF, false, true, AXIS>(p, b) : sq_ray_loop<SURF, false, false, AXIS>(p, b);
+}
+
 template <int MINB>
 __global__ void __launch_bounds__(256, MINB) trace_exchange_sq_kernel(const __grid_constant__ TraceParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* s_em = reinterpret_cast<double*>(smem_raw);
   double2* s_log = reinterpret_cast<double2*>(smem_raw + sizeof(double) * EM_DOUBLES);
-  uint32_t* hist = reinterpret_cast<uint32_t*>(smem_raw + sizeof(double) * EM_DOUBLES + sizeof(double2) * 64);
+  uint32_t* hist = reinterpret_cast<uint32_t*>(smem_raw + sizeof(double) * EM_DOUBLES + sizeof(double2) * LOGTAB_N);
 
   const unsigned bid = blockIdx.x;
   const int chunk = (int)(bid % (unsigned)p.row_chunks);
@@ -769,7 +788,7 @@ __global__ void __launch_bounds__(256, MINB) trace_exchange_sq_kernel(const __gr
   const int N = p.N;
 
   for (int i = threadIdx.x; i < N; i += blockDim.x) hist[i] = 0u;
-  for (int i = threadIdx.x; i < 64; i += blockDim.x) s_log[i] = c_logtab[i];
+  for (int i = threadIdx.x; i < LOGTAB_N; i += blockDim.x) s_log[i] = c_logtab[i];
   const int g = p.em_cell[e];
   const int wall = p.em_wall[e];
   const bool is_surface = wall >= 0;
@@ -788,6 +807,7 @@ __global__ void __launch_bounds__(256, MINB) trace_exchange_sq_kernel(const __gr
       s_em[0] = vx[0]; s_em[1] = vy[0]; s_em[2] = vx[1] - vx[0]; s_em[3] = vy[1] - vy[0]; s_em[4] = vx[2] - vx[0]; s_em[5] = vy[2] - vy[0];
       s_em[6] = vx[2]; s_em[7] = vy[2]; s_em[8] = vx[3] - vx[2]; s_em[9] = vy[3] - vy[2]; s_em[10] = vx[0] - vx[2]; s_em[11] = vy[0] - vy[2];
       s_em[14] = em_nv == 3 ? 2.0 : 0.5 * (vx[0] * (vy[1] - vy[2]) + vx[1] * (vy[2] - vy[0]) + vx[2] * (vy[0] - vy[1])) / p.cell_volume[g];
+      reinterpret_cast<uint32_t*>(s_em + 15)[0] = selector_threshold(s_em[14]);
     }
     s_em[12] = p.cell_mid[2 * g] * p.nudge; s_em[13] = p.cell_mid[2 * g + 1] * p.nudge;
   }
@@ -809,9 +829,8 @@ __global__ void __launch_bounds__(256, MINB) trace_exchange_sq_kernel(const __gr
   SqBlock b;
   b.s_em = s_em; b.s_log = s_log; b.hist = hist; b.beta_band = beta_band;
   b.inv_beta_u = beta_u > 0.0 ? 1.0 / beta_u : CUDART_INF;
-  b.c1 = -(p.face0.ax * p.face0.g1x + p.face0.ay * p.face0.g1y);
-  b.c2 = -(p.face0.ax * p.face0.g2x + p.face0.ay * p.face0.g2y);
-  b.one_m_nudge = 1.0 - p.nudge; b.midx_n = s_em[12]; b.midy_n = s_em[13];
+  b.midx_n = s_em[12]; b.midy_n = s_em[13];
+  b.sel_thr = reinterpret_cast<const uint32_t*>(s_em + 15)[0];
   b.e = (uint32_t)e; b.cw = ((uint32_t)band << 16);
   b.ray0 = p.ray_id_offset + r_begin;
   b.n_rays = r_end > r_begin ? (uint32_t)(r_end - r_begin) : 0u;
@@ -819,13 +838,8 @@ __global__ void __launch_bounds__(256, MINB) trace_exchange_sq_kernel(const __gr
 
   unsigned int n_lost;
   const bool rec = rec_slot >= 0;
-  if (is_surface) {
-    if (uniform) n_lost = rec ? sq_ray_loop<true, true, true>(p, b) : sq_ray_loop<true, true, false>(p, b);
-    else         n_lost = rec ? sq_ray_loop<true, false, true>(p, b) : sq_ray_loop<true, false, false>(p, b);
-  } else {
-    if (uniform) n_lost = rec ? sq_ray_loop<false, true, true>(p, b) : sq_ray_loop<false, true, false>(p, b);
-    else         n_lost = rec ? sq_ray_loop<false, false, true>(p, b) : sq_ray_loop<false, false, false>(p, b);
-  }
+  if (p.sq_axis) n_lost = is_surface ? sq_dispatch<true, true>(p, b, uniform, rec) : sq_dispatch<false, true>(p, b, uniform, rec);
+  else           n_lost = is_surface ? sq_dispatch<true, false>(p, b, uniform, rec) : sq_dispatch<false, false>(p, b, uniform, rec);
 
   for (int off = 16; off > 0; off >>= 1) n_lost += __shfl_down_sync(0xffffffffu, n_lost, off);
   if ((threadIdx.x & 31) == 0 && n_lost) {
@@ -1030,11 +1044,11 @@ __global__ void __launch_bounds__(256, MINB) trace_exchange_queue_kernel(const _
   const size_t coarse_bytes = sizeof(CoarseDev) * (size_t)p.n_coarse;
   double* s_em = reinterpret_cast<double*>(smem_raw + coarse_bytes);
   double2* s_log = reinterpret_cast<double2*>(smem_raw + coarse_bytes + sizeof(double) * EM_DOUBLES);
-  uint32_t* hist = reinterpret_cast<uint32_t*>(smem_raw + coarse_bytes + sizeof(double) * EM_DOUBLES + sizeof(double2) * 64);
+  uint32_t* hist = reinterpret_cast<uint32_t*>(smem_raw + coarse_bytes + sizeof(double) * EM_DOUBLES + sizeof(double2) * LOGTAB_N);
   const int N = p.N;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
   const int wq = 32 * p.queue_depth;                           // queue slots per warp
-  double* queue = reinterpret_cast<double*>(smem_raw + ((coarse_bytes + sizeof(double) * EM_DOUBLES + sizeof(double2) * 64 + sizeof(uint32_t) * (size_t)N + 15) & ~size_t(15)));
+  double* queue = reinterpret_cast<double*>(smem_raw + ((coarse_bytes + sizeof(double) * EM_DOUBLES + sizeof(double2) * LOGTAB_N + sizeof(uint32_t) * (size_t)N + 15) & ~size_t(15)));
 
   const unsigned bid = blockIdx.x;
   const int chunk = (int)(bid % (unsigned)p.row_chunks);
@@ -1051,7 +1065,7 @@ __global__ void __launch_bounds__(256, MINB) trace_exchange_queue_kernel(const _
     for (int i = threadIdx.x; i < nw; i += blockDim.x) dst[i] = src[i];
   }
   for (int i = threadIdx.x; i < N; i += blockDim.x) hist[i] = 0u;
-  for (int i = threadIdx.x; i < 64; i += blockDim.x) s_log[i] = c_logtab[i];
+  for (int i = threadIdx.x; i < LOGTAB_N; i += blockDim.x) s_log[i] = c_logtab[i];
 
   const int g = p.em_cell[e];
   const int wall = p.em_wall[e];
