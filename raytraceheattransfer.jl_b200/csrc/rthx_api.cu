@@ -397,7 +397,7 @@ extern "C" int rthx_create(rthx_handle** out, const rthx_mesh* m, int device_id)
 
   // locator grids + coarse descriptors
   std::vector<FaceSetDev> sets(1 + (size_t)nc);
-  std::vector<int32_t> bstart, bitems, lattice;
+  std::vector<int32_t> bstart, bitems, lattice, abs_tab;
   build_grid(&polys[ncell], nc, ncell, sets[0], bstart, bitems);
   std::vector<CoarseDev> coarse(nc);
   const double ext_tol = 1e-9;
@@ -415,6 +415,35 @@ extern "C" int rthx_create(rthx_handle** out, const rthx_mesh* m, int device_id)
     if (d.kind == KIND_AFFINE_QUAD) {   // slab form: opposite edges measured along the normals of edges 0 and 1
       d.h[2] = cp.vx[2] * cp.nx[0] + cp.vy[2] * cp.ny[0];
       d.h[3] = cp.vx[3] * cp.nx[1] + cp.vy[3] * cp.ny[1];
+      d.cen[0] = 0.5 * (d.h[0] + d.h[2]); d.hw[0] = 0.5 * (d.h[0] - d.h[2]);
+      d.cen[1] = 0.5 * (d.h[1] + d.h[3]); d.hw[1] = 0.5 * (d.h[1] - d.h[3]);
+    }
+    // Absorber table of an affine face: for every lattice cell the element a ray ending there is tallied in — entry 0 for a gas
+    // event (Ns + global cell index, getGlobalIndex2D.jl:10), entry 1+k for a hit on coarse edge k: the surface index of the fine
+    // wall lying on that edge (fine wall = k, except in the quad cells of a mirrored-triangle lattice, whose walls are numbered
+    // around the uncut parallelogram: the cut diagonal is no wall of theirs and the walls behind it shift by one), -1 where the
+    // fine wall is not solid or the lattice cell lies outside the triangle.
+    d.abs_off = -1;
+    if (d.kind != KIND_GENERIC) {
+      d.abs_off = (int32_t)(abs_tab.size() / 5);
+      const size_t ncell_lat = (size_t)d.Nx * d.Ny;
+      for (size_t l = 0; l < ncell_lat; ++l) {
+        const int f = d.kind == KIND_AFFINE_QUAD ? (int)l : lattice[(size_t)d.lat_off + l];
+        int32_t row[5] = {-1, -1, -1, -1, -1};
+        if (f >= 0) {
+          const int gc = f0 + f;
+          row[0] = ns + gc;
+          for (int k = 0; k < cp.n; ++k) {
+            int w = k;
+            if (d.kind == KIND_AFFINE_TRI && polys[gc].n != 3) {
+              if (k == d.diag) continue;
+              w = k < d.diag ? k : k + 1;
+            }
+            row[1 + k] = m->cell_surf_id[4 * (size_t)gc + w];
+          }
+        }
+        abs_tab.insert(abs_tab.end(), row, row + 5);
+      }
     }
   }
   // neighbour table: the unique coarse face sharing the (reversed) edge; T-junctions stay -1 (generic search)
@@ -448,6 +477,7 @@ extern "C" int rthx_create(rthx_handle** out, const rthx_mesh* m, int device_id)
   std::vector<double> mid(m->cell_mid, m->cell_mid + 2 * (size_t)ncell), vol(m->cell_volume, m->cell_volume + ncell);
   std::vector<int32_t> surf(m->cell_surf_id, m->cell_surf_id + 4 * (size_t)ncell);
   if (lattice.empty()) lattice.push_back(-1);
+  if (abs_tab.empty()) abs_tab.assign(5, -1);
   // MULTI_BOUNCE properties: scattering albedo per (band, cell) — 0 where beta = 0 — and emissivity per (band, surface)
   std::vector<double> omega((size_t)nb * ncell), epsv;
   for (size_t i = 0; i < omega.size(); ++i) omega[i] = beta[i] > 0.0 ? m->sigma_s[i] / beta[i] : 0.0;
@@ -460,7 +490,7 @@ extern "C" int rthx_create(rthx_handle** out, const rthx_mesh* m, int device_id)
   const size_t o_coarse = A.add(coarse), o_sets = A.add(sets), o_bstart = A.add(bstart), o_bitems = A.add(bitems),
                o_nv = A.add(poly_nv), o_pvx = A.add(pvx), o_pvy = A.add(pvy), o_pnx = A.add(pnx), o_pny = A.add(pny),
                o_mid = A.add(mid), o_vol = A.add(vol), o_surf = A.add(surf), o_beta = A.add(beta), o_ub = A.add(ub),
-               o_lat = A.add(lattice), o_omega = A.add(omega), o_eps = A.add(epsv), o_ec = A.add(em_cell), o_ew = A.add(em_wall), o_eco = A.add(em_coarse),
+               o_lat = A.add(lattice), o_abs = A.add(abs_tab), o_omega = A.add(omega), o_eps = A.add(epsv), o_ec = A.add(em_cell), o_ew = A.add(em_wall), o_eco = A.add(em_coarse),
                o_bins = A.add(std::vector<int32_t>(), (size_t)nb * 4 + 16), o_rec = A.add(std::vector<int32_t>(), (size_t)N),
                o_lost = A.add(std::vector<unsigned long long>(), ((size_t)nb * 4 + 16) * (size_t)N);
   if (h->arena_cap < A.host.size()) {
@@ -482,7 +512,7 @@ extern "C" int rthx_create(rthx_handle** out, const rthx_mesh* m, int device_id)
   P.cell_mid = (const double*)(b8 + o_mid); P.cell_volume = (const double*)(b8 + o_vol);
   P.cell_surf_id = (const int32_t*)(b8 + o_surf); P.beta = (const double*)(b8 + o_beta); P.uniform_beta = (const double*)(b8 + o_ub);
   P.omega = (const double*)(b8 + o_omega); P.eps = (const double*)(b8 + o_eps);
-  P.lattice = (const int32_t*)(b8 + o_lat); P.em_cell = (const int32_t*)(b8 + o_ec); P.em_wall = (const int32_t*)(b8 + o_ew);
+  P.lattice = (const int32_t*)(b8 + o_lat); P.abs_tab = (const int32_t*)(b8 + o_abs); P.em_cell = (const int32_t*)(b8 + o_ec); P.em_wall = (const int32_t*)(b8 + o_ew);
   P.em_coarse = (const int32_t*)(b8 + o_eco);
   h->bins_dev = (int32_t*)(b8 + o_bins); h->bins_cap = (size_t)nb * 4 + 16;
   h->rec_slot_dev = (int32_t*)(b8 + o_rec);
@@ -557,8 +587,9 @@ LaunchPlan make_plan(const rthx_handle* h, const rthx_trace_args* a, int rank, i
     const size_t base = (pl.smem_bytes + 15) & ~size_t(15);
     const size_t per_depth = (size_t)pl.block_threads * 40;
     const size_t budget = (size_t)h->prop.sharedMemPerMultiprocessor / 4 - 1024;
-    int depth = base < budget ? (int)std::min<size_t>(8, (budget - base) / per_depth) : 0;
-    if (const char* ev = std::getenv("RTHX_QUEUE_DEPTH")) { const int v = std::atoi(ev); if (v >= 0 && v <= 16) depth = v; }
+    int depth = base < budget ? (int)std::min<size_t>(4, (budget - base) / per_depth) : 0;
+    if (const char* ev = std::getenv("RTHX_QUEUE_DEPTH")) { const int v = std::atoi(ev); if (v >= 0 && v <= 4) depth = v; }
+    if (depth == 3) depth = 2;                       // compiled depths: 1, 2, 4 rays per lane and batch
     if (depth >= 1 && base + depth * per_depth <= h->prop.sharedMemPerBlockOptin) {
       pl.minb = 6; pl.queue_depth = depth; pl.smem_bytes = base + depth * per_depth;
     }
@@ -567,7 +598,7 @@ LaunchPlan make_plan(const rthx_handle* h, const rthx_trace_args* a, int rank, i
   long long chunks = a->row_chunks;
   if (chunks <= 0) {
     // enough blocks for ~32 waves of the resident set, but keep >= 2048 rays (and >= N/2, the flush scan) per block
-    const int per_sm = std::max(1, trace_kernel_max_blocks_per_sm(pl.block_threads, pl.smem_bytes, pl.hist_in_smem != 0, pl.fast != 0, pl.minb, pl.multi != 0, pl.sq != 0));
+    const int per_sm = std::max(1, trace_kernel_max_blocks_per_sm(pl.block_threads, pl.smem_bytes, pl.hist_in_smem != 0, pl.fast != 0, pl.minb, pl.multi != 0, pl.sq != 0, pl.queue_depth));
     const long long target = (long long)h->prop.multiProcessorCount * per_sm * 32;
     chunks = rows > 0 ? (target + rows - 1) / rows : 1;
     const long long min_rays = std::max<long long>(2048, h->N / 2);
@@ -701,7 +732,7 @@ int pipeline_launch(rthx_handle* h, const rthx_trace_args* a, int rank, int worl
   CU(h, ensure(&h->counts_dev, &h->counts_cap, (size_t)a->n_bins * (size_t)n_owned * N));
   LaunchPlan pl = make_plan(h, a, rank, world);
   // batches: >= ~6 waves of resident blocks each, at most 16
-  const int per_sm = std::max(1, trace_kernel_max_blocks_per_sm(pl.block_threads, pl.smem_bytes, pl.hist_in_smem != 0, pl.fast != 0, pl.minb, pl.multi != 0, pl.sq != 0));
+  const int per_sm = std::max(1, trace_kernel_max_blocks_per_sm(pl.block_threads, pl.smem_bytes, pl.hist_in_smem != 0, pl.fast != 0, pl.minb, pl.multi != 0, pl.sq != 0, pl.queue_depth));
   const long long resident = (long long)h->prop.multiProcessorCount * per_sm;
   int n_batches = (int)std::min<long long>(16, std::max<long long>(1, pl.n_blocks / (6 * resident)));
   n_batches = std::max(1, std::min(n_batches, n_owned));

@@ -14,6 +14,7 @@ struct alignas(16) CoarseDev {
   double vx[4], vy[4];   // CCW vertices
   double nx[4], ny[4];   // unit outward edge normals (the reference's `inwardNormals`, calculateInwardNormal.jl:1-12)
   double h[4];           // plane offsets: quads h0 = v0·n0, h1 = v1·n1, h2 = v2·n0, h3 = v3·n1 (slab form); else h_i = v_i·n_i
+  double cen[2], hw[2];  // quads: centre line (h_a + h_{a+2})/2 and half width (h_a - h_{a+2})/2 of the edge pair with normal n_a
   // affine lattice inverse (kinds 1,2): s = (p-a)·g1, t = (p-a)·g2, lattice cell (floor s, floor t) in [0,Nx)x[0,Ny)
   double ax, ay, g1x, g1y, g2x, g2y;
   int32_t nv;
@@ -24,7 +25,7 @@ struct alignas(16) CoarseDev {
   int32_t diag;          // kind 2: 0-based coarse edge that is the cut diagonal, else -1
   int32_t nbr[4];        // coarse face across edge k (-1: locate generically / none)
   uint8_t solid[4];
-  int32_t pad_;
+  int32_t abs_off;       // kinds 1,2: first row of this face in the absorber table (5 entries per lattice cell), else -1
 };
 static_assert(sizeof(CoarseDev) % 16 == 0, "CoarseDev must stay a multiple of 16 bytes (shared-memory layout behind it)");
 
@@ -58,6 +59,7 @@ struct TraceParams {
   const double* omega;         // [n_bands*n_cells]    scattering albedo sigma_s/(kappa+sigma_s)   (MULTI_BOUNCE)
   const double* eps;           // [n_bands*n_surfaces] wall emissivity                              (MULTI_BOUNCE)
   const int32_t* lattice;      // lattice -> local fine index tables (kind 2)
+  const int32_t* abs_tab;      // affine faces: [lattice cell][gas | wall on coarse edge 0..3] -> absorber index or -1
   const int32_t* em_cell;      // [N]
   const int32_t* em_wall;      // [N]  -1 for volume emitters
   const int32_t* em_coarse;    // [N]
@@ -107,10 +109,10 @@ struct TraceParams {
 
 // launchers implemented in rthx_kernels.cu
 cudaError_t launch_trace_exchange(const TraceParams& p, int n_blocks, int block_threads, size_t smem_bytes, bool fast, int minb, bool sq,
-                                  cudaStream_t stream);
+                                  cudaStream_t stream);   // minb == 6: the queue kernel with p.queue_depth in {1, 2, 4}
 cudaError_t configure_trace_kernel(size_t smem_bytes);
 cudaError_t launch_fp64_peak(double* out, int n_blocks, int block_threads, int iters, cudaStream_t stream);
-int trace_kernel_max_blocks_per_sm(int block_threads, size_t smem_bytes, bool hist, bool fast, int minb, bool multi, bool sq);
+int trace_kernel_max_blocks_per_sm(int block_threads, size_t smem_bytes, bool hist, bool fast, int minb, bool multi, bool sq, int queue_depth = 0);
 
 // ---- grey equilibrium solve (rthx_solve.cu) ---------------------------------------------------------------------
 struct SolveMatrix {

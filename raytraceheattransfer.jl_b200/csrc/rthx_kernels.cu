@@ -99,6 +99,15 @@ __device__ __forceinline__ double sqrt_pos(double x) {
   const double e = fma(-g, y, 1.0);
   return fma(fma(e, 0.375, 0.5), g * e, g);                 // g (1 + e/2 + 3 e^2/8): ~2^-58; 5 FP64 instructions
 }
+// a / |b|: the magnitude is taken on the high word (integer pipe); MUFU.RCP64H reads only that word
+__device__ __forceinline__ double div_pos_abs(double a, double b) {
+  const double ba = __hiloint2double(__double2hiint(b) & 0x7FFFFFFF, __double2loint(b));
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(ba));
+  r = fma(r, fma(-ba, r, 1.0), r);
+  const double q = a * r;
+  return fma(r, fma(-ba, q, a), q);
+}
 __device__ __forceinline__ double div_pos(double a, double b) {
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));     // MUFU.RCP64H: ~2^-20 relative
@@ -120,6 +129,19 @@ __device__ __forceinline__ double cos2pi_centered(double y) {
   double p = c_sinpi2[8];
 #pragma unroll
   for (int k = 7; k >= 0; --k) p = fma(p, w, c_sinpi2[k]);
+  return z * p;
+}
+// 2 cos(2 pi R): the same coefficients times two (exact), for sin(theta) = 2 sqrt(R (1 - R))
+__constant__ double c_sinpi4[9] = {
+    0x1.921fb54442d18p+1 * 0x1p2, -0x1.4abbce625be52p+2 * 0x1p4, 0x1.466bc6775aa7dp+1 * 0x1p6, -0x1.32d2cce627c86p-1 * 0x1p8,
+    0x1.5078348551854p-4 * 0x1p10, -0x1.e3074dfaf87afp-8 * 0x1p12, 0x1.e8f3675ee37ddp-12 * 0x1p14, -0x1.6f7acdb8f6580p-16 * 0x1p16,
+    0x1.9d462020fcc78p-21 * 0x1p18};
+__device__ __forceinline__ double cos2pi_centered_x2(double y) {
+  const double z = fabs(y) - 0.25;
+  const double w = z * z;
+  double p = c_sinpi4[8];
+#pragma unroll
+  for (int k = 7; k >= 0; --k) p = fma(p, w, c_sinpi4[k]);
   return z * p;
 }
 // u32 uniform minus 1/2, exact: [1,2) - (3/2 - 2^-33)
@@ -604,13 +626,83 @@ __device__ __forceinline__ uint32_t selector_threshold(double a) {
   return (uint32_t)((unsigned long long)t - 1ull);
 }
 
+// Block prologue of the SQ / queue kernels (one thread): the emitter description with the emission nudge
+// p + (mid - p) nu (emitSurfaceRay2D.jl:10, emitVolumeRay2D.jl:22) folded into the geometry, so that no per-ray instruction is
+// spent on it:  surface  p = [(1-nu) p1 + nu mid] + R [(1-nu) (p2 - p1)];  volume  p = [(1-nu) V0 + nu mid] + a1 [(1-nu) (V1-V0)] + ...
+// (positions equal the unfolded form to 1 ulp).
+//   surface emitter: [0,1] origin, [2,3] edge, [4,5] xVecLocal (unit edge), [6,7] yVecLocal (left normal)
+//   volume emitter : [0..5] triangle ABC as (V0, V1-V0, V2-V0), [6..11] triangle CDA likewise, [14] area(ABC)/volume,
+//                    [15] (as u32) the integer triangle selector
+__device__ __forceinline__ void stage_emitter_folded(const TraceParams& p, int g, int wall, double* s_em) {
+  const int em_nv = p.poly_nv[g];
+  const double* vx = p.poly_vx + 4 * g;
+  const double* vy = p.poly_vy + 4 * g;
+  const double omn = 1.0 - p.nudge, mxn = p.cell_mid[2 * g] * p.nudge, myn = p.cell_mid[2 * g + 1] * p.nudge;
+  if (wall >= 0) {
+    const int j = (wall + 1 == em_nv) ? 0 : wall + 1;
+    const double ex = vx[j] - vx[wall], ey = vy[j] - vy[wall];
+    const double len = sqrt(ex * ex + ey * ey);
+    s_em[0] = fma(vx[wall], omn, mxn); s_em[1] = fma(vy[wall], omn, myn); s_em[2] = ex * omn; s_em[3] = ey * omn;
+    s_em[4] = ex / len; s_em[5] = ey / len;
+    s_em[6] = -(ey / len); s_em[7] = ex / len;
+  } else {
+    s_em[0] = vx[0]; s_em[1] = vy[0]; s_em[2] = vx[1] - vx[0]; s_em[3] = vy[1] - vy[0]; s_em[4] = vx[2] - vx[0]; s_em[5] = vy[2] - vy[0];
+    s_em[6] = vx[2]; s_em[7] = vy[2]; s_em[8] = vx[3] - vx[2]; s_em[9] = vy[3] - vy[2]; s_em[10] = vx[0] - vx[2]; s_em[11] = vy[0] - vy[2];
+    s_em[14] = em_nv == 3 ? 2.0 : 0.5 * (vx[0] * (vy[1] - vy[2]) + vx[1] * (vy[2] - vy[0]) + vx[2] * (vy[0] - vy[1])) / p.cell_volume[g];
+    reinterpret_cast<uint32_t*>(s_em + 15)[0] = selector_threshold(s_em[14]);
+    for (int t = 0; t < 12; t += 6) {
+      s_em[t] = fma(s_em[t], omn, mxn); s_em[t + 1] = fma(s_em[t + 1], omn, myn);
+      for (int q = 2; q < 6; ++q) s_em[t + q] *= omn;
+    }
+  }
+}
+
+// Stage 1 for one ray from its eight Philox words: emission point (nudge included), in-plane direction and the free-path
+// variate.  dy_m is a double of magnitude |dy| and dy_hi the high word of dy: the volume sampler holds -dy = 2R - 1 and leaves
+// the negation to the consumers (an operand modifier in FP64 instructions, one xor where the sign bit is read).
+template <bool SURF>
+__device__ __forceinline__ void emit_ray_folded(const TraceParams& p, const double* __restrict__ s_em, uint32_t sel_thr, const uint4& w0, const uint4& w1,
+                                                double& px, double& py, double& dx, double& dy, double& dy_m, int& dy_hi, double& R_S) {
+  if (SURF) {
+    const double R = u32d(w0.x, p.k_u32);
+    px = fma(s_em[2], R, s_em[0]);
+    py = fma(s_em[3], R, s_em[1]);
+    // lambertSample2D: Float32 variates / sqrt / square, the rest in Float64
+    const float cosT = __fsqrt_rn(u23(w0.y));
+    const float cos2 = __fmul_rn(cosT, cosT);
+    const double sinT = sqrt_pos(1.0 - (double)cos2);
+    const double xdir = sinT * cos2pi_centered((double)u23(w0.z) - 0.5);
+    const double zdir = (double)cosT;
+    dx = s_em[4] * xdir + s_em[6] * zdir;
+    dy = s_em[5] * xdir + s_em[7] * zdir;
+    dy_m = dy;
+    dy_hi = __double2hiint(dy);
+    R_S = u52(w1.x, w1.y, p.k_u52);
+  } else {
+    const double R1 = u32d(w0.x, p.k_u32), R2 = u32d(w0.y, p.k_u32);
+    const double sq = sqrt_pos(R1);
+    // triangle ABC or CDA (emitVolumeRay2D.jl:7): (w + 1/2) 2^-32 < area(ABC)/area  <=>  w <= thr, an integer compare
+    const double* tri = s_em + ((w0.z <= sel_thr) ? 0 : 6);
+    const double a2 = sq * R2, a1 = sq - a2;
+    px = fma(a2, tri[4], fma(a1, tri[2], tri[0]));
+    py = fma(a2, tri[5], fma(a1, tri[3], tri[1]));
+    // theta = acos(1 - 2R): with c = R - 1/2 (one DADD from the mantissa injection), cos = -2c and sin = 2 sqrt(1/4 - c^2);
+    // 1/4 - c^2 = R (1 - R) exactly, so one fma rounds to the same double as the product did
+    const double c = __hiloint2double((int)(0x3FF00000u | (w1.y >> 12)), (int)((w1.y << 20) | (w1.x >> 12))) - p.k_u52c;
+    dx = sqrt_pos(fma(-c, c, 0.25)) * cos2pi_centered_x2(u32d_centered(w0.w, p.k_u32c));
+    dy_m = c + c;
+    dy = -dy_m;
+    dy_hi = __double2hiint(dy_m) ^ (int)0x80000000;
+    R_S = u52(w1.z, w1.w, p.k_u52);
+  }
+}
+
 struct SqBlock {            // block-uniform state of one (emitter row, band, chunk)
   const double* s_em;       // emitter description (shared memory, EM_DOUBLES)
   const double2* s_log;     // -log table (shared memory)
   uint32_t* hist;           // row histogram (shared memory)
   const double* beta_band;  // per-cell beta of the band (non-uniform bins)
   double inv_beta_u;
-  double midx_n, midy_n;    // cell midPoint * nudge
   uint32_t sel_thr;         // volume emitters: take triangle ABC iff Philox word <= sel_thr
   uint32_t e, cw;
   int64_t ray0;             // ray id of the block's first ray
@@ -640,32 +732,33 @@ __device__ __forceinline__ double flip_sign(double x, int sign_src_hi) {   // x 
 // AXIS: n0 = (0, +-1), n1 = (+-1, 0): d.n0 = +-dy, p.n0 = +-py — the four dot products disappear (bit-identical results).
 // Returns false when no edge lies ahead (the reference's u = Inf).
 template <bool AXIS>
-__device__ __forceinline__ bool dist_sq(const TraceParams& p, double px, double py, double dx, double dy, double& u, int& k) {
+__device__ __forceinline__ bool dist_sq(const TraceParams& p, double px, double py, double dx, double dy, double dy_m, int dy_hi, double& u, int& k) {
   const CoarseDev& f = p.face0;
-  double ad0, ad1, tf0, tf1;
+  double d0, d1, tf0, tf1;                        // d.n0, d.n1 up to sign (only |.| is used), sign(d.n_a) (p.n_a - cen_a)
   int s0, s1;                                     // high words carrying the sign of d.n0, d.n1
   if (AXIS) {
-    s0 = __double2hiint(dy) ^ (int)p.sq_flip0; s1 = __double2hiint(dx) ^ (int)p.sq_flip1;
-    ad0 = fabs(dy); ad1 = fabs(dx);
-    tf0 = flip_sign(py - p.sq_cy, __double2hiint(dy));    // sign(d.n0) (p.n0 - cen0) = sign(dy) (py - n0y cen0)
+    // dy_m: any double of magnitude |dy|, dy_hi: the high word of dy (a caller that holds -dy passes it with the flipped word
+    // and saves the negation: only |d.n0| and its sign are used here)
+    s0 = dy_hi ^ (int)p.sq_flip0; s1 = __double2hiint(dx) ^ (int)p.sq_flip1;
+    d0 = dy_m; d1 = dx;
+    tf0 = flip_sign(py - p.sq_cy, dy_hi);         // sign(d.n0) (p.n0 - cen0) = sign(dy) (py - n0y cen0)
     tf1 = flip_sign(px - p.sq_cx, __double2hiint(dx));
   } else {
-    const double den0 = fma(dx, f.nx[0], dy * f.ny[0]), den1 = fma(dx, f.nx[1], dy * f.ny[1]);
-    s0 = __double2hiint(den0); s1 = __double2hiint(den1);
-    ad0 = fabs(den0); ad1 = fabs(den1);
+    d0 = fma(dx, f.nx[0], dy * f.ny[0]); d1 = fma(dx, f.nx[1], dy * f.ny[1]);
+    s0 = __double2hiint(d0); s1 = __double2hiint(d1);
     tf0 = flip_sign(fma(px, f.nx[0], fma(py, f.ny[0], -p.sq_cen0)), s0);
     tf1 = flip_sign(fma(px, f.nx[1], fma(py, f.ny[1], -p.sq_cen1)), s1);
   }
   const double an0 = p.sq_hw0 - tf0, an1 = p.sq_hw1 - tf1;
   // an > 0 by the high word: exact except for 0 < an < 2^-1022
-  const bool ok0 = (ad0 >= p.k_eps) & (__double2hiint(an0) > 0), ok1 = (ad1 >= p.k_eps) & (__double2hiint(an1) > 0);
+  const bool ok0 = (fabs(d0) >= p.k_eps) & (__double2hiint(an0) > 0), ok1 = (fabs(d1) >= p.k_eps) & (__double2hiint(an1) > 0);
   const int e0 = s0 < 0 ? 2 : 0, e1 = s1 < 0 ? 3 : 1;
-  const double l = an0 * ad1, r = an1 * ad0;
+  const double l = an0 * fabs(d1), r = an1 * fabs(d0);
   const bool take0 = ok0 & (!ok1 | (l < r) | ((l == r) & (e0 < e1)));
   k = take0 ? e0 : e1;
-  const double an = take0 ? an0 : an1, ad = take0 ? ad0 : ad1;
+  const double an = take0 ? an0 : an1, ad = take0 ? d0 : d1;   // |ad| enters the division as an operand modifier
   const bool any = ok0 | ok1;
-  u = any ? div_pos(an, ad) : CUDART_INF;
+  u = any ? div_pos_abs(an, ad) : CUDART_INF;
   return any;
 }
 
@@ -685,37 +778,9 @@ __device__ __forceinline__ unsigned int sq_ray_loop(const TraceParams& p, const 
   }
   for (uint32_t i = threadIdx.x; i < b.n_rays; i += blockDim.x) {
     const uint4 w0 = w0n, w1 = w1n;
-    double px, py, dx, dy, R_S;
-    if (SURF) {
-      const double R = u32d(w0.x, p.k_u32);
-      px = fma(b.s_em[2], R, b.s_em[0]);
-      py = fma(b.s_em[3], R, b.s_em[1]);
-      const float cosT = __fsqrt_rn(u23(w0.y));
-      const float cos2 = __fmul_rn(cosT, cosT);
-      const double sinT = sqrt_pos(1.0 - (double)cos2);
-      const double xdir = sinT * cos2pi_centered((double)u23(w0.z) - 0.5);
-      const double zdir = (double)cosT;
-      dx = b.s_em[4] * xdir + b.s_em[6] * zdir;
-      dy = b.s_em[5] * xdir + b.s_em[7] * zdir;
-      R_S = u52(w1.x, w1.y, p.k_u52);
-    } else {
-      const double R1 = u32d(w0.x, p.k_u32), R2 = u32d(w0.y, p.k_u32);
-      const double sq = sqrt_pos(R1);
-      // triangle ABC or CDA (emitVolumeRay2D.jl:7): (w + 1/2) 2^-32 < area(ABC)/area  <=>  w <= thr, an integer compare
-      const double* tri = b.s_em + ((w0.z <= b.sel_thr) ? 0 : 6);
-      const double a2 = sq * R2, a1 = sq - a2;
-      px = fma(a2, tri[4], fma(a1, tri[2], tri[0]));
-      py = fma(a2, tri[5], fma(a1, tri[3], tri[1]));
-      // theta = acos(1 - 2R): with c = R - 1/2 (one DADD from the mantissa injection), cos = -2c and sin = 2 sqrt(1/4 - c^2);
-      // 1/4 - c^2 = R (1 - R) exactly, so one fma rounds to the same double as the product did
-      const double c = __hiloint2double((int)(0x3FF00000u | (w1.y >> 12)), (int)((w1.y << 20) | (w1.x >> 12))) - p.k_u52c;
-      const double sinH = sqrt_pos(fma(-c, c, 0.25));
-      dx = (sinH + sinH) * cos2pi_centered(u32d_centered(w0.w, p.k_u32c));
-      dy = -(c + c);
-      R_S = u52(w1.z, w1.w, p.k_u52);
-    }
-    px = fma(px, p.sq_one_m_nudge, b.midx_n);      // p + (mid - p) nudge  (emitSurfaceRay2D.jl:10, emitVolumeRay2D.jl:22)
-    py = fma(py, p.sq_one_m_nudge, b.midy_n);
+    double px, py, dx, dy, dy_m, R_S;
+    int dy_hi;
+    emit_ray_folded<SURF>(p, b.s_em, b.sel_thr, w0, w1, px, py, dx, dy, dy_m, dy_hi, R_S);
     if (REC) {
       double* o = p.rec_pts + 4 * (b.rec_base + i);
       o[0] = px; o[1] = py;
@@ -723,7 +788,7 @@ __device__ __forceinline__ unsigned int sq_ray_loop(const TraceParams& p, const 
     const double neg_log = neg_log_table(R_S, b.s_log);
     int k;
     double u;
-    const bool edge = dist_sq<AXIS>(p, px, py, dx, dy, u, k);
+    const bool edge = dist_sq<AXIS>(p, px, py, dx, dy, dy_m, dy_hi, u, k);
     double S;
     bool gas, ok = true;
     if (UNIFORM) {
@@ -792,25 +857,7 @@ __global__ void __launch_bounds__(256, MINB) trace_exchange_sq_kernel(const __gr
   const int g = p.em_cell[e];
   const int wall = p.em_wall[e];
   const bool is_surface = wall >= 0;
-  if (threadIdx.x == 0) {
-    const int em_nv = p.poly_nv[g];
-    const double* vx = p.poly_vx + 4 * g;
-    const double* vy = p.poly_vy + 4 * g;
-    if (is_surface) {
-      const int j = (wall + 1 == em_nv) ? 0 : wall + 1;
-      const double ex = vx[j] - vx[wall], ey = vy[j] - vy[wall];
-      const double len = sqrt(ex * ex + ey * ey);
-      s_em[0] = vx[wall]; s_em[1] = vy[wall]; s_em[2] = ex; s_em[3] = ey;
-      s_em[4] = ex / len; s_em[5] = ey / len;
-      s_em[6] = -(ey / len); s_em[7] = ex / len;
-    } else {
-      s_em[0] = vx[0]; s_em[1] = vy[0]; s_em[2] = vx[1] - vx[0]; s_em[3] = vy[1] - vy[0]; s_em[4] = vx[2] - vx[0]; s_em[5] = vy[2] - vy[0];
-      s_em[6] = vx[2]; s_em[7] = vy[2]; s_em[8] = vx[3] - vx[2]; s_em[9] = vy[3] - vy[2]; s_em[10] = vx[0] - vx[2]; s_em[11] = vy[0] - vy[2];
-      s_em[14] = em_nv == 3 ? 2.0 : 0.5 * (vx[0] * (vy[1] - vy[2]) + vx[1] * (vy[2] - vy[0]) + vx[2] * (vy[0] - vy[1])) / p.cell_volume[g];
-      reinterpret_cast<uint32_t*>(s_em + 15)[0] = selector_threshold(s_em[14]);
-    }
-    s_em[12] = p.cell_mid[2 * g] * p.nudge; s_em[13] = p.cell_mid[2 * g + 1] * p.nudge;
-  }
+  if (threadIdx.x == 0) stage_emitter_folded(p, g, wall, s_em);
 
   const int64_t per = (p.rays_per_emitter + p.row_chunks - 1) / p.row_chunks;
   const int64_t r_begin = (int64_t)chunk * per;
@@ -829,7 +876,6 @@ __global__ void __launch_bounds__(256, MINB) trace_exchange_sq_kernel(const __gr
   SqBlock b;
   b.s_em = s_em; b.s_log = s_log; b.hist = hist; b.beta_band = beta_band;
   b.inv_beta_u = beta_u > 0.0 ? 1.0 / beta_u : CUDART_INF;
-  b.midx_n = s_em[12]; b.midy_n = s_em[13];
   b.sel_thr = reinterpret_cast<const uint32_t*>(s_em + 15)[0];
   b.e = (uint32_t)e; b.cw = ((uint32_t)band << 16);
   b.ray0 = p.ray_id_offset + r_begin;
@@ -874,90 +920,109 @@ struct QueueBlock {          // block-uniform state of one (emitter row, band, c
   const double* s_em;
   const double2* s_log;
   uint32_t* hist;
-  double* q;                 // this warp's queue: px | py | dx | dy | -log R, `wq` doubles each
+  double* q;                 // this warp's queue, structure of arrays: px | py | dx | dy | S (or -log R), 32*DEPTH doubles each
   const double* beta_band;
   double inv_beta_u;
   int64_t r_begin, r_end;    // ray range of the block
   size_t rec_row;            // first recorder slot of the emitter row
-  uint32_t e, cw;
-  int c0, wq, n_warps, warp, lane, is_surface;
+  uint32_t e, cw, sel_thr;
+  int c0, n_warps, warp, lane;
 };
 
-template <bool UNIFORM, bool REC>
+// distToSurface2D on a coarse face of the queue kernel (the point is inside the face).
+//   parallelogram: slab form about the centre lines as in dist_sq, descriptor fields cen[] / hw[];
+//   triangle     : three edges, hit only when moving outward (d.n_i >= eps) with a positive plane distance.
+// Sign tests run on the high words, the argmin on cross-multiplied fractions (first index on ties), one division at the end.
+__device__ __forceinline__ bool dist_face(const CoarseDev& f, double px, double py, double dx, double dy, double eps, double& u, int& k) {
+  if (f.kind == KIND_AFFINE_QUAD) {
+    const double d0 = fma(dx, f.nx[0], dy * f.ny[0]), d1 = fma(dx, f.nx[1], dy * f.ny[1]);
+    const int s0 = __double2hiint(d0), s1 = __double2hiint(d1);
+    const double tf0 = flip_sign(fma(px, f.nx[0], fma(py, f.ny[0], -f.cen[0])), s0);
+    const double tf1 = flip_sign(fma(px, f.nx[1], fma(py, f.ny[1], -f.cen[1])), s1);
+    const double an0 = f.hw[0] - tf0, an1 = f.hw[1] - tf1;
+    const bool ok0 = (fabs(d0) >= eps) & (__double2hiint(an0) > 0), ok1 = (fabs(d1) >= eps) & (__double2hiint(an1) > 0);
+    const int e0 = s0 < 0 ? 2 : 0, e1 = s1 < 0 ? 3 : 1;
+    const double l = an0 * fabs(d1), r = an1 * fabs(d0);
+    const bool take0 = ok0 & (!ok1 | (l < r) | ((l == r) & (e0 < e1)));
+    k = take0 ? e0 : e1;
+    const double an = take0 ? an0 : an1, ad = take0 ? d0 : d1;
+    const bool any = ok0 | ok1;
+    u = any ? div_pos_abs(an, ad) : CUDART_INF;
+    return any;
+  }
+  double bn = 1.0, bd = 0.0;
+  int bk = 0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const double nx = f.nx[i], ny = f.ny[i];
+    const double den = fma(dx, nx, dy * ny);
+    const double num = f.h[i] - fma(px, nx, py * ny);
+    const bool better = (den >= eps) & (__double2hiint(num) > 0) & (num * bd < bn * den);
+    bn = better ? num : bn;
+    bd = better ? den : bd;
+    bk = better ? i : bk;
+  }
+  k = bk;
+  const bool any = __double2hiint(bd) > 0;
+  u = any ? div_pos(bn, bd) : CUDART_INF;
+  return any;
+}
+
+// lattice cell n + m Nx of a point in an affine coarse face, or -1 (one unsigned compare per axis, see locate_sq)
+__device__ __forceinline__ int lattice_cell(const CoarseDev& cf, double px, double py) {
+  const double rx = px - cf.ax, ry = py - cf.ay;
+  const double s = fma(rx, cf.g1x, ry * cf.g1y), t = fma(rx, cf.g2x, ry * cf.g2y);
+  const int n = __double2int_rd(s), m = __double2int_rd(t);
+  return (((unsigned)n < (unsigned)cf.Nx) & ((unsigned)m < (unsigned)cf.Ny)) ? n + m * cf.Nx : -1;
+}
+
+template <bool SURF, bool UNIFORM, bool REC, int DEPTH>
 __device__ __forceinline__ unsigned int queue_ray_loop(const TraceParams& p, const QueueBlock& b) {
-  const int wq = b.wq, lane = b.lane;
-  double* q_px = b.q;
-  double* q_py = q_px + wq;
-  double* q_dx = q_py + wq;
-  double* q_dy = q_dx + wq;
-  double* q_nl = q_dy + wq;
+  constexpr int WQ = 32 * DEPTH;                       // queue slots per warp
+  const int lane = b.lane;
+  double* const q = b.q;                               // field f of slot s at q[f * WQ + s]
   const unsigned lt_mask = (1u << lane) - 1u;
   unsigned int n_lost = 0;
   // in-flight ray of this lane (lives in registers across queue refills)
   bool active = false;
-  double px = 0.0, py = 0.0, dx = 0.0, dy = 0.0, neg_log = 0.0, S = 0.0, acc = 0.0;
+  double px = 0.0, py = 0.0, dx = 0.0, dy = 0.0, S = 0.0, acc = 0.0;   // S: remaining free path (UNIFORM) or -log R
   int c = b.c0, it = 0;
-  int64_t r_cur = 0;                                   // ray index of the in-flight ray (recorder slot)
-  // the warp's rays: batch j of the block covers [r_begin + j*n_warps*wq, ...), this warp takes its wq-slice of every batch
-  int64_t rb = b.r_begin + (int64_t)b.warp * wq;
-  const int64_t stride = (int64_t)b.n_warps * wq;
+  uint32_t r_cur = 0;                                  // ray index of the in-flight ray relative to r_begin (recorder slot)
+  // the warp's rays: batch j of the block covers [r_begin + j*n_warps*WQ, ...), this warp takes its WQ-slice of every batch
+  int64_t rb = b.r_begin + (int64_t)b.warp * WQ;
+  const int64_t stride = (int64_t)b.n_warps * WQ;
   while (true) {
     // ---- stage 1: emission at full occupancy into the warp's queue ----------------------------------------------------
-    const int n_valid = rb < b.r_end ? (int)min((int64_t)wq, b.r_end - rb) : 0;
+    const int n_valid = rb < b.r_end ? (int)min((int64_t)WQ, b.r_end - rb) : 0;
+#pragma unroll 1
     for (int s = lane; s < n_valid; s += 32) {
       const uint64_t ray_id = (uint64_t)(p.ray_id_offset + rb + s);
       const uint32_t c_lo = (uint32_t)ray_id, c_hi = (uint32_t)(ray_id >> 32);
       const uint4 w0 = philox4x32_10_rk(make_uint4(c_lo, c_hi, b.e, b.cw | 0u), p.rk);
       const uint4 w1 = philox4x32_10_rk(make_uint4(c_lo, c_hi, b.e, b.cw | 1u), p.rk);
-      double ex, ey, fx, fy, R_S;
-      if (b.is_surface) {
-        const double R = u32d(w0.x, p.k_u32);
-        ex = fma(b.s_em[2], R, b.s_em[0]);
-        ey = fma(b.s_em[3], R, b.s_em[1]);
-        const float cosT = __fsqrt_rn(u23(w0.y));
-        const float cos2 = __fmul_rn(cosT, cosT);
-        const double sinT = sqrt_pos(1.0 - (double)cos2);
-        const double xdir = sinT * cos2pi_unit((double)u23(w0.z));
-        const double zdir = (double)cosT;
-        fx = b.s_em[4] * xdir + b.s_em[6] * zdir;
-        fy = b.s_em[5] * xdir + b.s_em[7] * zdir;
-        R_S = u52(w1.x, w1.y, p.k_u52);
-      } else {
-        const double R1 = u32d(w0.x, p.k_u32), R2 = u32d(w0.y, p.k_u32);
-        const double sq = sqrt_pos(R1);
-        const double* tri = b.s_em + ((u32d(w0.z, p.k_u32) < b.s_em[14]) ? 0 : 6);
-        const double a2 = sq * R2, a1 = sq - a2;
-        ex = fma(a2, tri[4], fma(a1, tri[2], tri[0]));
-        ey = fma(a2, tri[5], fma(a1, tri[3], tri[1]));
-        const double Rt = u52(w1.x, w1.y, p.k_u52);
-        const double sinT = 2.0 * sqrt_pos(Rt * (1.0 - Rt));
-        fx = sinT * cos2pi_unit(u32d(w0.w, p.k_u32));
-        fy = fma(Rt, -2.0, 1.0);
-        R_S = u52(w1.z, w1.w, p.k_u52);
-      }
-      ex = fma(b.s_em[12] - ex, p.nudge, ex);
-      ey = fma(b.s_em[13] - ey, p.nudge, ey);
+      double ex, ey, fx, fy, fy_m, R_S;
+      int fy_hi;
+      emit_ray_folded<SURF>(p, b.s_em, b.sel_thr, w0, w1, ex, ey, fx, fy, fy_m, fy_hi, R_S);
       if (REC) {
         double* o = p.rec_pts + 4 * (b.rec_row + (size_t)(rb + s));
         o[0] = ex; o[1] = ey;
       }
-      q_px[s] = ex; q_py[s] = ey; q_dx[s] = fx; q_dy[s] = fy; q_nl[s] = neg_log_table(R_S, b.s_log);
+      const double nl = neg_log_table(R_S, b.s_log);
+      q[s] = ex; q[WQ + s] = ey; q[2 * WQ + s] = fx; q[3 * WQ + s] = fy; q[4 * WQ + s] = UNIFORM ? nl * b.inv_beta_u : nl;
     }
     __syncwarp();
     const bool last_batch = rb + stride >= b.r_end;    // nothing left to emit after this queue
+    const uint32_t rb_rel = (uint32_t)(rb - b.r_begin);
     // ---- stage 2: traversal; idle lanes take queue slots by warp vote --------------------------------------------------
     int next = 0;
     while (true) {
       // refill: every lane without a ray takes the next unprocessed slot
       const unsigned need = __ballot_sync(0xffffffffu, !active);
-      if (!active) {
-        const int idx = next + __popc(need & lt_mask);
-        if (idx < n_valid) {
-          px = q_px[idx]; py = q_py[idx]; dx = q_dx[idx]; dy = q_dy[idx]; neg_log = q_nl[idx];
-          S = UNIFORM ? neg_log * b.inv_beta_u : 0.0;
-          acc = 0.0; c = b.c0; it = 0; r_cur = rb + idx;
-          active = true;
-        }
+      const int idx = next + __popc(need & lt_mask);
+      if (!active & (idx < n_valid)) {
+        px = q[idx]; py = q[WQ + idx]; dx = q[2 * WQ + idx]; dy = q[3 * WQ + idx]; S = q[4 * WQ + idx];
+        acc = 0.0; c = b.c0; it = 0; r_cur = rb_rel + (uint32_t)idx;
+        active = true;
       }
       next += __popc(need);
       const unsigned busy = __ballot_sync(0xffffffffu, active);
@@ -969,26 +1034,28 @@ __device__ __forceinline__ unsigned int queue_ray_loop(const TraceParams& p, con
       if (active) {
         const CoarseDev& cf = b.coarse[c];
         int k;
-        const double u = dist_fast(cf, px, py, dx, dy, p.k_eps, k);
+        double u;
+        const bool edge = dist_face(cf, px, py, dx, dy, p.k_eps, u, k);  // an edge lies ahead
         bool gas, ok = true;
-        double tau_b = 0.0;
+        double tau_b = 0.0, Sg;
         if (UNIFORM) {
           gas = S < u;
+          Sg = S;
         } else {
-          const int f0 = locate_affine(p, cf, px, py);                  // traceRay.jl:87-100
+          const int l0 = lattice_cell(cf, px, py);                      // traceRay.jl:87-100
+          const int f0 = l0 < 0 ? -1 : (cf.kind == KIND_AFFINE_QUAD ? l0 : __ldg(p.lattice + cf.lat_off + l0));
           ok = f0 >= 0;
           const double local_beta = ok ? b.beta_band[cf.fine_off + f0] : 0.0;
           tau_b = local_beta * u;
-          gas = acc + tau_b >= neg_log;
-          if (gas) S = (neg_log - acc) / local_beta;
+          gas = acc + tau_b >= S;
+          Sg = (S - acc) / local_beta;
         }
-        const bool edge = u < CUDART_INF;                               // an edge lies ahead
         const bool solid = cf.solid[k] != 0;
         const int nc = cf.nbr[k];
         const bool cross = ok & !gas & edge & !solid & (nc >= 0) & (it < 9999);
         const bool tallied = ok & (gas | (edge & solid));               // ends in an element (unless the location fails)
         // traceRay.jl:33,44,56: gas S - nudge, solid wall u - nudge, crossing u + nudge
-        const double adv = gas ? S - p.nudge : (solid ? u - p.nudge : u + p.nudge);
+        const double adv = gas ? Sg - p.nudge : (solid ? u - p.nudge : u + p.nudge);
         if (cross | tallied) {
           px = fma(adv, dx, px);
           py = fma(adv, dy, py);
@@ -999,28 +1066,17 @@ __device__ __forceinline__ unsigned int queue_ray_loop(const TraceParams& p, con
           ++it;
         } else {
           active = false;
+          // absorber index of (lattice cell, gas | wall on coarse edge k): ONE table load shared by both endings
+          // (rthx_api.cu builds the table from the lattice -> fine map, the fine cells' vertex counts and cell_surf_id)
           int absorber = -1;
           if (tallied) {
-            const int f = locate_affine(p, cf, px, py);
-            if (f >= 0) {
-              const int gc = cf.fine_off + f;
-              if (gas) {
-                absorber = p.n_surfaces + gc;
-              } else {
-                int w = k;                                               // fine wall lying on coarse edge k
-                bool on_cut = false;
-                if (cf.kind != KIND_AFFINE_QUAD && __ldg(p.poly_nv + gc) != 3) {
-                  on_cut = k == cf.diag;                                 // quad cell of a mirrored-triangle lattice
-                  w = (k < cf.diag) ? k : k + 1;
-                }
-                if (!on_cut) absorber = __ldg(p.cell_surf_id + 4 * gc + w);   // -1: fine wall not solid -> lost
-              }
-            }
+            const int l = lattice_cell(cf, px, py);
+            if (l >= 0) absorber = __ldg(p.abs_tab + (size_t)(cf.abs_off + l) * 5 + (gas ? 0 : 1 + k));
           }
           if (absorber >= 0) {
             atomicAdd(&b.hist[absorber], 1u);
             if (REC) {
-              const size_t sl = b.rec_row + (size_t)r_cur;
+              const size_t sl = b.rec_row + (size_t)(b.r_begin + (int64_t)r_cur);
               double* o = p.rec_pts + 4 * sl;
               o[2] = px; o[3] = py;
               p.rec_valid[sl] = 1;
@@ -1038,7 +1094,13 @@ __device__ __forceinline__ unsigned int queue_ray_loop(const TraceParams& p, con
   return n_lost;
 }
 
-template <int MINB>
+template <bool SURF, int DEPTH>
+__device__ __forceinline__ unsigned int queue_dispatch(const TraceParams& p, const QueueBlock& b, bool uniform, bool rec) {
+  if (uniform) return rec ? queue_ray_loop<SURF, true, true, DEPTH>(p, b) : queue_ray_loop<SURF, true, false, DEPTH>(p, b);
+  return rec ? queue_ray_loop<SURF, false, true, DEPTH>(p, b) : queue_ray_loop<SURF, false, false, DEPTH>(p, b);
+}
+
+template <int MINB, int DEPTH>
 __global__ void __launch_bounds__(256, MINB) trace_exchange_queue_kernel(const __grid_constant__ TraceParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const size_t coarse_bytes = sizeof(CoarseDev) * (size_t)p.n_coarse;
@@ -1047,7 +1109,7 @@ __global__ void __launch_bounds__(256, MINB) trace_exchange_queue_kernel(const _
   uint32_t* hist = reinterpret_cast<uint32_t*>(smem_raw + coarse_bytes + sizeof(double) * EM_DOUBLES + sizeof(double2) * LOGTAB_N);
   const int N = p.N;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
-  const int wq = 32 * p.queue_depth;                           // queue slots per warp
+  constexpr int WQ = 32 * DEPTH;
   double* queue = reinterpret_cast<double*>(smem_raw + ((coarse_bytes + sizeof(double) * EM_DOUBLES + sizeof(double2) * LOGTAB_N + sizeof(uint32_t) * (size_t)N + 15) & ~size_t(15)));
 
   const unsigned bid = blockIdx.x;
@@ -1070,24 +1132,7 @@ __global__ void __launch_bounds__(256, MINB) trace_exchange_queue_kernel(const _
   const int g = p.em_cell[e];
   const int wall = p.em_wall[e];
   const bool is_surface = wall >= 0;
-  if (threadIdx.x == 0) {
-    const int em_nv = p.poly_nv[g];
-    const double* vx = p.poly_vx + 4 * g;
-    const double* vy = p.poly_vy + 4 * g;
-    if (is_surface) {
-      const int j = (wall + 1 == em_nv) ? 0 : wall + 1;
-      const double ex = vx[j] - vx[wall], ey = vy[j] - vy[wall];
-      const double len = sqrt(ex * ex + ey * ey);
-      s_em[0] = vx[wall]; s_em[1] = vy[wall]; s_em[2] = ex; s_em[3] = ey;
-      s_em[4] = ex / len; s_em[5] = ey / len;
-      s_em[6] = -(ey / len); s_em[7] = ex / len;
-    } else {
-      s_em[0] = vx[0]; s_em[1] = vy[0]; s_em[2] = vx[1] - vx[0]; s_em[3] = vy[1] - vy[0]; s_em[4] = vx[2] - vx[0]; s_em[5] = vy[2] - vy[0];
-      s_em[6] = vx[2]; s_em[7] = vy[2]; s_em[8] = vx[3] - vx[2]; s_em[9] = vy[3] - vy[2]; s_em[10] = vx[0] - vx[2]; s_em[11] = vy[0] - vy[2];
-      s_em[14] = em_nv == 3 ? 2.0 : 0.5 * (vx[0] * (vy[1] - vy[2]) + vx[1] * (vy[2] - vy[0]) + vx[2] * (vy[0] - vy[1])) / p.cell_volume[g];
-    }
-    s_em[12] = p.cell_mid[2 * g]; s_em[13] = p.cell_mid[2 * g + 1];
-  }
+  if (threadIdx.x == 0) stage_emitter_folded(p, g, wall, s_em);
 
   const int64_t per = (p.rays_per_emitter + p.row_chunks - 1) / p.row_chunks;
   const int64_t r_begin = (int64_t)chunk * per;
@@ -1106,17 +1151,17 @@ __global__ void __launch_bounds__(256, MINB) trace_exchange_queue_kernel(const _
   QueueBlock b;
   b.coarse = reinterpret_cast<const CoarseDev*>(smem_raw);
   b.s_em = s_em; b.s_log = s_log; b.hist = hist;
-  b.q = queue + (size_t)warp * 5 * wq;
+  b.q = queue + (size_t)warp * 5 * WQ;
   b.beta_band = beta_band;
   b.inv_beta_u = beta_u > 0.0 ? 1.0 / beta_u : CUDART_INF;
   b.r_begin = r_begin; b.r_end = r_end;
   b.rec_row = rec_slot >= 0 ? (size_t)rec_slot * (size_t)p.rays_per_emitter : 0;
   b.e = (uint32_t)e; b.cw = ((uint32_t)band << 16);
-  b.c0 = p.em_coarse[e]; b.wq = wq; b.n_warps = n_warps; b.warp = warp; b.lane = lane; b.is_surface = is_surface ? 1 : 0;
+  b.sel_thr = reinterpret_cast<const uint32_t*>(s_em + 15)[0];
+  b.c0 = p.em_coarse[e]; b.n_warps = n_warps; b.warp = warp; b.lane = lane;
 
-  unsigned int n_lost;
-  if (uniform) n_lost = rec_slot >= 0 ? queue_ray_loop<true, true>(p, b) : queue_ray_loop<true, false>(p, b);
-  else         n_lost = rec_slot >= 0 ? queue_ray_loop<false, true>(p, b) : queue_ray_loop<false, false>(p, b);
+  const unsigned int n_lost0 = is_surface ? queue_dispatch<true, DEPTH>(p, b, uniform, rec_slot >= 0) : queue_dispatch<false, DEPTH>(p, b, uniform, rec_slot >= 0);
+  unsigned int n_lost = n_lost0;
 
   // ---- flush --------------------------------------------------------------------------------------------------
   for (int off = 16; off > 0; off >>= 1) n_lost += __shfl_down_sync(0xffffffffu, n_lost, off);
@@ -1136,13 +1181,17 @@ __global__ void __launch_bounds__(256, MINB) trace_exchange_queue_kernel(const _
 
 // kernel variants: hist_in_smem x fast x multi; the register bound MINB only varies for the hot FIRST_INTERACTION FAST kernel
 typedef void (*TraceKernel)(const TraceParams);
-static TraceKernel kernel_variant(bool hist, bool fast, int minb, bool multi, bool sq) {
+static TraceKernel kernel_variant(bool hist, bool fast, int minb, bool multi, bool sq, int queue_depth = 0) {
   if (sq && hist && fast && !multi) {
     if (minb == 5) return (TraceKernel)trace_exchange_sq_kernel<5>;                         // RTHX_MINB=5: 48 registers, 5 blocks / SM (A/B knob)
     if (minb == 3) return (TraceKernel)trace_exchange_kernel<true, true, 4, false, true>;   // RTHX_MINB=3: the shared-loop form (A/B knob)
     return (TraceKernel)trace_exchange_sq_kernel<4>;
   }
-  if (minb == 6 && hist && fast && !multi && !sq) return (TraceKernel)trace_exchange_queue_kernel<4>;   // per-warp ray queue (multi-face meshes)
+  if (minb == 6 && hist && fast && !multi && !sq) {                                                     // per-warp ray queue (multi-face meshes)
+    if (queue_depth >= 4) return (TraceKernel)trace_exchange_queue_kernel<4, 4>;
+    if (queue_depth >= 2) return (TraceKernel)trace_exchange_queue_kernel<4, 2>;
+    return (TraceKernel)trace_exchange_queue_kernel<4, 1>;
+  }
   if (multi) {
     if (hist) return fast ? (TraceKernel)trace_exchange_kernel<true, true, 2, true, false> : (TraceKernel)trace_exchange_kernel<true, false, 2, true, false>;
     return fast ? (TraceKernel)trace_exchange_kernel<false, true, 2, true, false> : (TraceKernel)trace_exchange_kernel<false, false, 2, true, false>;
@@ -1161,23 +1210,24 @@ cudaError_t configure_trace_kernel(size_t smem_bytes) {
     for (int multi = 0; multi < 2; ++multi)
       for (int hist = 0; hist < 2; ++hist)
         for (int fast = 0; fast < 2; ++fast)
-          for (int minb = 2; minb <= 6; ++minb) {
-            cudaError_t e = cudaFuncSetAttribute((const void*)kernel_variant(hist, fast, minb, multi, sq), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-            if (e != cudaSuccess) return e;
-          }
+          for (int minb = 2; minb <= 6; ++minb)
+            for (int depth = 1; depth <= 4; depth *= 2) {
+              cudaError_t e = cudaFuncSetAttribute((const void*)kernel_variant(hist, fast, minb, multi, sq, depth), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+              if (e != cudaSuccess) return e;
+            }
   return cudaSuccess;
 }
 
-int trace_kernel_max_blocks_per_sm(int block_threads, size_t smem_bytes, bool hist, bool fast, int minb, bool multi, bool sq) {
+int trace_kernel_max_blocks_per_sm(int block_threads, size_t smem_bytes, bool hist, bool fast, int minb, bool multi, bool sq, int queue_depth) {
   int n = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, (const void*)kernel_variant(hist, fast, minb, multi, sq), block_threads, smem_bytes) != cudaSuccess) return 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, (const void*)kernel_variant(hist, fast, minb, multi, sq, queue_depth), block_threads, smem_bytes) != cudaSuccess) return 0;
   return n;
 }
 
 cudaError_t launch_trace_exchange(const TraceParams& p, int n_blocks, int block_threads, size_t smem_bytes, bool fast, int minb, bool sq,
                                   cudaStream_t stream) {
   if (n_blocks <= 0) return cudaSuccess;
-  TraceKernel k = kernel_variant(p.hist_in_smem != 0, fast, minb, p.multi_bounce != 0, sq);
+  TraceKernel k = kernel_variant(p.hist_in_smem != 0, fast, minb, p.multi_bounce != 0, sq, p.queue_depth);
   void* args[] = {(void*)&p};
   return cudaLaunchKernel((const void*)k, dim3(n_blocks), dim3(block_threads), args, smem_bytes, stream);
 }
