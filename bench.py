@@ -39,7 +39,8 @@ def parse_args():
     ap.add_argument("--workload", default="cfg3", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
     ap.add_argument("--rays", type=float, default=None, help="rays per GPU per step (default: 1e10 for cfg3)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
-    ap.add_argument("--cpu-sample-rays", type=float, default=1.5e8)
+    ap.add_argument("--cpu-sample-rays", type=float, default=1.0e9,
+                    help="rays of the bounded CPU-baseline sample (about 15 s on 16 cores); the reference arm takes a fifth of it per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-smoothing", action="store_true")
@@ -50,8 +51,9 @@ def parse_args():
     return ap.parse_args()
 
 
-# DRAM bytes per launch of trace_exchange_kernel measured by ncu (profiles/r1d_trace_exchange_metrics.csv)
-NCU_DRAM_BYTES_PER_LAUNCH = {"cfg3": 894779904 + 835332096}   # profiles/r1g_trace_exchange_metrics.csv
+# DRAM bytes per launch of the trace kernel measured by ncu --set full (dram__bytes_read.sum + dram__bytes_write.sum)
+NCU_DRAM_BYTES_PER_LAUNCH = {"cfg3": (895.0e6 + 835.0e6, "profiles/r1k_trace_exchange_sq_metrics.csv"),
+                             "cfg5": (None, "profiles/r1k_trace_exchange_queue_metrics.csv")}
 
 DEFAULT_RAYS = {"cfg1": 1e6, "cfg2": 1e8, "cfg3": 1e10, "cfg4": 1e8, "cfg5": 1e9}
 
@@ -444,14 +446,17 @@ def main():
                          f"algorithm, OpenMP, Julia absent); cpu: {cpu_model()}"}
     kernel_rays_per_s = (traced_per_step / world) / (kernel_ms * 1e-3)
     achieved = kernel_rays_per_s * A / 1e12
+    info = sh.tracer.info
+    kernel_name = ("trace_exchange_sq_kernel" if info["n_coarse"] == 1 and info["n_affine_faces"] == 1 else
+                   "trace_exchange_queue_kernel" if info["n_affine_faces"] == info["n_coarse"] else "trace_exchange_kernel")
     hbm_bytes_per_ray = 8.0 * N * N * nb / world / max(1, traced_per_step / world)
     roofline = {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                 "frac": achieved / fp64_peak if fp64_peak else None,
-                "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(args.workload),
+                "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(args.workload, (None, None))[0],
                 "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture "
-                                "profiles/r1g_trace_exchange_metrics.csv (cfg3; the reductions read-modify-write the zeroed "
-                                "8*N*N-byte count matrix once, independent of the ray count)",
-                "kernel": "trace_exchange_kernel", "kernel_ms": kernel_ms, "kernel_rays_per_s": kernel_rays_per_s,
+                                f"{NCU_DRAM_BYTES_PER_LAUNCH.get(args.workload, (None, 'none for this workload'))[1]} (the reductions "
+                                "read-modify-write the zeroed 8*N*N-byte count matrix once, independent of the ray count)",
+                "kernel": kernel_name, "kernel_ms": kernel_ms, "kernel_rays_per_s": kernel_rays_per_s,
                 "flop_per_ray": A,
                 "peak_source": "FP64 DFMA-chain micro-benchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
                 "hbm": {"algorithmic_bytes_per_ray": hbm_bytes_per_ray,

@@ -360,3 +360,70 @@ def test_full_size_cfg3_reproduces_crosbie_schrenker(rthx_mod, cuda_lib):
     assert rel <= 0.05                                            # the reference's own tolerance (test_2d_grey.jl:216)
     assert rel <= 0.01 and np.abs(S - A).max() < 0.01             # what 1e10 rays on 101x101 actually deliver
     assert abs(res["energy_error"]) < 1e-4
+
+
+def _square_from(verts, Ndiv, kappa=1.0, n_bins=1, kappa_cells=None):
+    from rthx import PolyVolume2D, RayTracingDomain2D
+    face = PolyVolume2D(list(verts), (True, True, True, True), n_bins, kappa, 0.0)
+    face.epsilon = [1.0] * 4
+    face.T_in_w = [1000.0, 0.0, 0.0, 0.0]
+    face.T_in_g = -1.0
+    face.q_in_g = 0.0
+    return RayTracingDomain2D([face], [Ndiv])
+
+
+def test_sq_axis_aligned_loop_is_bit_identical_to_the_general_loop(rthx_mod, oracle_mod, cuda_lib, monkeypatch):
+    """The single-quad kernel drops the four dot products of distToSurface2D / the lattice inverse when the face is an
+    axis-aligned rectangle (n0 = (0, +-1), n1 = (+-1, 0)).  Every product it drops is an exact zero, so the tallies must be
+    bit-identical to the general loop (RTHX_NO_AXIS=1) — for the usual vertex order and for one starting at the far corner
+    (both normals flipped) — and both agree with the oracle.  Vertex orders starting on a vertical edge are not
+    axis-specialised and run the general loop."""
+    orders = {
+        "bottom-left": [(0.0, 0.0), (2.0, 0.0), (2.0, 1.0), (0.0, 1.0)],
+        "top-right": [(2.0, 1.0), (0.0, 1.0), (0.0, 0.0), (2.0, 0.0)],
+        "bottom-right": [(2.0, 0.0), (2.0, 1.0), (0.0, 1.0), (0.0, 0.0)],
+    }
+    for name, verts in orders.items():
+        rtm = _square_from(verts, (7, 5), kappa=1.3)
+        flat, tr = tracer(rthx_mod, cuda_lib, rtm)
+        assert tr.info["n_affine_faces"] == 1
+        rpe = 20000
+        ref = oracle_mod.trace(flat, rpe, seed=41, rec_ids=[3, 40])
+        monkeypatch.delenv("RTHX_NO_AXIS", raising=False)
+        a = tr.trace(rpe, seed=41, rec_ids=[3, 40])
+        monkeypatch.setenv("RTHX_NO_AXIS", "1")
+        g = tr.trace(rpe, seed=41, rec_ids=[3, 40])
+        monkeypatch.delenv("RTHX_NO_AXIS", raising=False)
+        assert np.array_equal(a["counts"], g["counts"]) and np.array_equal(a["lost"], g["lost"]), name
+        assert np.array_equal(a["endpoints"], g["endpoints"]), name
+        check_exact(a, ref, rpe)
+        assert np.allclose(a["origins"], ref["origins"], rtol=0, atol=1e-13)
+        assert np.allclose(a["endpoints"], ref["endpoints"], rtol=0, atol=1e-9)
+
+
+def test_queue_kernel_mixed_quad_and_triangle_faces_with_recorder(rthx_mod, oracle_mod, cuda_lib):
+    """Multi-face FAST mesh with BOTH face kinds (a rectangle with a triangular roof across a transparent interface), cell-wise
+    different kappa (variable-beta path) and recorded rays: exercises dist_face for parallelograms and triangles, the absorber
+    table for quad lattices, mirrored-triangle lattices (quad and diagonal cells) and the recorder slots of the queue kernel."""
+    from rthx import PolyVolume2D, RayTracingDomain2D
+    for kappas in ((1.0, 1.0), (0.4, 2.5)):
+        box = PolyVolume2D([(0.0, 0.0), (2.0, 0.0), (2.0, 1.0), (0.0, 1.0)], (True, True, False, True), 1, kappas[0], 0.0)
+        roof = PolyVolume2D([(0.0, 1.0), (2.0, 1.0), (1.0, 2.0)], (False, True, True), 1, kappas[1], 0.0)
+        for f, n in ((box, 4), (roof, 3)):
+            f.epsilon = [1.0] * n
+            f.T_in_w = [0.0] * n
+            f.T_in_g = -1.0
+            f.q_in_g = 0.0
+        rtm = RayTracingDomain2D([box, roof], [(6, 4), (5, 5)])
+        flat, tr = tracer(rthx_mod, cuda_lib, rtm)
+        assert tr.info["n_affine_faces"] == 2
+        rpe = 20000
+        ids = [0, 5, flat.n_surfaces + 3, flat.n_elements - 1]
+        ref = oracle_mod.trace(flat, rpe, seed=43, rec_ids=ids)
+        got = tr.trace(rpe, seed=43, rec_ids=ids)
+        check_exact(got, ref, rpe, budget_frac=2e-4)
+        check_exact(tr.trace(rpe, seed=43, locator=GENERIC), ref, rpe)
+        assert got["origins"].shape == ref["origins"].shape or abs(len(got["origins"]) - len(ref["origins"])) <= 8
+        if got["origins"].shape == ref["origins"].shape:
+            assert np.allclose(got["origins"], ref["origins"], rtol=0, atol=1e-13)
+            assert np.allclose(got["endpoints"], ref["endpoints"], rtol=0, atol=1e-9)
