@@ -579,6 +579,12 @@ LaunchPlan make_plan(const rthx_handle* h, const rthx_trace_args* a, int rank, i
     pl.fast = 1; pl.minb = 4;
     // tuning knobs: 5 = 48 registers, 5 blocks / SM; 3 = the shared-loop SQ branch of the general kernel (A/B reference)
     if (const char* ev = std::getenv("RTHX_MINB")) { const int v = std::atoi(ev); if (v == 5 || v == 3) pl.minb = v; }
+    // block shape knob: 288 / 320 threads (9 / 10 warps) at 4 blocks per SM trade registers (56 / 48) for resident warps
+    if (const char* ev = std::getenv("RTHX_SQ_THREADS")) {
+      const int v = std::atoi(ev);
+      if (v == 288 && !a->block_threads) { pl.minb = 7; pl.block_threads = 288; }
+      if (v == 320 && !a->block_threads) { pl.minb = 8; pl.block_threads = 320; }
+    }
   }
   pl.smem_bytes = coarse_bytes + em_bytes + (pl.hist_in_smem ? hist_bytes : 0);
   // Multi-face FAST meshes: the queue kernel (per-warp ray queue in shared memory, 40 bytes per parked ray).  Depth = as many

@@ -812,8 +812,14 @@ __device__ __forceinline__ unsigned int sq_ray_loop(const TraceParams& p, const 
       px = fma(adv, dx, px);
       py = fma(adv, dy, py);
       const int f = locate_sq<AXIS>(p, px, py);
-      // one table load for both endings: entry 0 = Ns + cell (gas), entry 1+k = surface index of the fine wall on edge k
-      if (f >= 0) absorber = __ldg(p.abs_tab + (unsigned)(f * 5 + (gas ? 0 : 1 + k)));
+      // gas: Ns + cell; wall: entry 1+k of the cell's absorber-table row = surface index of the fine wall on coarse edge k.
+      // Only wall endings load: they touch the boundary cells' rows only, which stay in L1 — loading the
+      // gas entry as well made every ray wait on an L1 miss (10 201 rows; long-scoreboard stalls 0.02 -> 1.4 warps per issue).
+      if (f >= 0) {
+        int sid = p.n_surfaces + f;
+        if (!gas) sid = __ldg(p.abs_tab + (unsigned)(f * 5 + 1 + k));
+        absorber = sid;
+      }
     }
     if (absorber >= 0) {
       asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(hist_s + 4u * (uint32_t)absorber), "r"(1u) : "memory");
@@ -841,8 +847,8 @@ __device__ __forceinline__ unsigned int sq_dispatch(const TraceParams& p, const 
   return rec ? sq_ray_loop<SURF, false, true, AXIS>(p, b) : sq_ray_loop<SURF, false, false, AXIS>(p, b);
 }
 
-template <int MINB>
-__global__ void __launch_bounds__(256, MINB) trace_exchange_sq_kernel(const __grid_constant__ TraceParams p) {
+template <int MINB, int THREADS>
+__global__ void __launch_bounds__(THREADS, MINB) trace_exchange_sq_kernel(const __grid_constant__ TraceParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* s_em = reinterpret_cast<double*>(smem_raw);
   double2* s_log = reinterpret_cast<double2*>(smem_raw + sizeof(double) * EM_DOUBLES);
@@ -1188,9 +1194,11 @@ __global__ void __launch_bounds__(256, MINB) trace_exchange_queue_kernel(const _
 typedef void (*TraceKernel)(const TraceParams);
 static TraceKernel kernel_variant(bool hist, bool fast, int minb, bool multi, bool sq, int queue_depth = 0) {
   if (sq && hist && fast && !multi) {
-    if (minb == 5) return (TraceKernel)trace_exchange_sq_kernel<5>;                         // RTHX_MINB=5: 48 registers, 5 blocks / SM (A/B knob)
+    if (minb == 5) return (TraceKernel)trace_exchange_sq_kernel<5, 256>;                    // RTHX_MINB=5: 48 registers, 5 blocks / SM (A/B knob)
+    if (minb == 7) return (TraceKernel)trace_exchange_sq_kernel<4, 288>;                    // 4 blocks of 9 warps: 56 registers, 36 warps / SM
+    if (minb == 8) return (TraceKernel)trace_exchange_sq_kernel<4, 320>;                    // 4 blocks of 10 warps: 48 registers, 40 warps / SM
     if (minb == 3) return (TraceKernel)trace_exchange_kernel<true, true, 4, false, true>;   // RTHX_MINB=3: the shared-loop form (A/B knob)
-    return (TraceKernel)trace_exchange_sq_kernel<4>;
+    return (TraceKernel)trace_exchange_sq_kernel<4, 256>;
   }
   if (minb == 6 && hist && fast && !multi && !sq) {                                                     // per-warp ray queue (multi-face meshes)
     if (queue_depth >= 4) return (TraceKernel)trace_exchange_queue_kernel<4, 4>;
@@ -1215,7 +1223,7 @@ cudaError_t configure_trace_kernel(size_t smem_bytes) {
     for (int multi = 0; multi < 2; ++multi)
       for (int hist = 0; hist < 2; ++hist)
         for (int fast = 0; fast < 2; ++fast)
-          for (int minb = 2; minb <= 6; ++minb)
+          for (int minb = 2; minb <= 8; ++minb)
             for (int depth = 1; depth <= 4; depth *= 2) {
               cudaError_t e = cudaFuncSetAttribute((const void*)kernel_variant(hist, fast, minb, multi, sq, depth), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
               if (e != cudaSuccess) return e;
