@@ -55,6 +55,10 @@ def parse_args():
 NCU_DRAM_BYTES_PER_LAUNCH = {"cfg3": (895.0e6 + 835.0e6, "profiles/r1k_trace_exchange_sq_metrics.csv"),
                              "cfg5": (None, "profiles/r1k_trace_exchange_queue_metrics.csv")}
 
+# executed warp instructions per 32 rays of the trace kernel (ncu source page, profiles/<capture>_sass_mix.csv, TOTAL row)
+NCU_WARP_INSTR_PER_32_RAYS = {"cfg3": (245.6, "profiles/r1p_trace_exchange_sq_sass_mix.csv"),
+                              "cfg5": (680.9, "profiles/r1p_trace_exchange_queue_sass_mix.csv")}
+
 DEFAULT_RAYS = {"cfg1": 1e6, "cfg2": 1e8, "cfg3": 1e10, "cfg4": 1e8, "cfg5": 1e9}
 
 
@@ -462,6 +466,15 @@ def main():
                 "hbm": {"algorithmic_bytes_per_ray": hbm_bytes_per_ray,
                         "achieved_gbs": kernel_rays_per_s * hbm_bytes_per_ray / 1e9, "peak_gbs": 6559.4,
                         "note": "count-matrix write-out only; the path is not HBM-bound"}}
+    # secondary explanation: the kernel is bound by instruction issue (three half-rate pipes share one issue port per SM
+    # sub-partition), so state the issue-slot utilisation its measured rate implies
+    clocks = sampler.summary(t_win0, t_win1 + 0.1) if sampler else None
+    wi = NCU_WARP_INSTR_PER_32_RAYS.get(args.workload)
+    if wi and clocks and clocks.get("sm_mhz"):
+        slots = info["sm_count"] * 4 * clocks["sm_mhz"] * 1e6
+        roofline["issue"] = {"warp_instr_per_32_rays": wi[0], "source": wi[1], "issue_slots_per_s": slots,
+                             "frac": kernel_rays_per_s / 32.0 * wi[0] / slots,
+                             "note": "executed warp instructions (ncu) x measured ray rate / (SMs x 4 sub-partitions x SM clock)"}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
@@ -474,7 +487,7 @@ def main():
                    "l2": "count matrix (8*N*N bytes) exceeds the 126 MB L2 for cfg3; a fresh Philox seed every step",
                    "launch": {k: st[k] for k in ("n_blocks", "block_threads", "row_chunks", "smem_bytes", "hist_in_smem")}},
         "roofline": roofline, "smoothing": smoothing, "solve": solve, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps * world,
-        "clocks": sampler.summary(t_win0, t_win1 + 0.1) if sampler else None,
+        "clocks": clocks,
         "check": {"tallied_last_step": tallied, "lost_last_step": lost_total},
     }
     print(json.dumps(line))

@@ -6,6 +6,7 @@
 //   where the fine cells of a coarse face are verified to be the affine lattice produced by meshQuad.jl:116-136 /
 //   meshTriangle.jl:40-97, the analytic lattice inverse used instead of grid + point-in-polygon.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -76,6 +77,7 @@ std::mutex g_pool_mu;
 std::vector<DevRes> g_pool[64];
 cudaDeviceProp g_prop[64];
 bool g_prop_ok[64] = {};
+bool g_kernels_configured[64] = {};   // cudaFuncSetAttribute(max dynamic smem) done for every kernel variant on this device
 
 void devres_free(DevRes& r) {
   cudaFree(r.smooth_X); cudaFree(r.smooth_vec); cudaFree(r.smooth_src); cudaFree(r.solve_buf); cudaFree(r.solve_mat); cudaFree(r.dyk_buf);
@@ -118,13 +120,23 @@ static int fail(rthx_handle* h, int code, const std::string& msg) {
 // All mesh tables live in ONE device allocation filled by ONE host-to-device copy: with peer access enabled (NCCL
 // processes) every cudaMalloc / cudaFree maps or unmaps the range on the peers and costs milliseconds.
 struct Arena {
-  std::vector<unsigned char> host;
+  std::vector<unsigned char> host;   // image of the uploaded tables
+  size_t total = 0;                  // arena size including the device-only scratch regions behind the image
   template <class T>
   size_t add(const std::vector<T>& v, size_t min_elems = 1) {
     const size_t off = (host.size() + 255) & ~size_t(255);
     const size_t n = std::max(v.size(), min_elems);
     host.resize(off + n * sizeof(T), 0);
     if (!v.empty()) std::memcpy(host.data() + off, v.data(), v.size() * sizeof(T));
+    total = host.size();
+    return off;
+  }
+  // device-only region (cleared / written by the library before every use): no host bytes, nothing to copy.  Only valid after
+  // the last add().
+  template <class T>
+  size_t scratch(size_t n_elems) {
+    const size_t off = (total + 255) & ~size_t(255);
+    total = off + std::max<size_t>(n_elems, 1) * sizeof(T);
     return off;
   }
 };
@@ -351,6 +363,16 @@ extern "C" int rthx_create(rthx_handle** out, const rthx_mesh* m, int device_id)
   if (h->prop.major < 10) return bail(RTHX_ERR_CUDA, "rthx_create: device is not sm_100 class (kernels are built for sm_100a only)");
   if (!h->valid && (ce = devres_create(*h)) != cudaSuccess) return bail(RTHX_ERR_CUDA, std::string("stream/event creation: ") + cudaGetErrorString(ce));
 
+  // RTHX_CREATE_TIMING=1 prints the host-side phases of this call to stderr (diagnostic knob)
+  const bool timing = std::getenv("RTHX_CREATE_TIMING") != nullptr;
+  auto t_prev = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!timing) return;
+    const auto t = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "rthx_create: %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t - t_prev).count());
+    t_prev = t;
+  };
+  lap("device / pool");
   const int nc = m->n_coarse, ncell = m->n_cells, ns = m->n_surfaces, N = ns + ncell, nb = m->n_bands;
   h->n_coarse = nc; h->n_cells = ncell; h->ns = ns; h->N = N; h->n_bands = nb;
   if (m->fine_off[0] != 0 || m->fine_off[nc] != ncell) return bail(RTHX_ERR_ARG, "rthx_create: fine_off must span [0, n_cells]");
@@ -381,6 +403,7 @@ extern "C" int rthx_create(rthx_handle** out, const rthx_mesh* m, int device_id)
     if (m->fine_off[c + 1] <= m->fine_off[c]) return bail(RTHX_ERR_ARG, "rthx_create: every coarse face needs at least one fine cell");
   }
 
+  lap("polygons + normals");
   // emitter table
   std::vector<int32_t> em_cell(N, -1), em_wall(N, -1), em_coarse(N, -1);
   for (int c = 0; c < nc; ++c)
@@ -395,6 +418,7 @@ extern "C" int rthx_create(rthx_handle** out, const rthx_mesh* m, int device_id)
     }
   for (int e = 0; e < N; ++e) if (em_cell[e] < 0) return bail(RTHX_ERR_ARG, "rthx_create: surface index without a wall");
 
+  lap("emitter table");
   // locator grids + coarse descriptors
   std::vector<FaceSetDev> sets(1 + (size_t)nc);
   std::vector<int32_t> bstart, bitems, lattice, abs_tab;
@@ -446,6 +470,7 @@ extern "C" int rthx_create(rthx_handle** out, const rthx_mesh* m, int device_id)
       }
     }
   }
+  lap("grids + lattice detection");
   // neighbour table: the unique coarse face sharing the (reversed) edge; T-junctions stay -1 (generic search)
   for (int c = 0; c < nc; ++c) {
     const Poly& a = polys[(size_t)ncell + c];
@@ -484,25 +509,34 @@ extern "C" int rthx_create(rthx_handle** out, const rthx_mesh* m, int device_id)
   if (m->epsilon) epsv.assign(m->epsilon, m->epsilon + (size_t)nb * ns);
   h->has_eps = m->epsilon != nullptr || ns == 0;
 
+  lap("neighbours + property tables");
   TraceParams& P = h->base;
   std::memset(&P, 0, sizeof(P));
   Arena A;
+  {   // one allocation for the image: 24 tables, 256-byte aligned (growing the vector table by table cost 3.6 ms for cfg3)
+    size_t need = 64 * 256 + sizeof(CoarseDev) * coarse.size() + sizeof(FaceSetDev) * sets.size() + 4 * (bstart.size() + bitems.size() + poly_nv.size()) +
+                  8 * (pvx.size() * 4 + mid.size() + vol.size() + beta.size() + ub.size() + omega.size() + epsv.size()) +
+                  4 * (surf.size() + lattice.size() + abs_tab.size() + em_cell.size() * 3);
+    A.host.reserve(need);
+  }
   const size_t o_coarse = A.add(coarse), o_sets = A.add(sets), o_bstart = A.add(bstart), o_bitems = A.add(bitems),
                o_nv = A.add(poly_nv), o_pvx = A.add(pvx), o_pvy = A.add(pvy), o_pnx = A.add(pnx), o_pny = A.add(pny),
                o_mid = A.add(mid), o_vol = A.add(vol), o_surf = A.add(surf), o_beta = A.add(beta), o_ub = A.add(ub),
                o_lat = A.add(lattice), o_abs = A.add(abs_tab), o_omega = A.add(omega), o_eps = A.add(epsv), o_ec = A.add(em_cell), o_ew = A.add(em_wall), o_eco = A.add(em_coarse),
-               o_bins = A.add(std::vector<int32_t>(), (size_t)nb * 4 + 16), o_rec = A.add(std::vector<int32_t>(), (size_t)N),
-               o_lost = A.add(std::vector<unsigned long long>(), ((size_t)nb * 4 + 16) * (size_t)N);
-  if (h->arena_cap < A.host.size()) {
+               o_bins = A.scratch<int32_t>((size_t)nb * 4 + 16), o_rec = A.scratch<int32_t>((size_t)N),
+               o_lost = A.scratch<unsigned long long>(((size_t)nb * 4 + 16) * (size_t)N);
+  if (h->arena_cap < A.total) {
     cudaFree(h->arena);
     h->arena = nullptr; h->arena_cap = 0;
-    const size_t cap = A.host.size() + A.host.size() / 4;
+    const size_t cap = A.total + A.total / 4;
     if ((ce = cudaMalloc(&h->arena, cap)) != cudaSuccess) return bail(RTHX_ERR_CUDA, std::string("cudaMalloc(mesh arena): ") + cudaGetErrorString(ce));
     h->arena_cap = cap;
   }
+  lap("arena (host)");
   void* base = h->arena;
   if ((ce = cudaMemcpy(base, A.host.data(), A.host.size(), cudaMemcpyHostToDevice)) != cudaSuccess)
     return bail(RTHX_ERR_CUDA, std::string("cudaMemcpy(mesh arena): ") + cudaGetErrorString(ce));
+  lap("cudaMemcpy H2D");
   h->mesh_bytes = A.host.size();
   unsigned char* b8 = static_cast<unsigned char*>(base);
   P.coarse = (const CoarseDev*)(b8 + o_coarse); P.sets = (const FaceSetDev*)(b8 + o_sets);
@@ -525,7 +559,20 @@ extern "C" int rthx_create(rthx_handle** out, const rthx_mesh* m, int device_id)
   for (int c = 0; c < nc && h->fast_ok; ++c)
     for (int k = 0; k < coarse[c].nv; ++k)
       if (!coarse[c].solid[k] && coarse[c].nbr[k] < 0) h->fast_ok = false;   // open / T-junction edge: needs the generic search
-  if ((ce = configure_trace_kernel(h->prop.sharedMemPerBlockOptin)) != cudaSuccess) return bail(RTHX_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce));
+  {
+    // once per device and process: a few hundred cudaFuncSetAttribute calls cost milliseconds, and callers re-create the
+    // handle for every trace
+    ce = cudaSuccess;
+    {
+      std::lock_guard<std::mutex> lk(g_pool_mu);
+      if (!g_kernels_configured[device_id & 63]) {
+        ce = configure_trace_kernel(h->prop.sharedMemPerBlockOptin);
+        g_kernels_configured[device_id & 63] = ce == cudaSuccess;
+      }
+    }
+    if (ce != cudaSuccess) return bail(RTHX_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce));   // bail re-takes the pool lock
+  }
+  lap("kernel attributes");
   *out = h;
   return RTHX_OK;
 }
