@@ -66,7 +66,15 @@ def solve_grey(rtm, F, spectral_bin: int = 1):
         rtm.fine_mesh[c - 1][f - 1].T_g = float(T[ns + v - 1])
     for (c, f, w), s in rtm.surface_mapping.items():
         rtm.fine_mesh[c - 1][f - 1].T_w[w - 1] = float(T[s - 1])
-    return dict(T_w=T[:ns], T_g=T[ns:], j=j, energy_error=float(np.sum(j - r - Abs)))
+    q = e - Abs                                    # net source per element, writeResultsToDomainGrey!: q_w = e - Abs
+    return dict(T_w=T[:ns], T_g=T[ns:], j=j, q_w=q[:ns], q_g=q[ns:], area=area, energy_error=float(np.sum(j - r - Abs)))
+
+
+def diffusion_S(z, beta, D, eps_w1, eps_w2, E_bw1, E_bw2):
+    """Diffusion-limit source function between two plates, test/test_2d_diffusion.jl:19-23."""
+    q_z = (E_bw1 - E_bw2) / (3 * beta * D / 4 + 1 / eps_w1 + 1 / eps_w2 - 1)
+    E_b1 = E_bw1 + q_z * (1 / 2 - 1 / eps_w1)
+    return E_b1 - (3 * beta * z / 4) * q_z
 
 
 def centerline_source_function(rtm, Ndim: int, T_hot: float) -> np.ndarray:

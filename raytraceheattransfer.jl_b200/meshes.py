@@ -86,3 +86,26 @@ def two_quads_domain(Ndiv=((4, 3), (5, 3)), kappa=(1.0, 2.0), skew: float = 0.0)
         f.T_in_g = -1.0
     f1.T_in_w = [1000.0, 0, 0, 0]
     return RayTracingDomain2D([f1, f2], list(Ndiv))
+
+
+def parallel_plates_domain(W: float = 100.0, H: float = 1.0, Ndiv=(21, 2), eps_plates: float = 0.5, T_hot: float = 1000.0,
+                           kappa: float = 1e-3) -> RayTracingDomain2D:
+    """Wide thin enclosure of test/test_2d_grey_reflecting.jl:96-121 ('Parallel Plates vs Textbook'): grey-diffuse plates of
+    emissivity eps_plates at the bottom (hot) and the top (cold), black cold side walls, an almost transparent medium."""
+    face = PolyVolume2D([(0.0, 0.0), (W, 0.0), (W, H), (0.0, H)], (True, True, True, True), 1, kappa, 0.0)
+    face.T_in_w = [T_hot, 0.0, 0.0, 0.0]
+    face.q_in_w = [0.0, 0.0, 0.0, 0.0]
+    face.epsilon = [eps_plates, 1.0, eps_plates, 1.0]
+    face.T_in_g = -1.0
+    face.q_in_g = 0.0
+    return RayTracingDomain2D([face], [tuple(Ndiv)])
+
+
+def diffusion_slab_domain(N_side: int = 31, beta: float = 25.0, aspect: float = 1000.0, T_hot: float = 1000.0) -> RayTracingDomain2D:
+    """Optically thick 1000:1 slab of test/test_2d_diffusion.jl:28-39 (build_diffusion_grey): black walls, bottom hot."""
+    face = PolyVolume2D([(0.0, 0.0), (aspect, 0.0), (aspect, 1.0), (0.0, 1.0)], (True, True, True, True), 1, beta, 0.0)
+    face.T_in_w = [T_hot, 0.0, 0.0, 0.0]
+    face.epsilon = [1.0, 1.0, 1.0, 1.0]
+    face.T_in_g = -1.0
+    face.q_in_g = 0.0
+    return RayTracingDomain2D([face], [(N_side, N_side)])

@@ -159,3 +159,43 @@ def test_sparse_public_path_diffusion_mesh(rthx_mod, cuda_lib):
     got = np.array([c.T_g for c in rtm.fine_mesh[0]])
     ref = gs.solve_grey(rtm, F)
     assert np.abs(got ** 4 - ref["T_g"] ** 4).max() < 1e-9 * 1000.0 ** 4 and rtm.last_solve_stats["matvec_bytes"] == 12 * F.nnz + 8 * (F.shape[0] + 1)
+
+
+def test_parallel_plates_textbook_flux_through_the_public_call(rthx_mod, cuda_lib):
+    """The reference's 'Parallel Plates vs Textbook' (test/test_2d_grey_reflecting.jl:96-136) through the public call on the
+    GPU: mesh(1e7; method = :exchange, k_dykstra = 500), solveEquilibrium!, flux of the central hot-wall elements within the
+    reference's 5 % of sigma T^4 / (2/eps - 1), energy error < 1e-4."""
+    from oracle import grey_solver as gs
+    rtm = rthx_mod.meshes.parallel_plates_domain()
+    F = rtm(10_000_000, method="exchange", k_dykstra=500, verbose=False, seed=21)
+    rthx_mod.solveEquilibrium(rtm, F, verbose=False)
+    assert abs(rtm.energy_error) < 1e-4
+    Nx = 21
+    n_central = max(1, Nx // 5)
+    lo = (Nx - n_central) // 2 + 1
+    q = [rtm.fine_mesh[0][col - 1].q_w[0] / rtm.fine_mesh[0][col - 1].area[0] for col in range(lo, lo + n_central)]
+    q_textbook = gs.STEFAN_BOLTZMANN * 1000.0 ** 4 / (1 / 0.5 + 1 / 0.5 - 1)
+    assert abs(np.mean(q) - q_textbook) / q_textbook < 0.05
+
+
+def test_diffusion_limit_through_the_public_call(rthx_mod, cuda_lib):
+    """The reference's diffusion-limit validation (test/test_2d_diffusion.jl:57-76) through the public call on the GPU:
+    beta = 25, 1000:1 slab, 31 x 31, 1000 rays per emitter; F_smooth sparse and non-negative, RMS of S(tau) against the
+    diffusion solution < 0.02 for the smoothed solve and at most half the raw error, energy error < 1e-6."""
+    from oracle import grey_solver as gs
+    N_side = 31
+    rtm = rthx_mod.meshes.diffusion_slab_domain(N_side)
+    rtm((4 * N_side + N_side ** 2) * 1000, method="exchange", verbose=False, seed=22)
+    assert sp.issparse(rtm.F_smooth) and (rtm.F_smooth.data < 0).sum() == 0
+
+    def rms():
+        T = np.array([c.T_g for c in rtm.fine_mesh[0]]).reshape((N_side, N_side), order="F")[(N_side - 1) // 2, :]
+        tau = np.linspace(1 / (2 * N_side), 1 - 1 / (2 * N_side), N_side)
+        return float(np.sqrt(np.mean(((T / 1000.0) ** 4 - gs.diffusion_S(tau, 25.0, 1.0, 1.0, 1.0, 1.0, 0.0)) ** 2)))
+
+    rthx_mod.solveEquilibrium(rtm, rtm.F_raw, verbose=False)
+    err_raw = rms()
+    rthx_mod.solveEquilibrium(rtm, rtm.F_smooth, verbose=False)
+    err_ap = rms()
+    assert err_ap < 0.02 and err_ap < 0.5 * err_raw
+    assert abs(rtm.energy_error) < 1e-6 * 1.0e3

@@ -1,5 +1,6 @@
 """Pin the oracle: closed-form answers and the reference's own golden vectors for the path
-(Crosbie & Schrenker table, test/test_2d_grey.jl:25-33,216; circle centre, test/test_triangle_mesh.jl:66-69)."""
+(Crosbie & Schrenker table, test/test_2d_grey.jl:25-33,216; circle centre, test/test_triangle_mesh.jl:66-69; parallel-plate flux,
+test/test_2d_grey_reflecting.jl:96-136; diffusion-limit source function, test/test_2d_diffusion.jl:19-23,57-76)."""
 import math
 
 import numpy as np
@@ -189,3 +190,59 @@ def test_recorder_semantics(oracle_mod, rthx_mod):
     # ascending element order (the reference walks emitters in sorted order): element 9 is a bottom wall
     assert np.all(o[:500, 1] < 1e-12) and np.all(o[:500, 1] > 0)
     assert np.all((e >= 0) & (e <= 1))
+
+
+def parallel_plate_flux_error(rtm, q_w, area):
+    """test_2d_grey_reflecting.jl:123-136: mean q_w / area over the central fifth of the hot wall against the textbook
+    sigma T^4 / (1/eps + 1/eps - 1)."""
+    Nx = 21
+    n_central = max(1, Nx // 5)
+    lo = (Nx - n_central) // 2 + 1
+    q = []
+    for col in range(lo, lo + n_central):                     # fine cells 1..Nx are the bottom row, wall 1 the hot plate
+        s = rtm.surface_mapping[(1, col, 1)] - 1
+        q.append(q_w[s] / area[s])
+    q_textbook = gs.STEFAN_BOLTZMANN * 1000.0 ** 4 / (1 / 0.5 + 1 / 0.5 - 1)
+    return abs(np.mean(q) - q_textbook) / q_textbook
+
+
+def test_parallel_plates_textbook_flux(oracle_mod, rthx_mod):
+    """test_2d_grey_reflecting.jl 'Parallel Plates vs Textbook': 100 x 1 enclosure, (21, 2) cells, eps = 0.5 plates, 1e7 rays,
+    k_dykstra = 500; flux at the central hot-wall elements within 5 % (ANALYTICAL_TOLERANCE), energy error < 1e-4."""
+    rtm = rthx_mod.meshes.parallel_plates_domain()
+    flat = rthx_mod.flatten_domain(rtm)
+    rpe = 10_000_000 // flat.n_elements
+    out = oracle_mod.trace(flat, rpe, seed=21)
+    assert out["lost"].sum() == 0
+    F_raw = rthx_mod.counts_to_F(out["counts"][0], rpe, verbose_loss=False)
+    F_smooth = rthx_mod.smoothing.smooth_F(F_raw, rthx_mod.get_w(rtm), flat.n_surfaces, k_dykstra=500)
+    res = gs.solve_grey(rtm, F_smooth)
+    assert abs(res["energy_error"]) < 1e-4
+    assert parallel_plate_flux_error(rtm, res["q_w"], res["area"]) < 0.05
+
+
+def diffusion_rms(rtm, N_side):
+    """centerline_rms_S, test/test_2d_diffusion.jl:42-49."""
+    T = np.array([c.T_g for c in rtm.fine_mesh[0]]).reshape((N_side, N_side), order="F")[(N_side - 1) // 2, :]
+    tau = np.linspace(1 / (2 * N_side), 1 - 1 / (2 * N_side), N_side)
+    S_ref = gs.diffusion_S(tau, 25.0, 1.0, 1.0, 1.0, 1.0, 0.0)
+    return float(np.sqrt(np.mean(((T / 1000.0) ** 4 - S_ref) ** 2)))
+
+
+def test_diffusion_limit_source_function(oracle_mod, rthx_mod):
+    """test_2d_diffusion.jl 'sparse grey': beta = 25, 1000:1 slab, 31 x 31, 1000 rays per emitter.  F_smooth stays sparse and
+    non-negative; the smoothed solve reproduces the diffusion-limit S(tau) with RMS < 0.02 and at most half the raw error."""
+    import scipy.sparse as sp
+    N_side = 31
+    rtm = rthx_mod.meshes.diffusion_slab_domain(N_side)
+    flat = rthx_mod.flatten_domain(rtm)
+    out = oracle_mod.trace(flat, 1000, seed=22)
+    F_raw = rthx_mod.counts_to_F(out["counts"][0], 1000, verbose_loss=False)
+    F_smooth = rthx_mod.smoothing.smooth_F(F_raw, rthx_mod.get_w(rtm), flat.n_surfaces)
+    assert sp.issparse(F_smooth) and (F_smooth.data < 0).sum() == 0
+    gs.solve_grey(rtm, F_raw)
+    err_raw = diffusion_rms(rtm, N_side)
+    res = gs.solve_grey(rtm, F_smooth)
+    err_ap = diffusion_rms(rtm, N_side)
+    assert err_ap < 0.02 and err_ap < 0.5 * err_raw
+    assert abs(res["energy_error"]) < 1e-6 * 1.0e3            # the reference sums mesh.energy_error against 1e-6
