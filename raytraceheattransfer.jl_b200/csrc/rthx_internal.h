@@ -9,6 +9,8 @@ namespace rthx {
 
 enum : int { KIND_GENERIC = 0, KIND_AFFINE_QUAD = 1, KIND_AFFINE_TRI = 2 };
 
+constexpr int LOGTAB_N = 256;   // entries of the -log table staged in shared memory by every block (csrc/rthx_logtab.h, 16 bytes each)
+
 // One coarse face (user polygon).  Staged in shared memory by every thread block when the whole array fits.
 struct alignas(16) CoarseDev {
   double vx[4], vy[4];   // CCW vertices
