@@ -32,7 +32,7 @@ extern "C" {
 #endif
 
 #define RTHX_VERSION_MAJOR 0
-#define RTHX_VERSION_MINOR 1
+#define RTHX_VERSION_MINOR 2
 
 /* status codes */
 enum {
@@ -167,6 +167,9 @@ typedef struct rthx_info {
   int32_t device_id;
   int32_t sm_count;
   int32_t cc_major, cc_minor;
+  int32_t n_bilinear_faces;     /* coarse quadrilaterals that are no parallelograms, verified to be the bilinear lattice of
+                                   meshQuad.jl:116-136 (located by the analytic inverse of the bilinear map)          [0.2] */
+  int32_t reserved_;
 } rthx_info;
 
 typedef struct rthx_handle rthx_handle;

@@ -92,7 +92,7 @@ class rthx_info(C.Structure):
     _fields_ = [
         ("n_elements", C.c_int32), ("n_surfaces", C.c_int32), ("n_cells", C.c_int32), ("n_coarse", C.c_int32),
         ("n_bands", C.c_int32), ("n_affine_faces", C.c_int32), ("device_id", C.c_int32), ("sm_count", C.c_int32),
-        ("cc_major", C.c_int32), ("cc_minor", C.c_int32),
+        ("cc_major", C.c_int32), ("cc_minor", C.c_int32), ("n_bilinear_faces", C.c_int32), ("reserved_", C.c_int32),
     ]
 
     def as_dict(self):

@@ -52,7 +52,8 @@ struct DevRes {
 struct rthx_handle : DevRes {
   int device = 0;
   cudaDeviceProp prop{};
-  int n_coarse = 0, n_cells = 0, n_bands = 0, ns = 0, N = 0, n_affine = 0;
+  int n_coarse = 0, n_cells = 0, n_bands = 0, ns = 0, N = 0, n_affine = 0, n_bilinear = 0;
+  bool queue_ok = false;       // every face has an analytic locator (affine or bilinear) and a complete neighbour table
   bool coarse_fits_smem = false;
   bool has_eps = false;
   bool single_quad = false;    // one parallelogram coarse face: SQ kernel
@@ -211,9 +212,19 @@ bool detect_affine(const Poly& cp, const Poly* cells, int n_fine, CoarseDev& out
   const double tol = 1e-9 * std::max(ext, 1e-300);
   double qx[4], qy[4];
   int Nx = 0, Ny = 0, mirror = -1, diag = -1;
+  bool bilinear = false;
   if (cp.n == 4) {
     for (int i = 0; i < 4; ++i) { qx[i] = cp.vx[i]; qy[i] = cp.vy[i]; }
-    if (!close_pt(qx[0] - qx[1] + qx[2] - qx[3], qy[0] - qy[1] + qy[2] - qy[3], 0, 0, 1e-12 * std::max(scale, ext))) return false;
+    if (!close_pt(qx[0] - qx[1] + qx[2] - qx[3], qy[0] - qy[1] + qy[2] - qy[3], 0, 0, 1e-12 * std::max(scale, ext))) {
+      // no parallelogram: meshQuad.jl:116-136 still produces a structured lattice — the bilinear image of the unit square.
+      // Accept strictly convex CCW quadrilaterals (the inverse map below is single-valued on them).
+      for (int i = 0; i < 4; ++i) {
+        const int j = (i + 1) & 3, k = (i + 2) & 3;
+        const double cr = (qx[j] - qx[i]) * (qy[k] - qy[j]) - (qy[j] - qy[i]) * (qx[k] - qx[j]);
+        if (!(cr > 1e-9 * ext * ext)) return false;
+      }
+      bilinear = true;
+    }
     if (cells[0].n != 4) return false;
     const double e0 = std::hypot(cells[0].vx[1] - cells[0].vx[0], cells[0].vy[1] - cells[0].vy[0]);
     const double ab = std::hypot(qx[1] - qx[0], qy[1] - qy[0]);
@@ -243,11 +254,13 @@ bool detect_affine(const Poly& cp, const Poly* cells, int n_fine, CoarseDev& out
     if (nd < 1 || nd * (nd + 1) / 2 != n_fine) return false;
     Nx = Ny = (int)nd;
   }
-  // lattice vertex (n,m) of the affine map  A + n/Nx (B-A) + m/Ny (D-A)
+  // lattice vertex (n,m) of the map  A + s (B-A) + t (D-A) + s t (A-B+C-D),  s = n/Nx, t = m/Ny  (the last term vanishes for
+  // parallelograms and mirrored triangles: affine)
+  const double Gx = bilinear ? qx[0] - qx[1] + qx[2] - qx[3] : 0.0, Gy = bilinear ? qy[0] - qy[1] + qy[2] - qy[3] : 0.0;
   auto lat = [&](int n, int m, double& x, double& y) {
     const double s = (double)n / Nx, t = (double)m / Ny;
-    x = qx[0] + s * (qx[1] - qx[0]) + t * (qx[3] - qx[0]);
-    y = qy[0] + s * (qy[1] - qy[0]) + t * (qy[3] - qy[0]);
+    x = qx[0] + s * (qx[1] - qx[0]) + t * (qx[3] - qx[0]) + s * t * Gx;
+    y = qy[0] + s * (qy[1] - qy[0]) + t * (qy[3] - qy[0]) + s * t * Gy;
   };
   std::vector<int32_t> table;
   if (cp.n == 3) table.assign((size_t)Nx * Ny, -1);
@@ -286,6 +299,17 @@ bool detect_affine(const Poly& cp, const Poly* cells, int n_fine, CoarseDev& out
   const double det = ux * vy - uy * vx;
   if (!(std::fabs(det) > 0)) return false;
   out.ax = qx[0]; out.ay = qy[0];
+  if (bilinear) {
+    // device: a2 s^2 + a1 s + a0 = 0 with a2 = E x G, a1 = E x F - H x G, a0 = -H x F (H = p - A); t by projection on F + s G
+    out.g1x = ux; out.g1y = uy; out.g2x = vx; out.g2y = vy;
+    out.cen[0] = Gx; out.cen[1] = Gy;
+    const double a2 = ux * Gy - uy * Gx;
+    out.hw[0] = a2 != 0.0 ? 1.0 / a2 : INFINITY;
+    out.hw[1] = det;
+    out.Nx = Nx; out.Ny = Ny;
+    out.kind = KIND_BILINEAR_QUAD; out.lat_off = -1; out.diag = -1;
+    return true;
+  }
   out.g1x = Nx * (vy / det);  out.g1y = Nx * (-vx / det);
   out.g2x = Ny * (-uy / det); out.g2y = Ny * (ux / det);
   out.Nx = Nx; out.Ny = Ny;
@@ -434,7 +458,7 @@ extern "C" int rthx_create(rthx_handle** out, const rthx_mesh* m, int device_id)
     for (int i = 0; i < 4; ++i) { d.vx[i] = cp.vx[i]; d.vy[i] = cp.vy[i]; d.nx[i] = cp.nx[i]; d.ny[i] = cp.ny[i]; d.nbr[i] = -1; d.solid[i] = 0; }
     for (int i = 0; i < cp.n; ++i) d.solid[i] = m->coarse_solid[4 * c + i] ? 1 : 0;
     d.nv = cp.n; d.fine_off = f0; d.kind = KIND_GENERIC; d.lat_off = -1; d.diag = -1; d.Nx = d.Ny = 0;
-    if (detect_affine(cp, &polys[f0], nf, d, lattice)) h->n_affine++;
+    if (detect_affine(cp, &polys[f0], nf, d, lattice)) { if (d.kind == KIND_BILINEAR_QUAD) h->n_bilinear++; else h->n_affine++; }
     for (int i = 0; i < cp.n; ++i) d.h[i] = cp.vx[i] * cp.nx[i] + cp.vy[i] * cp.ny[i];
     if (d.kind == KIND_AFFINE_QUAD) {   // slab form: opposite edges measured along the normals of edges 0 and 1
       d.h[2] = cp.vx[2] * cp.nx[0] + cp.vy[2] * cp.ny[0];
@@ -452,7 +476,7 @@ extern "C" int rthx_create(rthx_handle** out, const rthx_mesh* m, int device_id)
       d.abs_off = (int32_t)(abs_tab.size() / 5);
       const size_t ncell_lat = (size_t)d.Nx * d.Ny;
       for (size_t l = 0; l < ncell_lat; ++l) {
-        const int f = d.kind == KIND_AFFINE_QUAD ? (int)l : lattice[(size_t)d.lat_off + l];
+        const int f = d.kind == KIND_AFFINE_TRI ? lattice[(size_t)d.lat_off + l] : (int)l;   // quad lattices (affine or bilinear): fine index = n + m Nx
         int32_t row[5] = {-1, -1, -1, -1, -1};
         if (f >= 0) {
           const int gc = f0 + f;
@@ -555,10 +579,11 @@ extern "C" int rthx_create(rthx_handle** out, const rthx_mesh* m, int device_id)
   h->coarse_fits_smem = sizeof(CoarseDev) * (size_t)nc <= 32 * 1024;
   h->face0 = coarse[0];
   h->single_quad = nc == 1 && coarse[0].kind == KIND_AFFINE_QUAD;
-  h->fast_ok = h->coarse_fits_smem && h->n_affine == nc;
-  for (int c = 0; c < nc && h->fast_ok; ++c)
+  h->queue_ok = h->coarse_fits_smem && h->n_affine + h->n_bilinear == nc;
+  for (int c = 0; c < nc && h->queue_ok; ++c)
     for (int k = 0; k < coarse[c].nv; ++k)
-      if (!coarse[c].solid[k] && coarse[c].nbr[k] < 0) h->fast_ok = false;   // open / T-junction edge: needs the generic search
+      if (!coarse[c].solid[k] && coarse[c].nbr[k] < 0) h->queue_ok = false;   // open / T-junction edge: needs the generic search
+  h->fast_ok = h->queue_ok && h->n_bilinear == 0;   // the FAST form of the general kernel knows the affine kinds only
   {
     // once per device and process: a few hundred cudaFuncSetAttribute calls cost milliseconds, and callers re-create the
     // handle for every trace
@@ -582,6 +607,7 @@ extern "C" int rthx_get_info(const rthx_handle* h, rthx_info* info) {
   info->n_elements = h->N; info->n_surfaces = h->ns; info->n_cells = h->n_cells; info->n_coarse = h->n_coarse;
   info->n_bands = h->n_bands; info->n_affine_faces = h->n_affine; info->device_id = h->device;
   info->sm_count = h->prop.multiProcessorCount; info->cc_major = h->prop.major; info->cc_minor = h->prop.minor;
+  info->n_bilinear_faces = h->n_bilinear; info->reserved_ = 0;
   return RTHX_OK;
 }
 
@@ -636,7 +662,8 @@ LaunchPlan make_plan(const rthx_handle* h, const rthx_trace_args* a, int rank, i
   pl.smem_bytes = coarse_bytes + em_bytes + (pl.hist_in_smem ? hist_bytes : 0);
   // Multi-face FAST meshes: the queue kernel (per-warp ray queue in shared memory, 40 bytes per parked ray).  Depth = as many
   // rays per lane as still leave 4 resident blocks per SM, at most 8; RTHX_QUEUE_DEPTH overrides (0 = the lock-step kernel).
-  if (pl.fast && !pl.multi && !pl.sq && pl.hist_in_smem && h->coarse_fits_smem && h->n_coarse > 1 && pl.block_threads == 256) {
+  if (h->queue_ok && a->locator != RTHX_LOCATOR_GENERIC && !pl.multi && !pl.sq && pl.hist_in_smem && pl.block_threads == 256 &&
+      (h->n_coarse > 1 || h->n_bilinear > 0)) {
     const size_t base = (pl.smem_bytes + 15) & ~size_t(15);
     const size_t per_depth = (size_t)pl.block_threads * 40;
     const size_t budget = (size_t)h->prop.sharedMemPerMultiprocessor / 4 - 1024;
@@ -644,14 +671,14 @@ LaunchPlan make_plan(const rthx_handle* h, const rthx_trace_args* a, int rank, i
     if (const char* ev = std::getenv("RTHX_QUEUE_DEPTH")) { const int v = std::atoi(ev); if (v >= 0 && v <= 4) depth = v; }
     if (depth == 3) depth = 2;                       // compiled depths: 1, 2, 4 rays per lane and batch
     if (depth >= 1 && base + depth * per_depth <= h->prop.sharedMemPerBlockOptin) {
-      pl.minb = 6; pl.queue_depth = depth; pl.smem_bytes = base + depth * per_depth;
+      pl.fast = 1; pl.minb = 6; pl.queue_depth = depth; pl.smem_bytes = base + depth * per_depth;
     }
   }
   const long long rows = (long long)pl.n_owned * a->n_bins;
   long long chunks = a->row_chunks;
   if (chunks <= 0) {
     // enough blocks for ~32 waves of the resident set, but keep >= 2048 rays (and >= N/2, the flush scan) per block
-    const int per_sm = std::max(1, trace_kernel_max_blocks_per_sm(pl.block_threads, pl.smem_bytes, pl.hist_in_smem != 0, pl.fast != 0, pl.minb, pl.multi != 0, pl.sq != 0, pl.queue_depth));
+    const int per_sm = std::max(1, trace_kernel_max_blocks_per_sm(pl.block_threads, pl.smem_bytes, pl.hist_in_smem != 0, pl.fast != 0, pl.minb, pl.multi != 0, pl.sq != 0, pl.queue_depth + (h->n_bilinear > 0 ? 8 : 0)));
     const long long target = (long long)h->prop.multiProcessorCount * per_sm * 32;
     chunks = rows > 0 ? (target + rows - 1) / rows : 1;
     const long long min_rays = std::max<long long>(2048, h->N / 2);
@@ -676,6 +703,7 @@ void fill_params(const rthx_handle* h, const rthx_trace_args* a, const LaunchPla
   P.compact_rows = compact ? 1 : 0;
   P.row_chunks = pl.row_chunks;
   P.queue_depth = pl.queue_depth;
+  P.queue_bilinear = h->n_bilinear > 0 ? 1 : 0;
   P.queue_refill = 24;
   if (const char* ev = std::getenv("RTHX_QUEUE_REFILL")) { const int v = std::atoi(ev); if (v >= 0 && v <= 32) P.queue_refill = v; }   // tuning knob
   P.coarse_in_smem = h->coarse_fits_smem ? 1 : 0;
@@ -785,7 +813,7 @@ int pipeline_launch(rthx_handle* h, const rthx_trace_args* a, int rank, int worl
   CU(h, ensure(&h->counts_dev, &h->counts_cap, (size_t)a->n_bins * (size_t)n_owned * N));
   LaunchPlan pl = make_plan(h, a, rank, world);
   // batches: >= ~6 waves of resident blocks each, at most 16
-  const int per_sm = std::max(1, trace_kernel_max_blocks_per_sm(pl.block_threads, pl.smem_bytes, pl.hist_in_smem != 0, pl.fast != 0, pl.minb, pl.multi != 0, pl.sq != 0, pl.queue_depth));
+  const int per_sm = std::max(1, trace_kernel_max_blocks_per_sm(pl.block_threads, pl.smem_bytes, pl.hist_in_smem != 0, pl.fast != 0, pl.minb, pl.multi != 0, pl.sq != 0, pl.queue_depth + (h->n_bilinear > 0 ? 8 : 0)));
   const long long resident = (long long)h->prop.multiProcessorCount * per_sm;
   int n_batches = (int)std::min<long long>(16, std::max<long long>(1, pl.n_blocks / (6 * resident)));
   n_batches = std::max(1, std::min(n_batches, n_owned));

@@ -7,7 +7,7 @@
 
 namespace rthx {
 
-enum : int { KIND_GENERIC = 0, KIND_AFFINE_QUAD = 1, KIND_AFFINE_TRI = 2 };
+enum : int { KIND_GENERIC = 0, KIND_AFFINE_QUAD = 1, KIND_AFFINE_TRI = 2, KIND_BILINEAR_QUAD = 3 };
 
 constexpr int LOGTAB_N = 256;   // entries of the -log table staged in shared memory by every block (csrc/rthx_logtab.h, 16 bytes each)
 
@@ -18,6 +18,9 @@ struct alignas(16) CoarseDev {
   double h[4];           // plane offsets: quads h0 = v0·n0, h1 = v1·n1, h2 = v2·n0, h3 = v3·n1 (slab form); else h_i = v_i·n_i
   double cen[2], hw[2];  // quads: centre line (h_a + h_{a+2})/2 and half width (h_a - h_{a+2})/2 of the edge pair with normal n_a
   // affine lattice inverse (kinds 1,2): s = (p-a)·g1, t = (p-a)·g2, lattice cell (floor s, floor t) in [0,Nx)x[0,Ny)
+  // bilinear lattice (kind 3, a convex quadrilateral that is no parallelogram: meshQuad.jl:116-136 maps the unit square by
+  //   P(s,t) = A + s E + t F + s t G): a = A, g1 = E = B-A, g2 = F = D-A, cen = G = A-B+C-D, hw[0] = 1/(E x G), hw[1] unused;
+  //   h_i = v_i·n_i for all four edges (no slab form)
   double ax, ay, g1x, g1y, g2x, g2y;
   int32_t nv;
   int32_t kind;
@@ -88,6 +91,8 @@ struct TraceParams {
   int32_t rec_bin;
   int32_t queue_refill;        // queue kernel: with the queue dry, emit the next batch once <= this many lanes still hold a ray
   int32_t queue_depth;         // queue kernel: rays parked per lane and batch (queue slots per warp = 32 * queue_depth)
+  int32_t queue_bilinear;      // queue kernel: the mesh has bilinear-lattice faces (selects the variant that knows them)
+  int32_t queue_pad_;
   int64_t rays_per_emitter;
   int64_t ray_id_offset;
   uint64_t seed;

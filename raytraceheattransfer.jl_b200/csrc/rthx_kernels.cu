@@ -474,7 +474,7 @@ __global__ void __launch_bounds__(256, MINB) trace_exchange_kernel(const __grid_
     absorber = -1;
     for (int it = 0; it < 10000; ++it) {
       const CoarseDev& cf = coarse[c];
-      const int kind = FAST ? cf.kind : (p.force_generic ? KIND_GENERIC : cf.kind);
+      const int kind = FAST ? cf.kind : ((p.force_generic || cf.kind == KIND_BILINEAR_QUAD) ? KIND_GENERIC : cf.kind);   // the bilinear inverse lives in the queue kernel only
       int k;
       const double u = FAST ? dist_fast(cf, px, py, dx, dy, p.k_eps, k) : dist_to_coarse(cf, px, py, dx, dy, p.k_eps, k);
       bool gas;
@@ -942,8 +942,9 @@ struct QueueBlock {          // block-uniform state of one (emitter row, band, c
 
 // distToSurface2D on a coarse face of the queue kernel (the point is inside the face).
 //   parallelogram: slab form about the centre lines as in dist_sq, descriptor fields cen[] / hw[];
-//   triangle     : three edges, hit only when moving outward (d.n_i >= eps) with a positive plane distance.
+//   triangle / general convex quadrilateral: every edge, hit only when moving outward (d.n_i >= eps) with a positive plane distance.
 // Sign tests run on the high words, the argmin on cross-multiplied fractions (first index on ties), one division at the end.
+template <bool BILIN>
 __device__ __forceinline__ bool dist_face(const CoarseDev& f, double px, double py, double dx, double dy, double eps, double& u, int& k) {
   if (f.kind == KIND_AFFINE_QUAD) {
     const double d0 = fma(dx, f.nx[0], dy * f.ny[0]), d1 = fma(dx, f.nx[1], dy * f.ny[1]);
@@ -964,7 +965,8 @@ __device__ __forceinline__ bool dist_face(const CoarseDev& f, double px, double 
   double bn = 1.0, bd = 0.0;
   int bk = 0;
 #pragma unroll
-  for (int i = 0; i < 3; ++i) {
+  for (int i = 0; i < 4; ++i) {
+    if (i == 3 && (!BILIN || f.nv != 4)) break;      // the fourth edge of a general (bilinear-lattice) quadrilateral
     const double nx = f.nx[i], ny = f.ny[i];
     const double den = fma(dx, nx, dy * ny);
     const double num = f.h[i] - fma(px, nx, py * ny);
@@ -980,14 +982,38 @@ __device__ __forceinline__ bool dist_face(const CoarseDev& f, double px, double 
 }
 
 // lattice cell n + m Nx of a point in an affine coarse face, or -1 (one unsigned compare per axis, see locate_sq)
+// Inverse of the bilinear map P(s,t) = A + s E + t F + s t G of a convex quadrilateral (meshQuad.jl:116-136 divides the unit
+// square of (s,t) uniformly): eliminating t gives  a2 s^2 + a1 s + a0 = 0,  a2 = E x G, a1 = E x F - H x G, a0 = -H x F (H = p - A);
+// both roots come from the cancellation-free form q = -(a1 + sign(a1) sqrt(disc)) / 2: s = a0 / q or q / a2, the one inside [0,1]
+// is the point's (the other lies outside for a convex quadrilateral; a2 = 0, a trapezoid, leaves the first); t by projection of
+// H - s E on F + s G.  Verified against the forward map on 3.6e5 random points of random convex quadrilaterals (error < 1e-12).
+__device__ __forceinline__ int lattice_cell_bilinear(const CoarseDev& cf, double px, double py) {
+  const double hx = px - cf.ax, hy = py - cf.ay;
+  const double ex = cf.g1x, ey = cf.g1y, fx = cf.g2x, fy = cf.g2y, gx = cf.cen[0], gy = cf.cen[1];
+  const double a2 = ex * gy - ey * gx;
+  const double a1 = cf.hw[1] - (hx * gy - hy * gx);
+  const double a0 = hy * fx - hx * fy;
+  const double disc = fma(a1, a1, -4.0 * a2 * a0);
+  if (!(disc >= 0.0)) return -1;
+  const double q = -0.5 * (a1 + copysign(sqrt(disc), a1));
+  const double sb = a0 / q, sa = q * cf.hw[0];
+  const double s = (sb >= -1e-9 && sb <= 1.0 + 1e-9) ? sb : sa;
+  const double tx = fma(s, gx, fx), ty = fma(s, gy, fy);
+  const double t = (fma(-s, ex, hx) * tx + fma(-s, ey, hy) * ty) / (tx * tx + ty * ty);
+  const int n = __double2int_rd(s * (double)cf.Nx), m = __double2int_rd(t * (double)cf.Ny);
+  return ((s >= 0.0) & (t >= 0.0) & ((unsigned)n < (unsigned)cf.Nx) & ((unsigned)m < (unsigned)cf.Ny)) ? n + m * cf.Nx : -1;
+}
+
+template <bool BILIN>
 __device__ __forceinline__ int lattice_cell(const CoarseDev& cf, double px, double py) {
+  if (BILIN && cf.kind == KIND_BILINEAR_QUAD) return lattice_cell_bilinear(cf, px, py);
   const double rx = px - cf.ax, ry = py - cf.ay;
   const double s = fma(rx, cf.g1x, ry * cf.g1y), t = fma(rx, cf.g2x, ry * cf.g2y);
   const int n = __double2int_rd(s), m = __double2int_rd(t);
   return (((unsigned)n < (unsigned)cf.Nx) & ((unsigned)m < (unsigned)cf.Ny)) ? n + m * cf.Nx : -1;
 }
 
-template <bool SURF, bool UNIFORM, bool REC, int DEPTH>
+template <bool SURF, bool UNIFORM, bool REC, int DEPTH, bool BILIN>
 __device__ __forceinline__ unsigned int queue_ray_loop(const TraceParams& p, const QueueBlock& b) {
   constexpr int WQ = 32 * DEPTH;                       // queue slots per warp
   const int lane = b.lane;
@@ -1046,15 +1072,15 @@ __device__ __forceinline__ unsigned int queue_ray_loop(const TraceParams& p, con
         const CoarseDev& cf = b.coarse[c];
         int k;
         double u;
-        const bool edge = dist_face(cf, px, py, dx, dy, p.k_eps, u, k);  // an edge lies ahead
+        const bool edge = dist_face<BILIN>(cf, px, py, dx, dy, p.k_eps, u, k);  // an edge lies ahead
         bool gas, ok = true;
         double tau_b = 0.0, Sg;
         if (UNIFORM) {
           gas = S < u;
           Sg = S;
         } else {
-          const int l0 = lattice_cell(cf, px, py);                      // traceRay.jl:87-100
-          const int f0 = l0 < 0 ? -1 : (cf.kind == KIND_AFFINE_QUAD ? l0 : __ldg(p.lattice + cf.lat_off + l0));
+          const int l0 = lattice_cell<BILIN>(cf, px, py);                      // traceRay.jl:87-100
+          const int f0 = l0 < 0 ? -1 : (cf.kind == KIND_AFFINE_TRI ? __ldg(p.lattice + cf.lat_off + l0) : l0);
           ok = f0 >= 0;
           const double local_beta = ok ? b.beta_band[cf.fine_off + f0] : 0.0;
           tau_b = local_beta * u;
@@ -1081,7 +1107,7 @@ __device__ __forceinline__ unsigned int queue_ray_loop(const TraceParams& p, con
           // (rthx_api.cu builds the table from the lattice -> fine map, the fine cells' vertex counts and cell_surf_id)
           int absorber = -1;
           if (tallied) {
-            const int l = lattice_cell(cf, px, py);
+            const int l = lattice_cell<BILIN>(cf, px, py);
             if (l >= 0) absorber = __ldg(p.abs_tab + (size_t)(cf.abs_off + l) * 5 + (gas ? 0 : 1 + k));
           }
           if (absorber >= 0) {
@@ -1105,13 +1131,15 @@ __device__ __forceinline__ unsigned int queue_ray_loop(const TraceParams& p, con
   return n_lost;
 }
 
-template <bool SURF, int DEPTH>
+template <bool SURF, int DEPTH, bool BILIN>
 __device__ __forceinline__ unsigned int queue_dispatch(const TraceParams& p, const QueueBlock& b, bool uniform, bool rec) {
-  if (uniform) return rec ? queue_ray_loop<SURF, true, true, DEPTH>(p, b) : queue_ray_loop<SURF, true, false, DEPTH>(p, b);
-  return rec ? queue_ray_loop<SURF, false, true, DEPTH>(p, b) : queue_ray_loop<SURF, false, false, DEPTH>(p, b);
+  if (uniform) return rec ? queue_ray_loop<SURF, true, true, DEPTH, BILIN>(p, b) : queue_ray_loop<SURF, true, false, DEPTH, BILIN>(p, b);
+  return rec ? queue_ray_loop<SURF, false, true, DEPTH, BILIN>(p, b) : queue_ray_loop<SURF, false, false, DEPTH, BILIN>(p, b);
 }
 
-template <int MINB, int DEPTH>
+// BILIN: the mesh has general convex quadrilateral faces (bilinear lattices); compiled separately so that meshes of parallelograms
+// and triangles keep the shorter traversal loop
+template <int MINB, int DEPTH, bool BILIN>
 __global__ void __launch_bounds__(256, MINB) trace_exchange_queue_kernel(const __grid_constant__ TraceParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const size_t coarse_bytes = sizeof(CoarseDev) * (size_t)p.n_coarse;
@@ -1171,7 +1199,7 @@ __global__ void __launch_bounds__(256, MINB) trace_exchange_queue_kernel(const _
   b.sel_thr = reinterpret_cast<const uint32_t*>(s_em + 15)[0];
   b.c0 = p.em_coarse[e]; b.n_warps = n_warps; b.warp = warp; b.lane = lane;
 
-  const unsigned int n_lost0 = is_surface ? queue_dispatch<true, DEPTH>(p, b, uniform, rec_slot >= 0) : queue_dispatch<false, DEPTH>(p, b, uniform, rec_slot >= 0);
+  const unsigned int n_lost0 = is_surface ? queue_dispatch<true, DEPTH, BILIN>(p, b, uniform, rec_slot >= 0) : queue_dispatch<false, DEPTH, BILIN>(p, b, uniform, rec_slot >= 0);
   unsigned int n_lost = n_lost0;
 
   // ---- flush --------------------------------------------------------------------------------------------------
@@ -1201,9 +1229,11 @@ static TraceKernel kernel_variant(bool hist, bool fast, int minb, bool multi, bo
     return (TraceKernel)trace_exchange_sq_kernel<4, 256>;
   }
   if (minb == 6 && hist && fast && !multi && !sq) {                                                     // per-warp ray queue (multi-face meshes)
-    if (queue_depth >= 4) return (TraceKernel)trace_exchange_queue_kernel<4, 4>;
-    if (queue_depth >= 2) return (TraceKernel)trace_exchange_queue_kernel<4, 2>;
-    return (TraceKernel)trace_exchange_queue_kernel<4, 1>;
+    const bool bilin = queue_depth >= 8;                                                                // depth + 8: bilinear faces present
+    const int d = queue_depth & 7;
+    if (d >= 4) return bilin ? (TraceKernel)trace_exchange_queue_kernel<4, 4, true> : (TraceKernel)trace_exchange_queue_kernel<4, 4, false>;
+    if (d >= 2) return bilin ? (TraceKernel)trace_exchange_queue_kernel<4, 2, true> : (TraceKernel)trace_exchange_queue_kernel<4, 2, false>;
+    return bilin ? (TraceKernel)trace_exchange_queue_kernel<4, 1, true> : (TraceKernel)trace_exchange_queue_kernel<4, 1, false>;
   }
   if (multi) {
     if (hist) return fast ? (TraceKernel)trace_exchange_kernel<true, true, 2, true, false> : (TraceKernel)trace_exchange_kernel<true, false, 2, true, false>;
@@ -1224,7 +1254,7 @@ cudaError_t configure_trace_kernel(size_t smem_bytes) {
       for (int hist = 0; hist < 2; ++hist)
         for (int fast = 0; fast < 2; ++fast)
           for (int minb = 2; minb <= 8; ++minb)
-            for (int depth = 1; depth <= 4; depth *= 2) {
+            for (int depth : {1, 2, 4, 9, 10, 12}) {
               cudaError_t e = cudaFuncSetAttribute((const void*)kernel_variant(hist, fast, minb, multi, sq, depth), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
               if (e != cudaSuccess) return e;
             }
@@ -1240,7 +1270,7 @@ int trace_kernel_max_blocks_per_sm(int block_threads, size_t smem_bytes, bool hi
 cudaError_t launch_trace_exchange(const TraceParams& p, int n_blocks, int block_threads, size_t smem_bytes, bool fast, int minb, bool sq,
                                   cudaStream_t stream) {
   if (n_blocks <= 0) return cudaSuccess;
-  TraceKernel k = kernel_variant(p.hist_in_smem != 0, fast, minb, p.multi_bounce != 0, sq, p.queue_depth);
+  TraceKernel k = kernel_variant(p.hist_in_smem != 0, fast, minb, p.multi_bounce != 0, sq, p.queue_depth + (p.queue_bilinear ? 8 : 0));
   void* args[] = {(void*)&p};
   return cudaLaunchKernel((const void*)k, dim3(n_blocks), dim3(block_threads), args, smem_bytes, stream);
 }

@@ -123,13 +123,50 @@ def test_variable_beta_across_faces(rthx_mod, oracle_mod, cuda_lib):
     check_exact(tr.trace(20000, seed=8), ref, 20000, budget_frac=2e-4)
 
 
-def test_non_affine_quad_falls_back_to_generic(rthx_mod, oracle_mod, cuda_lib):
+def test_non_parallelogram_quad_is_a_bilinear_lattice(rthx_mod, oracle_mod, cuda_lib, monkeypatch):
+    """A quadrilateral that is no parallelogram is meshed by meshQuad.jl:116-136 into the bilinear image of a uniform lattice:
+    located by the analytic inverse of the bilinear map in the queue kernel (next to an affine neighbour), by grid +
+    point-in-polygon under RTHX_LOCATOR_GENERIC and when the queue kernel is switched off (lock-step general kernel)."""
     rtm = rthx_mod.meshes.two_quads_domain(kappa=(1.0, 1.0), skew=0.3)
     flat, tr = tracer(rthx_mod, cuda_lib, rtm)
-    assert tr.info["n_affine_faces"] == 1                               # the skewed quad is not a parallelogram
+    assert tr.info["n_affine_faces"] == 1 and tr.info["n_bilinear_faces"] == 1     # the skewed quad is not a parallelogram
     ref = oracle_mod.trace(flat, 20000, seed=9)
     check_exact(tr.trace(20000, seed=9, locator=GENERIC), ref, 20000)
     check_exact(tr.trace(20000, seed=9), ref, 20000, budget_frac=2e-4)
+    monkeypatch.setenv("RTHX_QUEUE_DEPTH", "0")
+    check_exact(tr.trace(20000, seed=9), ref, 20000, budget_frac=2e-4)
+    monkeypatch.delenv("RTHX_QUEUE_DEPTH")
+
+
+def test_bilinear_single_faces_trapezoid_and_general_quad(rthx_mod, oracle_mod, cuda_lib):
+    """Single-face domains that are no parallelograms — a trapezoid (two parallel edges: the quadratic of the inverse map
+    degenerates to a linear equation along one axis) and a general convex quadrilateral — with uniform and with cell-wise
+    varying extinction and a recorder: the bilinear locator against the oracle's grid + point-in-polygon search."""
+    shapes = {
+        "trapezoid": [(0.0, 0.0), (2.0, 0.0), (1.5, 1.0), (0.5, 1.0)],
+        "trapezoid-rotated": [(2.0, 0.0), (1.5, 1.0), (0.5, 1.0), (0.0, 0.0)],
+        "general": [(0.0, 0.0), (2.0, 0.3), (2.3, 1.6), (-0.2, 1.1)],
+    }
+    for name, verts in shapes.items():
+        for variable in (False, True):
+            rtm = _square_from(verts, (7, 5), kappa=0.8)
+            if variable:
+                for i, cell in enumerate(rtm.fine_mesh[0]):
+                    cell.kappa_g = 0.3 + 0.1 * (i % 9)
+                rtm.refresh_spectral_flags()
+                assert rtm.uniform_across_bin == [-1.0]
+            flat, tr = tracer(rthx_mod, cuda_lib, rtm)
+            assert tr.info["n_bilinear_faces"] == 1 and tr.info["n_affine_faces"] == 0, name
+            rpe = 20000
+            ids = [0, 7, flat.n_surfaces + 11]
+            ref = oracle_mod.trace(flat, rpe, seed=47, rec_ids=ids)
+            got = tr.trace(rpe, seed=47, rec_ids=ids)
+            check_exact(got, ref, rpe, budget_frac=2e-5)
+            assert got["stats"]["smem_bytes"] > 10000                    # the queue kernel (40 bytes of queue per ray), not the generic one
+            check_exact(tr.trace(rpe, seed=47, locator=GENERIC), ref, rpe)
+            if got["origins"].shape == ref["origins"].shape:
+                assert np.allclose(got["origins"], ref["origins"], rtol=0, atol=1e-13)
+                assert np.allclose(got["endpoints"], ref["endpoints"], rtol=0, atol=1e-9)
 
 
 def test_determinism_across_launch_shapes_and_shards(rthx_mod, cuda_lib):
