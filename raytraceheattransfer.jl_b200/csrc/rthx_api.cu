@@ -53,7 +53,8 @@ struct rthx_handle : DevRes {
   int device = 0;
   cudaDeviceProp prop{};
   int n_coarse = 0, n_cells = 0, n_bands = 0, ns = 0, N = 0, n_affine = 0, n_bilinear = 0;
-  bool queue_ok = false;       // every face has an analytic locator (affine or bilinear) and a complete neighbour table
+  bool queue_ok = false;       // every face has an analytic locator (affine or bilinear)
+  bool queue_general = false;  // ... but some are bilinear or some interface has no unique neighbour: the general queue variant
   bool coarse_fits_smem = false;
   bool has_eps = false;
   bool single_quad = false;    // one parallelogram coarse face: SQ kernel
@@ -580,10 +581,12 @@ extern "C" int rthx_create(rthx_handle** out, const rthx_mesh* m, int device_id)
   h->face0 = coarse[0];
   h->single_quad = nc == 1 && coarse[0].kind == KIND_AFFINE_QUAD;
   h->queue_ok = h->coarse_fits_smem && h->n_affine + h->n_bilinear == nc;
-  for (int c = 0; c < nc && h->queue_ok; ++c)
+  bool nbr_complete = true;
+  for (int c = 0; c < nc; ++c)
     for (int k = 0; k < coarse[c].nv; ++k)
-      if (!coarse[c].solid[k] && coarse[c].nbr[k] < 0) h->queue_ok = false;   // open / T-junction edge: needs the generic search
-  h->fast_ok = h->queue_ok && h->n_bilinear == 0;   // the FAST form of the general kernel knows the affine kinds only
+      if (!coarse[c].solid[k] && coarse[c].nbr[k] < 0) nbr_complete = false;   // open / T-junction edge: needs the coarse point location
+  h->queue_general = h->n_bilinear > 0 || !nbr_complete;
+  h->fast_ok = h->queue_ok && !h->queue_general;   // the FAST form of the general kernel: affine kinds with a complete neighbour table
   {
     // once per device and process: a few hundred cudaFuncSetAttribute calls cost milliseconds, and callers re-create the
     // handle for every trace
@@ -663,7 +666,7 @@ LaunchPlan make_plan(const rthx_handle* h, const rthx_trace_args* a, int rank, i
   // Multi-face FAST meshes: the queue kernel (per-warp ray queue in shared memory, 40 bytes per parked ray).  Depth = as many
   // rays per lane as still leave 4 resident blocks per SM, at most 8; RTHX_QUEUE_DEPTH overrides (0 = the lock-step kernel).
   if (h->queue_ok && a->locator != RTHX_LOCATOR_GENERIC && !pl.multi && !pl.sq && pl.hist_in_smem && pl.block_threads == 256 &&
-      (h->n_coarse > 1 || h->n_bilinear > 0)) {
+      (h->n_coarse > 1 || h->queue_general)) {
     const size_t base = (pl.smem_bytes + 15) & ~size_t(15);
     const size_t per_depth = (size_t)pl.block_threads * 40;
     const size_t budget = (size_t)h->prop.sharedMemPerMultiprocessor / 4 - 1024;
@@ -678,7 +681,7 @@ LaunchPlan make_plan(const rthx_handle* h, const rthx_trace_args* a, int rank, i
   long long chunks = a->row_chunks;
   if (chunks <= 0) {
     // enough blocks for ~32 waves of the resident set, but keep >= 2048 rays (and >= N/2, the flush scan) per block
-    const int per_sm = std::max(1, trace_kernel_max_blocks_per_sm(pl.block_threads, pl.smem_bytes, pl.hist_in_smem != 0, pl.fast != 0, pl.minb, pl.multi != 0, pl.sq != 0, pl.queue_depth + (h->n_bilinear > 0 ? 8 : 0)));
+    const int per_sm = std::max(1, trace_kernel_max_blocks_per_sm(pl.block_threads, pl.smem_bytes, pl.hist_in_smem != 0, pl.fast != 0, pl.minb, pl.multi != 0, pl.sq != 0, pl.queue_depth + (h->queue_general ? 8 : 0)));
     const long long target = (long long)h->prop.multiProcessorCount * per_sm * 32;
     chunks = rows > 0 ? (target + rows - 1) / rows : 1;
     const long long min_rays = std::max<long long>(2048, h->N / 2);
@@ -703,7 +706,7 @@ void fill_params(const rthx_handle* h, const rthx_trace_args* a, const LaunchPla
   P.compact_rows = compact ? 1 : 0;
   P.row_chunks = pl.row_chunks;
   P.queue_depth = pl.queue_depth;
-  P.queue_bilinear = h->n_bilinear > 0 ? 1 : 0;
+  P.queue_bilinear = h->queue_general ? 1 : 0;
   P.queue_refill = 24;
   if (const char* ev = std::getenv("RTHX_QUEUE_REFILL")) { const int v = std::atoi(ev); if (v >= 0 && v <= 32) P.queue_refill = v; }   // tuning knob
   P.coarse_in_smem = h->coarse_fits_smem ? 1 : 0;
@@ -813,7 +816,7 @@ int pipeline_launch(rthx_handle* h, const rthx_trace_args* a, int rank, int worl
   CU(h, ensure(&h->counts_dev, &h->counts_cap, (size_t)a->n_bins * (size_t)n_owned * N));
   LaunchPlan pl = make_plan(h, a, rank, world);
   // batches: >= ~6 waves of resident blocks each, at most 16
-  const int per_sm = std::max(1, trace_kernel_max_blocks_per_sm(pl.block_threads, pl.smem_bytes, pl.hist_in_smem != 0, pl.fast != 0, pl.minb, pl.multi != 0, pl.sq != 0, pl.queue_depth + (h->n_bilinear > 0 ? 8 : 0)));
+  const int per_sm = std::max(1, trace_kernel_max_blocks_per_sm(pl.block_threads, pl.smem_bytes, pl.hist_in_smem != 0, pl.fast != 0, pl.minb, pl.multi != 0, pl.sq != 0, pl.queue_depth + (h->queue_general ? 8 : 0)));
   const long long resident = (long long)h->prop.multiProcessorCount * per_sm;
   int n_batches = (int)std::min<long long>(16, std::max<long long>(1, pl.n_blocks / (6 * resident)));
   n_batches = std::max(1, std::min(n_batches, n_owned));

@@ -1089,7 +1089,9 @@ __device__ __forceinline__ unsigned int queue_ray_loop(const TraceParams& p, con
         }
         const bool solid = cf.solid[k] != 0;
         const int nc = cf.nbr[k];
-        const bool cross = ok & !gas & edge & !solid & (nc >= 0) & (it < 9999);
+        // BILIN (the general variant) also serves interfaces without a unique neighbour face — T-junctions, open edges — by the
+        // reference's own coarse point location after the advance (traceRay.jl:56-65)
+        const bool cross = ok & !gas & edge & !solid & (BILIN | (nc >= 0)) & (it < 9999);
         const bool tallied = ok & (gas | (edge & solid));               // ends in an element (unless the location fails)
         // traceRay.jl:33,44,56: gas S - nudge, solid wall u - nudge, crossing u + nudge
         const double adv = gas ? Sg - p.nudge : (solid ? u - p.nudge : u + p.nudge);
@@ -1097,31 +1099,48 @@ __device__ __forceinline__ unsigned int queue_ray_loop(const TraceParams& p, con
           px = fma(adv, dx, px);
           py = fma(adv, dy, py);
         }
-        if (cross) {
-          if (UNIFORM) S -= u; else acc += tau_b;
-          c = nc;
-          ++it;
-        } else {
-          active = false;
-          // absorber index of (lattice cell, gas | wall on coarse edge k): ONE table load shared by both endings
-          // (rthx_api.cu builds the table from the lattice -> fine map, the fine cells' vertex counts and cell_surf_id)
-          int absorber = -1;
-          if (tallied) {
-            const int l = lattice_cell<BILIN>(cf, px, py);
-            if (l >= 0) absorber = __ldg(p.abs_tab + (size_t)(cf.abs_off + l) * 5 + (gas ? 0 : 1 + k));
-          }
-          if (absorber >= 0) {
-            atomicAdd(&b.hist[absorber], 1u);
-            if (REC) {
-              const size_t sl = b.rec_row + (size_t)(b.r_begin + (int64_t)r_cur);
-              double* o = p.rec_pts + 4 * sl;
-              o[2] = px; o[3] = py;
-              p.rec_valid[sl] = 1;
-            }
+        // a ray that ends: absorber index of (lattice cell, gas | wall on coarse edge k) in ONE table load shared by both endings
+        // (rthx_api.cu builds the table from the lattice -> fine map, the fine cells' vertex counts and cell_surf_id)
+#define RTHX_QUEUE_FINISH()                                                                                         \
+  do {                                                                                                              \
+    active = false;                                                                                                 \
+    int absorber = -1;                                                                                              \
+    if (tallied) {                                                                                                  \
+      const int l = lattice_cell<BILIN>(cf, px, py);                                                                \
+      if (l >= 0) absorber = __ldg(p.abs_tab + (size_t)(cf.abs_off + l) * 5 + (gas ? 0 : 1 + k));                   \
+    }                                                                                                               \
+    if (absorber >= 0) {                                                                                            \
+      atomicAdd(&b.hist[absorber], 1u);                                                                             \
+      if (REC) {                                                                                                    \
+        const size_t sl = b.rec_row + (size_t)(b.r_begin + (int64_t)r_cur);                                         \
+        double* o = p.rec_pts + 4 * sl;                                                                             \
+        o[2] = px; o[3] = py;                                                                                       \
+        p.rec_valid[sl] = 1;                                                                                        \
+      }                                                                                                             \
+    } else {                                                                                                        \
+      ++n_lost;                                                                                                     \
+    }                                                                                                               \
+  } while (0)
+        if (!BILIN) {
+          if (cross) {
+            if (UNIFORM) S -= u; else acc += tau_b;
+            c = nc;
+            ++it;
           } else {
-            ++n_lost;
+            RTHX_QUEUE_FINISH();
           }
+        } else {
+          bool ended = !cross;
+          if (cross) {
+            if (UNIFORM) S -= u; else acc += tau_b;
+            int nn = nc;
+            if (nn < 0) nn = find_face_generic(p, 0, px, py);
+            if (nn >= 0) { c = nn; ++it; }
+            else ended = true;                                           // left the domain: lost, like the reference's `nothing`
+          }
+          if (ended) RTHX_QUEUE_FINISH();                                // (a failed crossing has tallied == false: counted as lost)
         }
+#undef RTHX_QUEUE_FINISH
       }
     }
     __syncwarp();

@@ -464,3 +464,32 @@ def test_queue_kernel_mixed_quad_and_triangle_faces_with_recorder(rthx_mod, orac
         if got["origins"].shape == ref["origins"].shape:
             assert np.allclose(got["origins"], ref["origins"], rtol=0, atol=1e-13)
             assert np.allclose(got["endpoints"], ref["endpoints"], rtol=0, atol=1e-9)
+
+
+def test_t_junction_interfaces_keep_the_analytic_fine_locator(rthx_mod, oracle_mod, cuda_lib):
+    """One tall face next to two stacked faces: the tall face's open edge has no unique neighbour (a T-junction), so the next
+    coarse face is found by the reference's own point location after the advance (traceRay.jl:56-65) — in the general variant
+    of the queue kernel, which keeps the analytic lattice inverse for every fine-cell lookup."""
+    from rthx import PolyVolume2D, RayTracingDomain2D
+    left = PolyVolume2D([(0.0, 0.0), (1.0, 0.0), (1.0, 2.0), (0.0, 2.0)], (True, False, True, True), 1, 0.7, 0.0)
+    lower = PolyVolume2D([(1.0, 0.0), (2.0, 0.0), (2.0, 1.0), (1.0, 1.0)], (True, True, False, False), 1, 1.4, 0.0)
+    upper = PolyVolume2D([(1.0, 1.0), (2.0, 1.0), (2.0, 2.0), (1.0, 2.0)], (False, True, True, False), 1, 0.2, 0.0)
+    for f in (left, lower, upper):
+        f.epsilon = [1.0] * 4
+        f.T_in_w = [0.0] * 4
+        f.T_in_g = -1.0
+        f.q_in_g = 0.0
+    rtm = RayTracingDomain2D([left, lower, upper], [(3, 6), (4, 4), (5, 3)])
+    flat, tr = tracer(rthx_mod, cuda_lib, rtm)
+    assert tr.info["n_affine_faces"] == 3 and tr.info["n_bilinear_faces"] == 0
+    rpe = 20000
+    ref = oracle_mod.trace(flat, rpe, seed=53)
+    got = tr.trace(rpe, seed=53)
+    check_exact(got, ref, rpe, budget_frac=2e-4)
+    assert got["stats"]["smem_bytes"] > 10000                            # queue kernel
+    check_exact(tr.trace(rpe, seed=53, locator=GENERIC), ref, rpe)
+    # rays do cross the T-junction in both directions
+    ns = flat.n_surfaces
+    n_left = 18
+    c = got["counts"][0]
+    assert c[ns:ns + n_left, ns + n_left:].sum() > 1000 and c[ns + n_left:, ns:ns + n_left].sum() > 1000
