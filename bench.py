@@ -54,12 +54,12 @@ def parse_args():
 
 
 # DRAM bytes per launch of the trace kernel measured by ncu --set full (dram__bytes_read.sum + dram__bytes_write.sum)
-NCU_DRAM_BYTES_PER_LAUNCH = {"cfg3": (895.0e6 + 835.0e6, "profiles/r1k_trace_exchange_sq_metrics.csv"),
-                             "cfg5": (None, "profiles/r1k_trace_exchange_queue_metrics.csv")}
+NCU_DRAM_BYTES_PER_LAUNCH = {"cfg3": (894.04e6 + 833.20e6, "profiles/r1y_trace_exchange_sq_metrics.csv"),
+                             "cfg5": (None, "profiles/r1y_trace_exchange_queue_metrics.csv")}
 
 # executed warp instructions per 32 rays of the trace kernel (ncu source page, profiles/<capture>_sass_mix.csv, TOTAL row)
-NCU_WARP_INSTR_PER_32_RAYS = {"cfg3": (245.6, "profiles/r1p_trace_exchange_sq_sass_mix.csv"),
-                              "cfg5": (680.9, "profiles/r1p_trace_exchange_queue_sass_mix.csv")}
+NCU_WARP_INSTR_PER_32_RAYS = {"cfg3": (250.5, "profiles/r1y_trace_exchange_sq_sass_mix.csv"),
+                              "cfg5": (680.9, "profiles/r1y_trace_exchange_queue_sass_mix.csv")}
 
 DEFAULT_RAYS = {"cfg1": 1e6, "cfg2": 1e8, "cfg3": 1e10, "cfg4": 1e8, "cfg5": 1e9}
 
