@@ -101,7 +101,9 @@ def run_oracle_sample(flat, bins, rays_total, seed):
     N = flat.n_elements
     rpe = max(1, int(rays_total) // (N * len(bins)))
     t0 = time.perf_counter()
-    out = oracle.trace(flat, rpe, seed=seed, bins=bins, n_threads=0)
+    # every host core this process may run on, set explicitly: torchrun exports OMP_NUM_THREADS=1 to its workers
+    n_threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    out = oracle.trace(flat, rpe, seed=seed, bins=bins, n_threads=n_threads)
     dt = time.perf_counter() - t0
     traced = rpe * N * len(bins)
     return dict(rays_per_s=traced / dt, seconds=dt, rays=traced, rpe=rpe, stats=out["stats"])
