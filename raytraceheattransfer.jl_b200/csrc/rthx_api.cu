@@ -577,7 +577,7 @@ extern "C" int rthx_create(rthx_handle** out, const rthx_mesh* m, int device_id)
   h->rec_slot_dev = (int32_t*)(b8 + o_rec);
   h->lost_dev = (unsigned long long*)(b8 + o_lost); h->lost_cap = ((size_t)nb * 4 + 16) * (size_t)N;
   P.n_coarse = nc; P.n_cells = ncell; P.n_surfaces = ns; P.N = N;
-  h->coarse_fits_smem = sizeof(CoarseDev) * (size_t)nc <= 32 * 1024;
+  h->coarse_fits_smem = sizeof(CoarseDev) * (size_t)nc <= 96 * 1024;   // 384 coarse faces; more are read through L1/L2 by the generic kernel
   h->face0 = coarse[0];
   h->single_quad = nc == 1 && coarse[0].kind == KIND_AFFINE_QUAD;
   h->queue_ok = h->coarse_fits_smem && h->n_affine + h->n_bilinear == nc;
@@ -669,8 +669,12 @@ LaunchPlan make_plan(const rthx_handle* h, const rthx_trace_args* a, int rank, i
       (h->n_coarse > 1 || h->queue_general)) {
     const size_t base = (pl.smem_bytes + 15) & ~size_t(15);
     const size_t per_depth = (size_t)pl.block_threads * 40;
-    const size_t budget = (size_t)h->prop.sharedMemPerMultiprocessor / 4 - 1024;
-    int depth = base < budget ? (int)std::min<size_t>(4, (budget - base) / per_depth) : 0;
+    // aim at 4 resident blocks per SM; large descriptor tables / histograms settle for 3, 2 or 1
+    int depth = 0;
+    for (int blocks = 4; blocks >= 1 && depth == 0; --blocks) {
+      const size_t budget = std::min((size_t)h->prop.sharedMemPerMultiprocessor / blocks - 1024, (size_t)h->prop.sharedMemPerBlockOptin);
+      if (base + per_depth <= budget) depth = (int)std::min<size_t>(4, (budget - base) / per_depth);
+    }
     if (const char* ev = std::getenv("RTHX_QUEUE_DEPTH")) { const int v = std::atoi(ev); if (v >= 0 && v <= 4) depth = v; }
     if (depth == 3) depth = 2;                       // compiled depths: 1, 2, 4 rays per lane and batch
     if (depth >= 1 && base + depth * per_depth <= h->prop.sharedMemPerBlockOptin) {

@@ -276,17 +276,20 @@ def test_global_tally_fallback_path(rthx_mod, oracle_mod, cuda_lib, monkeypatch)
         check_exact(got, ref, 3000, budget_frac=2e-4)
 
 
-def test_many_coarse_faces_descriptors_in_global_memory(rthx_mod, oracle_mod, cuda_lib):
-    """More coarse faces than fit the 32 KB shared-memory staging area (150 wedges): descriptors are read through
-    L1/L2 and the kernel takes the non-FAST variant."""
-    rtm = rthx_mod.meshes.circle_domain(150, 2, half_hot=False)
-    flat, tr = tracer(rthx_mod, cuda_lib, rtm)
-    assert tr.info["n_affine_faces"] == 150
-    ref = oracle_mod.trace(flat, 4000, seed=32)
-    check_exact(tr.trace(4000, seed=32, locator=GENERIC), ref, 4000)
-    auto = tr.trace(4000, seed=32)
-    check_exact(auto, ref, 4000, budget_frac=5e-4)
-    assert auto["lost"].sum() <= ref["lost"].sum()
+def test_many_coarse_faces(rthx_mod, oracle_mod, cuda_lib):
+    """150 wedges: 38 KB of coarse descriptors still ride in shared memory next to the ray queue (fewer resident blocks);
+    600 wedges: more than the 96 KB staging limit, descriptors are read through L1/L2 and the kernel takes the non-FAST variant."""
+    for n_wedges, rpe in ((150, 4000), (600, 300)):
+        rtm = rthx_mod.meshes.circle_domain(n_wedges, 2, half_hot=False)
+        flat, tr = tracer(rthx_mod, cuda_lib, rtm)
+        assert tr.info["n_affine_faces"] == n_wedges
+        ref = oracle_mod.trace(flat, rpe, seed=32)
+        check_exact(tr.trace(rpe, seed=32, locator=GENERIC), ref, rpe)
+        auto = tr.trace(rpe, seed=32)
+        check_exact(auto, ref, rpe, budget_frac=5e-4)
+        assert auto["lost"].sum() <= ref["lost"].sum()
+        queue = auto["stats"]["smem_bytes"] > 256 * n_wedges + 10000       # descriptors + ray queue in shared memory
+        assert queue == (n_wedges == 150)
 
 
 def test_open_boundary_loses_rays_like_the_reference(rthx_mod, oracle_mod, cuda_lib):
