@@ -26,7 +26,10 @@
  * Parity pin: Julia is not installed in this image, so the reference cannot be executed; the oracle is
  * pinned against the reference's own golden vectors for this path — the Crosbie & Schrenker (1984) centre-line
  * table of test/test_2d_grey.jl:25-33 with its rtol=0.05 norm test (:216), the circle-centre temperature of
- * test/test_triangle_mesh.jl:66-69 — and against closed-form known answers (tests/test_oracle_*.py).
+ * test/test_triangle_mesh.jl:66-69, the parallel-plate flux of test/test_2d_grey_reflecting.jl:96-136 and the
+ * diffusion-limit source function of test/test_2d_diffusion.jl:19-23,57-76 — and against closed-form known
+ * answers (tests/test_oracle_*.py).  No golden F matrix or seed exists in the reference (its RNG is unseeded):
+ * F itself is pinned statistically, through these.
  */
 #include "rthx_oracle.h"
 
