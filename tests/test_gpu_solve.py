@@ -199,3 +199,20 @@ def test_diffusion_limit_through_the_public_call(rthx_mod, cuda_lib):
     err_ap = rms()
     assert err_ap < 0.02 and err_ap < 0.5 * err_raw
     assert abs(rtm.energy_error) < 1e-6 * 1.0e3
+
+
+def test_circle_golden_vectors_through_the_public_call(rthx_mod, cuda_lib):
+    """The reference's triangle-mesh validation (test/test_triangle_mesh.jl) through the public call on the GPU — queue kernel,
+    device-side smoothing, device-side solve: an isothermal rim gives T_g = T_hot within 1e-3 K (:44-45); with half the rim hot
+    the mean of the 16 centre cells is 840.896 K within 2 K (:66-69)."""
+    rtm = rthx_mod.meshes.circle_domain(16, 2, half_hot=False)
+    F = rtm(2_000_000, method="exchange", verbose=False, seed=9)
+    rthx_mod.solveEquilibrium(rtm, F, verbose=False)
+    T = np.array([c.T_g for fine in rtm.fine_mesh for c in fine])
+    assert T.min() > 1000 - 1e-3 and T.max() < 1000 + 1e-3
+    rtm2 = rthx_mod.meshes.circle_domain(16, 11, half_hot=True)
+    F2 = rtm2(100_000_000, method="exchange", verbose=False, seed=10)
+    rthx_mod.solveEquilibrium(rtm2, F2, verbose=False)
+    T_mid = np.array([fine[0].T_g for fine in rtm2.fine_mesh])
+    assert abs(840.896 - T_mid.mean()) < 2.0
+    assert abs(rtm2.energy_error) < 1e-4
