@@ -48,6 +48,9 @@ def parse_args():
     ap.add_argument("--row-chunks", type=int, default=0)
     ap.add_argument("--locator", default="auto", choices=["auto", "generic"],
                     help="generic = the reference-faithful grid + point-in-polygon locator everywhere (the path arbitrary, non-affine meshes take)")
+    ap.add_argument("--mode", default="first_interaction", choices=["first_interaction", "multi_bounce", "multi_bounce_specular"],
+                    help="first_interaction = what method=:exchange computes (the headline); multi_bounce = total-exchange mode, rays followed "
+                         "through scattering / wall reflection until absorbed (rthx.h RTHX_MULTI_BOUNCE)")
     ap.add_argument("--reduce", default="fused", choices=["fused", "nccl"],
                     help="N > 1: fused peer-memory flush over NVLink (default) or a private matrix per rank + NCCL reduce")
     return ap.parse_args()
@@ -266,7 +269,8 @@ def main():
     traced_per_step = rpe * N * nb
 
     sh = ShardedTracer(flat, device=local_rank, rank=rank, world=world, n_bins=nb, mode=args.reduce)
-    kw = dict(bins=bins, block_threads=args.block_threads, row_chunks=args.row_chunks, locator=1 if args.locator == "generic" else 0)
+    kw = dict(bins=bins, block_threads=args.block_threads, row_chunks=args.row_chunks, locator=1 if args.locator == "generic" else 0,
+              mode={"first_interaction": 0, "multi_bounce": 1, "multi_bounce_specular": 2}[args.mode])
     stream = torch.cuda.current_stream(dev)
 
     def step(seed, time_kernel=None):
@@ -455,7 +459,8 @@ def main():
     kernel_rays_per_s = (traced_per_step / world) / (kernel_ms * 1e-3)
     achieved = kernel_rays_per_s * A / 1e12
     info = sh.tracer.info
-    kernel_name = ("trace_exchange_kernel (generic locator)" if args.locator == "generic" else
+    kernel_name = ("trace_exchange_kernel<MULTI> (multi-bounce)" if args.mode != "first_interaction" else
+                   "trace_exchange_kernel (generic locator)" if args.locator == "generic" else
                    "trace_exchange_sq_kernel" if info["n_coarse"] == 1 and info["n_affine_faces"] == 1 else
                    "trace_exchange_queue_kernel" if info["n_affine_faces"] == info["n_coarse"] else "trace_exchange_kernel")
     hbm_bytes_per_ray = 8.0 * N * N * nb / world / max(1, traced_per_step / world)

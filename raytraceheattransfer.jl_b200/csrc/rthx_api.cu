@@ -649,18 +649,14 @@ LaunchPlan make_plan(const rthx_handle* h, const rthx_trace_args* a, int rank, i
   const size_t hist_bytes = sizeof(uint32_t) * (size_t)h->N, em_bytes = sizeof(double) * 16 + 16 * (size_t)LOGTAB_N;   // emitter block + log table
   pl.hist_in_smem = (coarse_bytes + em_bytes + hist_bytes <= h->prop.sharedMemPerBlockOptin) ? 1 : 0;
   if (const char* ev = std::getenv("RTHX_FORCE_GLOBAL_TALLY")) { if (std::atoi(ev)) pl.hist_in_smem = 0; }   // test knob: the N > ~57k path
-  pl.sq = (h->single_quad && a->locator != RTHX_LOCATOR_GENERIC && !pl.multi && pl.hist_in_smem) ? 1 : 0;
+  pl.sq = (h->single_quad && a->locator != RTHX_LOCATOR_GENERIC && pl.hist_in_smem) ? 1 : 0;
   if (const char* ev = std::getenv("RTHX_NO_SQ")) { if (std::atoi(ev)) pl.sq = 0; }   // test / tuning knob
-  if (pl.sq) {
+  if (pl.sq && pl.multi) {
+    pl.fast = 1; pl.minb = 4;                        // trace_exchange_sq_kernel<4, MULTI>
+  } else if (pl.sq) {
     pl.fast = 1; pl.minb = 4;
-    // tuning knobs: 5 = 48 registers, 5 blocks / SM; 3 = the shared-loop SQ branch of the general kernel (A/B reference)
-    if (const char* ev = std::getenv("RTHX_MINB")) { const int v = std::atoi(ev); if (v == 5 || v == 3) pl.minb = v; }
-    // block shape knob: 288 / 320 threads (9 / 10 warps) at 4 blocks per SM trade registers (56 / 48) for resident warps
-    if (const char* ev = std::getenv("RTHX_SQ_THREADS")) {
-      const int v = std::atoi(ev);
-      if (v == 288 && !a->block_threads) { pl.minb = 7; pl.block_threads = 288; }
-      if (v == 320 && !a->block_threads) { pl.minb = 8; pl.block_threads = 320; }
-    }
+    // tuning knob: 3 = the shared-loop SQ branch of the general kernel (A/B reference)
+    if (const char* ev = std::getenv("RTHX_MINB")) { const int v = std::atoi(ev); if (v == 3) pl.minb = v; }
   }
   pl.smem_bytes = coarse_bytes + em_bytes + (pl.hist_in_smem ? hist_bytes : 0);
   // Multi-face FAST meshes: the queue kernel (per-warp ray queue in shared memory, 40 bytes per parked ray).  Depth = as many

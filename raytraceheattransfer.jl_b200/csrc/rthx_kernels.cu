@@ -704,6 +704,8 @@ struct SqBlock {            // block-uniform state of one (emitter row, band, ch
   const double* beta_band;  // per-cell beta of the band (non-uniform bins)
   double inv_beta_u;
   uint32_t sel_thr;         // volume emitters: take triangle ABC iff Philox word <= sel_thr
+  const double* omega_band; // MULTI_BOUNCE: scattering albedo per cell of the band
+  const double* eps_band;   // MULTI_BOUNCE: emissivity per surface of the band
   uint32_t e, cw;
   int64_t ray0;             // ray id of the block's first ray
   uint32_t n_rays;          // rays of this block
@@ -841,14 +843,127 @@ __device__ __forceinline__ unsigned int sq_ray_loop(const TraceParams& p, const 
   return n_lost;
 }
 
-template <bool SURF, bool AXIS>
+// RTHX_MULTI_BOUNCE on the single-quad domain (the analogue of method=:direct's traceSingleRay.jl:7-81 without re-emission): the
+// ray is followed through scattering (isotropicScatter2D.jl:1-4) and wall reflection (diffuse: sampleReflectionDirection2D.jl:5-16
+// + lambertSample2D; specular: mirror) until it is absorbed; two more Philox calls per event exactly as in trace_exchange_kernel
+// <..., MULTI> (call# 2+2n: decision, azimuth, cos(theta), roulette; 3+2n: polar angle, next free path), the same fast arithmetic
+// as the first-interaction loop for everything else.
+template <bool SURF, bool UNIFORM, bool REC, bool AXIS>
+__device__ __forceinline__ unsigned int sq_multi_loop(const TraceParams& p, const SqBlock& b) {
+  const CoarseDev& cf = p.face0;
+  uint32_t hist_s;
+  asm volatile("mov.u32 %0, %1;" : "=r"(hist_s) : "r"((uint32_t)__cvta_generic_to_shared(b.hist)));
+  unsigned int n_lost = 0;
+  for (uint32_t i = threadIdx.x; i < b.n_rays; i += blockDim.x) {
+    const uint64_t ray_id = (uint64_t)(b.ray0 + (int64_t)i);
+    const uint32_t c_lo = (uint32_t)ray_id, c_hi = (uint32_t)(ray_id >> 32);
+    double px, py, dx, dy, dy_m, R_S;
+    int dy_hi;
+    {
+      const uint4 w0 = philox4x32_10_rk(make_uint4(c_lo, c_hi, b.e, b.cw | 0u), p.rk);
+      const uint4 w1 = philox4x32_10_rk(make_uint4(c_lo, c_hi, b.e, b.cw | 1u), p.rk);
+      emit_ray_folded<SURF>(p, b.s_em, b.sel_thr, w0, w1, px, py, dx, dy, dy_m, dy_hi, R_S);
+    }
+    if (REC) {
+      double* o = p.rec_pts + 4 * (b.rec_base + i);
+      o[0] = px; o[1] = py;
+    }
+    double neg_log = neg_log_table(R_S, b.s_log);
+    int absorber = -1;
+#pragma unroll 1
+    for (int event = 0;; ++event) {
+      // ---- first interaction from (p, d, -log R) ----
+      int k;
+      double u;
+      const bool edge = dist_sq<AXIS>(p, px, py, dx, dy, dy_m, dy_hi, u, k);
+      double S;
+      bool gas, ok = true;
+      if (UNIFORM) {
+        S = neg_log * b.inv_beta_u;
+        gas = S < u;
+      } else {
+        const int f0 = locate_sq<AXIS>(p, px, py);
+        ok = f0 >= 0;
+        const double local_beta = ok ? b.beta_band[f0] : 0.0;
+        gas = local_beta * u >= neg_log;
+        S = neg_log / local_beta;
+      }
+      absorber = -1;
+      const bool hit = !gas & edge & (cf.solid[k] != 0);
+      if (ok & (gas | hit)) {
+        const double adv = (gas ? S : u) - p.nudge;
+        px = fma(adv, dx, px);
+        py = fma(adv, dy, py);
+        const int f = locate_sq<AXIS>(p, px, py);
+        if (f >= 0) {
+          int sid = p.n_surfaces + f;
+          if (!gas) sid = __ldg(p.abs_tab + (unsigned)(f * 5 + 1 + k));
+          absorber = sid;
+        }
+      }
+      if (absorber < 0) break;                                     // lost
+      // ---- absorb, scatter or reflect (traceSingleRay.jl:24-79) ----
+      if (event >= 16000) { absorber = -1; break; }                // call# is a 16-bit field
+      const uint4 v0 = philox4x32_10_rk(make_uint4(c_lo, c_hi, b.e, b.cw | (uint32_t)(2 + 2 * event)), p.rk);
+      const uint4 v1 = philox4x32_10_rk(make_uint4(c_lo, c_hi, b.e, b.cw | (uint32_t)(3 + 2 * event)), p.rk);
+      if (event >= 1000 && u32d(v0.w, p.k_u32) > 0.8) { absorber = -1; break; }   // Russian roulette, traceSingleRay.jl:11
+      const double dec = u32d(v0.x, p.k_u32);
+      if (absorber >= p.n_surfaces) {
+        if (!(dec < b.omega_band[absorber - p.n_surfaces])) break;                  // absorbed in the gas
+        // isotropicScatter2D.jl:1-4: theta = acos(2R - 1), phi = 2 pi R; with c = R - 1/2: cos = 2c, sin = 2 sqrt(1/4 - c^2)
+        const double c = __hiloint2double((int)(0x3FF00000u | (v1.y >> 12)), (int)((v1.y << 20) | (v1.x >> 12))) - p.k_u52c;
+        dx = sqrt_pos(fma(-c, c, 0.25)) * cos2pi_centered_x2(u32d_centered(v0.y, p.k_u32c));
+        dy = c + c;
+      } else {
+        if (dec < b.eps_band[absorber]) break;                                      // absorbed by the wall
+        const double hnx = cf.nx[k], hny = cf.ny[k];               // outward normal of the coarse edge (= of every fine wall on it)
+        if (p.specular) {
+          const double dn = dx * hnx + dy * hny;                   // mirror the in-plane components; the axial one is unchanged
+          dx = fma(-2.0 * dn, hnx, dx);
+          dy = fma(-2.0 * dn, hny, dy);
+        } else {
+          // diffuse: Lambert about the inward normal n = -hit_n with x-axis (n.y, -n.x)
+          const float cosT = __fsqrt_rn(u23(v0.z));
+          const float cos2 = __fmul_rn(cosT, cosT);
+          const double xdir = sqrt_pos(1.0 - (double)cos2) * cos2pi_centered((double)u23(v0.y) - 0.5);
+          const double zdir = (double)cosT;
+          const double nxi = -hnx, nyi = -hny;
+          const double ndx = nyi * xdir + nxi * zdir;
+          dy = -nxi * xdir + nyi * zdir;
+          dx = ndx;
+        }
+      }
+      dy_m = dy;
+      dy_hi = __double2hiint(dy);
+      neg_log = neg_log_table(u52(v1.z, v1.w, p.k_u52), b.s_log);
+    }
+    if (absorber >= 0) {
+      asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(hist_s + 4u * (uint32_t)absorber), "r"(1u) : "memory");
+      if (REC) {
+        const size_t sl = b.rec_base + i;
+        double* o = p.rec_pts + 4 * sl;
+        o[2] = px; o[3] = py;
+        p.rec_valid[sl] = 1;
+      }
+    } else {
+      ++n_lost;
+    }
+  }
+  return n_lost;
+}
+
+template <bool SURF, bool AXIS, bool MULTI>
 __device__ __forceinline__ unsigned int sq_dispatch(const TraceParams& p, const SqBlock& b, bool uniform, bool rec) {
+  if (MULTI) {
+    if (uniform) return rec ? sq_multi_loop<SURF, true, true, AXIS>(p, b) : sq_multi_loop<SURF, true, false, AXIS>(p, b);
+    return rec ? sq_multi_loop<SURF, false, true, AXIS>(p, b) : sq_multi_loop<SURF, false, false, AXIS>(p, b);
+  }
   if (uniform) return rec ? sq_ray_loop<SURF, true, true, AXIS>(p, b) : sq_ray_loop<SURF, true, false, AXIS>(p, b);
   return rec ? sq_ray_loop<SURF, false, true, AXIS>(p, b) : sq_ray_loop<SURF, false, false, AXIS>(p, b);
 }
 
-template <int MINB, int THREADS>
-__global__ void __launch_bounds__(THREADS, MINB) trace_exchange_sq_kernel(const __grid_constant__ TraceParams p) {
+template <int MINB, bool MULTI>
+__global__ void __launch_bounds__(256, MINB) trace_exchange_sq_kernel(const __grid_constant__ TraceParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* s_em = reinterpret_cast<double*>(smem_raw);
   double2* s_log = reinterpret_cast<double2*>(smem_raw + sizeof(double) * EM_DOUBLES);
@@ -888,6 +1003,7 @@ __global__ void __launch_bounds__(THREADS, MINB) trace_exchange_sq_kernel(const 
   b.s_em = s_em; b.s_log = s_log; b.hist = hist; b.beta_band = beta_band;
   b.inv_beta_u = beta_u > 0.0 ? 1.0 / beta_u : CUDART_INF;
   b.sel_thr = reinterpret_cast<const uint32_t*>(s_em + 15)[0];
+  b.omega_band = p.omega + (size_t)band * p.n_cells; b.eps_band = p.eps + (size_t)band * p.n_surfaces;
   b.e = (uint32_t)e; b.cw = ((uint32_t)band << 16);
   b.ray0 = p.ray_id_offset + r_begin;
   b.n_rays = r_end > r_begin ? (uint32_t)(r_end - r_begin) : 0u;
@@ -895,8 +1011,8 @@ __global__ void __launch_bounds__(THREADS, MINB) trace_exchange_sq_kernel(const 
 
   unsigned int n_lost;
   const bool rec = rec_slot >= 0;
-  if (p.sq_axis) n_lost = is_surface ? sq_dispatch<true, true>(p, b, uniform, rec) : sq_dispatch<false, true>(p, b, uniform, rec);
-  else           n_lost = is_surface ? sq_dispatch<true, false>(p, b, uniform, rec) : sq_dispatch<false, false>(p, b, uniform, rec);
+  if (p.sq_axis) n_lost = is_surface ? sq_dispatch<true, true, MULTI>(p, b, uniform, rec) : sq_dispatch<false, true, MULTI>(p, b, uniform, rec);
+  else           n_lost = is_surface ? sq_dispatch<true, false, MULTI>(p, b, uniform, rec) : sq_dispatch<false, false, MULTI>(p, b, uniform, rec);
 
   for (int off = 16; off > 0; off >>= 1) n_lost += __shfl_down_sync(0xffffffffu, n_lost, off);
   if ((threadIdx.x & 31) == 0 && n_lost) {
@@ -1240,12 +1356,10 @@ __global__ void __launch_bounds__(256, MINB) trace_exchange_queue_kernel(const _
 // kernel variants: hist_in_smem x fast x multi; the register bound MINB only varies for the hot FIRST_INTERACTION FAST kernel
 typedef void (*TraceKernel)(const TraceParams);
 static TraceKernel kernel_variant(bool hist, bool fast, int minb, bool multi, bool sq, int queue_depth = 0) {
+  if (sq && hist && fast && multi) return (TraceKernel)trace_exchange_sq_kernel<4, true>;   // multi-bounce on the single-quad domain
   if (sq && hist && fast && !multi) {
-    if (minb == 5) return (TraceKernel)trace_exchange_sq_kernel<5, 256>;                    // RTHX_MINB=5: 48 registers, 5 blocks / SM (A/B knob)
-    if (minb == 7) return (TraceKernel)trace_exchange_sq_kernel<4, 288>;                    // 4 blocks of 9 warps: 56 registers, 36 warps / SM
-    if (minb == 8) return (TraceKernel)trace_exchange_sq_kernel<4, 320>;                    // 4 blocks of 10 warps: 48 registers, 40 warps / SM
     if (minb == 3) return (TraceKernel)trace_exchange_kernel<true, true, 4, false, true>;   // RTHX_MINB=3: the shared-loop form (A/B knob)
-    return (TraceKernel)trace_exchange_sq_kernel<4, 256>;
+    return (TraceKernel)trace_exchange_sq_kernel<4, false>;
   }
   if (minb == 6 && hist && fast && !multi && !sq) {                                                     // per-warp ray queue (multi-face meshes)
     const bool bilin = queue_depth >= 8;                                                                // depth + 8: bilinear faces present
@@ -1272,7 +1386,7 @@ cudaError_t configure_trace_kernel(size_t smem_bytes) {
     for (int multi = 0; multi < 2; ++multi)
       for (int hist = 0; hist < 2; ++hist)
         for (int fast = 0; fast < 2; ++fast)
-          for (int minb = 2; minb <= 8; ++minb)
+          for (int minb = 2; minb <= 6; ++minb)
             for (int depth : {1, 2, 4, 9, 10, 12}) {
               cudaError_t e = cudaFuncSetAttribute((const void*)kernel_variant(hist, fast, minb, multi, sq, depth), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
               if (e != cudaSuccess) return e;

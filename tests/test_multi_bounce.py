@@ -109,3 +109,37 @@ def test_gpu_multi_bounce_reduces_to_first_interaction(rthx_mod, cuda_lib):
     a = tr.trace(3000, seed=9)
     b = tr.trace(3000, seed=9, mode=MULTI)
     assert np.array_equal(a["counts"], b["counts"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", [MULTI, SPECULAR])
+def test_gpu_parity_multi_bounce_single_quad_variants(oracle_mod, rthx_mod, cuda_lib, mode):
+    """The single-quad multi-bounce loop (trace_exchange_sq_kernel<MULTI>) in its specialisations: axis-aligned and rotated
+    (general slab arithmetic, oblique wall normals for the reflection), uniform and per-cell extinction / albedo, recorder on."""
+    import math
+    from helpers import n_differing_rays
+    cases = []
+    for rot in (0.0, math.pi / 5):
+        for vary in (False, True):
+            rtm = rthx_mod.meshes.square_domain(7, kappa=0.6, sigma_s=0.9, epsilon=(0.3, 0.6, 0.9, 0.5), rotation_angle=rot)
+            if vary:
+                for i, cell in enumerate(rtm.fine_mesh[0]):
+                    cell.kappa_g = 0.2 + 0.1 * (i % 7)
+                    cell.sigma_s_g = 0.1 * (i % 5)
+                rtm.refresh_spectral_flags()
+                assert rtm.uniform_across_bin == [-1.0]
+            cases.append(rtm)
+    for rtm in cases:
+        flat = rthx_mod.flatten_domain(rtm)
+        tr = rthx_mod.DeviceTracer(flat, device=0)
+        rpe = 8000
+        ids = [2, flat.n_surfaces + 5]
+        ref = oracle_mod.trace(flat, rpe, seed=12, mode=mode, rec_ids=ids)
+        got = tr.trace(rpe, seed=12, mode=mode, rec_ids=ids)
+        assert np.all(got["counts"].sum(axis=2) + got["lost"] == rpe)
+        nd = n_differing_rays(got["counts"], ref["counts"])
+        total = int(ref["counts"].sum())
+        assert nd <= max(2, int(3e-4 * total)), (nd, total)
+        if got["origins"].shape == ref["origins"].shape:
+            assert np.allclose(got["origins"], ref["origins"], rtol=0, atol=1e-13)
+            assert np.mean(np.abs(got["endpoints"] - ref["endpoints"]).max(axis=1) < 1e-9) > 0.999
