@@ -809,16 +809,31 @@ int enqueue_trace(rthx_handle* h, const rthx_trace_args* a, int rank, int world,
 // compute streams (so the tail of one batch overlaps the head of the next) and whose device->host copies run on a third
 // stream as soon as the batch's kernel has finished.  All work is enqueued; the caller synchronises copy_stream.
 //   ev[0] start, ev[1] first kernel start, ev[2] last kernel end, ev[3] last copy end.
+// Row range of batch b of the pipelined host-output trace.  The last four batches are a quarter of the others: what follows the
+// last kernel is the device->host copy of the last batch only, so a short last batch shortens the tail of the call (cfg3: 56 MB
+// -> 17 MB behind the last kernel).  Fewer than 8 batches are split evenly.
+void batch_rows_of(int n_owned, int n_batches, int b, int& y0, int& y1) {
+  if (n_batches < 8) {
+    y0 = (int)((long long)n_owned * b / n_batches); y1 = (int)((long long)n_owned * (b + 1) / n_batches);
+    return;
+  }
+  const long long units = 4LL * (n_batches - 4) + 4;            // full batches weigh 4, the last four 1
+  auto edge = [&](int k) { return k <= n_batches - 4 ? 4LL * k : 4LL * (n_batches - 4) + (k - (n_batches - 4)); };
+  y0 = (int)((long long)n_owned * edge(b) / units); y1 = (int)((long long)n_owned * edge(b + 1) / units);
+}
+
 int pipeline_launch(rthx_handle* h, const rthx_trace_args* a, int rank, int world, bool with_rec, int n_slots,
                     LaunchPlan* plan_out, int* n_launches, int* n_batches_out) {
   const int N = h->N;
   const int n_owned = (N - rank + world - 1) / world;
   CU(h, ensure(&h->counts_dev, &h->counts_cap, (size_t)a->n_bins * (size_t)n_owned * N));
   LaunchPlan pl = make_plan(h, a, rank, world);
-  // batches: >= ~6 waves of resident blocks each, at most 16
+  // batches: >= ~2 waves of resident blocks each, at most 16 (consecutive batches alternate between two streams, so a batch's
+  // draining tail overlaps the next one's head; cfg3 at 1e10 rays: 16 batches, the copy behind the last kernel is 17 MB and the
+  // call ends 0.5 ms after the kernel — with 5 even batches it was 180 MB and 3.6 ms)
   const int per_sm = std::max(1, trace_kernel_max_blocks_per_sm(pl.block_threads, pl.smem_bytes, pl.hist_in_smem != 0, pl.fast != 0, pl.minb, pl.multi != 0, pl.sq != 0, pl.queue_depth + (h->queue_general ? 8 : 0)));
   const long long resident = (long long)h->prop.multiProcessorCount * per_sm;
-  int n_batches = (int)std::min<long long>(16, std::max<long long>(1, pl.n_blocks / (6 * resident)));
+  int n_batches = (int)std::min<long long>(16, std::max<long long>(1, pl.n_blocks / (2 * resident)));
   n_batches = std::max(1, std::min(n_batches, n_owned));
   if (const char* ev = std::getenv("RTHX_BATCHES")) { const int v = std::atoi(ev); if (v >= 1 && v <= 16) n_batches = std::min(v, std::max(1, n_owned)); }
   CU(h, cudaMemcpyAsync(h->bins_dev, a->bins, sizeof(int32_t) * (size_t)a->n_bins, cudaMemcpyHostToDevice, h->stream));
@@ -828,7 +843,8 @@ int pipeline_launch(rthx_handle* h, const rthx_trace_args* a, int rank, int worl
   CU(h, cudaEventRecord(h->ev[1], h->stream));
   CU(h, cudaStreamWaitEvent(h->stream2, h->ev[1], 0));
   for (int b = 0; b < n_batches; ++b) {
-    const int y0 = (int)((long long)n_owned * b / n_batches), y1 = (int)((long long)n_owned * (b + 1) / n_batches);
+    int y0, y1;
+    batch_rows_of(n_owned, n_batches, b, y0, y1);
     cudaStream_t cs = (b & 1) ? h->stream2 : h->stream;
     LaunchPlan tmp{};
     int rc = enqueue_trace(h, a, rank, world, /*compact=*/true, h->counts_dev, h->lost_dev, RTHX_ZERO_NONE, with_rec, n_slots, cs, &tmp, n_launches, y0, y1,
@@ -872,7 +888,7 @@ int pipeline_copy(rthx_handle* h, const rthx_trace_args* a, int rank, int world,
   cudaGetLastError();
   if (const char* ev = std::getenv("RTHX_FORCE_STAGING")) { if (std::atoi(ev)) pinned = false; }
   const size_t row_bytes = sizeof(uint64_t) * (size_t)N;
-  auto batch_rows = [&](int b, int& y0, int& y1) { y0 = (int)((long long)n_owned * b / n_batches); y1 = (int)((long long)n_owned * (b + 1) / n_batches); };
+  auto batch_rows = [&](int b, int& y0, int& y1) { batch_rows_of(n_owned, n_batches, b, y0, y1); };
   if (pinned) {
     for (int b = 0; b < n_batches; ++b) {
       int y0, y1; batch_rows(b, y0, y1);
