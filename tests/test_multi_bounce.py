@@ -82,7 +82,8 @@ def test_specular_mirror_symmetry(oracle_mod, rthx_mod):
 def test_gpu_parity_multi_bounce(oracle_mod, rthx_mod, cuda_lib, mode):
     from helpers import n_differing_rays
     cases = [domain(rthx_mod), rthx_mod.meshes.two_quads_domain(kappa=(0.5, 3.0)),
-             rthx_mod.meshes.circle_domain(16, 5)]
+             rthx_mod.meshes.circle_domain(16, 5),
+             rthx_mod.meshes.two_quads_domain(kappa=(0.5, 3.0), skew=0.3)]     # a bilinear face: multi-bounce locates it generically
     cases[1].coarse_mesh[0].epsilon = [0.5] * 4
     for rtm in cases:
         for fine in rtm.fine_mesh:                                  # grey walls + scattering everywhere
