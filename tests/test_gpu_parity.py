@@ -496,3 +496,28 @@ def test_t_junction_interfaces_keep_the_analytic_fine_locator(rthx_mod, oracle_m
     n_left = 18
     c = got["counts"][0]
     assert c[ns:ns + n_left, ns + n_left:].sum() > 1000 and c[ns + n_left:, ns:ns + n_left].sum() > 1000
+
+
+def test_host_output_pipeline_batches_do_not_change_the_result(rthx_mod, cuda_lib, monkeypatch):
+    """rthx_trace_exchange cuts the owned rows into row batches (two compute streams + a copy stream; the last four batches are
+    a quarter of the others): counts, lost and recorded rays are identical for 1, 7 (even split), 8 and 16 (tapered) batches,
+    for a pinned and a pageable host matrix, single bin and several bins, and for a sharded call (rows of one rank only)."""
+    import torch
+    rtm = rthx_mod.meshes.square_domain(15, kappa=1.0, sigma_s=0.5, n_bins=3, kappa_bins=[0.5, 1.0, 2.0])
+    flat, tr = tracer(rthx_mod, cuda_lib, rtm)
+    rpe, ids = 3000, [4, 100]
+    N = flat.n_elements
+    for bins in ([0], [2, 0, 1]):
+        monkeypatch.setenv("RTHX_BATCHES", "1")
+        base = tr.trace(rpe, seed=61, bins=bins, rec_ids=ids, rec_bin=bins[0])
+        for nb in ("7", "8", "16"):
+            monkeypatch.setenv("RTHX_BATCHES", nb)
+            got = tr.trace(rpe, seed=61, bins=bins, rec_ids=ids, rec_bin=bins[0])
+            assert np.array_equal(got["counts"], base["counts"]) and np.array_equal(got["lost"], base["lost"]), (bins, nb)
+            assert np.array_equal(got["endpoints"], base["endpoints"])
+            pinned = torch.empty((len(bins), N, N), dtype=torch.int64).pin_memory().numpy().view(np.uint64)
+            got = tr.trace(rpe, seed=61, bins=bins, counts_out=pinned)
+            assert np.array_equal(got["counts"], base["counts"]), (bins, nb, "pinned")
+            part = tr.trace(rpe, seed=61, bins=bins, emitter_rank=1, emitter_world=3)
+            assert np.array_equal(part["counts"][:, 1::3], base["counts"][:, 1::3]) and part["counts"][:, 0::3].sum() == 0
+    monkeypatch.delenv("RTHX_BATCHES")
