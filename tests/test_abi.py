@@ -85,3 +85,28 @@ def test_product_path_does_not_touch_the_oracle():
     if os.path.exists(so):
         out = subprocess.run(["ldd", so], capture_output=True, text=True).stdout
         assert "oracle" not in out
+
+
+def test_julia_shim_structs_match_the_abi(rthx_mod):
+    """julia/RTHXExchange.jl cannot run here (no Julia in the image): its struct declarations are compared field by field —
+    name, order, width and kind — with the ctypes structs, which test_struct_layouts_match_header ties to include/rthx.h."""
+    from rthx import _abi
+    src = open(os.path.join(ROOT, "julia", "RTHXExchange.jl")).read()
+    pairs = {"RthxMesh": _abi.rthx_mesh, "RthxTraceArgs": _abi.rthx_trace_args, "RthxRecOut": _abi.rthx_rec_out,
+             "RthxStats": _abi.rthx_stats, "RthxSolveArgs": _abi.rthx_solve_args, "RthxSolveStats": _abi.rthx_solve_stats}
+    kinds = {"Int32": ("i", 4), "Int64": ("i", 8), "UInt64": ("u", 8), "UInt8": ("u", 1), "Float64": ("f", 8)}
+
+    def ctypes_kind(t):
+        if hasattr(t, "contents") or t in (C.c_void_p, C.c_char_p):
+            return ("p", C.sizeof(C.c_void_p))
+        code = t._type_
+        return ({"d": "f", "f": "f"}.get(code, "u" if code in "BHILQ" else "i"), C.sizeof(t))
+
+    for jl_name, ct in pairs.items():
+        m = re.search(r"struct\s+%s\b(.*?)\n\s*(?:%s\(\)|end)" % (jl_name, jl_name), src, re.S)
+        assert m, jl_name
+        fields = re.findall(r"(\w+)::([A-Za-z0-9]+(?:\{[A-Za-z0-9]+\})?)", m.group(1))
+        assert [f for f, _ in fields] == [n for n, _ in ct._fields_], jl_name
+        for (fname, jt), (_, t) in zip(fields, ct._fields_):
+            want = ("p", C.sizeof(C.c_void_p)) if jt.startswith("Ptr{") else kinds[jt]
+            assert ctypes_kind(t) == want, (jl_name, fname, jt)
