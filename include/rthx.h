@@ -32,7 +32,7 @@ extern "C" {
 #endif
 
 #define RTHX_VERSION_MAJOR 0
-#define RTHX_VERSION_MINOR 2
+#define RTHX_VERSION_MINOR 3
 
 /* status codes */
 enum {
@@ -178,7 +178,13 @@ typedef struct rthx_handle rthx_handle;
  * lattice descriptors.  Replaces nothing in the reference (it keeps the mesh in Julia structs); it is the
  * device-side twin of RayTracingDomain2D.jl:2-111 + spatialAccelerations.jl:92-106. */
 int rthx_create(rthx_handle** out, const rthx_mesh* mesh, int device_id);
+/* The same for n devices at once (one handle each, for rthx_trace_exchange_multi): the host-side derivation runs ONCE, the
+ * image is uploaded to all devices concurrently from page-locked memory.  On error no handle is left behind.             [0.3] */
+int rthx_create_multi(rthx_handle** out, const rthx_mesh* mesh, const int* device_ids, int n);
 int rthx_destroy(rthx_handle* h);
+/* Number of usable sm_100 devices (what a `devices = all visible` default of the functor enumerates); RTHX_ERR_CUDA and 0
+ * without one.                                                                                                          [0.3] */
+int rthx_device_count(int* n);
 /* rthx_destroy parks streams, events and device buffers in a per-device pool that the next rthx_create adopts
  * (handles are typically re-created for every trace); this frees everything that is parked. */
 int rthx_release_cached(void);
@@ -208,9 +214,16 @@ int rthx_trace_exchange_device(rthx_handle* h, const rthx_trace_args* args,
                                void* counts_dev, void* lost_dev, void* stream,
                                int zero_first, rthx_stats* stats);
 
-/* Single-process multi-GPU trace: emitters are dealt round-robin to the n handles (one per device, same
- * mesh), all devices run concurrently and each copies only the rows it owns into the host matrix
- * (rows are disjoint, so no reduction is needed in-process).  args->emitter_rank/world are ignored. */
+/* Single-process multi-GPU trace: emitters are dealt round-robin to the n handles (one per device, same mesh — see
+ * rthx_create_multi), one host thread per device drives its launches and copies, all devices run concurrently.
+ * args->emitter_rank/world are ignored.
+ *   counts_out != NULL: each device copies only the rows it owns into the host matrix, pipelined behind its kernels over its own
+ *       PCIe link (rows are disjoint and tile the matrix: no reduction, nothing is cleared on the host);
+ *   counts_out == NULL: the devices flush their rows into ONE matrix in the memory of hs[0]'s device through peer access
+ *       (NVLink / NVSwitch; red.add.u64 at system scope, fused into the trace kernel).  The complete matrix stays resident on
+ *       hs[0] for rthx_counts_csr / rthx_counts_csc / rthx_smooth_F / rthx_smooth_DkAP, exactly as after a single-device
+ *       rthx_trace_exchange with counts_out == NULL.  Needs peer access between the devices (RTHX_ERR_CUDA otherwise).      [0.3]
+ * stats->kernel_ms / total_ms are those of the slowest device. */
 int rthx_trace_exchange_multi(rthx_handle** hs, int n, const rthx_trace_args* args,
                               uint64_t* counts_out, uint64_t* lost_out,
                               rthx_rec_out* rec, rthx_stats* stats);
@@ -238,6 +251,9 @@ typedef struct rthx_smooth_stats {
   int32_t pcg_iterations;       /* total PCG iterations of the dual solves inside the rounds */
   double  dykstra_delta;        /* delta_perp after the last checked round (delta_perp :DYK, :136-142) */
   double  dykstra_ms;           /* device time of the rounds */
+  int32_t converged;            /* 1: delta <= target, or the stalled contraction was accepted below the floor guard
+                                   target / sqrt(density) (AP :558-590); 0: max_iters reached — the reference @warns (:605-607) [0.3] */
+  int32_t pad_;
 } rthx_smooth_stats;
 int rthx_smooth_F(rthx_handle* h, int source, const void* src_host, int bin, int n, const double* w, int max_iters,
                   double target, int measure_pass, double* F_out, rthx_smooth_stats* stats);
@@ -310,6 +326,17 @@ int rthx_solve_grey(rthx_handle* h, const rthx_solve_args* args, double* j_out, 
  *                     NULL; this is the row-normalised F of row_normalize!, :161-169), row_lost not included. */
 int rthx_counts_nnz(rthx_handle* h, int bin, int64_t* nnz_out);
 int rthx_counts_csr(rthx_handle* h, int bin, int64_t* row_ptr, int32_t* cols, uint64_t* vals, double* F_vals);
+/* The same counts as the three arrays of a compressed-sparse-COLUMN matrix — the memory layout of the SparseMatrixCSC{Float64,Int}
+ * that computeExchangeFactorsBin returns (parallelRayTracing.jl:154-158), so the caller wraps them and neither runs
+ * sparse(I, J, V) over ~1e8 triplets nor transposes a CSR matrix on the host:
+ *   colptr [N+1] int64, rowval [nnz] int64 (rowval_is_i64 != 0; Julia `Int`) or int32 (scipy), rows ascending within a column,
+ *   vals [nnz] counts (may be NULL), F_vals [nnz] = count / row total (may be NULL);
+ *   index_base 0 or 1 is added to colptr and rowval (1 = Julia).
+ * rthx_counts_stats: non-zeros of the bin and the surface-gas cross-coupling chi of its row-normalised F
+ *   (cross_coupling_chi, smoothExchangeFactors.jl:212-241: sum of F_ij with exactly one of i, j a surface, over N) — what
+ *   smooth_F needs to choose its branch (:421-450) without touching the matrix on the host.                               [0.3] */
+int rthx_counts_stats(rthx_handle* h, int bin, int64_t* nnz_out, double* chi_out);
+int rthx_counts_csc(rthx_handle* h, int bin, int index_base, int rowval_is_i64, int64_t* colptr, void* rowval, uint64_t* vals, double* F_vals);
 
 /* Peer-memory plumbing for the fused flush in one-process-per-GPU runs: rank 0 allocates the UInt64 count matrix
  * with rthx_shared_alloc and publishes the 64-byte CUDA IPC handle; every other rank maps it with rthx_shared_open
@@ -322,10 +349,22 @@ int rthx_shared_open(int device_id, const unsigned char ipc_handle[64], void** d
 int rthx_shared_close(int device_id, void* dev_ptr);
 int rthx_shared_free(int device_id, void* dev_ptr);
 
+/* Step flags for the fused flush without a host-launched collective per step: 64-bit counters in the matrix owner's memory.
+ * rthx_flag_signal enqueues a system-scope release store of `value` to *flag (device memory, possibly peer-mapped) behind
+ * everything already on `stream` — a rank signals "my rows of step s have landed" after its trace kernel; rthx_flag_wait
+ * enqueues an acquire spin until flags[0..n) >= value in front of whatever follows on `stream`.  A wait gives up after
+ * timeout_s (<= 0: 30 s) and increments *err_flag (may be NULL) so that a dead peer cannot hang the device.                [0.3] */
+int rthx_flag_signal(void* flag, uint64_t value, void* stream);
+int rthx_flag_wait(const void* flags, int n, uint64_t value, double timeout_s, void* err_flag, void* stream);
+
 /* Page-lock a caller-owned host buffer (e.g. a matrix in POSIX shared memory that several ranks fill) so the
  * pipelined device->host copies of rthx_trace_exchange run at full PCIe speed and overlap with tracing. */
 int rthx_host_register(void* ptr, uint64_t bytes);
 int rthx_host_unregister(void* ptr);
+/* Page-locked host memory for output arrays (count matrix, CSC arrays, F_smooth): device->host copies into it run by DMA at
+ * full PCIe speed with no staging pass.  A Julia caller wraps the pointer with unsafe_wrap(Array, ptr, dims).            [0.3] */
+int rthx_host_alloc(void** ptr, uint64_t bytes);
+int rthx_host_free(void* ptr);
 
 /* FP64 FMA-chain micro-benchmark on the handle's device: the denominator of the FP64 roofline
  * (MEASURED_PEAKS.json has no FP64 entry).  Returns TFLOP/s (2 flop per DFMA). */

@@ -16,7 +16,7 @@ import RayTraceHeatTransfer: RayTracingDomain2D, group_uniform_bins
 
 const LIB = get(ENV, "RTHX_LIB", "librthx.so")
 const SEED = Ref{UInt64}(rand(UInt64))      # set RTHXExchange.SEED[] for reproducible runs
-const DEVICES = Ref{Vector{Cint}}(Cint[0])  # devices used by the single-process multi-GPU entry point
+const DEVICES = Ref{Vector{Cint}}(Cint[0])  # devices of the trace (rthx_create_multi / rthx_trace_exchange_multi); e.g. Cint.(0:7)
 
 # ---- struct twins of include/rthx.h (field order and types must match) -------------------------------------------
 struct RthxMesh
@@ -98,16 +98,28 @@ end
 
 check(rc, h) = rc == 0 || error("rthx: " * unsafe_string(ccall((:rthx_last_error, LIB), Cstring, (Ptr{Cvoid},), h)))
 
+# ---- page-locked result arrays: the device writes them by DMA, Julia wraps them without a copy -----------------------
+function pinned_vector(::Type{T}, n::Integer) where {T}
+    p = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:rthx_host_alloc, LIB), Cint, (Ref{Ptr{Cvoid}}, UInt64), p, max(n, 1) * sizeof(T)), C_NULL)
+    v = unsafe_wrap(Array, Ptr{T}(p[]), n; own = false)
+    finalizer(_ -> ccall((:rthx_host_free, LIB), Cint, (Ptr{Cvoid},), p[]), v)
+    return v
+end
+
 """
     trace_bins(rtm, rays_per_emitter, nudge, bins, rec) -> Vector{SparseMatrixCSC{Float64,Int}}
 
-Batched replacement of `computeExchangeFactorsBin` (parallelRayTracing.jl:64-159): all `bins` in one launch.
+Batched replacement of `computeExchangeFactorsBin` (parallelRayTracing.jl:64-159): all `bins` in one launch per device.
+The UInt64 count matrix never reaches the host: with several devices their rows are gathered on the first one over NVLink
+inside the trace kernels (`counts_out = C_NULL`), and `rthx_counts_csc` emits the three arrays of the
+`SparseMatrixCSC{Float64,Int}` that `sparse(I, J, V)` + `row_normalize!` (:144-169) would have built — 1-based, rows
+ascending within each column — straight into page-locked memory.
 """
 function trace_bins(rtm::RayTracingDomain2D, rays_per_emitter::Integer, nudge::Float64, bins::Vector{Int}, rec)
     mesh, arrays = flatten(rtm)
     N = Int(mesh.n_surfaces + mesh.n_cells)
     nbins = length(bins)
-    counts = Array{UInt64}(undef, N, N, nbins)           # [j, i, b]: column-major view of the C [b][i][j] layout
     lost = Array{UInt64}(undef, N, nbins)
     bins0 = Int32.(bins .- 1)
     rec_ids = rec === nothing ? Int32[] : Int32.(rec.ids .- 1)
@@ -115,20 +127,31 @@ function trace_bins(rtm::RayTracingDomain2D, rays_per_emitter::Integer, nudge::F
     origins = zeros(2, max(cap, 1)); endpoints = zeros(2, max(cap, 1))
     recout = RthxRecOut(cap, pointer(origins), pointer(endpoints), 0)
     stats = RthxStats()
-    handles = Ptr{Cvoid}[]
-    GC.@preserve arrays counts lost bins0 rec_ids origins endpoints begin
-        for d in DEVICES[]
-            h = Ref{Ptr{Cvoid}}(C_NULL)
-            check(ccall((:rthx_create, LIB), Cint, (Ref{Ptr{Cvoid}}, Ref{RthxMesh}, Cint), h, mesh, d), C_NULL)
-            push!(handles, h[])
-        end
+    devs = DEVICES[]
+    handles = fill(Ptr{Cvoid}(C_NULL), length(devs))
+    Fs = Vector{SparseMatrixCSC{Float64,Int}}(undef, nbins)
+    GC.@preserve arrays lost bins0 rec_ids origins endpoints begin
+        check(ccall((:rthx_create_multi, LIB), Cint, (Ptr{Ptr{Cvoid}}, Ref{RthxMesh}, Ptr{Cint}, Cint),
+                    handles, mesh, devs, length(devs)), C_NULL)
         args = RthxTraceArgs(rays_per_emitter, 0, SEED[], nudge, nbins, pointer(bins0), 0, 0, 0, 1,
                              length(rec_ids), isempty(rec_ids) ? C_NULL : pointer(rec_ids),
                              rec === nothing ? 0 : rec.bin - 1, 0, 0)
         rc = ccall((:rthx_trace_exchange_multi, LIB), Cint,
                    (Ptr{Ptr{Cvoid}}, Cint, Ref{RthxTraceArgs}, Ptr{UInt64}, Ptr{UInt64}, Ref{RthxRecOut}, Ref{RthxStats}),
-                   handles, length(handles), args, counts, lost, recout, stats)
+                   handles, length(handles), args, C_NULL, lost, recout, stats)
         check(rc, handles[1])
+        for b in 1:nbins
+            nnz = Ref{Int64}(0)
+            check(ccall((:rthx_counts_nnz, LIB), Cint, (Ptr{Cvoid}, Cint, Ref{Int64}), handles[1], b - 1, nnz), handles[1])
+            colptr = Vector{Int}(undef, N + 1)
+            rowval = pinned_vector(Int, nnz[]); nzval = pinned_vector(Float64, nnz[])
+            check(ccall((:rthx_counts_csc, LIB), Cint,
+                        (Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Int64}, Ptr{Cvoid}, Ptr{UInt64}, Ptr{Float64}),
+                        handles[1], b - 1, 1, 1, colptr, rowval, C_NULL, nzval), handles[1])
+            maxloss = Int(maximum(@view lost[:, b]))
+            println("Maximum ray tracing ray loss per emitter: $maxloss/$rays_per_emitter")   # unconditional, :163
+            Fs[b] = SparseMatrixCSC{Float64,Int}(N, N, colptr, rowval, nzval)                # no sort, no copy
+        end
         foreach(h -> ccall((:rthx_destroy, LIB), Cint, (Ptr{Cvoid},), h), handles)
     end
     SEED[] += 0x9E3779B97F4A7C15                          # a fresh stream for the next call, like unseeded rand()
@@ -137,23 +160,6 @@ function trace_bins(rtm::RayTracingDomain2D, rays_per_emitter::Integer, nudge::F
             push!(rec.origins[1], Point2{Float64}(origins[1, k], origins[2, k]))
             push!(rec.endpoints[1], Point2{Float64}(endpoints[1, k], endpoints[2, k]))
         end
-    end
-    Fs = Vector{SparseMatrixCSC{Float64,Int}}(undef, nbins)
-    for b in 1:nbins
-        I = Int[]; J = Int[]; V = Float64[]
-        maxloss = 0
-        for i in 1:N
-            rowsum = sum(@view counts[:, i, b])
-            maxloss = max(maxloss, rays_per_emitter - Int(rowsum))
-            rowsum == 0 && continue
-            for j in 1:N
-                c = counts[j, i, b]
-                c == 0 && continue
-                push!(I, i); push!(J, j); push!(V, c / rowsum)   # (c/R) / Σ(c/R): :144-146 + row_normalize! :161-169
-            end
-        end
-        println("Maximum ray tracing ray loss per emitter: $maxloss/$rays_per_emitter")   # unconditional, :163
-        Fs[b] = sparse(I, J, V, N, N)
     end
     return Fs
 end

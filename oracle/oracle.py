@@ -22,7 +22,7 @@ _LIB = None
 class oracle_stats(C.Structure):
     _fields_ = [("n_surface_gas", C.c_uint64), ("n_surface_wall", C.c_uint64), ("n_volume_gas", C.c_uint64),
                 ("n_volume_wall", C.c_uint64), ("n_crossings", C.c_uint64), ("n_lost", C.c_uint64),
-                ("n_threads", C.c_int32)]
+                ("n_threads", C.c_int32), ("pad_", C.c_int32), ("loop_seconds", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -60,13 +60,17 @@ def lib():
         L.rthx_oracle_u52.argtypes = [C.c_uint32, C.c_uint32]
         L.rthx_oracle_u23.restype = C.c_float
         L.rthx_oracle_u23.argtypes = [C.c_uint32]
+        L.rthx_oracle_set_faithful.restype = None
+        L.rthx_oracle_set_faithful.argtypes = [C.c_int]
         _LIB = L
     return _LIB
 
 
 def trace(flat, rays_per_emitter, seed=0x5EED0001, bins=(0,), nudge=None, n_threads=0, rec_ids=None, rec_bin=0,
-          ray_id_offset=0, emitter_rank=0, emitter_world=1, mode=0):
-    """Run the oracle on a FlatMesh.  Returns dict(counts[nb,N,N] u64, lost[nb,N] u64, stats, origins, endpoints)."""
+          ray_id_offset=0, emitter_rank=0, emitter_world=1, mode=0, faithful=False):
+    """Run the oracle on a FlatMesh.  Returns dict(counts[nb,N,N] u64, lost[nb,N] u64, stats, origins, endpoints).
+    faithful=True: the reference-faithful TIMING mode (per-thread xoshiro256++, Dict-like row tally) — not the Philox contract."""
+    lib().rthx_oracle_set_faithful(1 if faithful else 0)
     args, keep = rthx.make_trace_args(rays_per_emitter, seed=seed, bins=bins, nudge=nudge, rec_ids=rec_ids,
                                       rec_bin=rec_bin, ray_id_offset=ray_id_offset, emitter_rank=emitter_rank,
                                       emitter_world=emitter_world, mode=mode)

@@ -79,7 +79,73 @@ typedef struct {
   uint32_t w[8];
 } draws_t;
 
+/* ---- "reference-faithful" timing mode (bench.py's CPU baseline) -------------------------------
+ * The reference draws every variate from Julia's task-local xoshiro256++ (`rand()`, traceRay.jl:25,79 etc.) and tallies a
+ * row in a Dict{Int,Int} (parallelRayTracing.jl:104,124).  With the switch on, the oracle does the same: the words that feed
+ * the samplers come from a per-thread xoshiro256++ (seeded per thread by splitmix64) instead of Philox, and each emitter row
+ * is tallied in an open-addressing hash map that is flushed into the row when the emitter is done (:144-146).  Same
+ * geometry code, same draw order; results are statistically equivalent but NOT the Philox contract — for timing only. */
+static int g_faithful = 0;
+void rthx_oracle_set_faithful(int on) { g_faithful = on ? 1 : 0; }
+int rthx_oracle_get_faithful(void) { return g_faithful; }
+
+static _Thread_local uint64_t t_xo[4];
+static inline uint64_t rotl64(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+static inline uint64_t xoshiro_next(void) {                /* xoshiro256++ 1.0 (Blackman & Vigna), Julia's default RNG */
+  uint64_t* s = t_xo;
+  const uint64_t result = rotl64(s[0] + s[3], 23) + s[0];
+  const uint64_t t = s[1] << 17;
+  s[2] ^= s[0]; s[3] ^= s[1]; s[1] ^= s[2]; s[0] ^= s[3];
+  s[2] ^= t;
+  s[3] = rotl64(s[3], 45);
+  return result;
+}
+static void xoshiro_seed(uint64_t seed, uint64_t stream) {
+  uint64_t z = seed + 0x9E3779B97F4A7C15ull * (stream + 1);
+  for (int i = 0; i < 4; ++i) {                             /* splitmix64 */
+    z += 0x9E3779B97F4A7C15ull;
+    uint64_t x = z;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    t_xo[i] = x ^ (x >> 31);
+  }
+}
+static inline void xoshiro_words(uint32_t* w, int n64) {
+  for (int i = 0; i < n64; ++i) { const uint64_t x = xoshiro_next(); w[2 * i] = (uint32_t)x; w[2 * i + 1] = (uint32_t)(x >> 32); }
+}
+
+/* Dict{Int,Int}-like row tally: open addressing, linear probing, grows at load factor 2/3 (like Julia's Dict) */
+typedef struct { int32_t* keys; uint64_t* vals; uint32_t cap, n; } rowmap_t;
+static void rowmap_init(rowmap_t* m) {
+  m->cap = 16; m->n = 0;
+  m->keys = (int32_t*)malloc(sizeof(int32_t) * m->cap); m->vals = (uint64_t*)malloc(sizeof(uint64_t) * m->cap);
+  for (uint32_t i = 0; i < m->cap; ++i) m->keys[i] = -1;
+}
+static void rowmap_clear(rowmap_t* m) { for (uint32_t i = 0; i < m->cap; ++i) m->keys[i] = -1; m->n = 0; }
+static void rowmap_free(rowmap_t* m) { free(m->keys); free(m->vals); }
+static inline uint32_t rowmap_slot(const rowmap_t* m, int32_t key) {
+  uint32_t i = ((uint32_t)key * 0x9E3779B1u) & (m->cap - 1);
+  while (m->keys[i] != -1 && m->keys[i] != key) i = (i + 1) & (m->cap - 1);
+  return i;
+}
+static void rowmap_add(rowmap_t* m, int32_t key) {
+  uint32_t i = rowmap_slot(m, key);
+  if (m->keys[i] == key) { m->vals[i]++; return; }
+  if (3 * (m->n + 1) > 2 * m->cap) {
+    rowmap_t g; g.cap = m->cap * 4; g.n = m->n;
+    g.keys = (int32_t*)malloc(sizeof(int32_t) * g.cap); g.vals = (uint64_t*)malloc(sizeof(uint64_t) * g.cap);
+    for (uint32_t k = 0; k < g.cap; ++k) g.keys[k] = -1;
+    for (uint32_t k = 0; k < m->cap; ++k)
+      if (m->keys[k] != -1) { const uint32_t j = rowmap_slot(&g, m->keys[k]); g.keys[j] = m->keys[k]; g.vals[j] = m->vals[k]; }
+    rowmap_free(m);
+    *m = g;
+    i = rowmap_slot(m, key);
+  }
+  m->keys[i] = key; m->vals[i] = 1; m->n++;
+}
+
 static void draws_init(draws_t* d, uint64_t seed, uint64_t ray_id, uint32_t emitter, uint32_t band, int ncalls) {
+  if (g_faithful) { xoshiro_words(d->w, 2 * ncalls); return; }
   d->key[0] = (uint32_t)seed;
   d->key[1] = (uint32_t)(seed >> 32);
   d->ctr[0] = (uint32_t)ray_id;
@@ -93,6 +159,7 @@ static void draws_init(draws_t* d, uint64_t seed, uint64_t ray_id, uint32_t emit
 
 /* the two Philox calls of MULTI_BOUNCE event n: call# 2+2n and 3+2n */
 static void draws_event(draws_t* d, uint64_t seed, uint64_t ray_id, uint32_t emitter, uint32_t band, int event) {
+  if (g_faithful) { xoshiro_words(d->w, 4); return; }
   d->key[0] = (uint32_t)seed;
   d->key[1] = (uint32_t)(seed >> 32);
   d->ctr[0] = (uint32_t)ray_id;
@@ -586,8 +653,23 @@ int rthx_oracle_trace(const rthx_mesh* m, const rthx_trace_args* a, uint64_t* co
 #else
   (void)n_threads;
 #endif
+  const int faithful = g_faithful;
+#ifdef _OPENMP
+  const double t_loop0 = omp_get_wtime();
+#endif
   /* contiguous emitter ranges per thread, like parallelRayTracing.jl:83-91,102 */
-#pragma omp parallel for schedule(static) reduction(+ : c_sg, c_sw, c_vg, c_vw, c_cross, c_lost)
+#pragma omp parallel reduction(+ : c_sg, c_sw, c_vg, c_vw, c_cross, c_lost)
+  {
+  rowmap_t rm = {0, 0, 0, 0};
+  if (faithful) {
+    rowmap_init(&rm);
+#ifdef _OPENMP
+    xoshiro_seed(a->seed, (uint64_t)omp_get_thread_num());
+#else
+    xoshiro_seed(a->seed, 0);
+#endif
+  }
+#pragma omp for schedule(static)
   for (int e = 0; e < N; ++e) {
     if (e % a->emitter_world != a->emitter_rank) continue;
     for (int bi = 0; bi < a->n_bins; ++bi) {
@@ -600,7 +682,7 @@ int rthx_oracle_trace(const rthx_mesh* m, const rthx_trace_args* a, uint64_t* co
         const int ab = shoot(&o, beta_all, a, e, band, (uint64_t)(a->ray_id_offset + i), &r, &h);
         c_cross += (uint64_t)h.crossings;
         if (ab < 0) { nlost++; continue; }
-        row[ab]++;
+        if (faithful) rowmap_add(&rm, ab); else row[ab]++;
         if (e < o.ns) { if (h.wall) c_sw++; else c_sg++; } else { if (h.wall) c_vw++; else c_vg++; }
         if (recording) {
           const size_t s = (size_t)rec_slot[e] * (size_t)a->rays_per_emitter + (size_t)i;
@@ -608,10 +690,19 @@ int rthx_oracle_trace(const rthx_mesh* m, const rthx_trace_args* a, uint64_t* co
           rvalid[s] = 1;
         }
       }
+      if (faithful) {                      /* flush the emitter's tallies (parallelRayTracing.jl:144-146) */
+        for (uint32_t k = 0; k < rm.cap; ++k) if (rm.keys[k] != -1) row[rm.keys[k]] += rm.vals[k];
+        rowmap_clear(&rm);
+      }
       if (lost) lost[(size_t)bi * N + e] = nlost;
       c_lost += nlost;
     }
   }
+  if (faithful) rowmap_free(&rm);
+  }
+#ifdef _OPENMP
+  const double t_loop1 = omp_get_wtime();
+#endif
   if (rec) {
     rec->n_recorded = 0;
     if (rbuf) {
@@ -630,8 +721,10 @@ int rthx_oracle_trace(const rthx_mesh* m, const rthx_trace_args* a, uint64_t* co
     st->n_crossings = c_cross; st->n_lost = c_lost;
 #ifdef _OPENMP
     st->n_threads = omp_get_max_threads();
+    st->loop_seconds = t_loop1 - t_loop0;
 #else
     st->n_threads = 1;
+    st->loop_seconds = 0.0;
 #endif
   }
   free(rbuf); free(rvalid); free(rec_slot); free(beta_all);

@@ -11,7 +11,13 @@ typedef struct rthx_oracle_stats {
   uint64_t n_crossings;                                                /* coarse-face crossings */
   uint64_t n_lost;
   int32_t n_threads;
+  int32_t pad_;
+  double loop_seconds;                                                 /* wall time of the emitter loop alone (no mesh build, no zeroing) */
 } rthx_oracle_stats;
+
+/* 1: "reference-faithful" timing mode — per-thread xoshiro256++ instead of Philox, Dict-like row tally (rthx_oracle.c) */
+void rthx_oracle_set_faithful(int on);
+int rthx_oracle_get_faithful(void);
 
 int rthx_oracle_trace(const rthx_mesh* m, const rthx_trace_args* a, uint64_t* counts, uint64_t* lost,
                       rthx_rec_out* rec, int n_threads, rthx_oracle_stats* st);

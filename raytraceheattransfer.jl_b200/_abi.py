@@ -59,7 +59,7 @@ class rthx_smooth_stats(C.Structure):
     _fields_ = [("iterations", C.c_int32), ("launches", C.c_int32), ("delta_init", C.c_double), ("delta", C.c_double),
                 ("total_ms", C.c_double), ("ms_per_iteration", C.c_double), ("pass_ms", C.c_double), ("pass_gbs", C.c_double),
                 ("dykstra_rounds", C.c_int32), ("pcg_iterations", C.c_int32), ("dykstra_delta", C.c_double),
-                ("dykstra_ms", C.c_double)]
+                ("dykstra_ms", C.c_double), ("converged", C.c_int32), ("pad_", C.c_int32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -101,8 +101,8 @@ class rthx_info(C.Structure):
 
 # every symbol include/rthx.h declares (tests check the built library exports all of them)
 EXPORTED_SYMBOLS = (
-    "rthx_create", "rthx_destroy", "rthx_get_info", "rthx_trace_exchange", "rthx_trace_exchange_device",
+    "rthx_create", "rthx_create_multi", "rthx_device_count", "rthx_destroy", "rthx_get_info", "rthx_trace_exchange", "rthx_trace_exchange_device",
     "rthx_trace_exchange_multi", "rthx_measure_fp64_peak", "rthx_last_error", "rthx_version",
     "rthx_shared_alloc", "rthx_shared_open", "rthx_shared_close", "rthx_shared_free", "rthx_release_cached",
-    "rthx_smooth_F", "rthx_smooth_DkAP", "rthx_solve_grey", "rthx_host_register", "rthx_host_unregister", "rthx_counts_nnz", "rthx_counts_csr",
+    "rthx_smooth_F", "rthx_smooth_DkAP", "rthx_solve_grey", "rthx_flag_signal", "rthx_flag_wait", "rthx_host_register", "rthx_host_unregister", "rthx_host_alloc", "rthx_host_free", "rthx_counts_nnz", "rthx_counts_csr", "rthx_counts_stats", "rthx_counts_csc",
 )

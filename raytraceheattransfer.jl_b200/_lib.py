@@ -72,6 +72,10 @@ def load_library():
     L = C.CDLL(so)
     L.rthx_create.restype = C.c_int
     L.rthx_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(rthx_mesh), C.c_int]
+    L.rthx_create_multi.restype = C.c_int
+    L.rthx_create_multi.argtypes = [C.POINTER(C.c_void_p), C.POINTER(rthx_mesh), C.POINTER(C.c_int), C.c_int]
+    L.rthx_device_count.restype = C.c_int
+    L.rthx_device_count.argtypes = [C.POINTER(C.c_int)]
     L.rthx_destroy.restype = C.c_int
     L.rthx_destroy.argtypes = [C.c_void_p]
     L.rthx_get_info.restype = C.c_int
@@ -107,10 +111,22 @@ def load_library():
     L.rthx_counts_nnz.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int64)]
     L.rthx_counts_csr.restype = C.c_int
     L.rthx_counts_csr.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int64), c_i32p, c_u64p, c_f64p]
+    L.rthx_counts_stats.restype = C.c_int
+    L.rthx_counts_stats.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_double)]
+    L.rthx_counts_csc.restype = C.c_int
+    L.rthx_counts_csc.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int64), C.c_void_p, c_u64p, c_f64p]
+    L.rthx_flag_signal.restype = C.c_int
+    L.rthx_flag_signal.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+    L.rthx_flag_wait.restype = C.c_int
+    L.rthx_flag_wait.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_double, C.c_void_p, C.c_void_p]
     L.rthx_host_register.restype = C.c_int
     L.rthx_host_register.argtypes = [C.c_void_p, C.c_uint64]
     L.rthx_host_unregister.restype = C.c_int
     L.rthx_host_unregister.argtypes = [C.c_void_p]
+    L.rthx_host_alloc.restype = C.c_int
+    L.rthx_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_uint64]
+    L.rthx_host_free.restype = C.c_int
+    L.rthx_host_free.argtypes = [C.c_void_p]
     L.rthx_measure_fp64_peak.restype = C.c_int
     L.rthx_measure_fp64_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     L.rthx_last_error.restype = C.c_char_p
@@ -119,6 +135,17 @@ def load_library():
     L.rthx_version.argtypes = []
     _LIB = L
     return L
+
+
+def device_count() -> int:
+    """Number of usable CUDA devices as the library sees them (rthx_device_count); raises without one — no CPU fallback."""
+    L = load_library()
+    n = C.c_int(0)
+    rc = L.rthx_device_count(C.byref(n))
+    if rc != 0:
+        msg = L.rthx_last_error(None)
+        raise RthxError(f"rthx_device_count failed ({rc}): {msg.decode() if msg else ''}")
+    return n.value
 
 
 def make_trace_args(rays_per_emitter: int, seed: int = DEFAULT_SEED, bins: Sequence[int] = (0,),
@@ -148,18 +175,78 @@ def make_trace_args(rays_per_emitter: int, seed: int = DEFAULT_SEED, bins: Seque
     return a, (bins_arr, rec_arr)
 
 
+class _PinnedPool:
+    """Page-locked host buffers (rthx_host_alloc) for large result arrays.  cudaHostAlloc pins pages at ~1-2 GB/s, so a 900 MB
+    matrix costs more to allocate than to trace; buffers return here when their numpy array is garbage-collected and are
+    handed out again (best fit), up to `limit` bytes parked."""
+
+    def __init__(self, limit: int = 8 << 30):
+        self.free = []          # (capacity, address)
+        self.limit = limit
+
+    def take(self, nbytes: int):
+        nbytes = max(int(nbytes), 64)
+        best = None
+        for k, (cap, _) in enumerate(self.free):
+            if cap >= nbytes and (best is None or cap < self.free[best][0]) and cap <= 2 * nbytes + (1 << 20):
+                best = k
+        if best is not None:
+            return self.free.pop(best)
+        p = C.c_void_p()
+        L = load_library()
+        if L.rthx_host_alloc(C.byref(p), nbytes) != 0:
+            msg = L.rthx_last_error(None)
+            raise RthxError(f"rthx_host_alloc({nbytes}) failed: {msg.decode() if msg else ''}")
+        return nbytes, p.value
+
+    def give(self, cap: int, addr: int):
+        if sum(c for c, _ in self.free) + cap <= self.limit:
+            self.free.append((cap, addr))
+        else:
+            load_library().rthx_host_free(C.c_void_p(addr))
+
+    def release(self):
+        L = load_library()
+        for _, addr in self.free:
+            L.rthx_host_free(C.c_void_p(addr))
+        self.free = []
+
+
+_PINNED = _PinnedPool()
+
+
+def pinned_empty(shape, dtype=np.float64) -> np.ndarray:
+    """numpy array in page-locked host memory (device->host copies into it run by DMA, no staging pass)."""
+    import weakref
+    shape = (int(shape),) if np.isscalar(shape) else tuple(int(x) for x in shape)
+    n = int(np.prod(shape)) if len(shape) else 1
+    nbytes = n * np.dtype(dtype).itemsize
+    cap, addr = _PINNED.take(nbytes)
+    buf = (C.c_char * max(nbytes, 1)).from_address(addr)
+    arr = np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
+    weakref.finalize(buf, _PINNED.give, cap, addr)
+    return arr
+
+
+def release_pinned():
+    _PINNED.release()
+
+
 class DeviceTracer:
     """Owns one `rthx_handle` (mesh resident on one GPU)."""
 
-    def __init__(self, flat, device: int = 0):
+    def __init__(self, flat, device: int = 0, _handle=None):
         self._L = load_library()
         self.flat = flat
         self.device = int(device)
-        h = C.c_void_p()
-        rc = self._L.rthx_create(C.byref(h), C.byref(flat.c), self.device)
-        if rc != 0:
-            msg = self._L.rthx_last_error(None)
-            raise RthxError(f"rthx_create failed ({rc}): {msg.decode() if msg else ''}")
+        if _handle is not None:
+            h = _handle
+        else:
+            h = C.c_void_p()
+            rc = self._L.rthx_create(C.byref(h), C.byref(flat.c), self.device)
+            if rc != 0:
+                msg = self._L.rthx_last_error(None)
+                raise RthxError(f"rthx_create failed ({rc}): {msg.decode() if msg else ''}")
         self._h = h
         info = rthx_info()
         self._check(self._L.rthx_get_info(self._h, C.byref(info)))
@@ -193,8 +280,10 @@ class DeviceTracer:
             counts = None
         elif counts_out is not None:
             counts = counts_out
-        else:   # rows of other ranks are left untouched by the library: start from zeros when sharded
-            counts = (np.zeros if args.emitter_world > 1 else np.empty)((nb, N, N), np.uint64)
+        elif args.emitter_world > 1:   # rows of other ranks are left untouched by the library: start from zeros when sharded
+            counts = np.zeros((nb, N, N), np.uint64)
+        else:                          # page-locked for anything large: the pipelined row copies then run by DMA behind the kernels
+            counts = pinned_empty((nb, N, N), np.uint64) if nb * N * N > (1 << 16) else np.empty((nb, N, N), np.uint64)
         assert counts is None or (counts.dtype == np.uint64 and counts.size == nb * N * N and counts.flags["C_CONTIGUOUS"])
         lost = np.empty((nb, N), np.uint64)
         st = rthx_stats()
@@ -241,6 +330,31 @@ class DeviceTracer:
         n = nnz.value
         return row_ptr, cols[:n], (vals[:n] if values else None), (fv[:n] if normalised else None)
 
+    def counts_stats(self, bin: int = 0):
+        """(nnz, chi) of the counts resident on the device: non-zeros and the surface-gas cross-coupling of the
+        row-normalised F (cross_coupling_chi, smoothExchangeFactors.jl:212-241) — rthx_counts_stats."""
+        nnz, chi = C.c_int64(0), C.c_double(0.0)
+        self._check(self._L.rthx_counts_stats(self._h, int(bin), C.byref(nnz), C.byref(chi)))
+        return nnz.value, chi.value
+
+    def counts_csc(self, bin: int = 0, values: bool = False, normalised: bool = True, index64: bool = False, index_base: int = 0,
+                   pinned: bool = True):
+        """CSC read-out of the counts resident on the device (rthx_counts_csc): (colptr [N+1] i64, rowval [nnz] i32 | i64,
+        counts [nnz] u64 or None, F_vals [nnz] f64 = count / row total or None) — the three arrays of the reference's
+        SparseMatrixCSC, rows ascending within each column."""
+        nnz, _ = self.counts_stats(bin)
+        N, k = self.n_elements, max(1, nnz)
+        alloc = pinned_empty if pinned and k > (1 << 16) else (lambda shape, dtype: np.empty(shape, dtype))
+        colptr = np.empty(N + 1, np.int64)
+        rowval = alloc(k, np.int64 if index64 else np.int32)
+        vals = alloc(k, np.uint64) if values else None
+        fv = alloc(k, np.float64) if normalised else None
+        self._check(self._L.rthx_counts_csc(self._h, int(bin), int(index_base), 1 if index64 else 0,
+                                            colptr.ctypes.data_as(C.POINTER(C.c_int64)), rowval.ctypes.data_as(C.c_void_p),
+                                            vals.ctypes.data_as(c_u64p) if values else None,
+                                            fv.ctypes.data_as(c_f64p) if normalised else None))
+        return colptr, rowval[:nnz], (vals[:nnz] if values else None), (fv[:nnz] if normalised else None)
+
     def smooth(self, w, n: Optional[int] = None, counts: Optional[np.ndarray] = None, F: Optional[np.ndarray] = None,
                bin: int = 0, max_iters: int = 1000, target: float = 0.0, measure_pass: bool = False,
                out: Optional[np.ndarray] = None, k_dykstra: int = 0):
@@ -259,7 +373,7 @@ class DeviceTracer:
             source, ptr = RTHX_SMOOTH_FROM_F, src.ctypes.data_as(C.c_void_p)
         else:
             src, source, ptr = None, RTHX_SMOOTH_FROM_LAST_TRACE, None
-        F_out = out if out is not None else np.empty((n, n), np.float64)
+        F_out = out if out is not None else (pinned_empty((n, n), np.float64) if n * n > (1 << 16) else np.empty((n, n), np.float64))
         assert F_out.dtype == np.float64 and F_out.size == n * n and F_out.flags["C_CONTIGUOUS"]
         st = rthx_smooth_stats()
         self._check(self._L.rthx_smooth_DkAP(self._h, source, ptr, int(bin), n, w.ctypes.data_as(c_f64p), int(k_dykstra),
@@ -311,13 +425,35 @@ class DeviceTracer:
         return v.value
 
 
-def trace_multi(tracers: Sequence[DeviceTracer], rays_per_emitter: int, **kw):
-    """Single-process multi-GPU trace (rthx_trace_exchange_multi)."""
+def create_multi(flat, devices: Sequence[int]):
+    """One DeviceTracer per device from ONE host-side mesh preparation (rthx_create_multi)."""
+    L = load_library()
+    devs = [int(d) for d in devices]
+    hs = (C.c_void_p * len(devs))()
+    ids = (C.c_int * len(devs))(*devs)
+    rc = L.rthx_create_multi(hs, C.byref(flat.c), ids, len(devs))
+    if rc != 0:
+        msg = L.rthx_last_error(None)
+        raise RthxError(f"rthx_create_multi failed ({rc}): {msg.decode() if msg else ''}")
+    return [DeviceTracer(flat, device=d, _handle=C.c_void_p(hs[i])) for i, d in enumerate(devs)]
+
+
+def trace_multi(tracers: Sequence[DeviceTracer], rays_per_emitter: int, counts_out: Optional[np.ndarray] = None, dense: bool = True, **kw):
+    """Single-process multi-GPU trace (rthx_trace_exchange_multi).  dense=True: every device copies its rows into the host
+    matrix `counts_out` (allocated page-locked when not given).  dense=False: the devices flush their rows into one matrix on
+    tracers[0]'s device over NVLink peer memory; it stays resident there (counts is None) for `tracers[0].counts_csc()` /
+    `.counts_csr()` / `.smooth()`."""
     L = load_library()
     rec_ids = kw.get("rec_ids")
     args, keep = make_trace_args(rays_per_emitter, **kw)
     N, nb = tracers[0].n_elements, args.n_bins
-    counts = np.empty((nb, N, N), np.uint64)
+    if not dense:
+        counts = None
+    elif counts_out is not None:
+        counts = counts_out
+    else:
+        counts = pinned_empty((nb, N, N), np.uint64)
+    assert counts is None or (counts.dtype == np.uint64 and counts.size == nb * N * N and counts.flags["C_CONTIGUOUS"])
     lost = np.empty((nb, N), np.uint64)
     st = rthx_stats()
     hs = (C.c_void_p * len(tracers))(*[t._h for t in tracers])
@@ -328,12 +464,12 @@ def trace_multi(tracers: Sequence[DeviceTracer], rays_per_emitter: int, **kw):
         origins = np.zeros((max(cap, 1), 2))
         endpoints = np.zeros((max(cap, 1), 2))
         rec = rthx_rec_out(cap, origins.ctypes.data_as(c_f64p), endpoints.ctypes.data_as(c_f64p), 0)
-    rc = L.rthx_trace_exchange_multi(hs, len(tracers), C.byref(args), counts.ctypes.data_as(c_u64p),
+    rc = L.rthx_trace_exchange_multi(hs, len(tracers), C.byref(args), counts.ctypes.data_as(c_u64p) if counts is not None else None,
                                      lost.ctypes.data_as(c_u64p), C.byref(rec) if rec else None, C.byref(st))
     if rc != 0:
         msg = L.rthx_last_error(tracers[0]._h)
         raise RthxError(f"rthx_trace_exchange_multi failed ({rc}): {msg.decode() if msg else ''}")
-    out = dict(counts=counts, lost=lost, stats=st.as_dict())
+    out = dict(counts=counts.reshape(nb, N, N) if counts is not None else None, lost=lost, stats=st.as_dict())
     if rec is not None:
         out["origins"] = origins[: rec.n_recorded].copy()
         out["endpoints"] = endpoints[: rec.n_recorded].copy()

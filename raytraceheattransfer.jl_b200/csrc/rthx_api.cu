@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -31,12 +32,15 @@ struct DevRes {
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t bev[18] = {};            // per-batch completion events (+2 scratch)
   void* arena = nullptr;                    size_t arena_cap = 0;      // mesh tables
+  void* generic_arena = nullptr;            size_t generic_cap = 0;    // tables of the reference-faithful locator (built on first use)
   unsigned long long* counts_dev = nullptr; size_t counts_cap = 0;     // count matrix of the host-output entry points
   double* rec_pts_dev = nullptr;            size_t rec_pts_cap = 0;
   uint8_t* rec_valid_dev = nullptr;         size_t rec_valid_cap = 0;
   double* peak_dev = nullptr;
   int* csr_nnz = nullptr;                   size_t csr_cap = 0;        // per-row nnz (int), row totals, row pointers
-  unsigned long long* csr_rowsum = nullptr; long long* csr_rowptr = nullptr;
+  unsigned long long* csr_rowsum = nullptr; long long* csr_rowptr = nullptr; unsigned long long* csr_cross = nullptr;
+  int* csc_partial = nullptr;               size_t csc_partial_cap = 0; // CSC read-out: per (row tile, column) counts / offsets
+  long long* csc_colptr = nullptr;          size_t csc_colptr_cap = 0;
   void* csr_out = nullptr;                  size_t csr_out_cap = 0;    // compacted cols / vals / F_vals
   double* smooth_X = nullptr;               size_t smooth_cap = 0;     // n*n doubles of the smoothing iterate
   double* smooth_vec = nullptr;             size_t smooth_vec_cap = 0; // w, rs, r, u, part (5 n doubles)
@@ -49,8 +53,12 @@ struct DevRes {
   bool valid = false;
 };
 
+namespace { struct HostImage; }
+
 struct rthx_handle : DevRes {
   int device = 0;
+  std::shared_ptr<HostImage> image;    // host image of the mesh tables (shared by the handles of one rthx_create_multi call)
+  bool generic_ready = false;          // generic-locator tables uploaded (ensure_generic)
   cudaDeviceProp prop{};
   int n_coarse = 0, n_cells = 0, n_bands = 0, ns = 0, N = 0, n_affine = 0, n_bilinear = 0;
   bool queue_ok = false;       // every face has an analytic locator (affine or bilinear)
@@ -64,7 +72,9 @@ struct rthx_handle : DevRes {
   TraceParams base{};          // mesh pointers filled once
   int last_trace_bins = 0; size_t last_trace_rows = 0;
   int smooth_n = 0; size_t smooth_ldx = 0;                // F_smooth resident in smooth_X after rthx_smooth_F (0: none)
-  int csr_bin = -1; long long csr_total = 0;              // bin whose row pointers are prepared on the device   // layout of counts_dev left by the last host-output trace
+  int csr_bin = -1; long long csr_total = 0;              // bin whose row pointers are prepared on the device
+  int csc_bin = -1;                                       // bin whose column pointers are prepared on the device
+  double csr_chi = 0.0;                                   // surface-gas cross-coupling of that bin's row-normalised F
   // views into the arena
   unsigned long long* lost_dev = nullptr;   size_t lost_cap = 0;
   int32_t* bins_dev = nullptr;              size_t bins_cap = 0;
@@ -73,6 +83,7 @@ struct rthx_handle : DevRes {
 };
 
 static thread_local std::string g_create_err;
+static int ensure_generic(rthx_handle* h);
 
 namespace {
 std::mutex g_pool_mu;
@@ -83,8 +94,8 @@ bool g_kernels_configured[64] = {};   // cudaFuncSetAttribute(max dynamic smem) 
 
 void devres_free(DevRes& r) {
   cudaFree(r.smooth_X); cudaFree(r.smooth_vec); cudaFree(r.smooth_src); cudaFree(r.solve_buf); cudaFree(r.solve_mat); cudaFree(r.dyk_buf);
-  cudaFree(r.csr_nnz); cudaFree(r.csr_rowsum); cudaFree(r.csr_rowptr); cudaFree(r.csr_out);
-  cudaFree(r.arena); cudaFree(r.counts_dev); cudaFree(r.rec_pts_dev); cudaFree(r.rec_valid_dev); cudaFree(r.peak_dev);
+  cudaFree(r.csr_nnz); cudaFree(r.csr_rowsum); cudaFree(r.csr_rowptr); cudaFree(r.csr_out); cudaFree(r.csr_cross); cudaFree(r.csc_partial); cudaFree(r.csc_colptr);
+  cudaFree(r.arena); cudaFree(r.generic_arena); cudaFree(r.counts_dev); cudaFree(r.rec_pts_dev); cudaFree(r.rec_valid_dev); cudaFree(r.peak_dev);
   for (auto& e : r.ev) if (e) cudaEventDestroy(e);
   for (auto& e : r.bev) if (e) cudaEventDestroy(e);
   for (auto& e : r.cev) if (e) cudaEventDestroy(e);
@@ -184,29 +195,44 @@ void build_grid(const Poly* faces, int n, int poly_base, FaceSetDev& fs, std::ve
   const double pad = cell * 0.1;
   min_x -= pad; min_y -= pad; max_x += pad; max_y += pad;
   int nx = std::max(1, (int)std::ceil((max_x - min_x) / cell)), ny = std::max(1, (int)std::ceil((max_y - min_y) / cell));
-  std::vector<std::vector<int32_t>> cells((size_t)nx * ny);
+  // two passes over the faces (count, then fill) into one CSR block: no per-bucket vectors
+  const size_t nb = (size_t)nx * ny;
+  std::vector<int32_t> cnt(nb + 1, 0);
+  auto range = [&](const Poly& f, int& si, int& ei, int& sj, int& ej) {
+    si = std::max(1, (int)std::floor((f.bb[0] - min_x) / cell) + 1); ei = std::min(nx, (int)std::ceil((f.bb[1] - min_x) / cell));
+    sj = std::max(1, (int)std::floor((f.bb[2] - min_y) / cell) + 1); ej = std::min(ny, (int)std::ceil((f.bb[3] - min_y) / cell));
+  };
   for (int f = 0; f < n; ++f) {
-    int si = std::max(1, (int)std::floor((faces[f].bb[0] - min_x) / cell) + 1), ei = std::min(nx, (int)std::ceil((faces[f].bb[1] - min_x) / cell));
-    int sj = std::max(1, (int)std::floor((faces[f].bb[2] - min_y) / cell) + 1), ej = std::min(ny, (int)std::ceil((faces[f].bb[3] - min_y) / cell));
-    for (int i = si; i <= ei; ++i)
-      for (int j = sj; j <= ej; ++j) cells[(size_t)(i - 1) + (size_t)(j - 1) * nx].push_back(f);
+    int si, ei, sj, ej; range(faces[f], si, ei, sj, ej);
+    for (int j = sj; j <= ej; ++j)
+      for (int i = si; i <= ei; ++i) ++cnt[(size_t)(i - 1) + (size_t)(j - 1) * nx + 1];
+  }
+  for (size_t b = 0; b < nb; ++b) cnt[b + 1] += cnt[b];
+  const size_t items0 = bitems.size();
+  bitems.resize(items0 + (size_t)cnt[nb]);
+  std::vector<int32_t> cur(cnt.begin(), cnt.end() - 1);
+  for (int f = 0; f < n; ++f) {          // ascending face index within every bucket ("first PIP hit" is deterministic)
+    int si, ei, sj, ej; range(faces[f], si, ei, sj, ej);
+    for (int j = sj; j <= ej; ++j)
+      for (int i = si; i <= ei; ++i) bitems[items0 + (size_t)cur[(size_t)(i - 1) + (size_t)(j - 1) * nx]++] = f;
   }
   fs.ox = min_x; fs.oy = min_y; fs.inv_cell = 1.0 / cell; fs.nx = nx; fs.ny = ny;
   fs.poly_base = poly_base; fs.n_faces = n; fs.pad_ = 0;
-  // bucket_start holds absolute offsets into bucket_items; one shared terminator per set is written by the caller
-  if (bstart.empty()) bstart.push_back(0);
+  // bucket_start holds absolute offsets into bucket_items; one shared terminator per set
+  if (bstart.empty()) bstart.push_back((int32_t)items0);
   fs.bucket_off = (int32_t)bstart.size() - 1;
-  for (auto& c : cells) {
-    bitems.insert(bitems.end(), c.begin(), c.end());
-    bstart.push_back((int32_t)bitems.size());
-  }
+  for (size_t b = 0; b < nb; ++b) bstart.push_back((int32_t)(items0 + (size_t)cnt[b + 1]));
 }
 
 bool close_pt(double ax, double ay, double bx, double by, double tol) { return std::fabs(ax - bx) <= tol && std::fabs(ay - by) <= tol; }
 
-// Try to recognise the fine cells of coarse face `cf` as the affine lattice of meshQuad / meshTriangle.
-// On success fills the lattice fields of `out` (+ the lattice->fine table for triangles) and returns true.
-bool detect_affine(const Poly& cp, const Poly* cells, int n_fine, CoarseDev& out, std::vector<int32_t>& lattice) {
+// Try to recognise the fine cells [f0, f0 + n_fine) of coarse face `cp` as the lattice of meshQuad / meshTriangle (affine for
+// parallelograms and mirrored triangles, bilinear for general convex quadrilaterals).  The cells are read from the caller's
+// arrays.  On success fills the lattice fields of `out` (+ the lattice->fine table for triangles) and returns true.
+bool detect_affine(const Poly& cp, const rthx_mesh* m, int f0, int n_fine, CoarseDev& out, std::vector<int32_t>& lattice) {
+  const int32_t* cnv = m->cell_nv + f0;
+  const double* cvx = m->cell_vx + 4 * (size_t)f0;
+  const double* cvy = m->cell_vy + 4 * (size_t)f0;
   double scale = 0;
   for (int i = 0; i < cp.n; ++i) scale = std::max(scale, std::max(std::fabs(cp.vx[i]), std::fabs(cp.vy[i])));
   const double ext = std::max(cp.bb[1] - cp.bb[0], cp.bb[3] - cp.bb[2]);
@@ -226,8 +252,8 @@ bool detect_affine(const Poly& cp, const Poly* cells, int n_fine, CoarseDev& out
       }
       bilinear = true;
     }
-    if (cells[0].n != 4) return false;
-    const double e0 = std::hypot(cells[0].vx[1] - cells[0].vx[0], cells[0].vy[1] - cells[0].vy[0]);
+    if (cnv[0] != 4) return false;
+    const double e0 = std::hypot(cvx[1] - cvx[0], cvy[1] - cvy[0]);
     const double ab = std::hypot(qx[1] - qx[0], qy[1] - qy[0]);
     if (!(e0 > 0)) return false;
     Nx = (int)std::llround(ab / e0);
@@ -258,36 +284,38 @@ bool detect_affine(const Poly& cp, const Poly* cells, int n_fine, CoarseDev& out
   // lattice vertex (n,m) of the map  A + s (B-A) + t (D-A) + s t (A-B+C-D),  s = n/Nx, t = m/Ny  (the last term vanishes for
   // parallelograms and mirrored triangles: affine)
   const double Gx = bilinear ? qx[0] - qx[1] + qx[2] - qx[3] : 0.0, Gy = bilinear ? qy[0] - qy[1] + qy[2] - qy[3] : 0.0;
-  auto lat = [&](int n, int m, double& x, double& y) {
-    const double s = (double)n / Nx, t = (double)m / Ny;
+  auto lat = [&](int n, int m_, double& x, double& y) {
+    const double s = (double)n / Nx, t = (double)m_ / Ny;
     x = qx[0] + s * (qx[1] - qx[0]) + t * (qx[3] - qx[0]) + s * t * Gx;
     y = qy[0] + s * (qy[1] - qy[0]) + t * (qy[3] - qy[0]) + s * t * Gy;
   };
   std::vector<int32_t> table;
   if (cp.n == 3) table.assign((size_t)Nx * Ny, -1);
   int idx = 0;
-  for (int m = 0; m < Ny; ++m)
+  for (int mm = 0; mm < Ny; ++mm)
     for (int n = 0; n < Nx; ++n) {
       double lx[4], ly[4];
-      lat(n, m, lx[0], ly[0]); lat(n + 1, m, lx[1], ly[1]); lat(n + 1, m + 1, lx[2], ly[2]); lat(n, m + 1, lx[3], ly[3]);
+      lat(n, mm, lx[0], ly[0]); lat(n + 1, mm, lx[1], ly[1]); lat(n + 1, mm + 1, lx[2], ly[2]); lat(n, mm + 1, lx[3], ly[3]);
       if (idx < n_fine) {
-        const Poly& c = cells[idx];
+        const int cn = cnv[idx];
+        const double* x = cvx + 4 * (size_t)idx;
+        const double* y = cvy + 4 * (size_t)idx;
         bool match = false;
-        if (c.n == 4) {
+        if (cn == 4) {
           match = true;
-          for (int i = 0; i < 4; ++i) match = match && close_pt(c.vx[i], c.vy[i], lx[i], ly[i], tol);
+          for (int i = 0; i < 4; ++i) match = match && close_pt(x[i], y[i], lx[i], ly[i], tol);
         } else if (cp.n == 3) {
           // diagonal cell: the three lattice corners other than the mirrored one (meshTriangle.jl:55,83)
           match = true;
           int w = 0;
           for (int i = 0; i < 4; ++i) {
             if (i == mirror) continue;
-            match = match && close_pt(c.vx[w], c.vy[w], lx[i], ly[i], tol);
+            match = match && close_pt(x[w], y[w], lx[i], ly[i], tol);
             ++w;
           }
         }
         if (match) {
-          if (cp.n == 3) table[(size_t)n + (size_t)m * Nx] = idx;
+          if (cp.n == 3) table[(size_t)n + (size_t)mm * Nx] = idx;
           ++idx;
           continue;
         }
@@ -323,6 +351,252 @@ bool detect_affine(const Poly& cp, const Poly* cells, int n_fine, CoarseDev& out
   return true;
 }
 
+// Page-locked host buffers for mesh images, pooled per process: callers re-create the handle for every trace, and a
+// cudaHostAlloc / cudaFreeHost pair costs far more than the mesh preparation itself.
+std::mutex g_pin_mu;
+std::vector<std::pair<unsigned char*, size_t>> g_pin_pool;
+
+unsigned char* take_pinned(size_t bytes, size_t* cap) {
+  {
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    for (size_t i = 0; i < g_pin_pool.size(); ++i)
+      if (g_pin_pool[i].second >= bytes) {
+        unsigned char* p = g_pin_pool[i].first; *cap = g_pin_pool[i].second;
+        g_pin_pool.erase(g_pin_pool.begin() + (long)i);
+        return p;
+      }
+  }
+  void* p = nullptr;
+  const size_t want = bytes + bytes / 4 + 4096;
+#ifdef RTHX_PREP_BENCH   // tools/hostbench/prep_bench.cu: times the host preparation on a machine without a GPU
+  p = std::malloc(want);
+  if (!p) return nullptr;
+#else
+  if (cudaHostAlloc(&p, want, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+#endif
+  *cap = want;
+  return static_cast<unsigned char*>(p);
+}
+void give_pinned(unsigned char* p, size_t cap) {
+  if (!p) return;
+  std::lock_guard<std::mutex> lk(g_pin_mu);
+  if (g_pin_pool.size() < 8) { g_pin_pool.emplace_back(p, cap); return; }
+  cudaFreeHost(p);
+}
+
+// Everything rthx_create derives from the caller's arrays, as ONE image of the device arena in page-locked host memory, plus
+// the block-uniform facts the launch planner needs.  Built once per rthx_create / rthx_create_multi call and shared by the
+// handles created from it (the generic-locator tables are derived from it on first use).
+struct HostImage {
+  unsigned char* data = nullptr;
+  size_t cap = 0, bytes = 0, total = 0;      // pinned capacity, image bytes, arena bytes incl. the device-only scratch regions
+  size_t o_coarse = 0, o_sets = 0, o_bstart = 0, o_bitems = 0, o_nv = 0, o_pvx = 0, o_pvy = 0, o_mid = 0, o_vol = 0, o_surf = 0, o_beta = 0,
+         o_ub = 0, o_lat = 0, o_abs = 0, o_omega = 0, o_eps = 0, o_ec = 0, o_ew = 0, o_eco = 0, o_bins = 0, o_rec = 0, o_lost = 0;
+  int nc = 0, ncell = 0, ns = 0, N = 0, nb = 0, n_affine = 0, n_bilinear = 0;
+  bool has_eps = false, nbr_complete = true, needs_generic = false;
+  CoarseDev face0{};
+  std::vector<Poly> coarse_polys;
+  std::vector<int32_t> fine_off;
+  ~HostImage() { give_pinned(data, cap); }
+  template <class T> T* at(size_t off) const { return reinterpret_cast<T*>(data + off); }
+};
+
+struct Layout {            // running offset of the arena image: every table 256-byte aligned
+  size_t total = 0;
+  size_t add(size_t bytes) { const size_t off = (total + 255) & ~size_t(255); total = off + std::max<size_t>(bytes, 8); return off; }
+};
+
+// Host-only half of rthx_create.  Returns RTHX_OK and the image, or an error code with the message in `err`.
+int prepare_mesh(const rthx_mesh* m, std::shared_ptr<HostImage>& out, std::string& err) {
+  const bool timing = std::getenv("RTHX_CREATE_TIMING") != nullptr;
+  auto t_prev = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!timing) return;
+    const auto t = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "rthx_create: %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t - t_prev).count());
+    t_prev = t;
+  };
+  auto im = std::make_shared<HostImage>();
+  const int nc = m->n_coarse, ncell = m->n_cells, ns = m->n_surfaces, N = ns + ncell, nb = m->n_bands;
+  im->nc = nc; im->ncell = ncell; im->ns = ns; im->N = N; im->nb = nb;
+  if (m->fine_off[0] != 0 || m->fine_off[nc] != ncell) { err = "rthx_create: fine_off must span [0, n_cells]"; return RTHX_ERR_ARG; }
+  for (int g = 0; g < ncell; ++g)
+    if (m->cell_nv[g] != 3 && m->cell_nv[g] != 4) { err = "rthx_create: cell_nv must be 3 or 4"; return RTHX_ERR_ARG; }
+  im->fine_off.assign(m->fine_off, m->fine_off + nc + 1);
+  // coarse polygons (normals, bounding boxes); the fine cells get theirs only if the generic locator is ever needed
+  std::vector<Poly>& cpolys = im->coarse_polys;
+  cpolys.resize(nc);
+  for (int c = 0; c < nc; ++c) {
+    Poly& p = cpolys[c];
+    p.n = m->coarse_nv[c];
+    if (p.n != 3 && p.n != 4) { err = "rthx_create: coarse_nv must be 3 or 4"; return RTHX_ERR_ARG; }
+    double sx = 0, sy = 0;
+    for (int i = 0; i < p.n; ++i) { p.vx[i] = m->coarse_vx[4 * c + i]; p.vy[i] = m->coarse_vy[4 * c + i]; sx += p.vx[i]; sy += p.vy[i]; }
+    p.midx = sx / p.n; p.midy = sy / p.n;
+    if (p.n == 4)
+      p.volume = 0.5 * (p.vx[0] * (p.vy[1] - p.vy[2]) + p.vx[1] * (p.vy[2] - p.vy[0]) + p.vx[2] * (p.vy[0] - p.vy[1])) +
+                 0.5 * (p.vx[2] * (p.vy[3] - p.vy[0]) + p.vx[3] * (p.vy[0] - p.vy[2]) + p.vx[0] * (p.vy[2] - p.vy[3]));
+    else
+      p.volume = 0.5 * (p.vx[0] * (p.vy[1] - p.vy[2]) + p.vx[1] * (p.vy[2] - p.vy[0]) + p.vx[2] * (p.vy[0] - p.vy[1]));
+    poly_finish(p);
+    if (m->fine_off[c + 1] <= m->fine_off[c]) { err = "rthx_create: every coarse face needs at least one fine cell"; return RTHX_ERR_ARG; }
+  }
+  lap("coarse polygons");
+
+  // coarse descriptors: lattice detection, absorber tables, neighbour table; the coarse-set locator grid (set 0)
+  std::vector<FaceSetDev> sets(1 + (size_t)nc);
+  std::memset(sets.data(), 0, sizeof(FaceSetDev) * sets.size());
+  std::vector<int32_t> bstart, bitems, lattice, abs_tab;
+  build_grid(cpolys.data(), nc, ncell, sets[0], bstart, bitems);
+  std::vector<CoarseDev> coarse(nc);
+  const double ext_tol = 1e-9;
+  for (int c = 0; c < nc; ++c) {
+    const Poly& cp = cpolys[c];
+    const int f0 = m->fine_off[c], nf = m->fine_off[c + 1] - f0;
+    CoarseDev& d = coarse[c];
+    std::memset(&d, 0, sizeof(d));
+    for (int i = 0; i < 4; ++i) { d.vx[i] = cp.vx[i]; d.vy[i] = cp.vy[i]; d.nx[i] = cp.nx[i]; d.ny[i] = cp.ny[i]; d.nbr[i] = -1; d.solid[i] = 0; }
+    for (int i = 0; i < cp.n; ++i) d.solid[i] = m->coarse_solid[4 * c + i] ? 1 : 0;
+    d.nv = cp.n; d.fine_off = f0; d.kind = KIND_GENERIC; d.lat_off = -1; d.diag = -1; d.Nx = d.Ny = 0;
+    if (detect_affine(cp, m, f0, nf, d, lattice)) { if (d.kind == KIND_BILINEAR_QUAD) im->n_bilinear++; else im->n_affine++; }
+    for (int i = 0; i < cp.n; ++i) d.h[i] = cp.vx[i] * cp.nx[i] + cp.vy[i] * cp.ny[i];
+    if (d.kind == KIND_AFFINE_QUAD) {   // slab form: opposite edges measured along the normals of edges 0 and 1
+      d.h[2] = cp.vx[2] * cp.nx[0] + cp.vy[2] * cp.ny[0];
+      d.h[3] = cp.vx[3] * cp.nx[1] + cp.vy[3] * cp.ny[1];
+      d.cen[0] = 0.5 * (d.h[0] + d.h[2]); d.hw[0] = 0.5 * (d.h[0] - d.h[2]);
+      d.cen[1] = 0.5 * (d.h[1] + d.h[3]); d.hw[1] = 0.5 * (d.h[1] - d.h[3]);
+    }
+    // Absorber table of an affine face: for every lattice cell the element a ray ending there is tallied in — entry 0 for a gas
+    // event (Ns + global cell index, getGlobalIndex2D.jl:10), entry 1+k for a hit on coarse edge k: the surface index of the fine
+    // wall lying on that edge (fine wall = k, except in the quad cells of a mirrored-triangle lattice, whose walls are numbered
+    // around the uncut parallelogram: the cut diagonal is no wall of theirs and the walls behind it shift by one), -1 where the
+    // fine wall is not solid or the lattice cell lies outside the triangle.
+    d.abs_off = -1;
+    if (d.kind != KIND_GENERIC) {
+      d.abs_off = (int32_t)(abs_tab.size() / 5);
+      const size_t ncell_lat = (size_t)d.Nx * d.Ny;
+      const size_t base = abs_tab.size();
+      abs_tab.resize(base + 5 * ncell_lat, -1);
+      for (size_t l = 0; l < ncell_lat; ++l) {
+        const int f = d.kind == KIND_AFFINE_TRI ? lattice[(size_t)d.lat_off + l] : (int)l;   // quad lattices (affine or bilinear): fine index = n + m Nx
+        if (f < 0) continue;
+        int32_t* row = abs_tab.data() + base + 5 * l;
+        const int gc = f0 + f;
+        row[0] = ns + gc;
+        for (int k = 0; k < cp.n; ++k) {
+          int w = k;
+          if (d.kind == KIND_AFFINE_TRI && m->cell_nv[gc] != 3) {
+            if (k == d.diag) continue;
+            w = k < d.diag ? k : k + 1;
+          }
+          row[1 + k] = m->cell_surf_id[4 * (size_t)gc + w];
+        }
+      }
+    } else {
+      im->needs_generic = true;
+    }
+  }
+  lap("lattice detection + tables");
+  // neighbour table: the unique coarse face sharing the (reversed) edge; T-junctions stay -1 (generic search)
+  for (int c = 0; c < nc; ++c) {
+    const Poly& a = cpolys[c];
+    const double tol = ext_tol * std::max(a.bb[1] - a.bb[0], a.bb[3] - a.bb[2]);
+    for (int k = 0; k < a.n; ++k) {
+      if (coarse[c].solid[k]) continue;
+      const int k2 = (k + 1) % a.n;
+      int found = -1, n_found = 0;
+      for (int c2 = 0; c2 < nc; ++c2) {
+        if (c2 == c) continue;
+        const Poly& b = cpolys[c2];
+        for (int j = 0; j < b.n; ++j) {
+          const int j2 = (j + 1) % b.n;
+          if (close_pt(a.vx[k], a.vy[k], b.vx[j2], b.vy[j2], tol) && close_pt(a.vx[k2], a.vy[k2], b.vx[j], b.vy[j], tol)) { found = c2; ++n_found; }
+        }
+      }
+      coarse[c].nbr[k] = (n_found == 1) ? found : -1;
+      if (coarse[c].nbr[k] < 0) im->nbr_complete = false;   // open / T-junction edge: needs the coarse point location
+    }
+  }
+  if (sizeof(CoarseDev) * (size_t)nc > 96 * 1024) im->needs_generic = true;   // > 384 coarse faces: read through L1/L2 by the generic kernel
+  if (lattice.empty()) lattice.push_back(-1);
+  if (abs_tab.empty()) abs_tab.assign(5, -1);
+  im->face0 = coarse[0];
+  im->has_eps = m->epsilon != nullptr || ns == 0;
+  lap("neighbour table");
+
+  // layout of the image, then fill it in place (page-locked: the H2D copies of several devices run concurrently by DMA)
+  const size_t npoly = (size_t)ncell + nc;
+  Layout L;
+  im->o_coarse = L.add(sizeof(CoarseDev) * coarse.size()); im->o_sets = L.add(sizeof(FaceSetDev) * sets.size());
+  im->o_bstart = L.add(4 * bstart.size()); im->o_bitems = L.add(4 * bitems.size());
+  im->o_nv = L.add(4 * npoly); im->o_pvx = L.add(32 * npoly); im->o_pvy = L.add(32 * npoly);
+  im->o_mid = L.add(16 * (size_t)ncell); im->o_vol = L.add(8 * (size_t)ncell); im->o_surf = L.add(16 * (size_t)ncell);
+  im->o_beta = L.add(8 * (size_t)nb * ncell); im->o_ub = L.add(8 * (size_t)nb);
+  im->o_lat = L.add(4 * lattice.size()); im->o_abs = L.add(4 * abs_tab.size());
+  im->o_omega = L.add(8 * (size_t)nb * ncell); im->o_eps = L.add(m->epsilon ? 8 * (size_t)nb * ns : 0);
+  im->o_ec = L.add(4 * (size_t)N); im->o_ew = L.add(4 * (size_t)N); im->o_eco = L.add(4 * (size_t)N);
+  im->bytes = L.total;
+  im->o_bins = L.add(4 * ((size_t)nb * 4 + 16)); im->o_rec = L.add(4 * (size_t)N);
+  im->o_lost = L.add(8 * ((size_t)nb * 4 + 16) * (size_t)N);
+  im->total = L.total;
+  im->data = take_pinned(im->bytes, &im->cap);
+  if (!im->data) { err = "rthx_create: cudaHostAlloc(mesh image) failed"; return RTHX_ERR_NOMEM; }
+  lap("pinned image");
+  std::memcpy(im->at<CoarseDev>(im->o_coarse), coarse.data(), sizeof(CoarseDev) * coarse.size());
+  std::memcpy(im->at<FaceSetDev>(im->o_sets), sets.data(), sizeof(FaceSetDev) * sets.size());
+  std::memcpy(im->at<int32_t>(im->o_bstart), bstart.data(), 4 * bstart.size());
+  if (!bitems.empty()) std::memcpy(im->at<int32_t>(im->o_bitems), bitems.data(), 4 * bitems.size());
+  std::memcpy(im->at<int32_t>(im->o_lat), lattice.data(), 4 * lattice.size());
+  std::memcpy(im->at<int32_t>(im->o_abs), abs_tab.data(), 4 * abs_tab.size());
+  {
+    int32_t* nv = im->at<int32_t>(im->o_nv);
+    double* pvx = im->at<double>(im->o_pvx);
+    double* pvy = im->at<double>(im->o_pvy);
+    std::memcpy(nv, m->cell_nv, 4 * (size_t)ncell);
+    std::memcpy(pvx, m->cell_vx, 32 * (size_t)ncell);
+    std::memcpy(pvy, m->cell_vy, 32 * (size_t)ncell);
+    for (int g = 0; g < ncell; ++g) if (nv[g] == 3) { pvx[4 * (size_t)g + 3] = 0.0; pvy[4 * (size_t)g + 3] = 0.0; }   // unused 4th slot: any value on input
+    for (int c = 0; c < nc; ++c) {
+      nv[ncell + c] = cpolys[c].n;
+      for (int k = 0; k < 4; ++k) { pvx[4 * ((size_t)ncell + c) + k] = cpolys[c].vx[k]; pvy[4 * ((size_t)ncell + c) + k] = cpolys[c].vy[k]; }
+    }
+  }
+  std::memcpy(im->at<double>(im->o_mid), m->cell_mid, 16 * (size_t)ncell);
+  std::memcpy(im->at<double>(im->o_vol), m->cell_volume, 8 * (size_t)ncell);
+  std::memcpy(im->at<int32_t>(im->o_surf), m->cell_surf_id, 16 * (size_t)ncell);
+  std::memcpy(im->at<double>(im->o_ub), m->uniform_beta, 8 * (size_t)nb);
+  {
+    // beta = kappa + sigma_s; MULTI_BOUNCE properties: scattering albedo per (band, cell) — 0 where beta = 0 — and emissivity
+    double* beta = im->at<double>(im->o_beta);
+    double* omega = im->at<double>(im->o_omega);
+    const size_t n = (size_t)nb * ncell;
+    for (size_t i = 0; i < n; ++i) { const double b = m->kappa[i] + m->sigma_s[i]; beta[i] = b; omega[i] = b > 0.0 ? m->sigma_s[i] / b : 0.0; }
+    if (m->epsilon) std::memcpy(im->at<double>(im->o_eps), m->epsilon, 8 * (size_t)nb * ns);
+  }
+  {
+    // emitter table in global-index order (createIndexMapping2D.jl:1-20): surfaces 0..Ns-1, then Ns + cell
+    int32_t* em_cell = im->at<int32_t>(im->o_ec);
+    int32_t* em_wall = im->at<int32_t>(im->o_ew);
+    int32_t* em_coarse = im->at<int32_t>(im->o_eco);
+    for (int s = 0; s < ns; ++s) em_cell[s] = -1;
+    for (int c = 0; c < nc; ++c)
+      for (int g = m->fine_off[c]; g < m->fine_off[c + 1]; ++g) {
+        em_cell[ns + g] = g; em_wall[ns + g] = -1; em_coarse[ns + g] = c;
+        const int n = m->cell_nv[g];
+        for (int w = 0; w < n; ++w) {
+          const int s = m->cell_surf_id[4 * (size_t)g + w];
+          if (s < 0) continue;
+          if (s >= ns || em_cell[s] != -1) { err = "rthx_create: cell_surf_id is not a permutation of 0..Ns-1"; return RTHX_ERR_ARG; }
+          em_cell[s] = g; em_wall[s] = w; em_coarse[s] = c;
+        }
+      }
+    for (int s = 0; s < ns; ++s) if (em_cell[s] < 0) { err = "rthx_create: surface index without a wall"; return RTHX_ERR_ARG; }
+  }
+  lap("image fill");
+  out = im;
+  return RTHX_OK;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -356,23 +630,24 @@ extern "C" int rthx_release_cached(void) {
     g_pool[d].clear();
   }
   cudaSetDevice(cur);
+  {
+    std::lock_guard<std::mutex> lk2(g_pin_mu);
+    for (auto& pb : g_pin_pool) cudaFreeHost(pb.first);
+    g_pin_pool.clear();
+  }
   return RTHX_OK;
 }
 
-extern "C" int rthx_create(rthx_handle** out, const rthx_mesh* m, int device_id) {
-  if (!out) return fail(nullptr, RTHX_ERR_ARG, "rthx_create: out is NULL");
+namespace {
+
+// Device half of rthx_create: adopt pooled resources, upload the image (asynchronously on the handle's stream), wire the
+// table pointers.  `sync` waits for the upload; rthx_create_multi enqueues every device first and waits once.
+int create_on_device(rthx_handle** out, const std::shared_ptr<HostImage>& im, int device_id, int n_dev, bool sync) {
   *out = nullptr;
-  if (!m || m->n_coarse < 1 || m->n_cells < 1 || m->n_bands < 1 || m->n_surfaces < 0 || !m->coarse_nv || !m->coarse_vx ||
-      !m->coarse_vy || !m->coarse_solid || !m->fine_off || !m->cell_nv || !m->cell_vx || !m->cell_vy || !m->cell_mid ||
-      !m->cell_volume || !m->cell_surf_id || !m->kappa || !m->sigma_s || !m->uniform_beta)
-    return fail(nullptr, RTHX_ERR_ARG, "rthx_create: NULL or empty mesh field");
-  int n_dev = 0;
-  cudaError_t ce = cudaGetDeviceCount(&n_dev);
-  if (ce != cudaSuccess || n_dev == 0)
-    return fail(nullptr, RTHX_ERR_CUDA, std::string("rthx_create: no CUDA device (") + cudaGetErrorString(ce) + "); there is no CPU fallback");
   if (device_id < 0 || device_id >= n_dev) return fail(nullptr, RTHX_ERR_ARG, "rthx_create: bad device id");
   rthx_handle* h = new rthx_handle();
   h->device = device_id;
+  cudaError_t ce;
   auto bail = [&](int code, const std::string& msg) { g_create_err = msg; rthx_destroy(h); return code; };
   if ((ce = cudaSetDevice(device_id)) != cudaSuccess) return bail(RTHX_ERR_CUDA, cudaGetErrorString(ce));
   {
@@ -387,206 +662,42 @@ extern "C" int rthx_create(rthx_handle** out, const rthx_mesh* m, int device_id)
   }
   if (h->prop.major < 10) return bail(RTHX_ERR_CUDA, "rthx_create: device is not sm_100 class (kernels are built for sm_100a only)");
   if (!h->valid && (ce = devres_create(*h)) != cudaSuccess) return bail(RTHX_ERR_CUDA, std::string("stream/event creation: ") + cudaGetErrorString(ce));
-
-  // RTHX_CREATE_TIMING=1 prints the host-side phases of this call to stderr (diagnostic knob)
-  const bool timing = std::getenv("RTHX_CREATE_TIMING") != nullptr;
-  auto t_prev = std::chrono::steady_clock::now();
-  auto lap = [&](const char* what) {
-    if (!timing) return;
-    const auto t = std::chrono::steady_clock::now();
-    std::fprintf(stderr, "rthx_create: %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t - t_prev).count());
-    t_prev = t;
-  };
-  lap("device / pool");
-  const int nc = m->n_coarse, ncell = m->n_cells, ns = m->n_surfaces, N = ns + ncell, nb = m->n_bands;
-  h->n_coarse = nc; h->n_cells = ncell; h->ns = ns; h->N = N; h->n_bands = nb;
-  if (m->fine_off[0] != 0 || m->fine_off[nc] != ncell) return bail(RTHX_ERR_ARG, "rthx_create: fine_off must span [0, n_cells]");
-
-  // polygons: cells first, then coarse faces
-  std::vector<Poly> polys((size_t)ncell + nc);
-  for (int g = 0; g < ncell; ++g) {
-    Poly& p = polys[g];
-    p.n = m->cell_nv[g];
-    if (p.n != 3 && p.n != 4) return bail(RTHX_ERR_ARG, "rthx_create: cell_nv must be 3 or 4");
-    for (int i = 0; i < p.n; ++i) { p.vx[i] = m->cell_vx[4 * g + i]; p.vy[i] = m->cell_vy[4 * g + i]; }
-    p.midx = m->cell_mid[2 * g]; p.midy = m->cell_mid[2 * g + 1]; p.volume = m->cell_volume[g];
-    poly_finish(p);
-  }
-  for (int c = 0; c < nc; ++c) {
-    Poly& p = polys[(size_t)ncell + c];
-    p.n = m->coarse_nv[c];
-    if (p.n != 3 && p.n != 4) return bail(RTHX_ERR_ARG, "rthx_create: coarse_nv must be 3 or 4");
-    double sx = 0, sy = 0;
-    for (int i = 0; i < p.n; ++i) { p.vx[i] = m->coarse_vx[4 * c + i]; p.vy[i] = m->coarse_vy[4 * c + i]; sx += p.vx[i]; sy += p.vy[i]; }
-    p.midx = sx / p.n; p.midy = sy / p.n;
-    if (p.n == 4)
-      p.volume = 0.5 * (p.vx[0] * (p.vy[1] - p.vy[2]) + p.vx[1] * (p.vy[2] - p.vy[0]) + p.vx[2] * (p.vy[0] - p.vy[1])) +
-                 0.5 * (p.vx[2] * (p.vy[3] - p.vy[0]) + p.vx[3] * (p.vy[0] - p.vy[2]) + p.vx[0] * (p.vy[2] - p.vy[3]));
-    else
-      p.volume = 0.5 * (p.vx[0] * (p.vy[1] - p.vy[2]) + p.vx[1] * (p.vy[2] - p.vy[0]) + p.vx[2] * (p.vy[0] - p.vy[1]));
-    poly_finish(p);
-    if (m->fine_off[c + 1] <= m->fine_off[c]) return bail(RTHX_ERR_ARG, "rthx_create: every coarse face needs at least one fine cell");
-  }
-
-  lap("polygons + normals");
-  // emitter table
-  std::vector<int32_t> em_cell(N, -1), em_wall(N, -1), em_coarse(N, -1);
-  for (int c = 0; c < nc; ++c)
-    for (int g = m->fine_off[c]; g < m->fine_off[c + 1]; ++g) {
-      em_cell[ns + g] = g; em_wall[ns + g] = -1; em_coarse[ns + g] = c;
-      for (int w = 0; w < polys[g].n; ++w) {
-        const int s = m->cell_surf_id[4 * g + w];
-        if (s < 0) continue;
-        if (s >= ns || em_cell[s] != -1) return bail(RTHX_ERR_ARG, "rthx_create: cell_surf_id is not a permutation of 0..Ns-1");
-        em_cell[s] = g; em_wall[s] = w; em_coarse[s] = c;
-      }
-    }
-  for (int e = 0; e < N; ++e) if (em_cell[e] < 0) return bail(RTHX_ERR_ARG, "rthx_create: surface index without a wall");
-
-  lap("emitter table");
-  // locator grids + coarse descriptors
-  std::vector<FaceSetDev> sets(1 + (size_t)nc);
-  std::vector<int32_t> bstart, bitems, lattice, abs_tab;
-  build_grid(&polys[ncell], nc, ncell, sets[0], bstart, bitems);
-  std::vector<CoarseDev> coarse(nc);
-  const double ext_tol = 1e-9;
-  for (int c = 0; c < nc; ++c) {
-    const Poly& cp = polys[(size_t)ncell + c];
-    const int f0 = m->fine_off[c], nf = m->fine_off[c + 1] - f0;
-    build_grid(&polys[f0], nf, f0, sets[1 + c], bstart, bitems);
-    CoarseDev& d = coarse[c];
-    std::memset(&d, 0, sizeof(d));
-    for (int i = 0; i < 4; ++i) { d.vx[i] = cp.vx[i]; d.vy[i] = cp.vy[i]; d.nx[i] = cp.nx[i]; d.ny[i] = cp.ny[i]; d.nbr[i] = -1; d.solid[i] = 0; }
-    for (int i = 0; i < cp.n; ++i) d.solid[i] = m->coarse_solid[4 * c + i] ? 1 : 0;
-    d.nv = cp.n; d.fine_off = f0; d.kind = KIND_GENERIC; d.lat_off = -1; d.diag = -1; d.Nx = d.Ny = 0;
-    if (detect_affine(cp, &polys[f0], nf, d, lattice)) { if (d.kind == KIND_BILINEAR_QUAD) h->n_bilinear++; else h->n_affine++; }
-    for (int i = 0; i < cp.n; ++i) d.h[i] = cp.vx[i] * cp.nx[i] + cp.vy[i] * cp.ny[i];
-    if (d.kind == KIND_AFFINE_QUAD) {   // slab form: opposite edges measured along the normals of edges 0 and 1
-      d.h[2] = cp.vx[2] * cp.nx[0] + cp.vy[2] * cp.ny[0];
-      d.h[3] = cp.vx[3] * cp.nx[1] + cp.vy[3] * cp.ny[1];
-      d.cen[0] = 0.5 * (d.h[0] + d.h[2]); d.hw[0] = 0.5 * (d.h[0] - d.h[2]);
-      d.cen[1] = 0.5 * (d.h[1] + d.h[3]); d.hw[1] = 0.5 * (d.h[1] - d.h[3]);
-    }
-    // Absorber table of an affine face: for every lattice cell the element a ray ending there is tallied in — entry 0 for a gas
-    // event (Ns + global cell index, getGlobalIndex2D.jl:10), entry 1+k for a hit on coarse edge k: the surface index of the fine
-    // wall lying on that edge (fine wall = k, except in the quad cells of a mirrored-triangle lattice, whose walls are numbered
-    // around the uncut parallelogram: the cut diagonal is no wall of theirs and the walls behind it shift by one), -1 where the
-    // fine wall is not solid or the lattice cell lies outside the triangle.
-    d.abs_off = -1;
-    if (d.kind != KIND_GENERIC) {
-      d.abs_off = (int32_t)(abs_tab.size() / 5);
-      const size_t ncell_lat = (size_t)d.Nx * d.Ny;
-      for (size_t l = 0; l < ncell_lat; ++l) {
-        const int f = d.kind == KIND_AFFINE_TRI ? lattice[(size_t)d.lat_off + l] : (int)l;   // quad lattices (affine or bilinear): fine index = n + m Nx
-        int32_t row[5] = {-1, -1, -1, -1, -1};
-        if (f >= 0) {
-          const int gc = f0 + f;
-          row[0] = ns + gc;
-          for (int k = 0; k < cp.n; ++k) {
-            int w = k;
-            if (d.kind == KIND_AFFINE_TRI && polys[gc].n != 3) {
-              if (k == d.diag) continue;
-              w = k < d.diag ? k : k + 1;
-            }
-            row[1 + k] = m->cell_surf_id[4 * (size_t)gc + w];
-          }
-        }
-        abs_tab.insert(abs_tab.end(), row, row + 5);
-      }
-    }
-  }
-  lap("grids + lattice detection");
-  // neighbour table: the unique coarse face sharing the (reversed) edge; T-junctions stay -1 (generic search)
-  for (int c = 0; c < nc; ++c) {
-    const Poly& a = polys[(size_t)ncell + c];
-    const double tol = ext_tol * std::max(a.bb[1] - a.bb[0], a.bb[3] - a.bb[2]);
-    for (int k = 0; k < a.n; ++k) {
-      if (coarse[c].solid[k]) continue;
-      const int k2 = (k + 1) % a.n;
-      int found = -1, n_found = 0;
-      for (int c2 = 0; c2 < nc; ++c2) {
-        if (c2 == c) continue;
-        const Poly& b = polys[(size_t)ncell + c2];
-        for (int j = 0; j < b.n; ++j) {
-          const int j2 = (j + 1) % b.n;
-          if (close_pt(a.vx[k], a.vy[k], b.vx[j2], b.vy[j2], tol) && close_pt(a.vx[k2], a.vy[k2], b.vx[j], b.vy[j], tol)) { found = c2; ++n_found; }
-        }
-      }
-      coarse[c].nbr[k] = (n_found == 1) ? found : -1;
-    }
-  }
-
-  std::vector<int32_t> poly_nv(polys.size());
-  std::vector<double> pvx(polys.size() * 4), pvy(polys.size() * 4), pnx(polys.size() * 4), pny(polys.size() * 4);
-  for (size_t i = 0; i < polys.size(); ++i) {
-    poly_nv[i] = polys[i].n;
-    for (int k = 0; k < 4; ++k) { pvx[4 * i + k] = polys[i].vx[k]; pvy[4 * i + k] = polys[i].vy[k]; pnx[4 * i + k] = polys[i].nx[k]; pny[4 * i + k] = polys[i].ny[k]; }
-  }
-  std::vector<double> beta((size_t)nb * ncell), ub(m->uniform_beta, m->uniform_beta + nb);
-  for (size_t i = 0; i < beta.size(); ++i) beta[i] = m->kappa[i] + m->sigma_s[i];
-  std::vector<double> mid(m->cell_mid, m->cell_mid + 2 * (size_t)ncell), vol(m->cell_volume, m->cell_volume + ncell);
-  std::vector<int32_t> surf(m->cell_surf_id, m->cell_surf_id + 4 * (size_t)ncell);
-  if (lattice.empty()) lattice.push_back(-1);
-  if (abs_tab.empty()) abs_tab.assign(5, -1);
-  // MULTI_BOUNCE properties: scattering albedo per (band, cell) — 0 where beta = 0 — and emissivity per (band, surface)
-  std::vector<double> omega((size_t)nb * ncell), epsv;
-  for (size_t i = 0; i < omega.size(); ++i) omega[i] = beta[i] > 0.0 ? m->sigma_s[i] / beta[i] : 0.0;
-  if (m->epsilon) epsv.assign(m->epsilon, m->epsilon + (size_t)nb * ns);
-  h->has_eps = m->epsilon != nullptr || ns == 0;
-
-  lap("neighbours + property tables");
-  TraceParams& P = h->base;
-  std::memset(&P, 0, sizeof(P));
-  Arena A;
-  {   // one allocation for the image: 24 tables, 256-byte aligned (growing the vector table by table cost 3.6 ms for cfg3)
-    size_t need = 64 * 256 + sizeof(CoarseDev) * coarse.size() + sizeof(FaceSetDev) * sets.size() + 4 * (bstart.size() + bitems.size() + poly_nv.size()) +
-                  8 * (pvx.size() * 4 + mid.size() + vol.size() + beta.size() + ub.size() + omega.size() + epsv.size()) +
-                  4 * (surf.size() + lattice.size() + abs_tab.size() + em_cell.size() * 3);
-    A.host.reserve(need);
-  }
-  const size_t o_coarse = A.add(coarse), o_sets = A.add(sets), o_bstart = A.add(bstart), o_bitems = A.add(bitems),
-               o_nv = A.add(poly_nv), o_pvx = A.add(pvx), o_pvy = A.add(pvy), o_pnx = A.add(pnx), o_pny = A.add(pny),
-               o_mid = A.add(mid), o_vol = A.add(vol), o_surf = A.add(surf), o_beta = A.add(beta), o_ub = A.add(ub),
-               o_lat = A.add(lattice), o_abs = A.add(abs_tab), o_omega = A.add(omega), o_eps = A.add(epsv), o_ec = A.add(em_cell), o_ew = A.add(em_wall), o_eco = A.add(em_coarse),
-               o_bins = A.scratch<int32_t>((size_t)nb * 4 + 16), o_rec = A.scratch<int32_t>((size_t)N),
-               o_lost = A.scratch<unsigned long long>(((size_t)nb * 4 + 16) * (size_t)N);
-  if (h->arena_cap < A.total) {
+  h->image = im;
+  h->n_coarse = im->nc; h->n_cells = im->ncell; h->ns = im->ns; h->N = im->N; h->n_bands = im->nb;
+  h->n_affine = im->n_affine; h->n_bilinear = im->n_bilinear; h->has_eps = im->has_eps;
+  if (h->arena_cap < im->total) {
     cudaFree(h->arena);
     h->arena = nullptr; h->arena_cap = 0;
-    const size_t cap = A.total + A.total / 4;
+    const size_t cap = im->total + im->total / 4;
     if ((ce = cudaMalloc(&h->arena, cap)) != cudaSuccess) return bail(RTHX_ERR_CUDA, std::string("cudaMalloc(mesh arena): ") + cudaGetErrorString(ce));
     h->arena_cap = cap;
   }
-  lap("arena (host)");
-  void* base = h->arena;
-  if ((ce = cudaMemcpy(base, A.host.data(), A.host.size(), cudaMemcpyHostToDevice)) != cudaSuccess)
-    return bail(RTHX_ERR_CUDA, std::string("cudaMemcpy(mesh arena): ") + cudaGetErrorString(ce));
-  lap("cudaMemcpy H2D");
-  h->mesh_bytes = A.host.size();
-  unsigned char* b8 = static_cast<unsigned char*>(base);
-  P.coarse = (const CoarseDev*)(b8 + o_coarse); P.sets = (const FaceSetDev*)(b8 + o_sets);
-  P.bucket_start = (const int32_t*)(b8 + o_bstart); P.bucket_items = (const int32_t*)(b8 + o_bitems);
-  P.poly_nv = (const int32_t*)(b8 + o_nv); P.poly_vx = (const double*)(b8 + o_pvx); P.poly_vy = (const double*)(b8 + o_pvy);
-  P.poly_nx = (const double*)(b8 + o_pnx); P.poly_ny = (const double*)(b8 + o_pny);
-  P.cell_mid = (const double*)(b8 + o_mid); P.cell_volume = (const double*)(b8 + o_vol);
-  P.cell_surf_id = (const int32_t*)(b8 + o_surf); P.beta = (const double*)(b8 + o_beta); P.uniform_beta = (const double*)(b8 + o_ub);
-  P.omega = (const double*)(b8 + o_omega); P.eps = (const double*)(b8 + o_eps);
-  P.lattice = (const int32_t*)(b8 + o_lat); P.abs_tab = (const int32_t*)(b8 + o_abs); P.em_cell = (const int32_t*)(b8 + o_ec); P.em_wall = (const int32_t*)(b8 + o_ew);
-  P.em_coarse = (const int32_t*)(b8 + o_eco);
-  h->bins_dev = (int32_t*)(b8 + o_bins); h->bins_cap = (size_t)nb * 4 + 16;
-  h->rec_slot_dev = (int32_t*)(b8 + o_rec);
-  h->lost_dev = (unsigned long long*)(b8 + o_lost); h->lost_cap = ((size_t)nb * 4 + 16) * (size_t)N;
-  P.n_coarse = nc; P.n_cells = ncell; P.n_surfaces = ns; P.N = N;
-  h->coarse_fits_smem = sizeof(CoarseDev) * (size_t)nc <= 96 * 1024;   // 384 coarse faces; more are read through L1/L2 by the generic kernel
-  h->face0 = coarse[0];
-  h->single_quad = nc == 1 && coarse[0].kind == KIND_AFFINE_QUAD;
-  h->queue_ok = h->coarse_fits_smem && h->n_affine + h->n_bilinear == nc;
-  bool nbr_complete = true;
-  for (int c = 0; c < nc; ++c)
-    for (int k = 0; k < coarse[c].nv; ++k)
-      if (!coarse[c].solid[k] && coarse[c].nbr[k] < 0) nbr_complete = false;   // open / T-junction edge: needs the coarse point location
-  h->queue_general = h->n_bilinear > 0 || !nbr_complete;
+  if ((ce = cudaMemcpyAsync(h->arena, im->data, im->bytes, cudaMemcpyHostToDevice, h->stream)) != cudaSuccess)
+    return bail(RTHX_ERR_CUDA, std::string("cudaMemcpyAsync(mesh arena): ") + cudaGetErrorString(ce));
+  h->mesh_bytes = im->bytes;
+  TraceParams& P = h->base;
+  std::memset(&P, 0, sizeof(P));
+  unsigned char* b8 = static_cast<unsigned char*>(h->arena);
+  P.coarse = (const CoarseDev*)(b8 + im->o_coarse); P.sets = (const FaceSetDev*)(b8 + im->o_sets);
+  P.bucket_start = (const int32_t*)(b8 + im->o_bstart); P.bucket_items = (const int32_t*)(b8 + im->o_bitems);
+  P.poly_nv = (const int32_t*)(b8 + im->o_nv); P.poly_vx = (const double*)(b8 + im->o_pvx); P.poly_vy = (const double*)(b8 + im->o_pvy);
+  P.poly_nx = nullptr; P.poly_ny = nullptr;      // per-polygon normals belong to the generic tables (ensure_generic)
+  P.cell_mid = (const double*)(b8 + im->o_mid); P.cell_volume = (const double*)(b8 + im->o_vol);
+  P.cell_surf_id = (const int32_t*)(b8 + im->o_surf); P.beta = (const double*)(b8 + im->o_beta); P.uniform_beta = (const double*)(b8 + im->o_ub);
+  P.omega = (const double*)(b8 + im->o_omega); P.eps = (const double*)(b8 + im->o_eps);
+  P.lattice = (const int32_t*)(b8 + im->o_lat); P.abs_tab = (const int32_t*)(b8 + im->o_abs);
+  P.em_cell = (const int32_t*)(b8 + im->o_ec); P.em_wall = (const int32_t*)(b8 + im->o_ew); P.em_coarse = (const int32_t*)(b8 + im->o_eco);
+  h->bins_dev = (int32_t*)(b8 + im->o_bins); h->bins_cap = (size_t)im->nb * 4 + 16;
+  h->rec_slot_dev = (int32_t*)(b8 + im->o_rec);
+  h->lost_dev = (unsigned long long*)(b8 + im->o_lost); h->lost_cap = ((size_t)im->nb * 4 + 16) * (size_t)im->N;
+  P.n_coarse = im->nc; P.n_cells = im->ncell; P.n_surfaces = im->ns; P.N = im->N;
+  h->coarse_fits_smem = sizeof(CoarseDev) * (size_t)im->nc <= 96 * 1024;   // 384 coarse faces; more are read through L1/L2 by the generic kernel
+  h->face0 = im->face0;
+  h->single_quad = im->nc == 1 && im->face0.kind == KIND_AFFINE_QUAD;
+  h->queue_ok = h->coarse_fits_smem && im->n_affine + im->n_bilinear == im->nc;
+  h->queue_general = im->n_bilinear > 0 || !im->nbr_complete;
   h->fast_ok = h->queue_ok && !h->queue_general;   // the FAST form of the general kernel: affine kinds with a complete neighbour table
+  h->generic_ready = false;
   {
     // once per device and process: a few hundred cudaFuncSetAttribute calls cost milliseconds, and callers re-create the
     // handle for every trace
@@ -600,8 +711,127 @@ extern "C" int rthx_create(rthx_handle** out, const rthx_mesh* m, int device_id)
     }
     if (ce != cudaSuccess) return bail(RTHX_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce));   // bail re-takes the pool lock
   }
-  lap("kernel attributes");
+  if (im->needs_generic) {
+    const int rc = ensure_generic(h);
+    if (rc) return bail(rc, h->err);
+  }
+  if (sync && (ce = cudaStreamSynchronize(h->stream)) != cudaSuccess) return bail(RTHX_ERR_CUDA, std::string("mesh upload: ") + cudaGetErrorString(ce));
   *out = h;
+  return RTHX_OK;
+}
+
+int check_mesh_args(const rthx_mesh* m) {
+  if (!m || m->n_coarse < 1 || m->n_cells < 1 || m->n_bands < 1 || m->n_surfaces < 0 || !m->coarse_nv || !m->coarse_vx ||
+      !m->coarse_vy || !m->coarse_solid || !m->fine_off || !m->cell_nv || !m->cell_vx || !m->cell_vy || !m->cell_mid ||
+      !m->cell_volume || !m->cell_surf_id || !m->kappa || !m->sigma_s || !m->uniform_beta)
+    return fail(nullptr, RTHX_ERR_ARG, "rthx_create: NULL or empty mesh field");
+  return RTHX_OK;
+}
+
+}  // namespace
+
+// Tables of the reference-faithful locator (uniform grids per fine-cell set, per-polygon normals): derived from the image on
+// first use — at rthx_create for meshes with unverifiable lattices or more than 384 coarse faces, else by the first trace that
+// asks for RTHX_LOCATOR_GENERIC or needs the generic kernel.  cfg3: 1.1 ms of host work that the analytic paths never pay.
+static int ensure_generic(rthx_handle* h) {
+  if (h->generic_ready) return RTHX_OK;
+  const HostImage& im = *h->image;
+  const int nc = im.nc, ncell = im.ncell;
+  std::vector<Poly> polys((size_t)ncell + nc);
+  const int32_t* nv = im.at<int32_t>(im.o_nv);
+  const double* pvx = im.at<double>(im.o_pvx);
+  const double* pvy = im.at<double>(im.o_pvy);
+  const double* mid = im.at<double>(im.o_mid);
+  const double* vol = im.at<double>(im.o_vol);
+  for (int g = 0; g < ncell; ++g) {
+    Poly& p = polys[g];
+    p.n = nv[g];
+    for (int i = 0; i < p.n; ++i) { p.vx[i] = pvx[4 * (size_t)g + i]; p.vy[i] = pvy[4 * (size_t)g + i]; }
+    p.midx = mid[2 * (size_t)g]; p.midy = mid[2 * (size_t)g + 1]; p.volume = vol[g];
+    poly_finish(p);
+  }
+  for (int c = 0; c < nc; ++c) polys[(size_t)ncell + c] = im.coarse_polys[c];
+  std::vector<FaceSetDev> sets(1 + (size_t)nc);
+  std::vector<int32_t> bstart, bitems;
+  build_grid(&polys[ncell], nc, ncell, sets[0], bstart, bitems);
+  for (int c = 0; c < nc; ++c) build_grid(&polys[im.fine_off[c]], im.fine_off[c + 1] - im.fine_off[c], im.fine_off[c], sets[1 + c], bstart, bitems);
+  std::vector<double> pnx(polys.size() * 4), pny(polys.size() * 4);
+  for (size_t i = 0; i < polys.size(); ++i)
+    for (int k = 0; k < 4; ++k) { pnx[4 * i + k] = polys[i].nx[k]; pny[4 * i + k] = polys[i].ny[k]; }
+  Arena A;
+  const size_t o_sets = A.add(sets), o_bstart = A.add(bstart), o_bitems = A.add(bitems), o_pnx = A.add(pnx), o_pny = A.add(pny);
+  CU(h, cudaSetDevice(h->device));
+  if (h->generic_cap < A.total) {
+    cudaFree(h->generic_arena);
+    h->generic_arena = nullptr; h->generic_cap = 0;
+    CU(h, cudaMalloc(&h->generic_arena, A.total + A.total / 4));
+    h->generic_cap = A.total + A.total / 4;
+  }
+  CU(h, cudaMemcpy(h->generic_arena, A.host.data(), A.host.size(), cudaMemcpyHostToDevice));
+  unsigned char* b8 = static_cast<unsigned char*>(h->generic_arena);
+  TraceParams& P = h->base;
+  P.sets = (const FaceSetDev*)(b8 + o_sets); P.bucket_start = (const int32_t*)(b8 + o_bstart); P.bucket_items = (const int32_t*)(b8 + o_bitems);
+  P.poly_nx = (const double*)(b8 + o_pnx); P.poly_ny = (const double*)(b8 + o_pny);
+  h->mesh_bytes = im.bytes + A.host.size();
+  h->generic_ready = true;
+  return RTHX_OK;
+}
+
+extern "C" int rthx_device_count(int* n) {
+  if (!n) return RTHX_ERR_ARG;
+  *n = 0;
+  int n_dev = 0;
+  const cudaError_t ce = cudaGetDeviceCount(&n_dev);
+  if (ce != cudaSuccess || n_dev == 0) { cudaGetLastError(); return fail(nullptr, RTHX_ERR_CUDA, std::string("no CUDA device (") + cudaGetErrorString(ce) + "); there is no CPU fallback"); }
+  int usable = 0;
+  for (int d = 0; d < n_dev; ++d) {
+    int major = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major >= 10) ++usable;
+  }
+  *n = usable;
+  return usable ? RTHX_OK : fail(nullptr, RTHX_ERR_CUDA, "no sm_100 class device (kernels are built for sm_100a only)");
+}
+
+extern "C" int rthx_create(rthx_handle** out, const rthx_mesh* m, int device_id) {
+  if (!out) return fail(nullptr, RTHX_ERR_ARG, "rthx_create: out is NULL");
+  *out = nullptr;
+  return rthx_create_multi(out, m, &device_id, 1);
+}
+
+extern "C" int rthx_create_multi(rthx_handle** out, const rthx_mesh* m, const int* device_ids, int n) {
+  if (!out || !device_ids || n < 1) return fail(nullptr, RTHX_ERR_ARG, "rthx_create_multi: bad argument");
+  for (int i = 0; i < n; ++i) out[i] = nullptr;
+  int rc = check_mesh_args(m);
+  if (rc) return rc;
+  int n_dev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&n_dev);
+  if (ce != cudaSuccess || n_dev == 0)
+    return fail(nullptr, RTHX_ERR_CUDA, std::string("rthx_create: no CUDA device (") + cudaGetErrorString(ce) + "); there is no CPU fallback");
+  for (int i = 0; i < n; ++i) {
+    if (device_ids[i] < 0 || device_ids[i] >= n_dev) return fail(nullptr, RTHX_ERR_ARG, "rthx_create: bad device id");
+    for (int j = 0; j < i; ++j) if (device_ids[j] == device_ids[i]) return fail(nullptr, RTHX_ERR_ARG, "rthx_create_multi: duplicate device id");
+  }
+  const bool timing = std::getenv("RTHX_CREATE_TIMING") != nullptr;
+  const auto t0 = std::chrono::steady_clock::now();
+  std::shared_ptr<HostImage> im;
+  std::string err;
+  rc = prepare_mesh(m, im, err);
+  if (rc) return fail(nullptr, rc, err);
+  const auto t1 = std::chrono::steady_clock::now();
+  auto undo = [&]() { for (int i = 0; i < n; ++i) { if (out[i]) rthx_destroy(out[i]); out[i] = nullptr; } };
+  for (int i = 0; i < n; ++i) {
+    rc = create_on_device(&out[i], im, device_ids[i], n_dev, /*sync=*/false);
+    if (rc) { const std::string keep = g_create_err; undo(); g_create_err = keep; return rc; }
+  }
+  for (int i = 0; i < n; ++i) {       // every upload is in flight: wait for all of them
+    cudaSetDevice(out[i]->device);
+    if ((ce = cudaStreamSynchronize(out[i]->stream)) != cudaSuccess) { undo(); return fail(nullptr, RTHX_ERR_CUDA, std::string("mesh upload: ") + cudaGetErrorString(ce)); }
+  }
+  if (timing) {
+    const auto t2 = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "rthx_create: host preparation %.3f ms, %d device(s) %.3f ms\n", std::chrono::duration<double, std::milli>(t1 - t0).count(), n,
+                 std::chrono::duration<double, std::milli>(t2 - t1).count());
+  }
   return RTHX_OK;
 }
 
@@ -625,6 +855,8 @@ int check_args(rthx_handle* h, const rthx_trace_args* a) {
   if (!a) return fail(h, RTHX_ERR_ARG, "trace: args is NULL");
   if (a->rays_per_emitter < 0) return fail(h, RTHX_ERR_ARG, "trace: rays_per_emitter out of range");
   if (a->n_bins < 1 || !a->bins) return fail(h, RTHX_ERR_ARG, "trace: n_bins must be >= 1");
+  // the scratch regions behind the mesh image (bins, lost) are sized at rthx_create for 4 n_bands + 16 traced bins
+  if ((size_t)a->n_bins > h->bins_cap || (size_t)a->n_bins * (size_t)h->N > h->lost_cap) return fail(h, RTHX_ERR_ARG, "trace: too many bins in one call (limit 4 * n_bands + 16)");
   for (int i = 0; i < a->n_bins; ++i) if (a->bins[i] < 0 || a->bins[i] >= h->n_bands) return fail(h, RTHX_ERR_ARG, "trace: band index out of range");
   if (a->mode != RTHX_FIRST_INTERACTION && a->mode != RTHX_MULTI_BOUNCE && a->mode != RTHX_MULTI_BOUNCE_SPECULAR) return fail(h, RTHX_ERR_ARG, "trace: unknown mode");
   if (a->mode != RTHX_FIRST_INTERACTION && !h->has_eps) return fail(h, RTHX_ERR_ARG, "trace: MULTI_BOUNCE needs rthx_mesh.epsilon");
@@ -651,6 +883,12 @@ LaunchPlan make_plan(const rthx_handle* h, const rthx_trace_args* a, int rank, i
   if (const char* ev = std::getenv("RTHX_FORCE_GLOBAL_TALLY")) { if (std::atoi(ev)) pl.hist_in_smem = 0; }   // test knob: the N > ~57k path
   pl.sq = (h->single_quad && a->locator != RTHX_LOCATOR_GENERIC && pl.hist_in_smem) ? 1 : 0;
   if (const char* ev = std::getenv("RTHX_NO_SQ")) { if (std::atoi(ev)) pl.sq = 0; }   // test / tuning knob
+  // MULTI_BOUNCE on any mesh with analytic locators runs in the queue kernel's MULTI variant (lanes refill when their ray is
+  // absorbed); RTHX_MULTI_SQ=1 keeps the lock-step loop of the SQ kernel on single-quad domains (A/B knob)
+  bool multi_queue = pl.multi && h->queue_ok && a->locator != RTHX_LOCATOR_GENERIC && pl.hist_in_smem && pl.block_threads == 256;
+  if (const char* ev = std::getenv("RTHX_MULTI_SQ")) { if (std::atoi(ev) && pl.sq) multi_queue = false; }
+  if (const char* ev = std::getenv("RTHX_QUEUE_DEPTH")) { if (std::atoi(ev) == 0 && !pl.sq) multi_queue = false; }
+  if (multi_queue) pl.sq = 0;
   if (pl.sq && pl.multi) {
     pl.fast = 1; pl.minb = 4;                        // trace_exchange_sq_kernel<4, MULTI>
   } else if (pl.sq) {
@@ -661,18 +899,20 @@ LaunchPlan make_plan(const rthx_handle* h, const rthx_trace_args* a, int rank, i
   pl.smem_bytes = coarse_bytes + em_bytes + (pl.hist_in_smem ? hist_bytes : 0);
   // Multi-face FAST meshes: the queue kernel (per-warp ray queue in shared memory, 40 bytes per parked ray).  Depth = as many
   // rays per lane as still leave 4 resident blocks per SM, at most 8; RTHX_QUEUE_DEPTH overrides (0 = the lock-step kernel).
-  if (h->queue_ok && a->locator != RTHX_LOCATOR_GENERIC && !pl.multi && !pl.sq && pl.hist_in_smem && pl.block_threads == 256 &&
-      (h->n_coarse > 1 || h->queue_general)) {
+  if (h->queue_ok && a->locator != RTHX_LOCATOR_GENERIC && (!pl.multi || multi_queue) && !pl.sq && pl.hist_in_smem && pl.block_threads == 256 &&
+      (h->n_coarse > 1 || h->queue_general || multi_queue)) {
     const size_t base = (pl.smem_bytes + 15) & ~size_t(15);
     const size_t per_depth = (size_t)pl.block_threads * 40;
-    // aim at 4 resident blocks per SM; large descriptor tables / histograms settle for 3, 2 or 1
+    // aim at 4 resident blocks per SM (3 for the MULTI variant, which is bounded to 85 registers); large descriptor tables /
+    // histograms settle for fewer
     int depth = 0;
-    for (int blocks = 4; blocks >= 1 && depth == 0; --blocks) {
+    const size_t max_depth = multi_queue ? 2 : 4;
+    for (int blocks = multi_queue ? 3 : 4; blocks >= 1 && depth == 0; --blocks) {
       const size_t budget = std::min((size_t)h->prop.sharedMemPerMultiprocessor / blocks - 1024, (size_t)h->prop.sharedMemPerBlockOptin);
-      if (base + per_depth <= budget) depth = (int)std::min<size_t>(4, (budget - base) / per_depth);
+      if (base + per_depth <= budget) depth = (int)std::min<size_t>(max_depth, (budget - base) / per_depth);
     }
-    if (const char* ev = std::getenv("RTHX_QUEUE_DEPTH")) { const int v = std::atoi(ev); if (v >= 0 && v <= 4) depth = v; }
-    if (depth == 3) depth = 2;                       // compiled depths: 1, 2, 4 rays per lane and batch
+    if (const char* ev = std::getenv("RTHX_QUEUE_DEPTH")) { const int v = std::atoi(ev); if (v >= 0 && v <= (int)max_depth) depth = v; }
+    if (depth == 3) depth = 2;                       // compiled depths: 1, 2, 4 rays per lane and batch (MULTI: 1, 2)
     if (depth >= 1 && base + depth * per_depth <= h->prop.sharedMemPerBlockOptin) {
       pl.fast = 1; pl.minb = 6; pl.queue_depth = depth; pl.smem_bytes = base + depth * per_depth;
     }
@@ -688,10 +928,13 @@ LaunchPlan make_plan(const rthx_handle* h, const rthx_trace_args* a, int rank, i
     const long long max_chunks = std::max<long long>(1, a->rays_per_emitter / min_rays);
     chunks = std::max<long long>(1, std::min(chunks, max_chunks));
   }
-  // a u32 row histogram must not overflow
-  while ((a->rays_per_emitter + chunks - 1) / chunks > 0xFFFFFFFFll) chunks *= 2;
-  while (rows * chunks > 0x7FFFFFFFll && chunks > 1) chunks /= 2;
-  pl.row_chunks = (int)chunks;
+  // A block's rays are counted in 32 bits (u32 row histogram, u32 loop counter advancing by blockDim.x): at most 2^31 rays per
+  // block.  Auto-chosen chunk counts are raised to satisfy that; a plan that then exceeds the 1-D grid limit — or a caller-supplied
+  // row_chunks that violates either bound — is rejected (n_blocks = -1 -> RTHX_ERR_ARG), never silently wrapped.
+  if (a->row_chunks <= 0)
+    while ((a->rays_per_emitter + chunks - 1) / chunks > 0x7FFFFFFFll) chunks *= 2;
+  pl.row_chunks = (int)std::min<long long>(chunks, 0x7FFFFFFFll);
+  if ((a->rays_per_emitter + chunks - 1) / chunks > 0x7FFFFFFFll || rows * chunks > 0x7FFFFFFFll) { pl.n_blocks = -1; return pl; }
   pl.n_blocks = (int)(rows * chunks);
   return pl;
 }
@@ -773,7 +1016,8 @@ int enqueue_trace(rthx_handle* h, const rthx_trace_args* a, int rank, int world,
                   unsigned long long* lost, int zero_first, bool with_rec, int n_rec_slots, cudaStream_t stream,
                   LaunchPlan* plan_out, int* n_launches, int y0 = 0, int y1 = -1, bool upload_bins = true) {
   LaunchPlan pl = make_plan(h, a, rank, world);
-  if ((size_t)a->n_bins > h->bins_cap) return fail(h, RTHX_ERR_ARG, "trace: too many bins in one call");
+  if (pl.n_blocks < 0) return fail(h, RTHX_ERR_ARG, "trace: rays_per_emitter / row_chunks out of range (a block traces at most 2^31 rays, a launch at most 2^31 blocks)");
+  if (!pl.fast) { const int rcg = ensure_generic(h); if (rcg) return rcg; }     // the generic kernel reads the reference-faithful locator tables
   if (upload_bins) CU(h, cudaMemcpyAsync(h->bins_dev, a->bins, sizeof(int32_t) * (size_t)a->n_bins, cudaMemcpyHostToDevice, stream));
   const size_t rows = compact ? (size_t)pl.n_owned : (size_t)h->N;
   if (zero_first == RTHX_ZERO_ALL) {
@@ -826,8 +1070,12 @@ int pipeline_launch(rthx_handle* h, const rthx_trace_args* a, int rank, int worl
                     LaunchPlan* plan_out, int* n_launches, int* n_batches_out) {
   const int N = h->N;
   const int n_owned = (N - rank + world - 1) / world;
+  // counts_dev is about to be overwritten: whatever view an earlier trace left behind (resident bins, CSR row pointers) is void
+  // until the caller re-validates it (rthx_trace_exchange does, for a complete single-device trace)
+  h->last_trace_bins = 0; h->csr_bin = -1; h->csc_bin = -1;
   CU(h, ensure(&h->counts_dev, &h->counts_cap, (size_t)a->n_bins * (size_t)n_owned * N));
   LaunchPlan pl = make_plan(h, a, rank, world);
+  if (pl.n_blocks < 0) return fail(h, RTHX_ERR_ARG, "trace: rays_per_emitter / row_chunks out of range (a block traces at most 2^31 rays, a launch at most 2^31 blocks)");
   // batches: >= ~2 waves of resident blocks each, at most 16 (consecutive batches alternate between two streams, so a batch's
   // draining tail overlaps the next one's head; cfg3 at 1e10 rays: 16 batches, the copy behind the last kernel is 17 MB and the
   // call ends 0.5 ms after the kernel — with 5 even batches it was 180 MB and 3.6 ms)
@@ -1043,77 +1291,156 @@ extern "C" int rthx_trace_exchange_device(rthx_handle* h, const rthx_trace_args*
   return RTHX_OK;
 }
 
+namespace {
+
+// Per-device outcome of rthx_trace_exchange_multi (one host thread drives each device).
+struct MultiJob {
+  int rc = RTHX_OK;
+  std::string err;
+  LaunchPlan plan{};
+  int slots = 0, batches = 1, launches = 0;
+  double kernel_ms = 0, total_ms = 0;
+  std::vector<uint64_t> lost;
+};
+
+// Recorder read-back of one device in a multi-device trace: every device holds slots for all recorded elements, only the rows it
+// owns were written.  Appends one chunk per owned recorded element.
+struct RecChunk { int elem; std::vector<double> o, e; };
+
+int gather_recorder(rthx_handle* h, const rthx_trace_args* a, int rank, int world, int n_slots, std::vector<RecChunk>& chunks) {
+  if (n_slots <= 0) return RTHX_OK;
+  const int N = h->N;
+  const size_t rpe = (size_t)a->rays_per_emitter, pts = (size_t)n_slots * rpe;
+  std::vector<double> buf(pts * 4);
+  std::vector<uint8_t> valid(pts);
+  CU(h, cudaMemcpy(buf.data(), h->rec_pts_dev, sizeof(double) * pts * 4, cudaMemcpyDeviceToHost));
+  CU(h, cudaMemcpy(valid.data(), h->rec_valid_dev, pts, cudaMemcpyDeviceToHost));
+  std::vector<int32_t> slot(N, -1);
+  for (int k = 0; k < a->n_rec_ids; ++k) if (a->rec_ids[k] >= 0 && a->rec_ids[k] < N) slot[a->rec_ids[k]] = 0;
+  int ord = 0;
+  for (int e = 0; e < N; ++e) {
+    if (slot[e] != 0) continue;
+    const int s_ = ord++;
+    if (e % world != rank) continue;
+    RecChunk c; c.elem = e;
+    for (size_t r = 0; r < rpe; ++r) {
+      const size_t s = (size_t)s_ * rpe + r;
+      if (!valid[s]) continue;
+      c.o.push_back(buf[4 * s]); c.o.push_back(buf[4 * s + 1]); c.e.push_back(buf[4 * s + 2]); c.e.push_back(buf[4 * s + 3]);
+    }
+    chunks.push_back(std::move(c));
+  }
+  return RTHX_OK;
+}
+
+}  // namespace
+
+// Single-process multi-GPU trace.  One host thread per device enqueues that device's work and drains its copies, so neither the
+// launch sequences (a few dozen driver calls each) nor the staging of a pageable destination serialise across devices.
+//   counts_out != NULL : every device traces its rows e = i (mod n) into a compact matrix of its own and copies exactly those rows
+//                        into the caller's matrix (pipelined behind the kernels, each over its own PCIe link).  The rows tile the
+//                        matrix, so nothing is cleared on the host and nothing is reduced.
+//   counts_out == NULL : the devices flush their rows straight into ONE matrix in the memory of hs[0]'s device through peer access
+//                        (NVLink / NVSwitch, system-scope red.add.u64 fused into the trace kernel).  The complete matrix stays
+//                        resident on hs[0] for rthx_counts_csr / rthx_counts_csc / rthx_smooth_* / rthx_solve_grey.
 extern "C" int rthx_trace_exchange_multi(rthx_handle** hs, int n, const rthx_trace_args* a, uint64_t* counts_out, uint64_t* lost_out,
                                          rthx_rec_out* rec, rthx_stats* st) {
   if (!hs || n < 1 || !hs[0]) return RTHX_ERR_ARG;
   rthx_handle* h0 = hs[0];
   int rc = check_args(h0, a);
   if (rc) return rc;
-  if (!counts_out) return fail(h0, RTHX_ERR_ARG, "trace_multi: counts_out is NULL");
   const int N = h0->N;
-  for (int i = 0; i < n; ++i) if (!hs[i] || hs[i]->N != N || hs[i]->n_bands != h0->n_bands) return fail(h0, RTHX_ERR_ARG, "trace_multi: handles differ");
-  std::vector<LaunchPlan> plans(n);
-  std::vector<int> slots(n, 0), batches(n, 1);
-  int n_launches = 0;
-  // enqueue on every device first, then drain: the devices run concurrently
-  if (n > 1) std::memset(counts_out, 0, sizeof(uint64_t) * (size_t)a->n_bins * N * N);
   for (int i = 0; i < n; ++i) {
-    rthx_handle* h = hs[i];
-    CU(h0, cudaSetDevice(h->device));
-    CU(h0, cudaEventRecord(h->ev[0], h->stream));
-    rc = prepare_recorder(h, a, rec, &slots[i], h->stream);
-    if (rc) return fail(h0, rc, h->err);
-    rc = pipeline_launch(h, a, i, n, rec != nullptr, slots[i], &plans[i], &n_launches, &batches[i]);
-    if (rc) return fail(h0, rc, h->err);
+    if (!hs[i] || hs[i]->N != N || hs[i]->n_bands != h0->n_bands) return fail(h0, RTHX_ERR_ARG, "trace_multi: handles differ");
+    for (int j = 0; j < i; ++j) if (hs[j] == hs[i] || hs[j]->device == hs[i]->device) return fail(h0, RTHX_ERR_ARG, "trace_multi: one handle per device");
   }
-  for (int i = 0; i < n; ++i) {   // every device is busy by now: drain the copies device by device
-    rthx_handle* h = hs[i];
-    CU(h0, cudaSetDevice(h->device));
-    rc = pipeline_copy(h, a, i, n, counts_out, batches[i]);
-    if (rc) return fail(h0, rc, h->err);
-    CU(h0, cudaEventRecord(h->ev[3], h->copy_stream));
-  }
-  std::vector<uint64_t> lost_sum((size_t)a->n_bins * N, 0), lost_host((size_t)a->n_bins * N);
-  double max_ms = 0;
-  if (rec) rec->n_recorded = 0;
-  // recorded rays must come out in ascending element order: gather per device, then merge by element
-  struct RecChunk { int elem; std::vector<double> o, e; };
-  std::vector<RecChunk> chunks;
-  for (int i = 0; i < n; ++i) {
-    rthx_handle* h = hs[i];
-    CU(h0, cudaSetDevice(h->device));
-    CU(h0, cudaStreamSynchronize(h->copy_stream));
-    CU(h0, cudaMemcpyAsync(lost_host.data(), h->lost_dev, sizeof(uint64_t) * lost_host.size(), cudaMemcpyDeviceToHost, h->stream));
-    CU(h0, cudaStreamSynchronize(h->stream));
-    for (size_t k = 0; k < lost_sum.size(); ++k) lost_sum[k] += lost_host[k];
-    float ms = 0;
-    CU(h0, cudaEventElapsedTime(&ms, h->ev[0], h->ev[3]));
-    max_ms = std::max(max_ms, (double)ms);
-    if (rec && slots[i] > 0) {
-      // every device holds slots for all recorded elements; only the rows it owns were written
-      const size_t rpe = (size_t)a->rays_per_emitter, pts = (size_t)slots[i] * rpe;
-      std::vector<double> buf(pts * 4);
-      std::vector<uint8_t> valid(pts);
-      CU(h0, cudaMemcpy(buf.data(), h->rec_pts_dev, sizeof(double) * pts * 4, cudaMemcpyDeviceToHost));
-      CU(h0, cudaMemcpy(valid.data(), h->rec_valid_dev, pts, cudaMemcpyDeviceToHost));
-      std::vector<int32_t> slot(N, -1);
-      for (int k = 0; k < a->n_rec_ids; ++k) if (a->rec_ids[k] >= 0 && a->rec_ids[k] < N) slot[a->rec_ids[k]] = 0;
-      int ord = 0;
-      for (int e = 0; e < N; ++e) {
-        if (slot[e] != 0) continue;
-        const int s_ = ord++;
-        if (e % n != i) continue;
-        RecChunk c; c.elem = e;
-        for (size_t r = 0; r < rpe; ++r) {
-          const size_t s = (size_t)s_ * rpe + r;
-          if (!valid[s]) continue;
-          c.o.push_back(buf[4 * s]); c.o.push_back(buf[4 * s + 1]); c.e.push_back(buf[4 * s + 2]); c.e.push_back(buf[4 * s + 3]);
-        }
-        chunks.push_back(std::move(c));
-      }
+  const bool gather = counts_out == nullptr;
+  const size_t lost_n = (size_t)a->n_bins * N;
+  std::vector<MultiJob> jobs(n);
+  unsigned long long* shared_counts = nullptr;
+  if (gather) {
+    // the full matrix lives on hs[0]; the other devices need peer access to it
+    CU(h0, cudaSetDevice(h0->device));
+    h0->last_trace_bins = 0; h0->csr_bin = -1; h0->csc_bin = -1;
+    CU(h0, ensure(&h0->counts_dev, &h0->counts_cap, (size_t)a->n_bins * (size_t)N * N));
+    shared_counts = h0->counts_dev;
+    for (int i = 1; i < n; ++i) {
+      int can = 0;
+      CU(h0, cudaDeviceCanAccessPeer(&can, hs[i]->device, h0->device));
+      if (!can) return fail(h0, RTHX_ERR_CUDA, "trace_multi: no peer access between the devices (pass a host matrix instead)");
+      CU(h0, cudaSetDevice(hs[i]->device));
+      const cudaError_t pe = cudaDeviceEnablePeerAccess(h0->device, 0);
+      if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) return fail(h0, RTHX_ERR_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(pe));
+      cudaGetLastError();
+      hs[i]->last_trace_bins = 0; hs[i]->csr_bin = -1; hs[i]->csc_bin = -1;
     }
+    // device 0 clears the matrix and the lost counters; every device's kernel waits for that
+    CU(h0, cudaSetDevice(h0->device));
+    CU(h0, cudaEventRecord(h0->ev[0], h0->stream));
+    CU(h0, cudaMemsetAsync(shared_counts, 0, sizeof(unsigned long long) * (size_t)a->n_bins * N * N, h0->stream));
+    CU(h0, cudaMemsetAsync(h0->lost_dev, 0, sizeof(unsigned long long) * lost_n, h0->stream));
+    CU(h0, cudaEventRecord(h0->bev[17], h0->stream));
+  }
+  auto device_job = [&](int i) {
+    rthx_handle* h = hs[i];
+    MultiJob& J = jobs[i];
+    auto run = [&]() -> int {
+      CU(h, cudaSetDevice(h->device));
+      if (!gather || i > 0) CU(h, cudaEventRecord(h->ev[0], h->stream));
+      int r = prepare_recorder(h, a, rec, &J.slots, h->stream);
+      if (r) return r;
+      if (gather) {
+        if (i > 0) CU(h, cudaStreamWaitEvent(h->stream, h0->bev[17], 0));
+        CU(h, cudaEventRecord(h->ev[1], h->stream));
+        r = enqueue_trace(h, a, i, n, /*compact=*/false, shared_counts, h0->lost_dev, RTHX_ZERO_NONE, rec != nullptr, J.slots, h->stream, &J.plan, &J.launches);
+        if (r) return r;
+        CU(h, cudaEventRecord(h->ev[2], h->stream));
+        CU(h, cudaEventRecord(h->ev[3], h->stream));
+        CU(h, cudaStreamSynchronize(h->stream));
+      } else {
+        r = pipeline_launch(h, a, i, n, rec != nullptr, J.slots, &J.plan, &J.launches, &J.batches);
+        if (r) return r;
+        r = pipeline_copy(h, a, i, n, counts_out, J.batches);
+        if (r) return r;
+        J.lost.resize(lost_n);
+        CU(h, cudaMemcpyAsync(J.lost.data(), h->lost_dev, sizeof(uint64_t) * lost_n, cudaMemcpyDeviceToHost, h->copy_stream));
+        CU(h, cudaEventRecord(h->ev[3], h->copy_stream));
+        CU(h, cudaStreamSynchronize(h->copy_stream));
+        CU(h, cudaStreamSynchronize(h->stream));
+      }
+      float ms = 0;
+      CU(h, cudaEventElapsedTime(&ms, h->ev[1], h->ev[2])); J.kernel_ms = ms;
+      CU(h, cudaEventElapsedTime(&ms, h->ev[0], h->ev[3])); J.total_ms = ms;
+      return RTHX_OK;
+    };
+    J.rc = run();
+    if (J.rc) J.err = h->err;
+  };
+  {
+    std::vector<std::thread> th;
+    for (int i = 1; i < n; ++i) th.emplace_back(device_job, i);
+    device_job(0);
+    for (auto& t : th) t.join();
+  }
+  for (int i = 0; i < n; ++i) if (jobs[i].rc) return fail(h0, jobs[i].rc, jobs[i].err);
+  std::vector<uint64_t> lost_sum(lost_n, 0);
+  if (gather) {
+    CU(h0, cudaSetDevice(h0->device));
+    CU(h0, cudaMemcpy(lost_sum.data(), h0->lost_dev, sizeof(uint64_t) * lost_n, cudaMemcpyDeviceToHost));
+    h0->last_trace_bins = a->n_bins; h0->last_trace_rows = (size_t)N;
+  } else {
+    for (int i = 0; i < n; ++i)
+      for (size_t k = 0; k < lost_n; ++k) lost_sum[k] += jobs[i].lost[k];
   }
   if (rec) {
+    // recorded rays must come out in ascending element order: gather per device, then merge by element
+    rec->n_recorded = 0;
+    std::vector<RecChunk> chunks;
+    for (int i = 0; i < n; ++i) {
+      CU(h0, cudaSetDevice(hs[i]->device));
+      rc = gather_recorder(hs[i], a, i, n, jobs[i].slots, chunks);
+      if (rc) return fail(h0, rc, hs[i]->err);
+    }
     std::sort(chunks.begin(), chunks.end(), [](const RecChunk& x, const RecChunk& y) { return x.elem < y.elem; });
     for (auto& c : chunks)
       for (size_t k = 0; k < c.o.size(); k += 2) {
@@ -1123,17 +1450,34 @@ extern "C" int rthx_trace_exchange_multi(rthx_handle** hs, int n, const rthx_tra
         rec->endpoints[2 * q] = c.e[k]; rec->endpoints[2 * q + 1] = c.e[k + 1];
       }
   }
-  if (lost_out) std::memcpy(lost_out, lost_sum.data(), sizeof(uint64_t) * lost_sum.size());
+  if (lost_out) std::memcpy(lost_out, lost_sum.data(), sizeof(uint64_t) * lost_n);
   if (st) {
-    fill_stats(st, plans[0], a);
+    fill_stats(st, jobs[0].plan, a);
     st->rays_traced = (int64_t)N * a->n_bins * a->rays_per_emitter;
     int64_t nl = 0;
     for (uint64_t v : lost_sum) nl += (int64_t)v;
-    st->rays_lost = nl; st->total_ms = max_ms; st->kernel_ms = 0; st->n_launches = n_launches;
-    int nbk = 0;
-    for (auto& p : plans) nbk += p.n_blocks;
-    st->n_blocks = nbk;
+    st->rays_lost = nl;
+    int nbk = 0, nlaunch = 0;
+    double kmax = 0, tmax = 0;
+    for (auto& J : jobs) { nbk += J.plan.n_blocks; nlaunch += J.launches; kmax = std::max(kmax, J.kernel_ms); tmax = std::max(tmax, J.total_ms); }
+    st->n_blocks = nbk; st->n_launches = nlaunch + (gather ? 2 : 0);
+    st->kernel_ms = kmax; st->total_ms = tmax;     // the slowest device
   }
+  return RTHX_OK;
+}
+
+extern "C" int rthx_host_alloc(void** ptr, uint64_t bytes) {
+  if (!ptr || bytes == 0) return fail(nullptr, RTHX_ERR_ARG, "rthx_host_alloc: bad argument");
+  *ptr = nullptr;
+  cudaError_t e = cudaHostAlloc(ptr, (size_t)bytes, cudaHostAllocPortable);
+  if (e != cudaSuccess) { cudaGetLastError(); return fail(nullptr, e == cudaErrorMemoryAllocation ? RTHX_ERR_NOMEM : RTHX_ERR_CUDA, std::string("cudaHostAlloc: ") + cudaGetErrorString(e)); }
+  return RTHX_OK;
+}
+
+extern "C" int rthx_host_free(void* ptr) {
+  if (!ptr) return RTHX_OK;
+  cudaError_t e = cudaFreeHost(ptr);
+  if (e != cudaSuccess) return fail(nullptr, RTHX_ERR_CUDA, std::string("cudaFreeHost: ") + cudaGetErrorString(e));
   return RTHX_OK;
 }
 
@@ -1198,44 +1542,159 @@ extern "C" int rthx_shared_free(int device_id, void* dev_ptr) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// device-side step flags for one-process-per-GPU runs: the ranks of a fused peer flush synchronise through 64-bit counters in
+// the owner's memory (a release store over NVLink after the trace kernel, an acquire spin in front of the consumer) instead of
+// a host-launched collective per step
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+__global__ void flag_signal_kernel(unsigned long long* flag, unsigned long long value) {
+  __threadfence_system();                                   // cumulative: everything the stream's earlier kernels wrote (the red.sys
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(value) : "memory");   // flush of the rows) is visible before the flag
+}
+// lane i spins until flags[i] >= value; gives up after timeout_ns (a dead peer must not hang the GPU) and raises *err
+__global__ void flag_wait_kernel(const unsigned long long* flags, int n, unsigned long long value, unsigned long long timeout_ns, unsigned long long* err) {
+  unsigned long long t0, t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    for (;;) {
+      unsigned long long v;
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + i) : "memory");
+      if (v >= value) break;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      if (t - t0 > timeout_ns) { if (err) atomicAdd(err, 1ull); break; }
+      __nanosleep(200);
+    }
+  }
+  __threadfence_system();
+}
+}  // namespace
+
+extern "C" int rthx_flag_signal(void* flag, uint64_t value, void* stream) {
+  if (!flag) return fail(nullptr, RTHX_ERR_ARG, "rthx_flag_signal: NULL flag");
+  flag_signal_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((unsigned long long*)flag, (unsigned long long)value);
+  CUG(cudaGetLastError());
+  return RTHX_OK;
+}
+
+extern "C" int rthx_flag_wait(const void* flags, int n, uint64_t value, double timeout_s, void* err_flag, void* stream) {
+  if (!flags || n < 1) return fail(nullptr, RTHX_ERR_ARG, "rthx_flag_wait: bad argument");
+  const unsigned long long ns = (unsigned long long)((timeout_s > 0 ? timeout_s : 30.0) * 1e9);
+  flag_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((const unsigned long long*)flags, n, (unsigned long long)value, ns, (unsigned long long*)err_flag);
+  CUG(cudaGetLastError());
+  return RTHX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // sparse read-out of the resident counts
 // ---------------------------------------------------------------------------------------------------------------
 namespace rthx {
-cudaError_t launch_row_nnz(const unsigned long long* c, int n, size_t ld, int* nnz, unsigned long long* rowsum, cudaStream_t st);
+cudaError_t launch_row_nnz(const unsigned long long* c, int n, size_t ld, int n_surf, int* nnz, unsigned long long* rowsum, unsigned long long* cross,
+                           cudaStream_t st);
 cudaError_t launch_row_fill(const unsigned long long* c, int n, size_t ld, const long long* row_ptr, const unsigned long long* rowsum, int* cols,
                             unsigned long long* vals, double* fvals, cudaStream_t st);
+cudaError_t launch_csc_count(const unsigned long long* c, int n, size_t ld, int* partial, long long* colptr, cudaStream_t st);
+cudaError_t launch_csc_fill(const unsigned long long* c, int n, size_t ld, const int* partial, const long long* colptr, const unsigned long long* rowsum,
+                            int index_base, void* rowval, bool rowval_i64, unsigned long long* vals, double* fvals, cudaStream_t st);
+cudaError_t launch_add_base(long long* p, int n, long long base, cudaStream_t st);
 }  // namespace rthx
 
-extern "C" int rthx_counts_nnz(rthx_handle* h, int bin, int64_t* nnz_out) {
-  if (!h || !nnz_out) return RTHX_ERR_ARG;
-  if (bin < 0 || bin >= h->last_trace_bins || !h->counts_dev) return fail(h, RTHX_ERR_ARG, "counts_nnz: no resident counts for that bin (run rthx_trace_exchange on all emitters first)");
+namespace {
+
+// Device -> host copy of a result array on `stream`, blocking.  Page-locked destinations (cudaHostAlloc / cudaHostRegister,
+// rthx_host_alloc) are written by DMA directly; pageable ones (a plain Julia / numpy array) go through the handle's two pinned
+// staging buffers in 32 MB pieces, the host moving piece k-1 while piece k is in flight.
+int copy_out(rthx_handle* h, void* dst, const void* src_dev, size_t bytes, cudaStream_t stream) {
+  if (bytes == 0) return RTHX_OK;
+  cudaPointerAttributes pa;
+  bool pinned = cudaPointerGetAttributes(&pa, dst) == cudaSuccess && (pa.type == cudaMemoryTypeHost || pa.type == cudaMemoryTypeManaged);
+  cudaGetLastError();
+  if (pinned || bytes <= (size_t(1) << 20)) {
+    CU(h, cudaMemcpyAsync(dst, src_dev, bytes, cudaMemcpyDeviceToHost, stream));
+    CU(h, cudaStreamSynchronize(stream));
+    return RTHX_OK;
+  }
+  const size_t piece = size_t(32) << 20;
+  if (h->stage_cap < piece) {
+    for (auto& sp : h->stage) { if (sp) cudaFreeHost(sp); sp = nullptr; }
+    h->stage_cap = 0;
+    for (auto& sp : h->stage) CU(h, cudaMallocHost(&sp, piece));
+    h->stage_cap = piece;
+  }
+  const size_t n_pieces = (bytes + piece - 1) / piece;
+  for (size_t k = 0; k < n_pieces; ++k) {
+    const size_t off = k * piece, len = std::min(piece, bytes - off);
+    CU(h, cudaMemcpyAsync(h->stage[k & 1], (const char*)src_dev + off, len, cudaMemcpyDeviceToHost, stream));
+    CU(h, cudaEventRecord(h->cev[k & 1], stream));
+    if (k >= 1) {
+      CU(h, cudaEventSynchronize(h->cev[(k - 1) & 1]));
+      parallel_memcpy((char*)dst + (k - 1) * piece, h->stage[(k - 1) & 1], piece);
+    }
+  }
+  CU(h, cudaEventSynchronize(h->cev[(n_pieces - 1) & 1]));
+  parallel_memcpy((char*)dst + (n_pieces - 1) * piece, h->stage[(n_pieces - 1) & 1], bytes - (n_pieces - 1) * piece);
+  return RTHX_OK;
+}
+
+// Row pass over the resident counts of `bin`: non-zeros and total per row, row pointers on the device, and the surface-gas
+// cross-coupling chi of the row-normalised F (cross_coupling_chi, smoothExchangeFactors.jl:212-241).
+int prepare_rows(rthx_handle* h, int bin) {
+  if (bin < 0 || bin >= h->last_trace_bins || !h->counts_dev)
+    return fail(h, RTHX_ERR_ARG, "counts: no resident counts for that bin (run rthx_trace_exchange on all emitters with counts_out == NULL, or rthx_trace_exchange_multi with counts_out == NULL, first)");
+  if (h->csr_bin == bin) return RTHX_OK;
   CU(h, cudaSetDevice(h->device));
   const int N = h->N;
   if (h->csr_cap < (size_t)N + 1) {
-    cudaFree(h->csr_nnz); cudaFree(h->csr_rowsum); cudaFree(h->csr_rowptr);
-    h->csr_nnz = nullptr; h->csr_rowsum = nullptr; h->csr_rowptr = nullptr; h->csr_cap = 0;
+    cudaFree(h->csr_nnz); cudaFree(h->csr_rowsum); cudaFree(h->csr_rowptr); cudaFree(h->csr_cross);
+    h->csr_nnz = nullptr; h->csr_rowsum = nullptr; h->csr_rowptr = nullptr; h->csr_cross = nullptr; h->csr_cap = 0;
     CU(h, cudaMalloc(&h->csr_nnz, sizeof(int) * ((size_t)N + 1)));
     CU(h, cudaMalloc(&h->csr_rowsum, sizeof(unsigned long long) * ((size_t)N + 1)));
+    CU(h, cudaMalloc(&h->csr_cross, sizeof(unsigned long long) * ((size_t)N + 1)));
     CU(h, cudaMalloc(&h->csr_rowptr, sizeof(long long) * ((size_t)N + 1)));
     h->csr_cap = (size_t)N + 1;
   }
   const unsigned long long* c = h->counts_dev + (size_t)bin * h->last_trace_rows * N;
-  CU(h, rthx::launch_row_nnz(c, N, (size_t)N, h->csr_nnz, h->csr_rowsum, h->stream));
+  CU(h, rthx::launch_row_nnz(c, N, (size_t)N, h->ns, h->csr_nnz, h->csr_rowsum, h->csr_cross, h->stream));
   std::vector<int> nnz(N);
+  std::vector<unsigned long long> rowsum(N), cross(N);
   CU(h, cudaMemcpyAsync(nnz.data(), h->csr_nnz, sizeof(int) * N, cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaMemcpyAsync(rowsum.data(), h->csr_rowsum, sizeof(unsigned long long) * N, cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaMemcpyAsync(cross.data(), h->csr_cross, sizeof(unsigned long long) * N, cudaMemcpyDeviceToHost, h->stream));
   CU(h, cudaStreamSynchronize(h->stream));
   std::vector<long long> rp((size_t)N + 1, 0);
-  for (int i = 0; i < N; ++i) rp[i + 1] = rp[i] + nnz[i];
+  double chi = 0.0;
+  for (int i = 0; i < N; ++i) {
+    rp[i + 1] = rp[i] + nnz[i];
+    if (rowsum[i]) chi += (double)cross[i] / (double)rowsum[i];
+  }
   CU(h, cudaMemcpyAsync(h->csr_rowptr, rp.data(), sizeof(long long) * ((size_t)N + 1), cudaMemcpyHostToDevice, h->stream));
   CU(h, cudaStreamSynchronize(h->stream));
-  h->csr_bin = bin; h->csr_total = rp[N];
-  *nnz_out = rp[N];
+  h->csr_bin = bin; h->csr_total = rp[N]; h->csr_chi = N ? chi / N : 0.0;
+  return RTHX_OK;
+}
+
+}  // namespace
+
+extern "C" int rthx_counts_nnz(rthx_handle* h, int bin, int64_t* nnz_out) {
+  if (!h || !nnz_out) return RTHX_ERR_ARG;
+  const int rc = prepare_rows(h, bin);
+  if (rc) return rc;
+  *nnz_out = h->csr_total;
+  return RTHX_OK;
+}
+
+extern "C" int rthx_counts_stats(rthx_handle* h, int bin, int64_t* nnz_out, double* chi_out) {
+  if (!h) return RTHX_ERR_ARG;
+  const int rc = prepare_rows(h, bin);
+  if (rc) return rc;
+  if (nnz_out) *nnz_out = h->csr_total;
+  if (chi_out) *chi_out = h->csr_chi;
   return RTHX_OK;
 }
 
 extern "C" int rthx_counts_csr(rthx_handle* h, int bin, int64_t* row_ptr, int32_t* cols, uint64_t* vals, double* F_vals) {
   if (!h || !row_ptr || !cols) return RTHX_ERR_ARG;
-  if (h->csr_bin != bin) { int64_t dummy; int rc = rthx_counts_nnz(h, bin, &dummy); if (rc) return rc; }
+  int rc = prepare_rows(h, bin);
+  if (rc) return rc;
   CU(h, cudaSetDevice(h->device));
   const int N = h->N;
   const size_t nnz = (size_t)h->csr_total;
@@ -1250,13 +1709,49 @@ extern "C" int rthx_counts_csr(rthx_handle* h, int bin, int64_t* row_ptr, int32_
   int* d_cols = (int*)(d_f + std::max<size_t>(1, nnz));
   const unsigned long long* c = h->counts_dev + (size_t)bin * h->last_trace_rows * N;
   CU(h, rthx::launch_row_fill(c, N, (size_t)N, h->csr_rowptr, h->csr_rowsum, d_cols, d_vals, F_vals ? d_f : nullptr, h->stream));
-  CU(h, cudaMemcpyAsync(row_ptr, h->csr_rowptr, sizeof(long long) * ((size_t)N + 1), cudaMemcpyDeviceToHost, h->stream));
+  rc = copy_out(h, row_ptr, h->csr_rowptr, sizeof(long long) * ((size_t)N + 1), h->stream);
+  if (rc) return rc;
   if (nnz) {
-    CU(h, cudaMemcpyAsync(cols, d_cols, sizeof(int) * nnz, cudaMemcpyDeviceToHost, h->stream));
-    if (vals) CU(h, cudaMemcpyAsync(vals, d_vals, sizeof(unsigned long long) * nnz, cudaMemcpyDeviceToHost, h->stream));
-    if (F_vals) CU(h, cudaMemcpyAsync(F_vals, d_f, sizeof(double) * nnz, cudaMemcpyDeviceToHost, h->stream));
+    if ((rc = copy_out(h, cols, d_cols, sizeof(int) * nnz, h->stream))) return rc;
+    if (vals && (rc = copy_out(h, vals, d_vals, sizeof(unsigned long long) * nnz, h->stream))) return rc;
+    if (F_vals && (rc = copy_out(h, F_vals, d_f, sizeof(double) * nnz, h->stream))) return rc;
   }
   CU(h, cudaStreamSynchronize(h->stream));
+  return RTHX_OK;
+}
+
+extern "C" int rthx_counts_csc(rthx_handle* h, int bin, int index_base, int rowval_is_i64, int64_t* colptr, void* rowval, uint64_t* vals, double* F_vals) {
+  if (!h || !colptr || !rowval || (index_base != 0 && index_base != 1)) return RTHX_ERR_ARG;
+  int rc = prepare_rows(h, bin);              // row totals for the normalisation, nnz for the buffer sizes
+  if (rc) return rc;
+  CU(h, cudaSetDevice(h->device));
+  const int N = h->N;
+  const size_t nnz = (size_t)h->csr_total, nz1 = std::max<size_t>(1, nnz);
+  if (!rowval_is_i64 && (size_t)N + (size_t)index_base > 0x7FFFFFFFull) return fail(h, RTHX_ERR_ARG, "counts_csc: 32-bit row indices overflow");
+  const int n_tiles = (N + 63) / 64;
+  CU(h, ensure(&h->csc_partial, &h->csc_partial_cap, (size_t)n_tiles * (size_t)N));
+  CU(h, ensure(&h->csc_colptr, &h->csc_colptr_cap, (size_t)N + 1));
+  const size_t need = nz1 * (sizeof(long long) + (vals ? sizeof(unsigned long long) : 0) + (F_vals ? sizeof(double) : 0));
+  if (h->csr_out_cap < need) {
+    cudaFree(h->csr_out); h->csr_out = nullptr; h->csr_out_cap = 0;
+    CU(h, cudaMalloc(&h->csr_out, need));
+    h->csr_out_cap = need;
+  }
+  long long* d_rows = (long long*)h->csr_out;                 // 8 bytes per entry reserved, holds int or long long indices
+  unsigned long long* d_vals = vals ? (unsigned long long*)(d_rows + nz1) : nullptr;
+  double* d_f = F_vals ? (double*)(d_rows + nz1 + (vals ? nz1 : 0)) : nullptr;
+  const unsigned long long* c = h->counts_dev + (size_t)bin * h->last_trace_rows * N;
+  CU(h, rthx::launch_csc_count(c, N, (size_t)N, h->csc_partial, h->csc_colptr, h->stream));
+  CU(h, rthx::launch_csc_fill(c, N, (size_t)N, h->csc_partial, h->csc_colptr, h->csr_rowsum, index_base, d_rows, rowval_is_i64 != 0, d_vals, d_f, h->stream));
+  if (index_base) CU(h, rthx::launch_add_base(h->csc_colptr, N + 1, (long long)index_base, h->stream));
+  if ((rc = copy_out(h, colptr, h->csc_colptr, sizeof(long long) * ((size_t)N + 1), h->stream))) return rc;
+  if (nnz) {
+    if ((rc = copy_out(h, rowval, d_rows, (rowval_is_i64 ? sizeof(long long) : sizeof(int)) * nnz, h->stream))) return rc;
+    if (vals && (rc = copy_out(h, vals, d_vals, sizeof(unsigned long long) * nnz, h->stream))) return rc;
+    if (F_vals && (rc = copy_out(h, F_vals, d_f, sizeof(double) * nnz, h->stream))) return rc;
+  }
+  CU(h, cudaStreamSynchronize(h->stream));
+  h->csc_bin = bin;
   return RTHX_OK;
 }
 
@@ -1264,7 +1759,7 @@ extern "C" int rthx_counts_csr(rthx_handle* h, int bin, int64_t* row_ptr, int32_
 // reciprocity smoothing on the device
 // ---------------------------------------------------------------------------------------------------------------
 namespace rthx {
-struct SmoothResult { int iters; double delta, delta_init; double ms_total, ms_per_iter; int launches; };
+struct SmoothResult { int iters; double delta, delta_init; double ms_total, ms_per_iter; int launches; int converged; };
 cudaError_t run_ap(const unsigned long long* src_counts, const double* src_F, const double* src_rs, size_t ld, const double* w_dev, int n, size_t ldx,
                    int max_iters, double target, double* X, double* rs, double* r, double* u, double* part, std::vector<double>& part_host, cudaStream_t st,
                    cudaEvent_t e0, cudaEvent_t e1, SmoothResult* out);
@@ -1344,6 +1839,7 @@ extern "C" int rthx_smooth_DkAP(rthx_handle* h, int source, const void* src_host
     st->pass_gbs = pass_ms > 0 ? 16.0 * (double)nn / (pass_ms * 1e-3) / 1e9 : 0.0;
     st->dykstra_rounds = dres.rounds; st->pcg_iterations = dres.pcg_iters; st->dykstra_delta = dres.rounds ? dres.delta : 0.0; st->dykstra_ms = dres.ms;
     st->launches += dres.launches;
+    st->converged = res.converged; st->pad_ = 0;
   }
   return RTHX_OK;
 }

@@ -1049,6 +1049,8 @@ struct QueueBlock {          // block-uniform state of one (emitter row, band, c
   uint32_t* hist;
   double* q;                 // this warp's queue, structure of arrays: px | py | dx | dy | S (or -log R), 32*DEPTH doubles each
   const double* beta_band;
+  const double* omega_band;  // MULTI_BOUNCE: scattering albedo per cell of the band
+  const double* eps_band;    // MULTI_BOUNCE: emissivity per surface of the band
   double inv_beta_u;
   int64_t r_begin, r_end;    // ray range of the block
   size_t rec_row;            // first recorder slot of the emitter row
@@ -1129,7 +1131,13 @@ __device__ __forceinline__ int lattice_cell(const CoarseDev& cf, double px, doub
   return (((unsigned)n < (unsigned)cf.Nx) & ((unsigned)m < (unsigned)cf.Ny)) ? n + m * cf.Nx : -1;
 }
 
-template <bool SURF, bool UNIFORM, bool REC, int DEPTH, bool BILIN>
+// MULTI (RTHX_MULTI_BOUNCE[_SPECULAR], the analogue of method=:direct's traceSingleRay.jl:24-79 without re-emission): a ray whose
+// first interaction is found is not retired but absorbed, scattered (isotropicScatter2D.jl:1-4) or reflected (diffuse:
+// sampleReflectionDirection2D.jl:5-16 + lambertSample2D; specular: mirror) right in its lane — two more Philox calls per event,
+// call# 2+2n / 3+2n exactly as in trace_exchange_kernel<..., MULTI> — and keeps its lane until it is absorbed.  Lanes whose ray
+// ended refill from the queue as before, so the warp no longer waits for its longest event chain (the lock-step loop of
+// sq_multi_loop ran at 15.5 of 32 lanes on cfg3, omega = 0.5).
+template <bool SURF, bool UNIFORM, bool REC, int DEPTH, bool BILIN, bool MULTI>
 __device__ __forceinline__ unsigned int queue_ray_loop(const TraceParams& p, const QueueBlock& b) {
   constexpr int WQ = 32 * DEPTH;                       // queue slots per warp
   const int lane = b.lane;
@@ -1140,7 +1148,8 @@ __device__ __forceinline__ unsigned int queue_ray_loop(const TraceParams& p, con
   bool active = false;
   double px = 0.0, py = 0.0, dx = 0.0, dy = 0.0, S = 0.0, acc = 0.0;   // S: remaining free path (UNIFORM) or -log R
   int c = b.c0, it = 0;
-  uint32_t r_cur = 0;                                  // ray index of the in-flight ray relative to r_begin (recorder slot)
+  int event = 0;                                       // MULTI: interactions this ray has survived
+  uint32_t r_cur = 0;                                  // ray index of the in-flight ray relative to r_begin (recorder slot, Philox counter)
   // the warp's rays: batch j of the block covers [r_begin + j*n_warps*WQ, ...), this warp takes its WQ-slice of every batch
   int64_t rb = b.r_begin + (int64_t)b.warp * WQ;
   const int64_t stride = (int64_t)b.n_warps * WQ;
@@ -1175,6 +1184,7 @@ __device__ __forceinline__ unsigned int queue_ray_loop(const TraceParams& p, con
       if (!active & (idx < n_valid)) {
         px = q[idx]; py = q[WQ + idx]; dx = q[2 * WQ + idx]; dy = q[3 * WQ + idx]; S = q[4 * WQ + idx];
         acc = 0.0; c = b.c0; it = 0; r_cur = rb_rel + (uint32_t)idx;
+        if (MULTI) event = 0;
         active = true;
       }
       next += __popc(need);
@@ -1219,22 +1229,71 @@ __device__ __forceinline__ unsigned int queue_ray_loop(const TraceParams& p, con
         // (rthx_api.cu builds the table from the lattice -> fine map, the fine cells' vertex counts and cell_surf_id)
 #define RTHX_QUEUE_FINISH()                                                                                         \
   do {                                                                                                              \
-    active = false;                                                                                                 \
     int absorber = -1;                                                                                              \
     if (tallied) {                                                                                                  \
       const int l = lattice_cell<BILIN>(cf, px, py);                                                                \
       if (l >= 0) absorber = __ldg(p.abs_tab + (size_t)(cf.abs_off + l) * 5 + (gas ? 0 : 1 + k));                   \
     }                                                                                                               \
-    if (absorber >= 0) {                                                                                            \
-      atomicAdd(&b.hist[absorber], 1u);                                                                             \
-      if (REC) {                                                                                                    \
-        const size_t sl = b.rec_row + (size_t)(b.r_begin + (int64_t)r_cur);                                         \
-        double* o = p.rec_pts + 4 * sl;                                                                             \
-        o[2] = px; o[3] = py;                                                                                       \
-        p.rec_valid[sl] = 1;                                                                                        \
+    bool retire = true;                                                                                             \
+    if (MULTI && absorber >= 0) {                                                                                   \
+      /* absorb, scatter or reflect (traceSingleRay.jl:24-79): v0.x decision, v0.y azimuth / psi, v0.z cos-theta (walls), */ \
+      /* v0.w roulette, (v1.x,v1.y) polar angle (gas), (v1.z,v1.w) next free path */                               \
+      if (event >= 16000) {                                          /* call# is a 16-bit field */                  \
+        absorber = -1;                                                                                              \
+      } else {                                                                                                      \
+        const uint64_t ray_id = (uint64_t)(p.ray_id_offset + b.r_begin + (int64_t)r_cur);                           \
+        const uint32_t c_lo = (uint32_t)ray_id, c_hi = (uint32_t)(ray_id >> 32);                                    \
+        const uint4 v0 = philox4x32_10_rk(make_uint4(c_lo, c_hi, b.e, b.cw | (uint32_t)(2 + 2 * event)), p.rk);     \
+        const uint4 v1 = philox4x32_10_rk(make_uint4(c_lo, c_hi, b.e, b.cw | (uint32_t)(3 + 2 * event)), p.rk);     \
+        if (event >= 1000 && u32d(v0.w, p.k_u32) > 0.8) {             /* Russian roulette, traceSingleRay.jl:11 */  \
+          absorber = -1;                                                                                            \
+        } else {                                                                                                    \
+          const double dec = u32d(v0.x, p.k_u32);                                                                   \
+          if (absorber >= p.n_surfaces) {                                                                           \
+            if (dec < b.omega_band[absorber - p.n_surfaces]) {        /* scattered: theta = acos(2R - 1), phi = 2 pi R */ \
+              const double cc = __hiloint2double((int)(0x3FF00000u | (v1.y >> 12)), (int)((v1.y << 20) | (v1.x >> 12))) - p.k_u52c; \
+              dx = sqrt_pos(fma(-cc, cc, 0.25)) * cos2pi_centered_x2(u32d_centered(v0.y, p.k_u32c));                \
+              dy = cc + cc;                                                                                         \
+              retire = false;                                                                                       \
+            }                                                                                                       \
+          } else if (!(dec < b.eps_band[absorber])) {                 /* reflected */                               \
+            const double hnx = cf.nx[k], hny = cf.ny[k];              /* outward normal of the coarse edge (= of every fine wall on it) */ \
+            if (p.specular) {                                                                                       \
+              const double dn = dx * hnx + dy * hny;                                                                \
+              dx = fma(-2.0 * dn, hnx, dx);                                                                         \
+              dy = fma(-2.0 * dn, hny, dy);                                                                         \
+            } else {                                                                                                \
+              const float cosT = __fsqrt_rn(u23(v0.z));                                                             \
+              const float cos2 = __fmul_rn(cosT, cosT);                                                             \
+              const double xdir = sqrt_pos(1.0 - (double)cos2) * cos2pi_centered((double)u23(v0.y) - 0.5);          \
+              const double zdir = (double)cosT;                                                                     \
+              const double nxi = -hnx, nyi = -hny;                                                                  \
+              dx = nyi * xdir + nxi * zdir;                                                                         \
+              dy = -nxi * xdir + nyi * zdir;                                                                        \
+            }                                                                                                       \
+            retire = false;                                                                                         \
+          }                                                                                                         \
+          if (!retire) {                                              /* traced on from the interaction point, same coarse face */ \
+            const double nl = neg_log_table(u52(v1.z, v1.w, p.k_u52), b.s_log);                                     \
+            S = UNIFORM ? nl * b.inv_beta_u : nl;                                                                   \
+            acc = 0.0; it = 0; ++event;                                                                             \
+          }                                                                                                         \
+        }                                                                                                           \
       }                                                                                                             \
-    } else {                                                                                                        \
-      ++n_lost;                                                                                                     \
+    }                                                                                                               \
+    if (retire) {                                                                                                   \
+      active = false;                                                                                               \
+      if (absorber >= 0) {                                                                                          \
+        atomicAdd(&b.hist[absorber], 1u);                                                                           \
+        if (REC) {                                                                                                  \
+          const size_t sl = b.rec_row + (size_t)(b.r_begin + (int64_t)r_cur);                                       \
+          double* o = p.rec_pts + 4 * sl;                                                                           \
+          o[2] = px; o[3] = py;                                                                                     \
+          p.rec_valid[sl] = 1;                                                                                      \
+        }                                                                                                           \
+      } else {                                                                                                      \
+        ++n_lost;                                                                                                   \
+      }                                                                                                             \
     }                                                                                                               \
   } while (0)
         if (!BILIN) {
@@ -1266,15 +1325,15 @@ __device__ __forceinline__ unsigned int queue_ray_loop(const TraceParams& p, con
   return n_lost;
 }
 
-template <bool SURF, int DEPTH, bool BILIN>
+template <bool SURF, int DEPTH, bool BILIN, bool MULTI>
 __device__ __forceinline__ unsigned int queue_dispatch(const TraceParams& p, const QueueBlock& b, bool uniform, bool rec) {
-  if (uniform) return rec ? queue_ray_loop<SURF, true, true, DEPTH, BILIN>(p, b) : queue_ray_loop<SURF, true, false, DEPTH, BILIN>(p, b);
-  return rec ? queue_ray_loop<SURF, false, true, DEPTH, BILIN>(p, b) : queue_ray_loop<SURF, false, false, DEPTH, BILIN>(p, b);
+  if (uniform) return rec ? queue_ray_loop<SURF, true, true, DEPTH, BILIN, MULTI>(p, b) : queue_ray_loop<SURF, true, false, DEPTH, BILIN, MULTI>(p, b);
+  return rec ? queue_ray_loop<SURF, false, true, DEPTH, BILIN, MULTI>(p, b) : queue_ray_loop<SURF, false, false, DEPTH, BILIN, MULTI>(p, b);
 }
 
 // BILIN: the mesh has general convex quadrilateral faces (bilinear lattices); compiled separately so that meshes of parallelograms
 // and triangles keep the shorter traversal loop
-template <int MINB, int DEPTH, bool BILIN>
+template <int MINB, int DEPTH, bool BILIN, bool MULTI>
 __global__ void __launch_bounds__(256, MINB) trace_exchange_queue_kernel(const __grid_constant__ TraceParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const size_t coarse_bytes = sizeof(CoarseDev) * (size_t)p.n_coarse;
@@ -1327,6 +1386,7 @@ __global__ void __launch_bounds__(256, MINB) trace_exchange_queue_kernel(const _
   b.s_em = s_em; b.s_log = s_log; b.hist = hist;
   b.q = queue + (size_t)warp * 5 * WQ;
   b.beta_band = beta_band;
+  b.omega_band = p.omega + (size_t)band * p.n_cells; b.eps_band = p.eps + (size_t)band * p.n_surfaces;
   b.inv_beta_u = beta_u > 0.0 ? 1.0 / beta_u : CUDART_INF;
   b.r_begin = r_begin; b.r_end = r_end;
   b.rec_row = rec_slot >= 0 ? (size_t)rec_slot * (size_t)p.rays_per_emitter : 0;
@@ -1334,7 +1394,7 @@ __global__ void __launch_bounds__(256, MINB) trace_exchange_queue_kernel(const _
   b.sel_thr = reinterpret_cast<const uint32_t*>(s_em + 15)[0];
   b.c0 = p.em_coarse[e]; b.n_warps = n_warps; b.warp = warp; b.lane = lane;
 
-  const unsigned int n_lost0 = is_surface ? queue_dispatch<true, DEPTH, BILIN>(p, b, uniform, rec_slot >= 0) : queue_dispatch<false, DEPTH, BILIN>(p, b, uniform, rec_slot >= 0);
+  const unsigned int n_lost0 = is_surface ? queue_dispatch<true, DEPTH, BILIN, MULTI>(p, b, uniform, rec_slot >= 0) : queue_dispatch<false, DEPTH, BILIN, MULTI>(p, b, uniform, rec_slot >= 0);
   unsigned int n_lost = n_lost0;
 
   // ---- flush --------------------------------------------------------------------------------------------------
@@ -1361,12 +1421,16 @@ static TraceKernel kernel_variant(bool hist, bool fast, int minb, bool multi, bo
     if (minb == 3) return (TraceKernel)trace_exchange_kernel<true, true, 4, false, true>;   // RTHX_MINB=3: the shared-loop form (A/B knob)
     return (TraceKernel)trace_exchange_sq_kernel<4, false>;
   }
-  if (minb == 6 && hist && fast && !multi && !sq) {                                                     // per-warp ray queue (multi-face meshes)
+  if (minb == 6 && hist && fast && !sq) {                                                               // per-warp ray queue (multi-face meshes; MULTI_BOUNCE on any analytic mesh)
     const bool bilin = queue_depth >= 8;                                                                // depth + 8: bilinear faces present
     const int d = queue_depth & 7;
-    if (d >= 4) return bilin ? (TraceKernel)trace_exchange_queue_kernel<4, 4, true> : (TraceKernel)trace_exchange_queue_kernel<4, 4, false>;
-    if (d >= 2) return bilin ? (TraceKernel)trace_exchange_queue_kernel<4, 2, true> : (TraceKernel)trace_exchange_queue_kernel<4, 2, false>;
-    return bilin ? (TraceKernel)trace_exchange_queue_kernel<4, 1, true> : (TraceKernel)trace_exchange_queue_kernel<4, 1, false>;
+    if (multi) {                                                                                        // compiled depths: 1, 2
+      if (d >= 2) return bilin ? (TraceKernel)trace_exchange_queue_kernel<3, 2, true, true> : (TraceKernel)trace_exchange_queue_kernel<3, 2, false, true>;
+      return bilin ? (TraceKernel)trace_exchange_queue_kernel<3, 1, true, true> : (TraceKernel)trace_exchange_queue_kernel<3, 1, false, true>;
+    }
+    if (d >= 4) return bilin ? (TraceKernel)trace_exchange_queue_kernel<4, 4, true, false> : (TraceKernel)trace_exchange_queue_kernel<4, 4, false, false>;
+    if (d >= 2) return bilin ? (TraceKernel)trace_exchange_queue_kernel<4, 2, true, false> : (TraceKernel)trace_exchange_queue_kernel<4, 2, false, false>;
+    return bilin ? (TraceKernel)trace_exchange_queue_kernel<4, 1, true, false> : (TraceKernel)trace_exchange_queue_kernel<4, 1, false, false>;
   }
   if (multi) {
     if (hist) return fast ? (TraceKernel)trace_exchange_kernel<true, true, 2, true, false> : (TraceKernel)trace_exchange_kernel<true, false, 2, true, false>;

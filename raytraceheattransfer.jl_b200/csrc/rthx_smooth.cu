@@ -152,16 +152,24 @@ __global__ void __launch_bounds__(ROW_THREADS) recover_kernel(double* __restrict
 // ---------------------------------------------------------------------------------------------------------------
 // sparse (CSR) view of a count matrix: feeds sparse(I, J, V) without moving the zeros
 // ---------------------------------------------------------------------------------------------------------------
-// one warp per row: number of non-zero tallies and the row total
-__global__ void __launch_bounds__(256) row_nnz_kernel(const unsigned long long* __restrict__ c, int n, size_t ld, int* __restrict__ nnz,
-                                                      unsigned long long* __restrict__ rowsum) {
+// one warp per row: number of non-zero tallies, the row total and — for cross_coupling_chi (smoothExchangeFactors.jl:212-241) —
+// the tallies that couple a surface with a gas cell (exactly one of row / column index below n_surf)
+__global__ void __launch_bounds__(256) row_nnz_kernel(const unsigned long long* __restrict__ c, int n, size_t ld, int n_surf, int* __restrict__ nnz,
+                                                      unsigned long long* __restrict__ rowsum, unsigned long long* __restrict__ cross) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= n) return;
   int cnt = 0;
-  unsigned long long s = 0;
-  for (int j = lane; j < n; j += 32) { const unsigned long long v = c[(size_t)row * ld + j]; cnt += v != 0; s += v; }
-  for (int o = 16; o > 0; o >>= 1) { cnt += __shfl_down_sync(0xffffffffu, cnt, o); s += __shfl_down_sync(0xffffffffu, s, o); }
-  if (lane == 0) { nnz[row] = cnt; rowsum[row] = s; }
+  unsigned long long s = 0, x = 0;
+  const bool row_surf = row < n_surf;
+  for (int j = lane; j < n; j += 32) {
+    const unsigned long long v = c[(size_t)row * ld + j];
+    cnt += v != 0; s += v;
+    if ((j < n_surf) != row_surf) x += v;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    cnt += __shfl_down_sync(0xffffffffu, cnt, o); s += __shfl_down_sync(0xffffffffu, s, o); x += __shfl_down_sync(0xffffffffu, x, o);
+  }
+  if (lane == 0) { nnz[row] = cnt; rowsum[row] = s; if (cross) cross[row] = x; }
 }
 
 // one warp per row: write (column, count, count / rowsum) of the non-zeros in ascending column order at row_ptr[row]
@@ -186,8 +194,104 @@ __global__ void __launch_bounds__(256) row_fill_kernel(const unsigned long long*
   }
 }
 
-cudaError_t launch_row_nnz(const unsigned long long* c, int n, size_t ld, int* nnz, unsigned long long* rowsum, cudaStream_t st) {
-  row_nnz_kernel<<<(n + 7) / 8, 256, 0, st>>>(c, n, ld, nnz, rowsum);
+cudaError_t launch_row_nnz(const unsigned long long* c, int n, size_t ld, int n_surf, int* nnz, unsigned long long* rowsum, unsigned long long* cross,
+                           cudaStream_t st) {
+  row_nnz_kernel<<<(n + 7) / 8, 256, 0, st>>>(c, n, ld, n_surf, nnz, rowsum, cross);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// CSC view of a count matrix: what SparseMatrixCSC{Float64,Int} (Julia) / scipy.sparse.csc_matrix hold, emitted by the device so
+// that the host neither transposes a CSR matrix nor runs sparse(I, J, V) over ~1e8 triplets (parallelRayTracing.jl:144-154 takes
+// seconds there for cfg3).  Rows are cut into tiles of CSC_TILE; thread (tile, column) counts, then writes, its own run of the
+// column, so both passes read the row-major matrix coalesced (consecutive threads = consecutive columns) and every column comes
+// out in ascending row order.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int CSC_TILE = 64;
+
+__global__ void __launch_bounds__(256) col_nnz_partial_kernel(const unsigned long long* __restrict__ c, int n, size_t ld, int* __restrict__ partial) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x, t = blockIdx.y;
+  if (j >= n) return;
+  const int i0 = t * CSC_TILE, i1 = min(n, i0 + CSC_TILE);
+  int cnt = 0;
+  for (int i = i0; i < i1; ++i) cnt += c[(size_t)i * ld + j] != 0ull;
+  partial[(size_t)t * n + j] = cnt;
+}
+
+// per column: turn the tile counts into exclusive offsets within the column, and the column total
+__global__ void __launch_bounds__(256) col_offsets_kernel(int* __restrict__ partial, int n, int n_tiles, long long* __restrict__ coltotal) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  int s = 0;
+  for (int t = 0; t < n_tiles; ++t) { const int v = partial[(size_t)t * n + j]; partial[(size_t)t * n + j] = s; s += v; }
+  coltotal[j] = s;
+}
+
+// exclusive prefix sum of in[0..n) into out[0..n] (out[n] = total) by ONE block: every thread sums a contiguous segment, the
+// 1024 segment sums are scanned in shared memory, the segment is rewritten with its running prefix.  in and out may alias.
+__global__ void __launch_bounds__(1024) exclusive_scan_kernel(const long long* in, int n, long long* out) {
+  __shared__ long long seg[1024];
+  const int t = threadIdx.x;
+  const int per = (n + 1023) / 1024;
+  const int b = min(n, t * per), e = min(n, b + per);
+  long long s = 0;
+  for (int i = b; i < e; ++i) s += in[i];
+  seg[t] = s;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {
+    const long long v = t >= o ? seg[t - o] : 0;
+    __syncthreads();
+    seg[t] += v;
+    __syncthreads();
+  }
+  long long run = t ? seg[t - 1] : 0;
+  for (int i = b; i < e; ++i) { const long long v = in[i]; out[i] = run; run += v; }
+  if (t == 1023) out[n] = seg[1023];
+}
+
+template <class IDX>
+__global__ void __launch_bounds__(256) col_fill_kernel(const unsigned long long* __restrict__ c, int n, size_t ld, const int* __restrict__ partial,
+                                                       const long long* __restrict__ colptr, const unsigned long long* __restrict__ rowsum, int index_base,
+                                                       IDX* __restrict__ rowval, unsigned long long* __restrict__ vals, double* __restrict__ fvals) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x, t = blockIdx.y;
+  if (j >= n) return;
+  const int i0 = t * CSC_TILE, i1 = min(n, i0 + CSC_TILE);
+  long long k = colptr[j] + partial[(size_t)t * n + j];
+  for (int i = i0; i < i1; ++i) {
+    const unsigned long long v = c[(size_t)i * ld + j];
+    if (v) {
+      rowval[k] = (IDX)(i + index_base);
+      if (vals) vals[k] = v;
+      if (fvals) fvals[k] = (double)v / (double)rowsum[i];      // count / row total: parallelRayTracing.jl:144-146 + row_normalize! :161-169
+      ++k;
+    }
+  }
+}
+
+// column pointers of bin `c` (n x n, leading dimension ld) into colptr[0..n] (0-based, device); partial is [n_tiles][n] ints
+cudaError_t launch_csc_count(const unsigned long long* c, int n, size_t ld, int* partial, long long* colptr, cudaStream_t st) {
+  const int n_tiles = (n + CSC_TILE - 1) / CSC_TILE;
+  const dim3 grid((unsigned)((n + 255) / 256), (unsigned)n_tiles);
+  col_nnz_partial_kernel<<<grid, 256, 0, st>>>(c, n, ld, partial);
+  col_offsets_kernel<<<(n + 255) / 256, 256, 0, st>>>(partial, n, n_tiles, colptr);
+  exclusive_scan_kernel<<<1, 1024, 0, st>>>(colptr, n, colptr);
+  return cudaGetLastError();
+}
+cudaError_t launch_csc_fill(const unsigned long long* c, int n, size_t ld, const int* partial, const long long* colptr, const unsigned long long* rowsum,
+                            int index_base, void* rowval, bool rowval_i64, unsigned long long* vals, double* fvals, cudaStream_t st) {
+  const int n_tiles = (n + CSC_TILE - 1) / CSC_TILE;
+  const dim3 grid((unsigned)((n + 255) / 256), (unsigned)n_tiles);
+  if (rowval_i64) col_fill_kernel<long long><<<grid, 256, 0, st>>>(c, n, ld, partial, colptr, rowsum, index_base, (long long*)rowval, vals, fvals);
+  else col_fill_kernel<int><<<grid, 256, 0, st>>>(c, n, ld, partial, colptr, rowsum, index_base, (int*)rowval, vals, fvals);
+  return cudaGetLastError();
+}
+// colptr += base (1-based pointers for Julia), in place
+__global__ void add_base_kernel(long long* p, int n, long long base) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] += base;
+}
+cudaError_t launch_add_base(long long* p, int n, long long base, cudaStream_t st) {
+  add_base_kernel<<<(n + 255) / 256, 256, 0, st>>>(p, n, base);
   return cudaGetLastError();
 }
 cudaError_t launch_row_fill(const unsigned long long* c, int n, size_t ld, const long long* row_ptr, const unsigned long long* rowsum, int* cols,
@@ -196,7 +300,18 @@ cudaError_t launch_row_fill(const unsigned long long* c, int n, size_t ld, const
   return cudaGetLastError();
 }
 
-struct SmoothResult { int iters; double delta, delta_init; double ms_total, ms_per_iter; int launches; };
+struct SmoothResult { int iters; double delta, delta_init; double ms_total, ms_per_iter; int launches; int converged; };
+
+// non-zeros of the leading n x n block of a matrix (u64 counts or doubles): the density enters AP's floor-aware acceptance
+template <class T>
+__global__ void __launch_bounds__(256) nnz_count_kernel(const T* __restrict__ src, int n, size_t ld, unsigned long long* __restrict__ out) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= n) return;
+  unsigned int cnt = 0;
+  for (int j = lane; j < n; j += 32) cnt += src[(size_t)row * ld + j] != (T)0;
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, o);
+  if (lane == 0 && cnt) atomicAdd(out, (unsigned long long)cnt);
+}
 
 // Runs AP on the device.  `src_counts` (u64, leading dimension ld) or `src_F` (doubles; `src_rs` = its row sums when it
 // still has to be row-normalised, else nullptr) is a DEVICE pointer; X (n*ldx doubles) and the work vectors are device
@@ -230,11 +345,25 @@ cudaError_t run_ap(const unsigned long long* src_counts, const double* src_F, co
     *d = std::sqrt(s);
     return cudaSuccess;
   };
+  // floor-aware acceptance (smoothExchangeFactors.jl:558-560): guard = sqrt(N / nz_over_N) * target = target / sqrt(density)
+  double guard = target;
+  {
+    unsigned long long* nz_dev = reinterpret_cast<unsigned long long*>(part);   // part is free until the first delta check
+    if ((e = cudaMemsetAsync(nz_dev, 0, sizeof(unsigned long long), st)) != cudaSuccess) return e;
+    if (src_counts) nnz_count_kernel<unsigned long long><<<(n + 7) / 8, 256, 0, st>>>(src_counts, n, ld, nz_dev);
+    else nnz_count_kernel<double><<<(n + 7) / 8, 256, 0, st>>>(src_F, n, ld, nz_dev);
+    ++launches;
+    unsigned long long nz = 0;
+    if ((e = cudaMemcpyAsync(&nz, nz_dev, sizeof(nz), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
+    if (nz > 0) guard = target * std::sqrt((double)n * (double)n / (double)nz);
+  }
   double delta = 0;
   if ((e = delta_now(&delta)) != cudaSuccess) return e;
   const double delta_init = delta;
-  double best = delta;
-  int k = 0, k_next = 1, flat = 0;
+  double best = delta, delta_prev = delta, rho_est = 0.5;
+  int k = 0, k_next = 1, flat = 0, checks = 0, k_prev = 0;
+  bool floor_accepted = false;
   while (k < max_iters && delta > target) {
     scale_rows_kernel<<<n, ROW_THREADS, 0, st>>>(X, u, ldx, r);
     u_kernel<<<(unsigned)((ldx + 255) / 256), 256, 0, st>>>(w_dev, r, n, (int)ldx, u);
@@ -242,9 +371,16 @@ cudaError_t run_ap(const unsigned long long* src_counts, const double* src_F, co
     ++k;
     if (k >= k_next || k == max_iters) {
       if ((e = delta_now(&delta)) != cudaSuccess) return e;
-      flat = delta >= best * (1 - 1e-3) ? flat + 1 : 0;      // smoothExchangeFactors.jl:582: contraction exhausted
+      // the reference's stopping rule (smoothExchangeFactors.jl:578-590): contraction estimate and the flat count start with
+      // the third check; a stalled contraction is accepted only below the guard, otherwise the loop runs to max_iters
+      ++checks;
+      if (checks >= 3) {
+        rho_est = std::min(std::max(std::pow(delta / delta_prev, 1.0 / std::max(k - k_prev, 1)), 0.5), 0.9999);
+        flat = delta >= best * (1 - 1e-3) ? flat + 1 : 0;
+      }
       best = std::min(best, delta);
-      if (flat >= 3) break;
+      if (delta < guard && (rho_est > 0.99 || flat >= 3)) { floor_accepted = true; break; }
+      k_prev = k; delta_prev = delta;
       k_next = k + std::min(32, std::max(1, k));             // 1,2,4,...,32 then every 32 iterations
     }
   }
@@ -256,6 +392,7 @@ cudaError_t run_ap(const unsigned long long* src_counts, const double* src_F, co
   cudaEventElapsedTime(&ms, e0, e1);
   out->iters = k; out->delta = delta; out->delta_init = delta_init; out->ms_total = ms;
   out->ms_per_iter = k > 0 ? ms / k : 0.0; out->launches = launches;
+  out->converged = (delta <= target || floor_accepted) ? 1 : 0;     // else the reference warns "AP reached max_iters" (:605-607)
   return cudaGetLastError();
 }
 

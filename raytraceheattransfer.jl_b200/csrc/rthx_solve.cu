@@ -246,10 +246,11 @@ cudaError_t run_gmres(const SolveMatrix& A, int n, size_t nl, int m, int max_ite
   double beta = std::sqrt(nrm2);
   const double rhs_norm = beta;
   const double eps = atol + rtol * beta;                      // Krylov.jl: ε = atol + rtol * ‖r0‖
-  int iters = 0, restarts = 0;
+  int iters = 0, restarts = 0, stalled = 0;
   bool converged = beta <= eps;
   double res = beta;
   while (!converged && iters < max_iters) {
+    const double beta_cycle = beta;
     // v_0 = r / beta
     normalise_kernel<<<vb, 256, 0, st>>>(r, n, d + m + 1, V); ++launches;
     std::fill(g.begin(), g.end(), 0.0);
@@ -310,6 +311,10 @@ cudaError_t run_gmres(const SolveMatrix& A, int n, size_t nl, int m, int max_ite
     res = beta;
     if (beta <= eps) { converged = true; break; }
     if (iters >= max_iters) break;
+    // a purely relative target (atol = 0) can sit below the rounding floor of the products: two restart cycles in a row that
+    // no longer reduce the true residual end the solve as "not converged" instead of spinning to max_iters
+    stalled = beta > 0.9 * beta_cycle ? stalled + 1 : 0;
+    if (stalled >= 2) break;
     ++restarts;
     // Rounding can leave the recurrence residual below eps while the true one sits a hair above it; one more
     // cycle from the true residual settles that, so no special case is needed here.

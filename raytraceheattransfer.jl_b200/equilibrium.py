@@ -9,8 +9,8 @@
 Everything that is O(N) — the workspace, the boundary-condition vectors, the temperature recovery, the write-back —
 stays on the host exactly as in the reference.  The O(N^2)-per-iteration part, `j = M \\ h` with
 `M = I - Diagonal(coeff) * F'` and the incident power `g = F' j`, runs on the device through `rthx_solve_grey`
-(restarted GMRES(50), rtol 1e-12, as the reference's sparse branch :152-155; its dense `\\` branch :157 gives the same
-answer to that residual).  When `F` is the matrix the device-side smoothing of the last `mesh(...)` call left resident,
+(restarted GMRES(50), rtol 1e-12, as the reference's sparse branch :152-155 with Krylov.jl's atol = sqrt(eps); for a dense
+F — solved exactly by `\\` at :157 — the stop is purely relative, atol = 0, so j agrees with the direct solve to ~1e-12 |h|).  When `F` is the matrix the device-side smoothing of the last `mesh(...)` call left resident,
 it is read where it lies — no 900 MB host round trip for cfg3.  There is no CPU fallback: without the CUDA library or a
 B200 the call raises `RthxError`.
 """
@@ -113,10 +113,12 @@ def equilibriumGrey2D(rtm, F, spectral_bin: int = 1, device: int = 0, verbose: b
     say("Solving linear system...")
     tr = _device_for(rtm, device)
     resident = getattr(tr, "_resident_F", None)
+    # A dense F is solved exactly by the reference (`M \\ h`, :157): no absolute tolerance, the residual target is purely
+    # relative (1e-12 |h|).  Only the sparse branch inherits Krylov.jl's atol = sqrt(eps) (gmres!, :152-155).
     if resident is not None and resident[0] is F and _same_sample(F, resident[1]):
-        j, g, st = tr.solve_grey(coeff, h)                         # F_smooth is still on the device
+        j, g, st = tr.solve_grey(coeff, h, atol=0.0)               # F_smooth is still on the device
     else:
-        j, g, st = tr.solve_grey(coeff, h, F=F)
+        j, g, st = tr.solve_grey(coeff, h, F=F, atol=-1.0 if sp.issparse(F) else 0.0)
     rtm.last_solve_stats = st
     if not st["converged"]:
         print(f"Warning: GMRES stopped at residual {st['residual']:.3e} after {st['iterations']} iterations")

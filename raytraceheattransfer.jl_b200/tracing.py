@@ -63,29 +63,64 @@ def counts_to_F(counts: np.ndarray, rays_per_emitter: int, verbose_loss: bool = 
     return F.tocsc()
 
 
-def _tracer_for(rtm, device: int):
-    """Re-flatten on every call (user code mutates properties between construction and tracing) and create the
-    device handle; the handle of the previous call is dropped."""
+def resolve_devices(devices, device: int, rays_total: int) -> List[int]:
+    """The `devices` keyword of the functor (new): an int, a list of device ids, or None = every visible
+    B200 — capped so that each device still traces >= 2e8 rays (about 2 ms of work; below that the fixed per-device cost of a
+    multi-GPU trace exceeds what the extra device saves).  `device` is the single-GPU spelling kept from round 1."""
+    if devices is None:
+        from ._lib import device_count
+        n_use = max(1, min(device_count(), int(rays_total // 200_000_000)))
+        return [int(device)] if n_use == 1 else list(range(n_use))
+    if isinstance(devices, int):
+        return [devices]
+    devs = [int(d) for d in devices]
+    if not devs or len(set(devs)) != len(devs):
+        raise ValueError("devices must be a non-empty list of distinct device ids")
+    return devs
+
+
+def _tracers_for(rtm, devices: Sequence[int]):
+    """Re-flatten on every call (user code mutates properties between construction and tracing) and create the device
+    handles — one per device, from one host-side preparation; the handles of the previous call are dropped."""
+    import time
+    t0 = time.perf_counter()
     flat = flatten_domain(rtm)
-    old = getattr(rtm, "_device", None)
-    if old is not None:
+    t1 = time.perf_counter()
+    for old in getattr(rtm, "_devices", None) or ([rtm._device] if getattr(rtm, "_device", None) is not None else []):
         old.close()
-    rtm._device = DeviceTracer(flat, device=device)
-    return rtm._device
+    if len(devices) == 1:
+        trs = [DeviceTracer(flat, device=devices[0])]
+    else:
+        from ._lib import create_multi
+        trs = create_multi(flat, devices)
+    rtm._devices = trs
+    rtm._device = trs[0]          # the handle that holds the resident counts / F_smooth afterwards
+    rtm.last_phase_ms = {"flatten": 1e3 * (t1 - t0), "create": 1e3 * (time.perf_counter() - t1)}
+    return trs
 
 
 def computeExchangeFactorsBins(rtm, rays_per_emitter: int, nudge: float, spectral_bins: Sequence[int],
                                verbose: bool, rec, seed: int, device: int = 0,
-                               locator: int = RTHX_LOCATOR_AUTO) -> List[sp.csc_matrix]:
-    """Batched form of computeExchangeFactorsBin: traces every requested (1-based) bin in one launch."""
-    tr = _tracer_for(rtm, device)
+                               locator: int = RTHX_LOCATOR_AUTO, devices=None) -> List[sp.csc_matrix]:
+    """Batched form of computeExchangeFactorsBin: traces every requested (1-based) bin in one launch per device."""
+    import time
+    devs = resolve_devices(devices if devices is not None else [device], device, 0)
+    trs = _tracers_for(rtm, devs)
+    tr = trs[0]
     rec_ids = [i - 1 for i in rec.ids] if rec is not None else None
     rec_bin = (rec.bin - 1) if rec is not None else 0
-    verbose and print(f"  Using CUDA device {device} for spectral bins {list(spectral_bins)}")
-    # the counts stay on the device; only their non-zeros come back, already row-normalised, as CSR triplets
-    # (parallelRayTracing.jl:144-154 + row_normalize! :161-169) — no N^2 host traffic, no host-side compaction
-    out = tr.trace(rays_per_emitter, dense=False, seed=seed, bins=[b - 1 for b in spectral_bins], nudge=nudge,
-                   rec_ids=rec_ids, rec_bin=rec_bin, locator=locator)
+    verbose and print(f"  Using CUDA device(s) {devs} for spectral bins {list(spectral_bins)}")
+    # The counts stay on the device (with several devices: gathered on the first one over NVLink peer memory inside the trace
+    # kernels); only their non-zeros come back, already row-normalised, as the three arrays of the CSC matrix the reference
+    # returns (parallelRayTracing.jl:144-158 + row_normalize! :161-169) — no N^2 host traffic, no sparse(I, J, V), no transpose.
+    t0 = time.perf_counter()
+    kw = dict(seed=seed, bins=[b - 1 for b in spectral_bins], nudge=nudge, rec_ids=rec_ids, rec_bin=rec_bin, locator=locator)
+    if len(trs) == 1:
+        out = tr.trace(rays_per_emitter, dense=False, **kw)
+    else:
+        from ._lib import trace_multi
+        out = trace_multi(trs, rays_per_emitter, dense=False, **kw)
+    t1 = time.perf_counter()
     rtm.last_trace_stats = out["stats"]
     rtm.last_lost = out["lost"]
     if rec is not None and "origins" in out:
@@ -94,35 +129,47 @@ def computeExchangeFactorsBins(rtm, rays_per_emitter: int, nudge: float, spectra
         rec.endpoints[0] = np.concatenate([rec.endpoints[0], out["endpoints"]], axis=0)
     N = tr.n_elements
     mats = []
+    rtm.last_counts_stats = []
     for k in range(len(spectral_bins)):
-        row_ptr, cols, _, fvals = tr.counts_csr(k, values=False, normalised=True)
+        nnz, chi = tr.counts_stats(k)
+        rtm.last_counts_stats.append({"nnz": nnz, "chi": chi, "density": nnz / float(N * N) if N else 0.0})
+        colptr, rowval, _, fvals = tr.counts_csc(k, values=False, normalised=True)
         max_loss = int(out["lost"][k].max()) if N else 0
         print(f"Maximum ray tracing ray loss per emitter: {max_loss}/{rays_per_emitter}")   # unconditional, :163
-        mats.append(sp.csr_matrix((fvals, cols, row_ptr), shape=(N, N)).tocsc())
+        if nnz < 2 ** 31:
+            colptr = colptr.astype(np.int32)          # scipy wants one index type; N + 1 entries, the big array stays as it is
+        else:
+            rowval = rowval.astype(np.int64)
+        F = sp.csc_matrix((fvals, rowval, colptr), shape=(N, N), copy=False)
+        F.has_sorted_indices = True                    # rows ascend within each column by construction
+        mats.append(F)
+    rtm.last_phase_ms.update({"trace": 1e3 * (t1 - t0), "csc_F_raw": 1e3 * (time.perf_counter() - t1)})
     return mats
 
 
 def computeExchangeFactorsBin(rtm, rays_per_emitter: int, nudge: float, spectral_bin: int, verbose: bool = False,
                               rec=None, seed: int = 0x5EED0001, device: int = 0,
-                              locator: int = RTHX_LOCATOR_AUTO) -> sp.csc_matrix:
+                              locator: int = RTHX_LOCATOR_AUTO, devices=None) -> sp.csc_matrix:
     """computeExchangeFactorsBin(rtm, rays_per_emitter, nudge, spectral_bin, ..., rec) -> sparse F (1-based bin)."""
     return computeExchangeFactorsBins(rtm, rays_per_emitter, nudge, [spectral_bin], verbose, rec, seed, device,
-                                      locator)[0]
+                                      locator, devices)[0]
 
 
 def parallelRayTracing(rtm, rays_total: int, nudge: float, verbose: bool, rec=None, seed: Optional[int] = None,
-                       device: int = 0, locator: int = RTHX_LOCATOR_AUTO):
+                       device: int = 0, locator: int = RTHX_LOCATOR_AUTO, devices=None):
     """parallelRayTracing(rtm, rays_total, nudge, verbose; rec) -> (F_raw, rays_per_emitter)."""
     if seed is None:
         seed = secrets.randbits(64)   # the reference is unseeded: a fresh stream per call
     num_emitters = rtm.num_elements
     rays_per_emitter = rays_total // num_emitters                        # parallelRayTracing.jl:6
     n_bins = rtm.n_spectral_bins
+    devices = resolve_devices(devices, device, rays_total)
     if rtm.spectral_mode == "spectral_variable":
         verbose and print(f"Computing {n_bins} separate F matrices for variable spectral extinction")
         groups, reps, nonuniform = group_uniform_bins(rtm.uniform_across_bin)
         to_trace = list(nonuniform) + [g[0] for g in groups]
-        mats = computeExchangeFactorsBins(rtm, rays_per_emitter, nudge, to_trace, verbose, rec, seed, device, locator)
+        mats = computeExchangeFactorsBins(rtm, rays_per_emitter, nudge, to_trace, verbose, rec, seed, device, locator, devices)
+        rtm._traced_bins = list(to_trace)
         F_raw_vector: List[Optional[sp.csc_matrix]] = [None] * n_bins
         for b, F in zip(to_trace[: len(nonuniform)], mats[: len(nonuniform)]):
             F_raw_vector[b - 1] = F
@@ -134,7 +181,8 @@ def parallelRayTracing(rtm, rays_total: int, nudge: float, verbose: bool, rec=No
         verbose and print(f"Computing single F matrix for uniform spectral extinction ({n_bins} bins)")
     else:
         verbose and print("Computing single F matrix for grey extinction")
-    F_raw = computeExchangeFactorsBins(rtm, rays_per_emitter, nudge, [1], verbose, rec, seed, device, locator)[0]
+    F_raw = computeExchangeFactorsBins(rtm, rays_per_emitter, nudge, [1], verbose, rec, seed, device, locator, devices)[0]
+    rtm._traced_bins = [1]
     return F_raw, rays_per_emitter
 
 
@@ -168,20 +216,33 @@ def get_b(rtm) -> np.ndarray:
     return b
 
 
-def _smooth_on_device(rtm, F_raw, w, ns: int, max_iters: int, verbose: bool, k_dykstra=None):
-    """Dense branch of smooth_F (density > 0.25, smoothExchangeFactors.jl:432-434) on the GPU, straight from the counts
-    that the trace left on the device; returns None when the sparse host path applies (sparsity must be preserved)."""
+def _smooth_on_device(rtm, k: int, F_raw, w, ns: int, max_iters: int, verbose: bool, k_dykstra=None):
+    """Dense branch of smooth_F (density > 0.25, smoothExchangeFactors.jl:432-434) on the GPU, straight from the counts of
+    traced bin number `k` (0-based position in the last launch) that the trace left on the device; returns None when the
+    sparse host path applies (sparsity must be preserved)."""
+    import warnings
     tr = getattr(rtm, "_device", None)
     n = F_raw.shape[0]
     if tr is None or max_iters <= 0 or F_raw.nnz / float(n * n) <= 0.25:
         return None
     wn = w[:n] / np.min(w[:n])
     if k_dykstra is None:       # smooth_F :441-450: one Dykstra round when surfaces and gas are strongly coupled, else AP only
-        from .smoothing import default_k_dykstra
-        k_dykstra = default_k_dykstra(F_raw, ns, smooth_surfaces_only=rtm.surfaces_only)
+        stats = getattr(rtm, "last_counts_stats", None)
+        if rtm.surfaces_only:
+            chi = 0.0                                                  # convex enclosure (:425-426)
+        elif stats is not None and k < len(stats):
+            chi = stats[k]["chi"]                                      # cross_coupling_chi computed by the device row pass
+        else:
+            from .smoothing import cross_coupling_chi
+            chi = cross_coupling_chi(F_raw, ns)
+        k_dykstra = 1 if chi >= 0.4 else 0
     verbose and print(f"Matrix size: {n}x{n}; dense smoothing on the device ({k_dykstra} Dykstra rounds + AP)")
-    F_smooth, st = tr.smooth(wn, n=n, max_iters=max_iters, k_dykstra=int(k_dykstra))
+    F_smooth, st = tr.smooth(wn, n=n, bin=k, max_iters=max_iters, k_dykstra=int(k_dykstra))
     rtm.last_smooth_stats = st
+    if not st["converged"]:          # the reference @warns here (smoothExchangeFactors.jl:605-607)
+        warnings.warn(f"AP reached max_iters = {max_iters}. Final delta_R = {st['delta']:.3e}")
+    if st["delta"] > max(st["delta_init"], 16 * np.finfo(np.float64).eps):       # :608-610
+        warnings.warn("Smoothing increased the distance to the target manifold; use F_raw instead of F_smooth.")
     # the smoothed matrix also stays on the device: solveEquilibrium reads it there when handed this very array
     from .equilibrium import _sample_of
     tr._resident_F = (F_smooth, _sample_of(F_smooth))
@@ -192,37 +253,46 @@ def _smooth_on_device(rtm, F_raw, w, ns: int, max_iters: int, verbose: bool, k_d
 
 def exchangeRayTracing(rtm, rays_tot: int, nudge: float, max_iters: int, k_dykstra, verbose: bool, rec,
                        seed: Optional[int] = None, device: int = 0, locator: int = RTHX_LOCATOR_AUTO,
-                       smooth: bool = True):
+                       smooth: bool = True, devices=None):
     """exchangeRayTracing!(rtm, rays_tot, nudge, max_iters, k_dykstra, verbose, rec): trace, optional
     surfaces-only crop (:9-11), smooth (:14-70), store rtm.F_raw / rtm.F_smooth (:73-74)."""
+    import time
     from .smoothing import smooth_F
     F_raw, rays_per_emitter = parallelRayTracing(rtm, rays_tot, nudge, verbose, rec=rec, seed=seed, device=device,
-                                                 locator=locator)
+                                                 locator=locator, devices=devices)
+    t0 = time.perf_counter()
     ns = rtm.num_surfaces
     if rtm.surfaces_only and not isinstance(F_raw, list):
         F_raw = F_raw[:ns, :ns]
+
+    def smooth_one(k, F, spectral_bin):
+        # the device path where the reference would take its dense branch, the reference's sparse host iteration otherwise
+        w = get_w(rtm, spectral_bin=spectral_bin)
+        Fs = _smooth_on_device(rtm, k, F, w, ns, max_iters, verbose, k_dykstra=k_dykstra)
+        if Fs is None:
+            Fs = smooth_F(F, w, ns, max_iters=max_iters, k_dykstra=k_dykstra, verbose=verbose,
+                          smooth_surfaces_only=rtm.surfaces_only)
+        return Fs
+
     if not smooth:
         F_smooth = F_raw
     elif rtm.spectral_mode == "spectral_variable":
+        # one smoothing per traced bin, with that bin's weights (exchangeRayTracing.jl:14-48); grouped bins alias one matrix
         groups, reps, nonuniform = group_uniform_bins(rtm.uniform_across_bin)
         F_smooth = [None] * rtm.n_spectral_bins
+        traced = list(nonuniform) + [g[0] for g in groups]
+        done = {b: smooth_one(k, F_raw[b - 1], b) for k, b in enumerate(traced)}
         for b in nonuniform:
-            F_smooth[b - 1] = smooth_F(F_raw[b - 1], get_w(rtm, spectral_bin=b), ns, max_iters=max_iters,
-                                       k_dykstra=k_dykstra, verbose=verbose,
-                                       smooth_surfaces_only=rtm.surfaces_only)
+            F_smooth[b - 1] = done[b]
         for g in groups:
-            rep = g[0]
-            Fs = smooth_F(F_raw[rep - 1], get_w(rtm, spectral_bin=rep), ns, max_iters=max_iters,
-                          k_dykstra=k_dykstra, verbose=verbose, smooth_surfaces_only=rtm.surfaces_only)
             for j in g:
-                F_smooth[j - 1] = Fs
+                F_smooth[j - 1] = done[g[0]]
     else:
-        F_smooth = _smooth_on_device(rtm, F_raw, get_w(rtm), ns, max_iters, verbose, k_dykstra=k_dykstra)
-        if F_smooth is None:
-            F_smooth = smooth_F(F_raw, get_w(rtm), ns, max_iters=max_iters, k_dykstra=k_dykstra, verbose=verbose,
-                                smooth_surfaces_only=rtm.surfaces_only)
+        F_smooth = smooth_one(0, F_raw, 1)
     rtm.F_raw = F_raw
     rtm.F_smooth = F_smooth
+    if getattr(rtm, "last_phase_ms", None) is not None:
+        rtm.last_phase_ms["smoothing"] = 1e3 * (time.perf_counter() - t0)
     return F_smooth
 
 

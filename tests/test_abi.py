@@ -19,7 +19,7 @@ def test_header_symbols_all_exported(cuda_lib, rthx_mod):
     assert declared == set(EXPORTED_SYMBOLS)
     for name in declared:
         assert getattr(cuda_lib, name) is not None
-    assert cuda_lib.rthx_version() == 2                                 # 0.2: rthx_info.n_bilinear_faces
+    assert cuda_lib.rthx_version() == 3                                 # 0.3: rthx_smooth_stats.converged, rthx_create_multi, rthx_counts_csc, ...
 
 
 def test_struct_layouts_match_header(rthx_mod):

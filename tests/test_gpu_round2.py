@@ -1,0 +1,176 @@
+"""Round-2 rows: CSC read-out + chi on the device, rthx_create_multi / single-process multi-GPU trace (host rows and
+device-0 gather), argument guards, the lazily built generic-locator tables, AP's stopping rule and the `devices` keyword."""
+import warnings
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+pytestmark = pytest.mark.gpu
+
+
+def _n_gpus():
+    from rthx._lib import device_count
+    return device_count()
+
+
+def test_csc_equals_dense_and_stats(rthx_mod, cuda_lib):
+    rtm = rthx_mod.meshes.cfg4(Ndim=9, n_bins=3)
+    flat = rthx_mod.flatten_domain(rtm)
+    tr = rthx_mod.DeviceTracer(flat, device=0)
+    N, ns = tr.n_elements, flat.n_surfaces
+    dense = tr.trace(3000, seed=51, bins=[0, 1, 2])
+    tr.trace(3000, seed=51, bins=[0, 1, 2], dense=False)
+    for b in (1, 0, 2):
+        c = dense["counts"][b]
+        nnz, chi = tr.counts_stats(b)
+        assert nnz == int((c != 0).sum())
+        F = c / np.maximum(c.sum(axis=1, keepdims=True), 1)
+        chi_ref = (F[:ns, ns:].sum() + F[ns:, :ns].sum()) / N               # cross_coupling_chi, smoothExchangeFactors.jl:212-241
+        assert abs(chi - chi_ref) < 1e-12
+        for index64, base in ((False, 0), (True, 1)):
+            colptr, rowval, vals, fv = tr.counts_csc(b, values=True, normalised=True, index64=index64, index_base=base)
+            assert rowval.dtype == (np.int64 if index64 else np.int32) and colptr[0] == base and colptr[-1] == nnz + base
+            m = sp.csc_matrix((vals, rowval - base, colptr - base), shape=(N, N))
+            assert np.array_equal(m.toarray(), c)
+            for j in (0, ns, N - 1):                                          # rows ascend within a column
+                seg = rowval[colptr[j] - base:colptr[j + 1] - base]
+                assert np.all(np.diff(seg) > 0)
+            Fm = sp.csc_matrix((fv, rowval - base, colptr - base), shape=(N, N)).toarray()
+            assert np.allclose(Fm, F, rtol=0, atol=1e-15)
+    # the CSR view of the same residency still agrees
+    row_ptr, cols, vals, _ = tr.counts_csr(2)
+    assert np.array_equal(sp.csr_matrix((vals, cols, row_ptr), shape=(N, N)).toarray(), dense["counts"][2])
+
+
+def test_csc_into_pageable_arrays_over_staging(rthx_mod, cuda_lib):
+    """A pageable destination larger than one staging piece (32 MB) goes through the pinned double buffer."""
+    flat = rthx_mod.flatten_domain(rthx_mod.meshes.square_domain(41, kappa=0.3))
+    tr = rthx_mod.DeviceTracer(flat, device=0)
+    N = tr.n_elements
+    ref = tr.trace(20000, seed=5)["counts"][0]
+    tr.trace(20000, seed=5, dense=False)
+    a = tr.counts_csc(0, values=True, index64=True, pinned=True)
+    b = tr.counts_csc(0, values=True, index64=True, pinned=False)
+    assert a[1].nbytes > (32 << 20) // 4                                       # big enough to matter, and ...
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    assert np.array_equal(sp.csc_matrix((b[2], b[1], b[0]), shape=(N, N)).toarray(), ref)
+
+
+def test_multi_entry_point_on_one_device_and_state_reset(rthx_mod, cuda_lib):
+    """rthx_create_multi + rthx_trace_exchange_multi with n = 1 (what the Julia shim calls with DEVICES = [0]), host rows and
+    resident gather; a multi trace voids the resident view of an earlier single trace (stale csr state)."""
+    from rthx._lib import create_multi, trace_multi, RthxError
+    flat = rthx_mod.flatten_domain(rthx_mod.meshes.cfg5())
+    (tr,) = create_multi(flat, [0])
+    one = tr.trace(2000, seed=9)
+    assert tr.counts_stats(0)[0] == int((one["counts"][0] != 0).sum())
+    host = trace_multi([tr], 2000, seed=9)
+    assert np.array_equal(host["counts"], one["counts"]) and np.array_equal(host["lost"], one["lost"])
+    with pytest.raises(RthxError):                                              # compact rows are no N x N matrix: view is void
+        tr.counts_stats(0)
+    res = trace_multi([tr], 2000, seed=9, dense=False)
+    assert res["counts"] is None and np.array_equal(res["lost"], one["lost"])
+    colptr, rowval, vals, _ = tr.counts_csc(0, values=True)
+    N = tr.n_elements
+    assert np.array_equal(sp.csc_matrix((vals, rowval, colptr), shape=(N, N)).toarray(), one["counts"][0])
+
+
+def test_argument_guards(rthx_mod, cuda_lib):
+    from rthx._lib import RthxError
+    flat = rthx_mod.flatten_domain(rthx_mod.meshes.cfg1())
+    tr = rthx_mod.DeviceTracer(flat, device=0)
+    with pytest.raises(RthxError, match="too many bins"):
+        tr.trace(10, bins=[0] * 21)                                             # limit 4 * n_bands + 16 = 20
+    assert tr.trace(10, bins=[0] * 20)["counts"].shape[0] == 20
+    with pytest.raises(RthxError, match="out of range"):
+        tr.trace(2 ** 33, row_chunks=1, dense=False)                            # 2^33 rays in one block: u32 counters would wrap
+    with pytest.raises(RthxError, match="out of range"):
+        tr.trace(10, row_chunks=2 ** 31 - 1, dense=False)                       # rows * chunks beyond the grid limit
+
+
+def test_generic_tables_are_built_on_first_use(rthx_mod, oracle_mod, cuda_lib):
+    """The analytic paths never build the reference-faithful locator tables; the first RTHX_LOCATOR_GENERIC trace does, and
+    later analytic traces on the same handle are unaffected."""
+    flat = rthx_mod.flatten_domain(rthx_mod.meshes.cfg5())
+    tr = rthx_mod.DeviceTracer(flat, device=0)
+    a0 = tr.trace(1500, seed=3)
+    g = tr.trace(1500, seed=3, locator=1)
+    a1 = tr.trace(1500, seed=3)
+    ref = oracle_mod.trace(flat, 1500, seed=3)
+    assert np.array_equal(a0["counts"], a1["counts"])
+    assert np.array_equal(g["counts"], ref["counts"]) and np.array_equal(g["lost"], ref["lost"])
+
+
+def test_ap_stopping_rule_reports_convergence(rthx_mod, cuda_lib):
+    """Device AP exits only at the target or on an accepted floor (smoothExchangeFactors.jl:578-590); running out of
+    iterations is reported, and the public call warns like the reference's @warn (:605-607)."""
+    rtm = rthx_mod.meshes.cfg1()
+    flat = rthx_mod.flatten_domain(rtm)
+    tr = rthx_mod.DeviceTracer(flat, device=0)
+    tr.trace(20000, seed=4, dense=False)
+    w = rthx_mod.get_w(rtm)
+    F, st = tr.smooth(w / w.min(), max_iters=1000)
+    assert st["converged"] == 1 and st["delta"] <= 2 * 8 * np.finfo(float).eps
+    F3, st3 = tr.smooth(w / w.min(), max_iters=3)
+    assert st3["converged"] == 0 and st3["iterations"] == 3 and st3["delta"] > st["delta"]
+    with warnings.catch_warnings(record=True) as wlist:
+        warnings.simplefilter("always")
+        rtm(165 * 20000, method="exchange", verbose=False, seed=4, max_iters=3)
+    assert any("max_iters" in str(x.message) for x in wlist)
+
+
+def test_public_call_phases_and_csc_F_raw(rthx_mod, cuda_lib):
+    rtm = rthx_mod.meshes.cfg2()
+    F_smooth = rtm(1845 * 3000, method="exchange", verbose=False, seed=8)
+    assert sp.isspmatrix_csc(rtm.F_raw) and rtm.F_raw.has_sorted_indices
+    assert np.allclose(np.asarray(rtm.F_raw.sum(axis=1)).ravel(), 1.0)
+    assert set(rtm.last_phase_ms) >= {"flatten", "create", "trace", "csc_F_raw", "smoothing"}
+    # same F_raw as the dense read-out + the reference's composition (parallelRayTracing.jl:144-146 + row_normalize!)
+    tr = rthx_mod.DeviceTracer(rthx_mod.flatten_domain(rtm), device=0)
+    c = tr.trace(3000, seed=8)["counts"][0]
+    assert np.allclose(rtm.F_raw.toarray(), rthx_mod.counts_to_F(c, 3000, verbose_loss=False).toarray(), rtol=0, atol=1e-15)
+    assert isinstance(F_smooth, np.ndarray) and np.allclose(F_smooth.sum(axis=1), 1.0, atol=1e-9)
+
+
+@pytest.mark.skipif("_n_gpus() < 2", reason="needs two GPUs (gpurun --gpus 2)")
+def test_single_process_multi_gpu_is_bit_exact(rthx_mod, cuda_lib):
+    """rthx_trace_exchange_multi over every visible device: host rows, device-0 gather, recorder — all equal to one GPU."""
+    from rthx._lib import create_multi, trace_multi
+    n = _n_gpus()
+    for mesh in (rthx_mod.meshes.cfg4(Ndim=15, n_bins=3), rthx_mod.meshes.cfg5()):
+        flat = rthx_mod.flatten_domain(mesh)
+        bins = list(range(flat.n_bands))
+        one = rthx_mod.DeviceTracer(flat, device=0).trace(4000, seed=21, bins=bins, rec_ids=[3, 40, 41])
+        trs = create_multi(flat, list(range(n)))
+        N = trs[0].n_elements
+        host = trace_multi(trs, 4000, seed=21, bins=bins, rec_ids=[3, 40, 41])
+        assert np.array_equal(host["counts"], one["counts"]) and np.array_equal(host["lost"], one["lost"])
+        assert np.array_equal(host["origins"], one["origins"]) and np.array_equal(host["endpoints"], one["endpoints"])
+        pageable = np.full((len(bins), N, N), 7, np.uint64)                      # stale contents, staged copy path
+        trace_multi(trs, 4000, seed=21, bins=bins, counts_out=pageable)
+        assert np.array_equal(pageable, one["counts"])
+        for rep in range(2):                                                     # the second pass checks the zeroing
+            res = trace_multi(trs, 4000, seed=21, bins=bins, dense=False)
+        assert np.array_equal(res["lost"], one["lost"])
+        for b in bins:
+            colptr, rowval, vals, _ = trs[0].counts_csc(b, values=True)
+            assert np.array_equal(sp.csc_matrix((vals, rowval, colptr), shape=(N, N)).toarray(), one["counts"][b])
+        for t in trs:
+            t.close()
+
+
+@pytest.mark.skipif("_n_gpus() < 2", reason="needs two GPUs (gpurun --gpus 2)")
+def test_public_call_devices_keyword(rthx_mod, cuda_lib):
+    n = _n_gpus()
+    a = rthx_mod.meshes.cfg2()
+    b = rthx_mod.meshes.cfg2()
+    rec_a, rec_b = rthx_mod.RayRecorder([10, 20]), rthx_mod.RayRecorder([10, 20])
+    Fa = a(1845 * 2000, method="exchange", verbose=False, seed=77, devices=[0], rec=rec_a)
+    Fb = b(1845 * 2000, method="exchange", verbose=False, seed=77, devices=list(range(n)), rec=rec_b)
+    assert (a.F_raw != b.F_raw).nnz == 0
+    assert np.array_equal(Fa, Fb)
+    oa, ea = rthx_mod.collect_rays(rec_a)
+    ob, eb = rthx_mod.collect_rays(rec_b)
+    assert np.array_equal(oa, ob) and np.array_equal(ea, eb)
