@@ -39,6 +39,7 @@ struct DevRes {
   double* peak_dev = nullptr;
   int* csr_nnz = nullptr;                   size_t csr_cap = 0;        // per-row nnz (int), row totals, row pointers
   unsigned long long* csr_rowsum = nullptr; long long* csr_rowptr = nullptr; unsigned long long* csr_cross = nullptr;
+  unsigned int* row_done_dev = nullptr;     size_t row_done_cap = 0;   // fused peer flush: per-row hand-over tickets
   int* csc_partial = nullptr;               size_t csc_partial_cap = 0; // CSC read-out: per (row tile, column) counts / offsets
   long long* csc_colptr = nullptr;          size_t csc_colptr_cap = 0;
   void* csr_out = nullptr;                  size_t csr_out_cap = 0;    // compacted cols / vals / F_vals
@@ -94,7 +95,7 @@ bool g_kernels_configured[64] = {};   // cudaFuncSetAttribute(max dynamic smem) 
 
 void devres_free(DevRes& r) {
   cudaFree(r.smooth_X); cudaFree(r.smooth_vec); cudaFree(r.smooth_src); cudaFree(r.solve_buf); cudaFree(r.solve_mat); cudaFree(r.dyk_buf);
-  cudaFree(r.csr_nnz); cudaFree(r.csr_rowsum); cudaFree(r.csr_rowptr); cudaFree(r.csr_out); cudaFree(r.csr_cross); cudaFree(r.csc_partial); cudaFree(r.csc_colptr);
+  cudaFree(r.csr_nnz); cudaFree(r.csr_rowsum); cudaFree(r.csr_rowptr); cudaFree(r.csr_out); cudaFree(r.csr_cross); cudaFree(r.csc_partial); cudaFree(r.csc_colptr); cudaFree(r.row_done_dev);
   cudaFree(r.arena); cudaFree(r.generic_arena); cudaFree(r.counts_dev); cudaFree(r.rec_pts_dev); cudaFree(r.rec_valid_dev); cudaFree(r.peak_dev);
   for (auto& e : r.ev) if (e) cudaEventDestroy(e);
   for (auto& e : r.bev) if (e) cudaEventDestroy(e);
@@ -902,7 +903,7 @@ LaunchPlan make_plan(const rthx_handle* h, const rthx_trace_args* a, int rank, i
   if (h->queue_ok && a->locator != RTHX_LOCATOR_GENERIC && (!pl.multi || multi_queue) && !pl.sq && pl.hist_in_smem && pl.block_threads == 256 &&
       (h->n_coarse > 1 || h->queue_general || multi_queue)) {
     const size_t base = (pl.smem_bytes + 15) & ~size_t(15);
-    const size_t per_depth = (size_t)pl.block_threads * 40;
+    const size_t per_depth = (size_t)pl.block_threads * (multi_queue ? 48 : 40);   // bytes per parked ray: p, d, S (+ ray index and event word for MULTI)
     // aim at 4 resident blocks per SM (3 for the MULTI variant, which is bounded to 85 registers); large descriptor tables /
     // histograms settle for fewer
     int depth = 0;
@@ -1019,6 +1020,33 @@ int enqueue_trace(rthx_handle* h, const rthx_trace_args* a, int rank, int world,
   if (pl.n_blocks < 0) return fail(h, RTHX_ERR_ARG, "trace: rays_per_emitter / row_chunks out of range (a block traces at most 2^31 rays, a launch at most 2^31 blocks)");
   if (!pl.fast) { const int rcg = ensure_generic(h); if (rcg) return rcg; }     // the generic kernel reads the reference-faithful locator tables
   if (upload_bins) CU(h, cudaMemcpyAsync(h->bins_dev, a->bins, sizeof(int32_t) * (size_t)a->n_bins, cudaMemcpyHostToDevice, stream));
+  // A matrix in peer memory (fused multi-GPU flush) is never the target of reductions: the chunks of a row add up in a local
+  // compact staging matrix and the finished row is handed over with plain stores (flush_row_hist) — so the peer rows need no
+  // clearing either.  Without the shared-memory histogram (N > ~57 k) the old path stays: system-scope atomics into zeroed rows.
+  bool peer = false;
+  {
+    cudaPointerAttributes pa;
+    if (counts && cudaPointerGetAttributes(&pa, counts) == cudaSuccess && pa.type == cudaMemoryTypeDevice && pa.device != h->device) peer = true;
+    else cudaGetLastError();
+    if (const char* ev = std::getenv("RTHX_FLUSH_SYSTEM")) peer = std::atoi(ev) != 0;     // test knob: exercise the hand-over on one GPU
+    if (const char* ev = std::getenv("RTHX_PEER_ATOMICS")) { if (std::atoi(ev)) peer = false; }   // A/B knob: the old red.sys flush
+  }
+  const bool staged = peer && pl.hist_in_smem && !compact;
+  unsigned long long* stage_counts = nullptr;
+  unsigned int* row_done = nullptr;
+  if (staged) {
+    h->last_trace_bins = 0; h->csr_bin = -1; h->csc_bin = -1;            // counts_dev becomes the staging matrix
+    const size_t n_rows = (size_t)a->n_bins * (size_t)pl.n_owned;
+    if (pl.row_chunks > 1) {
+      CU(h, ensure(&h->counts_dev, &h->counts_cap, n_rows * (size_t)h->N));
+      CU(h, cudaMemsetAsync(h->counts_dev, 0, sizeof(unsigned long long) * n_rows * (size_t)h->N, stream));
+      stage_counts = h->counts_dev;
+      *n_launches += 1;
+    }
+    CU(h, ensure(&h->row_done_dev, &h->row_done_cap, std::max<size_t>(n_rows, 1)));
+    CU(h, cudaMemsetAsync(h->row_done_dev, 0, sizeof(unsigned int) * std::max<size_t>(n_rows, 1), stream));
+    row_done = h->row_done_dev;
+  }
   const size_t rows = compact ? (size_t)pl.n_owned : (size_t)h->N;
   if (zero_first == RTHX_ZERO_ALL) {
     CU(h, cudaMemsetAsync(counts, 0, sizeof(unsigned long long) * (size_t)a->n_bins * rows * h->N, stream));
@@ -1030,7 +1058,7 @@ int enqueue_trace(rthx_handle* h, const rthx_trace_args* a, int rank, int world,
     for (int b = 0; b < a->n_bins; ++b) {
       if (compact) {
         CU(h, cudaMemsetAsync(counts + (size_t)b * pl.n_owned * h->N, 0, rb * pl.n_owned, stream));
-      } else {
+      } else if (!staged) {
         CU(h, cudaMemset2DAsync(counts + ((size_t)b * h->N + rank) * h->N, rb * world, 0, rb, (size_t)pl.n_owned, stream));
       }
       CU(h, cudaMemset2DAsync(lost + (size_t)b * h->N + rank, sizeof(unsigned long long) * world, 0, sizeof(unsigned long long), (size_t)pl.n_owned, stream));
@@ -1039,6 +1067,11 @@ int enqueue_trace(rthx_handle* h, const rthx_trace_args* a, int rank, int world,
   }
   TraceParams P;
   fill_params(h, a, pl, rank, world, compact, counts, lost, P);
+  if (staged) {
+    P.peer_counts = counts; P.row_done = row_done;
+    P.counts = stage_counts; P.compact_rows = 1;                         // nullptr with row_chunks == 1: rows are written out directly
+    P.flush_system = 1;                                                  // the lost counters live next to the peer matrix
+  }
   if (with_rec && n_rec_slots > 0) { P.rec_slot = h->rec_slot_dev; P.rec_pts = h->rec_pts_dev; P.rec_valid = h->rec_valid_dev; }
   if (y1 < 0) y1 = pl.n_owned;
   P.y_offset = y0;
@@ -1374,25 +1407,20 @@ extern "C" int rthx_trace_exchange_multi(rthx_handle** hs, int n, const rthx_tra
       cudaGetLastError();
       hs[i]->last_trace_bins = 0; hs[i]->csr_bin = -1; hs[i]->csc_bin = -1;
     }
-    // device 0 clears the matrix and the lost counters; every device's kernel waits for that
-    CU(h0, cudaSetDevice(h0->device));
-    CU(h0, cudaEventRecord(h0->ev[0], h0->stream));
-    CU(h0, cudaMemsetAsync(shared_counts, 0, sizeof(unsigned long long) * (size_t)a->n_bins * N * N, h0->stream));
-    CU(h0, cudaMemsetAsync(h0->lost_dev, 0, sizeof(unsigned long long) * lost_n, h0->stream));
-    CU(h0, cudaEventRecord(h0->bev[17], h0->stream));
+    // nothing is cleared centrally: every device clears its own rows / lost counters (device 0 in place, the others need no
+    // clearing of the matrix at all — they hand finished rows over with plain stores)
   }
   auto device_job = [&](int i) {
     rthx_handle* h = hs[i];
     MultiJob& J = jobs[i];
     auto run = [&]() -> int {
       CU(h, cudaSetDevice(h->device));
-      if (!gather || i > 0) CU(h, cudaEventRecord(h->ev[0], h->stream));
+      CU(h, cudaEventRecord(h->ev[0], h->stream));
       int r = prepare_recorder(h, a, rec, &J.slots, h->stream);
       if (r) return r;
       if (gather) {
-        if (i > 0) CU(h, cudaStreamWaitEvent(h->stream, h0->bev[17], 0));
         CU(h, cudaEventRecord(h->ev[1], h->stream));
-        r = enqueue_trace(h, a, i, n, /*compact=*/false, shared_counts, h0->lost_dev, RTHX_ZERO_NONE, rec != nullptr, J.slots, h->stream, &J.plan, &J.launches);
+        r = enqueue_trace(h, a, i, n, /*compact=*/false, shared_counts, h0->lost_dev, RTHX_ZERO_OWN_ROWS, rec != nullptr, J.slots, h->stream, &J.plan, &J.launches);
         if (r) return r;
         CU(h, cudaEventRecord(h->ev[2], h->stream));
         CU(h, cudaEventRecord(h->ev[3], h->stream));
@@ -1460,7 +1488,7 @@ extern "C" int rthx_trace_exchange_multi(rthx_handle** hs, int n, const rthx_tra
     int nbk = 0, nlaunch = 0;
     double kmax = 0, tmax = 0;
     for (auto& J : jobs) { nbk += J.plan.n_blocks; nlaunch += J.launches; kmax = std::max(kmax, J.kernel_ms); tmax = std::max(tmax, J.total_ms); }
-    st->n_blocks = nbk; st->n_launches = nlaunch + (gather ? 2 : 0);
+    st->n_blocks = nbk; st->n_launches = nlaunch;
     st->kernel_ms = kmax; st->total_ms = tmax;     // the slowest device
   }
   return RTHX_OK;

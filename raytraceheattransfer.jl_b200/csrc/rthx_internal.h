@@ -73,6 +73,9 @@ struct TraceParams {
   // outputs
   unsigned long long* counts;  // row (bi, y) at ((bi*rows_per_bin + y) * N)
   unsigned long long* lost;    // [n_bins*N]
+  unsigned long long* peer_counts;  // fused multi-GPU flush: the matrix in peer memory ([n_bins][N][N]) that finished rows are handed
+                                    // over to; `counts` is then a local compact staging matrix.  nullptr: `counts` is the destination
+  unsigned int* row_done;      // [n_bins*n_owned] chunks of a row that have flushed (hand-over ticket), with peer_counts
   double* rec_pts;             // [n_rec*rays_per_emitter*4] origin xy, endpoint xy
   uint8_t* rec_valid;          // [n_rec*rays_per_emitter]
   // scalars

@@ -297,6 +297,45 @@ __device__ __forceinline__ int locate_fine(const TraceParams& p, const CoarseDev
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Flush of a block's row histogram into the count matrix.
+//   matrix on this GPU   : one red.global.add.u64 per non-zero bin (several chunks of a row add up in place);
+//   matrix in peer memory (one-process-per-GPU / multi-device gather, rows of different GPUs are disjoint): nothing on the wire is
+//       atomic.  A block that owns its whole row (row_chunks == 1) writes it out with plain coalesced stores; otherwise the chunks
+//       of a row add up in a LOCAL staging row first and the chunk that arrives last (per-row ticket) hands the finished row over.
+//       NVLink then carries exactly 8 N bytes per row, overlapped with the tracing of the other rows — with system-scope reductions
+//       per chunk it carried row_chunks times that in 8-byte atomics, which at 8 GPUs x 15 chunks doubled the kernel time.
+// The kernels keep their plain red.add flush inline for a matrix on their own GPU and call this (out of line) only for a matrix in
+// peer memory.  Everything it needs is recomputed from blockIdx and the parameter bank, so that it keeps no register alive across
+// the ray loop (the SQ loop sits exactly at the 64 registers of 4 resident blocks per SM).
+// `ticket`: one free word of the block's dynamic shared memory (the upper half of the emitter block's last slot) — a static
+// __shared__ variable would eat into the opt-in maximum the kernels are configured for.
+__device__ __noinline__ void handover_row_hist(const TraceParams& p, const uint32_t* hist, unsigned int* ticket) {
+  const int N = p.N;
+  const unsigned t1 = blockIdx.x / (unsigned)p.row_chunks;
+  const int bi = (int)(t1 % (unsigned)p.n_bins);
+  const int y = p.y_offset + (int)(t1 / (unsigned)p.n_bins);
+  const int e = p.emitter_rank + y * p.emitter_world;
+  unsigned long long* dst = p.peer_counts + ((size_t)bi * N + e) * (size_t)N;
+  if (p.row_chunks == 1) {
+    for (int i = threadIdx.x; i < N; i += blockDim.x) dst[i] = (unsigned long long)hist[i];
+    return;
+  }
+  unsigned long long* count_row = p.counts + ((size_t)bi * p.n_owned + y) * (size_t)N;      // local compact staging row
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const uint32_t v = hist[i];
+    if (v) atomicAdd(&count_row[i], (unsigned long long)v);
+  }
+  __threadfence();                                       // this chunk's reductions are visible before its ticket is drawn
+  __syncthreads();
+  if (threadIdx.x == 0) *ticket = atomicAdd(&p.row_done[(size_t)bi * p.n_owned + y], 1u);
+  __syncthreads();
+  if (*ticket == (unsigned int)p.row_chunks - 1u) {      // last chunk of the row: every other chunk has fenced and drawn before
+    __threadfence();
+    for (int i = threadIdx.x; i < N; i += blockDim.x) dst[i] = __ldcg(&count_row[i]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // K1: fused emit + trace + tally (+ record)
 //   HIST_SMEM: per-block shared-memory row histogram (else direct global atomics, N > ~57 k elements)
 //   FAST     : every coarse face is a verified affine lattice with a complete neighbour table and the coarse
@@ -596,6 +635,7 @@ __global__ void __launch_bounds__(256, MINB) trace_exchange_kernel(const __grid_
   }
   if (HIST_SMEM) {
     __syncthreads();
+    if (p.peer_counts != nullptr) { handover_row_hist(p, hist, reinterpret_cast<unsigned int*>(s_em + 15) + 1); return; }
     for (int i = threadIdx.x; i < N; i += blockDim.x) {
       const uint32_t v = hist[i];
       if (v) {
@@ -1020,6 +1060,7 @@ __global__ void __launch_bounds__(256, MINB) trace_exchange_sq_kernel(const __gr
     else atomicAdd(&p.lost[(size_t)bi * N + e], (unsigned long long)n_lost);
   }
   __syncthreads();
+  if (p.peer_counts != nullptr) { handover_row_hist(p, hist, reinterpret_cast<unsigned int*>(s_em + 15) + 1); return; }
   for (int i = threadIdx.x; i < N; i += blockDim.x) {
     const uint32_t v = hist[i];
     if (v) {
@@ -1131,13 +1172,7 @@ __device__ __forceinline__ int lattice_cell(const CoarseDev& cf, double px, doub
   return (((unsigned)n < (unsigned)cf.Nx) & ((unsigned)m < (unsigned)cf.Ny)) ? n + m * cf.Nx : -1;
 }
 
-// MULTI (RTHX_MULTI_BOUNCE[_SPECULAR], the analogue of method=:direct's traceSingleRay.jl:24-79 without re-emission): a ray whose
-// first interaction is found is not retired but absorbed, scattered (isotropicScatter2D.jl:1-4) or reflected (diffuse:
-// sampleReflectionDirection2D.jl:5-16 + lambertSample2D; specular: mirror) right in its lane — two more Philox calls per event,
-// call# 2+2n / 3+2n exactly as in trace_exchange_kernel<..., MULTI> — and keeps its lane until it is absorbed.  Lanes whose ray
-// ended refill from the queue as before, so the warp no longer waits for its longest event chain (the lock-step loop of
-// sq_multi_loop ran at 15.5 of 32 lanes on cfg3, omega = 0.5).
-template <bool SURF, bool UNIFORM, bool REC, int DEPTH, bool BILIN, bool MULTI>
+template <bool SURF, bool UNIFORM, bool REC, int DEPTH, bool BILIN>
 __device__ __forceinline__ unsigned int queue_ray_loop(const TraceParams& p, const QueueBlock& b) {
   constexpr int WQ = 32 * DEPTH;                       // queue slots per warp
   const int lane = b.lane;
@@ -1148,8 +1183,7 @@ __device__ __forceinline__ unsigned int queue_ray_loop(const TraceParams& p, con
   bool active = false;
   double px = 0.0, py = 0.0, dx = 0.0, dy = 0.0, S = 0.0, acc = 0.0;   // S: remaining free path (UNIFORM) or -log R
   int c = b.c0, it = 0;
-  int event = 0;                                       // MULTI: interactions this ray has survived
-  uint32_t r_cur = 0;                                  // ray index of the in-flight ray relative to r_begin (recorder slot, Philox counter)
+  uint32_t r_cur = 0;                                  // ray index of the in-flight ray relative to r_begin (recorder slot)
   // the warp's rays: batch j of the block covers [r_begin + j*n_warps*WQ, ...), this warp takes its WQ-slice of every batch
   int64_t rb = b.r_begin + (int64_t)b.warp * WQ;
   const int64_t stride = (int64_t)b.n_warps * WQ;
@@ -1184,7 +1218,6 @@ __device__ __forceinline__ unsigned int queue_ray_loop(const TraceParams& p, con
       if (!active & (idx < n_valid)) {
         px = q[idx]; py = q[WQ + idx]; dx = q[2 * WQ + idx]; dy = q[3 * WQ + idx]; S = q[4 * WQ + idx];
         acc = 0.0; c = b.c0; it = 0; r_cur = rb_rel + (uint32_t)idx;
-        if (MULTI) event = 0;
         active = true;
       }
       next += __popc(need);
@@ -1229,71 +1262,24 @@ __device__ __forceinline__ unsigned int queue_ray_loop(const TraceParams& p, con
         // (rthx_api.cu builds the table from the lattice -> fine map, the fine cells' vertex counts and cell_surf_id)
 #define RTHX_QUEUE_FINISH()                                                                                         \
   do {                                                                                                              \
+    active = false;                                                                                                 \
     int absorber = -1;                                                                                              \
     if (tallied) {                                                                                                  \
       const int l = lattice_cell<BILIN>(cf, px, py);                                                                \
-      if (l >= 0) absorber = __ldg(p.abs_tab + (size_t)(cf.abs_off + l) * 5 + (gas ? 0 : 1 + k));                   \
+      /* gas ending on a quad lattice: Ns + cell, no load (fine index = lattice index, meshQuad.jl:139,151) */        \
+      if (l >= 0) absorber = (gas & (cf.kind != KIND_AFFINE_TRI)) ? p.n_surfaces + cf.fine_off + l                   \
+                                                                  : __ldg(p.abs_tab + (size_t)(cf.abs_off + l) * 5 + (gas ? 0 : 1 + k)); \
     }                                                                                                               \
-    bool retire = true;                                                                                             \
-    if (MULTI && absorber >= 0) {                                                                                   \
-      /* absorb, scatter or reflect (traceSingleRay.jl:24-79): v0.x decision, v0.y azimuth / psi, v0.z cos-theta (walls), */ \
-      /* v0.w roulette, (v1.x,v1.y) polar angle (gas), (v1.z,v1.w) next free path */                               \
-      if (event >= 16000) {                                          /* call# is a 16-bit field */                  \
-        absorber = -1;                                                                                              \
-      } else {                                                                                                      \
-        const uint64_t ray_id = (uint64_t)(p.ray_id_offset + b.r_begin + (int64_t)r_cur);                           \
-        const uint32_t c_lo = (uint32_t)ray_id, c_hi = (uint32_t)(ray_id >> 32);                                    \
-        const uint4 v0 = philox4x32_10_rk(make_uint4(c_lo, c_hi, b.e, b.cw | (uint32_t)(2 + 2 * event)), p.rk);     \
-        const uint4 v1 = philox4x32_10_rk(make_uint4(c_lo, c_hi, b.e, b.cw | (uint32_t)(3 + 2 * event)), p.rk);     \
-        if (event >= 1000 && u32d(v0.w, p.k_u32) > 0.8) {             /* Russian roulette, traceSingleRay.jl:11 */  \
-          absorber = -1;                                                                                            \
-        } else {                                                                                                    \
-          const double dec = u32d(v0.x, p.k_u32);                                                                   \
-          if (absorber >= p.n_surfaces) {                                                                           \
-            if (dec < b.omega_band[absorber - p.n_surfaces]) {        /* scattered: theta = acos(2R - 1), phi = 2 pi R */ \
-              const double cc = __hiloint2double((int)(0x3FF00000u | (v1.y >> 12)), (int)((v1.y << 20) | (v1.x >> 12))) - p.k_u52c; \
-              dx = sqrt_pos(fma(-cc, cc, 0.25)) * cos2pi_centered_x2(u32d_centered(v0.y, p.k_u32c));                \
-              dy = cc + cc;                                                                                         \
-              retire = false;                                                                                       \
-            }                                                                                                       \
-          } else if (!(dec < b.eps_band[absorber])) {                 /* reflected */                               \
-            const double hnx = cf.nx[k], hny = cf.ny[k];              /* outward normal of the coarse edge (= of every fine wall on it) */ \
-            if (p.specular) {                                                                                       \
-              const double dn = dx * hnx + dy * hny;                                                                \
-              dx = fma(-2.0 * dn, hnx, dx);                                                                         \
-              dy = fma(-2.0 * dn, hny, dy);                                                                         \
-            } else {                                                                                                \
-              const float cosT = __fsqrt_rn(u23(v0.z));                                                             \
-              const float cos2 = __fmul_rn(cosT, cosT);                                                             \
-              const double xdir = sqrt_pos(1.0 - (double)cos2) * cos2pi_centered((double)u23(v0.y) - 0.5);          \
-              const double zdir = (double)cosT;                                                                     \
-              const double nxi = -hnx, nyi = -hny;                                                                  \
-              dx = nyi * xdir + nxi * zdir;                                                                         \
-              dy = -nxi * xdir + nyi * zdir;                                                                        \
-            }                                                                                                       \
-            retire = false;                                                                                         \
-          }                                                                                                         \
-          if (!retire) {                                              /* traced on from the interaction point, same coarse face */ \
-            const double nl = neg_log_table(u52(v1.z, v1.w, p.k_u52), b.s_log);                                     \
-            S = UNIFORM ? nl * b.inv_beta_u : nl;                                                                   \
-            acc = 0.0; it = 0; ++event;                                                                             \
-          }                                                                                                         \
-        }                                                                                                           \
+    if (absorber >= 0) {                                                                                            \
+      atomicAdd(&b.hist[absorber], 1u);                                                                             \
+      if (REC) {                                                                                                    \
+        const size_t sl = b.rec_row + (size_t)(b.r_begin + (int64_t)r_cur);                                         \
+        double* o = p.rec_pts + 4 * sl;                                                                             \
+        o[2] = px; o[3] = py;                                                                                       \
+        p.rec_valid[sl] = 1;                                                                                        \
       }                                                                                                             \
-    }                                                                                                               \
-    if (retire) {                                                                                                   \
-      active = false;                                                                                               \
-      if (absorber >= 0) {                                                                                          \
-        atomicAdd(&b.hist[absorber], 1u);                                                                           \
-        if (REC) {                                                                                                  \
-          const size_t sl = b.rec_row + (size_t)(b.r_begin + (int64_t)r_cur);                                       \
-          double* o = p.rec_pts + 4 * sl;                                                                           \
-          o[2] = px; o[3] = py;                                                                                     \
-          p.rec_valid[sl] = 1;                                                                                      \
-        }                                                                                                           \
-      } else {                                                                                                      \
-        ++n_lost;                                                                                                   \
-      }                                                                                                             \
+    } else {                                                                                                        \
+      ++n_lost;                                                                                                     \
     }                                                                                                               \
   } while (0)
         if (!BILIN) {
@@ -1325,10 +1311,275 @@ __device__ __forceinline__ unsigned int queue_ray_loop(const TraceParams& p, con
   return n_lost;
 }
 
-template <bool SURF, int DEPTH, bool BILIN, bool MULTI>
+template <bool SURF, int DEPTH, bool BILIN>
 __device__ __forceinline__ unsigned int queue_dispatch(const TraceParams& p, const QueueBlock& b, bool uniform, bool rec) {
-  if (uniform) return rec ? queue_ray_loop<SURF, true, true, DEPTH, BILIN, MULTI>(p, b) : queue_ray_loop<SURF, true, false, DEPTH, BILIN, MULTI>(p, b);
-  return rec ? queue_ray_loop<SURF, false, true, DEPTH, BILIN, MULTI>(p, b) : queue_ray_loop<SURF, false, false, DEPTH, BILIN, MULTI>(p, b);
+  if (uniform) return rec ? queue_ray_loop<SURF, true, true, DEPTH, BILIN>(p, b) : queue_ray_loop<SURF, true, false, DEPTH, BILIN>(p, b);
+  return rec ? queue_ray_loop<SURF, false, true, DEPTH, BILIN>(p, b) : queue_ray_loop<SURF, false, false, DEPTH, BILIN>(p, b);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K1-QM: RTHX_MULTI_BOUNCE[_SPECULAR] on the ray queue — the analogue of method=:direct's traceSingleRay.jl:24-79 without
+// re-emission, in two phases per warp so that every phase runs on full warps:
+//   produce : (a) rays that survived an interaction ("pending": interaction point, incoming direction, the Philox words of the
+//             event) get their new direction — isotropic scattering (isotropicScatter2D.jl:1-4), diffuse reflection about the
+//             inward wall normal (sampleReflectionDirection2D.jl:5-16 + lambertSample2D) or a mirror reflection — and their next
+//             free path, one lane per ray; (b) the rest of the queue is topped up with freshly emitted rays;
+//   consume : as in queue_ray_loop, one coarse-face step per iteration for every lane that holds a ray; a ray that interacts
+//             draws its fate (one Philox call: absorbed / continues / Russian roulette, :11) right there, is tallied if absorbed
+//             and otherwise parked as a pending entry in a slot of the queue that was already consumed; the lane refills.
+// In the lock-step loop (sq_multi_loop) a warp waits for its longest event chain: 15.5 of 32 lanes on cfg3 with omega = 0.5.
+// Which lane continues which ray is irrelevant for the result: every draw is keyed by (ray id, emitter, band, call#), call#
+// 2+2n / 3+2n for event n exactly as in trace_exchange_kernel<..., MULTI>, so the tallies stay bit-identical to it.
+// Slot layout (structure of arrays over the WQ slots of a warp): px | py | dx | dy | S as doubles, rid | meta as u32;
+//   meta = event | coarse face << 14 | (pending only) edge << 23 | gas << 25; a pending entry keeps (v0.y, v0.z) in the S slot.
+// ------------------------------------------------------------------------------------------------------------
+template <bool SURF, bool UNIFORM, bool REC, int DEPTH, bool BILIN>
+__device__ __forceinline__ unsigned int queue_multi_loop(const TraceParams& p, const QueueBlock& b) {
+  constexpr int WQ = 32 * DEPTH;
+  const int lane = b.lane;
+  double* const q = b.q;                               // field f of slot s at q[f * WQ + s]
+  uint32_t* const qi = reinterpret_cast<uint32_t*>(q + 5 * WQ);   // rid at qi[s], meta at qi[WQ + s]
+  const unsigned lt_mask = (1u << lane) - 1u;
+  unsigned int n_lost = 0;
+  // in-flight ray of this lane
+  bool active = false;
+  double px = 0.0, py = 0.0, dx = 0.0, dy = 0.0, S = 0.0, acc = 0.0;
+  int c = b.c0, it = 0, event = 0;
+  uint32_t r_cur = 0;
+  // this warp's contiguous share of the block's rays (indices relative to r_begin)
+  const int64_t n_block = b.r_end - b.r_begin;
+  const int64_t per_warp = (n_block + b.n_warps - 1) / b.n_warps;
+  int64_t r_next = min(n_block, (int64_t)b.warp * per_warp);
+  const int64_t r_stop = min(n_block, r_next + per_warp);
+  int n_pend = 0;                                      // parked survivors, slots [0, n_pend); they persist across phases
+  while (true) {
+    // ---- produce ---------------------------------------------------------------------------------------------------------
+    // Both halves run on FULL warps: survivors are converted in groups of 32 (the rest stays parked for a later phase) and fresh
+    // rays are emitted in groups of 32, except when the warp's rays run out (then everything parked is converted).
+    const int64_t remaining = r_stop - r_next;
+    int n_conv = remaining > 0 ? (n_pend & ~31) : n_pend;
+    int n_fresh = (int)min((int64_t)(WQ - n_pend), remaining);
+    if ((int64_t)n_fresh < remaining) n_fresh &= ~31;
+    if (n_conv == 0 && n_fresh == 0) { n_conv = n_pend; n_fresh = (int)min((int64_t)(WQ - n_pend), remaining); }   // progress (shallow queues)
+    const int keep = n_pend - n_conv;                  // slots [0, keep) stay parked; [keep, n_pend) become ready in place
+    // (a) pending -> ready, in place, one lane per ray
+#pragma unroll 1
+    for (int s = keep + lane; s < n_pend; s += 32) {
+      const uint32_t rid = qi[s], meta = qi[WQ + s];
+      const int ev = (int)(meta & 0x3FFFu), cc = (int)((meta >> 14) & 0x1FFu), k = (int)((meta >> 23) & 3u);
+      const bool gas = (meta >> 25) & 1u;
+      const uint2 v0yz = *reinterpret_cast<const uint2*>(&q[4 * WQ + s]);       // (v0.y, v0.z) of the event's first call
+      const uint64_t ray_id = (uint64_t)(p.ray_id_offset + b.r_begin + (int64_t)rid);
+      const uint4 v1 = philox4x32_10_rk(make_uint4((uint32_t)ray_id, (uint32_t)(ray_id >> 32), b.e, b.cw | (uint32_t)(3 + 2 * ev)), p.rk);
+      double ndx, ndy;
+      if (gas) {
+        // theta = acos(2R - 1), phi = 2 pi R; with c = R - 1/2: cos = 2c, sin = 2 sqrt(1/4 - c^2)
+        const double ch = __hiloint2double((int)(0x3FF00000u | (v1.y >> 12)), (int)((v1.y << 20) | (v1.x >> 12))) - p.k_u52c;
+        ndx = sqrt_pos(fma(-ch, ch, 0.25)) * cos2pi_centered_x2(u32d_centered(v0yz.x, p.k_u32c));
+        ndy = ch + ch;
+      } else {
+        const CoarseDev& cf = b.coarse[cc];
+        const double hnx = cf.nx[k], hny = cf.ny[k];                 // outward normal of the coarse edge (= of every fine wall on it)
+        if (p.specular) {
+          const double idx_ = q[2 * WQ + s], idy_ = q[3 * WQ + s];   // incoming direction: mirror the in-plane components
+          const double dn = idx_ * hnx + idy_ * hny;
+          ndx = fma(-2.0 * dn, hnx, idx_);
+          ndy = fma(-2.0 * dn, hny, idy_);
+        } else {
+          // Lambert about the inward normal n = -hit_n with x-axis (n.y, -n.x)
+          const float cosT = __fsqrt_rn(u23(v0yz.y));
+          const float cos2 = __fmul_rn(cosT, cosT);
+          const double xdir = sqrt_pos(1.0 - (double)cos2) * cos2pi_centered((double)u23(v0yz.x) - 0.5);
+          const double zdir = (double)cosT;
+          const double nxi = -hnx, nyi = -hny;
+          ndx = nyi * xdir + nxi * zdir;
+          ndy = -nxi * xdir + nyi * zdir;
+        }
+      }
+      const double nl = neg_log_table(u52(v1.z, v1.w, p.k_u52), b.s_log);
+      q[2 * WQ + s] = ndx; q[3 * WQ + s] = ndy; q[4 * WQ + s] = UNIFORM ? nl * b.inv_beta_u : nl;
+      qi[WQ + s] = (uint32_t)(ev + 1) | ((uint32_t)cc << 14);
+    }
+    // (b) fresh rays behind them
+#pragma unroll 1
+    for (int s = lane; s < n_fresh; s += 32) {
+      const uint32_t rid = (uint32_t)(r_next + s);
+      const uint64_t ray_id = (uint64_t)(p.ray_id_offset + b.r_begin + (int64_t)rid);
+      const uint32_t c_lo = (uint32_t)ray_id, c_hi = (uint32_t)(ray_id >> 32);
+      const uint4 w0 = philox4x32_10_rk(make_uint4(c_lo, c_hi, b.e, b.cw | 0u), p.rk);
+      const uint4 w1 = philox4x32_10_rk(make_uint4(c_lo, c_hi, b.e, b.cw | 1u), p.rk);
+      double ex, ey, fx, fy, fy_m, R_S;
+      int fy_hi;
+      emit_ray_folded<SURF>(p, b.s_em, b.sel_thr, w0, w1, ex, ey, fx, fy, fy_m, fy_hi, R_S);
+      if (REC) {
+        double* o = p.rec_pts + 4 * (b.rec_row + (size_t)(b.r_begin + (int64_t)rid));
+        o[0] = ex; o[1] = ey;
+      }
+      const double nl = neg_log_table(R_S, b.s_log);
+      const int t = n_pend + s;
+      q[t] = ex; q[WQ + t] = ey; q[2 * WQ + t] = fx; q[3 * WQ + t] = fy; q[4 * WQ + t] = UNIFORM ? nl * b.inv_beta_u : nl;
+      qi[t] = rid; qi[WQ + t] = (uint32_t)b.c0 << 14;
+    }
+    const int n_valid = n_pend + n_fresh;              // ready rays: slots [keep, n_valid)
+    r_next += n_fresh;
+    n_pend = keep;
+    __syncwarp();
+    if (n_valid == keep && __ballot_sync(0xffffffffu, active) == 0u) break;   // nothing ready, nothing in flight (then nothing is parked either)
+    const bool more_fresh = r_next < r_stop;
+    // ---- consume ----------------------------------------------------------------------------------------------------------
+    int next = keep;
+    while (true) {
+      // refill: every lane without a ray takes the next unprocessed slot
+      const unsigned need = __ballot_sync(0xffffffffu, !active);
+      const int idx = next + __popc(need & lt_mask);
+      if (!active & (idx < n_valid)) {
+        px = q[idx]; py = q[WQ + idx]; dx = q[2 * WQ + idx]; dy = q[3 * WQ + idx]; S = q[4 * WQ + idx];
+        r_cur = qi[idx];
+        const uint32_t meta = qi[WQ + idx];
+        event = (int)(meta & 0x3FFFu); c = (int)(meta >> 14);
+        acc = 0.0; it = 0;
+        active = true;
+      }
+      next = min(next + __popc(need), n_valid);
+      const unsigned busy = __ballot_sync(0xffffffffu, active);
+      if (busy == 0u) break;                                           // queue dry and nothing in flight
+      // queue dry while more rays can be produced (fresh ones or parked survivors): go and produce at full occupancy once few
+      // lanes still hold a ray; those rays stay in their lanes
+      if (next >= n_valid && (more_fresh | (n_pend > 0)) && __popc(busy) <= p.queue_refill) break;
+      bool park = false;                                               // this lane's ray survived an interaction
+      uint32_t park_meta = 0u, park_y = 0u, park_z = 0u;
+      if (active) {
+        const CoarseDev& cf = b.coarse[c];
+        int k;
+        double u;
+        const bool edge = dist_face<BILIN>(cf, px, py, dx, dy, p.k_eps, u, k);
+        bool gas, ok = true;
+        double tau_b = 0.0, Sg;
+        if (UNIFORM) {
+          gas = S < u;
+          Sg = S;
+        } else {
+          const int l0 = lattice_cell<BILIN>(cf, px, py);                      // traceRay.jl:87-100
+          const int f0 = l0 < 0 ? -1 : (cf.kind == KIND_AFFINE_TRI ? __ldg(p.lattice + cf.lat_off + l0) : l0);
+          ok = f0 >= 0;
+          const double local_beta = ok ? b.beta_band[cf.fine_off + f0] : 0.0;
+          tau_b = local_beta * u;
+          gas = acc + tau_b >= S;
+          Sg = (S - acc) / local_beta;
+        }
+        const bool solid = cf.solid[k] != 0;
+        const int nc = cf.nbr[k];
+        const bool cross = ok & !gas & edge & !solid & (BILIN | (nc >= 0)) & (it < 9999);
+        const bool tallied = ok & (gas | (edge & solid));
+        const double adv = gas ? Sg - p.nudge : (solid ? u - p.nudge : u + p.nudge);
+        if (cross | tallied) {
+          px = fma(adv, dx, px);
+          py = fma(adv, dy, py);
+        }
+        bool ended = !cross;
+        if (cross) {
+          if (UNIFORM) S -= u; else acc += tau_b;
+          int nn = nc;
+          if (BILIN) { if (nn < 0) nn = find_face_generic(p, 0, px, py); }
+          if (nn >= 0) { c = nn; ++it; }
+          else ended = true;                                           // left the domain: lost, like the reference's `nothing`
+        }
+        if (ended) {
+          int absorber = -1;
+          if (tallied) {
+            const int l = lattice_cell<BILIN>(cf, px, py);
+            if (l >= 0) absorber = (gas & (cf.kind != KIND_AFFINE_TRI)) ? p.n_surfaces + cf.fine_off + l
+                                                                        : __ldg(p.abs_tab + (size_t)(cf.abs_off + l) * 5 + (gas ? 0 : 1 + k));
+          }
+          if (absorber >= 0) {
+            // absorb, or live on (traceSingleRay.jl:24-79): v0.x decision, v0.w roulette; v0.y / v0.z feed the new direction
+            if (event >= 16000) {                                      // call# is a 16-bit field
+              absorber = -1;
+            } else {
+              const uint64_t ray_id = (uint64_t)(p.ray_id_offset + b.r_begin + (int64_t)r_cur);
+              const uint4 v0 = philox4x32_10_rk(make_uint4((uint32_t)ray_id, (uint32_t)(ray_id >> 32), b.e, b.cw | (uint32_t)(2 + 2 * event)), p.rk);
+              if (event >= 1000 && u32d(v0.w, p.k_u32) > 0.8) {        // Russian roulette, traceSingleRay.jl:11
+                absorber = -1;
+              } else {
+                const double dec = u32d(v0.x, p.k_u32);
+                const double lim = absorber >= p.n_surfaces ? b.omega_band[absorber - p.n_surfaces] : b.eps_band[absorber];
+                park = absorber >= p.n_surfaces ? (dec < lim) : !(dec < lim);
+                park_meta = (uint32_t)event | ((uint32_t)c << 14) | ((uint32_t)k << 23) | (gas ? (1u << 25) : 0u);
+                park_y = v0.y; park_z = v0.z;
+              }
+            }
+          }
+          if (!park) {
+            active = false;
+            if (absorber >= 0) {
+              atomicAdd(&b.hist[absorber], 1u);
+              if (REC) {
+                const size_t sl = b.rec_row + (size_t)(b.r_begin + (int64_t)r_cur);
+                double* o = p.rec_pts + 4 * sl;
+                o[2] = px; o[3] = py;
+                p.rec_valid[sl] = 1;
+              }
+            } else {
+              ++n_lost;
+            }
+          }
+        }
+      }
+      // park the survivors in consumed slots: [0, next) while the queue still holds rays, the whole buffer once it is dry
+      const unsigned pm = __ballot_sync(0xffffffffu, park);
+      if (pm) {
+        __syncwarp();                                                  // this iteration's refill loads are done before slots are overwritten
+        const int cap = next >= n_valid ? WQ : next;
+        const int slot = n_pend + __popc(pm & lt_mask);
+        if (park) {
+          if (slot < cap) {
+            q[slot] = px; q[WQ + slot] = py; q[2 * WQ + slot] = dx; q[3 * WQ + slot] = dy;
+            *reinterpret_cast<uint2*>(&q[4 * WQ + slot]) = make_uint2(park_y, park_z);
+            qi[slot] = r_cur; qi[WQ + slot] = park_meta;
+            active = false;
+          } else {
+            // no free slot (only rays carried over a produce phase can outnumber the consumed slots): continue in the lane
+            const int k = (int)((park_meta >> 23) & 3u);
+            const uint64_t ray_id = (uint64_t)(p.ray_id_offset + b.r_begin + (int64_t)r_cur);
+            const uint4 v1 = philox4x32_10_rk(make_uint4((uint32_t)ray_id, (uint32_t)(ray_id >> 32), b.e, b.cw | (uint32_t)(3 + 2 * event)), p.rk);
+            if ((park_meta >> 25) & 1u) {
+              const double ch = __hiloint2double((int)(0x3FF00000u | (v1.y >> 12)), (int)((v1.y << 20) | (v1.x >> 12))) - p.k_u52c;
+              dx = sqrt_pos(fma(-ch, ch, 0.25)) * cos2pi_centered_x2(u32d_centered(park_y, p.k_u32c));
+              dy = ch + ch;
+            } else {
+              const CoarseDev& cf = b.coarse[c];
+              const double hnx = cf.nx[k], hny = cf.ny[k];
+              if (p.specular) {
+                const double dn = dx * hnx + dy * hny;
+                dx = fma(-2.0 * dn, hnx, dx);
+                dy = fma(-2.0 * dn, hny, dy);
+              } else {
+                const float cosT = __fsqrt_rn(u23(park_z));
+                const float cos2 = __fmul_rn(cosT, cosT);
+                const double xdir = sqrt_pos(1.0 - (double)cos2) * cos2pi_centered((double)u23(park_y) - 0.5);
+                const double zdir = (double)cosT;
+                const double nxi = -hnx, nyi = -hny;
+                dx = nyi * xdir + nxi * zdir;
+                dy = -nxi * xdir + nyi * zdir;
+              }
+            }
+            const double nl = neg_log_table(u52(v1.z, v1.w, p.k_u52), b.s_log);
+            S = UNIFORM ? nl * b.inv_beta_u : nl;
+            acc = 0.0; it = 0; ++event;
+          }
+        }
+        n_pend = min(cap, n_pend + __popc(pm));
+      }
+    }
+    __syncwarp();
+  }
+  return n_lost;
+}
+
+template <bool SURF, int DEPTH, bool BILIN>
+__device__ __forceinline__ unsigned int queue_multi_dispatch(const TraceParams& p, const QueueBlock& b, bool uniform, bool rec) {
+  if (uniform) return rec ? queue_multi_loop<SURF, true, true, DEPTH, BILIN>(p, b) : queue_multi_loop<SURF, true, false, DEPTH, BILIN>(p, b);
+  return rec ? queue_multi_loop<SURF, false, true, DEPTH, BILIN>(p, b) : queue_multi_loop<SURF, false, false, DEPTH, BILIN>(p, b);
 }
 
 // BILIN: the mesh has general convex quadrilateral faces (bilinear lattices); compiled separately so that meshes of parallelograms
@@ -1384,7 +1635,7 @@ __global__ void __launch_bounds__(256, MINB) trace_exchange_queue_kernel(const _
   QueueBlock b;
   b.coarse = reinterpret_cast<const CoarseDev*>(smem_raw);
   b.s_em = s_em; b.s_log = s_log; b.hist = hist;
-  b.q = queue + (size_t)warp * 5 * WQ;
+  b.q = queue + (size_t)warp * (MULTI ? 6 : 5) * WQ;          // MULTI: + rid / meta words per slot
   b.beta_band = beta_band;
   b.omega_band = p.omega + (size_t)band * p.n_cells; b.eps_band = p.eps + (size_t)band * p.n_surfaces;
   b.inv_beta_u = beta_u > 0.0 ? 1.0 / beta_u : CUDART_INF;
@@ -1394,7 +1645,9 @@ __global__ void __launch_bounds__(256, MINB) trace_exchange_queue_kernel(const _
   b.sel_thr = reinterpret_cast<const uint32_t*>(s_em + 15)[0];
   b.c0 = p.em_coarse[e]; b.n_warps = n_warps; b.warp = warp; b.lane = lane;
 
-  const unsigned int n_lost0 = is_surface ? queue_dispatch<true, DEPTH, BILIN, MULTI>(p, b, uniform, rec_slot >= 0) : queue_dispatch<false, DEPTH, BILIN, MULTI>(p, b, uniform, rec_slot >= 0);
+  unsigned int n_lost0;
+  if (MULTI) n_lost0 = is_surface ? queue_multi_dispatch<true, DEPTH, BILIN>(p, b, uniform, rec_slot >= 0) : queue_multi_dispatch<false, DEPTH, BILIN>(p, b, uniform, rec_slot >= 0);
+  else n_lost0 = is_surface ? queue_dispatch<true, DEPTH, BILIN>(p, b, uniform, rec_slot >= 0) : queue_dispatch<false, DEPTH, BILIN>(p, b, uniform, rec_slot >= 0);
   unsigned int n_lost = n_lost0;
 
   // ---- flush --------------------------------------------------------------------------------------------------
@@ -1404,6 +1657,7 @@ __global__ void __launch_bounds__(256, MINB) trace_exchange_queue_kernel(const _
     else atomicAdd(&p.lost[(size_t)bi * N + e], (unsigned long long)n_lost);
   }
   __syncthreads();
+  if (p.peer_counts != nullptr) { handover_row_hist(p, hist, reinterpret_cast<unsigned int*>(s_em + 15) + 1); return; }
   for (int i = threadIdx.x; i < N; i += blockDim.x) {
     const uint32_t v = hist[i];
     if (v) {
