@@ -207,9 +207,12 @@ int rthx_trace_exchange(rthx_handle* h, const rthx_trace_args* args,
  * counts_dev [n_bins*N*N] uint64, lost_dev [n_bins*N] uint64 on the handle's device (or peer-mapped).
  * zero_first: RTHX_ZERO_NONE, RTHX_ZERO_ALL (clear both buffers on the stream before the launch) or
  * RTHX_ZERO_OWN_ROWS (clear only the rows / lost entries of the emitters this call owns — for a matrix shared by
- * several ranks).  Does not synchronise; stats carries the launch geometry only.  Recording is not available on
- * this entry point. */
-enum { RTHX_ZERO_NONE = 0, RTHX_ZERO_ALL = 1, RTHX_ZERO_OWN_ROWS = 2 };
+ * several ranks), optionally OR-ed with RTHX_DEST_PEER: the buffers live in ANOTHER device's memory.  A peer-mapped pointer
+ * of the same process is recognised by itself; a CUDA-IPC mapping (rthx_shared_open) reports the mapping device, so its
+ * callers must say so.  For a peer matrix the chunks of a row add up in a local staging row and the finished row is handed
+ * over with plain coalesced stores — no atomics on NVLink, no clearing of the peer rows.                              [0.3]
+ * Does not synchronise; stats carries the launch geometry only.  Recording is not available on this entry point. */
+enum { RTHX_ZERO_NONE = 0, RTHX_ZERO_ALL = 1, RTHX_ZERO_OWN_ROWS = 2, RTHX_DEST_PEER = 16 };
 int rthx_trace_exchange_device(rthx_handle* h, const rthx_trace_args* args,
                                void* counts_dev, void* lost_dev, void* stream,
                                int zero_first, rthx_stats* stats);

@@ -10,6 +10,7 @@ RTHX_MULTI_BOUNCE_SPECULAR = 2
 RTHX_LOCATOR_AUTO = 0
 RTHX_LOCATOR_GENERIC = 1
 RTHX_ZERO_NONE, RTHX_ZERO_ALL, RTHX_ZERO_OWN_ROWS = 0, 1, 2
+RTHX_DEST_PEER = 16      # OR into zero_first: the matrix lives in another device's memory (CUDA IPC mapping)
 
 c_i32p = C.POINTER(C.c_int32)
 c_f64p = C.POINTER(C.c_double)

@@ -225,6 +225,12 @@ void build_grid(const Poly* faces, int n, int poly_base, FaceSetDev& fs, std::ve
   for (size_t b = 0; b < nb; ++b) bstart.push_back((int32_t)(items0 + (size_t)cnt[b + 1]));
 }
 
+// packed record of the generic locator (point_in_rec, rthx_kernels.cu): bbox, vx[4], vy[4]; a triangle repeats vertex 0 in slot 3
+void poly_record(const Poly& p, double* rec) {
+  rec[0] = p.bb[0]; rec[1] = p.bb[1]; rec[2] = p.bb[2]; rec[3] = p.bb[3];
+  for (int i = 0; i < 4; ++i) { const int k = i < p.n ? i : 0; rec[4 + i] = p.vx[k]; rec[8 + i] = p.vy[k]; }
+}
+
 bool close_pt(double ax, double ay, double bx, double by, double tol) { return std::fabs(ax - bx) <= tol && std::fabs(ay - by) <= tol; }
 
 // Try to recognise the fine cells [f0, f0 + n_fine) of coarse face `cp` as the lattice of meshQuad / meshTriangle (affine for
@@ -391,7 +397,7 @@ void give_pinned(unsigned char* p, size_t cap) {
 struct HostImage {
   unsigned char* data = nullptr;
   size_t cap = 0, bytes = 0, total = 0;      // pinned capacity, image bytes, arena bytes incl. the device-only scratch regions
-  size_t o_coarse = 0, o_sets = 0, o_bstart = 0, o_bitems = 0, o_nv = 0, o_pvx = 0, o_pvy = 0, o_mid = 0, o_vol = 0, o_surf = 0, o_beta = 0,
+  size_t o_coarse = 0, o_sets = 0, o_bstart = 0, o_bitems = 0, o_crec = 0, o_nv = 0, o_pvx = 0, o_pvy = 0, o_mid = 0, o_vol = 0, o_surf = 0, o_beta = 0,
          o_ub = 0, o_lat = 0, o_abs = 0, o_omega = 0, o_eps = 0, o_ec = 0, o_ew = 0, o_eco = 0, o_bins = 0, o_rec = 0, o_lost = 0;
   int nc = 0, ncell = 0, ns = 0, N = 0, nb = 0, n_affine = 0, n_bilinear = 0;
   bool has_eps = false, nbr_complete = true, needs_generic = false;
@@ -530,6 +536,7 @@ int prepare_mesh(const rthx_mesh* m, std::shared_ptr<HostImage>& out, std::strin
   Layout L;
   im->o_coarse = L.add(sizeof(CoarseDev) * coarse.size()); im->o_sets = L.add(sizeof(FaceSetDev) * sets.size());
   im->o_bstart = L.add(4 * bstart.size()); im->o_bitems = L.add(4 * bitems.size());
+  im->o_crec = L.add(96 * (size_t)nc);
   im->o_nv = L.add(4 * npoly); im->o_pvx = L.add(32 * npoly); im->o_pvy = L.add(32 * npoly);
   im->o_mid = L.add(16 * (size_t)ncell); im->o_vol = L.add(8 * (size_t)ncell); im->o_surf = L.add(16 * (size_t)ncell);
   im->o_beta = L.add(8 * (size_t)nb * ncell); im->o_ub = L.add(8 * (size_t)nb);
@@ -547,6 +554,7 @@ int prepare_mesh(const rthx_mesh* m, std::shared_ptr<HostImage>& out, std::strin
   std::memcpy(im->at<FaceSetDev>(im->o_sets), sets.data(), sizeof(FaceSetDev) * sets.size());
   std::memcpy(im->at<int32_t>(im->o_bstart), bstart.data(), 4 * bstart.size());
   if (!bitems.empty()) std::memcpy(im->at<int32_t>(im->o_bitems), bitems.data(), 4 * bitems.size());
+  for (int c = 0; c < nc; ++c) poly_record(cpolys[c], im->at<double>(im->o_crec) + 12 * (size_t)c);
   std::memcpy(im->at<int32_t>(im->o_lat), lattice.data(), 4 * lattice.size());
   std::memcpy(im->at<int32_t>(im->o_abs), abs_tab.data(), 4 * abs_tab.size());
   {
@@ -683,6 +691,9 @@ int create_on_device(rthx_handle** out, const std::shared_ptr<HostImage>& im, in
   P.bucket_start = (const int32_t*)(b8 + im->o_bstart); P.bucket_items = (const int32_t*)(b8 + im->o_bitems);
   P.poly_nv = (const int32_t*)(b8 + im->o_nv); P.poly_vx = (const double*)(b8 + im->o_pvx); P.poly_vy = (const double*)(b8 + im->o_pvy);
   P.poly_nx = nullptr; P.poly_ny = nullptr;      // per-polygon normals belong to the generic tables (ensure_generic)
+  // packed records: only those of the coarse polygons (indices >= n_cells, the coarse-set locator of the general queue variant)
+  // exist until the generic tables are built — the base pointer is offset accordingly and never dereferenced below n_cells
+  P.poly_rec = (const double*)(b8 + im->o_crec) - 12 * (size_t)im->ncell;
   P.cell_mid = (const double*)(b8 + im->o_mid); P.cell_volume = (const double*)(b8 + im->o_vol);
   P.cell_surf_id = (const int32_t*)(b8 + im->o_surf); P.beta = (const double*)(b8 + im->o_beta); P.uniform_beta = (const double*)(b8 + im->o_ub);
   P.omega = (const double*)(b8 + im->o_omega); P.eps = (const double*)(b8 + im->o_eps);
@@ -756,11 +767,13 @@ static int ensure_generic(rthx_handle* h) {
   std::vector<int32_t> bstart, bitems;
   build_grid(&polys[ncell], nc, ncell, sets[0], bstart, bitems);
   for (int c = 0; c < nc; ++c) build_grid(&polys[im.fine_off[c]], im.fine_off[c + 1] - im.fine_off[c], im.fine_off[c], sets[1 + c], bstart, bitems);
-  std::vector<double> pnx(polys.size() * 4), pny(polys.size() * 4);
-  for (size_t i = 0; i < polys.size(); ++i)
+  std::vector<double> pnx(polys.size() * 4), pny(polys.size() * 4), recs(polys.size() * 12);
+  for (size_t i = 0; i < polys.size(); ++i) {
     for (int k = 0; k < 4; ++k) { pnx[4 * i + k] = polys[i].nx[k]; pny[4 * i + k] = polys[i].ny[k]; }
+    poly_record(polys[i], recs.data() + 12 * i);
+  }
   Arena A;
-  const size_t o_sets = A.add(sets), o_bstart = A.add(bstart), o_bitems = A.add(bitems), o_pnx = A.add(pnx), o_pny = A.add(pny);
+  const size_t o_sets = A.add(sets), o_bstart = A.add(bstart), o_bitems = A.add(bitems), o_pnx = A.add(pnx), o_pny = A.add(pny), o_rec = A.add(recs);
   CU(h, cudaSetDevice(h->device));
   if (h->generic_cap < A.total) {
     cudaFree(h->generic_arena);
@@ -773,6 +786,7 @@ static int ensure_generic(rthx_handle* h) {
   TraceParams& P = h->base;
   P.sets = (const FaceSetDev*)(b8 + o_sets); P.bucket_start = (const int32_t*)(b8 + o_bstart); P.bucket_items = (const int32_t*)(b8 + o_bitems);
   P.poly_nx = (const double*)(b8 + o_pnx); P.poly_ny = (const double*)(b8 + o_pny);
+  P.poly_rec = (const double*)(b8 + o_rec);
   h->mesh_bytes = im.bytes + A.host.size();
   h->generic_ready = true;
   return RTHX_OK;
@@ -1023,7 +1037,9 @@ int enqueue_trace(rthx_handle* h, const rthx_trace_args* a, int rank, int world,
   // A matrix in peer memory (fused multi-GPU flush) is never the target of reductions: the chunks of a row add up in a local
   // compact staging matrix and the finished row is handed over with plain stores (flush_row_hist) — so the peer rows need no
   // clearing either.  Without the shared-memory histogram (N > ~57 k) the old path stays: system-scope atomics into zeroed rows.
-  bool peer = false;
+  // (a CUDA-IPC mapping reports the mapping device, not the owner: such callers say so with RTHX_DEST_PEER)
+  bool peer = (zero_first & RTHX_DEST_PEER) != 0;
+  zero_first &= ~RTHX_DEST_PEER;
   {
     cudaPointerAttributes pa;
     if (counts && cudaPointerGetAttributes(&pa, counts) == cudaSuccess && pa.type == cudaMemoryTypeDevice && pa.device != h->device) peer = true;

@@ -56,6 +56,8 @@ struct TraceParams {
   const double* poly_vy;
   const double* poly_nx;       // unit outward normals per polygon edge
   const double* poly_ny;
+  const double* poly_rec;      // [n_poly*12] packed records of the generic locator: bbox (xmin, xmax, ymin, ymax), vx[4], vy[4] (a triangle repeats
+                               // vertex 0 in slot 3).  Until the generic tables are built only the coarse polygons' records exist (indices >= n_cells).
   const double* cell_mid;      // [n_cells*2]
   const double* cell_volume;   // [n_cells]
   const int32_t* cell_surf_id; // [n_cells*4]

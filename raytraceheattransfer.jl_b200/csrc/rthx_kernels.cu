@@ -219,39 +219,54 @@ __device__ __forceinline__ double dist_fast(const CoarseDev& f, double px, doubl
   return bd > 0.0 ? div_pos(bn, bd) : CUDART_INF;
 }
 
-// Faithful distToSurface2D on an arbitrary polygon of the generic tables (used by the generic locator for the
-// wall index of a fine cell, traceRay.jl:51).
+// distToSurface2D on an arbitrary polygon of the generic tables, index of the nearest edge only (the wall of a fine cell a ray
+// ends on, traceRay.jl:51): u_i = ((v_i - p).n_i)/(d.n_i) over the edges with |d.n_i| >= 1e-10 and u_i > 0, first index on ties.
+// The argmin runs on cross-multiplied fractions — no division (the faithful form divided once per edge).
 __device__ __forceinline__ int wall_of_poly(const TraceParams& p, int poly, double px, double py, double dx, double dy) {
   const int nv = p.poly_nv[poly];
-  double best = CUDART_INF;
+  double bn = 1.0, bd = 0.0;   // best |num| / |den|; bd == 0: no candidate yet
   int bi = 0;
-  for (int i = 0; i < nv; ++i) {
-    const double nx = p.poly_nx[poly * 4 + i], ny = p.poly_ny[poly * 4 + i];
-    const double den = dx * nx + dy * ny;
-    double u = CUDART_INF;
-    if (fabs(den) >= 1e-10) u = ((p.poly_vx[poly * 4 + i] - px) * nx + (p.poly_vy[poly * 4 + i] - py) * ny) / den;
-    if (u <= 0.0) u = CUDART_INF;
-    if (u < best) { best = u; bi = i; }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (i < nv) {
+      const double nx = p.poly_nx[poly * 4 + i], ny = p.poly_ny[poly * 4 + i];
+      const double den = dx * nx + dy * ny;
+      const double num = (p.poly_vx[poly * 4 + i] - px) * nx + (p.poly_vy[poly * 4 + i] - py) * ny;
+      const double an = fabs(num), ad = fabs(den);
+      const bool better = (ad >= 1e-10) & (num * den > 0.0) & (an * bd < bn * ad);
+      bn = better ? an : bn; bd = better ? ad : bd; bi = better ? i : bi;
+    }
   }
   return bi;
 }
 
-// pointInPolygonFast2D, findFace2D.jl:77-101 (crossing number).
-__device__ __forceinline__ bool point_in_poly(const TraceParams& p, int poly, double px, double py) {
-  const int nv = p.poly_nv[poly];
-  bool inside = false;
-  int j = nv - 1;
-  for (int i = 0; i < nv; ++i) {
-    const double xi = p.poly_vx[poly * 4 + i], yi = p.poly_vy[poly * 4 + i];
-    const double xj = p.poly_vx[poly * 4 + j], yj = p.poly_vy[poly * 4 + j];
-    if ((yi > py) != (yj > py)) {
-      const double slope = (xj - xi) / (yj - yi);
-      const double ix = xi + slope * (py - yi);
-      if (px < ix) inside = !inside;
-    }
-    j = i;
+// pointInPolygonFast2D, findFace2D.jl:77-101 (crossing number) on a packed polygon record
+//   rec = { xmin, xmax, ymin, ymax, vx[4], vy[4] }   (12 doubles; a triangle repeats its first vertex in slot 3: the zero-length edge
+//                                                      never straddles py, so four edges serve both kinds without a count)
+// Two things differ from the reference's arithmetic, both exact except on a null set (a point within rounding of an edge):
+//   * bounding-box prefilter: the ~8 candidates of a bucket that do not contain the point are rejected by four compares; a point
+//     the crossing test would accept lies inside the box;
+//   * the crossing test "px < xi + (xj-xi)/(yj-yi) (py-yi)" is evaluated without the division:
+//     t = (px-xi)(yj-yi) - (xj-xi)(py-yi) has the sign of (px - ix)(yj-yi), so the edge is crossed iff t (yj-yi) < 0.
+// The CPU oracle keeps the reference's form; the exact-parity tests bound the difference (<= 2e-6 of the rays).
+__device__ __forceinline__ bool point_in_rec(const double* __restrict__ rec, double px, double py) {
+  const double2 bx = __ldg(reinterpret_cast<const double2*>(rec)), by = __ldg(reinterpret_cast<const double2*>(rec) + 1);
+  if (!((px >= bx.x) & (px <= bx.y) & (py >= by.x) & (py <= by.y))) return false;
+  const double2 x01 = __ldg(reinterpret_cast<const double2*>(rec) + 2), x23 = __ldg(reinterpret_cast<const double2*>(rec) + 3);
+  const double2 y01 = __ldg(reinterpret_cast<const double2*>(rec) + 4), y23 = __ldg(reinterpret_cast<const double2*>(rec) + 5);
+  const double vx[4] = {x01.x, x01.y, x23.x, x23.y}, vy[4] = {y01.x, y01.y, y23.x, y23.y};
+  unsigned inside = 0u;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int j = (i + 3) & 3;
+    const double xi = vx[i], yi = vy[i], xj = vx[j], yj = vy[j];
+    const bool straddle = (yi > py) != (yj > py);
+    const double dyv = yj - yi;
+    const double t = fma(px - xi, dyv, -((xj - xi) * (py - yi)));
+    const bool crossed = straddle & (t != 0.0) & (((__double2hiint(t) ^ __double2hiint(dyv)) < 0));
+    inside ^= crossed ? 1u : 0u;
   }
-  return inside;
+  return inside != 0u;
 }
 
 // findFaceUniformGrid2D, findFace2D.jl:2-27: bucket of the uniform grid, first face passing the PIP test.
@@ -262,10 +277,11 @@ __device__ __noinline__ int find_face_generic(const TraceParams& p, int set, dou
   const double fi = floor((px - fs.ox) * fs.inv_cell), fj = floor((py - fs.oy) * fs.inv_cell);
   if (!(fi >= 0.0 && fi < (double)fs.nx && fj >= 0.0 && fj < (double)fs.ny)) return -1;
   const int b = fs.bucket_off + (int)fi + (int)fj * fs.nx;
-  const int k0 = p.bucket_start[b], k1 = p.bucket_start[b + 1];
+  const int k0 = __ldg(p.bucket_start + b), k1 = __ldg(p.bucket_start + b + 1);
+  const double* recs = p.poly_rec + (size_t)fs.poly_base * 12;
   for (int k = k0; k < k1; ++k) {
-    const int f = p.bucket_items[k];
-    if (point_in_poly(p, fs.poly_base + f, px, py)) return f;
+    const int f = __ldg(p.bucket_items + k);
+    if (point_in_rec(recs + (size_t)f * 12, px, py)) return f;
   }
   return -1;
 }
@@ -1691,7 +1707,7 @@ static TraceKernel kernel_variant(bool hist, bool fast, int minb, bool multi, bo
     return fast ? (TraceKernel)trace_exchange_kernel<false, true, 2, true, false> : (TraceKernel)trace_exchange_kernel<false, false, 2, true, false>;
   }
   if (!hist) return fast ? (TraceKernel)trace_exchange_kernel<false, true, 2, false, false> : (TraceKernel)trace_exchange_kernel<false, false, 2, false, false>;
-  if (!fast) return (TraceKernel)trace_exchange_kernel<true, false, 2, false, false>;
+  if (!fast) return (TraceKernel)trace_exchange_kernel<true, false, 3, false, false>;     // generic locator: 80 registers, 3 blocks per SM
   switch (minb) {
     case 3: return (TraceKernel)trace_exchange_kernel<true, true, 3, false, false>;
     case 4: return (TraceKernel)trace_exchange_kernel<true, true, 4, false, false>;

@@ -21,7 +21,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-from ._abi import RTHX_ZERO_ALL, RTHX_ZERO_OWN_ROWS
+from ._abi import RTHX_ZERO_ALL, RTHX_ZERO_OWN_ROWS, RTHX_DEST_PEER
 
 
 def owned_emitters(n_elements: int, rank: int, world: int) -> np.ndarray:
@@ -118,8 +118,10 @@ class ShardedTracer:
         if s >= 2:
             # matrix b held step s-2: wait until rank 0 has released it (consumed counter >= s-1)
             self._check(self._L.rthx_flag_wait(C.c_void_p(fl + 8 * W), 1, s - 1, 30.0, C.c_void_p(fl + 8 * (W + 1)), C.c_void_p(stream)))
+        # ranks other than 0 see the matrix through a CUDA-IPC mapping: say so, the library then stages rows locally and hands them over
         st = self.tracer.trace_device(rays_per_emitter, self._counts_ptrs[b], self._lost_ptrs[b], stream=stream,
-                                      zero_first=RTHX_ZERO_OWN_ROWS, emitter_rank=self.rank, emitter_world=self.world, **kw)
+                                      zero_first=RTHX_ZERO_OWN_ROWS | (RTHX_DEST_PEER if self.rank != 0 else 0),
+                                      emitter_rank=self.rank, emitter_world=self.world, **kw)
         self._check(self._L.rthx_flag_signal(C.c_void_p(fl + 8 * self.rank), s + 1, C.c_void_p(stream)))
         return st
 

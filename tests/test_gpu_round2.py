@@ -179,10 +179,11 @@ def test_public_call_devices_keyword(rthx_mod, cuda_lib):
 @pytest.mark.parametrize("row_chunks", [1, 0, 5])
 def test_row_handover_flush_on_one_gpu(rthx_mod, cuda_lib, monkeypatch, row_chunks):
     """The flush used for matrices in peer memory — chunks add up in a local staging row, the last chunk hands the finished row
-    over with plain stores (row_chunks == 1: written out directly) — exercised on one GPU through RTHX_FLUSH_SYSTEM=1, two
-    interleaved "ranks" filling one matrix with stale contents.  Bit-identical to the plain trace."""
+    over with plain stores (row_chunks == 1: written out directly) — exercised on one GPU through RTHX_DEST_PEER (what a rank says
+    about a CUDA-IPC mapping of rank 0's matrix), two interleaved "ranks" filling one matrix with stale contents.  Bit-identical to
+    the plain trace."""
     import torch
-    from rthx._abi import RTHX_ZERO_OWN_ROWS
+    from rthx._abi import RTHX_ZERO_OWN_ROWS, RTHX_DEST_PEER
     flat = rthx_mod.flatten_domain(rthx_mod.meshes.cfg4(Ndim=13, n_bins=2))
     tr = rthx_mod.DeviceTracer(flat, device=0)
     N = tr.n_elements
@@ -190,10 +191,9 @@ def test_row_handover_flush_on_one_gpu(rthx_mod, cuda_lib, monkeypatch, row_chun
     dev = torch.device("cuda", 0)
     counts = torch.full((2, N, N), 7, dtype=torch.int64, device=dev)
     lost = torch.full((2, N), 7, dtype=torch.int64, device=dev)
-    monkeypatch.setenv("RTHX_FLUSH_SYSTEM", "1")
     stream = torch.cuda.current_stream(dev).cuda_stream
     for rank in (1, 0):
-        st = tr.trace_device(30000, counts.data_ptr(), lost.data_ptr(), stream=stream, zero_first=RTHX_ZERO_OWN_ROWS, seed=31, bins=[1, 0],
+        st = tr.trace_device(30000, counts.data_ptr(), lost.data_ptr(), stream=stream, zero_first=RTHX_ZERO_OWN_ROWS | RTHX_DEST_PEER, seed=31, bins=[1, 0],
                              emitter_rank=rank, emitter_world=2, row_chunks=row_chunks)
     torch.cuda.synchronize(dev)
     if row_chunks:
