@@ -325,8 +325,12 @@ int rthx_solve_grey(rthx_handle* h, const rthx_solve_args* args, double* j_out, 
  * (test/test_2d_diffusion.jl:64) never move their N^2 zeros.  rthx_trace_exchange accepts counts_out == NULL for
  * callers that only want this view.
  *   rthx_counts_nnz : number of non-zeros of traced bin `bin` (also prepares the row pointers on the device);
- *   rthx_counts_csr : row_ptr [N+1], cols [nnz], vals [nnz] (may be NULL), F_vals [nnz] = count / row total (may be
- *                     NULL; this is the row-normalised F of row_normalize!, :161-169), row_lost not included. */
+ *   rthx_counts_csr : row_ptr [R+1], cols [nnz], vals [nnz] (may be NULL), F_vals [nnz] = count / row total (may be
+ *                     NULL; this is the row-normalised F of row_normalize!, :161-169), row_lost not included.
+ * R = N after a trace of all emitters.  After a SHARDED trace (emitter_world > 1) the resident rows are those the call owned,
+ * R = ceil((N - emitter_rank) / emitter_world), row y being element emitter_rank + y * emitter_world: meshes whose dense
+ * 8 N^2-byte matrix does not fit (N >> 57 k elements) are traced as a sequence of such row tiles on one device, each read out
+ * as CSR and merged on the host (raytraceheattransfer.jl_b200/_lib.py trace_row_tiles).                               [0.3] */
 int rthx_counts_nnz(rthx_handle* h, int bin, int64_t* nnz_out);
 int rthx_counts_csr(rthx_handle* h, int bin, int64_t* row_ptr, int32_t* cols, uint64_t* vals, double* F_vals);
 /* The same counts as the three arrays of a compressed-sparse-COLUMN matrix — the memory layout of the SparseMatrixCSC{Float64,Int}

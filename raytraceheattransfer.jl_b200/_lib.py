@@ -297,6 +297,7 @@ class DeviceTracer:
         self._check(self._L.rthx_trace_exchange(self._h, C.byref(args), counts.ctypes.data_as(c_u64p) if counts is not None else None,
                                                 lost.ctypes.data_as(c_u64p), C.byref(rec) if rec else None,
                                                 C.byref(st)))
+        self._last_shard = (int(args.emitter_rank), int(args.emitter_world))     # rows resident on the device: e = rank + y * world
         out = dict(counts=counts.reshape(nb, N, N) if counts is not None else None, lost=lost, stats=st.as_dict())
         if rec is not None:
             out["origins"] = origins[: rec.n_recorded].copy()
@@ -316,11 +317,14 @@ class DeviceTracer:
 
     def counts_csr(self, bin: int = 0, values: bool = True, normalised: bool = True):
         """CSR read-out of the counts resident on the device (rthx_counts_nnz / rthx_counts_csr): returns
-        (row_ptr [N+1] i64, cols [nnz] i32, counts [nnz] u64 or None, F_vals [nnz] f64 = count/row total or None)."""
+        (row_ptr [R+1] i64, cols [nnz] i32, counts [nnz] u64 or None, F_vals [nnz] f64 = count/row total or None); R = N after a
+        plain trace, the number of owned rows (elements rank + y * world) after a sharded one."""
         nnz = C.c_int64(0)
         self._check(self._L.rthx_counts_nnz(self._h, int(bin), C.byref(nnz)))
         N, k = self.n_elements, max(1, nnz.value)
-        row_ptr = np.empty(N + 1, np.int64)
+        rank, world = getattr(self, "_last_shard", (0, 1))
+        R = (N - rank + world - 1) // world          # after a sharded trace (a row tile) the view covers the rows e = rank + y * world
+        row_ptr = np.empty(R + 1, np.int64)
         cols = np.empty(k, np.int32)
         vals = np.empty(k, np.uint64) if values else None
         fv = np.empty(k, np.float64) if normalised else None
@@ -469,11 +473,53 @@ def trace_multi(tracers: Sequence[DeviceTracer], rays_per_emitter: int, counts_o
     if rc != 0:
         msg = L.rthx_last_error(tracers[0]._h)
         raise RthxError(f"rthx_trace_exchange_multi failed ({rc}): {msg.decode() if msg else ''}")
+    tracers[0]._last_shard = (0, 1)
     out = dict(counts=counts.reshape(nb, N, N) if counts is not None else None, lost=lost, stats=st.as_dict())
     if rec is not None:
         out["origins"] = origins[: rec.n_recorded].copy()
         out["endpoints"] = endpoints[: rec.n_recorded].copy()
     return out
+
+
+def trace_row_tiles(tracer: DeviceTracer, rays_per_emitter: int, n_tiles: int, **kw):
+    """Exchange factors of a mesh whose dense 8 N^2-byte count matrix does not fit (N >> 57 k elements): the
+    emitter rows are traced in `n_tiles` interleaved tiles (rows e = t (mod n_tiles) — the multi-GPU partition, run in sequence on
+    one device), each tile's counts stay on the device and only their non-zeros come back (rthx_counts_csr); the tiles are merged
+    into ONE row-normalised CSR matrix.  Counts are those of the untiled trace bit for bit (the Philox stream is keyed by ray
+    id and emitter).  Returns a list of (row_ptr [N+1], cols, F_vals) per traced bin, plus lost [nb, N] and chi per bin."""
+    N = tracer.n_elements
+    n_tiles = max(1, min(int(n_tiles), N))
+    bins = kw.get("bins", (0,))
+    nb = len(bins)
+    nnz_row = [np.zeros(N, np.int64) for _ in range(nb)]
+    parts = [[None] * n_tiles for _ in range(nb)]
+    lost = np.zeros((nb, N), np.uint64)
+    chi = np.zeros(nb)
+    for t in range(n_tiles):
+        out = tracer.trace(rays_per_emitter, dense=False, emitter_rank=t, emitter_world=n_tiles, **kw)
+        stats = out["stats"]
+        lost += out["lost"]
+        for k in range(nb):
+            chi[k] += tracer.counts_stats(k)[1]
+            rp, cols, _, fv = tracer.counts_csr(k, values=False, normalised=True)
+            nnz_row[k][t::n_tiles] = np.diff(rp)
+            parts[k][t] = (rp, cols.copy(), fv.copy())
+    mats = []
+    for k in range(nb):
+        row_ptr = np.zeros(N + 1, np.int64)
+        np.cumsum(nnz_row[k], out=row_ptr[1:])
+        cols = np.empty(int(row_ptr[-1]), np.int32)
+        vals = np.empty(int(row_ptr[-1]), np.float64)
+        for t in range(n_tiles):
+            rp, c_t, f_t = parts[k][t]
+            rows = np.arange(t, N, n_tiles)
+            lens = np.diff(rp)
+            # destination of every entry of the tile: start of its global row + offset inside the row
+            dst = np.repeat(row_ptr[rows] - rp[:-1], lens) + np.arange(int(rp[-1]), dtype=np.int64)
+            cols[dst] = c_t
+            vals[dst] = f_t
+        mats.append((row_ptr, cols, vals))
+    return dict(csr=mats, lost=lost, chi=chi, stats=stats)
 
 
 class SharedDeviceBuffer:

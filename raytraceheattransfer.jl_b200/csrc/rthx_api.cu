@@ -71,7 +71,8 @@ struct rthx_handle : DevRes {
   bool fast_ok = false;        // every coarse face affine + complete neighbour table + descriptors fit in smem
   size_t mesh_bytes = 0;
   TraceParams base{};          // mesh pointers filled once
-  int last_trace_bins = 0; size_t last_trace_rows = 0;
+  int last_trace_bins = 0; size_t last_trace_rows = 0;    // resident counts: bins, rows per bin (N, or the rows of a shard)
+  int last_rank = 0, last_world = 1;                      // ... row y of the resident matrix is element last_rank + y * last_world
   int smooth_n = 0; size_t smooth_ldx = 0;                // F_smooth resident in smooth_X after rthx_smooth_F (0: none)
   int csr_bin = -1; long long csr_total = 0;              // bin whose row pointers are prepared on the device
   int csc_bin = -1;                                       // bin whose column pointers are prepared on the device
@@ -397,7 +398,7 @@ void give_pinned(unsigned char* p, size_t cap) {
 struct HostImage {
   unsigned char* data = nullptr;
   size_t cap = 0, bytes = 0, total = 0;      // pinned capacity, image bytes, arena bytes incl. the device-only scratch regions
-  size_t o_coarse = 0, o_sets = 0, o_bstart = 0, o_bitems = 0, o_crec = 0, o_nv = 0, o_pvx = 0, o_pvy = 0, o_mid = 0, o_vol = 0, o_surf = 0, o_beta = 0,
+  size_t o_coarse = 0, o_sets = 0, o_bstart = 0, o_bitems = 0, o_bbb = 0, o_crec = 0, o_nv = 0, o_pvx = 0, o_pvy = 0, o_mid = 0, o_vol = 0, o_surf = 0, o_beta = 0,
          o_ub = 0, o_lat = 0, o_abs = 0, o_omega = 0, o_eps = 0, o_ec = 0, o_ew = 0, o_eco = 0, o_bins = 0, o_rec = 0, o_lost = 0;
   int nc = 0, ncell = 0, ns = 0, N = 0, nb = 0, n_affine = 0, n_bilinear = 0;
   bool has_eps = false, nbr_complete = true, needs_generic = false;
@@ -536,7 +537,7 @@ int prepare_mesh(const rthx_mesh* m, std::shared_ptr<HostImage>& out, std::strin
   Layout L;
   im->o_coarse = L.add(sizeof(CoarseDev) * coarse.size()); im->o_sets = L.add(sizeof(FaceSetDev) * sets.size());
   im->o_bstart = L.add(4 * bstart.size()); im->o_bitems = L.add(4 * bitems.size());
-  im->o_crec = L.add(96 * (size_t)nc);
+  im->o_crec = L.add(96 * (size_t)nc); im->o_bbb = L.add(32 * bitems.size());
   im->o_nv = L.add(4 * npoly); im->o_pvx = L.add(32 * npoly); im->o_pvy = L.add(32 * npoly);
   im->o_mid = L.add(16 * (size_t)ncell); im->o_vol = L.add(8 * (size_t)ncell); im->o_surf = L.add(16 * (size_t)ncell);
   im->o_beta = L.add(8 * (size_t)nb * ncell); im->o_ub = L.add(8 * (size_t)nb);
@@ -555,6 +556,7 @@ int prepare_mesh(const rthx_mesh* m, std::shared_ptr<HostImage>& out, std::strin
   std::memcpy(im->at<int32_t>(im->o_bstart), bstart.data(), 4 * bstart.size());
   if (!bitems.empty()) std::memcpy(im->at<int32_t>(im->o_bitems), bitems.data(), 4 * bitems.size());
   for (int c = 0; c < nc; ++c) poly_record(cpolys[c], im->at<double>(im->o_crec) + 12 * (size_t)c);
+  for (size_t k = 0; k < bitems.size(); ++k) std::memcpy(im->at<double>(im->o_bbb) + 4 * k, cpolys[bitems[k]].bb, 32);   // set 0 only: items are coarse faces
   std::memcpy(im->at<int32_t>(im->o_lat), lattice.data(), 4 * lattice.size());
   std::memcpy(im->at<int32_t>(im->o_abs), abs_tab.data(), 4 * abs_tab.size());
   {
@@ -689,6 +691,7 @@ int create_on_device(rthx_handle** out, const std::shared_ptr<HostImage>& im, in
   unsigned char* b8 = static_cast<unsigned char*>(h->arena);
   P.coarse = (const CoarseDev*)(b8 + im->o_coarse); P.sets = (const FaceSetDev*)(b8 + im->o_sets);
   P.bucket_start = (const int32_t*)(b8 + im->o_bstart); P.bucket_items = (const int32_t*)(b8 + im->o_bitems);
+  P.bucket_bb = (const double*)(b8 + im->o_bbb);
   P.poly_nv = (const int32_t*)(b8 + im->o_nv); P.poly_vx = (const double*)(b8 + im->o_pvx); P.poly_vy = (const double*)(b8 + im->o_pvy);
   P.poly_nx = nullptr; P.poly_ny = nullptr;      // per-polygon normals belong to the generic tables (ensure_generic)
   // packed records: only those of the coarse polygons (indices >= n_cells, the coarse-set locator of the general queue variant)
@@ -772,8 +775,16 @@ static int ensure_generic(rthx_handle* h) {
     for (int k = 0; k < 4; ++k) { pnx[4 * i + k] = polys[i].nx[k]; pny[4 * i + k] = polys[i].ny[k]; }
     poly_record(polys[i], recs.data() + 12 * i);
   }
+  // bounding boxes next to the bucket lists: item k of set s names polygon poly_base(s) + bitems[k]
+  std::vector<double> bbb(bitems.size() * 4);
+  for (size_t sidx = 0; sidx < sets.size(); ++sidx) {
+    const FaceSetDev& fs = sets[sidx];
+    const size_t k0 = (size_t)bstart[fs.bucket_off], k1 = (size_t)bstart[(size_t)fs.bucket_off + (size_t)fs.nx * fs.ny];
+    for (size_t k = k0; k < k1; ++k) std::memcpy(&bbb[4 * k], polys[(size_t)fs.poly_base + bitems[k]].bb, 32);
+  }
   Arena A;
-  const size_t o_sets = A.add(sets), o_bstart = A.add(bstart), o_bitems = A.add(bitems), o_pnx = A.add(pnx), o_pny = A.add(pny), o_rec = A.add(recs);
+  const size_t o_sets = A.add(sets), o_bstart = A.add(bstart), o_bitems = A.add(bitems), o_pnx = A.add(pnx), o_pny = A.add(pny), o_rec = A.add(recs),
+               o_bbb = A.add(bbb);
   CU(h, cudaSetDevice(h->device));
   if (h->generic_cap < A.total) {
     cudaFree(h->generic_arena);
@@ -786,7 +797,7 @@ static int ensure_generic(rthx_handle* h) {
   TraceParams& P = h->base;
   P.sets = (const FaceSetDev*)(b8 + o_sets); P.bucket_start = (const int32_t*)(b8 + o_bstart); P.bucket_items = (const int32_t*)(b8 + o_bitems);
   P.poly_nx = (const double*)(b8 + o_pnx); P.poly_ny = (const double*)(b8 + o_pny);
-  P.poly_rec = (const double*)(b8 + o_rec);
+  P.poly_rec = (const double*)(b8 + o_rec); P.bucket_bb = (const double*)(b8 + o_bbb);
   h->mesh_bytes = im.bytes + A.host.size();
   h->generic_ready = true;
   return RTHX_OK;
@@ -1300,9 +1311,10 @@ extern "C" int rthx_trace_exchange(rthx_handle* h, const rthx_trace_args* a, uin
   } else {
     CU(h, cudaStreamWaitEvent(h->copy_stream, h->ev[2], 0));
   }
-  h->last_trace_bins = a->emitter_world == 1 ? a->n_bins : 0;
-  h->last_trace_rows = (size_t)N;
-  h->csr_bin = -1;
+  // the (compact) rows this call owns stay resident: all of them for a plain trace, those of a shard / row tile otherwise
+  h->last_trace_bins = a->n_bins;
+  h->last_trace_rows = (size_t)pl.n_owned; h->last_rank = a->emitter_rank; h->last_world = a->emitter_world;
+  h->csr_bin = -1; h->csc_bin = -1;
   std::vector<uint64_t> lost_host((size_t)a->n_bins * N);
   CU(h, cudaMemcpyAsync(lost_host.data(), h->lost_dev, sizeof(uint64_t) * lost_host.size(), cudaMemcpyDeviceToHost, h->copy_stream));
   CU(h, cudaEventRecord(h->ev[3], h->copy_stream));
@@ -1401,7 +1413,7 @@ extern "C" int rthx_trace_exchange_multi(rthx_handle** hs, int n, const rthx_tra
   const int N = h0->N;
   for (int i = 0; i < n; ++i) {
     if (!hs[i] || hs[i]->N != N || hs[i]->n_bands != h0->n_bands) return fail(h0, RTHX_ERR_ARG, "trace_multi: handles differ");
-    for (int j = 0; j < i; ++j) if (hs[j] == hs[i] || hs[j]->device == hs[i]->device) return fail(h0, RTHX_ERR_ARG, "trace_multi: one handle per device");
+    for (int j = 0; j < i; ++j) if (hs[j] == hs[i]) return fail(h0, RTHX_ERR_ARG, "trace_multi: the same handle twice");   // several handles on one device are fine
   }
   const bool gather = counts_out == nullptr;
   const size_t lost_n = (size_t)a->n_bins * N;
@@ -1414,6 +1426,8 @@ extern "C" int rthx_trace_exchange_multi(rthx_handle** hs, int n, const rthx_tra
     CU(h0, ensure(&h0->counts_dev, &h0->counts_cap, (size_t)a->n_bins * (size_t)N * N));
     shared_counts = h0->counts_dev;
     for (int i = 1; i < n; ++i) {
+      hs[i]->last_trace_bins = 0; hs[i]->csr_bin = -1; hs[i]->csc_bin = -1;
+      if (hs[i]->device == h0->device) continue;
       int can = 0;
       CU(h0, cudaDeviceCanAccessPeer(&can, hs[i]->device, h0->device));
       if (!can) return fail(h0, RTHX_ERR_CUDA, "trace_multi: no peer access between the devices (pass a host matrix instead)");
@@ -1421,7 +1435,6 @@ extern "C" int rthx_trace_exchange_multi(rthx_handle** hs, int n, const rthx_tra
       const cudaError_t pe = cudaDeviceEnablePeerAccess(h0->device, 0);
       if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) return fail(h0, RTHX_ERR_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(pe));
       cudaGetLastError();
-      hs[i]->last_trace_bins = 0; hs[i]->csr_bin = -1; hs[i]->csc_bin = -1;
     }
     // nothing is cleared centrally: every device clears its own rows / lost counters (device 0 in place, the others need no
     // clearing of the matrix at all — they hand finished rows over with plain stores)
@@ -1471,7 +1484,7 @@ extern "C" int rthx_trace_exchange_multi(rthx_handle** hs, int n, const rthx_tra
   if (gather) {
     CU(h0, cudaSetDevice(h0->device));
     CU(h0, cudaMemcpy(lost_sum.data(), h0->lost_dev, sizeof(uint64_t) * lost_n, cudaMemcpyDeviceToHost));
-    h0->last_trace_bins = a->n_bins; h0->last_trace_rows = (size_t)N;
+    h0->last_trace_bins = a->n_bins; h0->last_trace_rows = (size_t)N; h0->last_rank = 0; h0->last_world = 1;
   } else {
     for (int i = 0; i < n; ++i)
       for (size_t k = 0; k < lost_n; ++k) lost_sum[k] += jobs[i].lost[k];
@@ -1632,9 +1645,9 @@ extern "C" int rthx_flag_wait(const void* flags, int n, uint64_t value, double t
 // sparse read-out of the resident counts
 // ---------------------------------------------------------------------------------------------------------------
 namespace rthx {
-cudaError_t launch_row_nnz(const unsigned long long* c, int n, size_t ld, int n_surf, int* nnz, unsigned long long* rowsum, unsigned long long* cross,
-                           cudaStream_t st);
-cudaError_t launch_row_fill(const unsigned long long* c, int n, size_t ld, const long long* row_ptr, const unsigned long long* rowsum, int* cols,
+cudaError_t launch_row_nnz(const unsigned long long* c, int n_rows, int n_cols, size_t ld, int n_surf, int row_first, int row_stride, int* nnz,
+                           unsigned long long* rowsum, unsigned long long* cross, cudaStream_t st);
+cudaError_t launch_row_fill(const unsigned long long* c, int n_rows, int n_cols, size_t ld, const long long* row_ptr, const unsigned long long* rowsum, int* cols,
                             unsigned long long* vals, double* fvals, cudaStream_t st);
 cudaError_t launch_csc_count(const unsigned long long* c, int n, size_t ld, int* partial, long long* colptr, cudaStream_t st);
 cudaError_t launch_csc_fill(const unsigned long long* c, int n, size_t ld, const int* partial, const long long* colptr, const unsigned long long* rowsum,
@@ -1680,13 +1693,14 @@ int copy_out(rthx_handle* h, void* dst, const void* src_dev, size_t bytes, cudaS
 }
 
 // Row pass over the resident counts of `bin`: non-zeros and total per row, row pointers on the device, and the surface-gas
-// cross-coupling chi of the row-normalised F (cross_coupling_chi, smoothExchangeFactors.jl:212-241).
+// cross-coupling chi of the row-normalised F (cross_coupling_chi, smoothExchangeFactors.jl:212-241).  After a sharded trace
+// (emitter_world > 1: one row tile of a matrix too large to hold at once) the rows are those of the shard and chi is their share.
 int prepare_rows(rthx_handle* h, int bin) {
   if (bin < 0 || bin >= h->last_trace_bins || !h->counts_dev)
-    return fail(h, RTHX_ERR_ARG, "counts: no resident counts for that bin (run rthx_trace_exchange on all emitters with counts_out == NULL, or rthx_trace_exchange_multi with counts_out == NULL, first)");
+    return fail(h, RTHX_ERR_ARG, "counts: no resident counts for that bin (run rthx_trace_exchange with counts_out == NULL, or rthx_trace_exchange_multi with counts_out == NULL, first)");
   if (h->csr_bin == bin) return RTHX_OK;
   CU(h, cudaSetDevice(h->device));
-  const int N = h->N;
+  const int N = h->N, R = (int)h->last_trace_rows;
   if (h->csr_cap < (size_t)N + 1) {
     cudaFree(h->csr_nnz); cudaFree(h->csr_rowsum); cudaFree(h->csr_rowptr); cudaFree(h->csr_cross);
     h->csr_nnz = nullptr; h->csr_rowsum = nullptr; h->csr_rowptr = nullptr; h->csr_cross = nullptr; h->csr_cap = 0;
@@ -1697,22 +1711,24 @@ int prepare_rows(rthx_handle* h, int bin) {
     h->csr_cap = (size_t)N + 1;
   }
   const unsigned long long* c = h->counts_dev + (size_t)bin * h->last_trace_rows * N;
-  CU(h, rthx::launch_row_nnz(c, N, (size_t)N, h->ns, h->csr_nnz, h->csr_rowsum, h->csr_cross, h->stream));
-  std::vector<int> nnz(N);
-  std::vector<unsigned long long> rowsum(N), cross(N);
-  CU(h, cudaMemcpyAsync(nnz.data(), h->csr_nnz, sizeof(int) * N, cudaMemcpyDeviceToHost, h->stream));
-  CU(h, cudaMemcpyAsync(rowsum.data(), h->csr_rowsum, sizeof(unsigned long long) * N, cudaMemcpyDeviceToHost, h->stream));
-  CU(h, cudaMemcpyAsync(cross.data(), h->csr_cross, sizeof(unsigned long long) * N, cudaMemcpyDeviceToHost, h->stream));
+  CU(h, rthx::launch_row_nnz(c, R, N, (size_t)N, h->ns, h->last_rank, h->last_world, h->csr_nnz, h->csr_rowsum, h->csr_cross, h->stream));
+  std::vector<int> nnz(std::max(R, 1));
+  std::vector<unsigned long long> rowsum(std::max(R, 1)), cross(std::max(R, 1));
+  if (R > 0) {
+    CU(h, cudaMemcpyAsync(nnz.data(), h->csr_nnz, sizeof(int) * R, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaMemcpyAsync(rowsum.data(), h->csr_rowsum, sizeof(unsigned long long) * R, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaMemcpyAsync(cross.data(), h->csr_cross, sizeof(unsigned long long) * R, cudaMemcpyDeviceToHost, h->stream));
+  }
   CU(h, cudaStreamSynchronize(h->stream));
-  std::vector<long long> rp((size_t)N + 1, 0);
+  std::vector<long long> rp((size_t)R + 1, 0);
   double chi = 0.0;
-  for (int i = 0; i < N; ++i) {
+  for (int i = 0; i < R; ++i) {
     rp[i + 1] = rp[i] + nnz[i];
     if (rowsum[i]) chi += (double)cross[i] / (double)rowsum[i];
   }
-  CU(h, cudaMemcpyAsync(h->csr_rowptr, rp.data(), sizeof(long long) * ((size_t)N + 1), cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaMemcpyAsync(h->csr_rowptr, rp.data(), sizeof(long long) * ((size_t)R + 1), cudaMemcpyHostToDevice, h->stream));
   CU(h, cudaStreamSynchronize(h->stream));
-  h->csr_bin = bin; h->csr_total = rp[N]; h->csr_chi = N ? chi / N : 0.0;
+  h->csr_bin = bin; h->csr_total = rp[R]; h->csr_chi = N ? chi / N : 0.0;
   return RTHX_OK;
 }
 
@@ -1752,8 +1768,9 @@ extern "C" int rthx_counts_csr(rthx_handle* h, int bin, int64_t* row_ptr, int32_
   double* d_f = (double*)(d_vals + std::max<size_t>(1, nnz));
   int* d_cols = (int*)(d_f + std::max<size_t>(1, nnz));
   const unsigned long long* c = h->counts_dev + (size_t)bin * h->last_trace_rows * N;
-  CU(h, rthx::launch_row_fill(c, N, (size_t)N, h->csr_rowptr, h->csr_rowsum, d_cols, d_vals, F_vals ? d_f : nullptr, h->stream));
-  rc = copy_out(h, row_ptr, h->csr_rowptr, sizeof(long long) * ((size_t)N + 1), h->stream);
+  const int R = (int)h->last_trace_rows;
+  CU(h, rthx::launch_row_fill(c, R, N, (size_t)N, h->csr_rowptr, h->csr_rowsum, d_cols, d_vals, F_vals ? d_f : nullptr, h->stream));
+  rc = copy_out(h, row_ptr, h->csr_rowptr, sizeof(long long) * ((size_t)R + 1), h->stream);
   if (rc) return rc;
   if (nnz) {
     if ((rc = copy_out(h, cols, d_cols, sizeof(int) * nnz, h->stream))) return rc;
@@ -1766,6 +1783,8 @@ extern "C" int rthx_counts_csr(rthx_handle* h, int bin, int64_t* row_ptr, int32_
 
 extern "C" int rthx_counts_csc(rthx_handle* h, int bin, int index_base, int rowval_is_i64, int64_t* colptr, void* rowval, uint64_t* vals, double* F_vals) {
   if (!h || !colptr || !rowval || (index_base != 0 && index_base != 1)) return RTHX_ERR_ARG;
+  if (h->last_trace_bins > 0 && (h->last_world != 1 || (int)h->last_trace_rows != h->N))
+    return fail(h, RTHX_ERR_ARG, "counts_csc: the resident counts are the rows of a shard (emitter_world > 1); the column view needs the whole matrix");
   int rc = prepare_rows(h, bin);              // row totals for the normalisation, nnz for the buffer sizes
   if (rc) return rc;
   CU(h, cudaSetDevice(h->device));
@@ -1829,7 +1848,8 @@ extern "C" int rthx_smooth_DkAP(rthx_handle* h, int source, const void* src_host
   const double* src_F = nullptr;
   size_t ld = (size_t)n;
   if (source == RTHX_SMOOTH_FROM_LAST_TRACE) {
-    if (bin < 0 || bin >= h->last_trace_bins || !h->counts_dev || n > h->N) return fail(h, RTHX_ERR_ARG, "smooth: no resident counts for that bin (run rthx_trace_exchange on all emitters first)");
+    if (bin < 0 || bin >= h->last_trace_bins || !h->counts_dev || n > h->N || h->last_world != 1 || (int)h->last_trace_rows != h->N)
+      return fail(h, RTHX_ERR_ARG, "smooth: no resident counts for that bin (run rthx_trace_exchange on all emitters first)");
     src_counts = h->counts_dev + (size_t)bin * h->last_trace_rows * h->N;
     ld = (size_t)h->N;
   } else if (source == RTHX_SMOOTH_FROM_COUNTS || source == RTHX_SMOOTH_FROM_F) {

@@ -51,6 +51,7 @@ struct TraceParams {
   const FaceSetDev* sets;
   const int32_t* bucket_start;
   const int32_t* bucket_items;
+  const double* bucket_bb;     // [n_items*4] bounding box (xmin, xmax, ymin, ymax) of the polygon bucket_items[k] names
   const int32_t* poly_nv;
   const double* poly_vx;       // [n_poly*4]
   const double* poly_vy;

@@ -244,14 +244,12 @@ __device__ __forceinline__ int wall_of_poly(const TraceParams& p, int poly, doub
 //   rec = { xmin, xmax, ymin, ymax, vx[4], vy[4] }   (12 doubles; a triangle repeats its first vertex in slot 3: the zero-length edge
 //                                                      never straddles py, so four edges serve both kinds without a count)
 // Two things differ from the reference's arithmetic, both exact except on a null set (a point within rounding of an edge):
-//   * bounding-box prefilter: the ~8 candidates of a bucket that do not contain the point are rejected by four compares; a point
-//     the crossing test would accept lies inside the box;
+//   * bounding-box prefilter (find_face_generic): the ~8 candidates of a bucket that do not contain the point are rejected by four
+//     compares; a point the crossing test would accept lies inside the box;
 //   * the crossing test "px < xi + (xj-xi)/(yj-yi) (py-yi)" is evaluated without the division:
 //     t = (px-xi)(yj-yi) - (xj-xi)(py-yi) has the sign of (px - ix)(yj-yi), so the edge is crossed iff t (yj-yi) < 0.
 // The CPU oracle keeps the reference's form; the exact-parity tests bound the difference (<= 2e-6 of the rays).
 __device__ __forceinline__ bool point_in_rec(const double* __restrict__ rec, double px, double py) {
-  const double2 bx = __ldg(reinterpret_cast<const double2*>(rec)), by = __ldg(reinterpret_cast<const double2*>(rec) + 1);
-  if (!((px >= bx.x) & (px <= bx.y) & (py >= by.x) & (py <= by.y))) return false;
   const double2 x01 = __ldg(reinterpret_cast<const double2*>(rec) + 2), x23 = __ldg(reinterpret_cast<const double2*>(rec) + 3);
   const double2 y01 = __ldg(reinterpret_cast<const double2*>(rec) + 4), y23 = __ldg(reinterpret_cast<const double2*>(rec) + 5);
   const double vx[4] = {x01.x, x01.y, x23.x, x23.y}, vy[4] = {y01.x, y01.y, y23.x, y23.y};
@@ -272,16 +270,36 @@ __device__ __forceinline__ bool point_in_rec(const double* __restrict__ rec, dou
 // findFaceUniformGrid2D, findFace2D.jl:2-27: bucket of the uniform grid, first face passing the PIP test.
 // (The bbox-prefilter fallback of :30-45 can only succeed where the bucket scan succeeds, up to rounding of the
 // bucket index on a set of measure zero; it is restated in the CPU oracle and omitted here.)
+// SIMT shape of the scan: a lane that walked its bucket serially, leaving at the first hit, kept 10 of 32 lanes busy and chained
+// two L2 round trips per candidate (item -> record).  Instead the bounding boxes are stored next to the bucket lists
+// (bucket_bb[k] belongs to bucket_items[k]) and every lane first tests the boxes of ALL its candidates — independent loads, no
+// early exit, the same trip count for every lane of a regular mesh — into a bit mask; the crossing-number test then runs on the
+// set bits in order (one, unless boxes overlap).  Buckets longer than 32 entries are scanned in passes of 32.
 __device__ __noinline__ int find_face_generic(const TraceParams& p, int set, double px, double py) {
-  const FaceSetDev fs = p.sets[set];
-  const double fi = floor((px - fs.ox) * fs.inv_cell), fj = floor((py - fs.oy) * fs.inv_cell);
-  if (!(fi >= 0.0 && fi < (double)fs.nx && fj >= 0.0 && fj < (double)fs.ny)) return -1;
-  const int b = fs.bucket_off + (int)fi + (int)fj * fs.nx;
+  const FaceSetDev* fsp = p.sets + set;
+  const double ox = __ldg(&fsp->ox), oy = __ldg(&fsp->oy), inv_cell = __ldg(&fsp->inv_cell);
+  const int gnx = __ldg(&fsp->nx), gny = __ldg(&fsp->ny), boff = __ldg(&fsp->bucket_off), pbase = __ldg(&fsp->poly_base);
+  const double fi = floor((px - ox) * inv_cell), fj = floor((py - oy) * inv_cell);
+  if (!(fi >= 0.0 && fi < (double)gnx && fj >= 0.0 && fj < (double)gny)) return -1;
+  const int b = boff + (int)fi + (int)fj * gnx;
   const int k0 = __ldg(p.bucket_start + b), k1 = __ldg(p.bucket_start + b + 1);
-  const double* recs = p.poly_rec + (size_t)fs.poly_base * 12;
-  for (int k = k0; k < k1; ++k) {
-    const int f = __ldg(p.bucket_items + k);
-    if (point_in_rec(recs + (size_t)f * 12, px, py)) return f;
+  const double* recs = p.poly_rec + (size_t)pbase * 12;
+  const double2* bb = reinterpret_cast<const double2*>(p.bucket_bb);
+  for (int kb = k0; kb < k1; kb += 32) {
+    const int n = min(32, k1 - kb);
+    unsigned mask = 0u;
+#pragma unroll 4
+    for (int j = 0; j < n; ++j) {
+      const double2 bx = __ldg(bb + 2 * (size_t)(kb + j)), by = __ldg(bb + 2 * (size_t)(kb + j) + 1);
+      const bool in = (px >= bx.x) & (px <= bx.y) & (py >= by.x) & (py <= by.y);
+      mask |= in ? (1u << j) : 0u;
+    }
+    while (mask) {
+      const int j = __ffs((int)mask) - 1;
+      const int f = __ldg(p.bucket_items + kb + j);
+      if (point_in_rec(recs + (size_t)f * 12, px, py)) return f;
+      mask &= mask - 1u;
+    }
   }
   return -1;
 }
@@ -397,8 +415,7 @@ __global__ void __launch_bounds__(256, MINB) trace_exchange_kernel(const __grid_
   }
   if (HIST_SMEM)
     for (int i = threadIdx.x; i < N; i += blockDim.x) hist[i] = 0u;
-  if (FAST)
-    for (int i = threadIdx.x; i < LOGTAB_N; i += blockDim.x) s_log[i] = c_logtab[i];
+  for (int i = threadIdx.x; i < LOGTAB_N; i += blockDim.x) s_log[i] = c_logtab[i];
   // FAST: a plain shared-memory pointer (LDS); otherwise a generic pointer that may be shared or global
   const CoarseDev* coarse = FAST ? s_coarse : (p.coarse_in_smem ? s_coarse : p.coarse);
 
@@ -461,15 +478,15 @@ __global__ void __launch_bounds__(256, MINB) trace_exchange_kernel(const __grid_
       // lambertSample2D: Float32 variates / sqrt / square, the rest in Float64
       const float cosT = __fsqrt_rn(u23(w0.y));
       const float cos2 = __fmul_rn(cosT, cosT);
-      const double sinT = FAST ? sqrt_pos(1.0 - (double)cos2) : sqrt(1.0 - (double)cos2);
-      const double xdir = sinT * (FAST ? cos2pi_unit((double)u23(w0.z)) : cospi(2.0 * (double)u23(w0.z)));
+      const double sinT = sqrt_pos(1.0 - (double)cos2);
+      const double xdir = sinT * cos2pi_unit((double)u23(w0.z));
       const double zdir = (double)cosT;
       dx = s_em[4] * xdir + s_em[6] * zdir;
       dy = s_em[5] * xdir + s_em[7] * zdir;
       R_S = u52(w1.x, w1.y, p.k_u52);
     } else {
       const double R1 = u32d(w0.x, p.k_u32), R2 = u32d(w0.y, p.k_u32);
-      const double sq = FAST ? sqrt_pos(R1) : sqrt(R1);
+      const double sq = sqrt_pos(R1);
       // uniform point of triangle (V0,V1,V2): V0 + sqrt(R1)(1-R2)(V1-V0) + sqrt(R1) R2 (V2-V0), emitVolumeRay2D.jl:9,12
       const double* tri = s_em + ((u32d(w0.z, p.k_u32) < s_em[14]) ? 0 : 6);
       const double a2 = sq * R2, a1 = sq - a2;
@@ -477,9 +494,9 @@ __global__ void __launch_bounds__(256, MINB) trace_exchange_kernel(const __grid_
       py = fma(a2, tri[5], fma(a1, tri[3], tri[1]));
       // theta = acos(1-2R): cos(theta) = 1-2R, sin(theta) = 2 sqrt(R(1-R)) (algebraically identical)
       const double Rt = u52(w1.x, w1.y, p.k_u52);
-      const double sinT = 2.0 * (FAST ? sqrt_pos(Rt * (1.0 - Rt)) : sqrt(Rt * (1.0 - Rt)));
+      const double sinT = 2.0 * sqrt_pos(Rt * (1.0 - Rt));
       const double phiR = u32d(w0.w, p.k_u32);
-      dx = sinT * (FAST ? cos2pi_unit(phiR) : cospi(2.0 * phiR));
+      dx = sinT * cos2pi_unit(phiR);
       dy = fma(Rt, -2.0, 1.0);
       R_S = u52(w1.z, w1.w, p.k_u52);
     }
@@ -493,7 +510,7 @@ __global__ void __launch_bounds__(256, MINB) trace_exchange_kernel(const __grid_
     // ---- stage 2: first-interaction traversal (traceRayUniform / traceRayVariable) --------------------------
     // MULTI (RTHX_MULTI_BOUNCE): the traversal is repeated from every scattering / reflection event until the ray is
     // absorbed (traceSingleRay.jl:7-81 without the re-emission branches); otherwise the body runs exactly once.
-    double neg_log = FAST ? neg_log_table(R_S, s_log) : -log(R_S);
+    double neg_log = neg_log_table(R_S, s_log);
     int c = c0;
     int absorber = -1;
     if constexpr (SQ) {

@@ -153,15 +153,17 @@ __global__ void __launch_bounds__(ROW_THREADS) recover_kernel(double* __restrict
 // sparse (CSR) view of a count matrix: feeds sparse(I, J, V) without moving the zeros
 // ---------------------------------------------------------------------------------------------------------------
 // one warp per row: number of non-zero tallies, the row total and — for cross_coupling_chi (smoothExchangeFactors.jl:212-241) —
-// the tallies that couple a surface with a gas cell (exactly one of row / column index below n_surf)
-__global__ void __launch_bounds__(256) row_nnz_kernel(const unsigned long long* __restrict__ c, int n, size_t ld, int n_surf, int* __restrict__ nnz,
-                                                      unsigned long long* __restrict__ rowsum, unsigned long long* __restrict__ cross) {
+// the tallies that couple a surface with a gas cell (exactly one of row / column index below n_surf).  The matrix may hold only
+// the rows of a shard (row y = element row_first + y * row_stride), n_rows x n_cols with leading dimension ld.
+__global__ void __launch_bounds__(256) row_nnz_kernel(const unsigned long long* __restrict__ c, int n_rows, int n_cols, size_t ld, int n_surf, int row_first,
+                                                      int row_stride, int* __restrict__ nnz, unsigned long long* __restrict__ rowsum,
+                                                      unsigned long long* __restrict__ cross) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (row >= n) return;
+  if (row >= n_rows) return;
   int cnt = 0;
   unsigned long long s = 0, x = 0;
-  const bool row_surf = row < n_surf;
-  for (int j = lane; j < n; j += 32) {
+  const bool row_surf = row_first + row * row_stride < n_surf;
+  for (int j = lane; j < n_cols; j += 32) {
     const unsigned long long v = c[(size_t)row * ld + j];
     cnt += v != 0; s += v;
     if ((j < n_surf) != row_surf) x += v;
@@ -173,30 +175,35 @@ __global__ void __launch_bounds__(256) row_nnz_kernel(const unsigned long long* 
 }
 
 // one warp per row: write (column, count, count / rowsum) of the non-zeros in ascending column order at row_ptr[row]
-__global__ void __launch_bounds__(256) row_fill_kernel(const unsigned long long* __restrict__ c, int n, size_t ld, const long long* __restrict__ row_ptr,
+__global__ void __launch_bounds__(256) row_fill_kernel(const unsigned long long* __restrict__ c, int n_rows, int n_cols, size_t ld, const long long* __restrict__ row_ptr,
                                                        const unsigned long long* __restrict__ rowsum, int* __restrict__ cols,
                                                        unsigned long long* __restrict__ vals, double* __restrict__ fvals) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (row >= n) return;
+  if (row >= n_rows) return;
   long long base = row_ptr[row];
   const double inv = rowsum[row] ? 1.0 / (double)rowsum[row] : 0.0;
-  for (int j0 = 0; j0 < n; j0 += 32) {
+  for (int j0 = 0; j0 < n_cols; j0 += 32) {
     const int j = j0 + lane;
-    const unsigned long long v = j < n ? c[(size_t)row * ld + j] : 0ull;
+    const unsigned long long v = j < n_cols ? c[(size_t)row * ld + j] : 0ull;
     const unsigned m = __ballot_sync(0xffffffffu, v != 0);
     if (v != 0) {
       const long long k = base + __popc(m & ((1u << lane) - 1u));
       cols[k] = j;
-      vals[k] = v;
+      if (vals) vals[k] = v;
       if (fvals) fvals[k] = (double)v * inv;
     }
     base += __popc(m);
   }
 }
 
-cudaError_t launch_row_nnz(const unsigned long long* c, int n, size_t ld, int n_surf, int* nnz, unsigned long long* rowsum, unsigned long long* cross,
-                           cudaStream_t st) {
-  row_nnz_kernel<<<(n + 7) / 8, 256, 0, st>>>(c, n, ld, n_surf, nnz, rowsum, cross);
+cudaError_t launch_row_nnz(const unsigned long long* c, int n_rows, int n_cols, size_t ld, int n_surf, int row_first, int row_stride, int* nnz,
+                           unsigned long long* rowsum, unsigned long long* cross, cudaStream_t st) {
+  if (n_rows > 0) row_nnz_kernel<<<(n_rows + 7) / 8, 256, 0, st>>>(c, n_rows, n_cols, ld, n_surf, row_first, row_stride, nnz, rowsum, cross);
+  return cudaGetLastError();
+}
+cudaError_t launch_row_fill(const unsigned long long* c, int n_rows, int n_cols, size_t ld, const long long* row_ptr, const unsigned long long* rowsum, int* cols,
+                            unsigned long long* vals, double* fvals, cudaStream_t st) {
+  if (n_rows > 0) row_fill_kernel<<<(n_rows + 7) / 8, 256, 0, st>>>(c, n_rows, n_cols, ld, row_ptr, rowsum, cols, vals, fvals);
   return cudaGetLastError();
 }
 
@@ -292,11 +299,6 @@ __global__ void add_base_kernel(long long* p, int n, long long base) {
 }
 cudaError_t launch_add_base(long long* p, int n, long long base, cudaStream_t st) {
   add_base_kernel<<<(n + 255) / 256, 256, 0, st>>>(p, n, base);
-  return cudaGetLastError();
-}
-cudaError_t launch_row_fill(const unsigned long long* c, int n, size_t ld, const long long* row_ptr, const unsigned long long* rowsum, int* cols,
-                            unsigned long long* vals, double* fvals, cudaStream_t st) {
-  row_fill_kernel<<<(n + 7) / 8, 256, 0, st>>>(c, n, ld, row_ptr, rowsum, cols, vals, fvals);
   return cudaGetLastError();
 }
 

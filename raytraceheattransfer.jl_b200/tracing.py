@@ -99,9 +99,14 @@ def _tracers_for(rtm, devices: Sequence[int]):
     return trs
 
 
+def auto_row_tiles(n_elements: int, n_bins: int, budget_bytes: float = 48e9) -> int:
+    """Row tiles needed to keep the resident UInt64 counts (8 N^2 bytes per traced bin) within `budget_bytes` of device memory."""
+    return max(1, int(np.ceil(8.0 * n_elements * n_elements * n_bins / budget_bytes)))
+
+
 def computeExchangeFactorsBins(rtm, rays_per_emitter: int, nudge: float, spectral_bins: Sequence[int],
                                verbose: bool, rec, seed: int, device: int = 0,
-                               locator: int = RTHX_LOCATOR_AUTO, devices=None) -> List[sp.csc_matrix]:
+                               locator: int = RTHX_LOCATOR_AUTO, devices=None, row_tiles: Optional[int] = None) -> List[sp.csc_matrix]:
     """Batched form of computeExchangeFactorsBin: traces every requested (1-based) bin in one launch per device."""
     import time
     devs = resolve_devices(devices if devices is not None else [device], device, 0)
@@ -115,6 +120,28 @@ def computeExchangeFactorsBins(rtm, rays_per_emitter: int, nudge: float, spectra
     # returns (parallelRayTracing.jl:144-158 + row_normalize! :161-169) — no N^2 host traffic, no sparse(I, J, V), no transpose.
     t0 = time.perf_counter()
     kw = dict(seed=seed, bins=[b - 1 for b in spectral_bins], nudge=nudge, rec_ids=rec_ids, rec_bin=rec_bin, locator=locator)
+    n_tiles = auto_row_tiles(tr.n_elements, len(spectral_bins)) if row_tiles is None else int(row_tiles)
+    if n_tiles > 1:
+        # N >> 57 k elements: the dense count matrix is the limit, not the tally — trace the rows in tiles,
+        # keep only each tile's non-zeros.  One device; the recorder is not available on this path.
+        if rec is not None:
+            raise ValueError("RayRecorder is not supported together with row tiles")
+        from ._lib import trace_row_tiles
+        kw.pop("rec_ids"); kw.pop("rec_bin")
+        res = trace_row_tiles(tr, rays_per_emitter, n_tiles, **kw)
+        t1 = time.perf_counter()
+        rtm.last_trace_stats = dict(res["stats"], row_tiles=n_tiles)
+        rtm.last_lost = res["lost"]
+        N = tr.n_elements
+        mats = []
+        rtm.last_counts_stats = []
+        for k in range(len(spectral_bins)):
+            row_ptr, cols, vals = res["csr"][k]
+            print(f"Maximum ray tracing ray loss per emitter: {int(res['lost'][k].max()) if N else 0}/{rays_per_emitter}")   # unconditional, :163
+            rtm.last_counts_stats.append({"nnz": int(row_ptr[-1]), "chi": float(res["chi"][k]), "density": row_ptr[-1] / float(N * N)})
+            mats.append(sp.csr_matrix((vals, cols, row_ptr), shape=(N, N)).tocsc())
+        rtm.last_phase_ms.update({"trace": 1e3 * (t1 - t0), "csc_F_raw": 1e3 * (time.perf_counter() - t1), "row_tiles": n_tiles})
+        return mats
     if len(trs) == 1:
         out = tr.trace(rays_per_emitter, dense=False, **kw)
     else:
@@ -149,14 +176,14 @@ def computeExchangeFactorsBins(rtm, rays_per_emitter: int, nudge: float, spectra
 
 def computeExchangeFactorsBin(rtm, rays_per_emitter: int, nudge: float, spectral_bin: int, verbose: bool = False,
                               rec=None, seed: int = 0x5EED0001, device: int = 0,
-                              locator: int = RTHX_LOCATOR_AUTO, devices=None) -> sp.csc_matrix:
+                              locator: int = RTHX_LOCATOR_AUTO, devices=None, row_tiles: Optional[int] = None) -> sp.csc_matrix:
     """computeExchangeFactorsBin(rtm, rays_per_emitter, nudge, spectral_bin, ..., rec) -> sparse F (1-based bin)."""
     return computeExchangeFactorsBins(rtm, rays_per_emitter, nudge, [spectral_bin], verbose, rec, seed, device,
-                                      locator, devices)[0]
+                                      locator, devices, row_tiles)[0]
 
 
 def parallelRayTracing(rtm, rays_total: int, nudge: float, verbose: bool, rec=None, seed: Optional[int] = None,
-                       device: int = 0, locator: int = RTHX_LOCATOR_AUTO, devices=None):
+                       device: int = 0, locator: int = RTHX_LOCATOR_AUTO, devices=None, row_tiles: Optional[int] = None):
     """parallelRayTracing(rtm, rays_total, nudge, verbose; rec) -> (F_raw, rays_per_emitter)."""
     if seed is None:
         seed = secrets.randbits(64)   # the reference is unseeded: a fresh stream per call
@@ -168,7 +195,7 @@ def parallelRayTracing(rtm, rays_total: int, nudge: float, verbose: bool, rec=No
         verbose and print(f"Computing {n_bins} separate F matrices for variable spectral extinction")
         groups, reps, nonuniform = group_uniform_bins(rtm.uniform_across_bin)
         to_trace = list(nonuniform) + [g[0] for g in groups]
-        mats = computeExchangeFactorsBins(rtm, rays_per_emitter, nudge, to_trace, verbose, rec, seed, device, locator, devices)
+        mats = computeExchangeFactorsBins(rtm, rays_per_emitter, nudge, to_trace, verbose, rec, seed, device, locator, devices, row_tiles)
         rtm._traced_bins = list(to_trace)
         F_raw_vector: List[Optional[sp.csc_matrix]] = [None] * n_bins
         for b, F in zip(to_trace[: len(nonuniform)], mats[: len(nonuniform)]):
@@ -181,7 +208,7 @@ def parallelRayTracing(rtm, rays_total: int, nudge: float, verbose: bool, rec=No
         verbose and print(f"Computing single F matrix for uniform spectral extinction ({n_bins} bins)")
     else:
         verbose and print("Computing single F matrix for grey extinction")
-    F_raw = computeExchangeFactorsBins(rtm, rays_per_emitter, nudge, [1], verbose, rec, seed, device, locator, devices)[0]
+    F_raw = computeExchangeFactorsBins(rtm, rays_per_emitter, nudge, [1], verbose, rec, seed, device, locator, devices, row_tiles)[0]
     rtm._traced_bins = [1]
     return F_raw, rays_per_emitter
 
@@ -225,6 +252,8 @@ def _smooth_on_device(rtm, k: int, F_raw, w, ns: int, max_iters: int, verbose: b
     n = F_raw.shape[0]
     if tr is None or max_iters <= 0 or F_raw.nnz / float(n * n) <= 0.25:
         return None
+    if (getattr(rtm, "last_trace_stats", None) or {}).get("row_tiles", 1) > 1:
+        return None                                          # traced in row tiles: only the last tile is resident
     wn = w[:n] / np.min(w[:n])
     if k_dykstra is None:       # smooth_F :441-450: one Dykstra round when surfaces and gas are strongly coupled, else AP only
         stats = getattr(rtm, "last_counts_stats", None)
@@ -253,13 +282,13 @@ def _smooth_on_device(rtm, k: int, F_raw, w, ns: int, max_iters: int, verbose: b
 
 def exchangeRayTracing(rtm, rays_tot: int, nudge: float, max_iters: int, k_dykstra, verbose: bool, rec,
                        seed: Optional[int] = None, device: int = 0, locator: int = RTHX_LOCATOR_AUTO,
-                       smooth: bool = True, devices=None):
+                       smooth: bool = True, devices=None, row_tiles: Optional[int] = None):
     """exchangeRayTracing!(rtm, rays_tot, nudge, max_iters, k_dykstra, verbose, rec): trace, optional
     surfaces-only crop (:9-11), smooth (:14-70), store rtm.F_raw / rtm.F_smooth (:73-74)."""
     import time
     from .smoothing import smooth_F
     F_raw, rays_per_emitter = parallelRayTracing(rtm, rays_tot, nudge, verbose, rec=rec, seed=seed, device=device,
-                                                 locator=locator, devices=devices)
+                                                 locator=locator, devices=devices, row_tiles=row_tiles)
     t0 = time.perf_counter()
     ns = rtm.num_surfaces
     if rtm.surfaces_only and not isinstance(F_raw, list):

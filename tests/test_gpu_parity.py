@@ -221,6 +221,11 @@ def test_multi_handle_single_process(rthx_mod, cuda_lib):
     multi = trace_multi(trs, 3000, seed=13, rec_ids=[9, 150])
     assert np.array_equal(one["counts"], multi["counts"]) and np.array_equal(one["lost"], multi["lost"])
     assert np.array_equal(one["origins"], multi["origins"]) and np.array_equal(one["endpoints"], multi["endpoints"])
+    res = trace_multi(trs, 3000, seed=13, dense=False)                      # rows gathered on trs[0]'s device, matrix stays resident
+    row_ptr, cols, vals, _ = trs[0].counts_csr(0)
+    import scipy.sparse as sp
+    assert np.array_equal(sp.csr_matrix((vals, cols, row_ptr), shape=one["counts"][0].shape).toarray(), one["counts"][0])
+    assert np.array_equal(res["lost"], one["lost"])
 
 
 def test_full_size_properties_cfg3(rthx_mod, cuda_lib):
