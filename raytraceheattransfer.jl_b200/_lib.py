@@ -32,7 +32,8 @@ class RthxError(RuntimeError):
 
 
 def library_path() -> str:
-    return os.path.join(_CSRC, "librthx.so")
+    # RTHX_LIBRARY: an alternative build of the same sources (A/B experiments, e.g. tools/gpu_evidence_r2.sh); never a fallback
+    return os.environ.get("RTHX_LIBRARY") or os.path.join(_CSRC, "librthx.so")
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:

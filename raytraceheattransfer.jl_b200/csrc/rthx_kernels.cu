@@ -896,6 +896,17 @@ __device__ __forceinline__ unsigned int sq_ray_loop(const TraceParams& p, const 
         absorber = sid;
       }
     }
+#ifdef RTHX_TALLY_MATCH
+    // A/B variant (tools/gpu_evidence_r2.sh builds it as a second library): warp-aggregated tally — lanes that hit the same bin
+    // elect one of them to add the group's count.  Measured on cfg3: slower than one red.shared.add.u32 per ray.
+    {
+      const unsigned act = __activemask();
+      const unsigned grp = __match_any_sync(act, absorber);
+      if (absorber >= 0 && (int)(__ffs((int)grp) - 1) == (int)(threadIdx.x & 31))
+        asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(hist_s + 4u * (uint32_t)absorber), "r"((unsigned)__popc(grp)) : "memory");
+      if (absorber < 0) ++n_lost;
+    }
+#else
     if (absorber >= 0) {
       asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(hist_s + 4u * (uint32_t)absorber), "r"(1u) : "memory");
       if (REC) {
@@ -907,6 +918,7 @@ __device__ __forceinline__ unsigned int sq_ray_loop(const TraceParams& p, const 
     } else {
       ++n_lost;
     }
+#endif
     {
       const uint64_t ray_id = (uint64_t)(b.ray0 + (int64_t)(i + blockDim.x));
       w0n = philox4x32_10_rk(make_uint4((uint32_t)ray_id, (uint32_t)(ray_id >> 32), b.e, b.cw | 0u), p.rk);
@@ -1299,9 +1311,7 @@ __device__ __forceinline__ unsigned int queue_ray_loop(const TraceParams& p, con
     int absorber = -1;                                                                                              \
     if (tallied) {                                                                                                  \
       const int l = lattice_cell<BILIN>(cf, px, py);                                                                \
-      /* gas ending on a quad lattice: Ns + cell, no load (fine index = lattice index, meshQuad.jl:139,151) */        \
-      if (l >= 0) absorber = (gas & (cf.kind != KIND_AFFINE_TRI)) ? p.n_surfaces + cf.fine_off + l                   \
-                                                                  : __ldg(p.abs_tab + (size_t)(cf.abs_off + l) * 5 + (gas ? 0 : 1 + k)); \
+      if (l >= 0) absorber = __ldg(p.abs_tab + (size_t)(cf.abs_off + l) * 5 + (gas ? 0 : 1 + k));                   \
     }                                                                                                               \
     if (absorber >= 0) {                                                                                            \
       atomicAdd(&b.hist[absorber], 1u);                                                                             \
