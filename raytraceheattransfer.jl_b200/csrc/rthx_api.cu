@@ -903,6 +903,10 @@ LaunchPlan make_plan(const rthx_handle* h, const rthx_trace_args* a, int rank, i
   pl.multi = a->mode != RTHX_FIRST_INTERACTION ? 1 : 0;
   pl.minb = pl.multi ? 2 : 4;
   if (const char* ev = std::getenv("RTHX_MINB")) { const int v = std::atoi(ev); if (v >= 2 && v <= 4) pl.minb = v; }   // tuning knob
+  if (!pl.fast && !pl.multi) {     // generic locator kernel: 3 resident blocks (80 registers) unless RTHX_GENERIC_MINB=4 (64 registers, spills)
+    pl.minb = 3;
+    if (const char* ev = std::getenv("RTHX_GENERIC_MINB")) { if (std::atoi(ev) == 4) pl.minb = 4; }
+  }
   const size_t coarse_bytes = h->coarse_fits_smem ? sizeof(CoarseDev) * (size_t)h->n_coarse : 0;
   const size_t hist_bytes = sizeof(uint32_t) * (size_t)h->N, em_bytes = sizeof(double) * 16 + 16 * (size_t)LOGTAB_N;   // emitter block + log table
   pl.hist_in_smem = (coarse_bytes + em_bytes + hist_bytes <= h->prop.sharedMemPerBlockOptin) ? 1 : 0;

@@ -561,20 +561,20 @@ __global__ void __launch_bounds__(256, MINB) trace_exchange_kernel(const __grid_
         gas = acc + tau_b >= neg_log;
         if (gas) S = (neg_log - acc) / local_beta;
       }
-      if (gas) {
-        px = fma(S - p.nudge, dx, px);
-        py = fma(S - p.nudge, dy, py);
-        const int f = locate_fine<FAST>(p, cf, c, kind, px, py);
-        if (f >= 0) absorber = p.n_surfaces + cf.fine_off + f;
-        break;
-      } else if (!(u < CUDART_INF)) {
-        break;                                                  // no edge ahead: the reference ends in NaN -> lost
-      } else if (cf.solid[k]) {
-        px = fma(u - p.nudge, dx, px);
-        py = fma(u - p.nudge, dy, py);
+      // Gas events and solid-wall hits share ONE advance and ONE fine-cell location (the same arithmetic as the two branches of
+      // traceRay.jl:31-52, selected per lane): with separate call sites a warp holding both kinds of ray ran the point location —
+      // the expensive part of the generic locator — twice at half occupancy (ncu: 2.0 calls per warp and ray at 16 lanes).
+      const bool noedge = !(u < CUDART_INF);
+      if (!gas & noedge) break;                                   // no edge ahead: the reference ends in NaN -> lost
+      const bool solid = !gas && cf.solid[k];
+      const double adv = gas ? S - p.nudge : (solid ? u - p.nudge : u + p.nudge);   // traceRay.jl:33,44,56
+      px = fma(adv, dx, px);
+      py = fma(adv, dy, py);
+      if (gas | solid) {
         const int f = locate_fine<FAST>(p, cf, c, kind, px, py);
         if (f < 0) break;
         const int gc = cf.fine_off + f;
+        if (gas) { absorber = p.n_surfaces + gc; break; }
         int w;
         if (!FAST && kind == KIND_GENERIC) {
           w = wall_of_poly(p, gc, px, py, dx, dy);              // traceRay.jl:51
@@ -593,8 +593,6 @@ __global__ void __launch_bounds__(256, MINB) trace_exchange_kernel(const __grid_
         absorber = __ldg(p.cell_surf_id + 4 * gc + w);          // -1: fine wall not solid -> lost
         break;
       } else {
-        px = fma(u + p.nudge, dx, px);
-        py = fma(u + p.nudge, dy, py);
         if (uniform) S -= u; else acc += tau_b;
         int nc;
         if (FAST) {
@@ -1734,7 +1732,8 @@ static TraceKernel kernel_variant(bool hist, bool fast, int minb, bool multi, bo
     return fast ? (TraceKernel)trace_exchange_kernel<false, true, 2, true, false> : (TraceKernel)trace_exchange_kernel<false, false, 2, true, false>;
   }
   if (!hist) return fast ? (TraceKernel)trace_exchange_kernel<false, true, 2, false, false> : (TraceKernel)trace_exchange_kernel<false, false, 2, false, false>;
-  if (!fast) return (TraceKernel)trace_exchange_kernel<true, false, 3, false, false>;     // generic locator: 80 registers, 3 blocks per SM
+  if (!fast) return minb == 4 ? (TraceKernel)trace_exchange_kernel<true, false, 4, false, false>     // generic locator: 64 registers (spills 132 B), 4 blocks per SM
+                              : (TraceKernel)trace_exchange_kernel<true, false, 3, false, false>;    // 80 registers, 3 blocks per SM
   switch (minb) {
     case 3: return (TraceKernel)trace_exchange_kernel<true, true, 3, false, false>;
     case 4: return (TraceKernel)trace_exchange_kernel<true, true, 4, false, false>;
