@@ -66,11 +66,11 @@ def parse_args():
 
 
 # DRAM bytes per launch of the trace kernel measured by ncu --set full (dram__bytes_read.sum + dram__bytes_write.sum)
-NCU_DRAM_BYTES_PER_LAUNCH = {"cfg3": (894.04e6 + 833.20e6, "profiles/r1y_trace_exchange_sq_metrics.csv"),
+NCU_DRAM_BYTES_PER_LAUNCH = {"cfg3": (893.59e6 + 831.82e6, "profiles/r2/r2p_trace_exchange_sq_metrics.csv"),
                              "cfg5": (None, "profiles/r1y_trace_exchange_queue_metrics.csv")}
 
 # executed warp instructions per 32 rays of the trace kernel (ncu source page, profiles/<capture>_sass_mix.csv, TOTAL row)
-NCU_WARP_INSTR_PER_32_RAYS = {"cfg3": (250.5, "profiles/r1y_trace_exchange_sq_sass_mix.csv"),
+NCU_WARP_INSTR_PER_32_RAYS = {"cfg3": (250.8, "profiles/r2/r2p_trace_exchange_sq_sass_mix.csv"),
                               "cfg5": (680.9, "profiles/r1y_trace_exchange_queue_sass_mix.csv")}
 
 DEFAULT_RAYS = {"cfg1": 1e6, "cfg2": 1e8, "cfg3": 1e10, "cfg4": 1e8, "cfg5": 1e9}
@@ -138,7 +138,8 @@ def host_threads():
 
 
 def run_oracle_sample(flat, bins, rays_total, seed, faithful=False):
-    """Time the CPU oracle (all host threads, pinned) on a bounded sample of the workload."""
+    """Time the CPU oracle (all host threads) on a bounded sample of the workload.  Threads are NOT pinned: OMP_PROC_BIND / OMP_PLACES
+    put every thread on one core inside the GPU box's container (measured: 5.3e6 instead of 7.7e7 rays/s)."""
     from oracle import oracle
     N = flat.n_elements
     rpe = max(1, int(rays_total) // (N * len(bins)))
@@ -154,7 +155,7 @@ def cpu_sample_text(sample, mode, r):
     what = ("reference-faithful C restatement: contiguous emitter ranges per thread, per-thread xoshiro256++, Dict-like row tally "
             "(parallelRayTracing.jl:83-91,104,124)" if mode == "faithful" else
             "the parity oracle: C restatement with the Philox contract and a dense row tally")
-    return (f"{int(sample):d} rays per step of the same workload ({what}; OpenMP, threads pinned, Julia absent); wall time of the whole "
+    return (f"{int(sample):d} rays per step of the same workload ({what}; OpenMP, Julia absent); wall time of the whole "
             f"call; emitter loop alone: {r['loop_rays_per_s']:.3e} rays/s; cpu: {cpu_model()}")
 
 
@@ -243,8 +244,6 @@ def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    os.environ.setdefault("OMP_PROC_BIND", "true")
-    os.environ.setdefault("OMP_PLACES", "cores")
     world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
     rtm, flat, bins = build_workload(args.workload)
     cfg = workload_config(args, flat.n_elements, len(bins), world)
@@ -616,8 +615,6 @@ def main():
 
     # ---- roofline (FP64 pipe) and CPU baseline ---------------------------------------------------------------
     fp64_peak = sh.tracer.measure_fp64_peak()
-    os.environ.setdefault("OMP_PROC_BIND", "true")
-    os.environ.setdefault("OMP_PLACES", "cores")
     # the algorithmic flop count per ray is a property of the workload: the (emitter kind, ending) mix from the oracle's counters
     # on a small sample, at every N
     mix = run_oracle_sample(flat, bins, 2.0e7, seed=7)
