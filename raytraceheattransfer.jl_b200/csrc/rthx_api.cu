@@ -837,6 +837,9 @@ extern "C" int rthx_create_multi(rthx_handle** out, const rthx_mesh* m, const in
     if (device_ids[i] < 0 || device_ids[i] >= n_dev) return fail(nullptr, RTHX_ERR_ARG, "rthx_create: bad device id");
     for (int j = 0; j < i; ++j) if (device_ids[j] == device_ids[i]) return fail(nullptr, RTHX_ERR_ARG, "rthx_create_multi: duplicate device id");
   }
+  int caller_device = 0;
+  cudaGetDevice(&caller_device);
+  struct RestoreDevice { int d; bool on; ~RestoreDevice() { if (on) cudaSetDevice(d); } } restore_device{caller_device, n > 1};   // a single-device create leaves that device current, as before
   const bool timing = std::getenv("RTHX_CREATE_TIMING") != nullptr;
   const auto t0 = std::chrono::steady_clock::now();
   std::shared_ptr<HostImage> im;
@@ -1015,6 +1018,8 @@ void fill_params(const rthx_handle* h, const rthx_trace_args* a, const LaunchPla
     const bool axis = f.nx[0] == 0.0 && std::fabs(f.ny[0]) == 1.0 && std::fabs(f.nx[1]) == 1.0 && f.ny[1] == 0.0 && f.g1y == 0.0 && f.g2x == 0.0;
     P.sq_axis = axis ? 1 : 0;
     if (const char* ev = std::getenv("RTHX_NO_AXIS")) { if (std::atoi(ev)) P.sq_axis = 0; }   // test knob: the general SQ loop
+    P.queue_sq = (h->single_quad && pl.multi && pl.queue_depth > 0) ? (P.sq_axis ? 1 : 2) : 0;
+    if (const char* ev = std::getenv("RTHX_NO_QUEUE_SQ")) { if (std::atoi(ev)) P.queue_sq = 0; }   // A/B knob: the generic step on a single quad
     P.sq_cy = f.ny[0] * P.sq_cen0; P.sq_cx = f.nx[1] * P.sq_cen1;
     P.sq_flip0 = f.ny[0] < 0.0 ? 0x80000000u : 0u; P.sq_flip1 = f.nx[1] < 0.0 ? 0x80000000u : 0u;
   }
@@ -1419,6 +1424,9 @@ extern "C" int rthx_trace_exchange_multi(rthx_handle** hs, int n, const rthx_tra
     if (!hs[i] || hs[i]->N != N || hs[i]->n_bands != h0->n_bands) return fail(h0, RTHX_ERR_ARG, "trace_multi: handles differ");
     for (int j = 0; j < i; ++j) if (hs[j] == hs[i]) return fail(h0, RTHX_ERR_ARG, "trace_multi: the same handle twice");   // several handles on one device are fine
   }
+  int caller_device = 0;
+  cudaGetDevice(&caller_device);
+  struct RestoreDevice { int d; ~RestoreDevice() { cudaSetDevice(d); } } restore_device{caller_device};   // whatever path returns
   const bool gather = counts_out == nullptr;
   const size_t lost_n = (size_t)a->n_bins * N;
   std::vector<MultiJob> jobs(n);
@@ -1478,9 +1486,15 @@ extern "C" int rthx_trace_exchange_multi(rthx_handle** hs, int n, const rthx_tra
     if (J.rc) J.err = h->err;
   };
   {
+    // one host thread per device; if the process cannot start threads the devices are driven in turn (slower, still correct) —
+    // no C++ exception may cross the C ABI
     std::vector<std::thread> th;
-    for (int i = 1; i < n; ++i) th.emplace_back(device_job, i);
+    std::vector<int> inline_jobs;
+    for (int i = 1; i < n; ++i) {
+      try { th.emplace_back(device_job, i); } catch (...) { inline_jobs.push_back(i); }
+    }
     device_job(0);
+    for (int i : inline_jobs) device_job(i);
     for (auto& t : th) t.join();
   }
   for (int i = 0; i < n; ++i) if (jobs[i].rc) return fail(h0, jobs[i].rc, jobs[i].err);
@@ -1622,7 +1636,7 @@ __global__ void flag_wait_kernel(const unsigned long long* flags, int n, unsigne
       asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + i) : "memory");
       if (v >= value) break;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-      if (t - t0 > timeout_ns) { if (err) atomicAdd(err, 1ull); break; }
+      if (t - t0 > timeout_ns) { if (err) atomicAdd_system(err, 1ull); break; }   // the counter may live in the owner's (peer) memory
       __nanosleep(200);
     }
   }

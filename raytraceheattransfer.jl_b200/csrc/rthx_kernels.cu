@@ -1374,7 +1374,10 @@ __device__ __forceinline__ unsigned int queue_dispatch(const TraceParams& p, con
 // Slot layout (structure of arrays over the WQ slots of a warp): px | py | dx | dy | S as doubles, rid | meta as u32;
 //   meta = event | coarse face << 14 | (pending only) edge << 23 | gas << 25; a pending entry keeps (v0.y, v0.z) in the S slot.
 // ------------------------------------------------------------------------------------------------------------
-template <bool SURF, bool UNIFORM, bool REC, int DEPTH, bool BILIN>
+//   SQK: 0 = any mesh with analytic locators (coarse descriptors in shared memory); 1 / 2 = the whole domain is ONE parallelogram
+//        (axis-aligned / general): the consume step is the SQ kernel's — face constants from the kernel-parameter bank, slab distance,
+//        folded lattice inverse, no crossings — and there is no coarse index to carry.
+template <bool SURF, bool UNIFORM, bool REC, int DEPTH, bool BILIN, int SQK>
 __device__ __forceinline__ unsigned int queue_multi_loop(const TraceParams& p, const QueueBlock& b) {
   constexpr int WQ = 32 * DEPTH;
   const int lane = b.lane;
@@ -1419,7 +1422,7 @@ __device__ __forceinline__ unsigned int queue_multi_loop(const TraceParams& p, c
         ndx = sqrt_pos(fma(-ch, ch, 0.25)) * cos2pi_centered_x2(u32d_centered(v0yz.x, p.k_u32c));
         ndy = ch + ch;
       } else {
-        const CoarseDev& cf = b.coarse[cc];
+        const CoarseDev& cf = SQK ? p.face0 : b.coarse[cc];
         const double hnx = cf.nx[k], hny = cf.ny[k];                 // outward normal of the coarse edge (= of every fine wall on it)
         if (p.specular) {
           const double idx_ = q[2 * WQ + s], idy_ = q[3 * WQ + s];   // incoming direction: mirror the in-plane components
@@ -1490,48 +1493,77 @@ __device__ __forceinline__ unsigned int queue_multi_loop(const TraceParams& p, c
       bool park = false;                                               // this lane's ray survived an interaction
       uint32_t park_meta = 0u, park_y = 0u, park_z = 0u;
       if (active) {
-        const CoarseDev& cf = b.coarse[c];
         int k;
-        double u;
-        const bool edge = dist_face<BILIN>(cf, px, py, dx, dy, p.k_eps, u, k);
-        bool gas, ok = true;
-        double tau_b = 0.0, Sg;
-        if (UNIFORM) {
-          gas = S < u;
-          Sg = S;
+        bool gas, ended = true;
+        int absorber = -1;
+        if constexpr (SQK != 0) {
+          // single parallelogram: one distToSurface2D, one decision, one fine-cell location (traceRay.jl:27-52), as in sq_ray_loop
+          constexpr bool AXIS = SQK == 1;
+          const CoarseDev& cf = p.face0;
+          double u;
+          const bool edge = dist_sq<AXIS>(p, px, py, dx, dy, dy, __double2hiint(dy), u, k);
+          bool ok = true;
+          double Sg;
+          if (UNIFORM) {
+            gas = S < u;
+            Sg = S;
+          } else {
+            const int f0 = locate_sq<AXIS>(p, px, py);                           // traceRay.jl:87-100
+            ok = f0 >= 0;
+            const double local_beta = ok ? b.beta_band[f0] : 0.0;
+            gas = local_beta * u >= S;
+            Sg = S / local_beta;
+          }
+          const bool hit = !gas & edge & (cf.solid[k] != 0);                     // an open edge has no neighbour face: the ray is lost
+          if (ok & (gas | hit)) {
+            const double adv = (gas ? Sg : u) - p.nudge;
+            px = fma(adv, dx, px);
+            py = fma(adv, dy, py);
+            const int f = locate_sq<AXIS>(p, px, py);
+            if (f >= 0) absorber = gas ? p.n_surfaces + f : __ldg(p.abs_tab + (unsigned)(f * 5 + 1 + k));
+          }
         } else {
-          const int l0 = lattice_cell<BILIN>(cf, px, py);                      // traceRay.jl:87-100
-          const int f0 = l0 < 0 ? -1 : (cf.kind == KIND_AFFINE_TRI ? __ldg(p.lattice + cf.lat_off + l0) : l0);
-          ok = f0 >= 0;
-          const double local_beta = ok ? b.beta_band[cf.fine_off + f0] : 0.0;
-          tau_b = local_beta * u;
-          gas = acc + tau_b >= S;
-          Sg = (S - acc) / local_beta;
-        }
-        const bool solid = cf.solid[k] != 0;
-        const int nc = cf.nbr[k];
-        const bool cross = ok & !gas & edge & !solid & (BILIN | (nc >= 0)) & (it < 9999);
-        const bool tallied = ok & (gas | (edge & solid));
-        const double adv = gas ? Sg - p.nudge : (solid ? u - p.nudge : u + p.nudge);
-        if (cross | tallied) {
-          px = fma(adv, dx, px);
-          py = fma(adv, dy, py);
-        }
-        bool ended = !cross;
-        if (cross) {
-          if (UNIFORM) S -= u; else acc += tau_b;
-          int nn = nc;
-          if (BILIN) { if (nn < 0) nn = find_face_generic(p, 0, px, py); }
-          if (nn >= 0) { c = nn; ++it; }
-          else ended = true;                                           // left the domain: lost, like the reference's `nothing`
-        }
-        if (ended) {
-          int absorber = -1;
-          if (tallied) {
+          const CoarseDev& cf = b.coarse[c];
+          double u;
+          const bool edge = dist_face<BILIN>(cf, px, py, dx, dy, p.k_eps, u, k);
+          bool ok = true;
+          double tau_b = 0.0, Sg;
+          if (UNIFORM) {
+            gas = S < u;
+            Sg = S;
+          } else {
+            const int l0 = lattice_cell<BILIN>(cf, px, py);                      // traceRay.jl:87-100
+            const int f0 = l0 < 0 ? -1 : (cf.kind == KIND_AFFINE_TRI ? __ldg(p.lattice + cf.lat_off + l0) : l0);
+            ok = f0 >= 0;
+            const double local_beta = ok ? b.beta_band[cf.fine_off + f0] : 0.0;
+            tau_b = local_beta * u;
+            gas = acc + tau_b >= S;
+            Sg = (S - acc) / local_beta;
+          }
+          const bool solid = cf.solid[k] != 0;
+          const int nc = cf.nbr[k];
+          const bool cross = ok & !gas & edge & !solid & (BILIN | (nc >= 0)) & (it < 9999);
+          const bool tallied = ok & (gas | (edge & solid));
+          const double adv = gas ? Sg - p.nudge : (solid ? u - p.nudge : u + p.nudge);
+          if (cross | tallied) {
+            px = fma(adv, dx, px);
+            py = fma(adv, dy, py);
+          }
+          ended = !cross;
+          if (cross) {
+            if (UNIFORM) S -= u; else acc += tau_b;
+            int nn = nc;
+            if (BILIN) { if (nn < 0) nn = find_face_generic(p, 0, px, py); }
+            if (nn >= 0) { c = nn; ++it; }
+            else ended = true;                                           // left the domain: lost, like the reference's `nothing`
+          }
+          if (ended & tallied) {
             const int l = lattice_cell<BILIN>(cf, px, py);
             if (l >= 0) absorber = (gas & (cf.kind != KIND_AFFINE_TRI)) ? p.n_surfaces + cf.fine_off + l
                                                                         : __ldg(p.abs_tab + (size_t)(cf.abs_off + l) * 5 + (gas ? 0 : 1 + k));
           }
+        }
+        if (ended) {
           if (absorber >= 0) {
             // absorb, or live on (traceSingleRay.jl:24-79): v0.x decision, v0.w roulette; v0.y / v0.z feed the new direction
             if (event >= 16000) {                                      // call# is a 16-bit field
@@ -1588,7 +1620,7 @@ __device__ __forceinline__ unsigned int queue_multi_loop(const TraceParams& p, c
               dx = sqrt_pos(fma(-ch, ch, 0.25)) * cos2pi_centered_x2(u32d_centered(park_y, p.k_u32c));
               dy = ch + ch;
             } else {
-              const CoarseDev& cf = b.coarse[c];
+              const CoarseDev& cf = SQK ? p.face0 : b.coarse[c];
               const double hnx = cf.nx[k], hny = cf.ny[k];
               if (p.specular) {
                 const double dn = dx * hnx + dy * hny;
@@ -1617,10 +1649,10 @@ __device__ __forceinline__ unsigned int queue_multi_loop(const TraceParams& p, c
   return n_lost;
 }
 
-template <bool SURF, int DEPTH, bool BILIN>
+template <bool SURF, int DEPTH, bool BILIN, int SQK>
 __device__ __forceinline__ unsigned int queue_multi_dispatch(const TraceParams& p, const QueueBlock& b, bool uniform, bool rec) {
-  if (uniform) return rec ? queue_multi_loop<SURF, true, true, DEPTH, BILIN>(p, b) : queue_multi_loop<SURF, true, false, DEPTH, BILIN>(p, b);
-  return rec ? queue_multi_loop<SURF, false, true, DEPTH, BILIN>(p, b) : queue_multi_loop<SURF, false, false, DEPTH, BILIN>(p, b);
+  if (uniform) return rec ? queue_multi_loop<SURF, true, true, DEPTH, BILIN, SQK>(p, b) : queue_multi_loop<SURF, true, false, DEPTH, BILIN, SQK>(p, b);
+  return rec ? queue_multi_loop<SURF, false, true, DEPTH, BILIN, SQK>(p, b) : queue_multi_loop<SURF, false, false, DEPTH, BILIN, SQK>(p, b);
 }
 
 // BILIN: the mesh has general convex quadrilateral faces (bilinear lattices); compiled separately so that meshes of parallelograms
@@ -1687,7 +1719,12 @@ __global__ void __launch_bounds__(256, MINB) trace_exchange_queue_kernel(const _
   b.c0 = p.em_coarse[e]; b.n_warps = n_warps; b.warp = warp; b.lane = lane;
 
   unsigned int n_lost0;
-  if (MULTI) n_lost0 = is_surface ? queue_multi_dispatch<true, DEPTH, BILIN>(p, b, uniform, rec_slot >= 0) : queue_multi_dispatch<false, DEPTH, BILIN>(p, b, uniform, rec_slot >= 0);
+  if (MULTI) {
+    // a single parallelogram (p.queue_sq: 1 axis-aligned, 2 general) takes the SQ form of the step; BILIN instances never do
+    if (!BILIN && p.queue_sq == 1) n_lost0 = is_surface ? queue_multi_dispatch<true, DEPTH, false, 1>(p, b, uniform, rec_slot >= 0) : queue_multi_dispatch<false, DEPTH, false, 1>(p, b, uniform, rec_slot >= 0);
+    else if (!BILIN && p.queue_sq == 2) n_lost0 = is_surface ? queue_multi_dispatch<true, DEPTH, false, 2>(p, b, uniform, rec_slot >= 0) : queue_multi_dispatch<false, DEPTH, false, 2>(p, b, uniform, rec_slot >= 0);
+    else n_lost0 = is_surface ? queue_multi_dispatch<true, DEPTH, BILIN, 0>(p, b, uniform, rec_slot >= 0) : queue_multi_dispatch<false, DEPTH, BILIN, 0>(p, b, uniform, rec_slot >= 0);
+  }
   else n_lost0 = is_surface ? queue_dispatch<true, DEPTH, BILIN>(p, b, uniform, rec_slot >= 0) : queue_dispatch<false, DEPTH, BILIN>(p, b, uniform, rec_slot >= 0);
   unsigned int n_lost = n_lost0;
 
