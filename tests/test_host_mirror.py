@@ -204,3 +204,30 @@ def test_dykstra_restatement_properties(rthx_mod):
     assert sm.default_k_dykstra(sp.csc_matrix(np.eye(n)), ns) == 0 and sm.default_k_dykstra(Fn, ns, smooth_surfaces_only=True) == 0
     strong = np.zeros((n, n)); strong[:ns, ns:] = 1.0 / (n - ns); strong[ns:, :ns] = 1.0 / ns
     assert sm.cross_coupling_chi(strong, ns) == pytest.approx(1.0) and sm.default_k_dykstra(strong, ns) == 1
+
+
+def test_triangle_submesh_against_a_hand_execution_of_the_reference(rthx_mod):
+    """Independent pin of the mesh restatement (both sides of every parity test consume domain.py, so a slip in the cell order would
+    cancel there): meshTriangle.jl:2-103 executed BY HAND for the triangle (0,0),(1,0),(0,1), Ndim = 2.
+      longest edge = edge 2 (first maximum of [1, sqrt 2, 1], :15-18)  ->  diag_ind = 2, mirror_ind = 3, mirrored point (1,1) (:27-42),
+      new_points = (v1, v2, mirrored, v3) (:47), tria_ids = [1, 2, 4] (:55); meshQuad 2 x 2 visits (n, m) = (1,1), (2,1), (1,2), (2,2)
+      (meshQuad.jl:139,151); cell (1,1) lies on the triangle's side -> kept as a quad (:89-93); (2,1) and (1,2) straddle the diagonal ->
+      triangles of their vertices [1, 2, 4] with walls [own 1, the diagonal (parent wall 2), own 4] (:73-86); (2,2) is dropped (:94-96).
+    Surfaces are numbered along the walk, wall by wall (createIndexMapping2D.jl:1-20)."""
+    face = rthx_mod.PolyVolume2D([(0, 0), (1, 0), (0, 1)], (True, True, True), 1, 1.0, 0.0)
+    dom = rthx_mod.RayTracingDomain2D([face], [(2, 2)])
+    cells = dom.fine_mesh[0]
+    expect = [
+        ([(0, 0), (.5, 0), (.5, .5), (0, .5)], (True, False, False, True)),      # quad: bottom on edge 1, left on edge 3
+        ([(.5, 0), (1, 0), (.5, .5)], (True, True, False)),                      # triangle: bottom on edge 1, diagonal, inner
+        ([(0, .5), (.5, .5), (0, 1)], (False, True, True)),                      # triangle: inner, diagonal, left on edge 3
+    ]
+    assert len(cells) == 3
+    for cell, (verts, solid) in zip(cells, expect):
+        assert len(cell.vertices) == len(verts)
+        assert all(abs(a - x) < 1e-15 and abs(b - y) < 1e-15 for (a, b), (x, y) in zip(cell.vertices, verts))
+        assert tuple(bool(s) for s in cell.solidWalls) == solid
+    assert dom.surface_mapping == {(1, 1, 1): 1, (1, 1, 4): 2, (1, 2, 1): 3, (1, 2, 2): 4, (1, 3, 2): 5, (1, 3, 3): 6}
+    assert dom.volume_mapping == {(1, 1): 1, (1, 2): 2, (1, 3): 3}
+    flat = rthx_mod.flatten_domain(dom)
+    assert flat.cell_surf_id.tolist() == [[0, -1, -1, 1], [2, 3, -1, -1], [-1, 4, 5, -1]]
