@@ -233,3 +233,37 @@ def test_public_call_beyond_the_shared_memory_histogram_in_row_tiles(rthx_mod, c
     assert sp.issparse(F) and F.shape == (N, N) and F.nnz < 64 * N
     assert np.allclose(np.asarray(F.sum(axis=1)).ravel(), 1.0)
     assert rtm.last_trace_stats["hist_in_smem"] == 0 and rtm.last_phase_ms["row_tiles"] == 4
+
+
+def test_step_flags_signal_wait_and_timeout(rthx_mod, cuda_lib):
+    """rthx_flag_signal / rthx_flag_wait: a wait behind its signal passes, a wait for a value nobody writes gives up after its
+    timeout and raises the error counter instead of hanging the device."""
+    import ctypes as C
+    import torch
+    dev = torch.device("cuda", 0)
+    flags = torch.zeros(8, dtype=torch.int64, device=dev)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    base = flags.data_ptr()
+    assert cuda_lib.rthx_flag_signal(C.c_void_p(base), 5, C.c_void_p(st)) == 0
+    assert cuda_lib.rthx_flag_signal(C.c_void_p(base + 8), 7, C.c_void_p(st)) == 0
+    assert cuda_lib.rthx_flag_wait(C.c_void_p(base), 2, 5, 1.0, C.c_void_p(base + 56), C.c_void_p(st)) == 0
+    torch.cuda.synchronize(dev)
+    assert flags.tolist()[:2] == [5, 7] and flags[7].item() == 0
+    assert cuda_lib.rthx_flag_wait(C.c_void_p(base), 2, 6, 0.05, C.c_void_p(base + 56), C.c_void_p(st)) == 0   # flags[0] = 5 < 6: times out
+    torch.cuda.synchronize(dev)
+    assert flags[7].item() == 1
+
+
+def test_device_count_and_pinned_arrays(rthx_mod, cuda_lib):
+    from rthx._lib import device_count, pinned_empty, release_pinned
+    import torch
+    assert device_count() == torch.cuda.device_count() >= 1
+    a = pinned_empty((1000, 300), np.float64)
+    a[:] = 3.0
+    assert a.shape == (1000, 300) and a.flags["C_CONTIGUOUS"] and float(a.sum()) == 9e5
+    addr = a.ctypes.data
+    del a
+    b = pinned_empty(1000 * 300, np.float64)              # the freed buffer comes back from the pool
+    assert b.ctypes.data == addr
+    del b
+    release_pinned()
