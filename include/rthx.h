@@ -368,6 +368,12 @@ int rthx_flag_wait(const void* flags, int n, uint64_t value, double timeout_s, v
  * pipelined device->host copies of rthx_trace_exchange run at full PCIe speed and overlap with tracing. */
 int rthx_host_register(void* ptr, uint64_t bytes);
 int rthx_host_unregister(void* ptr);
+/* After a multi-GPU trace the result arrays (CSC arrays, F_smooth: ~1 GB each for cfg3) live on ONE device and their device->host
+ * copies are bound by that device's PCIe link while the other links idle.  rthx_set_copy_helpers registers the handles on the other
+ * devices: large copies into page-locked memory are then cut into one slice per device, each slice hopping to its helper over
+ * NVLink and leaving through that device's own link.  n = 0 clears the list; the helpers must outlive their use.          [0.3] */
+int rthx_set_copy_helpers(rthx_handle* h, rthx_handle** helpers, int n);
+
 /* Page-locked host memory for output arrays (count matrix, CSC arrays, F_smooth): device->host copies into it run by DMA at
  * full PCIe speed with no staging pass.  A Julia caller wraps the pointer with unsafe_wrap(Array, ptr, dims).            [0.3] */
 int rthx_host_alloc(void** ptr, uint64_t bytes);

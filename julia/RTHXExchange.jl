@@ -130,7 +130,7 @@ function trace_bins(rtm::RayTracingDomain2D, rays_per_emitter::Integer, nudge::F
     devs = DEVICES[]
     handles = fill(Ptr{Cvoid}(C_NULL), length(devs))
     Fs = Vector{SparseMatrixCSC{Float64,Int}}(undef, nbins)
-    GC.@preserve arrays lost bins0 rec_ids origins endpoints begin
+    GC.@preserve arrays lost bins0 rec_ids origins endpoints handles begin
         check(ccall((:rthx_create_multi, LIB), Cint, (Ptr{Ptr{Cvoid}}, Ref{RthxMesh}, Ptr{Cint}, Cint),
                     handles, mesh, devs, length(devs)), C_NULL)
         args = RthxTraceArgs(rays_per_emitter, 0, SEED[], nudge, nbins, pointer(bins0), 0, 0, 0, 1,
@@ -140,6 +140,9 @@ function trace_bins(rtm::RayTracingDomain2D, rays_per_emitter::Integer, nudge::F
                    (Ptr{Ptr{Cvoid}}, Cint, Ref{RthxTraceArgs}, Ptr{UInt64}, Ptr{UInt64}, Ref{RthxRecOut}, Ref{RthxStats}),
                    handles, length(handles), args, C_NULL, lost, recout, stats)
         check(rc, handles[1])
+        length(handles) > 1 &&                                                   # the read-outs leave through every device's PCIe link
+            check(ccall((:rthx_set_copy_helpers, LIB), Cint, (Ptr{Cvoid}, Ptr{Ptr{Cvoid}}, Cint),
+                        handles[1], pointer(handles, 2), length(handles) - 1), handles[1])
         for b in 1:nbins
             nnz = Ref{Int64}(0)
             check(ccall((:rthx_counts_nnz, LIB), Cint, (Ptr{Cvoid}, Cint, Ref{Int64}), handles[1], b - 1, nnz), handles[1])

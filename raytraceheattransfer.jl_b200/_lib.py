@@ -124,6 +124,8 @@ def load_library():
     L.rthx_host_register.argtypes = [C.c_void_p, C.c_uint64]
     L.rthx_host_unregister.restype = C.c_int
     L.rthx_host_unregister.argtypes = [C.c_void_p]
+    L.rthx_set_copy_helpers.restype = C.c_int
+    L.rthx_set_copy_helpers.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int]
     L.rthx_host_alloc.restype = C.c_int
     L.rthx_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_uint64]
     L.rthx_host_free.restype = C.c_int
@@ -334,6 +336,13 @@ class DeviceTracer:
                                             fv.ctypes.data_as(c_f64p) if normalised else None))
         n = nnz.value
         return row_ptr, cols[:n], (vals[:n] if values else None), (fv[:n] if normalised else None)
+
+    def set_copy_helpers(self, others: Sequence["DeviceTracer"]):
+        """Let large device->host result copies of this tracer (CSC arrays, F_smooth) use the PCIe links of the tracers on the other
+        devices as well (rthx_set_copy_helpers); an empty list clears the registration."""
+        hs = (C.c_void_p * max(1, len(others)))(*[t._h for t in others])
+        self._check(self._L.rthx_set_copy_helpers(self._h, hs, len(others)))
+        self._copy_helpers = list(others)          # keep them alive
 
     def counts_stats(self, bin: int = 0):
         """(nnz, chi) of the counts resident on the device: non-zeros and the surface-gas cross-coupling of the

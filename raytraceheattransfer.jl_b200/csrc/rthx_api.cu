@@ -50,6 +50,7 @@ struct DevRes {
   double* solve_buf = nullptr;              size_t solve_cap = 0;      // Krylov basis + work vectors + matvec partials
   double* solve_mat = nullptr;              size_t solve_mat_cap = 0;  // staged host F of rthx_solve_grey (dense padded / CSC)
   void* stage[2] = {nullptr, nullptr};      size_t stage_cap = 0;      // pinned staging for pageable destinations
+  void* xfer[2] = {nullptr, nullptr};       size_t xfer_cap = 0;       // device staging of a copy helper (multi-link device->host copies)
   cudaEvent_t cev[2] = {nullptr, nullptr};
   bool valid = false;
 };
@@ -60,6 +61,7 @@ struct rthx_handle : DevRes {
   int device = 0;
   std::shared_ptr<HostImage> image;    // host image of the mesh tables (shared by the handles of one rthx_create_multi call)
   bool generic_ready = false;          // generic-locator tables uploaded (ensure_generic)
+  std::vector<rthx_handle*> helpers;   // handles on OTHER devices whose PCIe links carry slices of large result copies (rthx_set_copy_helpers)
   cudaDeviceProp prop{};
   int n_coarse = 0, n_cells = 0, n_bands = 0, ns = 0, N = 0, n_affine = 0, n_bilinear = 0;
   bool queue_ok = false;       // every face has an analytic locator (affine or bilinear)
@@ -102,6 +104,7 @@ void devres_free(DevRes& r) {
   for (auto& e : r.bev) if (e) cudaEventDestroy(e);
   for (auto& e : r.cev) if (e) cudaEventDestroy(e);
   for (auto& sp : r.stage) if (sp) cudaFreeHost(sp);
+  for (auto& xp : r.xfer) if (xp) cudaFree(xp);
   if (r.stream) cudaStreamDestroy(r.stream);
   if (r.stream2) cudaStreamDestroy(r.stream2);
   if (r.copy_stream) cudaStreamDestroy(r.copy_stream);
@@ -1541,6 +1544,16 @@ extern "C" int rthx_trace_exchange_multi(rthx_handle** hs, int n, const rthx_tra
   return RTHX_OK;
 }
 
+extern "C" int rthx_set_copy_helpers(rthx_handle* h, rthx_handle** helpers, int n) {
+  if (!h || n < 0 || (n > 0 && !helpers)) return RTHX_ERR_ARG;
+  h->helpers.clear();
+  for (int i = 0; i < n; ++i) {
+    if (!helpers[i] || helpers[i] == h) return fail(h, RTHX_ERR_ARG, "set_copy_helpers: bad helper handle");
+    if (helpers[i]->device != h->device) h->helpers.push_back(helpers[i]);     // a helper on the same device has no link of its own
+  }
+  return RTHX_OK;
+}
+
 extern "C" int rthx_host_alloc(void** ptr, uint64_t bytes) {
   if (!ptr || bytes == 0) return fail(nullptr, RTHX_ERR_ARG, "rthx_host_alloc: bad argument");
   *ptr = nullptr;
@@ -1675,16 +1688,82 @@ cudaError_t launch_add_base(long long* p, int n, long long base, cudaStream_t st
 
 namespace {
 
-// Device -> host copy of a result array on `stream`, blocking.  Page-locked destinations (cudaHostAlloc / cudaHostRegister,
-// rthx_host_alloc) are written by DMA directly; pageable ones (a plain Julia / numpy array) go through the handle's two pinned
-// staging buffers in 32 MB pieces, the host moving piece k-1 while piece k is in flight.
-int copy_out(rthx_handle* h, void* dst, const void* src_dev, size_t bytes, cudaStream_t stream) {
-  if (bytes == 0) return RTHX_OK;
+// Device -> host copy of a result array on `stream`, blocking: `height` rows of `width` bytes (source pitch spitch, destination
+// pitch dpitch; a flat array is one row).
+//   * page-locked destination (cudaHostAlloc / cudaHostRegister, rthx_host_alloc): DMA.  With copy helpers registered
+//     (rthx_set_copy_helpers: the handles of a multi-GPU trace on the other devices) a large copy is cut into one slice per device:
+//     the owner's slice goes out over its own PCIe link, every other slice hops to its helper over NVLink (cudaMemcpyPeerAsync into
+//     two 16 MB staging buffers, alternating streams) and leaves through THAT device's link — the 1.35 GB of cfg3's CSC arrays and
+//     the 900 MB of F_smooth are PCIe-bound on one link (25 + 16 ms) and the other links are idle after a multi-GPU trace;
+//   * pageable destination (a plain Julia / numpy array): through the handle's two pinned staging buffers in 32 MB pieces, the host
+//     moving piece k-1 while piece k is in flight.
+int copy_out_2d(rthx_handle* h, void* dst, size_t dpitch, const void* src_dev, size_t spitch, size_t width, size_t height, cudaStream_t stream) {
+  if (width == 0 || height == 0) return RTHX_OK;
   cudaPointerAttributes pa;
-  bool pinned = cudaPointerGetAttributes(&pa, dst) == cudaSuccess && (pa.type == cudaMemoryTypeHost || pa.type == cudaMemoryTypeManaged);
+  const bool pinned = cudaPointerGetAttributes(&pa, dst) == cudaSuccess && (pa.type == cudaMemoryTypeHost || pa.type == cudaMemoryTypeManaged);
   cudaGetLastError();
-  if (pinned || bytes <= (size_t(1) << 20)) {
-    CU(h, cudaMemcpyAsync(dst, src_dev, bytes, cudaMemcpyDeviceToHost, stream));
+  const size_t bytes = width * height;
+  auto direct = [&](size_t r0, size_t r1, cudaStream_t st) -> cudaError_t {
+    if (r1 <= r0) return cudaSuccess;
+    if (height == 1) return cudaMemcpyAsync(dst, src_dev, width, cudaMemcpyDeviceToHost, st);
+    return cudaMemcpy2DAsync((char*)dst + r0 * dpitch, dpitch, (const char*)src_dev + r0 * spitch, spitch, width, r1 - r0, cudaMemcpyDeviceToHost, st);
+  };
+  const bool multi_link = pinned && !h->helpers.empty() && bytes >= (size_t(64) << 20) && std::getenv("RTHX_NO_COPY_HELPERS") == nullptr;
+  if (pinned && !multi_link) {
+    CU(h, direct(0, height, stream));
+    CU(h, cudaStreamSynchronize(stream));
+    return RTHX_OK;
+  }
+  if (multi_link) {
+    // a flat array is re-cut into rows of 1 MB so that both shapes share the row-sliced code (the tail goes out with the owner's slice)
+    size_t W = width, H = height, SP = spitch, DP = dpitch, tail = 0;
+    if (height == 1) { W = SP = DP = size_t(1) << 20; H = width / W; tail = width - H * W; }
+    const size_t n_links = h->helpers.size() + 1;
+    const size_t chunk_rows = std::max<size_t>(1, (size_t(16) << 20) / SP);
+    CU(h, cudaEventRecord(h->bev[16], stream));                       // the producer's work is done
+    CU(h, cudaStreamWaitEvent(h->copy_stream, h->bev[16], 0));
+    int rc = RTHX_OK;
+    for (size_t l = 0; l < n_links && rc == RTHX_OK; ++l) {
+      const size_t r0 = H * l / n_links, r1 = H * (l + 1) / n_links;
+      if (l == 0) {
+        if (r1 > r0) CU(h, cudaMemcpy2DAsync(dst, DP, src_dev, SP, W, r1 - r0, cudaMemcpyDeviceToHost, h->copy_stream));
+        if (tail) CU(h, cudaMemcpyAsync((char*)dst + H * W, (const char*)src_dev + H * W, tail, cudaMemcpyDeviceToHost, h->copy_stream));
+        continue;
+      }
+      rthx_handle* g = h->helpers[l - 1];
+      auto enqueue = [&]() -> int {
+        CU(g, cudaSetDevice(g->device));
+        const size_t need = chunk_rows * SP;
+        if (g->xfer_cap < need) {
+          for (auto& xp : g->xfer) { if (xp) cudaFree(xp); xp = nullptr; }
+          g->xfer_cap = 0;
+          for (auto& xp : g->xfer) CU(g, cudaMalloc(&xp, need));
+          g->xfer_cap = need;
+        }
+        CU(g, cudaStreamWaitEvent(g->stream, h->bev[16], 0));
+        CU(g, cudaStreamWaitEvent(g->stream2, h->bev[16], 0));
+        size_t k = 0;
+        for (size_t a = r0; a < r1; a += chunk_rows, ++k) {
+          const size_t b = std::min(r1, a + chunk_rows);
+          cudaStream_t st = (k & 1) ? g->stream2 : g->stream;
+          CU(g, cudaMemcpyPeerAsync(g->xfer[k & 1], g->device, (const char*)src_dev + a * SP, h->device, (b - a - 1) * SP + W, st));
+          CU(g, cudaMemcpy2DAsync((char*)dst + a * DP, DP, g->xfer[k & 1], SP, W, b - a, cudaMemcpyDeviceToHost, st));
+        }
+        return RTHX_OK;
+      };
+      rc = enqueue();
+      if (rc) h->err = g->err;
+    }
+    // wait for every link (also after an error, so that nothing is left in flight on the caller's buffers)
+    for (rthx_handle* g : h->helpers) { cudaSetDevice(g->device); cudaStreamSynchronize(g->stream); cudaStreamSynchronize(g->stream2); }
+    cudaSetDevice(h->device);
+    if (rc) return rc;
+    CU(h, cudaStreamSynchronize(h->copy_stream));
+    return RTHX_OK;
+  }
+  // pageable destination
+  if (bytes <= (size_t(1) << 20)) {
+    CU(h, direct(0, height, stream));
     CU(h, cudaStreamSynchronize(stream));
     return RTHX_OK;
   }
@@ -1695,19 +1774,32 @@ int copy_out(rthx_handle* h, void* dst, const void* src_dev, size_t bytes, cudaS
     for (auto& sp : h->stage) CU(h, cudaMallocHost(&sp, piece));
     h->stage_cap = piece;
   }
-  const size_t n_pieces = (bytes + piece - 1) / piece;
+  // pieces are whole rows (a flat array: 32 MB runs); the staging buffers hold them packed (pitch = width)
+  const size_t rows_per_piece = height == 1 ? 1 : std::max<size_t>(1, piece / width);
+  const size_t n_pieces = height == 1 ? (width + piece - 1) / piece : (height + rows_per_piece - 1) / rows_per_piece;
+  auto piece_range = [&](size_t k, size_t& off_src, size_t& off_dst, size_t& w, size_t& rows) {
+    if (height == 1) { off_src = off_dst = k * piece; w = std::min(piece, width - k * piece); rows = 1; }
+    else { const size_t a = k * rows_per_piece; rows = std::min(rows_per_piece, height - a); off_src = a * spitch; off_dst = a * dpitch; w = width; }
+  };
+  auto unload = [&](size_t k) {
+    size_t os, od, w, rows; piece_range(k, os, od, w, rows);
+    if (rows == 1 || dpitch == w) parallel_memcpy((char*)dst + od, h->stage[k & 1], w * rows);
+    else for (size_t r = 0; r < rows; ++r) std::memcpy((char*)dst + od + r * dpitch, (const char*)h->stage[k & 1] + r * w, w);
+  };
   for (size_t k = 0; k < n_pieces; ++k) {
-    const size_t off = k * piece, len = std::min(piece, bytes - off);
-    CU(h, cudaMemcpyAsync(h->stage[k & 1], (const char*)src_dev + off, len, cudaMemcpyDeviceToHost, stream));
+    size_t os, od, w, rows; piece_range(k, os, od, w, rows);
+    if (rows == 1) CU(h, cudaMemcpyAsync(h->stage[k & 1], (const char*)src_dev + os, w, cudaMemcpyDeviceToHost, stream));
+    else CU(h, cudaMemcpy2DAsync(h->stage[k & 1], w, (const char*)src_dev + os, spitch, w, rows, cudaMemcpyDeviceToHost, stream));
     CU(h, cudaEventRecord(h->cev[k & 1], stream));
-    if (k >= 1) {
-      CU(h, cudaEventSynchronize(h->cev[(k - 1) & 1]));
-      parallel_memcpy((char*)dst + (k - 1) * piece, h->stage[(k - 1) & 1], piece);
-    }
+    if (k >= 1) { CU(h, cudaEventSynchronize(h->cev[(k - 1) & 1])); unload(k - 1); }
   }
   CU(h, cudaEventSynchronize(h->cev[(n_pieces - 1) & 1]));
-  parallel_memcpy((char*)dst + (n_pieces - 1) * piece, h->stage[(n_pieces - 1) & 1], bytes - (n_pieces - 1) * piece);
+  unload(n_pieces - 1);
   return RTHX_OK;
+}
+
+int copy_out(rthx_handle* h, void* dst, const void* src_dev, size_t bytes, cudaStream_t stream) {
+  return copy_out_2d(h, dst, bytes, src_dev, bytes, bytes, 1, stream);
 }
 
 // Row pass over the resident counts of `bin`: non-zeros and total per row, row pointers on the device, and the surface-gas
@@ -1905,9 +1997,10 @@ extern "C" int rthx_smooth_DkAP(rthx_handle* h, int source, const void* src_host
     src_counts = nullptr; src_F = Fd; src_rs = rsd; ld = ldx;
   }
   CU(h, rthx::run_ap(src_counts, src_F, src_rs, ld, w_dev, n, ldx, max_iters, tgt, h->smooth_X, rs, r, u, part, part_host, h->stream, h->ev[0], h->ev[1], &res));
-  CU(h, cudaMemcpy2DAsync(F_out, sizeof(double) * (size_t)n, h->smooth_X, sizeof(double) * ldx, sizeof(double) * (size_t)n, (size_t)n,
-                          cudaMemcpyDeviceToHost, h->stream));
-  CU(h, cudaStreamSynchronize(h->stream));
+  {
+    const int rcc = copy_out_2d(h, F_out, sizeof(double) * (size_t)n, h->smooth_X, sizeof(double) * ldx, sizeof(double) * (size_t)n, (size_t)n, h->stream);
+    if (rcc) return rcc;
+  }
   h->smooth_n = n; h->smooth_ldx = ldx;
   double pass_ms = 0;
   if (measure_pass) {

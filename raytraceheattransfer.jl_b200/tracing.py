@@ -147,6 +147,7 @@ def computeExchangeFactorsBins(rtm, rays_per_emitter: int, nudge: float, spectra
     else:
         from ._lib import trace_multi
         out = trace_multi(trs, rays_per_emitter, dense=False, **kw)
+        tr.set_copy_helpers(trs[1:])           # the read-outs below leave through every device's PCIe link
     t1 = time.perf_counter()
     rtm.last_trace_stats = out["stats"]
     rtm.last_lost = out["lost"]

@@ -267,3 +267,30 @@ def test_device_count_and_pinned_arrays(rthx_mod, cuda_lib):
     assert b.ctypes.data == addr
     del b
     release_pinned()
+
+
+@pytest.mark.skipif("_n_gpus() < 2", reason="needs two GPUs (gpurun --gpus 2)")
+def test_multi_link_result_copies_equal_single_link(rthx_mod, cuda_lib):
+    """rthx_set_copy_helpers: the CSC arrays and F_smooth (> 64 MB each here) leave device 0 in slices over every device's PCIe link
+    (NVLink hop + that device's D2H); bit-identical to the single-link copies, flat arrays and pitched rows alike."""
+    from rthx._lib import create_multi, trace_multi
+    n = _n_gpus()
+    rtm = rthx_mod.meshes.square_domain(75, kappa=0.3)
+    flat = rthx_mod.flatten_domain(rtm)
+    trs = create_multi(flat, list(range(n)))
+    tr = trs[0]
+    N = tr.n_elements
+    trace_multi(trs, 40000, dense=False, seed=3)
+    w = rthx_mod.get_w(rtm)
+    a = tr.counts_csc(0, values=True, index64=True)
+    Fa, _ = tr.smooth(w / w.min(), max_iters=40)
+    assert a[1].nbytes >= (64 << 20) and Fa.nbytes >= (64 << 20)
+    tr.set_copy_helpers(trs[1:])
+    b = tr.counts_csc(0, values=True, index64=True)
+    Fb, _ = tr.smooth(w / w.min(), max_iters=40)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    assert np.array_equal(Fa, Fb)
+    tr.set_copy_helpers([])
+    for t in trs:
+        t.close()
