@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "rthx_internal.h"
+#include "rthx_grid.h"
 
 using namespace rthx;
 
@@ -163,77 +164,6 @@ struct Arena {
 // host-side mesh preparation
 // ---------------------------------------------------------------------------------------------------------------
 namespace {
-
-struct Poly { int n; double vx[4], vy[4], nx[4], ny[4], midx, midy, volume, bb[4]; };
-
-void edge_normal(double x1, double y1, double x2, double y2, double midx, double midy, double* nx, double* ny) {
-  const double ex = x2 - x1, ey = y2 - y1;
-  double ax = ey, ay = -ex;
-  const double len = std::sqrt(ax * ax + ay * ay);
-  ax /= len; ay /= len;
-  const double wmx = (x1 + x2) / 2, wmy = (y1 + y2) / 2;
-  if (ax * (wmx - midx) + ay * (wmy - midy) < 0) { ax = -ax; ay = -ay; }
-  *nx = ax; *ny = ay;
-}
-
-void poly_finish(Poly& p) {
-  p.bb[0] = p.bb[2] = INFINITY; p.bb[1] = p.bb[3] = -INFINITY;
-  for (int i = 0; i < p.n; ++i) {
-    const int j = (i + 1) % p.n;
-    edge_normal(p.vx[i], p.vy[i], p.vx[j], p.vy[j], p.midx, p.midy, &p.nx[i], &p.ny[i]);
-    p.bb[0] = std::min(p.bb[0], p.vx[i]); p.bb[1] = std::max(p.bb[1], p.vx[i]);
-    p.bb[2] = std::min(p.bb[2], p.vy[i]); p.bb[3] = std::max(p.bb[3], p.vy[i]);
-  }
-  for (int i = p.n; i < 4; ++i) { p.vx[i] = p.vy[i] = p.nx[i] = p.ny[i] = 0.0; }
-}
-
-// spatialAccelerations.jl:72-89 + :2-59; buckets appended to the global CSR arrays.
-void build_grid(const Poly* faces, int n, int poly_base, FaceSetDev& fs, std::vector<int32_t>& bstart, std::vector<int32_t>& bitems) {
-  double total = 0;
-  for (int i = 0; i < n; ++i) total += faces[i].volume;
-  const double cell = std::sqrt(total / n) * 2.0;
-  double min_x = INFINITY, min_y = INFINITY, max_x = -INFINITY, max_y = -INFINITY;
-  for (int i = 0; i < n; ++i) {
-    min_x = std::min(min_x, faces[i].bb[0]); max_x = std::max(max_x, faces[i].bb[1]);
-    min_y = std::min(min_y, faces[i].bb[2]); max_y = std::max(max_y, faces[i].bb[3]);
-  }
-  const double pad = cell * 0.1;
-  min_x -= pad; min_y -= pad; max_x += pad; max_y += pad;
-  int nx = std::max(1, (int)std::ceil((max_x - min_x) / cell)), ny = std::max(1, (int)std::ceil((max_y - min_y) / cell));
-  // two passes over the faces (count, then fill) into one CSR block: no per-bucket vectors
-  const size_t nb = (size_t)nx * ny;
-  std::vector<int32_t> cnt(nb + 1, 0);
-  auto range = [&](const Poly& f, int& si, int& ei, int& sj, int& ej) {
-    si = std::max(1, (int)std::floor((f.bb[0] - min_x) / cell) + 1); ei = std::min(nx, (int)std::ceil((f.bb[1] - min_x) / cell));
-    sj = std::max(1, (int)std::floor((f.bb[2] - min_y) / cell) + 1); ej = std::min(ny, (int)std::ceil((f.bb[3] - min_y) / cell));
-  };
-  for (int f = 0; f < n; ++f) {
-    int si, ei, sj, ej; range(faces[f], si, ei, sj, ej);
-    for (int j = sj; j <= ej; ++j)
-      for (int i = si; i <= ei; ++i) ++cnt[(size_t)(i - 1) + (size_t)(j - 1) * nx + 1];
-  }
-  for (size_t b = 0; b < nb; ++b) cnt[b + 1] += cnt[b];
-  const size_t items0 = bitems.size();
-  bitems.resize(items0 + (size_t)cnt[nb]);
-  std::vector<int32_t> cur(cnt.begin(), cnt.end() - 1);
-  for (int f = 0; f < n; ++f) {          // ascending face index within every bucket ("first PIP hit" is deterministic)
-    int si, ei, sj, ej; range(faces[f], si, ei, sj, ej);
-    for (int j = sj; j <= ej; ++j)
-      for (int i = si; i <= ei; ++i) bitems[items0 + (size_t)cur[(size_t)(i - 1) + (size_t)(j - 1) * nx]++] = f;
-  }
-  fs.ox = min_x; fs.oy = min_y; fs.inv_cell = 1.0 / cell; fs.nx = nx; fs.ny = ny;
-  fs.poly_base = poly_base; fs.n_faces = n; fs.pad_ = 0;
-  // bucket_start holds absolute offsets into bucket_items; one shared terminator per set
-  if (bstart.empty()) bstart.push_back((int32_t)items0);
-  fs.bucket_off = (int32_t)bstart.size() - 1;
-  for (size_t b = 0; b < nb; ++b) bstart.push_back((int32_t)(items0 + (size_t)cnt[b + 1]));
-}
-
-// packed record of the generic locator (point_in_rec, rthx_kernels.cu): bbox, vx[4], vy[4]; a triangle repeats vertex 0 in slot 3
-void poly_record(const Poly& p, double* rec) {
-  rec[0] = p.bb[0]; rec[1] = p.bb[1]; rec[2] = p.bb[2]; rec[3] = p.bb[3];
-  for (int i = 0; i < 4; ++i) { const int k = i < p.n ? i : 0; rec[4 + i] = p.vx[k]; rec[8 + i] = p.vy[k]; }
-}
 
 bool close_pt(double ax, double ay, double bx, double by, double tol) { return std::fabs(ax - bx) <= tol && std::fabs(ay - by) <= tol; }
 
@@ -401,7 +331,7 @@ void give_pinned(unsigned char* p, size_t cap) {
 struct HostImage {
   unsigned char* data = nullptr;
   size_t cap = 0, bytes = 0, total = 0;      // pinned capacity, image bytes, arena bytes incl. the device-only scratch regions
-  size_t o_coarse = 0, o_sets = 0, o_bstart = 0, o_bitems = 0, o_bbb = 0, o_crec = 0, o_nv = 0, o_pvx = 0, o_pvy = 0, o_mid = 0, o_vol = 0, o_surf = 0, o_beta = 0,
+  size_t o_coarse = 0, o_sets = 0, o_bent = 0, o_bcand = 0, o_frec = 0, o_nv = 0, o_pvx = 0, o_pvy = 0, o_mid = 0, o_vol = 0, o_surf = 0, o_beta = 0,
          o_ub = 0, o_lat = 0, o_abs = 0, o_omega = 0, o_eps = 0, o_ec = 0, o_ew = 0, o_eco = 0, o_bins = 0, o_rec = 0, o_lost = 0;
   int nc = 0, ncell = 0, ns = 0, N = 0, nb = 0, n_affine = 0, n_bilinear = 0;
   bool has_eps = false, nbr_complete = true, needs_generic = false;
@@ -457,8 +387,8 @@ int prepare_mesh(const rthx_mesh* m, std::shared_ptr<HostImage>& out, std::strin
   // coarse descriptors: lattice detection, absorber tables, neighbour table; the coarse-set locator grid (set 0)
   std::vector<FaceSetDev> sets(1 + (size_t)nc);
   std::memset(sets.data(), 0, sizeof(FaceSetDev) * sets.size());
-  std::vector<int32_t> bstart, bitems, lattice, abs_tab;
-  build_grid(cpolys.data(), nc, ncell, sets[0], bstart, bitems);
+  std::vector<int32_t> bent, bcand, lattice, abs_tab;
+  build_grid(cpolys.data(), nc, ncell, sets[0], bent, bcand);  // set 0 (coarse faces) only; the fine sets belong to ensure_generic
   std::vector<CoarseDev> coarse(nc);
   const double ext_tol = 1e-9;
   for (int c = 0; c < nc; ++c) {
@@ -539,8 +469,7 @@ int prepare_mesh(const rthx_mesh* m, std::shared_ptr<HostImage>& out, std::strin
   const size_t npoly = (size_t)ncell + nc;
   Layout L;
   im->o_coarse = L.add(sizeof(CoarseDev) * coarse.size()); im->o_sets = L.add(sizeof(FaceSetDev) * sets.size());
-  im->o_bstart = L.add(4 * bstart.size()); im->o_bitems = L.add(4 * bitems.size());
-  im->o_crec = L.add(96 * (size_t)nc); im->o_bbb = L.add(32 * bitems.size());
+  im->o_bent = L.add(4 * bent.size()); im->o_bcand = L.add(4 * bcand.size()); im->o_frec = L.add(8 * FREC * (size_t)nc);
   im->o_nv = L.add(4 * npoly); im->o_pvx = L.add(32 * npoly); im->o_pvy = L.add(32 * npoly);
   im->o_mid = L.add(16 * (size_t)ncell); im->o_vol = L.add(8 * (size_t)ncell); im->o_surf = L.add(16 * (size_t)ncell);
   im->o_beta = L.add(8 * (size_t)nb * ncell); im->o_ub = L.add(8 * (size_t)nb);
@@ -556,10 +485,9 @@ int prepare_mesh(const rthx_mesh* m, std::shared_ptr<HostImage>& out, std::strin
   lap("pinned image");
   std::memcpy(im->at<CoarseDev>(im->o_coarse), coarse.data(), sizeof(CoarseDev) * coarse.size());
   std::memcpy(im->at<FaceSetDev>(im->o_sets), sets.data(), sizeof(FaceSetDev) * sets.size());
-  std::memcpy(im->at<int32_t>(im->o_bstart), bstart.data(), 4 * bstart.size());
-  if (!bitems.empty()) std::memcpy(im->at<int32_t>(im->o_bitems), bitems.data(), 4 * bitems.size());
-  for (int c = 0; c < nc; ++c) poly_record(cpolys[c], im->at<double>(im->o_crec) + 12 * (size_t)c);
-  for (size_t k = 0; k < bitems.size(); ++k) std::memcpy(im->at<double>(im->o_bbb) + 4 * k, cpolys[bitems[k]].bb, 32);   // set 0 only: items are coarse faces
+  std::memcpy(im->at<int32_t>(im->o_bent), bent.data(), 4 * bent.size());
+  if (!bcand.empty()) std::memcpy(im->at<int32_t>(im->o_bcand), bcand.data(), 4 * bcand.size());
+  for (int c = 0; c < nc; ++c) face_record(cpolys[c], nullptr, im->at<double>(im->o_frec) + FREC * (size_t)c);
   std::memcpy(im->at<int32_t>(im->o_lat), lattice.data(), 4 * lattice.size());
   std::memcpy(im->at<int32_t>(im->o_abs), abs_tab.data(), 4 * abs_tab.size());
   {
@@ -693,13 +621,12 @@ int create_on_device(rthx_handle** out, const std::shared_ptr<HostImage>& im, in
   std::memset(&P, 0, sizeof(P));
   unsigned char* b8 = static_cast<unsigned char*>(h->arena);
   P.coarse = (const CoarseDev*)(b8 + im->o_coarse); P.sets = (const FaceSetDev*)(b8 + im->o_sets);
-  P.bucket_start = (const int32_t*)(b8 + im->o_bstart); P.bucket_items = (const int32_t*)(b8 + im->o_bitems);
-  P.bucket_bb = (const double*)(b8 + im->o_bbb);
+  // bucket grid + polygon records of the coarse set only (the general queue variant's crossing search; records are indexed by
+  // polygon = n_cells + coarse face, so the base pointer is offset and never dereferenced below n_cells); ensure_generic re-points them
+  P.bucket_ent = (const int4*)(b8 + im->o_bent); P.bucket_cand = (const int32_t*)(b8 + im->o_bcand);
+  P.face_rec = (const double*)(b8 + im->o_frec) - FREC * (size_t)im->ncell;
   P.poly_nv = (const int32_t*)(b8 + im->o_nv); P.poly_vx = (const double*)(b8 + im->o_pvx); P.poly_vy = (const double*)(b8 + im->o_pvy);
   P.poly_nx = nullptr; P.poly_ny = nullptr;      // per-polygon normals belong to the generic tables (ensure_generic)
-  // packed records: only those of the coarse polygons (indices >= n_cells, the coarse-set locator of the general queue variant)
-  // exist until the generic tables are built — the base pointer is offset accordingly and never dereferenced below n_cells
-  P.poly_rec = (const double*)(b8 + im->o_crec) - 12 * (size_t)im->ncell;
   P.cell_mid = (const double*)(b8 + im->o_mid); P.cell_volume = (const double*)(b8 + im->o_vol);
   P.cell_surf_id = (const int32_t*)(b8 + im->o_surf); P.beta = (const double*)(b8 + im->o_beta); P.uniform_beta = (const double*)(b8 + im->o_ub);
   P.omega = (const double*)(b8 + im->o_omega); P.eps = (const double*)(b8 + im->o_eps);
@@ -770,24 +697,18 @@ static int ensure_generic(rthx_handle* h) {
   }
   for (int c = 0; c < nc; ++c) polys[(size_t)ncell + c] = im.coarse_polys[c];
   std::vector<FaceSetDev> sets(1 + (size_t)nc);
-  std::vector<int32_t> bstart, bitems;
-  build_grid(&polys[ncell], nc, ncell, sets[0], bstart, bitems);
-  for (int c = 0; c < nc; ++c) build_grid(&polys[im.fine_off[c]], im.fine_off[c + 1] - im.fine_off[c], im.fine_off[c], sets[1 + c], bstart, bitems);
-  std::vector<double> pnx(polys.size() * 4), pny(polys.size() * 4), recs(polys.size() * 12);
+  std::vector<int32_t> bent, bcand;
+  build_grid(&polys[ncell], nc, ncell, sets[0], bent, bcand);
+  for (int c = 0; c < nc; ++c) build_grid(&polys[im.fine_off[c]], im.fine_off[c + 1] - im.fine_off[c], im.fine_off[c], sets[1 + c], bent, bcand);
+  std::vector<double> pnx((size_t)ncell * 4), pny((size_t)ncell * 4), frec(polys.size() * FREC);
+  const int32_t* surf = im.at<int32_t>(im.o_surf);
   for (size_t i = 0; i < polys.size(); ++i) {
-    for (int k = 0; k < 4; ++k) { pnx[4 * i + k] = polys[i].nx[k]; pny[4 * i + k] = polys[i].ny[k]; }
-    poly_record(polys[i], recs.data() + 12 * i);
-  }
-  // bounding boxes next to the bucket lists: item k of set s names polygon poly_base(s) + bitems[k]
-  std::vector<double> bbb(bitems.size() * 4);
-  for (size_t sidx = 0; sidx < sets.size(); ++sidx) {
-    const FaceSetDev& fs = sets[sidx];
-    const size_t k0 = (size_t)bstart[fs.bucket_off], k1 = (size_t)bstart[(size_t)fs.bucket_off + (size_t)fs.nx * fs.ny];
-    for (size_t k = k0; k < k1; ++k) std::memcpy(&bbb[4 * k], polys[(size_t)fs.poly_base + bitems[k]].bb, 32);
+    if (i < (size_t)ncell)
+      for (int k = 0; k < 4; ++k) { pnx[4 * i + k] = polys[i].nx[k]; pny[4 * i + k] = polys[i].ny[k]; }
+    face_record(polys[i], i < (size_t)ncell ? surf + 4 * i : nullptr, &frec[FREC * i]);
   }
   Arena A;
-  const size_t o_sets = A.add(sets), o_bstart = A.add(bstart), o_bitems = A.add(bitems), o_pnx = A.add(pnx), o_pny = A.add(pny), o_rec = A.add(recs),
-               o_bbb = A.add(bbb);
+  const size_t o_sets = A.add(sets), o_bent = A.add(bent), o_bcand = A.add(bcand), o_pnx = A.add(pnx), o_pny = A.add(pny), o_frec = A.add(frec);
   CU(h, cudaSetDevice(h->device));
   if (h->generic_cap < A.total) {
     cudaFree(h->generic_arena);
@@ -798,9 +719,9 @@ static int ensure_generic(rthx_handle* h) {
   CU(h, cudaMemcpy(h->generic_arena, A.host.data(), A.host.size(), cudaMemcpyHostToDevice));
   unsigned char* b8 = static_cast<unsigned char*>(h->generic_arena);
   TraceParams& P = h->base;
-  P.sets = (const FaceSetDev*)(b8 + o_sets); P.bucket_start = (const int32_t*)(b8 + o_bstart); P.bucket_items = (const int32_t*)(b8 + o_bitems);
+  P.sets = (const FaceSetDev*)(b8 + o_sets); P.bucket_ent = (const int4*)(b8 + o_bent); P.bucket_cand = (const int32_t*)(b8 + o_bcand);
+  P.face_rec = (const double*)(b8 + o_frec);
   P.poly_nx = (const double*)(b8 + o_pnx); P.poly_ny = (const double*)(b8 + o_pny);
-  P.poly_rec = (const double*)(b8 + o_rec); P.bucket_bb = (const double*)(b8 + o_bbb);
   h->mesh_bytes = im.bytes + A.host.size();
   h->generic_ready = true;
   return RTHX_OK;

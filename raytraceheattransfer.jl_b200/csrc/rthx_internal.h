@@ -37,28 +37,27 @@ static_assert(sizeof(CoarseDev) % 16 == 0, "CoarseDev must stay a multiple of 16
 // Uniform-grid face set for the reference-faithful locator (spatialAccelerations.jl:2-59).
 // Set 0 = coarse mesh, set 1+c = fine cells of coarse face c.
 struct FaceSetDev {
-  double ox, oy, inv_cell;
+  double ox, oy;         // grid origin
+  double inv_cx, inv_cy; // 1 / bucket size per axis
   int32_t nx, ny;
-  int32_t bucket_off;    // offset into bucket_start (which holds absolute offsets into bucket_items)
+  int32_t bucket_off;    // first bucket of this set in bucket_ent
   int32_t poly_base;     // local face f of this set is polygon poly_base + f (cells first, then coarse faces)
-  int32_t n_faces;
-  int32_t pad_;
 };
+static_assert(sizeof(FaceSetDev) == 48, "FaceSetDev is read with three 16-byte loads");
 
 struct TraceParams {
   // mesh (device pointers)
   const CoarseDev* coarse;
   const FaceSetDev* sets;
-  const int32_t* bucket_start;
-  const int32_t* bucket_items;
-  const double* bucket_bb;     // [n_items*4] bounding box (xmin, xmax, ymin, ymax) of the polygon bucket_items[k] names
+  const int4* bucket_ent;      // per bucket {code, a, b, c}: -1 empty | 0 sole face a | k = 1..3 candidates a, b, c | k > 3 candidates bucket_cand[a .. a+k)
+  const int32_t* bucket_cand;
+  const double* face_rec;      // [n_poly*12] one 96-byte record per polygon: vx[4], vy[4] (a triangle repeats vertex 0 in slot 3), {vertex count,
+                               // normal-orientation bits, surface ids of walls 0..3} (rthx_api.cu, face_record)
   const int32_t* poly_nv;
   const double* poly_vx;       // [n_poly*4]
   const double* poly_vy;
-  const double* poly_nx;       // unit outward normals per polygon edge
+  const double* poly_nx;       // [n_cells*4] unit outward normals per cell edge (generic tables only)
   const double* poly_ny;
-  const double* poly_rec;      // [n_poly*12] packed records of the generic locator: bbox (xmin, xmax, ymin, ymax), vx[4], vy[4] (a triangle repeats
-                               // vertex 0 in slot 3).  Until the generic tables are built only the coarse polygons' records exist (indices >= n_cells).
   const double* cell_mid;      // [n_cells*2]
   const double* cell_volume;   // [n_cells]
   const int32_t* cell_surf_id; // [n_cells*4]

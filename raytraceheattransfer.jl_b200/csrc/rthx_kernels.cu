@@ -219,40 +219,53 @@ __device__ __forceinline__ double dist_fast(const CoarseDev& f, double px, doubl
   return bd > 0.0 ? div_pos(bn, bd) : CUDART_INF;
 }
 
-// distToSurface2D on an arbitrary polygon of the generic tables, index of the nearest edge only (the wall of a fine cell a ray
-// ends on, traceRay.jl:51): u_i = ((v_i - p).n_i)/(d.n_i) over the edges with |d.n_i| >= 1e-10 and u_i > 0, first index on ties.
-// The argmin runs on cross-multiplied fractions — no division (the faithful form divided once per edge).
-__device__ __forceinline__ int wall_of_poly(const TraceParams& p, int poly, double px, double py, double dx, double dy) {
-  const int nv = p.poly_nv[poly];
+// Generic locator.  One 96-byte record per polygon (rthx_api.cu, face_record), read with 32-byte loads — the generic kernel is
+// bound by the L1 data pipe, which moves one 32-byte sector per lane and load instruction whatever the access width:
+//   rec = { vx[4], vy[4], {vertex count, normal-orientation bits, surface id of walls 0..3, -} }
+// (a triangle repeats its first vertex in slot 3: the zero-length edge never straddles py, so four edges serve both kinds).
+struct __align__(32) Quad64 { double a, b, c, d; };
+__device__ __forceinline__ Quad64 ldg256(const double* __restrict__ ptr) {          // LDG.E.256 (sm_100)
+  Quad64 r;
+  asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.a), "=d"(r.b), "=d"(r.c), "=d"(r.d) : "l"(ptr));
+  return r;
+}
+
+// distToSurface2D on the polygon of a record, index of the nearest edge only (the wall of a fine cell a ray ends on,
+// traceRay.jl:51): u_i = ((v_i - p).n_i)/(d.n_i) over the edges with |d.n_i| >= 1e-10 and u_i > 0, first index on ties.
+// The argmin runs on cross-multiplied fractions — no division — and on the UNNORMALISED outward normals a_i = +-(ey, -ex) of the
+// edges (v_i -> v_i+1), built from the vertices: u_i is a ratio, the factor |e_i| cancels, and the threshold reads
+// (d.a_i)^2 >= 1e-20 |e_i|^2.  No per-polygon normal arrays are read: vertices + tail are three sectors.
+// Returns the wall index; `surf` gets the surface id of that wall (-1: not a solid wall).
+__device__ __forceinline__ int wall_of_rec(const double* __restrict__ rec, double px, double py, double dx, double dy, int& surf) {
+  const Quad64 X = ldg256(rec), Y = ldg256(rec + 4), T = ldg256(rec + 8);
+  const double vx[4] = {X.a, X.b, X.c, X.d}, vy[4] = {Y.a, Y.b, Y.c, Y.d};
+  const int nv = __double2loint(T.a), bits = __double2hiint(T.a);
   double bn = 1.0, bd = 0.0;   // best |num| / |den|; bd == 0: no candidate yet
   int bi = 0;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    if (i < nv) {
-      const double nx = p.poly_nx[poly * 4 + i], ny = p.poly_ny[poly * 4 + i];
-      const double den = dx * nx + dy * ny;
-      const double num = (p.poly_vx[poly * 4 + i] - px) * nx + (p.poly_vy[poly * 4 + i] - py) * ny;
-      const double an = fabs(num), ad = fabs(den);
-      const bool better = (ad >= 1e-10) & (num * den > 0.0) & (an * bd < bn * ad);
-      bn = better ? an : bn; bd = better ? ad : bd; bi = better ? i : bi;
-    }
+    const int j = (i + 1) & 3;                                                       // (slot 3 of a triangle is vertex 0)
+    const double ex = vx[j] - vx[i], ey = vy[j] - vy[i];
+    const bool flip = (bits >> i) & 1;
+    const double ax = flip ? -ey : ey, ay = flip ? ex : -ex;
+    const double den = dx * ax + dy * ay;
+    const double num = (vx[i] - px) * ax + (vy[i] - py) * ay;
+    const double an = fabs(num), ad = fabs(den);
+    const bool better = (i < nv) & (den * den >= 1e-20 * (ex * ex + ey * ey)) & (num * den > 0.0) & (an * bd < bn * ad);
+    bn = better ? an : bn; bd = better ? ad : bd; bi = better ? i : bi;
   }
+  surf = bi == 0 ? __double2loint(T.b) : (bi == 1 ? __double2hiint(T.b) : (bi == 2 ? __double2loint(T.c) : __double2hiint(T.c)));
   return bi;
 }
 
-// pointInPolygonFast2D, findFace2D.jl:77-101 (crossing number) on a packed polygon record
-//   rec = { xmin, xmax, ymin, ymax, vx[4], vy[4] }   (12 doubles; a triangle repeats its first vertex in slot 3: the zero-length edge
-//                                                      never straddles py, so four edges serve both kinds without a count)
-// Two things differ from the reference's arithmetic, both exact except on a null set (a point within rounding of an edge):
-//   * bounding-box prefilter (find_face_generic): the ~8 candidates of a bucket that do not contain the point are rejected by four
-//     compares; a point the crossing test would accept lies inside the box;
-//   * the crossing test "px < xi + (xj-xi)/(yj-yi) (py-yi)" is evaluated without the division:
-//     t = (px-xi)(yj-yi) - (xj-xi)(py-yi) has the sign of (px - ix)(yj-yi), so the edge is crossed iff t (yj-yi) < 0.
-// The CPU oracle keeps the reference's form; the exact-parity tests bound the difference (<= 2e-6 of the rays).
+// pointInPolygonFast2D, findFace2D.jl:77-101 (crossing number) on the vertices of a record.
+// The crossing test "px < xi + (xj-xi)/(yj-yi) (py-yi)" is evaluated without the division:
+//   t = (px-xi)(yj-yi) - (xj-xi)(py-yi) has the sign of (px - ix)(yj-yi), so the edge is crossed iff t (yj-yi) < 0
+// — exact except for a point within rounding of an edge.  The CPU oracle keeps the reference's form; the exact-parity tests bound
+// the difference (<= 2e-6 of the rays).
 __device__ __forceinline__ bool point_in_rec(const double* __restrict__ rec, double px, double py) {
-  const double2 x01 = __ldg(reinterpret_cast<const double2*>(rec) + 2), x23 = __ldg(reinterpret_cast<const double2*>(rec) + 3);
-  const double2 y01 = __ldg(reinterpret_cast<const double2*>(rec) + 4), y23 = __ldg(reinterpret_cast<const double2*>(rec) + 5);
-  const double vx[4] = {x01.x, x01.y, x23.x, x23.y}, vy[4] = {y01.x, y01.y, y23.x, y23.y};
+  const Quad64 X = ldg256(rec), Y = ldg256(rec + 4);
+  const double vx[4] = {X.a, X.b, X.c, X.d}, vy[4] = {Y.a, Y.b, Y.c, Y.d};
   unsigned inside = 0u;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -267,39 +280,36 @@ __device__ __forceinline__ bool point_in_rec(const double* __restrict__ rec, dou
   return inside != 0u;
 }
 
-// findFaceUniformGrid2D, findFace2D.jl:2-27: bucket of the uniform grid, first face passing the PIP test.
-// (The bbox-prefilter fallback of :30-45 can only succeed where the bucket scan succeeds, up to rounding of the
-// bucket index on a set of measure zero; it is restated in the CPU oracle and omitted here.)
-// SIMT shape of the scan: a lane that walked its bucket serially, leaving at the first hit, kept 10 of 32 lanes busy and chained
-// two L2 round trips per candidate (item -> record).  Instead the bounding boxes are stored next to the bucket lists
-// (bucket_bb[k] belongs to bucket_items[k]) and every lane first tests the boxes of ALL its candidates — independent loads, no
-// early exit, the same trip count for every lane of a regular mesh — into a bit mask; the crossing-number test then runs on the
-// set bits in order (one, unless boxes overlap).  Buckets longer than 32 entries are scanned in passes of 32.
+// findFaceUniformGrid2D, findFace2D.jl:2-27: the face of set `set` that contains (px, py) — local face index or -1.
+// The reference scans a bucket of ~9 bounding-box candidates for the first face passing the crossing-number test.  Which face
+// contains a point does not depend on the grid, so the device's grid (rthx_api.cu, build_grid) is ~8x finer per axis, lists only the
+// polygons that really meet the bucket, and marks the buckets that lie wholly inside one face:
+//   trip 1: the set's grid (three uniform 16-byte loads) and the bucket's 16-byte entry {code, a, b, c};
+//           code 0 (77 % of the buckets of a regular mesh): the answer is a — one sector per location, no vertex test;
+//   trip 2: code k >= 1: crossing-number test on candidates a, b, c (k > 3: bucket_cand[a..a+k)) in ascending face order, first hit.
+// (The bbox-prefilter fallback of findFace2D.jl:30-45 can only succeed where the bucket scan succeeds, up to rounding of the bucket
+// index on a set of measure zero; it is restated in the CPU oracle and omitted here.)
+// History: round 1 walked the reference's bucket serially (10 of 32 lanes busy, two L2 trips per candidate, 3.1e9 rays/s on cfg3);
+// round 2 first tested all bounding boxes of a bucket into a bit mask (1.2e10), then put box + vertices of every bucket entry in one
+// 128-byte record (1.37e10: ncu showed the L1 data pipe 98.7 % busy with ~19 sectors per ray, hence this layout).
 __device__ __noinline__ int find_face_generic(const TraceParams& p, int set, double px, double py) {
-  const FaceSetDev* fsp = p.sets + set;
-  const double ox = __ldg(&fsp->ox), oy = __ldg(&fsp->oy), inv_cell = __ldg(&fsp->inv_cell);
-  const int gnx = __ldg(&fsp->nx), gny = __ldg(&fsp->ny), boff = __ldg(&fsp->bucket_off), pbase = __ldg(&fsp->poly_base);
-  const double fi = floor((px - ox) * inv_cell), fj = floor((py - oy) * inv_cell);
-  if (!(fi >= 0.0 && fi < (double)gnx && fj >= 0.0 && fj < (double)gny)) return -1;
-  const int b = boff + (int)fi + (int)fj * gnx;
-  const int k0 = __ldg(p.bucket_start + b), k1 = __ldg(p.bucket_start + b + 1);
-  const double* recs = p.poly_rec + (size_t)pbase * 12;
-  const double2* bb = reinterpret_cast<const double2*>(p.bucket_bb);
-  for (int kb = k0; kb < k1; kb += 32) {
-    const int n = min(32, k1 - kb);
-    unsigned mask = 0u;
-#pragma unroll 4
-    for (int j = 0; j < n; ++j) {
-      const double2 bx = __ldg(bb + 2 * (size_t)(kb + j)), by = __ldg(bb + 2 * (size_t)(kb + j) + 1);
-      const bool in = (px >= bx.x) & (px <= bx.y) & (py >= by.x) & (py <= by.y);
-      mask |= in ? (1u << j) : 0u;
-    }
-    while (mask) {
-      const int j = __ffs((int)mask) - 1;
-      const int f = __ldg(p.bucket_items + kb + j);
-      if (point_in_rec(recs + (size_t)f * 12, px, py)) return f;
-      mask &= mask - 1u;
-    }
+  const double2* fs2 = reinterpret_cast<const double2*>(p.sets + set);
+  const double2 org = __ldg(fs2), inv = __ldg(fs2 + 1);
+  const int4 g = __ldg(reinterpret_cast<const int4*>(fs2 + 2));        // nx, ny, bucket_off, poly_base
+  const double fi = floor((px - org.x) * inv.x), fj = floor((py - org.y) * inv.y);
+  if (!(fi >= 0.0 && fi < (double)g.x && fj >= 0.0 && fj < (double)g.y)) return -1;
+  const int4 e = __ldg(p.bucket_ent + (g.z + (int)fi + (int)fj * g.x));
+  if (e.x == 0) return e.y;
+  const double* recs = p.face_rec + 12 * (size_t)g.w;
+  if (e.x <= 3) {
+    if (e.x >= 1 && point_in_rec(recs + 12 * (size_t)e.y, px, py)) return e.y;
+    if (e.x >= 2 && point_in_rec(recs + 12 * (size_t)e.z, px, py)) return e.z;
+    if (e.x >= 3 && point_in_rec(recs + 12 * (size_t)e.w, px, py)) return e.w;
+    return -1;
+  }
+  for (int k = 0; k < e.x; ++k) {
+    const int f = __ldg(p.bucket_cand + e.y + k);
+    if (point_in_rec(recs + 12 * (size_t)f, px, py)) return f;
   }
   return -1;
 }
@@ -577,8 +587,9 @@ __global__ void __launch_bounds__(256, MINB) trace_exchange_kernel(const __grid_
         if (gas) { absorber = p.n_surfaces + gc; break; }
         int w;
         if (!FAST && kind == KIND_GENERIC) {
-          w = wall_of_poly(p, gc, px, py, dx, dy);              // traceRay.jl:51
+          w = wall_of_rec(p.face_rec + 12 * (size_t)gc, px, py, dx, dy, absorber);   // traceRay.jl:51; absorber -1: fine wall not solid -> lost
           if (MULTI) { hit_nx = p.poly_nx[4 * gc + w]; hit_ny = p.poly_ny[4 * gc + w]; }
+          break;
         } else {
           if (MULTI) { hit_nx = cf.nx[k]; hit_ny = cf.ny[k]; }  // fine walls on a coarse edge share its normal
           if (kind == KIND_AFFINE_QUAD) {
