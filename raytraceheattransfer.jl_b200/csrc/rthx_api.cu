@@ -802,7 +802,7 @@ extern "C" int rthx_get_info(const rthx_handle* h, rthx_info* info) {
 // ---------------------------------------------------------------------------------------------------------------
 namespace {
 
-struct LaunchPlan { int n_owned, n_blocks, block_threads, row_chunks, hist_in_smem, fast, minb, multi, sq, queue_depth; size_t smem_bytes; };
+struct LaunchPlan { int n_owned, n_blocks, block_threads, row_chunks, hist_in_smem, fast, minb, multi, sq, queue_depth, queue_gen; size_t smem_bytes; };
 
 int check_args(rthx_handle* h, const rthx_trace_args* a) {
   if (!a) return fail(h, RTHX_ERR_ARG, "trace: args is NULL");
@@ -821,6 +821,12 @@ int check_args(rthx_handle* h, const rthx_trace_args* a) {
   return RTHX_OK;
 }
 
+// variant bits of the queue kernel (rthx_kernels.cu, kernel_variant): 8 general faces, 16 generic locator (implies 8), 32 its 80-register build
+int queue_variant_bits(const rthx_handle* h, const LaunchPlan& pl) {
+  if (pl.queue_gen) return 8 + 16 + (pl.queue_gen == 3 ? 32 : 0);
+  return h->queue_general ? 8 : 0;
+}
+
 LaunchPlan make_plan(const rthx_handle* h, const rthx_trace_args* a, int rank, int world) {
   LaunchPlan pl{};
   pl.n_owned = (h->N - rank + world - 1) / world;
@@ -830,9 +836,9 @@ LaunchPlan make_plan(const rthx_handle* h, const rthx_trace_args* a, int rank, i
   pl.multi = a->mode != RTHX_FIRST_INTERACTION ? 1 : 0;
   pl.minb = pl.multi ? 2 : 4;
   if (const char* ev = std::getenv("RTHX_MINB")) { const int v = std::atoi(ev); if (v >= 2 && v <= 4) pl.minb = v; }   // tuning knob
-  if (!pl.fast && !pl.multi) {     // generic locator kernel: 3 resident blocks (80 registers) unless RTHX_GENERIC_MINB=4 (64 registers, spills)
-    pl.minb = 3;
-    if (const char* ev = std::getenv("RTHX_GENERIC_MINB")) { if (std::atoi(ev) == 4) pl.minb = 4; }
+  if (!pl.fast && !pl.multi) {     // generic locator kernel: 4 resident blocks (64 registers; +4 % with the sole-bucket locator) unless RTHX_GENERIC_MINB=3 (80 registers)
+    pl.minb = 4;
+    if (const char* ev = std::getenv("RTHX_GENERIC_MINB")) { if (std::atoi(ev) == 3) pl.minb = 3; }
   }
   const size_t coarse_bytes = h->coarse_fits_smem ? sizeof(CoarseDev) * (size_t)h->n_coarse : 0;
   const size_t hist_bytes = sizeof(uint32_t) * (size_t)h->N, em_bytes = sizeof(double) * 16 + 16 * (size_t)LOGTAB_N;   // emitter block + log table
@@ -856,8 +862,15 @@ LaunchPlan make_plan(const rthx_handle* h, const rthx_trace_args* a, int rank, i
   pl.smem_bytes = coarse_bytes + em_bytes + (pl.hist_in_smem ? hist_bytes : 0);
   // Multi-face FAST meshes: the queue kernel (per-warp ray queue in shared memory, 40 bytes per parked ray).  Depth = as many
   // rays per lane as still leave 4 resident blocks per SM, at most 8; RTHX_QUEUE_DEPTH overrides (0 = the lock-step kernel).
-  if (h->queue_ok && a->locator != RTHX_LOCATOR_GENERIC && (!pl.multi || multi_queue) && !pl.sq && pl.hist_in_smem && pl.block_threads == 256 &&
-      (h->n_coarse > 1 || h->queue_general || multi_queue)) {
+  // The same kernel's general variant also takes multi-face meshes through the GENERIC locator (faces without a verified lattice,
+  // RTHX_LOCATOR_GENERIC) as long as the coarse descriptors fit in shared memory: a ray crosses several coarse faces there too, and
+  // the lock-step kernel keeps 13 of 32 lanes busy.  RTHX_NO_QUEUE_GENERIC=1 keeps the lock-step kernel (A/B knob).
+  pl.queue_gen = (!pl.multi && (a->locator == RTHX_LOCATOR_GENERIC || !h->queue_ok) && h->coarse_fits_smem && h->n_coarse > 1 &&
+                  pl.hist_in_smem && pl.block_threads == 256) ? 1 : 0;
+  if (const char* ev = std::getenv("RTHX_NO_QUEUE_GENERIC")) { if (std::atoi(ev)) pl.queue_gen = 0; }
+  if (pl.queue_gen) { if (const char* ev = std::getenv("RTHX_GENERIC_MINB")) { if (std::atoi(ev) == 3) pl.queue_gen = 3; } }   // 3: the 80-register build (A/B knob)
+  if (((h->queue_ok && a->locator != RTHX_LOCATOR_GENERIC && (!pl.multi || multi_queue) && (h->n_coarse > 1 || h->queue_general || multi_queue)) || pl.queue_gen) &&
+      !pl.sq && pl.hist_in_smem && pl.block_threads == 256) {
     const size_t base = (pl.smem_bytes + 15) & ~size_t(15);
     const size_t per_depth = (size_t)pl.block_threads * (multi_queue ? 48 : 40);   // bytes per parked ray: p, d, S (+ ray index and event word for MULTI)
     // aim at 4 resident blocks per SM (3 for the MULTI variant, which is bounded to 85 registers); large descriptor tables /
@@ -870,15 +883,16 @@ LaunchPlan make_plan(const rthx_handle* h, const rthx_trace_args* a, int rank, i
     }
     if (const char* ev = std::getenv("RTHX_QUEUE_DEPTH")) { const int v = std::atoi(ev); if (v >= 0 && v <= (int)max_depth) depth = v; }
     if (depth == 3) depth = 2;                       // compiled depths: 1, 2, 4 rays per lane and batch (MULTI: 1, 2)
-    if (depth >= 1 && base + depth * per_depth <= h->prop.sharedMemPerBlockOptin) {
+    if (depth >= (pl.queue_gen ? 2 : 1) && base + depth * per_depth <= h->prop.sharedMemPerBlockOptin) {   // (the generic variant is compiled for depths 2 and 4)
       pl.fast = 1; pl.minb = 6; pl.queue_depth = depth; pl.smem_bytes = base + depth * per_depth;
     }
   }
+  if (!pl.queue_depth) pl.queue_gen = 0;
   const long long rows = (long long)pl.n_owned * a->n_bins;
   long long chunks = a->row_chunks;
   if (chunks <= 0) {
     // enough blocks for ~32 waves of the resident set, but keep >= 2048 rays (and >= N/2, the flush scan) per block
-    const int per_sm = std::max(1, trace_kernel_max_blocks_per_sm(pl.block_threads, pl.smem_bytes, pl.hist_in_smem != 0, pl.fast != 0, pl.minb, pl.multi != 0, pl.sq != 0, pl.queue_depth + (h->queue_general ? 8 : 0)));
+    const int per_sm = std::max(1, trace_kernel_max_blocks_per_sm(pl.block_threads, pl.smem_bytes, pl.hist_in_smem != 0, pl.fast != 0, pl.minb, pl.multi != 0, pl.sq != 0, pl.queue_depth + queue_variant_bits(h, pl)));
     const long long target = (long long)h->prop.multiProcessorCount * per_sm * 32;
     chunks = rows > 0 ? (target + rows - 1) / rows : 1;
     const long long min_rays = std::max<long long>(2048, h->N / 2);
@@ -906,7 +920,7 @@ void fill_params(const rthx_handle* h, const rthx_trace_args* a, const LaunchPla
   P.compact_rows = compact ? 1 : 0;
   P.row_chunks = pl.row_chunks;
   P.queue_depth = pl.queue_depth;
-  P.queue_bilinear = h->queue_general ? 1 : 0;
+  P.queue_bilinear = queue_variant_bits(h, pl);
   P.queue_refill = 24;
   if (const char* ev = std::getenv("RTHX_QUEUE_REFILL")) { const int v = std::atoi(ev); if (v >= 0 && v <= 32) P.queue_refill = v; }   // tuning knob
   P.coarse_in_smem = h->coarse_fits_smem ? 1 : 0;
@@ -976,7 +990,7 @@ int enqueue_trace(rthx_handle* h, const rthx_trace_args* a, int rank, int world,
                   LaunchPlan* plan_out, int* n_launches, int y0 = 0, int y1 = -1, bool upload_bins = true) {
   LaunchPlan pl = make_plan(h, a, rank, world);
   if (pl.n_blocks < 0) return fail(h, RTHX_ERR_ARG, "trace: rays_per_emitter / row_chunks out of range (a block traces at most 2^31 rays, a launch at most 2^31 blocks)");
-  if (!pl.fast) { const int rcg = ensure_generic(h); if (rcg) return rcg; }     // the generic kernel reads the reference-faithful locator tables
+  if (!pl.fast || pl.queue_gen) { const int rcg = ensure_generic(h); if (rcg) return rcg; }     // the generic kernel reads the reference-faithful locator tables
   if (upload_bins) CU(h, cudaMemcpyAsync(h->bins_dev, a->bins, sizeof(int32_t) * (size_t)a->n_bins, cudaMemcpyHostToDevice, stream));
   // A matrix in peer memory (fused multi-GPU flush) is never the target of reductions: the chunks of a row add up in a local
   // compact staging matrix and the finished row is handed over with plain stores (flush_row_hist) — so the peer rows need no
@@ -1072,7 +1086,7 @@ int pipeline_launch(rthx_handle* h, const rthx_trace_args* a, int rank, int worl
   // batches: >= ~2 waves of resident blocks each, at most 16 (consecutive batches alternate between two streams, so a batch's
   // draining tail overlaps the next one's head; cfg3 at 1e10 rays: 16 batches, the copy behind the last kernel is 17 MB and the
   // call ends 0.5 ms after the kernel — with 5 even batches it was 180 MB and 3.6 ms)
-  const int per_sm = std::max(1, trace_kernel_max_blocks_per_sm(pl.block_threads, pl.smem_bytes, pl.hist_in_smem != 0, pl.fast != 0, pl.minb, pl.multi != 0, pl.sq != 0, pl.queue_depth + (h->queue_general ? 8 : 0)));
+  const int per_sm = std::max(1, trace_kernel_max_blocks_per_sm(pl.block_threads, pl.smem_bytes, pl.hist_in_smem != 0, pl.fast != 0, pl.minb, pl.multi != 0, pl.sq != 0, pl.queue_depth + queue_variant_bits(h, pl)));
   const long long resident = (long long)h->prop.multiProcessorCount * per_sm;
   int n_batches = (int)std::min<long long>(16, std::max<long long>(1, pl.n_blocks / (2 * resident)));
   n_batches = std::max(1, std::min(n_batches, n_owned));

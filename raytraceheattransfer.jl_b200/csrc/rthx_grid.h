@@ -41,21 +41,23 @@ inline void poly_finish(Poly& p) {
 // buckets of 2 sqrt(mean area), ~9 bounding-box candidates each): the generic kernel is bound by the L1 data pipe — one 32-byte
 // sector per lane and load instruction, ~19 per ray with round 2's first tables (ncu: l1tex__data_pipe_lsu_wavefronts 98.7 %) — so
 // the tables are shaped to answer most locations from ONE sector:
-//   * buckets of 1/RTHX_GRID_FINE (default 1/8) of the mean bounding-box extent per axis (anisotropic: a 1000:1 slab keeps its
-//     candidate count), at most 80 n + 256 of them;
+//   * buckets of 1/RTHX_GRID_FINE (default 1/12) of the mean bounding-box extent per axis (anisotropic: a 1000:1 slab keeps its
+//     candidate count), at most RTHX_GRID_PER_FACE n + 256 of them (default 200: 3.2 KB of entries per face).  Measured on cfg3 /
+//     cfg5 (tools/gpu_generic_sweep.sh): 1/4 2.49e10 / 4.1e9, 1/8 2.87e10 / 4.7e9, 1/12 3.00e10 / 5.8e9, 1/16 3.08e10 / 5.7e9 rays/s;
 //   * candidates by the separating-axis test polygon <-> bucket rectangle (not bounding-box overlap: triangles and skewed cells
 //     stop leaking into their neighbours' buckets);
 //   * a bucket that lies wholly inside its only candidate is marked SOLE: the locator returns the face without any vertex test
-//     ((1 - 1/8)^2 = 77 % of the buckets of a regular mesh);
+//     ((1 - 1/12)^2 = 84 % of the buckets of a regular mesh);
 //   * one 16-byte entry per bucket {code, a, b, c}: code -1 empty, 0 sole (a = face), k = 1..3 candidates a, b, c (crossing-number
 //     test in ascending face order: "first PIP hit" as in the reference), k > 3 candidates cand[a .. a + k).
 // Non-convex polygons (the reference never builds one) fall back to bounding-box candidates and are never sole.
 // Margins: a polygon is dropped from a bucket only if an edge separates them by more than 1e-9 of the bucket size, the bucket is
 // sole only if it is inside by twice that; the rectangle itself is widened by 1e-9 buckets (rounding of the device's bucket index).
-struct GridCfg { int fine = 8; };
-inline GridCfg grid_cfg() {
+struct GridCfg { int fine = 12; int per_face = 200; };
+inline GridCfg grid_cfg() {       // A/B knobs (tools/gpu_generic_sweep.sh); the defaults are the measured optimum on cfg3 / cfg5
   GridCfg g;
   if (const char* ev = std::getenv("RTHX_GRID_FINE")) g.fine = std::min(32, std::max(1, std::atoi(ev)));
+  if (const char* ev = std::getenv("RTHX_GRID_PER_FACE")) g.per_face = std::min(1024, std::max(1, std::atoi(ev)));
   return g;
 }
 
@@ -73,7 +75,7 @@ inline void build_grid(const Poly* faces, int n, int poly_base, FaceSetDev& fs, 
   double sx = n ? ex / n / fine : 1.0, sy = n ? ey / n / fine : 1.0;
   if (!(sx > 0) || !std::isfinite(sx)) sx = iso > 0 ? iso : 1.0;
   if (!(sy > 0) || !std::isfinite(sy)) sy = iso > 0 ? iso : 1.0;
-  const double max_buckets = 80.0 * n + 256.0;
+  const double max_buckets = (double)grid_cfg().per_face * n + 256.0;
   int nx = 1, ny = 1;
   double ox = 0, oy = 0;
   for (int attempt = 0;; ++attempt) {

@@ -96,7 +96,7 @@ struct TraceParams {
   int32_t rec_bin;
   int32_t queue_refill;        // queue kernel: with the queue dry, emit the next batch once <= this many lanes still hold a ray
   int32_t queue_depth;         // queue kernel: rays parked per lane and batch (queue slots per warp = 32 * queue_depth)
-  int32_t queue_bilinear;      // queue kernel: the mesh has bilinear-lattice faces (selects the variant that knows them)
+  int32_t queue_bilinear;      // queue kernel variant bits: 8 general faces (bilinear lattices, T-junctions), 16 generic locator, 32 its 80-register build
   int32_t queue_sq;            // MULTI queue kernel: the domain is one parallelogram (1 axis-aligned, 2 general): SQ form of the step
   int64_t rays_per_emitter;
   int64_t ray_id_offset;

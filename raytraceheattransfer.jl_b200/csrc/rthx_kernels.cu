@@ -282,10 +282,10 @@ __device__ __forceinline__ bool point_in_rec(const double* __restrict__ rec, dou
 
 // findFaceUniformGrid2D, findFace2D.jl:2-27: the face of set `set` that contains (px, py) — local face index or -1.
 // The reference scans a bucket of ~9 bounding-box candidates for the first face passing the crossing-number test.  Which face
-// contains a point does not depend on the grid, so the device's grid (rthx_api.cu, build_grid) is ~8x finer per axis, lists only the
+// contains a point does not depend on the grid, so the device's grid (rthx_grid.h, build_grid) is ~12x finer per axis, lists only the
 // polygons that really meet the bucket, and marks the buckets that lie wholly inside one face:
 //   trip 1: the set's grid (three uniform 16-byte loads) and the bucket's 16-byte entry {code, a, b, c};
-//           code 0 (77 % of the buckets of a regular mesh): the answer is a — one sector per location, no vertex test;
+//           code 0 (84 % of the buckets of a regular mesh): the answer is a — one sector per location, no vertex test;
 //   trip 2: code k >= 1: crossing-number test on candidates a, b, c (k > 3: bucket_cand[a..a+k)) in ascending face order, first hit.
 // (The bbox-prefilter fallback of findFace2D.jl:30-45 can only succeed where the bucket scan succeeds, up to rounding of the bucket
 // index on a set of measure zero; it is restated in the CPU oracle and omitted here.)
@@ -1226,7 +1226,7 @@ __device__ __forceinline__ int lattice_cell(const CoarseDev& cf, double px, doub
   return (((unsigned)n < (unsigned)cf.Nx) & ((unsigned)m < (unsigned)cf.Ny)) ? n + m * cf.Nx : -1;
 }
 
-template <bool SURF, bool UNIFORM, bool REC, int DEPTH, bool BILIN>
+template <bool SURF, bool UNIFORM, bool REC, int DEPTH, bool BILIN, bool GEN>
 __device__ __forceinline__ unsigned int queue_ray_loop(const TraceParams& p, const QueueBlock& b) {
   constexpr int WQ = 32 * DEPTH;                       // queue slots per warp
   const int lane = b.lane;
@@ -1283,6 +1283,9 @@ __device__ __forceinline__ unsigned int queue_ray_loop(const TraceParams& p, con
       // wall, crossing: only the advance length differs); the only divergent region is "this ray ended"
       if (active) {
         const CoarseDev& cf = b.coarse[c];
+        // GEN (a general variant of its own, so that meshes of analytic faces keep their registers): faces without an analytic
+        // locator, and every face under RTHX_LOCATOR_GENERIC, are located by bucket grid + crossing number
+        const bool gen = GEN && (p.force_generic != 0 || cf.kind == KIND_GENERIC);
         int k;
         double u;
         const bool edge = dist_face<BILIN>(cf, px, py, dx, dy, p.k_eps, u, k);  // an edge lies ahead
@@ -1292,8 +1295,13 @@ __device__ __forceinline__ unsigned int queue_ray_loop(const TraceParams& p, con
           gas = S < u;
           Sg = S;
         } else {
-          const int l0 = lattice_cell<BILIN>(cf, px, py);                      // traceRay.jl:87-100
-          const int f0 = l0 < 0 ? -1 : (cf.kind == KIND_AFFINE_TRI ? __ldg(p.lattice + cf.lat_off + l0) : l0);
+          int f0;                                                              // traceRay.jl:87-100
+          if (GEN && gen) {
+            f0 = find_face_generic(p, 1 + c, px, py);
+          } else {
+            const int l0 = lattice_cell<BILIN>(cf, px, py);
+            f0 = l0 < 0 ? -1 : (cf.kind == KIND_AFFINE_TRI ? __ldg(p.lattice + cf.lat_off + l0) : l0);
+          }
           ok = f0 >= 0;
           const double local_beta = ok ? b.beta_band[cf.fine_off + f0] : 0.0;
           tau_b = local_beta * u;
@@ -1319,8 +1327,16 @@ __device__ __forceinline__ unsigned int queue_ray_loop(const TraceParams& p, con
     active = false;                                                                                                 \
     int absorber = -1;                                                                                              \
     if (tallied) {                                                                                                  \
-      const int l = lattice_cell<BILIN>(cf, px, py);                                                                \
-      if (l >= 0) absorber = __ldg(p.abs_tab + (size_t)(cf.abs_off + l) * 5 + (gas ? 0 : 1 + k));                   \
+      if (GEN && gen) {                                                                                             \
+        const int f = find_face_generic(p, 1 + c, px, py);                                                          \
+        if (f >= 0) {                                                                                               \
+          if (gas) absorber = p.n_surfaces + cf.fine_off + f;                                                       \
+          else wall_of_rec(p.face_rec + 12 * (size_t)(cf.fine_off + f), px, py, dx, dy, absorber); /* traceRay.jl:51 */ \
+        }                                                                                                           \
+      } else {                                                                                                      \
+        const int l = lattice_cell<BILIN>(cf, px, py);                                                              \
+        if (l >= 0) absorber = __ldg(p.abs_tab + (size_t)(cf.abs_off + l) * 5 + (gas ? 0 : 1 + k));                 \
+      }                                                                                                             \
     }                                                                                                               \
     if (absorber >= 0) {                                                                                            \
       atomicAdd(&b.hist[absorber], 1u);                                                                             \
@@ -1346,7 +1362,7 @@ __device__ __forceinline__ unsigned int queue_ray_loop(const TraceParams& p, con
           bool ended = !cross;
           if (cross) {
             if (UNIFORM) S -= u; else acc += tau_b;
-            int nn = nc;
+            int nn = (GEN && p.force_generic) ? -1 : nc;                 // RTHX_LOCATOR_GENERIC: the reference's search after every crossing
             if (nn < 0) nn = find_face_generic(p, 0, px, py);
             if (nn >= 0) { c = nn; ++it; }
             else ended = true;                                           // left the domain: lost, like the reference's `nothing`
@@ -1363,10 +1379,10 @@ __device__ __forceinline__ unsigned int queue_ray_loop(const TraceParams& p, con
   return n_lost;
 }
 
-template <bool SURF, int DEPTH, bool BILIN>
+template <bool SURF, int DEPTH, bool BILIN, bool GEN>
 __device__ __forceinline__ unsigned int queue_dispatch(const TraceParams& p, const QueueBlock& b, bool uniform, bool rec) {
-  if (uniform) return rec ? queue_ray_loop<SURF, true, true, DEPTH, BILIN>(p, b) : queue_ray_loop<SURF, true, false, DEPTH, BILIN>(p, b);
-  return rec ? queue_ray_loop<SURF, false, true, DEPTH, BILIN>(p, b) : queue_ray_loop<SURF, false, false, DEPTH, BILIN>(p, b);
+  if (uniform) return rec ? queue_ray_loop<SURF, true, true, DEPTH, BILIN, GEN>(p, b) : queue_ray_loop<SURF, true, false, DEPTH, BILIN, GEN>(p, b);
+  return rec ? queue_ray_loop<SURF, false, true, DEPTH, BILIN, GEN>(p, b) : queue_ray_loop<SURF, false, false, DEPTH, BILIN, GEN>(p, b);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -1668,7 +1684,7 @@ __device__ __forceinline__ unsigned int queue_multi_dispatch(const TraceParams& 
 
 // BILIN: the mesh has general convex quadrilateral faces (bilinear lattices); compiled separately so that meshes of parallelograms
 // and triangles keep the shorter traversal loop
-template <int MINB, int DEPTH, bool BILIN, bool MULTI>
+template <int MINB, int DEPTH, bool BILIN, bool MULTI, bool GEN = false>
 __global__ void __launch_bounds__(256, MINB) trace_exchange_queue_kernel(const __grid_constant__ TraceParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const size_t coarse_bytes = sizeof(CoarseDev) * (size_t)p.n_coarse;
@@ -1736,7 +1752,7 @@ __global__ void __launch_bounds__(256, MINB) trace_exchange_queue_kernel(const _
     else if (!BILIN && p.queue_sq == 2) n_lost0 = is_surface ? queue_multi_dispatch<true, DEPTH, false, 2>(p, b, uniform, rec_slot >= 0) : queue_multi_dispatch<false, DEPTH, false, 2>(p, b, uniform, rec_slot >= 0);
     else n_lost0 = is_surface ? queue_multi_dispatch<true, DEPTH, BILIN, 0>(p, b, uniform, rec_slot >= 0) : queue_multi_dispatch<false, DEPTH, BILIN, 0>(p, b, uniform, rec_slot >= 0);
   }
-  else n_lost0 = is_surface ? queue_dispatch<true, DEPTH, BILIN>(p, b, uniform, rec_slot >= 0) : queue_dispatch<false, DEPTH, BILIN>(p, b, uniform, rec_slot >= 0);
+  else n_lost0 = is_surface ? queue_dispatch<true, DEPTH, BILIN, GEN>(p, b, uniform, rec_slot >= 0) : queue_dispatch<false, DEPTH, BILIN, GEN>(p, b, uniform, rec_slot >= 0);
   unsigned int n_lost = n_lost0;
 
   // ---- flush --------------------------------------------------------------------------------------------------
@@ -1765,8 +1781,12 @@ static TraceKernel kernel_variant(bool hist, bool fast, int minb, bool multi, bo
     return (TraceKernel)trace_exchange_sq_kernel<4, false>;
   }
   if (minb == 6 && hist && fast && !sq) {                                                               // per-warp ray queue (multi-face meshes; MULTI_BOUNCE on any analytic mesh)
-    const bool bilin = queue_depth >= 8;                                                                // depth + 8: bilinear faces present
+    const bool bilin = (queue_depth & 8) != 0;                                                          // depth + 8: bilinear faces present
     const int d = queue_depth & 7;
+    if (queue_depth & 16) {                                                                             // depth + 16: faces on the generic locator (FIRST_INTERACTION; compiled depths 2, 4)
+      if (queue_depth & 32) return d >= 4 ? (TraceKernel)trace_exchange_queue_kernel<3, 4, true, false, true> : (TraceKernel)trace_exchange_queue_kernel<3, 2, true, false, true>;   // RTHX_GENERIC_MINB=3
+      return d >= 4 ? (TraceKernel)trace_exchange_queue_kernel<4, 4, true, false, true> : (TraceKernel)trace_exchange_queue_kernel<4, 2, true, false, true>;
+    }
     if (multi) {                                                                                        // compiled depths: 1, 2
       if (d >= 2) return bilin ? (TraceKernel)trace_exchange_queue_kernel<3, 2, true, true> : (TraceKernel)trace_exchange_queue_kernel<3, 2, false, true>;
       return bilin ? (TraceKernel)trace_exchange_queue_kernel<3, 1, true, true> : (TraceKernel)trace_exchange_queue_kernel<3, 1, false, true>;
@@ -1780,7 +1800,7 @@ static TraceKernel kernel_variant(bool hist, bool fast, int minb, bool multi, bo
     return fast ? (TraceKernel)trace_exchange_kernel<false, true, 2, true, false> : (TraceKernel)trace_exchange_kernel<false, false, 2, true, false>;
   }
   if (!hist) return fast ? (TraceKernel)trace_exchange_kernel<false, true, 2, false, false> : (TraceKernel)trace_exchange_kernel<false, false, 2, false, false>;
-  if (!fast) return minb == 4 ? (TraceKernel)trace_exchange_kernel<true, false, 4, false, false>     // generic locator: 64 registers (spills 132 B), 4 blocks per SM
+  if (!fast) return minb == 4 ? (TraceKernel)trace_exchange_kernel<true, false, 4, false, false>     // generic locator: 64 registers, 4 blocks per SM (default)
                               : (TraceKernel)trace_exchange_kernel<true, false, 3, false, false>;    // 80 registers, 3 blocks per SM
   switch (minb) {
     case 3: return (TraceKernel)trace_exchange_kernel<true, true, 3, false, false>;
@@ -1795,7 +1815,7 @@ cudaError_t configure_trace_kernel(size_t smem_bytes) {
       for (int hist = 0; hist < 2; ++hist)
         for (int fast = 0; fast < 2; ++fast)
           for (int minb = 2; minb <= 6; ++minb)
-            for (int depth : {1, 2, 4, 9, 10, 12}) {
+            for (int depth : {1, 2, 4, 9, 10, 12, 18, 20, 50, 52}) {
               cudaError_t e = cudaFuncSetAttribute((const void*)kernel_variant(hist, fast, minb, multi, sq, depth), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
               if (e != cudaSuccess) return e;
             }
@@ -1811,7 +1831,7 @@ int trace_kernel_max_blocks_per_sm(int block_threads, size_t smem_bytes, bool hi
 cudaError_t launch_trace_exchange(const TraceParams& p, int n_blocks, int block_threads, size_t smem_bytes, bool fast, int minb, bool sq,
                                   cudaStream_t stream) {
   if (n_blocks <= 0) return cudaSuccess;
-  TraceKernel k = kernel_variant(p.hist_in_smem != 0, fast, minb, p.multi_bounce != 0, sq, p.queue_depth + (p.queue_bilinear ? 8 : 0));
+  TraceKernel k = kernel_variant(p.hist_in_smem != 0, fast, minb, p.multi_bounce != 0, sq, p.queue_depth + p.queue_bilinear);   // queue_bilinear: variant bits 8 | 16 | 32
   void* args[] = {(void*)&p};
   return cudaLaunchKernel((const void*)k, dim3(n_blocks), dim3(block_threads), args, smem_bytes, stream);
 }

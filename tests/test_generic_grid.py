@@ -47,7 +47,7 @@ def test_grid_locator_equals_full_scan(checker, name, pts):
     # the point of the layout: most located points need no vertex test at all on quadrilateral meshes
     if name != "cfg5":
         assert st["sole"] / st["found"] > 0.6, st
-    assert st["buckets"] <= 80 * (flat.n_cells + flat.c.n_coarse) + 256 * (1 + flat.c.n_coarse), st
+    assert st["buckets"] <= 200 * (flat.n_cells + flat.c.n_coarse) + 256 * (1 + flat.c.n_coarse), st
 
 
 def test_grid_locator_on_triangles_and_flat_cells(checker):
@@ -65,7 +65,7 @@ def test_grid_fine_knob(checker, monkeypatch):
     flat = rthx.flatten_domain(rthx.meshes.cfg1())
     monkeypatch.setenv("RTHX_GRID_FINE", "2")
     st2 = checker(flat, 20000)
-    monkeypatch.setenv("RTHX_GRID_FINE", "8")
-    st8 = checker(flat, 20000)
-    assert st2["mismatches"] == 0 and st8["mismatches"] == 0
-    assert st8["sole"] > st2["sole"] and st8["buckets"] > st2["buckets"]
+    monkeypatch.setenv("RTHX_GRID_FINE", "12")
+    st12 = checker(flat, 20000)
+    assert st2["mismatches"] == 0 and st12["mismatches"] == 0
+    assert st12["sole"] > st2["sole"] and st12["buckets"] > st2["buckets"]
