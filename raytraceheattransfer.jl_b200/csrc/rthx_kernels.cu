@@ -1320,6 +1320,13 @@ __device__ __forceinline__ unsigned int queue_ray_loop(const TraceParams& p, con
           px = fma(adv, dx, px);
           py = fma(adv, dy, py);
         }
+        // GEN: ONE call of the generic locator per iteration serves both kinds of lane — the coarse face behind a crossing (set 0)
+        // and the fine cell a ray ends in (set 1 + c).  With a call in each branch the warp ran the locator twice per iteration at
+        // ~12 of 32 lanes (ncu: 2810 warp instructions per 32 rays on cfg5).
+        const bool loc_cross = GEN && cross && (p.force_generic != 0 || nc < 0);   // RTHX_LOCATOR_GENERIC: the reference's search after every crossing
+        const bool loc_end = GEN && gen && !cross && tallied;
+        int loc = -1;
+        if (GEN && (loc_cross | loc_end)) loc = find_face_generic(p, loc_cross ? 0 : 1 + c, px, py);
         // a ray that ends: absorber index of (lattice cell, gas | wall on coarse edge k) in ONE table load shared by both endings
         // (rthx_api.cu builds the table from the lattice -> fine map, the fine cells' vertex counts and cell_surf_id)
 #define RTHX_QUEUE_FINISH()                                                                                         \
@@ -1328,7 +1335,7 @@ __device__ __forceinline__ unsigned int queue_ray_loop(const TraceParams& p, con
     int absorber = -1;                                                                                              \
     if (tallied) {                                                                                                  \
       if (GEN && gen) {                                                                                             \
-        const int f = find_face_generic(p, 1 + c, px, py);                                                          \
+        const int f = loc;                                                                                          \
         if (f >= 0) {                                                                                               \
           if (gas) absorber = p.n_surfaces + cf.fine_off + f;                                                       \
           else wall_of_rec(p.face_rec + 12 * (size_t)(cf.fine_off + f), px, py, dx, dy, absorber); /* traceRay.jl:51 */ \
@@ -1362,8 +1369,13 @@ __device__ __forceinline__ unsigned int queue_ray_loop(const TraceParams& p, con
           bool ended = !cross;
           if (cross) {
             if (UNIFORM) S -= u; else acc += tau_b;
-            int nn = (GEN && p.force_generic) ? -1 : nc;                 // RTHX_LOCATOR_GENERIC: the reference's search after every crossing
-            if (nn < 0) nn = find_face_generic(p, 0, px, py);
+            int nn;
+            if (GEN) {
+              nn = loc_cross ? loc : nc;
+            } else {
+              nn = nc;
+              if (nn < 0) nn = find_face_generic(p, 0, px, py);
+            }
             if (nn >= 0) { c = nn; ++it; }
             else ended = true;                                           // left the domain: lost, like the reference's `nothing`
           }
