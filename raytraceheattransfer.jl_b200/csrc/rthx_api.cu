@@ -89,6 +89,7 @@ struct rthx_handle : DevRes {
 
 static thread_local std::string g_create_err;
 static int ensure_generic(rthx_handle* h);
+static void release_generic_cache();
 
 namespace {
 std::mutex g_pool_mu;
@@ -577,6 +578,7 @@ extern "C" int rthx_release_cached(void) {
     for (auto& pb : g_pin_pool) cudaFreeHost(pb.first);
     g_pin_pool.clear();
   }
+  release_generic_cache();
   return RTHX_OK;
 }
 
@@ -678,10 +680,60 @@ int check_mesh_args(const rthx_mesh* m) {
 // Tables of the reference-faithful locator (uniform grids per fine-cell set, per-polygon normals): derived from the image on
 // first use — at rthx_create for meshes with unverifiable lattices or more than 384 coarse faces, else by the first trace that
 // asks for RTHX_LOCATOR_GENERIC or needs the generic kernel.  cfg3: 1.1 ms of host work that the analytic paths never pay.
-static int ensure_generic(rthx_handle* h) {
-  if (h->generic_ready) return RTHX_OK;
-  const HostImage& im = *h->image;
+// Host image of the generic tables, kept in a small most-recently-used cache keyed by a 128-bit hash of the geometry they are derived
+// from (and of the grid knobs): callers re-create handles for every trace and rthx_create_multi makes one per device, but the tables
+// of a mesh are built once per process (cfg3: ~25 ms of host work, 10 MB).
+namespace {
+struct GenericTables {
+  std::vector<unsigned char> host;
+  size_t o_sets = 0, o_bent = 0, o_bcand = 0, o_pnx = 0, o_pny = 0, o_frec = 0;
+  uint64_t key[2] = {0, 0};
+  int ncell = 0, nc = 0;
+};
+std::mutex g_gen_mu;
+std::vector<std::shared_ptr<const GenericTables>> g_gen_cache;   // most recent first, at most 3 entries
+
+void hash_bytes(uint64_t h[2], const void* data, size_t n) {    // two independent multiply-xorshift streams over 8-byte words
+  const unsigned char* p = static_cast<const unsigned char*>(data);
+  uint64_t a = h[0] ^ (n * 0x9E3779B97F4A7C15ull), b = h[1] + n;
+  size_t i = 0;
+  for (; i + 8 <= n; i += 8) {
+    uint64_t w;
+    std::memcpy(&w, p + i, 8);
+    a = (a ^ w) * 0xFF51AFD7ED558CCDull; a ^= a >> 32;
+    b = (b + w) * 0xC4CEB9FE1A85EC53ull; b ^= b >> 29;
+  }
+  uint64_t w = 0;
+  if (i < n) std::memcpy(&w, p + i, n - i);
+  a = (a ^ w) * 0xFF51AFD7ED558CCDull; a ^= a >> 33;
+  b = (b + w) * 0xC4CEB9FE1A85EC53ull; b ^= b >> 31;
+  h[0] = a; h[1] = b;
+}
+
+std::shared_ptr<const GenericTables> generic_tables(const HostImage& im) {
   const int nc = im.nc, ncell = im.ncell;
+  uint64_t key[2] = {0x243F6A8885A308D3ull, 0x13198A2E03707344ull};
+  hash_bytes(key, im.at<int32_t>(im.o_nv), 4 * (size_t)ncell);
+  hash_bytes(key, im.at<double>(im.o_pvx), 32 * (size_t)ncell);
+  hash_bytes(key, im.at<double>(im.o_pvy), 32 * (size_t)ncell);
+  hash_bytes(key, im.at<double>(im.o_mid), 16 * (size_t)ncell);
+  hash_bytes(key, im.at<double>(im.o_vol), 8 * (size_t)ncell);
+  hash_bytes(key, im.at<int32_t>(im.o_surf), 16 * (size_t)ncell);
+  hash_bytes(key, im.fine_off.data(), 4 * im.fine_off.size());
+  for (const Poly& cp : im.coarse_polys) { const int32_t n = cp.n; hash_bytes(key, &n, 4); hash_bytes(key, cp.vx, 32); hash_bytes(key, cp.vy, 32); }   // (field by field: no padding bytes)
+  for (const char* knob : {"RTHX_GRID_FINE", "RTHX_GRID_PER_FACE"}) { const char* ev = std::getenv(knob); hash_bytes(key, ev ? ev : "", ev ? std::strlen(ev) : 0); }
+  {
+    std::lock_guard<std::mutex> lk(g_gen_mu);
+    for (size_t i = 0; i < g_gen_cache.size(); ++i) {
+      const auto& t = g_gen_cache[i];
+      if (t->key[0] == key[0] && t->key[1] == key[1] && t->ncell == ncell && t->nc == nc) {
+        auto hit = t;
+        g_gen_cache.erase(g_gen_cache.begin() + (long)i);
+        g_gen_cache.insert(g_gen_cache.begin(), hit);
+        return hit;
+      }
+    }
+  }
   std::vector<Poly> polys((size_t)ncell + nc);
   const int32_t* nv = im.at<int32_t>(im.o_nv);
   const double* pvx = im.at<double>(im.o_pvx);
@@ -708,7 +760,28 @@ static int ensure_generic(rthx_handle* h) {
     face_record(polys[i], i < (size_t)ncell ? surf + 4 * i : nullptr, &frec[FREC * i]);
   }
   Arena A;
-  const size_t o_sets = A.add(sets), o_bent = A.add(bent), o_bcand = A.add(bcand), o_pnx = A.add(pnx), o_pny = A.add(pny), o_frec = A.add(frec);
+  auto t = std::make_shared<GenericTables>();
+  t->o_sets = A.add(sets); t->o_bent = A.add(bent); t->o_bcand = A.add(bcand); t->o_pnx = A.add(pnx); t->o_pny = A.add(pny); t->o_frec = A.add(frec);
+  t->host = std::move(A.host);
+  t->key[0] = key[0]; t->key[1] = key[1]; t->ncell = ncell; t->nc = nc;
+  std::lock_guard<std::mutex> lk(g_gen_mu);
+  g_gen_cache.insert(g_gen_cache.begin(), t);
+  if (g_gen_cache.size() > 3) g_gen_cache.pop_back();
+  return t;
+}
+}  // namespace
+
+static void release_generic_cache() {
+  std::lock_guard<std::mutex> lk(g_gen_mu);
+  g_gen_cache.clear();
+}
+
+static int ensure_generic(rthx_handle* h) {
+  if (h->generic_ready) return RTHX_OK;
+  const HostImage& im = *h->image;
+  const std::shared_ptr<const GenericTables> gt = generic_tables(im);
+  struct { const std::vector<unsigned char>& host; size_t total; } A{gt->host, gt->host.size()};
+  const size_t o_sets = gt->o_sets, o_bent = gt->o_bent, o_bcand = gt->o_bcand, o_pnx = gt->o_pnx, o_pny = gt->o_pny, o_frec = gt->o_frec;
   CU(h, cudaSetDevice(h->device));
   if (h->generic_cap < A.total) {
     cudaFree(h->generic_arena);
