@@ -564,12 +564,17 @@ def main():
     if world == 1 and not args.no_extras and args.workload == "cfg3" and args.mode == "first_interaction":
       try:
         other_configs = {}
-        for name in ("cfg1", "cfg2", "cfg4", "cfg5"):
+        # ... and the two slower paths of the same kernel family on cfg3 / cfg5: the generic locator (what a mesh without a
+        # verifiable lattice takes) and the total-exchange mode (every ray followed to absorption)
+        variants = [(n, n, {}) for n in ("cfg1", "cfg2", "cfg4", "cfg5")] + \
+                   [("cfg3_generic_locator", "cfg3", {"locator": 1}), ("cfg5_generic_locator", "cfg5", {"locator": 1}),
+                    ("cfg3_multi_bounce", "cfg3", {"mode": 1})]
+        for key, name, extra in variants:
             _, f2, b2 = build_workload(name)
             n2 = f2.n_elements
-            rpe2 = int(DEFAULT_RAYS[name]) // n2
+            rpe2 = int(min(DEFAULT_RAYS[name], 1e9)) // n2
             s2 = ShardedTracer(f2, device=local_rank, rank=0, world=1, n_bins=len(b2), mode="local")
-            kw2 = dict(kw, bins=b2)
+            kw2 = dict(kw, bins=b2, **extra)
             for w in range(3):
                 s2.enqueue(rpe2, seed=10 + w, **kw2)
             torch.cuda.synchronize(dev)
@@ -581,7 +586,7 @@ def main():
             torch.cuda.synchronize(dev)
             ms = a.elapsed_time(b) / 5
             traced = rpe2 * n2 * len(b2)
-            other_configs[name] = {"workload": workload_desc(name), "elements": n2, "bands": len(b2), "rays_per_step": traced,
+            other_configs[key] = {"workload": workload_desc(name), "elements": n2, "bands": len(b2), "rays_per_step": traced,
                                    "ms_per_step": ms, "value": traced / (ms * 1e-3), "steps": 5, "warmup": 3,
                                    "tallied_plus_lost_ok": bool(int(s2.counts.sum().item()) + int(s2.lost.sum().item()) == traced)}
             s2.close()
