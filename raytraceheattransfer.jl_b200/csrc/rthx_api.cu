@@ -712,6 +712,14 @@ void hash_bytes(uint64_t h[2], const void* data, size_t n) {    // two independe
 
 std::shared_ptr<const GenericTables> generic_tables(const HostImage& im) {
   const int nc = im.nc, ncell = im.ncell;
+  const bool timing = std::getenv("RTHX_CREATE_TIMING") != nullptr;
+  auto t_prev = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!timing) return;
+    const auto t = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "generic tables: %-24s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t - t_prev).count());
+    t_prev = t;
+  };
   uint64_t key[2] = {0x243F6A8885A308D3ull, 0x13198A2E03707344ull};
   hash_bytes(key, im.at<int32_t>(im.o_nv), 4 * (size_t)ncell);
   hash_bytes(key, im.at<double>(im.o_pvx), 32 * (size_t)ncell);
@@ -734,6 +742,7 @@ std::shared_ptr<const GenericTables> generic_tables(const HostImage& im) {
       }
     }
   }
+  lap("hash + cache lookup");
   std::vector<Poly> polys((size_t)ncell + nc);
   const int32_t* nv = im.at<int32_t>(im.o_nv);
   const double* pvx = im.at<double>(im.o_pvx);
@@ -748,10 +757,12 @@ std::shared_ptr<const GenericTables> generic_tables(const HostImage& im) {
     poly_finish(p);
   }
   for (int c = 0; c < nc; ++c) polys[(size_t)ncell + c] = im.coarse_polys[c];
+  lap("polygons + normals");
   std::vector<FaceSetDev> sets(1 + (size_t)nc);
   std::vector<int32_t> bent, bcand;
   build_grid(&polys[ncell], nc, ncell, sets[0], bent, bcand);
   for (int c = 0; c < nc; ++c) build_grid(&polys[im.fine_off[c]], im.fine_off[c + 1] - im.fine_off[c], im.fine_off[c], sets[1 + c], bent, bcand);
+  lap("bucket grids");
   std::vector<double> pnx((size_t)ncell * 4), pny((size_t)ncell * 4), frec(polys.size() * FREC);
   const int32_t* surf = im.at<int32_t>(im.o_surf);
   for (size_t i = 0; i < polys.size(); ++i) {
@@ -759,11 +770,14 @@ std::shared_ptr<const GenericTables> generic_tables(const HostImage& im) {
       for (int k = 0; k < 4; ++k) { pnx[4 * i + k] = polys[i].nx[k]; pny[4 * i + k] = polys[i].ny[k]; }
     face_record(polys[i], i < (size_t)ncell ? surf + 4 * i : nullptr, &frec[FREC * i]);
   }
+  lap("polygon records");
   Arena A;
+  A.host.reserve(sizeof(FaceSetDev) * sets.size() + 4 * (bent.size() + bcand.size()) + 8 * (pnx.size() + pny.size() + frec.size()) + 8 * 256);   // one allocation
   auto t = std::make_shared<GenericTables>();
   t->o_sets = A.add(sets); t->o_bent = A.add(bent); t->o_bcand = A.add(bcand); t->o_pnx = A.add(pnx); t->o_pny = A.add(pny); t->o_frec = A.add(frec);
   t->host = std::move(A.host);
   t->key[0] = key[0]; t->key[1] = key[1]; t->ncell = ncell; t->nc = nc;
+  lap("table image");
   std::lock_guard<std::mutex> lk(g_gen_mu);
   g_gen_cache.insert(g_gen_cache.begin(), t);
   if (g_gen_cache.size() > 3) g_gen_cache.pop_back();
@@ -782,6 +796,8 @@ static int ensure_generic(rthx_handle* h) {
   const std::shared_ptr<const GenericTables> gt = generic_tables(im);
   struct { const std::vector<unsigned char>& host; size_t total; } A{gt->host, gt->host.size()};
   const size_t o_sets = gt->o_sets, o_bent = gt->o_bent, o_bcand = gt->o_bcand, o_pnx = gt->o_pnx, o_pny = gt->o_pny, o_frec = gt->o_frec;
+  const bool timing = std::getenv("RTHX_CREATE_TIMING") != nullptr;
+  const auto t_up = std::chrono::steady_clock::now();
   CU(h, cudaSetDevice(h->device));
   if (h->generic_cap < A.total) {
     cudaFree(h->generic_arena);
@@ -790,6 +806,8 @@ static int ensure_generic(rthx_handle* h) {
     h->generic_cap = A.total + A.total / 4;
   }
   CU(h, cudaMemcpy(h->generic_arena, A.host.data(), A.host.size(), cudaMemcpyHostToDevice));
+  if (timing) std::fprintf(stderr, "generic tables: %-24s %8.3f ms (%.1f MB)\n", "device arena + upload",
+                           std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_up).count(), A.host.size() / 1e6);
   unsigned char* b8 = static_cast<unsigned char*>(h->generic_arena);
   TraceParams& P = h->base;
   P.sets = (const FaceSetDev*)(b8 + o_sets); P.bucket_ent = (const int4*)(b8 + o_bent); P.bucket_cand = (const int32_t*)(b8 + o_bcand);

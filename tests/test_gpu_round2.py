@@ -328,3 +328,34 @@ def test_generic_locator_on_the_ray_queue_equals_lock_step(rthx_mod, oracle_mod,
     assert nd <= max(2, total // 500_000), nd
     assert abs(int(out["queue"]["lost"].sum()) - int(ref["lost"].sum())) <= 2
     assert np.allclose(out["queue"]["origins"], ref["origins"], atol=1e-12)
+
+
+def test_generic_tables_come_from_the_process_cache(rthx_mod, cuda_lib):
+    """The generic tables of a mesh are built once per process: a second handle on the same geometry (callers re-create handles
+    for every trace) and a handle created after rthx_release_cached() give the same integers as the first; another mesh of the
+    same size does not hit the first one's entry."""
+    from rthx import _lib
+    m = rthx_mod.meshes
+    flat = rthx_mod.flatten_domain(m.two_quads_domain(skew=0.25))
+    other = rthx_mod.flatten_domain(m.two_quads_domain(skew=0.15))       # same topology and sizes, different vertices
+    outs = []
+    for i in range(2):
+        tr = rthx_mod.DeviceTracer(flat, device=0)
+        outs.append(tr.trace(2000, seed=9, locator=1))
+        tr.close()
+    tr = rthx_mod.DeviceTracer(other, device=0)
+    o_other = tr.trace(2000, seed=9, locator=1)
+    tr.close()
+    _lib.load_library().rthx_release_cached()
+    tr = rthx_mod.DeviceTracer(flat, device=0)
+    outs.append(tr.trace(2000, seed=9, locator=1))
+    a_other = tr.trace(2000, seed=9)            # analytic locator on the same handle
+    tr.close()
+    assert np.array_equal(outs[0]["counts"], outs[1]["counts"]) and np.array_equal(outs[0]["counts"], outs[2]["counts"])
+    assert not np.array_equal(outs[0]["counts"], o_other["counts"])
+    tr = rthx_mod.DeviceTracer(other, device=0)
+    a = tr.trace(2000, seed=9)
+    tr.close()
+    nd = int(np.abs(a["counts"].astype(np.int64) - o_other["counts"].astype(np.int64)).sum() // 2)
+    assert nd <= 2, nd                          # the other mesh was located with ITS tables (generic == analytic within the budget)
+    assert a_other["counts"].sum() > 0
