@@ -223,7 +223,7 @@ int rthx_trace_exchange_device(rthx_handle* h, const rthx_trace_args* args,
  *   counts_out != NULL: each device copies only the rows it owns into the host matrix, pipelined behind its kernels over its own
  *       PCIe link (rows are disjoint and tile the matrix: no reduction, nothing is cleared on the host);
  *   counts_out == NULL: the devices flush their rows into ONE matrix in the memory of hs[0]'s device through peer access
- *       (NVLink / NVSwitch; red.add.u64 at system scope, fused into the trace kernel).  The complete matrix stays resident on
+ *       (NVLink / NVSwitch; finished rows are handed over with plain stores, fused into the trace kernel).  The complete matrix stays resident on
  *       hs[0] for rthx_counts_csr / rthx_counts_csc / rthx_smooth_F / rthx_smooth_DkAP, exactly as after a single-device
  *       rthx_trace_exchange with counts_out == NULL.  Needs peer access between the devices (RTHX_ERR_CUDA otherwise).      [0.3]
  * stats->kernel_ms / total_ms are those of the slowest device. */
@@ -348,9 +348,10 @@ int rthx_counts_csc(rthx_handle* h, int bin, int index_base, int rowval_is_i64, 
 /* Peer-memory plumbing for the fused flush in one-process-per-GPU runs: rank 0 allocates the UInt64 count matrix
  * with rthx_shared_alloc and publishes the 64-byte CUDA IPC handle; every other rank maps it with rthx_shared_open
  * (peer access over NVLink is enabled lazily) and passes the mapped pointer as `counts_dev` to
- * rthx_trace_exchange_device with zero_first = RTHX_ZERO_OWN_ROWS.  Each rank's kernel then flushes its own (disjoint)
- * rows straight into rank 0's memory with red.global.add.u64 over NVLink — the reduce is fused into the trace kernel
- * and only a barrier remains. */
+ * rthx_trace_exchange_device with zero_first = RTHX_ZERO_OWN_ROWS | RTHX_DEST_PEER (an IPC mapping reports the mapping device: the caller
+ * declares it).  Each rank's kernel then hands its own (disjoint) finished rows over to rank 0's memory with plain coalesced
+ * stores over NVLink — the "reduce" is fused into the trace kernel, nothing on the wire is atomic and only the step flags
+ * below remain. */
 int rthx_shared_alloc(int device_id, uint64_t bytes, void** dev_ptr, unsigned char ipc_handle[64]);
 int rthx_shared_open(int device_id, const unsigned char ipc_handle[64], void** dev_ptr);
 int rthx_shared_close(int device_id, void* dev_ptr);

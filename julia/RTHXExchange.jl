@@ -99,6 +99,8 @@ end
 check(rc, h) = rc == 0 || error("rthx: " * unsafe_string(ccall((:rthx_last_error, LIB), Cstring, (Ptr{Cvoid},), h)))
 
 # ---- page-locked result arrays: the device writes them by DMA, Julia wraps them without a copy -----------------------
+# (wrapped foreign memory cannot be resized: code that inserts NEW stored entries into the returned F_raw — `F[i, j] = x` on a
+#  structural zero, `dropzeros!` — must `copy(F)` first; `smooth_F` and `equilibriumGrey2D!` only read it)
 function pinned_vector(::Type{T}, n::Integer) where {T}
     p = Ref{Ptr{Cvoid}}(C_NULL)
     check(ccall((:rthx_host_alloc, LIB), Cint, (Ref{Ptr{Cvoid}}, UInt64), p, max(n, 1) * sizeof(T)), C_NULL)

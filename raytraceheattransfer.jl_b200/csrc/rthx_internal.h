@@ -1,5 +1,6 @@
 // rthx_internal.h — structures shared between the host API (rthx_api.cu) and the kernels (rthx_kernels.cu).
 #pragma once
+#include <cstddef>
 #include <cstdint>
 #include <cuda_runtime.h>
 
@@ -98,7 +99,12 @@ struct TraceParams {
   int32_t queue_depth;         // queue kernel: rays parked per lane and batch (queue slots per warp = 32 * queue_depth)
   int32_t queue_bilinear;      // queue kernel variant bits: 8 general faces (bilinear lattices, T-junctions), 16 generic locator, 32 its 80-register build
   int32_t queue_sq;            // MULTI queue kernel: the domain is one parallelogram (1 axis-aligned, 2 general): SQ form of the step
-  int64_t rays_per_emitter;
+  // The 64-bit block below starts on a 16-byte boundary of the parameter bank whatever the number of pointers above: the kernels take
+  // the constants and the Philox round keys as c[0][..] operands / 128-bit uniform loads, and ptxas' register allocation depends on
+  // their alignment.  Measured when a pointer was dropped above (everything slid by 8 bytes, rk[] to an address = 8 mod 16): the
+  // MULTI_BOUNCE queue kernel went from 127 to 377 local-memory instructions (stack 64 -> 88 bytes) and from 3.48e10 to 2.97e10 rays/s
+  // on cfg3 (profiles/r4/r4c_*), the SQ kernel from 3 to 9.
+  alignas(16) int64_t rays_per_emitter;
   int64_t ray_id_offset;
   uint64_t seed;
   double nudge;
@@ -118,6 +124,9 @@ struct TraceParams {
   uint32_t rk[20];  // Philox round keys (key + r*W), two per round
   CoarseDev face0;  // SQ kernels: the single coarse face, read from the parameter bank
 };
+
+static_assert(offsetof(TraceParams, rays_per_emitter) % 16 == 0 && offsetof(TraceParams, k_u52) % 16 == 0 && offsetof(TraceParams, rk) % 16 == 0,
+              "TraceParams: constants and round keys keep their 16-byte alignment in the parameter bank");
 
 // launchers implemented in rthx_kernels.cu
 cudaError_t launch_trace_exchange(const TraceParams& p, int n_blocks, int block_threads, size_t smem_bytes, bool fast, int minb, bool sq,

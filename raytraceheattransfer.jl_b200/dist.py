@@ -5,8 +5,8 @@ e ≡ r (mod world) — interleaving balances the cheap surface rows against the
 UInt64 count matrix on rank 0:
 
   mode="fused" (default for world > 1): rank 0 owns the matrix; every other rank maps it through CUDA IPC and its
-      trace kernel flushes its own (disjoint) rows straight into rank 0's HBM with red.global.add.u64 over
-      NVLink/NVSwitch, overlapped with tracing.  The "reduce" is fused into the kernel; the ranks synchronise through
+      trace kernel hands its own (disjoint) finished rows over to rank 0's HBM with plain coalesced stores over
+      NVLink/NVSwitch (RTHX_DEST_PEER), overlapped with tracing.  The "reduce" is fused into the kernel; the ranks synchronise through
       device-side step flags in rank 0's memory (no host-launched collective per step).
   mode="nccl": every rank fills a private full-size matrix (other rows zero) and ONE `reduce(SUM)` of the int64
       view sums them onto rank 0 (NCCL over NVLink on GPUs, gloo in the CPU tests).
