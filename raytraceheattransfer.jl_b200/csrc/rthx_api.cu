@@ -333,7 +333,7 @@ struct HostImage {
   unsigned char* data = nullptr;
   size_t cap = 0, bytes = 0, total = 0;      // pinned capacity, image bytes, arena bytes incl. the device-only scratch regions
   size_t o_coarse = 0, o_sets = 0, o_bent = 0, o_bcand = 0, o_frec = 0, o_nv = 0, o_pvx = 0, o_pvy = 0, o_mid = 0, o_vol = 0, o_surf = 0, o_beta = 0,
-         o_ub = 0, o_lat = 0, o_abs = 0, o_omega = 0, o_eps = 0, o_ec = 0, o_ew = 0, o_eco = 0, o_bins = 0, o_rec = 0, o_lost = 0;
+         o_ub = 0, o_lat = 0, o_abs = 0, o_omega = 0, o_omu = 0, o_eps = 0, o_ec = 0, o_ew = 0, o_eco = 0, o_bins = 0, o_rec = 0, o_lost = 0;
   int nc = 0, ncell = 0, ns = 0, N = 0, nb = 0, n_affine = 0, n_bilinear = 0;
   bool has_eps = false, nbr_complete = true, needs_generic = false;
   CoarseDev face0{};
@@ -475,7 +475,7 @@ int prepare_mesh(const rthx_mesh* m, std::shared_ptr<HostImage>& out, std::strin
   im->o_mid = L.add(16 * (size_t)ncell); im->o_vol = L.add(8 * (size_t)ncell); im->o_surf = L.add(16 * (size_t)ncell);
   im->o_beta = L.add(8 * (size_t)nb * ncell); im->o_ub = L.add(8 * (size_t)nb);
   im->o_lat = L.add(4 * lattice.size()); im->o_abs = L.add(4 * abs_tab.size());
-  im->o_omega = L.add(8 * (size_t)nb * ncell); im->o_eps = L.add(m->epsilon ? 8 * (size_t)nb * ns : 0);
+  im->o_omega = L.add(8 * (size_t)nb * ncell); im->o_omu = L.add(8 * (size_t)nb); im->o_eps = L.add(m->epsilon ? 8 * (size_t)nb * ns : 0);
   im->o_ec = L.add(4 * (size_t)N); im->o_ew = L.add(4 * (size_t)N); im->o_eco = L.add(4 * (size_t)N);
   im->bytes = L.total;
   im->o_bins = L.add(4 * ((size_t)nb * 4 + 16)); im->o_rec = L.add(4 * (size_t)N);
@@ -514,6 +514,13 @@ int prepare_mesh(const rthx_mesh* m, std::shared_ptr<HostImage>& out, std::strin
     double* omega = im->at<double>(im->o_omega);
     const size_t n = (size_t)nb * ncell;
     for (size_t i = 0; i < n; ++i) { const double b = m->kappa[i] + m->sigma_s[i]; beta[i] = b; omega[i] = b > 0.0 ? m->sigma_s[i] / b : 0.0; }
+    double* omu = im->at<double>(im->o_omu);               // a band whose cells share one albedo: the kernels read it once per block
+    for (int b = 0; b < nb; ++b) {
+      const double* ob = omega + (size_t)b * ncell;
+      bool same = ncell > 0;
+      for (int i = 1; i < ncell && same; ++i) same = ob[i] == ob[0];
+      omu[b] = same ? ob[0] : -1.0;
+    }
     if (m->epsilon) std::memcpy(im->at<double>(im->o_eps), m->epsilon, 8 * (size_t)nb * ns);
   }
   {
@@ -631,7 +638,7 @@ int create_on_device(rthx_handle** out, const std::shared_ptr<HostImage>& im, in
   P.poly_nx = nullptr; P.poly_ny = nullptr;      // per-polygon normals belong to the generic tables (ensure_generic)
   P.cell_mid = (const double*)(b8 + im->o_mid); P.cell_volume = (const double*)(b8 + im->o_vol);
   P.cell_surf_id = (const int32_t*)(b8 + im->o_surf); P.beta = (const double*)(b8 + im->o_beta); P.uniform_beta = (const double*)(b8 + im->o_ub);
-  P.omega = (const double*)(b8 + im->o_omega); P.eps = (const double*)(b8 + im->o_eps);
+  P.omega = (const double*)(b8 + im->o_omega); P.omega_u = (const double*)(b8 + im->o_omu); P.eps = (const double*)(b8 + im->o_eps);
   P.lattice = (const int32_t*)(b8 + im->o_lat); P.abs_tab = (const int32_t*)(b8 + im->o_abs);
   P.em_cell = (const int32_t*)(b8 + im->o_ec); P.em_wall = (const int32_t*)(b8 + im->o_ew); P.em_coarse = (const int32_t*)(b8 + im->o_eco);
   h->bins_dev = (int32_t*)(b8 + im->o_bins); h->bins_cap = (size_t)im->nb * 4 + 16;

@@ -1608,14 +1608,19 @@ __device__ __forceinline__ unsigned int queue_multi_loop(const TraceParams& p, c
             if (event >= 16000) {                                      // call# is a 16-bit field
               absorber = -1;
             } else {
+              // albedo of the cell / emissivity of the wall.  The per-cell albedo array (80 KB for cfg3) lives in L2: where a band has
+              // ONE albedo (p.omega_u, staged in the emitter block) the load is skipped — ptxas sinks it behind the ten Philox
+              // rounds whatever the source order, and the event then waits for L2 (long_scoreboard 1.6 cycles per issue)
+              const bool in_gas = absorber >= p.n_surfaces;
+              double lim = b.s_em[13];                                 // the band's albedo where all cells share one (or -1)
+              if (!in_gas | (lim < 0.0)) lim = __ldg(in_gas ? b.omega_band + (absorber - p.n_surfaces) : b.eps_band + absorber);
               const uint64_t ray_id = (uint64_t)(p.ray_id_offset + b.r_begin + (int64_t)r_cur);
               const uint4 v0 = philox4x32_10_rk(make_uint4((uint32_t)ray_id, (uint32_t)(ray_id >> 32), b.e, b.cw | (uint32_t)(2 + 2 * event)), p.rk);
               if (event >= 1000 && u32d(v0.w, p.k_u32) > 0.8) {        // Russian roulette, traceSingleRay.jl:11
                 absorber = -1;
               } else {
                 const double dec = u32d(v0.x, p.k_u32);
-                const double lim = absorber >= p.n_surfaces ? b.omega_band[absorber - p.n_surfaces] : b.eps_band[absorber];
-                park = absorber >= p.n_surfaces ? (dec < lim) : !(dec < lim);
+                park = in_gas ? (dec < lim) : !(dec < lim);
                 park_meta = (uint32_t)event | ((uint32_t)c << 14) | ((uint32_t)k << 23) | (gas ? (1u << 25) : 0u);
                 park_y = v0.y; park_z = v0.z;
               }
@@ -1728,7 +1733,7 @@ __global__ void __launch_bounds__(256, MINB) trace_exchange_queue_kernel(const _
   const int g = p.em_cell[e];
   const int wall = p.em_wall[e];
   const bool is_surface = wall >= 0;
-  if (threadIdx.x == 0) stage_emitter_folded(p, g, wall, s_em);
+  if (threadIdx.x == 0) { stage_emitter_folded(p, g, wall, s_em); if (MULTI) s_em[13] = p.omega_u[band]; }   // [13]: free slot of the emitter block
 
   const int64_t per = (p.rays_per_emitter + p.row_chunks - 1) / p.row_chunks;
   const int64_t r_begin = (int64_t)chunk * per;
