@@ -475,7 +475,7 @@ int prepare_mesh(const rthx_mesh* m, std::shared_ptr<HostImage>& out, std::strin
   im->o_mid = L.add(16 * (size_t)ncell); im->o_vol = L.add(8 * (size_t)ncell); im->o_surf = L.add(16 * (size_t)ncell);
   im->o_beta = L.add(8 * (size_t)nb * ncell); im->o_ub = L.add(8 * (size_t)nb);
   im->o_lat = L.add(4 * lattice.size()); im->o_abs = L.add(4 * abs_tab.size());
-  im->o_omega = L.add(8 * (size_t)nb * ncell); im->o_omu = L.add(8 * (size_t)nb); im->o_eps = L.add(m->epsilon ? 8 * (size_t)nb * ns : 0);
+  im->o_omega = L.add(8 * (size_t)nb * ncell); im->o_omu = L.add(16 * (size_t)nb); im->o_eps = L.add(m->epsilon ? 8 * (size_t)nb * ns : 0);
   im->o_ec = L.add(4 * (size_t)N); im->o_ew = L.add(4 * (size_t)N); im->o_eco = L.add(4 * (size_t)N);
   im->bytes = L.total;
   im->o_bins = L.add(4 * ((size_t)nb * 4 + 16)); im->o_rec = L.add(4 * (size_t)N);
@@ -514,12 +514,16 @@ int prepare_mesh(const rthx_mesh* m, std::shared_ptr<HostImage>& out, std::strin
     double* omega = im->at<double>(im->o_omega);
     const size_t n = (size_t)nb * ncell;
     for (size_t i = 0; i < n; ++i) { const double b = m->kappa[i] + m->sigma_s[i]; beta[i] = b; omega[i] = b > 0.0 ? m->sigma_s[i] / b : 0.0; }
-    double* omu = im->at<double>(im->o_omu);               // a band whose cells share one albedo: the kernels read it once per block
-    for (int b = 0; b < nb; ++b) {
+    double* band_u = im->at<double>(im->o_omu);            // a band whose cells share one albedo / whose walls share one emissivity:
+    for (int b = 0; b < nb; ++b) {                         // the kernels read it once per block instead of once per event
       const double* ob = omega + (size_t)b * ncell;
       bool same = ncell > 0;
       for (int i = 1; i < ncell && same; ++i) same = ob[i] == ob[0];
-      omu[b] = same ? ob[0] : -1.0;
+      band_u[2 * b] = same ? ob[0] : -1.0;
+      const double* eb = m->epsilon ? m->epsilon + (size_t)b * ns : nullptr;
+      same = eb != nullptr && ns > 0;
+      for (int i = 1; i < ns && same; ++i) same = eb[i] == eb[0];
+      band_u[2 * b + 1] = same ? eb[0] : -1.0;
     }
     if (m->epsilon) std::memcpy(im->at<double>(im->o_eps), m->epsilon, 8 * (size_t)nb * ns);
   }
@@ -638,7 +642,7 @@ int create_on_device(rthx_handle** out, const std::shared_ptr<HostImage>& im, in
   P.poly_nx = nullptr; P.poly_ny = nullptr;      // per-polygon normals belong to the generic tables (ensure_generic)
   P.cell_mid = (const double*)(b8 + im->o_mid); P.cell_volume = (const double*)(b8 + im->o_vol);
   P.cell_surf_id = (const int32_t*)(b8 + im->o_surf); P.beta = (const double*)(b8 + im->o_beta); P.uniform_beta = (const double*)(b8 + im->o_ub);
-  P.omega = (const double*)(b8 + im->o_omega); P.omega_u = (const double*)(b8 + im->o_omu); P.eps = (const double*)(b8 + im->o_eps);
+  P.omega = (const double*)(b8 + im->o_omega); P.band_u = (const double*)(b8 + im->o_omu); P.eps = (const double*)(b8 + im->o_eps);
   P.lattice = (const int32_t*)(b8 + im->o_lat); P.abs_tab = (const int32_t*)(b8 + im->o_abs);
   P.em_cell = (const int32_t*)(b8 + im->o_ec); P.em_wall = (const int32_t*)(b8 + im->o_ew); P.em_coarse = (const int32_t*)(b8 + im->o_eco);
   h->bins_dev = (int32_t*)(b8 + im->o_bins); h->bins_cap = (size_t)im->nb * 4 + 16;

@@ -65,7 +65,8 @@ struct TraceParams {
   const double* beta;          // [n_bands*n_cells]
   const double* uniform_beta;  // [n_bands]
   const double* omega;         // [n_bands*n_cells]    scattering albedo sigma_s/(kappa+sigma_s)   (MULTI_BOUNCE)
-  const double* omega_u;       // [n_bands] the albedo shared by every cell of the band, or -1 (the queue kernel then skips the per-cell load)
+  const double* band_u;        // [n_bands*2] {albedo shared by every cell, emissivity shared by every surface} of the band, -1 where they differ
+                               // (the MULTI queue kernel then skips the per-cell / per-surface load)
   const double* eps;           // [n_bands*n_surfaces] wall emissivity                              (MULTI_BOUNCE)
   const int32_t* lattice;      // lattice -> local fine index tables (kind 2)
   const int32_t* abs_tab;      // affine faces: [lattice cell][gas | wall on coarse edge 0..3] -> absorber index or -1

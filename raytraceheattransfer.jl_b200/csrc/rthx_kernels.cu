@@ -9,6 +9,7 @@
 //       into the global count matrix (parallelRayTracing.jl:104,124,144-146);
 //   (4) optional RayRecorder output of origin / endpoint (parallelRayTracing.jl:108,120-123,135-138).
 // No tensor cores: the path is branchy FP64 geometry + integer RNG + integer atomics, not a contraction.
+#include <climits>
 #include "rthx_internal.h"
 
 #include <math_constants.h>
@@ -1233,6 +1234,20 @@ __device__ __forceinline__ unsigned int queue_ray_loop(const TraceParams& p, con
   double* const q = b.q;                               // field f of slot s at q[f * WQ + s]
   const unsigned lt_mask = (1u << lane) - 1u;
   unsigned int n_lost = 0;
+  // Deferred tally (analytic locators, no recorder): the absorber index comes out of a table in global memory (L1 / L2); tallying
+  // it on the spot makes the warp wait for the load.  The index is kept in a register instead and tallied in the lane's NEXT step
+  // (or behind the loop), a refill and a distToSurface2D later: the load has that long to arrive.
+  constexpr bool DEFER = !REC && !GEN;
+  constexpr int NO_PEND = INT_MIN;
+  int pend_abs = NO_PEND;
+#define RTHX_QUEUE_TALLY_PENDING()                     \
+  do {                                                 \
+    if (DEFER && pend_abs != NO_PEND) {                \
+      if (pend_abs >= 0) atomicAdd(&b.hist[pend_abs], 1u); \
+      else ++n_lost;                                   \
+      pend_abs = NO_PEND;                              \
+    }                                                  \
+  } while (0)
   // in-flight ray of this lane (lives in registers across queue refills)
   bool active = false;
   double px = 0.0, py = 0.0, dx = 0.0, dy = 0.0, S = 0.0, acc = 0.0;   // S: remaining free path (UNIFORM) or -log R
@@ -1289,6 +1304,7 @@ __device__ __forceinline__ unsigned int queue_ray_loop(const TraceParams& p, con
         int k;
         double u;
         const bool edge = dist_face<BILIN>(cf, px, py, dx, dy, p.k_eps, u, k);  // an edge lies ahead
+        RTHX_QUEUE_TALLY_PENDING();                                            // the ending of this lane's previous ray
         bool gas, ok = true;
         double tau_b = 0.0, Sg;
         if (UNIFORM) {
@@ -1345,7 +1361,9 @@ __device__ __forceinline__ unsigned int queue_ray_loop(const TraceParams& p, con
         if (l >= 0) absorber = __ldg(p.abs_tab + (size_t)(cf.abs_off + l) * 5 + (gas ? 0 : 1 + k));                 \
       }                                                                                                             \
     }                                                                                                               \
-    if (absorber >= 0) {                                                                                            \
+    if (DEFER) {                                                                                                    \
+      pend_abs = absorber;                       /* tallied by RTHX_QUEUE_TALLY_PENDING in the lane's next step */     \
+    } else if (absorber >= 0) {                                                                                     \
       atomicAdd(&b.hist[absorber], 1u);                                                                             \
       if (REC) {                                                                                                    \
         const size_t sl = b.rec_row + (size_t)(b.r_begin + (int64_t)r_cur);                                         \
@@ -1388,6 +1406,8 @@ __device__ __forceinline__ unsigned int queue_ray_loop(const TraceParams& p, con
     if (last_batch) break;                             // the inner loop only leaves the last batch with nothing in flight
     rb += stride;
   }
+  RTHX_QUEUE_TALLY_PENDING();                          // lanes that took no further ray
+#undef RTHX_QUEUE_TALLY_PENDING
   return n_lost;
 }
 
@@ -1609,11 +1629,11 @@ __device__ __forceinline__ unsigned int queue_multi_loop(const TraceParams& p, c
               absorber = -1;
             } else {
               // albedo of the cell / emissivity of the wall.  The per-cell albedo array (80 KB for cfg3) lives in L2: where a band has
-              // ONE albedo (p.omega_u, staged in the emitter block) the load is skipped — ptxas sinks it behind the ten Philox
+              // ONE albedo (p.band_u, staged in the emitter block) the load is skipped — ptxas sinks it behind the ten Philox
               // rounds whatever the source order, and the event then waits for L2 (long_scoreboard 1.6 cycles per issue)
               const bool in_gas = absorber >= p.n_surfaces;
-              double lim = b.s_em[13];                                 // the band's albedo where all cells share one (or -1)
-              if (!in_gas | (lim < 0.0)) lim = __ldg(in_gas ? b.omega_band + (absorber - p.n_surfaces) : b.eps_band + absorber);
+              double lim = b.s_em[in_gas ? 13 : 12];                   // the band's albedo / emissivity where all cells / walls share one (or -1)
+              if (lim < 0.0) lim = __ldg(in_gas ? b.omega_band + (absorber - p.n_surfaces) : b.eps_band + absorber);
               const uint64_t ray_id = (uint64_t)(p.ray_id_offset + b.r_begin + (int64_t)r_cur);
               const uint4 v0 = philox4x32_10_rk(make_uint4((uint32_t)ray_id, (uint32_t)(ray_id >> 32), b.e, b.cw | (uint32_t)(2 + 2 * event)), p.rk);
               if (event >= 1000 && u32d(v0.w, p.k_u32) > 0.8) {        // Russian roulette, traceSingleRay.jl:11
@@ -1733,7 +1753,7 @@ __global__ void __launch_bounds__(256, MINB) trace_exchange_queue_kernel(const _
   const int g = p.em_cell[e];
   const int wall = p.em_wall[e];
   const bool is_surface = wall >= 0;
-  if (threadIdx.x == 0) { stage_emitter_folded(p, g, wall, s_em); if (MULTI) s_em[13] = p.omega_u[band]; }   // [13]: free slot of the emitter block
+  if (threadIdx.x == 0) { stage_emitter_folded(p, g, wall, s_em); if (MULTI) { s_em[12] = p.band_u[2 * band + 1]; s_em[13] = p.band_u[2 * band]; } }   // [12], [13]: free slots of the emitter block
 
   const int64_t per = (p.rays_per_emitter + p.row_chunks - 1) / p.row_chunks;
   const int64_t r_begin = (int64_t)chunk * per;
