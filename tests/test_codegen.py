@@ -14,10 +14,12 @@ import pytest
 BOUNDS = {
     "trace_exchange_sq_kernel<4, false>": (64, 8),                       # cfg1-4: the headline kernel
     "trace_exchange_sq_kernel<4, true>": (64, 24),                       # lock-step MULTI_BOUNCE loop (RTHX_MULTI_SQ=1)
-    "trace_exchange_queue_kernel<4, 4, false, false, false>": (64, 32),  # cfg5: per-warp ray queue, depth 4
-    "trace_exchange_queue_kernel<4, 2, false, false, false>": (64, 32),
+    "trace_exchange_queue_kernel<4, 4, false, false, false>": (64, 16),  # cfg5: per-warp ray queue, depth 4
+    "trace_exchange_queue_kernel<4, 2, false, false, false>": (64, 16),
+    "trace_exchange_queue_kernel<4, 4, true, false, false>": (64, 64),   # general faces (bilinear lattices, T-junctions)
     "trace_exchange_queue_kernel<3, 2, false, true, false>": (80, 64),   # MULTI_BOUNCE on the ray queue
     "trace_exchange_queue_kernel<4, 4, true, false, true>": (64, 88),    # generic locator on the ray queue
+    "trace_exchange_kernel<true, false, 4, false, false>": (64, 40),     # generic locator, lock-step (single-face meshes)
 }
 
 
